@@ -1,0 +1,201 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference, CPU fp32).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py
+
+The reference is imported through four stub packages under oracle/ref_stubs/ (timm, matplotlib,
+mpl_toolkits, pytorch_msssim are absent from this image and irrelevant to the hot path;
+SURVEY.md section 8c).  Nothing in tests/ or the product imports the reference at run time: the vectors
+written here are the only thing that travels.
+
+Model: pMCTF(num_me_stages=4), torch.manual_seed(0), then the following PERTURBATIONS so that the
+random-init degeneracies (SURVEY.md section 7 "Random-init degeneracy") do not hide bugs:
+  * every hot-path 3x3 conv weight (temporal_filtering.*, *.wavelet_transform.*) is multiplied by 4
+    and every hot-path conv bias is drawn from N(0, 0.05)          [seed 1234]
+  * the (3,1) skip taps are reset to their bior4.4 init values (pMCTF._init_weights had
+    overwritten them, pMCTF_L.py:116-122) plus N(0, 0.01), biases N(0, 0.05)
+  * QP = [1/32, 1/2], QP_ll = [1/16, 3/4] for both coders; hp_q_scale[i] = [0.9-0.1 i, 1.3-0.1 i]
+Inputs: seeded synthetic frames (smooth noise in 16..235 plus texture), flows N(0, 4^2) px with
+an out-of-frame band.  Everything is recorded in the files themselves.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.join(HERE, "ref_stubs"), "/root/reference"]
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+from pMCTF.layers import RoundNoGradient  # noqa: E402
+from pMCTF.layers.video.video_net import bilineardownsacling, flow_warp  # noqa: E402
+from pMCTF.models.video.pMCTF_L import pMCTF  # noqa: E402
+
+
+def is_hot(k):
+    return k.startswith("temporal_filtering.") or ".wavelet_transform.lift_h." in k or k.startswith("hp_q_scale") \
+        or k.endswith(".QP") or k.endswith(".QP_ll")
+
+
+def build_model():
+    torch.manual_seed(0)
+    m = pMCTF(num_me_stages=4).eval()
+    g = torch.Generator().manual_seed(1234)
+    bior = [-1.586134342059924, -0.052980118572961, 0.882911075530934, 0.443506852043971]
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if not (k.startswith("temporal_filtering.") or ".wavelet_transform.lift_h." in k):
+                continue
+            leaf = k.split(".")[-2]
+            if leaf.startswith("conv_"):  # skip taps (1,1,3,1)
+                i = ["conv_P1", "conv_U1", "conv_P2", "conv_U2"].index(leaf)
+                if k.endswith("weight"):
+                    base = torch.tensor([0.0, bior[i], bior[i]] if i % 2 == 0 else [bior[i], bior[i], 0.0])
+                    p.copy_((base + 0.01 * torch.randn(3, generator=g)).view(1, 1, 3, 1))
+                else:
+                    p.copy_(0.05 * torch.randn(p.shape, generator=g))
+            elif k.endswith("weight"):
+                p.mul_(4.0)
+            else:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+        for coder in (m.lp_coder, m.hp_coder):
+            coder.QP.copy_(torch.tensor([1 / 32, 1 / 2]).view(2, 1, 1, 1))
+            coder.QP_ll.copy_(torch.tensor([1 / 16, 3 / 4]).view(2, 1, 1, 1))
+        for i, p in enumerate(m.hp_q_scale):
+            p.copy_(torch.tensor([0.9 - 0.1 * i, 1.3 - 0.1 * i]).view(2, 1, 1, 1))
+    return m
+
+
+def frames(n, h, w, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, 1, h + 16, w + 16, generator=g)
+    k = torch.ones(1, 1, 5, 5) / 25
+    for _ in range(2):
+        x = F.conv2d(x, k, padding=2)
+    x = x[:, :, 8:-8, 8:-8]
+    x = (x - x.amin()) / (x.amax() - x.amin())
+    x = 16 + 219 * x + 6 * torch.randn(n, 1, h, w, generator=g)
+    return x.clamp(0, 255).round()
+
+
+def flows(n, h, w, seed, sigma=4.0):
+    g = torch.Generator().manual_seed(seed)
+    f = sigma * torch.randn(n, 2, h, w, generator=g)
+    f = F.avg_pool2d(F.pad(f, (2, 2, 2, 2), mode="replicate"), 5, stride=1)
+    f = f * 2.5
+    f[:, :, :2, :] -= 40.0  # points out of the frame at the top
+    f[:, :, :, -2:] += 37.5  # and at the right border
+    return f
+
+
+def npy(t):
+    return t.detach().cpu().numpy().astype(np.float32)
+
+
+@torch.no_grad()
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    m = build_model()
+    sd = {k: npy(v) for k, v in m.state_dict().items() if is_hot(k)}
+    np.savez_compressed(os.path.join(OUT, "weights.npz"), **sd)
+    meta = f"torch {torch.__version__}; cpu capability {torch.backends.cpu.get_cpu_capability()}; threads 8"
+
+    # ---- a1/a2: warp + chroma MV ------------------------------------------------------------
+    c = {}
+    for tag, (n, ch, h, w, fn) in {"luma": (1, 1, 40, 72, 1), "chromaN": (2, 1, 20, 36, 2), "tile": (2, 1, 24, 40, 1),
+                                   "rgb": (1, 3, 16, 24, 1)}.items():
+        g = torch.Generator().manual_seed({"luma": 11, "chromaN": 12, "tile": 13, "rgb": 14}[tag])
+        im = torch.rand(n, ch, h, w, generator=g) * 255
+        fl = flows(fn, h, w, 20 + n + h)
+        fl_t = fl.tile((n // fn, 1, 1, 1)) if fn != n else fl
+        c[f"{tag}.im"], c[f"{tag}.flow"] = npy(im), npy(fl)
+        c[f"{tag}.out_pos"] = npy(flow_warp(im, fl_t))
+        c[f"{tag}.out_neg"] = npy(flow_warp(im, -fl_t))
+        c[f"{tag}.lin_x"] = npy(torch.linspace(-1.0, 1.0, w))
+        c[f"{tag}.lin_y"] = npy(torch.linspace(-1.0, 1.0, h))
+    mv = flows(1, 32, 48, 31)
+    c["down.mv"], c["down.out"] = npy(mv), npy(bilineardownsacling(mv) / 2)
+    np.savez_compressed(os.path.join(OUT, "warp.npz"), meta=meta, **c)
+
+    # ---- a3/a4: PredictUpdate, temporal filters -----------------------------------------------
+    c = {}
+    x = frames(2, 24, 40, 41)
+    tf0 = m.temporal_filtering[0]
+    c["x"] = npy(x)
+    c["P_t0"] = npy(tf0.P_t(x))
+    c["P_1_norm"] = npy(m.hp_coder.wavelet_transform.lift_h.P_1(x / 256.0))
+    c["predict0"] = npy(tf0.predict_filter(x))
+    c["update3"] = npy(m.temporal_filtering[3].update_filter(x - 100.0))
+    np.savez_compressed(os.path.join(OUT, "pu.npz"), meta=meta, **c)
+
+    # ---- a5/a6: forward/inverse MCTF (luma + chroma with tiled, down-scaled MV) ---------------
+    c = {}
+    H, W = 64, 96
+    fr = frames(2, H, W, 51)
+    ch = frames(4, H // 2, W // 2, 52)
+    mvh = flows(1, H, W, 53)
+    c["lin_x"], c["lin_y"] = npy(torch.linspace(-1.0, 1.0, W)), npy(torch.linspace(-1.0, 1.0, H))
+    c["lin_xc"], c["lin_yc"] = npy(torch.linspace(-1.0, 1.0, W // 2)), npy(torch.linspace(-1.0, 1.0, H // 2))
+    c["ref"], c["cur"], c["ref_c"], c["cur_c"], c["mv"] = npy(fr[0:1]), npy(fr[1:2]), npy(ch[0:2]), npy(ch[2:4]), npy(mvh)
+    for s in (0, 3):
+        L, Hh, pred, inv = m.forward_MCTF(fr[0:1], fr[1:2], mvh, stage_idx=s)
+        c[f"s{s}.L"], c[f"s{s}.H"], c[f"s{s}.pred"], c[f"s{s}.inv"] = npy(L), npy(Hh), npy(pred), npy(inv)
+        r, cu = m.inverse_MCTF(L, Hh, mvh, stage_idx=s)
+        c[f"s{s}.ref_rec"], c[f"s{s}.cur_rec"] = npy(r), npy(cu)
+        mvc = bilineardownsacling(mvh) / 2
+        Lc, Hc, _, _ = m.forward_MCTF(ch[0:2], ch[2:4], mvc, stage_idx=s)
+        c[f"s{s}.Lc"], c[f"s{s}.Hc"] = npy(Lc), npy(Hc)
+        rc, cc = m.inverse_MCTF(Lc, Hc, mvh, downscale=True, stage_idx=s)
+        c[f"s{s}.ref_c_rec"], c[f"s{s}.cur_c_rec"] = npy(rc), npy(cc)
+    np.savez_compressed(os.path.join(OUT, "mctf.npz"), meta=meta, **c)
+
+    # ---- a7-a12: spatial lifting, quantise ----------------------------------------------------
+    c = {}
+    coder = m.hp_coder
+    lift = coder.wavelet_transform
+    x = frames(2, 32, 48, 61) - 60.0
+    l, h = lift.lift_h.forward_lift(x)
+    c["x1d"], c["l1d"], c["h1d"] = npy(x), npy(l), npy(h)
+    c["x1d_rec"] = npy(lift.lift_h.backward_lift(l, h))
+    d = lift.forward_lift_2d(x)
+    for k in ("ll", "lh", "hl", "hh"):
+        c[f"2d.{k}"] = npy(d[k].contiguous())
+    c["x2d_rec"] = npy(lift.backward_lift_2d(d))
+    x = frames(1, 64, 96, 62)
+    c["x"] = npy(x)
+    y = coder.encode(x)
+    for lvl in range(4):
+        for k in ("ll", "lh", "hl", "hh"):
+            c[f"enc.{lvl}.{k}"] = npy(y[lvl][k].contiguous())
+    c["dec"] = npy(coder.decode({lvl: dict(y[lvl]) for lvl in range(4)}))
+    # spatial_wavelet_dec (pWave.py:314-349) up to, not including, the PostProcess net
+    for qi in (0, 4, 8, 12, 16, 20):
+        for tag, scale in (("lp", None), ("hp1", m.get_curr_q(m.hp_q_scale[1], qi))):
+            q = coder.get_curr_q(coder.QP, qi)
+            qll = coder.get_curr_q(coder.QP_ll, qi)
+            if scale is not None:
+                q, qll = q * scale, qll * scale
+            yy = coder.encode(x)
+            hat = {lvl: {} for lvl in range(4)}
+            hat[3]["ll"] = RoundNoGradient.apply(coder.quantize_subband(yy[3]["ll"], qll))
+            for lvl in range(3, -1, -1):
+                for b in ("lh", "hl", "hh"):
+                    hat[lvl][b] = RoundNoGradient.apply(coder.quantize_subband(yy[lvl][b], q))
+            rec = coder.dequantize_subbands(hat, q, qll)
+            xh = coder.decode(rec)
+            p = f"q{qi}.{tag}."
+            c[p + "q"], c[p + "qll"], c[p + "x_hat"] = npy(q), npy(qll), npy(xh)
+            for lvl in hat:
+                for b, v in hat[lvl].items():
+                    c[p + f"sym.{lvl}.{b}"] = npy(v.contiguous()).astype(np.int16)
+    np.savez_compressed(os.path.join(OUT, "pwave.npz"), meta=meta, **c)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

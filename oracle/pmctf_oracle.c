@@ -1,0 +1,477 @@
+/*
+ * pmctf_oracle.c -- CPU restatement of the reference's MCTF + pWave++ lifting hot path.
+ *
+ * THIS FILE IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+ * (learned-pmctf_b200/) never links, imports or calls anything in oracle/.
+ *
+ * Parity status: the reference (FAU-LMS/Learned-pMCTF) ships NO golden vectors or tests
+ * (SURVEY.md section 4).  The oracle is therefore pinned against outputs of the reference
+ * itself, generated in the build container by oracle/make_golden.py (imports the
+ * unmodified reference from /root/reference, CPU fp32) and committed under tests/golden/.
+ *
+ * What is restated (all citations relative to /root/reference):
+ *   flow_warp / torch_warp             pMCTF/layers/video/video_net.py:32-55   (+ ATen CPU grid_sampler_2d)
+ *   bilineardownsacling(mv)/2          pMCTF/layers/video/video_net.py:66-71   (+ ATen CPU upsample_bilinear2d)
+ *   PredictUpdate                      pMCTF/layers/lifting_1d.py:25-49
+ *   TemporalLifting.predict/update     pMCTF/layers/video/wavelet_transform_temporal_mctf.py:27-45
+ *   pMCTF.forward_MCTF / inverse_MCTF  pMCTF/models/video/pMCTF_L.py:297-330
+ *   split / merge                      pMCTF/layers/lifting_1d.py:10-22
+ *   iWave1D.forward_lift/backward_lift pMCTF/layers/lifting_1d.py:103-189
+ *   LiftingScheme2D fwd/bwd            pMCTF/layers/wavelet_transform.py:25-57
+ *   quantise / dequantise              pMCTF/models/pWave.py:184-202, layers/layers.py:71-92
+ *
+ * Arithmetic contract (shared, as a SPECIFICATION, with the CUDA kernels -- the code is
+ * written independently on each side):
+ *   - every convolution output is one sequential fp32 FMA chain: acc = bias, then
+ *     acc = fma(w[co][ci][ky][kx], in[ci][y+ky-1][x+kx-1], acc) in (ci, ky, kx) order;
+ *   - tanh is the deterministic routine tanh_det() below (IEEE +,*,fma,/ and rint only);
+ *   - every other elementwise op is a single correctly rounded fp32 operation in the
+ *     reference's own order (no contraction: build with -ffp-contract=off).
+ *   The reference's MKLDNN convolutions and Sleef tanh use a different (unspecified)
+ *   summation order, so oracle-vs-reference agreement is to ~1e-5 on the 0..255 scale
+ *   (measured in tests/test_oracle_golden.py); oracle-vs-CUDA agreement is bit-exact.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_API __attribute__((visibility("default")))
+#define NCH 16
+
+typedef struct {
+    const float *w1, *b1; /* (16,1,3,3), (16) */
+    const float *w2, *b2; /* (16,16,3,3), (16) */
+    const float *w3, *b3; /* (16,16,3,3), (16) */
+    const float *w4, *b4; /* (1,16,3,3), (1)  */
+} orc_pu_t;
+
+typedef struct {
+    /* conv_P1, conv_U1, conv_P2, conv_U2: weight (1,1,3,1) + bias (1)   lifting_1d.py:71-89 */
+    float tap[4][3];
+    float bias[4];
+    orc_pu_t pu[4]; /* P_1, U_1, P_2, U_2 in application order          lifting_1d.py:93-96 */
+    float scale_l, scale_h; /* lifting_1d.py:98-101 */
+    float dynamic_range;    /* 256.0  lifting_1d.py:62 */
+    int lossy;
+} orc_iwave_t;
+
+/* ------------------------------------------------------------------------------------------ */
+/* deterministic tanh: tanh(x) = em1/(em1+2), em1 = expm1(2|x|), built from IEEE ops only      */
+static inline float tanh_det(float x)
+{
+    float ax = fminf(fabsf(x), 10.0f); /* tanh(10) rounds to 1.0f */
+    float z = ax + ax;
+    float kf = rintf(z * 1.44269504f);
+    float r = fmaf(kf, -0.693145752f, z);
+    r = fmaf(kf, -1.42860677e-06f, r);
+    float q = 1.98412698e-4f;
+    q = fmaf(q, r, 1.38888889e-3f);
+    q = fmaf(q, r, 8.33333333e-3f);
+    q = fmaf(q, r, 4.16666667e-2f);
+    q = fmaf(q, r, 1.66666667e-1f);
+    q = fmaf(q, r, 0.5f);
+    float r2 = r * r;
+    float p = fmaf(q, r2, r);
+    int32_t k = (int32_t)kf;
+    union { int32_t i; float f; } s;
+    s.i = (k + 127) << 23;
+    float em1 = fmaf(s.f, p, s.f - 1.0f);
+    float t = em1 / (em1 + 2.0f);
+    return copysignf(t, x);
+}
+
+ORC_API void orc_tanh(const float *x, float *y, long n)
+{
+    for (long i = 0; i < n; ++i) y[i] = tanh_det(x[i]);
+}
+
+/* torch.linspace(-1, 1, n) as the scalar (CUDA-kernel) formula; ATen's vectorised CPU kernel
+ * differs in the last bit and depends on the host's SIMD width, so tests that compare with
+ * the CPU-generated goldens pass the golden's own tables instead.  video_net.py:36-39 */
+ORC_API void orc_linspace(float *out, int n)
+{
+    const float start = -1.0f, end = 1.0f;
+    const float step = (end - start) / (float)(n - 1);
+    const int half = n / 2;
+    for (int i = 0; i < n; ++i)
+        out[i] = (i < half) ? start + step * (float)i : end - step * (float)(n - i - 1);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* flow_warp: video_net.py:32-55.  im [N,C,H,W], flow [flowN,2,H,W] (flowN==1: broadcast over N,
+ * the `.tile` of pMCTF_L.py:299-300), sign multiplies the flow (-mv_hat: pMCTF_L.py:307).      */
+ORC_API void orc_flow_warp(const float *im, const float *flow, const float *lin_x, const float *lin_y,
+                           float *out, int N, int C, int H, int W, int flowN, float sign, int round_out)
+{
+    const float sx = (float)(((double)W - 1.0) / 2.0); /* python float, cast at the tensor op */
+    const float sy = (float)(((double)H - 1.0) / 2.0);
+    const float wmax = (float)(W - 1), hmax = (float)(H - 1);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int n = 0; n < N; ++n)
+        for (int y = 0; y < H; ++y) {
+            const float *fxp = flow + ((size_t)(flowN == 1 ? 0 : n) * 2 + 0) * H * W + (size_t)y * W;
+            const float *fyp = fxp + (size_t)H * W;
+            for (int x = 0; x < W; ++x) {
+                float gx = lin_x[x] + (sign * fxp[x]) / sx; /* video_net.py:42-45 */
+                float gy = lin_y[y] + (sign * fyp[x]) / sy;
+                /* ATen grid_sampler unnormalize (align_corners=True) + border clip */
+                float ix = (gx + 1.0f) * sx;
+                float iy = (gy + 1.0f) * sy;
+                ix = fminf(fmaxf(ix, 0.0f), wmax);
+                iy = fminf(fmaxf(iy, 0.0f), hmax);
+                float x0 = floorf(ix), y0 = floorf(iy);
+                float w = ix - x0, e = 1.0f - w, nn = iy - y0, s = 1.0f - nn;
+                float nw = s * e, ne = s * w, sw = nn * e, se = nn * w;
+                int x0i = (int)x0, y0i = (int)y0;
+                int x1ok = x0i + 1 <= W - 1, y1ok = y0i + 1 <= H - 1;
+                for (int c = 0; c < C; ++c) {
+                    const float *p = im + ((size_t)n * C + c) * H * W;
+                    float vnw = p[(size_t)y0i * W + x0i];
+                    float vne = x1ok ? p[(size_t)y0i * W + x0i + 1] : 0.0f;
+                    float vsw = y1ok ? p[(size_t)(y0i + 1) * W + x0i] : 0.0f;
+                    float vse = (x1ok && y1ok) ? p[(size_t)(y0i + 1) * W + x0i + 1] : 0.0f;
+                    float acc = vnw * nw;
+                    acc = fmaf(vne, ne, acc);
+                    acc = fmaf(vsw, sw, acc);
+                    acc = fmaf(vse, se, acc);
+                    if (round_out) acc = rintf(acc); /* lossless: pMCTF_L.py:302-303 */
+                    out[((size_t)n * C + c) * H * W + (size_t)y * W + x] = acc;
+                }
+            }
+        }
+}
+
+/* bilineardownsacling(mv) / 2: video_net.py:66-71, used at pMCTF_L.py:317,336,401.
+ * mv [N,2,H,W] -> [N,2,H/2,W/2]; ATen CPU order is ((v00+v01)+v10)+v11 with weights 1/4.       */
+ORC_API void orc_chroma_mv_down(const float *mv, float *out, int N, int H, int W)
+{
+    const int h2 = H / 2, w2 = W / 2;
+    for (int p = 0; p < N * 2; ++p)
+        for (int y = 0; y < h2; ++y)
+            for (int x = 0; x < w2; ++x) {
+                const float *a = mv + (size_t)p * H * W + (size_t)(2 * y) * W + 2 * x;
+                float v = ((a[0] * 0.25f + a[1] * 0.25f) + a[W] * 0.25f) + a[W + 1] * 0.25f;
+                out[(size_t)p * h2 * w2 + (size_t)y * w2 + x] = v / 2.0f;
+            }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* PredictUpdate: lifting_1d.py:25-49.  One plane x[H][W] (already multiplied by in_mul by the
+ * caller) -> out[H][W].  Band-tiled so the 16-channel intermediates stay in cache.             */
+#define XB 64 /* x block held in registers */
+
+/* generic 3x3 layer on a band: in[cin][rows_in][Wp], out[cout][rows_out][Wp]; Wp = W+2 with a
+ * zero column on each side; out row r uses in rows r, r+1, r+2 (in starts one row earlier).   */
+static void conv3x3_band(const float *in, int cin, int rows_in, const float *wgt, const float *bias,
+                         float *out, int cout, int rows_out, int W, int Wp)
+{
+    for (int co = 0; co < cout; ++co)
+        for (int r = 0; r < rows_out; ++r)
+            for (int xb = 0; xb < W; xb += XB) {
+                const int nx = (W - xb < XB) ? W - xb : XB;
+                float acc[XB];
+                for (int i = 0; i < XB; ++i) acc[i] = bias[co];
+                for (int ci = 0; ci < cin; ++ci)
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const float *row = in + ((size_t)ci * rows_in + r + ky) * Wp + xb;
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const float wv = wgt[((co * cin + ci) * 3 + ky) * 3 + kx];
+                            if (nx == XB) {
+                                for (int i = 0; i < XB; ++i) acc[i] = __builtin_fmaf(wv, row[i + kx], acc[i]);
+                            } else {
+                                for (int i = 0; i < nx; ++i) acc[i] = __builtin_fmaf(wv, row[i + kx], acc[i]);
+                            }
+                        }
+                    }
+                float *o = out + ((size_t)co * rows_out + r) * Wp + 1 + xb;
+                for (int i = 0; i < nx; ++i) o[i] = acc[i];
+            }
+}
+
+static void band_fix(float *buf, int ch, int rows, int Wp, int W, int row0_img, int H, int do_tanh)
+{
+    /* zero padding semantics of every layer: rows outside the image and the two border columns
+     * are 0 (layers.py:54-56, padding=1 zeros); optional tanh (lifting_1d.py:39,42).           */
+    for (int c = 0; c < ch; ++c)
+        for (int r = 0; r < rows; ++r) {
+            float *p = buf + ((size_t)c * rows + r) * Wp;
+            const int yi = row0_img + r;
+            if (yi < 0 || yi >= H) {
+                memset(p, 0, sizeof(float) * Wp);
+                continue;
+            }
+            p[0] = 0.0f;
+            p[W + 1] = 0.0f;
+            if (do_tanh)
+                for (int x = 1; x <= W; ++x) p[x] = tanh_det(p[x]);
+        }
+}
+
+#define BAND 16
+
+ORC_API void orc_predict_update(const float *x, const orc_pu_t *pu, float *out, int N, int H, int W, float in_mul)
+{
+    const int Wp = W + 2;
+    const int nb = (H + BAND - 1) / BAND;
+#pragma omp parallel
+    {
+        float *xin = (float *)malloc(sizeof(float) * (BAND + 8) * Wp);
+        float *c1 = (float *)malloc(sizeof(float) * NCH * (BAND + 6) * Wp);
+        float *a1 = (float *)malloc(sizeof(float) * NCH * (BAND + 6) * Wp);
+        float *a2 = (float *)malloc(sizeof(float) * NCH * (BAND + 4) * Wp);
+        float *a3 = (float *)malloc(sizeof(float) * NCH * (BAND + 2) * Wp);
+        float *o4 = (float *)malloc(sizeof(float) * BAND * Wp);
+#pragma omp for collapse(2) schedule(dynamic)
+        for (int n = 0; n < N; ++n)
+            for (int b = 0; b < nb; ++b) {
+                const int y0 = b * BAND;
+                const int rows = (H - y0 < BAND) ? H - y0 : BAND;
+                const float *xp = x + (size_t)n * H * W;
+                /* input rows y0-4 .. y0+rows+4, zero outside */
+                for (int r = 0; r < rows + 8; ++r) {
+                    float *d = xin + (size_t)r * Wp;
+                    const int yi = y0 - 4 + r;
+                    if (yi < 0 || yi >= H) {
+                        memset(d, 0, sizeof(float) * Wp);
+                    } else {
+                        d[0] = 0.0f;
+                        d[W + 1] = 0.0f;
+                        for (int xx = 0; xx < W; ++xx) d[1 + xx] = xp[(size_t)yi * W + xx] * in_mul;
+                    }
+                }
+                /* conv1 -> c1 rows y0-3.. (rows+6) */
+                conv3x3_band(xin, 1, rows + 8, pu->w1, pu->b1, c1, NCH, rows + 6, W, Wp);
+                memcpy(a1, c1, sizeof(float) * NCH * (rows + 6) * Wp);
+                band_fix(c1, NCH, rows + 6, Wp, W, y0 - 3, H, 0);
+                band_fix(a1, NCH, rows + 6, Wp, W, y0 - 3, H, 1); /* tanh(conv1) */
+                conv3x3_band(a1, NCH, rows + 6, pu->w2, pu->b2, a2, NCH, rows + 4, W, Wp);
+                band_fix(a2, NCH, rows + 4, Wp, W, y0 - 2, H, 1); /* tanh(conv2) */
+                conv3x3_band(a2, NCH, rows + 4, pu->w3, pu->b3, a3, NCH, rows + 2, W, Wp);
+                /* x = conv1 + conv3   lifting_1d.py:45 */
+                for (int c = 0; c < NCH; ++c)
+                    for (int r = 0; r < rows + 2; ++r) {
+                        float *p3 = a3 + ((size_t)c * (rows + 2) + r) * Wp;
+                        const float *p1 = c1 + ((size_t)c * (rows + 6) + r + 2) * Wp;
+                        for (int xx = 1; xx <= W; ++xx) p3[xx] = p1[xx] + p3[xx];
+                    }
+                band_fix(a3, NCH, rows + 2, Wp, W, y0 - 1, H, 0);
+                conv3x3_band(a3, NCH, rows + 2, pu->w4, pu->b4, o4, 1, rows, W, Wp);
+                for (int r = 0; r < rows; ++r)
+                    memcpy(out + (size_t)n * H * W + (size_t)(y0 + r) * W, o4 + (size_t)r * Wp + 1, sizeof(float) * W);
+            }
+        free(xin); free(c1); free(a1); free(a2); free(a3); free(o4);
+    }
+}
+
+/* TemporalLifting.predict_filter / update_filter: wavelet_transform_temporal_mctf.py:27-45.
+ * out = (x + PU(x)*0.1) * scale   (lossy);  out = x + round(PU(x)*0.1)   (lossless)          */
+ORC_API void orc_temporal_filter(const float *x, const orc_pu_t *pu, float scale, int lossy,
+                                 float *out, int N, int H, int W)
+{
+    const size_t n = (size_t)N * H * W;
+    float *t = (float *)malloc(sizeof(float) * n);
+    orc_predict_update(x, pu, t, N, H, W, 1.0f);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) {
+        float tmp = t[i] * 0.1f;
+        if (!lossy) tmp = rintf(tmp);
+        float v = x[i] + tmp;
+        if (lossy) v = v * scale;
+        out[i] = v;
+    }
+    free(t);
+}
+
+/* pMCTF.forward_MCTF: pMCTF_L.py:297-312.  Planes [N,H,W] (C=1), mv [mvN,2,H,W].
+ * pred / inv may be NULL.                                                                     */
+ORC_API void orc_forward_mctf(const float *ref, const float *cur, const float *mv, int mvN,
+                              const float *lin_x, const float *lin_y, const orc_pu_t *P_t, const orc_pu_t *U_t,
+                              float scale_p, float scale_u, int lossy,
+                              float *L, float *Hh, float *pred_out, float *inv_out, int N, int H, int W)
+{
+    const size_t n = (size_t)N * H * W;
+    float *wbuf = (float *)malloc(sizeof(float) * n);
+    float *pred = (float *)malloc(sizeof(float) * n);
+    orc_flow_warp(ref, mv, lin_x, lin_y, wbuf, N, 1, H, W, mvN, 1.0f, !lossy);
+    orc_temporal_filter(wbuf, P_t, scale_p, lossy, pred, N, H, W);
+    for (size_t i = 0; i < n; ++i) Hh[i] = cur[i] - pred[i];
+    if (pred_out) memcpy(pred_out, pred, sizeof(float) * n);
+    orc_flow_warp(Hh, mv, lin_x, lin_y, wbuf, N, 1, H, W, mvN, -1.0f, !lossy);
+    orc_temporal_filter(wbuf, U_t, scale_u, lossy, pred, N, H, W);
+    for (size_t i = 0; i < n; ++i) L[i] = ref[i] + pred[i];
+    if (inv_out) memcpy(inv_out, pred, sizeof(float) * n);
+    free(wbuf); free(pred);
+}
+
+/* pMCTF.inverse_MCTF: pMCTF_L.py:314-330 (mv already down-scaled by the caller if chroma).     */
+ORC_API void orc_inverse_mctf(const float *L, const float *Hh, const float *mv, int mvN,
+                              const float *lin_x, const float *lin_y, const orc_pu_t *P_t, const orc_pu_t *U_t,
+                              float scale_p, float scale_u, int lossy,
+                              float *ref, float *cur, int N, int H, int W)
+{
+    const size_t n = (size_t)N * H * W;
+    float *wbuf = (float *)malloc(sizeof(float) * n);
+    float *f = (float *)malloc(sizeof(float) * n);
+    orc_flow_warp(Hh, mv, lin_x, lin_y, wbuf, N, 1, H, W, mvN, -1.0f, !lossy);
+    orc_temporal_filter(wbuf, U_t, scale_u, lossy, f, N, H, W);
+    for (size_t i = 0; i < n; ++i) ref[i] = L[i] - f[i];
+    orc_flow_warp(ref, mv, lin_x, lin_y, wbuf, N, 1, H, W, mvN, 1.0f, !lossy);
+    orc_temporal_filter(wbuf, P_t, scale_p, lossy, f, N, H, W);
+    for (size_t i = 0; i < n; ++i) cur[i] = Hh[i] + f[i];
+    free(wbuf); free(f);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* one lifting step of iWave1D on contiguous phases [N,h,W]: lifting_1d.py:104-112 (and the
+ * three repeats).  dst = dst + sign * (skip + 0.1 * (PU(skip/256) * 256)),
+ * skip = conv(3,1)(reflect-pad-rows(src)) + bias.                                              */
+static void lift_step(const float *src, float *dst, const float tap[3], float bias, const orc_pu_t *pu,
+                      float dyn, int lossy, float sign, int N, int h, int W)
+{
+    const size_t n = (size_t)N * h * W;
+    float *skip = (float *)malloc(sizeof(float) * n);
+    float *l = (float *)malloc(sizeof(float) * n);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int b = 0; b < N; ++b)
+        for (int y = 0; y < h; ++y) {
+            /* ReflectionPad2d((0,0,1,1)): row -1 -> row 1, row h -> row h-2   lifting_1d.py:91 */
+            const int ym = (y == 0) ? 1 : y - 1;
+            const int yp = (y == h - 1) ? h - 2 : y + 1;
+            const float *r0 = src + ((size_t)b * h + ym) * W;
+            const float *r1 = src + ((size_t)b * h + y) * W;
+            const float *r2 = src + ((size_t)b * h + yp) * W;
+            float *o = skip + ((size_t)b * h + y) * W;
+            for (int x = 0; x < W; ++x) {
+                float acc = bias;
+                acc = __builtin_fmaf(tap[0], r0[x], acc);
+                acc = __builtin_fmaf(tap[1], r1[x], acc);
+                acc = __builtin_fmaf(tap[2], r2[x], acc);
+                o[x] = acc;
+            }
+        }
+    /* skip / 256 is an exact power-of-two scaling == * (1/256) */
+    orc_predict_update(skip, pu, l, N, h, W, 1.0f / dyn);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) {
+        float lv = l[i] * dyn;
+        float tmp = skip[i] + lv * 0.1f;
+        if (!lossy) tmp = rintf(tmp);
+        dst[i] = (sign > 0) ? dst[i] + tmp : dst[i] - tmp;
+    }
+    free(skip); free(l);
+}
+
+/* iWave1D.forward_lift: lifting_1d.py:103-145.  x [N,H,W] -> l,h [N,H/2,W] (split along rows). */
+ORC_API void orc_iwave1d_forward(const float *x, const orc_iwave_t *p, float *l, float *hh, int N, int H, int W)
+{
+    const int h = H / 2;
+    for (int b = 0; b < N; ++b)
+        for (int y = 0; y < h; ++y) { /* split: lifting_1d.py:10-13 */
+            memcpy(l + ((size_t)b * h + y) * W, x + ((size_t)b * H + 2 * y) * W, sizeof(float) * W);
+            memcpy(hh + ((size_t)b * h + y) * W, x + ((size_t)b * H + 2 * y + 1) * W, sizeof(float) * W);
+        }
+    lift_step(l, hh, p->tap[0], p->bias[0], &p->pu[0], p->dynamic_range, p->lossy, +1.0f, N, h, W); /* P1 -> x_o */
+    lift_step(hh, l, p->tap[1], p->bias[1], &p->pu[1], p->dynamic_range, p->lossy, +1.0f, N, h, W); /* U1 -> x_e */
+    lift_step(l, hh, p->tap[2], p->bias[2], &p->pu[2], p->dynamic_range, p->lossy, +1.0f, N, h, W); /* P2 */
+    lift_step(hh, l, p->tap[3], p->bias[3], &p->pu[3], p->dynamic_range, p->lossy, +1.0f, N, h, W); /* U2 */
+    if (p->lossy) { /* lifting_1d.py:141-143 */
+        const size_t n = (size_t)N * h * W;
+        for (size_t i = 0; i < n; ++i) { l[i] = l[i] * p->scale_l; hh[i] = hh[i] * p->scale_h; }
+    }
+}
+
+/* iWave1D.backward_lift: lifting_1d.py:147-189 (merge: :16-22).                                */
+ORC_API void orc_iwave1d_backward(const float *l_in, const float *h_in, const orc_iwave_t *p, float *x, int N, int H, int W)
+{
+    const int h = H / 2;
+    const size_t n = (size_t)N * h * W;
+    float *l = (float *)malloc(sizeof(float) * n);
+    float *hh = (float *)malloc(sizeof(float) * n);
+    for (size_t i = 0; i < n; ++i) {
+        l[i] = p->lossy ? l_in[i] / p->scale_l : l_in[i];
+        hh[i] = p->lossy ? h_in[i] / p->scale_h : h_in[i];
+    }
+    lift_step(hh, l, p->tap[3], p->bias[3], &p->pu[3], p->dynamic_range, p->lossy, -1.0f, N, h, W); /* U2 */
+    lift_step(l, hh, p->tap[2], p->bias[2], &p->pu[2], p->dynamic_range, p->lossy, -1.0f, N, h, W); /* P2 */
+    lift_step(hh, l, p->tap[1], p->bias[1], &p->pu[1], p->dynamic_range, p->lossy, -1.0f, N, h, W); /* U1 */
+    lift_step(l, hh, p->tap[0], p->bias[0], &p->pu[0], p->dynamic_range, p->lossy, -1.0f, N, h, W); /* P1 */
+    for (int b = 0; b < N; ++b)
+        for (int y = 0; y < h; ++y) {
+            memcpy(x + ((size_t)b * H + 2 * y) * W, l + ((size_t)b * h + y) * W, sizeof(float) * W);
+            memcpy(x + ((size_t)b * H + 2 * y + 1) * W, hh + ((size_t)b * h + y) * W, sizeof(float) * W);
+        }
+    free(l); free(hh);
+}
+
+static void transpose(const float *a, float *b, int N, int H, int W)
+{ /* [N,H,W] -> [N,W,H]: the permute(0,1,3,2) of wavelet_transform.py:32-40 */
+    for (int n = 0; n < N; ++n)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) b[((size_t)n * W + x) * H + y] = a[((size_t)n * H + y) * W + x];
+}
+
+/* LiftingScheme2D.forward_lift_2d: wavelet_transform.py:25-43.  x [N,H,W] -> 4 x [N,H/2,W/2].
+ * l_out/h_out ([N,H/2,W], the row-pass outputs, returned in the reference dict as transposed
+ * views) may be NULL.                                                                         */
+ORC_API void orc_lift2d_forward(const float *x, const orc_iwave_t *p, float *ll, float *lh, float *hl, float *hh,
+                                float *l_out, float *h_out, int N, int H, int W)
+{
+    const int h2 = H / 2, w2 = W / 2;
+    const size_t nh = (size_t)N * h2 * W, nq = (size_t)N * h2 * w2;
+    float *l = (float *)malloc(sizeof(float) * nh), *h = (float *)malloc(sizeof(float) * nh);
+    float *t = (float *)malloc(sizeof(float) * nh);
+    float *a = (float *)malloc(sizeof(float) * nq), *b = (float *)malloc(sizeof(float) * nq);
+    orc_iwave1d_forward(x, p, l, h, N, H, W);
+    if (l_out) memcpy(l_out, l, sizeof(float) * nh);
+    if (h_out) memcpy(h_out, h, sizeof(float) * nh);
+    transpose(l, t, N, h2, W);                 /* [N,W,h2] */
+    orc_iwave1d_forward(t, p, a, b, N, W, h2); /* -> [N,w2,h2] each; lift_v is lift_h (:20-21) */
+    transpose(a, ll, N, w2, h2);
+    transpose(b, lh, N, w2, h2);
+    transpose(h, t, N, h2, W);
+    orc_iwave1d_forward(t, p, a, b, N, W, h2);
+    transpose(a, hl, N, w2, h2);
+    transpose(b, hh, N, w2, h2);
+    free(l); free(h); free(t); free(a); free(b);
+}
+
+/* LiftingScheme2D.backward_lift_2d: wavelet_transform.py:45-57.                                */
+ORC_API void orc_lift2d_backward(const float *ll, const float *lh, const float *hl, const float *hh,
+                                 const orc_iwave_t *p, float *x, int N, int H, int W)
+{
+    const int h2 = H / 2, w2 = W / 2;
+    const size_t nh = (size_t)N * h2 * W, nq = (size_t)N * h2 * w2;
+    float *l = (float *)malloc(sizeof(float) * nh), *h = (float *)malloc(sizeof(float) * nh);
+    float *t = (float *)malloc(sizeof(float) * nh);
+    float *a = (float *)malloc(sizeof(float) * nq), *b = (float *)malloc(sizeof(float) * nq);
+    transpose(ll, a, N, h2, w2); /* [N,w2,h2] */
+    transpose(lh, b, N, h2, w2);
+    orc_iwave1d_backward(a, b, p, t, N, W, h2); /* [N,W,h2] */
+    transpose(t, l, N, W, h2);
+    transpose(hl, a, N, h2, w2);
+    transpose(hh, b, N, h2, w2);
+    orc_iwave1d_backward(a, b, p, t, N, W, h2);
+    transpose(t, h, N, W, h2);
+    orc_iwave1d_backward(l, h, p, x, N, H, W);
+    free(l); free(h); free(t); free(a); free(b);
+}
+
+/* quantize_subband (+ optional RoundNoGradient): pWave.py:184-189,256-257,337; layers.py:71-92.
+ * out = [rint](clamp(s * q, -clip, clip)); torch.round is half-to-even == rintf.               */
+ORC_API void orc_quantize(const float *s, float q, float clip, int lossy, int do_round, float *out, long n)
+{
+    for (long i = 0; i < n; ++i) {
+        float v = lossy ? s[i] * q : s[i];
+        v = fminf(fmaxf(v, -clip), clip);
+        if (do_round) v = rintf(v);
+        out[i] = v;
+    }
+}
+
+/* dequantize_subbands: pWave.py:191-202.  out = s_hat / q                                      */
+ORC_API void orc_dequantize(const float *s_hat, float q, int lossy, float *out, long n)
+{
+    for (long i = 0; i < n; ++i) out[i] = lossy ? s_hat[i] / q : s_hat[i];
+}
