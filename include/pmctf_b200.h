@@ -1,0 +1,182 @@
+/*
+ * pmctf_b200.h -- C ABI of the B200 (sm_100a) implementation of Learned-pMCTF's
+ * motion-compensated temporal lifting + pWave++ spatial lifting hot path.
+ *
+ * The reference has no FFI for this path: its boundary is the Python nn.Module surface
+ * (SURVEY.md section 8b).  Each entry point below replaces the reference function cited beside it
+ * (paths relative to the reference repository) and is what a maintainer would bind with ctypes
+ * from those modules (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer to fp32 unless noted;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - nothing here allocates, frees or synchronises: the caller owns inputs, outputs and
+ *     workspaces and keeps them alive until the stream has drained;
+ *   - every function returns 0 on success, a negative PMCTF_E* code for rejected arguments
+ *     (nothing was launched) or a positive cudaError_t from the launch;
+ *   - there is no CPU fallback.
+ *
+ * Arithmetic contract (DESIGN.md "Numerics"): fp32 throughout; every convolution output is one
+ * sequential fma chain in (ci, ky, kx) order starting from the bias; tanh is the deterministic
+ * routine documented in DESIGN.md; all other ops are single correctly rounded fp32 operations
+ * in the reference's order.  oracle/pmctf_oracle.c restates the same contract on the CPU and
+ * the two agree bit for bit.
+ */
+#ifndef PMCTF_B200_H
+#define PMCTF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMCTF_ABI_VERSION 1
+
+#define PMCTF_EINVAL (-1)   /* null pointer / non-positive size / unsupported flag */
+#define PMCTF_ESHAPE (-2)   /* shape not supported (odd split size, plane too small for reflection) */
+#define PMCTF_EWORKSPACE (-3) /* workspace too small */
+
+#define PMCTF_PU_PACKED_FLOATS 5000 /* size of one packed PredictUpdate weight block */
+#define PMCTF_IWAVE_PACKED_FLOATS (4 * PMCTF_PU_PACKED_FLOATS)
+
+/* A strided view of a batch of single-channel planes: element (n, y, x) lives at
+ * p[n*bs + y*rs + x*cs] (strides in elements).  This is how split (lifting_1d.py:10-13),
+ * merge (:16-22) and the permute(0,1,3,2) views of wavelet_transform.py:32-54 are expressed
+ * without copies. */
+typedef struct {
+    float *p;
+    long long bs, rs, cs;
+} pmctf_plane_t;
+
+enum { PMCTF_SRC_PLANE = 0, PMCTF_SRC_WARP = 1, PMCTF_SRC_SKIP3 = 2 };
+enum { PMCTF_MODE_ACCUM = 0, PMCTF_MODE_FILTER = 1, PMCTF_MODE_PU = 2 };
+
+/* One fused lifting step:
+ *      s   = source(src)                         plane | warp(src, sign*mv) | 3-tap skip conv of src
+ *      t   = PU(s * in_mul) * post_mul           PredictUpdate, lifting_1d.py:25-49
+ *      tmp = s + t * 0.1   [rint if round_tmp]   lifting_1d.py:108-111 / wavelet_transform_temporal_mctf.py:28-32
+ *      r   = tmp * out_mul                       scale_p / scale_u (wavelet_transform_temporal_mctf.py:33-35)
+ *      out = (base/base_div1/base_div2 + sign*r) * final_mul     MODE_ACCUM
+ *      out = r                                                  MODE_FILTER
+ *      out = t                                                  MODE_PU
+ *      pred (optional) = r ; aux (optional, SKIP3/PLANE) = (src/src_div1/src_div2) * aux_mul
+ * All planes are logical [n, h, w]; warp sources must be dense NCHW (rs == w, cs == 1). */
+typedef struct {
+    int n, h, w;
+    int src_kind, mode;
+    pmctf_plane_t src;
+    float src_div1, src_div2;
+    /* PMCTF_SRC_WARP: video_net.py:32-55 */
+    const float *mv;      /* [mv_n, 2, mv_h, mv_w]; n/mv_n consecutive planes share a field (mv_n == 1: the
+                           * `.tile` of pMCTF_L.py:299-300; mv_n == n/2: batched chroma pairs) */
+    int mv_n, mv_down;    /* mv_down: mv is the LUMA field [.,2,2h,2w]; use 2x2 mean / 2 (video_net.py:66-71) */
+    float mv_sign;
+    const float *lin_x, *lin_y; /* torch.linspace(-1,1,w) / (-1,1,h) tables (video_net.py:36-39) */
+    int round_src;        /* lossless: pMCTF_L.py:302-303 */
+    /* PMCTF_SRC_SKIP3: conv (3,1) + bias on the row-reflect-padded source, lifting_1d.py:105-106 */
+    float tap0, tap1, tap2, tap_bias;
+    /* PredictUpdate weights packed by pmctf_pack_pu_weights */
+    const float *pu_packed;
+    float in_mul, post_mul, out_mul;
+    int round_tmp;
+    pmctf_plane_t base;
+    float base_div1, base_div2, sign, final_mul;
+    pmctf_plane_t out, pred, aux;
+    float aux_mul;
+} pmctf_step_t;
+
+/* iWave1D parameters (lifting_1d.py:52-101) */
+typedef struct {
+    float tap[4][3];       /* conv_P1, conv_U1, conv_P2, conv_U2 weights (1,1,3,1) */
+    float bias[4];
+    const float *pu_packed; /* 4 packed blocks: P_1, U_1, P_2, U_2 */
+    float scale_l, scale_h; /* lifting_1d.py:98-101 */
+    float dynamic_range;    /* 256: lifting_1d.py:62 */
+    int lossy;
+} pmctf_iwave_t;
+
+/* TemporalLifting parameters (wavelet_transform_temporal_mctf.py:11-25) */
+typedef struct {
+    const float *P_t_packed, *U_t_packed;
+    float scale_p, scale_u; /* 1/sqrt(2), 0.5 */
+    int lossy;
+} pmctf_temporal_t;
+
+int pmctf_abi_version(void);
+const char *pmctf_error_string(int code);
+
+/* Repack one PredictUpdate's 8 tensors (OIHW, as in the state_dict) into the kernel layout.
+ * Replaces nothing in the reference; run once per weight version. */
+int pmctf_pack_pu_weights(const float *w1, const float *b1, const float *w2, const float *b2,
+                          const float *w3, const float *b3, const float *w4, const float *b4,
+                          float *packed, void *stream);
+
+/* flow_warp(im, flow): pMCTF/layers/video/video_net.py:32-55.
+ * im [N,C,H,W], flow [flowN,2,H,W] in pixels (flowN divides N), out [N,C,H,W]. */
+int pmctf_flow_warp(const float *im, const float *flow, const float *lin_x, const float *lin_y, float *out,
+                    int N, int C, int H, int W, int flowN, float sign, int round_out, void *stream);
+
+/* bilineardownsacling(mv) / 2: video_net.py:66-71 as used at pMCTF_L.py:317,336,401.
+ * mv [N,2,H,W] -> out [N,2,H/2,W/2]. */
+int pmctf_chroma_mv_down(const float *mv, float *out, int N, int H, int W, void *stream);
+
+/* The generic fused step (see pmctf_step_t). */
+int pmctf_lift_step(const pmctf_step_t *step, void *stream);
+
+/* PredictUpdate.forward: lifting_1d.py:36-49.  x, out dense [N,1,H,W]. */
+int pmctf_predict_update(const float *x, const float *pu_packed, float in_mul, float *out,
+                         int N, int H, int W, void *stream);
+
+/* TemporalLifting.predict_filter / update_filter: wavelet_transform_temporal_mctf.py:27-45
+ * (which = 0 predict, 1 update). */
+int pmctf_temporal_filter(const float *x, const pmctf_temporal_t *t, int which, float *out,
+                          int N, int H, int W, void *stream);
+
+/* pMCTF.forward_MCTF: pMCTF/models/video/pMCTF_L.py:297-312.  ref, cur, L, H dense [N,1,H,W];
+ * mv [mv_n,2,H,W] (or the luma field [mv_n,2,2H,2W] with mv_down=1, fusing pMCTF_L.py:401);
+ * pred / inv may be NULL (they only feed the MSE terms, pMCTF_L.py:351,373). */
+int pmctf_forward_mctf(const float *ref, const float *cur, const float *mv, int mv_n, int mv_down,
+                       const float *lin_x, const float *lin_y, const pmctf_temporal_t *t,
+                       float *L, float *Hh, float *pred, float *inv, int N, int H, int W, void *stream);
+
+/* pMCTF.inverse_MCTF: pMCTF_L.py:314-330 (mv_down=1 == downscale=True). */
+int pmctf_inverse_mctf(const float *L, const float *Hh, const float *mv, int mv_n, int mv_down,
+                       const float *lin_x, const float *lin_y, const pmctf_temporal_t *t,
+                       float *ref, float *cur, int N, int H, int W, void *stream);
+
+/* iWave1D.forward_lift / backward_lift on strided views: lifting_1d.py:103-189.
+ * x is the logical [n, 2*h2, w] input; l, h are logical [n, h2, w] outputs (any strides).
+ * workspace: n*h2*w floats (forward: the unscaled high band), 2*n*h2*w floats (backward). */
+int pmctf_iwave1d_forward(const pmctf_plane_t *x, const pmctf_iwave_t *p, const pmctf_plane_t *l,
+                          const pmctf_plane_t *h, int n, int h2, int w, float *workspace,
+                          long long workspace_floats, void *stream);
+int pmctf_iwave1d_backward(const pmctf_plane_t *l, const pmctf_plane_t *h, const pmctf_iwave_t *p,
+                           const pmctf_plane_t *x, int n, int h2, int w, float *workspace,
+                           long long workspace_floats, void *stream);
+
+/* LiftingScheme2D.forward_lift_2d / backward_lift_2d: wavelet_transform.py:25-57.
+ * x dense [N,1,H,W]; ll, lh, hl, hh dense [N,1,H/2,W/2]; l_out, h_out dense [N,1,H/2,W] (the
+ * row-pass outputs the reference returns as 'l','h', may be NULL); workspace_floats >=
+ * pmctf_lift2d_workspace(N,H,W) = 2*N*H*W. */
+long long pmctf_lift2d_workspace(int N, int H, int W);
+int pmctf_lift2d_forward(const float *x, const pmctf_iwave_t *p, float *ll, float *lh, float *hl, float *hh,
+                         float *l_out, float *h_out, int N, int H, int W,
+                         float *workspace, long long workspace_floats, void *stream);
+int pmctf_lift2d_backward(const float *ll, const float *lh, const float *hl, const float *hh,
+                          const pmctf_iwave_t *p, float *x, int N, int H, int W,
+                          float *workspace, long long workspace_floats, void *stream);
+/* backward_lift_2d with dequantize_subbands (pWave.py:191-202) fused into the first loads:
+ * ll is divided by ll_div (q_ll at the coarsest level, 1 elsewhere), lh/hl/hh by q. */
+int pmctf_lift2d_backward_q(const float *ll, const float *lh, const float *hl, const float *hh,
+                            float ll_div, float q, const pmctf_iwave_t *p, float *x, int N, int H, int W,
+                            float *workspace, long long workspace_floats, void *stream);
+
+/* quantize_subband (+ RoundNoGradient): pWave.py:184-189,256-257,337; layers.py:71-92.
+ * out = [rint](clamp(s*q, +-clip)).  dequantize_subbands: pWave.py:191-202, out = s_hat / q. */
+int pmctf_quantize(const float *s, float q, float clip, int lossy, int do_round, float *out,
+                   long long n, void *stream);
+int pmctf_dequantize(const float *s_hat, float q, int lossy, float *out, long long n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMCTF_B200_H */

@@ -1,0 +1,116 @@
+"""ctypes binding of the C-ABI library (include/pmctf_b200.h) -- the only way the Python host
+reaches the GPU kernels.  There is no fallback: if the library is missing or a call is rejected
+a RuntimeError is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "lib", "libpmctf_b200.so")
+SOURCES = [os.path.join(_HERE, "csrc", "pmctf_kernels.cu")]
+INCLUDE = os.path.join(ROOT, "include")
+
+PU_PACKED_FLOATS = 5000
+SRC_PLANE, SRC_WARP, SRC_SKIP3 = 0, 1, 2
+MODE_ACCUM, MODE_FILTER, MODE_PU = 0, 1, 2
+
+_f = C.c_float
+_fp = C.c_void_p  # device pointers travel as integers
+
+
+class Plane(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("bs", C.c_longlong), ("rs", C.c_longlong), ("cs", C.c_longlong)]
+
+
+class Step(C.Structure):
+    _fields_ = [("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("src_kind", C.c_int), ("mode", C.c_int),
+                ("src", Plane), ("src_div1", _f), ("src_div2", _f),
+                ("mv", _fp), ("mv_n", C.c_int), ("mv_down", C.c_int), ("mv_sign", _f),
+                ("lin_x", _fp), ("lin_y", _fp), ("round_src", C.c_int),
+                ("tap0", _f), ("tap1", _f), ("tap2", _f), ("tap_bias", _f),
+                ("pu_packed", _fp), ("in_mul", _f), ("post_mul", _f), ("out_mul", _f), ("round_tmp", C.c_int),
+                ("base", Plane), ("base_div1", _f), ("base_div2", _f), ("sign", _f), ("final_mul", _f),
+                ("out", Plane), ("pred", Plane), ("aux", Plane), ("aux_mul", _f)]
+
+
+class IWave(C.Structure):
+    _fields_ = [("tap", (_f * 3) * 4), ("bias", _f * 4), ("pu_packed", _fp), ("scale_l", _f), ("scale_h", _f),
+                ("dynamic_range", _f), ("lossy", C.c_int)]
+
+
+class Temporal(C.Structure):
+    _fields_ = [("P_t_packed", _fp), ("U_t_packed", _fp), ("scale_p", _f), ("scale_u", _f), ("lossy", C.c_int)]
+
+
+# name -> argtypes; every entry returns int except the ones listed in _RESTYPES.  This table is
+# also what tests/test_cabi.py checks against include/pmctf_b200.h.
+_I, _LL, _P = C.c_int, C.c_longlong, C.c_void_p
+SIGNATURES = {
+    "pmctf_abi_version": [],
+    "pmctf_error_string": [_I],
+    "pmctf_pack_pu_weights": [_P] * 10,
+    "pmctf_flow_warp": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _f, _I, _P],
+    "pmctf_chroma_mv_down": [_P, _P, _I, _I, _I, _P],
+    "pmctf_lift_step": [C.POINTER(Step), _P],
+    "pmctf_predict_update": [_P, _P, _f, _P, _I, _I, _I, _P],
+    "pmctf_temporal_filter": [_P, C.POINTER(Temporal), _I, _P, _I, _I, _I, _P],
+    "pmctf_forward_mctf": [_P, _P, _P, _I, _I, _P, _P, C.POINTER(Temporal), _P, _P, _P, _P, _I, _I, _I, _P],
+    "pmctf_inverse_mctf": [_P, _P, _P, _I, _I, _P, _P, C.POINTER(Temporal), _P, _P, _I, _I, _I, _P],
+    "pmctf_iwave1d_forward": [C.POINTER(Plane), C.POINTER(IWave), C.POINTER(Plane), C.POINTER(Plane), _I, _I, _I, _P, _LL, _P],
+    "pmctf_iwave1d_backward": [C.POINTER(Plane), C.POINTER(Plane), C.POINTER(IWave), C.POINTER(Plane), _I, _I, _I, _P, _LL, _P],
+    "pmctf_lift2d_workspace": [_I, _I, _I],
+    "pmctf_lift2d_forward": [_P, C.POINTER(IWave), _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _LL, _P],
+    "pmctf_lift2d_backward": [_P, _P, _P, _P, C.POINTER(IWave), _P, _I, _I, _I, _P, _LL, _P],
+    "pmctf_lift2d_backward_q": [_P, _P, _P, _P, _f, _f, C.POINTER(IWave), _P, _I, _I, _I, _P, _LL, _P],
+    "pmctf_quantize": [_P, _f, _f, _I, _I, _P, _LL, _P],
+    "pmctf_dequantize": [_P, _f, _I, _P, _LL, _P],
+}
+_RESTYPES = {"pmctf_error_string": C.c_char_p, "pmctf_lift2d_workspace": C.c_longlong}
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a into lib/libpmctf_b200.so (in-tree, so the built file
+    travels with the repository snapshot to the GPU box)."""
+    newest = max(os.path.getmtime(p) for p in SOURCES + [os.path.join(INCLUDE, "pmctf_b200.h")])
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB_PATH, *SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU or PyTorch fallback for the pMCTF hot path)")
+        L = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        if L.pmctf_abi_version() != 1:
+            raise RuntimeError("libpmctf_b200.so ABI version mismatch; rebuild")
+        _lib = L
+    return _lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        msg = lib().pmctf_error_string(code)
+        raise RuntimeError(f"{what} failed ({code}): {msg.decode() if msg else '?'}")

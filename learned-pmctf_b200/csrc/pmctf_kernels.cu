@@ -1,0 +1,912 @@
+// pmctf_kernels.cu -- sm_100a kernels for the MCTF + pWave++ lifting hot path.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false ...
+// (-fmad=false is part of the arithmetic contract: fma happens only where fmaf() is written.)
+//
+// Kernels
+//   lift_step_kernel<SRC>   fused {plane | flow-warp | 3-tap skip} -> PredictUpdate CNN (4 conv
+//                           layers chained in shared memory, halo recompute) -> lifting
+//                           accumulate.  One launch == one lifting step == one HBM pass.
+//   flow_warp_kernel        stand-alone bilinear backward warp (flow_warp of the reference)
+//   chroma_mv_down_kernel   2x2 mean / 2 of the luma motion field
+//   quantize / dequantize   per-subband elementwise
+//   pack_pu_kernel          OIHW -> kernel weight layout
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pmctf_b200.h"
+
+namespace pmctf {
+
+// ------------------------------------------------------------------------------------------
+// tile geometry (logical coordinates: what the reference's conv2d sees)
+constexpr int TH = 32, TW = 32;
+constexpr int S_ROWS = TH + 8, S_COLS = TW + 8, S_P = 41;    // source tile s, origin (-4,-4)
+constexpr int T_ROWS = TH + 10, T_P = 41;                    // raw src tile for SKIP3, origin (-5,-4)
+constexpr int A1_ROWS = TH + 6, A1_COLS = TW + 6, A1_P = 40; // tanh(conv1), origin (-3,-3)
+constexpr int A2_ROWS = TH + 4, A2_COLS = TW + 4, A2_P = 40; // tanh(conv2), origin (-2,-2)
+constexpr int A3_ROWS = TH + 2, A3_COLS = TW + 2, A3_P = 36; // conv1 + conv3, origin (-1,-1)
+constexpr int O_P = 33;                                      // PU output tile
+
+// packed PredictUpdate weights (floats)
+constexpr int W1_OFF = 0;      // [9][16]          (k, co)
+constexpr int B1_OFF = 144;    // [16]
+constexpr int W2_OFF = 160;    // [16 ci][9][16 co]
+constexpr int B2_OFF = 2464;
+constexpr int W3_OFF = 2480;
+constexpr int B3_OFF = 4784;
+constexpr int W4_OFF = 4800;   // [16 ci][12] (9 used)
+constexpr int B4_OFF = 4992;
+constexpr int WPACK = PMCTF_PU_PACKED_FLOATS;
+static_assert(WPACK == 5000, "header and kernel disagree on the packed size");
+
+// shared memory carve-up (floats)
+constexpr int SM_W = 0;
+constexpr int SM_S = SM_W + WPACK;                 // 5000
+constexpr int SM_T = SM_S + S_ROWS * S_P;          // + 1640
+constexpr int SM_A1 = SM_T + 1724;                 // T tile 42*41 = 1722, padded for 16 B alignment
+constexpr int SM_A2 = SM_A1 + 16 * A1_ROWS * A1_P; // + 24320
+constexpr int SM_END = SM_A2 + 16 * A2_ROWS * A2_P;
+constexpr int SMEM_BYTES = SM_END * 4;
+static_assert((SM_A1 * 4) % 16 == 0 && (SM_A2 * 4) % 16 == 0, "activation planes must be 16 B aligned");
+static_assert(16 * A3_ROWS * A3_P <= 16 * A1_ROWS * A1_P, "a3 aliases a1");
+static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit the 227 KB per-CTA limit");
+
+constexpr int NT = 672; // 21 warps, <= 96 registers each, one CTA per SM
+
+// ------------------------------------------------------------------------------------------
+// deterministic tanh (same specification as oracle/pmctf_oracle.c: IEEE +,*,fma,/,rint only)
+__device__ __forceinline__ float tanh_det(float x)
+{
+    float ax = fminf(fabsf(x), 10.0f);
+    float z = ax + ax;
+    float kf = rintf(z * 1.44269504f);
+    float r = fmaf(kf, -0.693145752f, z);
+    r = fmaf(kf, -1.42860677e-06f, r);
+    float q = 1.98412698e-4f;
+    q = fmaf(q, r, 1.38888889e-3f);
+    q = fmaf(q, r, 8.33333333e-3f);
+    q = fmaf(q, r, 4.16666667e-2f);
+    q = fmaf(q, r, 1.66666667e-1f);
+    q = fmaf(q, r, 0.5f);
+    float r2 = r * r;
+    float p = fmaf(q, r2, r);
+    int k = (int)kf;
+    float s = __int_as_float((k + 127) << 23);
+    float em1 = fmaf(s, p, s - 1.0f);
+    float t = em1 / (em1 + 2.0f);
+    return copysignf(t, x);
+}
+
+struct PlaneD {
+    float *p;
+    long long gs, bs, rs, cs;
+};
+
+__device__ __forceinline__ long long plane_off(const PlaneD &pl, int group_n, int n)
+{
+    const int g = n / group_n;
+    return (long long)g * pl.gs + (long long)(n - g * group_n) * pl.bs;
+}
+
+struct StepD {
+    int n, group_n, h, w;
+    int mode;
+    PlaneD src;
+    float src_div1, src_div2;
+    const float *mv;
+    int mv_share, mv_down, mv_h, mv_w; // mv_share = n / mv_n
+    float mv_sign, sx, sy;
+    const float *lin_x, *lin_y;
+    int round_src;
+    float tap0, tap1, tap2, tap_bias;
+    const float *pu_packed;
+    float in_mul, post_mul, out_mul;
+    int round_tmp;
+    PlaneD base;
+    float base_div1, base_div1_g1, base_div2, sign, final_mul; // base_div1_g1: divisor for plane group >= 1
+    PlaneD out, pred, aux;
+    float aux_mul;
+};
+
+// bilinear border-clamped backward warp of one sample: video_net.py:42-50 + ATen grid_sampler_2d
+// (align_corners=True, padding_mode=border), op for op as in oracle/pmctf_oracle.c:orc_flow_warp
+__device__ __forceinline__ float warp_sample(const float *__restrict__ im, long long rs, long long cs, int H, int W,
+                                             float lx, float ly, float fx, float fy, float sx, float sy)
+{
+    float gx = lx + fx / sx;
+    float gy = ly + fy / sy;
+    float ix = (gx + 1.0f) * sx;
+    float iy = (gy + 1.0f) * sy;
+    ix = fminf(fmaxf(ix, 0.0f), (float)(W - 1));
+    iy = fminf(fmaxf(iy, 0.0f), (float)(H - 1));
+    float x0 = floorf(ix), y0 = floorf(iy);
+    float w = ix - x0, e = 1.0f - w, nn = iy - y0, s = 1.0f - nn;
+    float nw = s * e, ne = s * w, sw = nn * e, se = nn * w;
+    int x0i = (int)x0, y0i = (int)y0;
+    bool x1ok = x0i + 1 <= W - 1, y1ok = y0i + 1 <= H - 1;
+    const float *p = im + (long long)y0i * rs + (long long)x0i * cs;
+    float vnw = __ldg(p);
+    float vne = x1ok ? __ldg(p + cs) : 0.0f;
+    float vsw = y1ok ? __ldg(p + rs) : 0.0f;
+    float vse = (x1ok && y1ok) ? __ldg(p + rs + cs) : 0.0f;
+    float acc = vnw * nw;
+    acc = fmaf(vne, ne, acc);
+    acc = fmaf(vsw, sw, acc);
+    acc = fmaf(vse, se, acc);
+    return acc;
+}
+
+// motion vector at (y, x) of plane n; mv_down fuses bilineardownsacling(mv)/2 (video_net.py:66-71)
+__device__ __forceinline__ void load_mv(const float *__restrict__ mv, int mv_share, int mv_down, int mv_h, int mv_w, int n,
+                                        int y, int x, float sign, float &fx, float &fy)
+{
+    const long long plane = (long long)mv_h * mv_w;
+    const float *b = mv + (long long)(n / mv_share) * 2 * plane; // mv_share consecutive planes use one field
+    if (!mv_down) {
+        fx = sign * __ldg(b + (long long)y * mv_w + x);
+        fy = sign * __ldg(b + plane + (long long)y * mv_w + x);
+    } else {
+        const float *a = b + (long long)(2 * y) * mv_w + 2 * x;
+        float2 r0 = __ldg(reinterpret_cast<const float2 *>(a));
+        float2 r1 = __ldg(reinterpret_cast<const float2 *>(a + mv_w));
+        fx = sign * ((((r0.x * 0.25f + r0.y * 0.25f) + r1.x * 0.25f) + r1.y * 0.25f) / 2.0f);
+        a += plane;
+        r0 = __ldg(reinterpret_cast<const float2 *>(a));
+        r1 = __ldg(reinterpret_cast<const float2 *>(a + mv_w));
+        fy = sign * ((((r0.x * 0.25f + r0.y * 0.25f) + r1.x * 0.25f) + r1.y * 0.25f) / 2.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 16 -> 16 channel 3x3 layer on shared-memory planes.  Each work item is CO_T output channels
+// x 4 consecutive pixels; every accumulator is one sequential fma chain in (ci, ky, kx) order.
+template <int CO_T, int IN_P, int OUT_ROWS, int OUT_STRIPS, typename Epi>
+__device__ __forceinline__ void conv16_layer(const float *__restrict__ in, const int in_plane,
+                                             const float *__restrict__ wp, const float *__restrict__ bias, Epi epi)
+{
+    constexpr int NCG = 16 / CO_T;
+    constexpr int PER_CG = OUT_ROWS * OUT_STRIPS;
+    constexpr int ITEMS = NCG * PER_CG;
+    for (int it = threadIdx.x; it < ITEMS; it += NT) {
+        const int cg = it / PER_CG;
+        const int rem = it - cg * PER_CG;
+        const int r = rem / OUT_STRIPS;
+        const int st = rem - r * OUT_STRIPS;
+        float acc[CO_T][4];
+#pragma unroll
+        for (int co = 0; co < CO_T; ++co) {
+            const float b = bias[cg * CO_T + co];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[co][p] = b;
+        }
+        const float *ip = in + r * IN_P + st * 4;
+        const float *wc = wp + cg * CO_T;
+#pragma unroll 1
+        for (int ci = 0; ci < 16; ++ci) {
+            float patch[3][6];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const float4 a = *reinterpret_cast<const float4 *>(ip + ky * IN_P);
+                const float2 b = *reinterpret_cast<const float2 *>(ip + ky * IN_P + 4);
+                patch[ky][0] = a.x; patch[ky][1] = a.y; patch[ky][2] = a.z; patch[ky][3] = a.w;
+                patch[ky][4] = b.x; patch[ky][5] = b.y;
+            }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                float wv[CO_T];
+#pragma unroll
+                for (int c4 = 0; c4 < CO_T / 4; ++c4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(wc + k * 16 + c4 * 4);
+                    wv[c4 * 4 + 0] = t.x; wv[c4 * 4 + 1] = t.y; wv[c4 * 4 + 2] = t.z; wv[c4 * 4 + 3] = t.w;
+                }
+                const int ky = k / 3, kx = k - ky * 3;
+#pragma unroll
+                for (int co = 0; co < CO_T; ++co)
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) acc[co][p] = fmaf(wv[co], patch[ky][kx + p], acc[co][p]);
+            }
+            ip += in_plane;
+            wc += 144;
+        }
+        epi(cg, r, st, acc);
+    }
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(NT, 1) lift_step_kernel(const __grid_constant__ StepD a)
+{
+    extern __shared__ __align__(16) float smem[];
+    float *sw = smem + SM_W;
+    float *ss = smem + SM_S;
+    float *stile = smem + SM_T;
+    float *a1 = smem + SM_A1;
+    float *a2 = smem + SM_A2;
+    float *a3 = a1;   // a1 is dead once conv2 has been computed
+    float *so = a2;   // a2 is dead once conv3 has been computed
+
+    const int tid = threadIdx.x;
+    const int n = blockIdx.z;
+    const int y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+    const int H = a.h, W = a.w;
+
+    // ---- phase A: weights + source tile ------------------------------------------------------
+    {
+        const float4 *g = reinterpret_cast<const float4 *>(a.pu_packed);
+        float4 *d = reinterpret_cast<float4 *>(sw);
+        for (int i = tid; i < WPACK / 4; i += NT) d[i] = __ldg(g + i);
+    }
+    const bool xfast_src = a.src.cs <= a.src.rs;
+    if (SRC == PMCTF_SRC_PLANE || SRC == PMCTF_SRC_SKIP3) {
+        // raw source tile (with the reference's divisions applied), zero outside the image;
+        // threads run along the axis with the smaller stride so global loads coalesce.
+        constexpr int ROWS = (SRC == PMCTF_SRC_SKIP3) ? T_ROWS : S_ROWS;
+        constexpr int ROFF = (SRC == PMCTF_SRC_SKIP3) ? 5 : 4;
+        float *dst = (SRC == PMCTF_SRC_SKIP3) ? stile : ss;
+        const float *sp = a.src.p + plane_off(a.src, a.group_n, n);
+        const bool dodiv = (a.src_div1 != 1.0f) || (a.src_div2 != 1.0f);
+        for (int i = tid; i < ROWS * S_COLS; i += NT) {
+            int r, c;
+            if (xfast_src) { r = i / S_COLS; c = i - r * S_COLS; }
+            else { c = i / ROWS; r = i - c * ROWS; }
+            const int gy = y0 - ROFF + r, gx = x0 - 4 + c;
+            float v = 0.0f;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                v = __ldg(sp + (long long)gy * a.src.rs + (long long)gx * a.src.cs);
+                if (dodiv) v = (v / a.src_div1) / a.src_div2;
+            }
+            dst[r * S_P + c] = v;
+        }
+    } else {
+        // s = warp(src, sign * mv): pMCTF_L.py:301,307 -> video_net.py:32-55
+        const float *sp = a.src.p + plane_off(a.src, a.group_n, n);
+        for (int i = tid; i < S_ROWS * S_COLS; i += NT) {
+            const int r = i / S_COLS, c = i - r * S_COLS;
+            const int gy = y0 - 4 + r, gx = x0 - 4 + c;
+            float v = 0.0f;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                float fx, fy;
+                load_mv(a.mv, a.mv_share, a.mv_down, a.mv_h, a.mv_w, n, gy, gx, a.mv_sign, fx, fy);
+                v = warp_sample(sp, a.src.rs, a.src.cs, H, W, __ldg(a.lin_x + gx), __ldg(a.lin_y + gy), fx, fy, a.sx, a.sy);
+                if (a.round_src) v = rintf(v);
+            }
+            ss[r * S_P + c] = v;
+        }
+    }
+    __syncthreads();
+    if (SRC == PMCTF_SRC_SKIP3) {
+        // skip = conv(3,1)(ReflectionPad2d((0,0,1,1))(src)) + bias: lifting_1d.py:91,105-106
+        for (int i = tid; i < S_ROWS * S_COLS; i += NT) {
+            const int r = i / S_COLS, c = i - r * S_COLS;
+            const int gy = y0 - 4 + r, gx = x0 - 4 + c;
+            float v = 0.0f;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                const int ym = (gy == 0) ? 1 : gy - 1;
+                const int yp = (gy == H - 1) ? H - 2 : gy + 1;
+                const int base = y0 - 5;
+                v = a.tap_bias;
+                v = fmaf(a.tap0, stile[(ym - base) * T_P + c], v);
+                v = fmaf(a.tap1, stile[(gy - base) * T_P + c], v);
+                v = fmaf(a.tap2, stile[(yp - base) * T_P + c], v);
+            }
+            ss[r * S_P + c] = v;
+        }
+        __syncthreads();
+    }
+
+    // ---- phase C: conv1 (1 -> 16) + tanh -> a1 -------------------------------------------------
+    {
+        const float in_mul = a.in_mul;
+        constexpr int PER = A1_ROWS * A1_COLS;
+        for (int it = tid; it < 4 * PER; it += NT) {
+            const int cq = it / PER;
+            const int rem = it - cq * PER;
+            const int r = rem / A1_COLS, c = rem - r * A1_COLS;
+            const int gy = y0 - 3 + r, gx = x0 - 3 + c;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                const float4 b = *reinterpret_cast<const float4 *>(sw + B1_OFF + cq * 4);
+                float acc0 = b.x, acc1 = b.y, acc2 = b.z, acc3 = b.w;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const int ky = k / 3, kx = k - ky * 3;
+                    const float v = ss[(r + ky) * S_P + c + kx] * in_mul;
+                    const float4 wv = *reinterpret_cast<const float4 *>(sw + W1_OFF + k * 16 + cq * 4);
+                    acc0 = fmaf(wv.x, v, acc0); acc1 = fmaf(wv.y, v, acc1);
+                    acc2 = fmaf(wv.z, v, acc2); acc3 = fmaf(wv.w, v, acc3);
+                }
+                o = make_float4(tanh_det(acc0), tanh_det(acc1), tanh_det(acc2), tanh_det(acc3));
+            }
+            float *d = a1 + (cq * 4) * (A1_ROWS * A1_P) + r * A1_P + c;
+            d[0] = o.x; d[A1_ROWS * A1_P] = o.y; d[2 * A1_ROWS * A1_P] = o.z; d[3 * A1_ROWS * A1_P] = o.w;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase D: conv2 (16 -> 16) + tanh -> a2 -------------------------------------------------
+    conv16_layer<8, A1_P, A2_ROWS, A2_COLS / 4>(a1, A1_ROWS * A1_P, sw + W2_OFF, sw + B2_OFF,
+        [&](int cg, int r, int st, float (&acc)[8][4]) {
+            const int gy = y0 - 2 + r;
+            const bool rowin = gy >= 0 && gy < H;
+#pragma unroll
+            for (int co = 0; co < 8; ++co) {
+                float v[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int gx = x0 - 2 + st * 4 + p;
+                    v[p] = (rowin && gx >= 0 && gx < W) ? tanh_det(acc[co][p]) : 0.0f;
+                }
+                *reinterpret_cast<float4 *>(a2 + (cg * 8 + co) * (A2_ROWS * A2_P) + r * A2_P + st * 4) =
+                    make_float4(v[0], v[1], v[2], v[3]);
+            }
+        });
+    __syncthreads();
+
+    // ---- phase E: conv3 (16 -> 16) + conv1 residual -> a3 ---------------------------------------
+    conv16_layer<8, A2_P, A3_ROWS, (A3_COLS + 3) / 4>(a2, A2_ROWS * A2_P, sw + W3_OFF, sw + B3_OFF,
+        [&](int cg, int r, int st, float (&acc)[8][4]) {
+            const int gy = y0 - 1 + r;
+            const bool rowin = gy >= 0 && gy < H;
+            const float in_mul = a.in_mul;
+            float v[8][4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int c = st * 4 + p;
+                const int gx = x0 - 1 + c;
+                const bool in = rowin && gx >= 0 && gx < W && c < A3_COLS;
+                // conv1 at this position, recomputed with the identical fma chain (lifting_1d.py:45)
+                float c1[8];
+#pragma unroll
+                for (int co = 0; co < 8; ++co) c1[co] = sw[B1_OFF + cg * 8 + co];
+                if (in) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        const int ky = k / 3, kx = k - ky * 3;
+                        const float sv = ss[(r + 2 + ky) * S_P + c + 2 + kx] * in_mul;
+#pragma unroll
+                        for (int co = 0; co < 8; ++co) c1[co] = fmaf(sw[W1_OFF + k * 16 + cg * 8 + co], sv, c1[co]);
+                    }
+                }
+#pragma unroll
+                for (int co = 0; co < 8; ++co) v[co][p] = in ? (c1[co] + acc[co][p]) : 0.0f;
+            }
+#pragma unroll
+            for (int co = 0; co < 8; ++co)
+                *reinterpret_cast<float4 *>(a3 + (cg * 8 + co) * (A3_ROWS * A3_P) + r * A3_P + st * 4) =
+                    make_float4(v[co][0], v[co][1], v[co][2], v[co][3]);
+        });
+    __syncthreads();
+
+    // ---- phase F: conv4 (16 -> 1) -> so ----------------------------------------------------------
+    for (int it = tid; it < TH * (TW / 2); it += NT) {
+        const int r = it / (TW / 2), st = it - r * (TW / 2);
+        float acc0 = sw[B4_OFF], acc1 = acc0;
+        const float *ip = a3 + r * A3_P + st * 2;
+        const float *wc = sw + W4_OFF;
+#pragma unroll 4
+        for (int ci = 0; ci < 16; ++ci) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(wc);
+            const float4 w1 = *reinterpret_cast<const float4 *>(wc + 4);
+            const float w8 = wc[8];
+            const float wk[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w8};
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const float2 p0 = *reinterpret_cast<const float2 *>(ip + ky * A3_P);
+                const float2 p1 = *reinterpret_cast<const float2 *>(ip + ky * A3_P + 2);
+                const float pv[4] = {p0.x, p0.y, p1.x, p1.y};
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    acc0 = fmaf(wk[ky * 3 + kx], pv[kx], acc0);
+                    acc1 = fmaf(wk[ky * 3 + kx], pv[kx + 1], acc1);
+                }
+            }
+            ip += A3_ROWS * A3_P;
+            wc += 12;
+        }
+        so[r * O_P + st * 2] = acc0;
+        so[r * O_P + st * 2 + 1] = acc1;
+    }
+    __syncthreads();
+
+    // ---- phase G: lifting arithmetic + stores, threads along the output's contiguous axis ---------
+    {
+        const bool xfast = a.out.cs <= a.out.rs;
+        const long long o_off = plane_off(a.out, a.group_n, n);
+        const long long b_off = a.base.p ? plane_off(a.base, a.group_n, n) : 0;
+        const long long p_off = a.pred.p ? plane_off(a.pred, a.group_n, n) : 0;
+        const long long x_off = a.aux.p ? plane_off(a.aux, a.group_n, n) : 0;
+        const float bd1 = (n >= a.group_n) ? a.base_div1_g1 : a.base_div1;
+        const bool bdiv = (bd1 != 1.0f) || (a.base_div2 != 1.0f);
+        for (int i = tid; i < TH * TW; i += NT) {
+            int r, c;
+            if (xfast) { r = i / TW; c = i - r * TW; }
+            else { c = i / TH; r = i - c * TH; }
+            const int gy = y0 + r, gx = x0 + c;
+            if (gy >= H || gx >= W) continue;
+            const float pu = so[r * O_P + c];
+            float res;
+            if (a.mode == PMCTF_MODE_PU) {
+                res = pu;
+            } else {
+                const float s = ss[(r + 4) * S_P + c + 4];
+                const float t = pu * a.post_mul;
+                float tmp = s + t * 0.1f;
+                if (a.round_tmp) tmp = rintf(tmp);
+                const float rr = tmp * a.out_mul;
+                if (a.pred.p) a.pred.p[p_off + (long long)gy * a.pred.rs + (long long)gx * a.pred.cs] = rr;
+                if (a.mode == PMCTF_MODE_FILTER) {
+                    res = rr;
+                } else {
+                    float b = __ldg(a.base.p + b_off + (long long)gy * a.base.rs + (long long)gx * a.base.cs);
+                    if (bdiv) b = (b / bd1) / a.base_div2;
+                    res = (a.sign > 0.0f) ? b + rr : b - rr;
+                    res = res * a.final_mul;
+                }
+            }
+            a.out.p[o_off + (long long)gy * a.out.rs + (long long)gx * a.out.cs] = res;
+            if (a.aux.p) {
+                const float raw = (SRC == PMCTF_SRC_SKIP3) ? stile[(r + 5) * T_P + c + 4] : ss[(r + 4) * S_P + c + 4];
+                a.aux.p[x_off + (long long)gy * a.aux.rs + (long long)gx * a.aux.cs] = raw * a.aux_mul;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// flow_warp (video_net.py:32-55): one thread per output pixel, all C channels
+__global__ void __launch_bounds__(256) flow_warp_kernel(const float *__restrict__ im, const float *__restrict__ flow,
+                                                        const float *__restrict__ lin_x, const float *__restrict__ lin_y,
+                                                        float *__restrict__ out, int N, int C, int H, int W, int flowN,
+                                                        float sign, float sx, float sy, int round_out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int n = blockIdx.z;
+    if (x >= W) return;
+    float fx, fy;
+    load_mv(flow, N / flowN, 0, H, W, n, y, x, sign, fx, fy);
+    const float lx = __ldg(lin_x + x), ly = __ldg(lin_y + y);
+    for (int c = 0; c < C; ++c) {
+        const float *p = im + ((long long)n * C + c) * H * W;
+        float v = warp_sample(p, W, 1, H, W, lx, ly, fx, fy, sx, sy);
+        if (round_out) v = rintf(v);
+        out[((long long)n * C + c) * H * W + (long long)y * W + x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) chroma_mv_down_kernel(const float *__restrict__ mv, float *__restrict__ out,
+                                                             int planes, int H, int W)
+{
+    const int w2 = W / 2, h2 = H / 2;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, p = blockIdx.z;
+    if (x >= w2 || p >= planes) return;
+    const float *a = mv + (long long)p * H * W + (long long)(2 * y) * W + 2 * x;
+    const float2 r0 = __ldg(reinterpret_cast<const float2 *>(a));
+    const float2 r1 = __ldg(reinterpret_cast<const float2 *>(a + W));
+    const float v = ((r0.x * 0.25f + r0.y * 0.25f) + r1.x * 0.25f) + r1.y * 0.25f;
+    out[(long long)p * h2 * w2 + (long long)y * w2 + x] = v / 2.0f;
+}
+
+__global__ void __launch_bounds__(256) quantize_kernel(const float *__restrict__ s, float q, float clip, int lossy,
+                                                       int do_round, float *__restrict__ out, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = lossy ? s[i] * q : s[i];
+        v = fminf(fmaxf(v, -clip), clip);
+        if (do_round) v = rintf(v);
+        out[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) dequantize_kernel(const float *__restrict__ s, float q, int lossy,
+                                                         float *__restrict__ out, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = lossy ? s[i] / q : s[i];
+}
+
+__global__ void pack_pu_kernel(const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                               const float *b3, const float *w4, const float *b4, float *packed)
+{
+    for (int i = threadIdx.x; i < WPACK; i += blockDim.x) {
+        float v = 0.0f;
+        if (i < B1_OFF) { const int k = i / 16, co = i % 16; v = w1[co * 9 + k]; }
+        else if (i < W2_OFF) v = b1[i - B1_OFF];
+        else if (i < B2_OFF) { const int j = i - W2_OFF; const int ci = j / 144, k = (j % 144) / 16, co = j % 16; v = w2[(co * 16 + ci) * 9 + k]; }
+        else if (i < W3_OFF) v = b2[i - B2_OFF];
+        else if (i < B3_OFF) { const int j = i - W3_OFF; const int ci = j / 144, k = (j % 144) / 16, co = j % 16; v = w3[(co * 16 + ci) * 9 + k]; }
+        else if (i < W4_OFF) v = b3[i - B3_OFF];
+        else if (i < B4_OFF) { const int j = i - W4_OFF; const int ci = j / 12, k = j % 12; v = (k < 9) ? w4[ci * 9 + k] : 0.0f; }
+        else if (i == B4_OFF) v = b4[0];
+        packed[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+static PlaneD to_dev(const pmctf_plane_t &p, long long gs)
+{
+    PlaneD d;
+    d.p = p.p; d.gs = gs; d.bs = p.bs; d.rs = p.rs; d.cs = p.cs;
+    return d;
+}
+
+static int launch_step(const StepD &d, int src_kind, cudaStream_t st)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e;
+        e = cudaFuncSetAttribute(lift_step_kernel<PMCTF_SRC_PLANE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(lift_step_kernel<PMCTF_SRC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(lift_step_kernel<PMCTF_SRC_SKIP3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    dim3 grid((d.w + TW - 1) / TW, (d.h + TH - 1) / TH, d.n);
+    if (grid.y > 65535 || grid.z > 65535) return PMCTF_ESHAPE;
+    switch (src_kind) {
+    case PMCTF_SRC_PLANE: lift_step_kernel<PMCTF_SRC_PLANE><<<grid, NT, SMEM_BYTES, st>>>(d); break;
+    case PMCTF_SRC_WARP: lift_step_kernel<PMCTF_SRC_WARP><<<grid, NT, SMEM_BYTES, st>>>(d); break;
+    case PMCTF_SRC_SKIP3: lift_step_kernel<PMCTF_SRC_SKIP3><<<grid, NT, SMEM_BYTES, st>>>(d); break;
+    default: return PMCTF_EINVAL;
+    }
+    return (int)cudaGetLastError();
+}
+
+// validated conversion of the public step descriptor (group strides are an internal extension
+// used by the 2-D transform to batch the two column passes)
+static int run_step(const pmctf_step_t &s, int group_n, long long gs_src, long long gs_base, long long gs_out,
+                    long long gs_pred, long long gs_aux, cudaStream_t st, float base_div1_g1 = -1.0f)
+{
+    if (s.n <= 0 || s.h <= 0 || s.w <= 0 || !s.pu_packed || !s.out.p || !s.src.p) return PMCTF_EINVAL;
+    if (s.mode < 0 || s.mode > 2) return PMCTF_EINVAL;
+    if (s.mode == PMCTF_MODE_ACCUM && !s.base.p) return PMCTF_EINVAL;
+    if (s.src_kind == PMCTF_SRC_SKIP3 && s.h < 2) return PMCTF_ESHAPE; // reflection needs two rows
+    if (s.src_kind == PMCTF_SRC_WARP) {
+        if (!s.mv || !s.lin_x || !s.lin_y) return PMCTF_EINVAL;
+        if (s.mv_n < 1 || s.n % s.mv_n) return PMCTF_ESHAPE;
+        if (s.h < 2 || s.w < 2) return PMCTF_ESHAPE;
+        if (s.aux.p) return PMCTF_EINVAL;
+    }
+    StepD d;
+    d.n = s.n; d.group_n = group_n; d.h = s.h; d.w = s.w; d.mode = s.mode;
+    d.src = to_dev(s.src, gs_src); d.src_div1 = s.src_div1; d.src_div2 = s.src_div2;
+    d.mv = s.mv; d.mv_share = s.mv_n > 0 ? s.n / s.mv_n : 1; d.mv_down = s.mv_down;
+    d.mv_h = s.mv_down ? 2 * s.h : s.h; d.mv_w = s.mv_down ? 2 * s.w : s.w;
+    d.mv_sign = s.mv_sign;
+    d.sx = (float)(((double)s.w - 1.0) / 2.0); d.sy = (float)(((double)s.h - 1.0) / 2.0);
+    d.lin_x = s.lin_x; d.lin_y = s.lin_y; d.round_src = s.round_src;
+    d.tap0 = s.tap0; d.tap1 = s.tap1; d.tap2 = s.tap2; d.tap_bias = s.tap_bias;
+    d.pu_packed = s.pu_packed; d.in_mul = s.in_mul; d.post_mul = s.post_mul; d.out_mul = s.out_mul;
+    d.round_tmp = s.round_tmp;
+    d.base = to_dev(s.base, gs_base); d.base_div1 = s.base_div1; d.base_div2 = s.base_div2;
+    d.base_div1_g1 = base_div1_g1 > 0.0f ? base_div1_g1 : s.base_div1;
+    d.sign = s.sign; d.final_mul = s.final_mul;
+    d.out = to_dev(s.out, gs_out); d.pred = to_dev(s.pred, gs_pred); d.aux = to_dev(s.aux, gs_aux);
+    d.aux_mul = s.aux_mul;
+    return launch_step(d, s.src_kind, st);
+}
+
+static pmctf_plane_t dense(const float *p, int H, int W)
+{
+    pmctf_plane_t pl;
+    pl.p = const_cast<float *>(p); pl.bs = (long long)H * W; pl.rs = W; pl.cs = 1;
+    return pl;
+}
+
+static pmctf_step_t blank_step(int n, int h, int w)
+{
+    pmctf_step_t s = {};
+    s.n = n; s.h = h; s.w = w;
+    s.src_div1 = s.src_div2 = s.base_div1 = s.base_div2 = 1.0f;
+    s.in_mul = s.post_mul = s.out_mul = s.final_mul = s.aux_mul = 1.0f;
+    s.sign = 1.0f; s.mv_sign = 1.0f;
+    return s;
+}
+
+} // namespace pmctf
+
+using namespace pmctf;
+
+// ==========================================================================================
+extern "C" {
+
+int pmctf_abi_version(void) { return PMCTF_ABI_VERSION; }
+
+const char *pmctf_error_string(int code)
+{
+    switch (code) {
+    case 0: return "success";
+    case PMCTF_EINVAL: return "pmctf: invalid argument (null pointer, non-positive size or bad flag)";
+    case PMCTF_ESHAPE: return "pmctf: unsupported shape";
+    case PMCTF_EWORKSPACE: return "pmctf: workspace too small";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "pmctf: unknown error";
+    }
+}
+
+int pmctf_pack_pu_weights(const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                          const float *b3, const float *w4, const float *b4, float *packed, void *stream)
+{
+    if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !w4 || !b4 || !packed) return PMCTF_EINVAL;
+    pack_pu_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(w1, b1, w2, b2, w3, b3, w4, b4, packed);
+    return (int)cudaGetLastError();
+}
+
+int pmctf_flow_warp(const float *im, const float *flow, const float *lin_x, const float *lin_y, float *out, int N,
+                    int C, int H, int W, int flowN, float sign, int round_out, void *stream)
+{
+    if (!im || !flow || !lin_x || !lin_y || !out || N <= 0 || C <= 0) return PMCTF_EINVAL;
+    if (H < 2 || W < 2 || flowN < 1 || (N % flowN) || H > 65535 || N > 65535) return PMCTF_ESHAPE;
+    dim3 grid((W + 255) / 256, H, N);
+    flow_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(im, flow, lin_x, lin_y, out, N, C, H, W, flowN, sign,
+                                                            (float)(((double)W - 1.0) / 2.0),
+                                                            (float)(((double)H - 1.0) / 2.0), round_out);
+    return (int)cudaGetLastError();
+}
+
+int pmctf_chroma_mv_down(const float *mv, float *out, int N, int H, int W, void *stream)
+{
+    if (!mv || !out || N <= 0) return PMCTF_EINVAL;
+    if (H < 2 || W < 2 || (H & 1) || (W & 1) || H / 2 > 65535 || 2 * N > 65535) return PMCTF_ESHAPE;
+    dim3 grid((W / 2 + 255) / 256, H / 2, 2 * N);
+    chroma_mv_down_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mv, out, 2 * N, H, W);
+    return (int)cudaGetLastError();
+}
+
+int pmctf_lift_step(const pmctf_step_t *step, void *stream)
+{
+    if (!step) return PMCTF_EINVAL;
+    return run_step(*step, step->n, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+int pmctf_predict_update(const float *x, const float *pu_packed, float in_mul, float *out, int N, int H, int W,
+                         void *stream)
+{
+    if (!x || !out || !pu_packed) return PMCTF_EINVAL;
+    pmctf_step_t s = blank_step(N, H, W);
+    s.src_kind = PMCTF_SRC_PLANE; s.mode = PMCTF_MODE_PU;
+    s.src = dense(x, H, W); s.out = dense(out, H, W);
+    s.pu_packed = pu_packed; s.in_mul = in_mul;
+    return run_step(s, N, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+int pmctf_temporal_filter(const float *x, const pmctf_temporal_t *t, int which, float *out, int N, int H, int W,
+                          void *stream)
+{
+    if (!x || !out || !t || (which != 0 && which != 1)) return PMCTF_EINVAL;
+    pmctf_step_t s = blank_step(N, H, W);
+    s.src_kind = PMCTF_SRC_PLANE; s.mode = PMCTF_MODE_FILTER;
+    s.src = dense(x, H, W); s.out = dense(out, H, W);
+    s.pu_packed = which == 0 ? t->P_t_packed : t->U_t_packed;
+    s.out_mul = t->lossy ? (which == 0 ? t->scale_p : t->scale_u) : 1.0f;
+    s.round_tmp = !t->lossy;
+    return run_step(s, N, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+static pmctf_step_t mctf_step(const float *src, const float *base, float *out, float *pred, const float *mv, int mv_n,
+                              int mv_down, float mv_sign, const float *lin_x, const float *lin_y, const float *packed,
+                              float out_mul, float sign, int lossy, int N, int H, int W)
+{
+    pmctf_step_t s = blank_step(N, H, W);
+    s.src_kind = PMCTF_SRC_WARP; s.mode = PMCTF_MODE_ACCUM;
+    s.src = dense(src, H, W); s.base = dense(base, H, W); s.out = dense(out, H, W);
+    if (pred) s.pred = dense(pred, H, W);
+    s.mv = mv; s.mv_n = mv_n; s.mv_down = mv_down; s.mv_sign = mv_sign; s.lin_x = lin_x; s.lin_y = lin_y;
+    s.round_src = !lossy; s.round_tmp = !lossy;
+    s.pu_packed = packed; s.out_mul = lossy ? out_mul : 1.0f; s.sign = sign;
+    return s;
+}
+
+int pmctf_forward_mctf(const float *ref, const float *cur, const float *mv, int mv_n, int mv_down, const float *lin_x,
+                       const float *lin_y, const pmctf_temporal_t *t, float *L, float *Hh, float *pred, float *inv,
+                       int N, int H, int W, void *stream)
+{
+    if (!ref || !cur || !mv || !t || !L || !Hh) return PMCTF_EINVAL;
+    // H_t = cur - predict(warp(ref, mv))                 pMCTF_L.py:301-305
+    pmctf_step_t s1 = mctf_step(ref, cur, Hh, pred, mv, mv_n, mv_down, 1.0f, lin_x, lin_y, t->P_t_packed, t->scale_p,
+                                -1.0f, t->lossy, N, H, W);
+    int e = run_step(s1, N, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+    if (e) return e;
+    // L_t = ref + update(warp(H_t, -mv))                 pMCTF_L.py:307-311
+    pmctf_step_t s2 = mctf_step(Hh, ref, L, inv, mv, mv_n, mv_down, -1.0f, lin_x, lin_y, t->U_t_packed, t->scale_u,
+                                1.0f, t->lossy, N, H, W);
+    return run_step(s2, N, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+int pmctf_inverse_mctf(const float *L, const float *Hh, const float *mv, int mv_n, int mv_down, const float *lin_x,
+                       const float *lin_y, const pmctf_temporal_t *t, float *ref, float *cur, int N, int H, int W,
+                       void *stream)
+{
+    if (!L || !Hh || !mv || !t || !ref || !cur) return PMCTF_EINVAL;
+    // ref = L - update(warp(H, -mv))                     pMCTF_L.py:320-324
+    pmctf_step_t s1 = mctf_step(Hh, L, ref, nullptr, mv, mv_n, mv_down, -1.0f, lin_x, lin_y, t->U_t_packed, t->scale_u,
+                                -1.0f, t->lossy, N, H, W);
+    int e = run_step(s1, N, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+    if (e) return e;
+    // cur = H + predict(warp(ref, mv))                   pMCTF_L.py:325-329
+    pmctf_step_t s2 = mctf_step(ref, Hh, cur, nullptr, mv, mv_n, mv_down, 1.0f, lin_x, lin_y, t->P_t_packed, t->scale_p,
+                                1.0f, t->lossy, N, H, W);
+    return run_step(s2, N, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+// one spatial lifting step on logical planes: dst = (base/bd + sign*(skip + 0.1*256*PU(skip/256))) * fm
+static int spatial_step(const pmctf_iwave_t *p, int which, const pmctf_plane_t &src, float sd1, float sd2,
+                        const pmctf_plane_t &base, float bd1, float bd2, const pmctf_plane_t &out, float sign,
+                        float final_mul, const pmctf_plane_t *aux, float aux_mul, int n, int group_n, int h, int w,
+                        long long gs_src, long long gs_base, long long gs_out, long long gs_aux, cudaStream_t st,
+                        float bd1_g1 = -1.0f)
+{
+    pmctf_step_t s = blank_step(n, h, w);
+    s.src_kind = PMCTF_SRC_SKIP3; s.mode = PMCTF_MODE_ACCUM;
+    s.src = src; s.src_div1 = sd1; s.src_div2 = sd2;
+    s.tap0 = p->tap[which][0]; s.tap1 = p->tap[which][1]; s.tap2 = p->tap[which][2]; s.tap_bias = p->bias[which];
+    s.pu_packed = p->pu_packed + (long long)which * PMCTF_PU_PACKED_FLOATS;
+    s.in_mul = 1.0f / p->dynamic_range; // exact: dynamic_range is a power of two (lifting_1d.py:62,108)
+    s.post_mul = p->dynamic_range;
+    s.round_tmp = !p->lossy;
+    s.base = base; s.base_div1 = bd1; s.base_div2 = bd2; s.sign = sign; s.final_mul = final_mul;
+    s.out = out;
+    if (aux) { s.aux = *aux; s.aux_mul = aux_mul; }
+    return run_step(s, group_n, gs_src, gs_base, gs_out, 0, gs_aux, st, bd1_g1);
+}
+
+static pmctf_plane_t phase(const pmctf_plane_t &x, int odd)
+{ // split: lifting_1d.py:10-13
+    pmctf_plane_t p = x;
+    p.p = x.p + (odd ? x.rs : 0);
+    p.rs = 2 * x.rs;
+    return p;
+}
+
+// forward_lift with explicit group strides (gs_* = element offset between the two plane groups)
+static int iwave_forward(const pmctf_plane_t &x, long long gs_x, const pmctf_iwave_t *p, const pmctf_plane_t &l,
+                         long long gs_l, const pmctf_plane_t &hh, long long gs_h, float *ws, int n, int group_n, int h2,
+                         int w, cudaStream_t st)
+{
+    if ((float)(int)p->dynamic_range != p->dynamic_range || ((int)p->dynamic_range & ((int)p->dynamic_range - 1)))
+        return PMCTF_EINVAL;
+    pmctf_plane_t xe = phase(x, 0), xo = phase(x, 1);
+    pmctf_plane_t hu; // unscaled h, workspace [n, h2, w] dense
+    hu.p = ws; hu.bs = (long long)h2 * w; hu.rs = w; hu.cs = 1;
+    const long long gs_hu = (long long)group_n * hu.bs;
+    const float sl = p->lossy ? p->scale_l : 1.0f, sh = p->lossy ? p->scale_h : 1.0f;
+    int e;
+    // P1: x_o += f(x_e)   lifting_1d.py:104-112
+    e = spatial_step(p, 0, xe, 1, 1, xo, 1, 1, hu, +1, 1.0f, nullptr, 1, n, group_n, h2, w, gs_x, gs_x, gs_hu, 0, st);
+    if (e) return e;
+    // U1: x_e += f(x_o)   :114-122
+    e = spatial_step(p, 1, hu, 1, 1, xe, 1, 1, l, +1, 1.0f, nullptr, 1, n, group_n, h2, w, gs_hu, gs_x, gs_l, 0, st);
+    if (e) return e;
+    // P2                  :124-132
+    e = spatial_step(p, 2, l, 1, 1, hu, 1, 1, hu, +1, 1.0f, nullptr, 1, n, group_n, h2, w, gs_l, gs_hu, gs_hu, 0, st);
+    if (e) return e;
+    // U2 + scaling        :134-143   (l *= scale_l in the epilogue, h * scale_h copied through)
+    return spatial_step(p, 3, hu, 1, 1, l, 1, 1, l, +1, sl, &hh, sh, n, group_n, h2, w, gs_hu, gs_l, gs_l, gs_h, st);
+}
+
+static int iwave_backward(const pmctf_plane_t &l, long long gs_l, float l_div, float l_div_g1, const pmctf_plane_t &hh,
+                          long long gs_h, float h_div, const pmctf_iwave_t *p, const pmctf_plane_t &x, long long gs_x, float *ws, int n,
+                          int group_n, int h2, int w, cudaStream_t st)
+{
+    pmctf_plane_t xe = phase(x, 0), xo = phase(x, 1);
+    pmctf_plane_t lw, hw;
+    lw.p = ws; lw.bs = (long long)h2 * w; lw.rs = w; lw.cs = 1;
+    hw = lw; hw.p = ws + (long long)n * lw.bs;
+    const long long gs_w = (long long)group_n * lw.bs;
+    const float sl = p->lossy ? p->scale_l : 1.0f, sh = p->lossy ? p->scale_h : 1.0f;
+    int e;
+    // l = l/scale_l - f(h/scale_h)      lifting_1d.py:148-159   (l_div/h_div: fused dequantise, pWave.py:191-202)
+    e = spatial_step(p, 3, hh, h_div, sh, l, l_div, sl, lw, -1, 1.0f, &hw, 1.0f, n, group_n, h2, w, gs_h, gs_l, gs_w, gs_w, st,
+                     l_div_g1);
+    if (e) return e;
+    e = spatial_step(p, 2, lw, 1, 1, hw, 1, 1, hw, -1, 1.0f, nullptr, 1, n, group_n, h2, w, gs_w, gs_w, gs_w, 0, st); // :161-168
+    if (e) return e;
+    e = spatial_step(p, 1, hw, 1, 1, lw, 1, 1, lw, -1, 1.0f, nullptr, 1, n, group_n, h2, w, gs_w, gs_w, gs_w, 0, st); // :170-177
+    if (e) return e;
+    // P1 + merge (:179-189, :16-22): odd rows = h - f(l), even rows = l copied through
+    return spatial_step(p, 0, lw, 1, 1, hw, 1, 1, xo, -1, 1.0f, &xe, 1.0f, n, group_n, h2, w, gs_w, gs_w, gs_x, gs_x, st);
+}
+
+int pmctf_iwave1d_forward(const pmctf_plane_t *x, const pmctf_iwave_t *p, const pmctf_plane_t *l, const pmctf_plane_t *h,
+                          int n, int h2, int w, float *workspace, long long workspace_floats, void *stream)
+{
+    if (!x || !p || !l || !h || !x->p || !l->p || !h->p || !p->pu_packed || !workspace || n <= 0) return PMCTF_EINVAL;
+    if (h2 < 2 || w < 1) return PMCTF_ESHAPE;
+    if (workspace_floats < (long long)n * h2 * w) return PMCTF_EWORKSPACE;
+    return iwave_forward(*x, 0, p, *l, 0, *h, 0, workspace, n, n, h2, w, (cudaStream_t)stream);
+}
+
+int pmctf_iwave1d_backward(const pmctf_plane_t *l, const pmctf_plane_t *h, const pmctf_iwave_t *p, const pmctf_plane_t *x,
+                           int n, int h2, int w, float *workspace, long long workspace_floats, void *stream)
+{
+    if (!x || !p || !l || !h || !x->p || !l->p || !h->p || !p->pu_packed || !workspace || n <= 0) return PMCTF_EINVAL;
+    if (h2 < 2 || w < 1) return PMCTF_ESHAPE;
+    if (workspace_floats < 2LL * n * h2 * w) return PMCTF_EWORKSPACE;
+    return iwave_backward(*l, 0, 1.0f, 1.0f, *h, 0, 1.0f, p, *x, 0, workspace, n, n, h2, w, (cudaStream_t)stream);
+}
+
+long long pmctf_lift2d_workspace(int N, int H, int W) { return 2LL * N * H * W; }
+
+// transposed logical view of a dense [n, rows, cols] buffer: logical (y', x') = physical (x', y')
+static pmctf_plane_t transposed(float *p, int rows, int cols)
+{
+    pmctf_plane_t t;
+    t.p = p; t.bs = (long long)rows * cols; t.rs = 1; t.cs = cols;
+    return t;
+}
+
+int pmctf_lift2d_forward(const float *x, const pmctf_iwave_t *p, float *ll, float *lh, float *hl, float *hh, float *l_out,
+                         float *h_out, int N, int H, int W, float *workspace, long long workspace_floats, void *stream)
+{
+    if (!x || !p || !ll || !lh || !hl || !hh || !workspace || !p->pu_packed || N <= 0) return PMCTF_EINVAL;
+    if ((H & 1) || (W & 1) || H < 4 || W < 4) return PMCTF_ESHAPE;
+    if (workspace_floats < pmctf_lift2d_workspace(N, H, W)) return PMCTF_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int h2 = H / 2, w2 = W / 2;
+    const long long half = (long long)N * h2 * W;
+    float *ws0 = workspace, *lbuf = l_out ? l_out : workspace + half, *hbuf = h_out ? h_out : workspace + 2 * half;
+    float *ws1 = workspace + 3 * half;
+    // rows: wavelet_transform.py:29
+    pmctf_plane_t xin = dense(x, H, W);
+    int e = iwave_forward(xin, 0, p, dense(lbuf, h2, W), 0, dense(hbuf, h2, W), 0, ws0, N, N, h2, W, st);
+    if (e) return e;
+    // columns of l and of h in one batch of 2N logical planes [W, h2] (transposed views, :32-40):
+    // group 0 = l -> (ll, lh), group 1 = h -> (hl, hh)
+    pmctf_plane_t xt = transposed(lbuf, h2, W);
+    pmctf_plane_t lo = transposed(ll, h2, w2), ho = transposed(lh, h2, w2);
+    return iwave_forward(xt, hbuf - lbuf, p, lo, hl - ll, ho, hh - lh, ws1, 2 * N, N, w2, h2, st);
+}
+
+int pmctf_lift2d_backward_q(const float *ll, const float *lh, const float *hl, const float *hh, float ll_div, float q,
+                            const pmctf_iwave_t *p, float *x, int N, int H, int W, float *workspace,
+                            long long workspace_floats, void *stream)
+{
+    if (!x || !p || !ll || !lh || !hl || !hh || !workspace || !p->pu_packed || N <= 0) return PMCTF_EINVAL;
+    if (!(ll_div > 0.0f) || !(q > 0.0f)) return PMCTF_EINVAL;
+    if ((H & 1) || (W & 1) || H < 4 || W < 4) return PMCTF_ESHAPE;
+    if (workspace_floats < pmctf_lift2d_workspace(N, H, W)) return PMCTF_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int h2 = H / 2, w2 = W / 2;
+    const long long half = (long long)N * h2 * W;
+    float *lbuf = workspace, *hbuf = workspace + half, *ws = workspace + 2 * half;
+    // columns (wavelet_transform.py:46-54) as ONE batch of 2N transposed logical planes:
+    // group 0 = (ll, lh) -> l, group 1 = (hl, hh) -> h.  The fused dequantise (pWave.py:191-202)
+    // divides ll by ll_div and the three detail bands by q.
+    pmctf_plane_t li = transposed(const_cast<float *>(ll), h2, w2), hi = transposed(const_cast<float *>(lh), h2, w2);
+    pmctf_plane_t xt = transposed(lbuf, h2, W);
+    int e = iwave_backward(li, hl - ll, ll_div, q, hi, hh - lh, q, p, xt, hbuf - lbuf, ws, 2 * N, N, w2, h2, st);
+    if (e) return e;
+    // rows (:56)
+    return iwave_backward(dense(lbuf, h2, W), 0, 1.0f, 1.0f, dense(hbuf, h2, W), 0, 1.0f, p, dense(x, H, W), 0, ws, N, N,
+                          h2, W, st);
+}
+
+int pmctf_lift2d_backward(const float *ll, const float *lh, const float *hl, const float *hh, const pmctf_iwave_t *p,
+                          float *x, int N, int H, int W, float *workspace, long long workspace_floats, void *stream)
+{
+    return pmctf_lift2d_backward_q(ll, lh, hl, hh, 1.0f, 1.0f, p, x, N, H, W, workspace, workspace_floats, stream);
+}
+
+int pmctf_quantize(const float *s, float q, float clip, int lossy, int do_round, float *out, long long n, void *stream)
+{
+    if (!s || !out || n < 0) return PMCTF_EINVAL;
+    if (n == 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    quantize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s, q, clip, lossy, do_round, out, n);
+    return (int)cudaGetLastError();
+}
+
+int pmctf_dequantize(const float *s_hat, float q, int lossy, float *out, long long n, void *stream)
+{
+    if (!s_hat || !out || n < 0) return PMCTF_EINVAL;
+    if (n == 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    dequantize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s_hat, q, lossy, out, n);
+    return (int)cudaGetLastError();
+}
+
+} // extern "C"

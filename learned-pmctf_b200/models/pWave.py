@@ -1,0 +1,189 @@
+"""pWave++ analysis / synthesis transform and quantisation on the B200 kernels
+(reference: pMCTF/models/pWave.py:26-349, hot-path part only).
+
+What is here: the 4-level lifting transform (encode / decode), quantise / dequantise, the
+q_index -> step interpolation, and the reference's own "transform only" loop
+spatial_wavelet_dec.  What is NOT here (out of scope for this tier): the
+context / entropy models, the rANS coder and the PostProcess net.  `accelerate()` in
+models/video/pMCTF_L.py grafts these methods onto an instance of the reference class, which keeps
+all of those in stock torch.
+
+state_dict keys are the reference's: wavelet_transform.{lift_h,lift_v}.*, QP, QP_ll.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..layers import LiftingScheme2D
+
+BANDS = ("lh", "hl", "hh")
+
+
+class _QCache:
+    """q = exp(log q_min + (log q_max - log q_min)/20 * q_index) (pWave.py:209-225), evaluated
+    with torch on the CPU copy of the parameter so that the value is the one the reference's CPU
+    run produces, then cached as a Python float (kernel scalar argument) per parameter version."""
+
+    def __init__(self):
+        self.cache = {}
+
+    def scalar(self, param: torch.Tensor, q_index, qp_num: int) -> float:
+        key = (param.data_ptr(), param._version, q_index)
+        v = self.cache.get(key)
+        if v is None:
+            p = param.detach().to("cpu", torch.float32)
+            lo, hi = p[0:1], p[1:2]
+            step = (torch.log(hi) - torch.log(lo)) / (qp_num - 1)
+            v = float(torch.exp(torch.log(lo) + step * q_index).reshape(()))
+            if len(self.cache) > 4096:
+                self.cache.clear()
+            self.cache[key] = v
+        return v
+
+
+class pWaveTransform:
+    """Mixin with the hot-path methods; shared by the stand-alone `pWave` below and by instances of
+    the reference's own class after `accelerate()`."""
+
+    decomp_levels: int
+    lossy: bool
+    clip_value: float
+
+    # --- q handling (pWave.py:209-229) ------------------------------------------------------
+    @staticmethod
+    def get_qp_num():
+        return 21
+
+    def get_one_q_scale(self, q_scale, q_index):
+        min_q = q_scale[0:1, :, :, :]
+        max_q = q_scale[1:2, :, :, :]
+        step = (torch.log(max_q) - torch.log(min_q)) / (self.get_qp_num() - 1)
+        return torch.exp(torch.log(min_q) + step * q_index)
+
+    def get_curr_q(self, q_scale, q_index):
+        if isinstance(q_index, list):
+            return torch.cat([self.get_one_q_scale(q_scale, i) for i in q_index], dim=0)
+        return self.get_one_q_scale(q_scale, q_index)
+
+    def _q_float(self, q) -> float:
+        """Scalar value of a [1,1,1,1] step tensor (or a float)."""
+        if isinstance(q, torch.Tensor):
+            if q.numel() != 1:
+                raise NotImplementedError("per-sample q_index lists are not supported on the fused path (batch shares one step)")
+            return float(q.detach().reshape(()).to("cpu"))
+        return float(q)
+
+    # --- transform (pWave.py:139-157) ---------------------------------------------------------
+    def encode(self, x):
+        subbands, ll = {}, x
+        for lvl in range(self.decomp_levels):
+            d = self.wavelet_transform.forward_lift_2d(ll)
+            subbands[lvl] = d
+            ll = d["ll"]
+        return subbands
+
+    def encode_bands(self, x):
+        """encode() without the unused row-pass 'l'/'h' dictionary entries."""
+        subbands, ll = {}, x
+        for lvl in range(self.decomp_levels):
+            d = self.wavelet_transform.forward_lift_2d_bands(ll)
+            subbands[lvl] = d
+            ll = d["ll"]
+        return subbands
+
+    def decode(self, subbands):
+        """Like the reference, writes each reconstructed `ll` back into the caller's dict (:153-157)."""
+        y = None
+        for lvl in range(self.decomp_levels - 1, -1, -1):
+            y = self.wavelet_transform.backward_lift_2d(subbands[lvl])
+            if lvl > 0:
+                subbands[lvl - 1]["ll"] = y
+        return y
+
+    def decode_dequant(self, subbands_hat, q_scale, q_scale_ll):
+        """dequantize_subbands (pWave.py:191-202) + decode (:150-157) with the divisions fused into
+        the first loads of each inverse level."""
+        q = self._q_float(q_scale) if self.lossy else 1.0
+        qll = self._q_float(q_scale_ll) if self.lossy else 1.0
+        top = self.decomp_levels - 1
+        ll = subbands_hat[top]["ll"]
+        for lvl in range(top, -1, -1):
+            sb = dict(subbands_hat[lvl])
+            sb["ll"] = ll
+            ll = self.wavelet_transform.backward_lift_2d(sb, ll_div=qll if lvl == top else 1.0, q=q)
+        return ll
+
+    # --- quantisation (pWave.py:168-202) -------------------------------------------------------
+    def quantize_subband(self, subband, q_scale):
+        """clamp(s * q, +-clip), not rounded (pWave.py:184-189)."""
+        return ops.quantize(subband, self._q_float(q_scale), self.clip_value, self.lossy, do_round=False)
+
+    def quantize_subbands(self, subbands, q_scale, q_scale_ll):
+        """round(clamp(s * q)) for every coded band (pWave.py:168-182)."""
+        q, qll = self._q_float(q_scale), self._q_float(q_scale_ll)
+        out = {}
+        for lvl in range(self.decomp_levels - 1, -1, -1):
+            out[lvl] = {}
+            for b in (("ll",) + BANDS if lvl == self.decomp_levels - 1 else BANDS):
+                out[lvl][b] = ops.quantize(subbands[lvl][b], qll if b == "ll" else q, self.clip_value, self.lossy,
+                                           do_round=self.lossy)
+        return out
+
+    def dequantize_subbands(self, subbands_hat, q_scale, q_scale_ll):
+        q, qll = self._q_float(q_scale), self._q_float(q_scale_ll)
+        out = {}
+        for lvl in range(self.decomp_levels - 1, -1, -1):
+            out[lvl] = {b: ops.dequantize(v, qll if b == "ll" else q, self.lossy) for b, v in subbands_hat[lvl].items()}
+        return out
+
+    def dequantize_subband(self, subband, q_scale):
+        return ops.dequantize(subband, self._q_float(q_scale), self.lossy)
+
+    # --- the reference's transform-only loop (pWave.py:314-349) --------------------------------
+    def spatial_wavelet_dec(self, x, q_scale=None, q_scale_ll=None, post_process=True, return_symbols=False):
+        """encode -> round(clamp(s*q)) on every band -> dequantise -> decode [-> PostProcess].
+        `post_process` applies self.dequantModule when the instance has one (reference class)."""
+        if q_scale is None:
+            q_scale, q_scale_ll = self.QP[-1], self.QP_ll[-1]
+        y = self.encode_bands(x)
+        hat = self.quantize_subbands(y, q_scale, q_scale_ll)
+        x_hat = self.decode_dequant(hat, q_scale, q_scale_ll)
+        if post_process and self.lossy and hasattr(self, "dequantModule"):
+            x_hat = self.dequantModule(x_hat / self.dynamic_range) * self.dynamic_range
+        return (x_hat, hat) if return_symbols else x_hat
+
+
+class pWave(pWaveTransform, nn.Module):
+    """Stand-alone hot-path subset of the reference's pWave (pWave.py:26-98): same constructor,
+    same parameter names for the transform and the quantiser."""
+
+    def __init__(self, bitdepth=8, decomp_levels=4, lossy=True):
+        super().__init__()
+        self.bitdepth = 8
+        self.dynamic_range = float(2 ** bitdepth)
+        self.lossy = lossy
+        self.in_channels = 1
+        self.decomp_levels = decomp_levels
+        self.wavelet_transform = LiftingScheme2D(bitdepth=bitdepth, lossy=lossy, in_channels=1)
+        self.clip_value = 8192.0 if lossy else float(torch.iinfo(torch.int16).max)  # pWave.py:55-58
+        self.QP = nn.Parameter(torch.ones((2, 1, 1, 1), dtype=torch.float) * 1 / 16)      # pWave.py:84-85
+        self.QP_ll = nn.Parameter(torch.ones((2, 1, 1, 1), dtype=torch.float) * 1 / 16)
+        self._qc = _QCache()
+
+    def q_pair(self, q_index=None, qp_scale=None):
+        """(q, q_ll) as the reference derives them in forward/compress (pWave.py:231-238,383-392)."""
+        if q_index is None:
+            return self.QP[-1], self.QP_ll[-1]
+        q, qll = self.get_curr_q(self.QP, q_index), self.get_curr_q(self.QP_ll, q_index)
+        if qp_scale is not None:
+            q, qll = q * qp_scale, qll * qp_scale
+        return q, qll
+
+    def forward(self, x, q_index=None, qp_scale=None):
+        """Transform-only forward: returns what the reference's forward_one_channel computes up to
+        the entropy model (pWave.py:240-257, 293-296): x_hat (pre-PostProcess) and the symbols."""
+        q, qll = self.q_pair(q_index, qp_scale)
+        x_hat, hat = self.spatial_wavelet_dec(x, q, qll, post_process=False, return_symbols=True)
+        return {"x_hat": x_hat, "subbands": hat}

@@ -1,0 +1,124 @@
+"""pMCTF-L temporal lifting on the B200 kernels (reference: pMCTF/models/video/pMCTF_L.py:29-330).
+
+`pMCTF` below is the stand-alone hot-path subset (temporal_filtering, hp_q_scale, lp_coder /
+hp_coder transforms) with the reference's constructor and parameter names.  `accelerate(model)`
+grafts the same methods onto an instance of the reference's own pMCTF, so the full codec
+(test_pMCTF_flex.py) runs with motion estimation, entropy models and post-filter in stock torch
+and the lifting path on these kernels -- see INTEGRATION.md."""
+from __future__ import annotations
+
+import types
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...layers.video.video_net import bilineardownsacling, flow_warp
+from ...layers.video.wavelet_transform_temporal_mctf import TemporalLifting
+from ..pWave import pWave, pWaveTransform
+
+
+class MCTFMixin:
+    num_me_stages: int
+    lossy: bool
+
+    def motion_compensation(self, ref_frame, mv):
+        return flow_warp(ref_frame, mv)  # pMCTF_L.py:191-193
+
+    @staticmethod
+    def get_qp_num():
+        return 21
+
+    def get_one_q_scale(self, q_scale, q_index):  # pMCTF_L.py:195-200
+        min_q, max_q = q_scale[0:1], q_scale[1:2]
+        step = (torch.log(max_q) - torch.log(min_q)) / (self.get_qp_num() - 1)
+        return torch.exp(torch.log(min_q) + step * q_index)
+
+    def get_curr_q(self, q_scale, q_index):  # pMCTF_L.py:202-209
+        if isinstance(q_index, list):
+            return torch.cat([self.get_one_q_scale(q_scale, i) for i in q_index], dim=0)
+        return self.get_one_q_scale(q_scale, q_index)
+
+    def _temporal(self, stage_idx):
+        return self.temporal_filtering[min(self.num_me_stages - 1, stage_idx)].descriptor()
+
+    def forward_MCTF(self, ref_frame, cur_frame, mv_hat, stage_idx=0, mv_down=False, want_pred=True):
+        """H = cur - P(warp(ref, mv)); L = ref + U(warp(H, -mv)) -> (L_t, H_t, pred, inv)  (pMCTF_L.py:297-312).
+        Two launches: each fuses warp + PredictUpdate CNN + lifting arithmetic.  `mv_down=True`
+        takes the luma motion field and applies the chroma 2x2-mean/2 on the fly (pMCTF_L.py:401)."""
+        return ops.forward_mctf(ref_frame, cur_frame, mv_hat, self._temporal(stage_idx), mv_down, want_pred)
+
+    def inverse_MCTF(self, L_t, H_t, mv_hat, downscale=False, stage_idx=0):
+        """ref = L - U(warp(H, -mv)); cur = H + P(warp(ref, mv))  (pMCTF_L.py:314-330)."""
+        return ops.inverse_mctf(L_t, H_t, mv_hat, self._temporal(stage_idx), downscale)
+
+
+class pMCTF(MCTFMixin, nn.Module):
+    def __init__(self, bitdepth=8, decomp_levels=4, lossy=True, two_stage_me=True, num_me_stages=2, quant_stage=True,
+                 **kwargs):
+        super().__init__()
+        self.bitdepth = bitdepth
+        self.dynamic_range = 2 ** bitdepth - 1
+        self.lossy = lossy
+        self.lp_coder = pWave(bitdepth, decomp_levels, lossy)
+        self.hp_coder = pWave(bitdepth, decomp_levels, lossy)
+        self.temporal_filtering = nn.ModuleList([TemporalLifting(lossy=lossy) for _ in range(num_me_stages)])
+        self.quant_stage = quant_stage
+        if quant_stage:
+            self.hp_q_scale = nn.ParameterList([nn.Parameter(torch.ones((2, 1, 1, 1))) for _ in range(num_me_stages)])
+        self.two_stage_me = two_stage_me
+        self.num_me_stages = num_me_stages
+
+    def hp_qp_scale(self, stage_idx, q_index):
+        """Temporal-layer-adaptive step scaling (pMCTF_L.py:343-347,404-408)."""
+        if not self.quant_stage:
+            return None
+        return self.get_curr_q(self.hp_q_scale[stage_idx], q_index)
+
+    def load_reference_state_dict(self, sd):
+        """Load the hot-path entries of a full reference checkpoint (3224 keys for num_me_stages=4);
+        every key this model owns must be present."""
+        own = self.state_dict()
+        missing = [k for k in own if k not in sd]
+        if missing:
+            raise KeyError(f"reference state_dict lacks hot-path keys: {missing[:5]} ...")
+        return self.load_state_dict({k: sd[k] for k in own}, strict=True)
+
+
+_PWAVE_METHODS = ("encode", "decode", "decode_dequant", "encode_bands", "quantize_subband", "quantize_subbands",
+                  "dequantize_subbands", "dequantize_subband", "spatial_wavelet_dec", "_q_float")
+_MCTF_METHODS = ("motion_compensation", "forward_MCTF", "inverse_MCTF", "_temporal")
+
+
+def accelerate(ref_model):
+    """Graft the B200 hot path onto an instance of the REFERENCE pMCTF (pMCTF_L.py:29): its
+    TemporalLifting / LiftingScheme2D submodules are replaced by ours with the SAME parameter
+    tensors (state_dict keys and values unchanged), and the hot-path methods are rebound.  The
+    rest of the model (SpyNet, MV codec, context models, rANS, PostProcess) is untouched."""
+    from ...layers import LiftingScheme2D
+
+    def adopt(dst: nn.Module, src: nn.Module):
+        src_params = dict(src.named_parameters(remove_duplicate=False))
+        for name, _ in list(dst.named_parameters(remove_duplicate=False)):
+            mod, leaf = dst, name
+            *path, leaf = name.split(".")
+            for p in path:
+                mod = getattr(mod, p)
+            mod._parameters[leaf] = src_params[name]
+        return dst
+
+    for i, tl in enumerate(ref_model.temporal_filtering):
+        ref_model.temporal_filtering[i] = adopt(TemporalLifting(lossy=tl.lossy).to(next(tl.parameters()).device), tl)
+    for coder in (ref_model.lp_coder, ref_model.hp_coder):
+        wt = coder.wavelet_transform
+        new = LiftingScheme2D(bitdepth=coder.bitdepth, lossy=coder.lossy).to(next(wt.parameters()).device)
+        coder.wavelet_transform = adopt(new, wt)
+        for m in _PWAVE_METHODS:
+            setattr(coder, m, types.MethodType(getattr(pWaveTransform, m), coder))
+    for m in _MCTF_METHODS:
+        setattr(ref_model, m, types.MethodType(getattr(MCTFMixin, m), ref_model))
+    import sys
+    mod = sys.modules.get(type(ref_model).__module__)
+    if mod is not None:  # the model file binds these names at import (pMCTF_L.py:14)
+        mod.flow_warp, mod.bilineardownsacling = flow_warp, bilineardownsacling
+    return ref_model

@@ -1,0 +1,290 @@
+"""Tensor-level operators of the hot path.  Every function validates its arguments like the
+C ABI does, allocates outputs/workspaces with torch on the input's device, and launches on
+torch's current CUDA stream.  CUDA tensors only: there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+SCALE_L = float(np.float32(1.149604398860241))  # lifting_1d.py:57-58,98-101 (bior4.4)
+SCALE_H = float(np.float32(0.869864451624781))
+SCALE_P = float(np.float32(1 / math.sqrt(2)))   # wavelet_transform_temporal_mctf.py:24-25
+SCALE_U = 0.5
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, name: str, ndim: Optional[int] = None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: the pMCTF hot path runs on CUDA tensors only (got {getattr(t, 'device', type(t))}); "
+                           "there is no CPU fallback")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise RuntimeError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+    return t
+
+
+def _no_grad_only(*ts):
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts):
+        raise NotImplementedError("learned_pmctf_b200: backward of the fused CUDA ops is not implemented yet; "
+                                  "call under torch.no_grad() (as test_pMCTF_flex.py does)")
+
+
+# ---------------------------------------------------------------------------------------------
+_LIN_CACHE: dict = {}
+
+
+def linspace_table(n: int, device) -> torch.Tensor:
+    """torch.linspace(-1, 1, n) evaluated with the scalar formula of ATen's CUDA kernel
+    (video_net.py:36-39 runs it on the frame's device).  Cached per (n, device), like the
+    reference's backward_grid cache (video_net.py:10,33-40)."""
+    key = (n, str(device))
+    t = _LIN_CACHE.get(key)
+    if t is None:
+        step = np.float32(2.0) / np.float32(n - 1)
+        i = np.arange(n)
+        lo = np.float32(-1.0) + step * i.astype(np.float32)
+        hi = np.float32(1.0) - step * (n - i - 1).astype(np.float32)
+        t = torch.from_numpy(np.where(i < n // 2, lo, hi).astype(np.float32)).to(device)
+        _LIN_CACHE[key] = t
+    return t
+
+
+_WS_CACHE: dict = {}
+
+
+def workspace(floats: int, device, tag: str = "") -> torch.Tensor:
+    """Grow-only per-(device, stream, tag) scratch buffer; stream-ordered reuse is safe because
+    every consumer is launched on the same stream."""
+    key = (str(device), _stream(), tag)
+    t = _WS_CACHE.get(key)
+    if t is None or t.numel() < floats:
+        t = torch.empty(max(floats, 1), dtype=torch.float32, device=device)
+        _WS_CACHE[key] = t
+    return t
+
+
+def plane_of(t: torch.Tensor) -> nat.Plane:
+    """[N,1,H,W] tensor (any strides) -> strided plane descriptor."""
+    assert t.dim() == 4 and t.size(1) == 1
+    return nat.Plane(t.data_ptr(), t.stride(0), t.stride(2), t.stride(3))
+
+
+# ---------------------------------------------------------------------------------------------
+def pack_pu(params, out: torch.Tensor):
+    """params: (w1,b1,...,w4,b4) CUDA tensors in the state_dict's OIHW layout."""
+    ps = [_chk(p.detach().contiguous(), "PredictUpdate parameter") for p in params]
+    shapes = [(16, 1, 3, 3), (16,), (16, 16, 3, 3), (16,), (16, 16, 3, 3), (16,), (1, 16, 3, 3), (1,)]
+    for p, s in zip(ps, shapes):
+        if tuple(p.shape) != s:
+            raise RuntimeError(f"PredictUpdate parameter has shape {tuple(p.shape)}, expected {s} (lifting_1d.py:28-34)")
+    assert out.numel() == nat.PU_PACKED_FLOATS and out.is_contiguous()
+    nat.check(nat.lib().pmctf_pack_pu_weights(*[p.data_ptr() for p in ps], out.data_ptr(), _stream()), "pack_pu_weights")
+    return ps  # keep alive until the stream has consumed them
+
+
+def flow_warp(im: torch.Tensor, flow: torch.Tensor, sign: float = 1.0, lin_x=None, lin_y=None, round_out=False):
+    """flow_warp / torch_warp: video_net.py:32-55."""
+    _no_grad_only(im, flow)
+    im, flow = _chk(im, "im", 4).contiguous(), _chk(flow, "flow", 4).contiguous()
+    N, Cc, H, W = im.shape
+    if flow.shape[1:] != (2, H, W) or N % flow.shape[0]:
+        raise RuntimeError(f"flow shape {tuple(flow.shape)} does not match image {tuple(im.shape)}")
+    lx = linspace_table(W, im.device) if lin_x is None else _chk(lin_x, "lin_x")
+    ly = linspace_table(H, im.device) if lin_y is None else _chk(lin_y, "lin_y")
+    out = torch.empty_like(im)
+    nat.check(nat.lib().pmctf_flow_warp(im.data_ptr(), flow.data_ptr(), lx.data_ptr(), ly.data_ptr(), out.data_ptr(),
+                                        N, Cc, H, W, flow.shape[0], sign, int(round_out), _stream()), "flow_warp")
+    return out
+
+
+def chroma_mv_down(mv: torch.Tensor):
+    """bilineardownsacling(mv) / 2: video_net.py:66-71, pMCTF_L.py:317,336,401."""
+    _no_grad_only(mv)
+    mv = _chk(mv, "mv", 4).contiguous()
+    N, two, H, W = mv.shape
+    if two != 2:
+        raise RuntimeError("mv must be [N,2,H,W]")
+    out = torch.empty((N, 2, H // 2, W // 2), dtype=torch.float32, device=mv.device)
+    nat.check(nat.lib().pmctf_chroma_mv_down(mv.data_ptr(), out.data_ptr(), N, H, W, _stream()), "chroma_mv_down")
+    return out
+
+
+def predict_update(x: torch.Tensor, packed: torch.Tensor, in_mul: float = 1.0):
+    """PredictUpdate.forward: lifting_1d.py:36-49."""
+    _no_grad_only(x)
+    x = _chk(x, "x", 4).contiguous()
+    N, Cc, H, W = x.shape
+    if Cc != 1:
+        raise RuntimeError("PredictUpdate on the hot path is single-channel (in_ch=1)")
+    out = torch.empty_like(x)
+    nat.check(nat.lib().pmctf_predict_update(x.data_ptr(), packed.data_ptr(), in_mul, out.data_ptr(), N, H, W, _stream()),
+              "predict_update")
+    return out
+
+
+def temporal_filter(x: torch.Tensor, t: nat.Temporal, which: int):
+    _no_grad_only(x)
+    x = _chk(x, "x", 4).contiguous()
+    N, Cc, H, W = x.shape
+    if Cc != 1:
+        raise RuntimeError("TemporalLifting is single-channel")
+    out = torch.empty_like(x)
+    nat.check(nat.lib().pmctf_temporal_filter(x.data_ptr(), C.byref(t), which, out.data_ptr(), N, H, W, _stream()),
+              "temporal_filter")
+    return out
+
+
+def _mv_args(frame: torch.Tensor, mv: torch.Tensor, mv_down: bool):
+    N, Cc, H, W = frame.shape
+    if Cc != 1:
+        raise RuntimeError("MCTF planes are single-channel ([N,1,H,W]; chroma is batched over N, test_pMCTF_flex.py:153-164)")
+    exp = (2, 2 * H, 2 * W) if mv_down else (2, H, W)
+    if tuple(mv.shape[1:]) != exp or N % mv.shape[0]:
+        raise RuntimeError(f"mv shape {tuple(mv.shape)} does not match frame {tuple(frame.shape)} (mv_down={mv_down})")
+    return N, H, W
+
+
+def forward_mctf(ref, cur, mv, t: nat.Temporal, mv_down=False, want_pred=True, lin_x=None, lin_y=None):
+    """pMCTF.forward_MCTF: pMCTF_L.py:297-312 -> (L_t, H_t, pred, inv)."""
+    _no_grad_only(ref, cur, mv)
+    ref, cur, mv = _chk(ref, "ref", 4).contiguous(), _chk(cur, "cur", 4).contiguous(), _chk(mv, "mv", 4).contiguous()
+    if ref.shape != cur.shape:
+        raise RuntimeError("ref and cur must have the same shape")
+    N, H, W = _mv_args(ref, mv, mv_down)
+    lx = linspace_table(W, ref.device) if lin_x is None else lin_x
+    ly = linspace_table(H, ref.device) if lin_y is None else lin_y
+    L, Hh = torch.empty_like(ref), torch.empty_like(ref)
+    pred = torch.empty_like(ref) if want_pred else None
+    inv = torch.empty_like(ref) if want_pred else None
+    nat.check(nat.lib().pmctf_forward_mctf(ref.data_ptr(), cur.data_ptr(), mv.data_ptr(), mv.shape[0], int(mv_down),
+                                           lx.data_ptr(), ly.data_ptr(), C.byref(t), L.data_ptr(), Hh.data_ptr(),
+                                           pred.data_ptr() if want_pred else None, inv.data_ptr() if want_pred else None,
+                                           N, H, W, _stream()), "forward_mctf")
+    return L, Hh, pred, inv
+
+
+def inverse_mctf(L, Hh, mv, t: nat.Temporal, mv_down=False, lin_x=None, lin_y=None):
+    """pMCTF.inverse_MCTF: pMCTF_L.py:314-330 -> (ref, cur)."""
+    _no_grad_only(L, Hh, mv)
+    L, Hh, mv = _chk(L, "L_t", 4).contiguous(), _chk(Hh, "H_t", 4).contiguous(), _chk(mv, "mv", 4).contiguous()
+    if L.shape != Hh.shape:
+        raise RuntimeError("L_t and H_t must have the same shape")
+    N, H, W = _mv_args(L, mv, mv_down)
+    lx = linspace_table(W, L.device) if lin_x is None else lin_x
+    ly = linspace_table(H, L.device) if lin_y is None else lin_y
+    ref, cur = torch.empty_like(L), torch.empty_like(L)
+    nat.check(nat.lib().pmctf_inverse_mctf(L.data_ptr(), Hh.data_ptr(), mv.data_ptr(), mv.shape[0], int(mv_down),
+                                           lx.data_ptr(), ly.data_ptr(), C.byref(t), ref.data_ptr(), cur.data_ptr(),
+                                           N, H, W, _stream()), "inverse_mctf")
+    return ref, cur
+
+
+def iwave1d_forward(x: torch.Tensor, p: nat.IWave):
+    """iWave1D.forward_lift on a (possibly permuted) [N,1,H,W] view: lifting_1d.py:103-145.
+    Outputs are allocated with the same dimension order as the input's memory, so a transposed
+    input gives transposed-view outputs exactly like the reference's permute chain."""
+    _no_grad_only(x)
+    _chk(x, "x", 4)
+    N, Cc, H, W = x.shape
+    if Cc != 1 or H % 2 or H < 4:
+        raise RuntimeError(f"forward_lift needs [N,1,H,W] with even H >= 4, got {tuple(x.shape)}")
+    h2 = H // 2
+    if x.stride(3) <= x.stride(2):
+        l = torch.empty((N, 1, h2, W), dtype=torch.float32, device=x.device)
+        h = torch.empty_like(l)
+    else:  # transposed view: keep W as the slow axis in memory
+        l = torch.empty((N, 1, W, h2), dtype=torch.float32, device=x.device).permute(0, 1, 3, 2)
+        h = torch.empty((N, 1, W, h2), dtype=torch.float32, device=x.device).permute(0, 1, 3, 2)
+    ws = workspace(N * h2 * W, x.device, "iw1d")
+    px, pl, ph = plane_of(x), plane_of(l), plane_of(h)
+    nat.check(nat.lib().pmctf_iwave1d_forward(C.byref(px), C.byref(p), C.byref(pl), C.byref(ph), N, h2, W,
+                                              ws.data_ptr(), ws.numel(), _stream()), "iwave1d_forward")
+    return l, h
+
+
+def iwave1d_backward(l: torch.Tensor, h: torch.Tensor, p: nat.IWave):
+    """iWave1D.backward_lift: lifting_1d.py:147-189."""
+    _no_grad_only(l, h)
+    _chk(l, "l", 4), _chk(h, "h", 4)
+    if l.shape != h.shape or l.size(1) != 1 or l.size(2) < 2:
+        raise RuntimeError(f"backward_lift needs two [N,1,h,W] bands with h >= 2, got {tuple(l.shape)} / {tuple(h.shape)}")
+    N, _, h2, W = l.shape
+    if l.stride(3) <= l.stride(2):
+        x = torch.empty((N, 1, 2 * h2, W), dtype=torch.float32, device=l.device)
+    else:
+        x = torch.empty((N, 1, W, 2 * h2), dtype=torch.float32, device=l.device).permute(0, 1, 3, 2)
+    ws = workspace(2 * N * h2 * W, l.device, "iw1d")
+    pl, ph, px = plane_of(l), plane_of(h), plane_of(x)
+    nat.check(nat.lib().pmctf_iwave1d_backward(C.byref(pl), C.byref(ph), C.byref(p), C.byref(px), N, h2, W,
+                                               ws.data_ptr(), ws.numel(), _stream()), "iwave1d_backward")
+    return x
+
+
+def lift2d_forward(x: torch.Tensor, p: nat.IWave, want_lh_rows: bool = False):
+    """LiftingScheme2D.forward_lift_2d: wavelet_transform.py:25-43 -> dict (ll, lh, hl, hh [, l, h])."""
+    _no_grad_only(x)
+    x = _chk(x, "x", 4).contiguous()
+    N, Cc, H, W = x.shape
+    if Cc != 1 or H % 2 or W % 2 or H < 4 or W < 4:
+        raise RuntimeError(f"forward_lift_2d needs [N,1,H,W] with even H, W >= 4, got {tuple(x.shape)}")
+    bands = torch.empty((4, N, 1, H // 2, W // 2), dtype=torch.float32, device=x.device)
+    rows = torch.empty((2, N, 1, H // 2, W), dtype=torch.float32, device=x.device) if want_lh_rows else None
+    ws = workspace(2 * N * H * W, x.device, "l2d")
+    nat.check(nat.lib().pmctf_lift2d_forward(x.data_ptr(), C.byref(p), bands[0].data_ptr(), bands[1].data_ptr(),
+                                             bands[2].data_ptr(), bands[3].data_ptr(),
+                                             rows[0].data_ptr() if want_lh_rows else None,
+                                             rows[1].data_ptr() if want_lh_rows else None,
+                                             N, H, W, ws.data_ptr(), ws.numel(), _stream()), "lift2d_forward")
+    d = {"ll": bands[0], "lh": bands[1], "hl": bands[2], "hh": bands[3]}
+    if want_lh_rows:  # the reference returns the transposed views (wavelet_transform.py:32,37,42)
+        d["l"], d["h"] = rows[0].permute(0, 1, 3, 2), rows[1].permute(0, 1, 3, 2)
+    return d
+
+
+def lift2d_backward(ll, lh, hl, hh, p: nat.IWave, ll_div: float = 1.0, q: float = 1.0):
+    """LiftingScheme2D.backward_lift_2d: wavelet_transform.py:45-57, optionally with the
+    dequantise of pWave.py:191-202 fused (ll / ll_div, details / q)."""
+    _no_grad_only(ll, lh, hl, hh)
+    ts = [_chk(t, n, 4).contiguous() for t, n in ((ll, "ll"), (lh, "lh"), (hl, "hl"), (hh, "hh"))]
+    if any(t.shape != ts[0].shape for t in ts) or ts[0].size(1) != 1:
+        raise RuntimeError("backward_lift_2d needs four [N,1,h,w] subbands of equal shape")
+    N, _, h2, w2 = ts[0].shape
+    if h2 < 2 or w2 < 2:
+        raise RuntimeError("subbands must be at least 2x2 (reflection padding)")
+    H, W = 2 * h2, 2 * w2
+    x = torch.empty((N, 1, H, W), dtype=torch.float32, device=ts[0].device)
+    ws = workspace(2 * N * H * W, x.device, "l2d")
+    nat.check(nat.lib().pmctf_lift2d_backward_q(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(),
+                                                ll_div, q, C.byref(p), x.data_ptr(), N, H, W, ws.data_ptr(), ws.numel(),
+                                                _stream()), "lift2d_backward")
+    return x
+
+
+def quantize(s: torch.Tensor, q: float, clip: float = 8192.0, lossy: bool = True, do_round: bool = True):
+    """[round](clamp(s*q, +-clip)): pWave.py:184-189,256-257,337; layers.py:71-92."""
+    _no_grad_only(s)
+    s = _chk(s, "subband").contiguous()
+    out = torch.empty_like(s)
+    nat.check(nat.lib().pmctf_quantize(s.data_ptr(), q, clip, int(lossy), int(do_round), out.data_ptr(), s.numel(), _stream()),
+              "quantize")
+    return out
+
+
+def dequantize(s_hat: torch.Tensor, q: float, lossy: bool = True):
+    """s_hat / q: pWave.py:191-202."""
+    _no_grad_only(s_hat)
+    s_hat = _chk(s_hat, "subband").contiguous()
+    out = torch.empty_like(s_hat)
+    nat.check(nat.lib().pmctf_dequantize(s_hat.data_ptr(), q, int(lossy), out.data_ptr(), s_hat.numel(), _stream()), "dequantize")
+    return out
