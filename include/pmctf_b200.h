@@ -38,13 +38,17 @@ extern "C" {
 #define PMCTF_PU_PACKED_FLOATS 5000 /* size of one packed PredictUpdate weight block */
 #define PMCTF_IWAVE_PACKED_FLOATS (4 * PMCTF_PU_PACKED_FLOATS)
 
-/* A strided view of a batch of single-channel planes: element (n, y, x) lives at
- * p[n*bs + y*rs + x*cs] (strides in elements).  This is how split (lifting_1d.py:10-13),
- * merge (:16-22) and the permute(0,1,3,2) views of wavelet_transform.py:32-54 are expressed
- * without copies. */
+/* A strided view of a batch of single-channel planes (strides in elements).  Element (n, y, x)
+ * lives at p[n*bs + y*rs + x*cs] when group_n == 0, and at
+ * p[(n / group_n)*gs + (n % group_n)*bs + y*rs + x*cs] otherwise (two-level batch: e.g. the Cb/Cr
+ * planes of every second frame of a GOP).  This is how split (lifting_1d.py:10-13), merge
+ * (:16-22), the permute(0,1,3,2) views of wavelet_transform.py:32-54 and the ref/cur frame
+ * selection of the dyadic GOP schedule (test_pMCTF_flex.py:143-146) are expressed without copies. */
 typedef struct {
     float *p;
     long long bs, rs, cs;
+    long long gs;
+    int group_n;
 } pmctf_plane_t;
 
 enum { PMCTF_SRC_PLANE = 0, PMCTF_SRC_WARP = 1, PMCTF_SRC_SKIP3 = 2 };
@@ -59,7 +63,7 @@ enum { PMCTF_MODE_ACCUM = 0, PMCTF_MODE_FILTER = 1, PMCTF_MODE_PU = 2 };
  *      out = r                                                  MODE_FILTER
  *      out = t                                                  MODE_PU
  *      pred (optional) = r ; aux (optional, SKIP3/PLANE) = (src/src_div1/src_div2) * aux_mul
- * All planes are logical [n, h, w]; warp sources must be dense NCHW (rs == w, cs == 1). */
+ * All planes are logical [n, h, w] with arbitrary strides. */
 typedef struct {
     int n, h, w;
     int src_kind, mode;
@@ -131,17 +135,20 @@ int pmctf_predict_update(const float *x, const float *pu_packed, float in_mul, f
 int pmctf_temporal_filter(const float *x, const pmctf_temporal_t *t, int which, float *out,
                           int N, int H, int W, void *stream);
 
-/* pMCTF.forward_MCTF: pMCTF/models/video/pMCTF_L.py:297-312.  ref, cur, L, H dense [N,1,H,W];
- * mv [mv_n,2,H,W] (or the luma field [mv_n,2,2H,2W] with mv_down=1, fusing pMCTF_L.py:401);
- * pred / inv may be NULL (they only feed the MSE terms, pMCTF_L.py:351,373). */
-int pmctf_forward_mctf(const float *ref, const float *cur, const float *mv, int mv_n, int mv_down,
+/* pMCTF.forward_MCTF: pMCTF/models/video/pMCTF_L.py:297-312.  ref, cur, L, H: N logical planes
+ * [H, W] each (any strides); mv dense [mv_n,2,H,W] (or the luma field [mv_n,2,2H,2W] with
+ * mv_down=1, fusing pMCTF_L.py:401), N/mv_n consecutive planes share one field;
+ * pred / inv may be NULL (they only feed the MSE terms, pMCTF_L.py:351,373).
+ * L must not alias ref or cur; H may alias cur. */
+int pmctf_forward_mctf(const pmctf_plane_t *ref, const pmctf_plane_t *cur, const float *mv, int mv_n, int mv_down,
                        const float *lin_x, const float *lin_y, const pmctf_temporal_t *t,
-                       float *L, float *Hh, float *pred, float *inv, int N, int H, int W, void *stream);
+                       const pmctf_plane_t *L, const pmctf_plane_t *Hh, const pmctf_plane_t *pred,
+                       const pmctf_plane_t *inv, int N, int H, int W, void *stream);
 
 /* pMCTF.inverse_MCTF: pMCTF_L.py:314-330 (mv_down=1 == downscale=True). */
-int pmctf_inverse_mctf(const float *L, const float *Hh, const float *mv, int mv_n, int mv_down,
+int pmctf_inverse_mctf(const pmctf_plane_t *L, const pmctf_plane_t *Hh, const float *mv, int mv_n, int mv_down,
                        const float *lin_x, const float *lin_y, const pmctf_temporal_t *t,
-                       float *ref, float *cur, int N, int H, int W, void *stream);
+                       const pmctf_plane_t *ref, const pmctf_plane_t *cur, int N, int H, int W, void *stream);
 
 /* iWave1D.forward_lift / backward_lift on strided views: lifting_1d.py:103-189.
  * x is the logical [n, 2*h2, w] input; l, h are logical [n, h2, w] outputs (any strides).

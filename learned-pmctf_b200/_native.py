@@ -23,7 +23,8 @@ _fp = C.c_void_p  # device pointers travel as integers
 
 
 class Plane(C.Structure):
-    _fields_ = [("p", C.c_void_p), ("bs", C.c_longlong), ("rs", C.c_longlong), ("cs", C.c_longlong)]
+    _fields_ = [("p", C.c_void_p), ("bs", C.c_longlong), ("rs", C.c_longlong), ("cs", C.c_longlong),
+                ("gs", C.c_longlong), ("group_n", C.c_int)]
 
 
 class Step(C.Structure):
@@ -58,8 +59,10 @@ SIGNATURES = {
     "pmctf_lift_step": [C.POINTER(Step), _P],
     "pmctf_predict_update": [_P, _P, _f, _P, _I, _I, _I, _P],
     "pmctf_temporal_filter": [_P, C.POINTER(Temporal), _I, _P, _I, _I, _I, _P],
-    "pmctf_forward_mctf": [_P, _P, _P, _I, _I, _P, _P, C.POINTER(Temporal), _P, _P, _P, _P, _I, _I, _I, _P],
-    "pmctf_inverse_mctf": [_P, _P, _P, _I, _I, _P, _P, C.POINTER(Temporal), _P, _P, _I, _I, _I, _P],
+    "pmctf_forward_mctf": [C.POINTER(Plane), C.POINTER(Plane), _P, _I, _I, _P, _P, C.POINTER(Temporal),
+                           C.POINTER(Plane), C.POINTER(Plane), C.POINTER(Plane), C.POINTER(Plane), _I, _I, _I, _P],
+    "pmctf_inverse_mctf": [C.POINTER(Plane), C.POINTER(Plane), _P, _I, _I, _P, _P, C.POINTER(Temporal),
+                           C.POINTER(Plane), C.POINTER(Plane), _I, _I, _I, _P],
     "pmctf_iwave1d_forward": [C.POINTER(Plane), C.POINTER(IWave), C.POINTER(Plane), C.POINTER(Plane), _I, _I, _I, _P, _LL, _P],
     "pmctf_iwave1d_backward": [C.POINTER(Plane), C.POINTER(Plane), C.POINTER(IWave), C.POINTER(Plane), _I, _I, _I, _P, _LL, _P],
     "pmctf_lift2d_workspace": [_I, _I, _I],

@@ -81,16 +81,18 @@ __device__ __forceinline__ float tanh_det(float x)
 struct PlaneD {
     float *p;
     long long gs, bs, rs, cs;
+    int group_n; // 0: single level (n * bs)
 };
 
-__device__ __forceinline__ long long plane_off(const PlaneD &pl, int group_n, int n)
+__device__ __forceinline__ long long plane_off(const PlaneD &pl, int n)
 {
-    const int g = n / group_n;
-    return (long long)g * pl.gs + (long long)(n - g * group_n) * pl.bs;
+    if (pl.group_n <= 0) return (long long)n * pl.bs;
+    const int g = n / pl.group_n;
+    return (long long)g * pl.gs + (long long)(n - g * pl.group_n) * pl.bs;
 }
 
 struct StepD {
-    int n, group_n, h, w;
+    int n, div_group_n, h, w; // div_group_n: planes >= this index use base_div1_g1
     int mode;
     PlaneD src;
     float src_div1, src_div2;
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_kernel(const __grid_constant_
         constexpr int ROWS = (SRC == PMCTF_SRC_SKIP3) ? T_ROWS : S_ROWS;
         constexpr int ROFF = (SRC == PMCTF_SRC_SKIP3) ? 5 : 4;
         float *dst = (SRC == PMCTF_SRC_SKIP3) ? stile : ss;
-        const float *sp = a.src.p + plane_off(a.src, a.group_n, n);
+        const float *sp = a.src.p + plane_off(a.src, n);
         const bool dodiv = (a.src_div1 != 1.0f) || (a.src_div2 != 1.0f);
         for (int i = tid; i < ROWS * S_COLS; i += NT) {
             int r, c;
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_kernel(const __grid_constant_
         }
     } else {
         // s = warp(src, sign * mv): pMCTF_L.py:301,307 -> video_net.py:32-55
-        const float *sp = a.src.p + plane_off(a.src, a.group_n, n);
+        const float *sp = a.src.p + plane_off(a.src, n);
         for (int i = tid; i < S_ROWS * S_COLS; i += NT) {
             const int r = i / S_COLS, c = i - r * S_COLS;
             const int gy = y0 - 4 + r, gx = x0 - 4 + c;
@@ -411,11 +413,11 @@ __global__ void __launch_bounds__(NT, 1) lift_step_kernel(const __grid_constant_
     // ---- phase G: lifting arithmetic + stores, threads along the output's contiguous axis ---------
     {
         const bool xfast = a.out.cs <= a.out.rs;
-        const long long o_off = plane_off(a.out, a.group_n, n);
-        const long long b_off = a.base.p ? plane_off(a.base, a.group_n, n) : 0;
-        const long long p_off = a.pred.p ? plane_off(a.pred, a.group_n, n) : 0;
-        const long long x_off = a.aux.p ? plane_off(a.aux, a.group_n, n) : 0;
-        const float bd1 = (n >= a.group_n) ? a.base_div1_g1 : a.base_div1;
+        const long long o_off = plane_off(a.out, n);
+        const long long b_off = a.base.p ? plane_off(a.base, n) : 0;
+        const long long p_off = a.pred.p ? plane_off(a.pred, n) : 0;
+        const long long x_off = a.aux.p ? plane_off(a.aux, n) : 0;
+        const float bd1 = (n >= a.div_group_n) ? a.base_div1_g1 : a.base_div1;
         const bool bdiv = (bd1 != 1.0f) || (a.base_div2 != 1.0f);
         for (int i = tid; i < TH * TW; i += NT) {
             int r, c;
@@ -524,10 +526,10 @@ __global__ void pack_pu_kernel(const float *w1, const float *b1, const float *w2
 }
 
 // ------------------------------------------------------------------------------------------
-static PlaneD to_dev(const pmctf_plane_t &p, long long gs)
+static PlaneD to_dev(const pmctf_plane_t &p)
 {
     PlaneD d;
-    d.p = p.p; d.gs = gs; d.bs = p.bs; d.rs = p.rs; d.cs = p.cs;
+    d.p = p.p; d.gs = p.gs; d.bs = p.bs; d.rs = p.rs; d.cs = p.cs; d.group_n = p.group_n;
     return d;
 }
 
@@ -555,10 +557,8 @@ static int launch_step(const StepD &d, int src_kind, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
-// validated conversion of the public step descriptor (group strides are an internal extension
-// used by the 2-D transform to batch the two column passes)
-static int run_step(const pmctf_step_t &s, int group_n, long long gs_src, long long gs_base, long long gs_out,
-                    long long gs_pred, long long gs_aux, cudaStream_t st, float base_div1_g1 = -1.0f)
+// validated conversion of the public step descriptor
+static int run_step(const pmctf_step_t &s, cudaStream_t st, int div_group_n = 0x7fffffff, float base_div1_g1 = 1.0f)
 {
     if (s.n <= 0 || s.h <= 0 || s.w <= 0 || !s.pu_packed || !s.out.p || !s.src.p) return PMCTF_EINVAL;
     if (s.mode < 0 || s.mode > 2) return PMCTF_EINVAL;
@@ -571,8 +571,8 @@ static int run_step(const pmctf_step_t &s, int group_n, long long gs_src, long l
         if (s.aux.p) return PMCTF_EINVAL;
     }
     StepD d;
-    d.n = s.n; d.group_n = group_n; d.h = s.h; d.w = s.w; d.mode = s.mode;
-    d.src = to_dev(s.src, gs_src); d.src_div1 = s.src_div1; d.src_div2 = s.src_div2;
+    d.n = s.n; d.div_group_n = div_group_n; d.h = s.h; d.w = s.w; d.mode = s.mode;
+    d.src = to_dev(s.src); d.src_div1 = s.src_div1; d.src_div2 = s.src_div2;
     d.mv = s.mv; d.mv_share = s.mv_n > 0 ? s.n / s.mv_n : 1; d.mv_down = s.mv_down;
     d.mv_h = s.mv_down ? 2 * s.h : s.h; d.mv_w = s.mv_down ? 2 * s.w : s.w;
     d.mv_sign = s.mv_sign;
@@ -581,18 +581,26 @@ static int run_step(const pmctf_step_t &s, int group_n, long long gs_src, long l
     d.tap0 = s.tap0; d.tap1 = s.tap1; d.tap2 = s.tap2; d.tap_bias = s.tap_bias;
     d.pu_packed = s.pu_packed; d.in_mul = s.in_mul; d.post_mul = s.post_mul; d.out_mul = s.out_mul;
     d.round_tmp = s.round_tmp;
-    d.base = to_dev(s.base, gs_base); d.base_div1 = s.base_div1; d.base_div2 = s.base_div2;
-    d.base_div1_g1 = base_div1_g1 > 0.0f ? base_div1_g1 : s.base_div1;
+    d.base = to_dev(s.base); d.base_div1 = s.base_div1; d.base_div2 = s.base_div2;
+    d.base_div1_g1 = base_div1_g1;
     d.sign = s.sign; d.final_mul = s.final_mul;
-    d.out = to_dev(s.out, gs_out); d.pred = to_dev(s.pred, gs_pred); d.aux = to_dev(s.aux, gs_aux);
+    d.out = to_dev(s.out); d.pred = to_dev(s.pred); d.aux = to_dev(s.aux);
     d.aux_mul = s.aux_mul;
     return launch_step(d, s.src_kind, st);
 }
 
 static pmctf_plane_t dense(const float *p, int H, int W)
 {
-    pmctf_plane_t pl;
+    pmctf_plane_t pl = {};
     pl.p = const_cast<float *>(p); pl.bs = (long long)H * W; pl.rs = W; pl.cs = 1;
+    return pl;
+}
+
+// two groups of `group_n` dense planes each, the second group starting at p1
+static pmctf_plane_t two_groups(pmctf_plane_t pl, const float *p1, int group_n)
+{
+    pl.gs = p1 - pl.p;
+    pl.group_n = group_n;
     return pl;
 }
 
@@ -658,7 +666,7 @@ int pmctf_chroma_mv_down(const float *mv, float *out, int N, int H, int W, void 
 int pmctf_lift_step(const pmctf_step_t *step, void *stream)
 {
     if (!step) return PMCTF_EINVAL;
-    return run_step(*step, step->n, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+    return run_step(*step, (cudaStream_t)stream);
 }
 
 int pmctf_predict_update(const float *x, const float *pu_packed, float in_mul, float *out, int N, int H, int W,
@@ -669,7 +677,7 @@ int pmctf_predict_update(const float *x, const float *pu_packed, float in_mul, f
     s.src_kind = PMCTF_SRC_PLANE; s.mode = PMCTF_MODE_PU;
     s.src = dense(x, H, W); s.out = dense(out, H, W);
     s.pu_packed = pu_packed; s.in_mul = in_mul;
-    return run_step(s, N, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+    return run_step(s, (cudaStream_t)stream);
 }
 
 int pmctf_temporal_filter(const float *x, const pmctf_temporal_t *t, int which, float *out, int N, int H, int W,
@@ -682,74 +690,80 @@ int pmctf_temporal_filter(const float *x, const pmctf_temporal_t *t, int which, 
     s.pu_packed = which == 0 ? t->P_t_packed : t->U_t_packed;
     s.out_mul = t->lossy ? (which == 0 ? t->scale_p : t->scale_u) : 1.0f;
     s.round_tmp = !t->lossy;
-    return run_step(s, N, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+    return run_step(s, (cudaStream_t)stream);
 }
 
-static pmctf_step_t mctf_step(const float *src, const float *base, float *out, float *pred, const float *mv, int mv_n,
-                              int mv_down, float mv_sign, const float *lin_x, const float *lin_y, const float *packed,
-                              float out_mul, float sign, int lossy, int N, int H, int W)
+static pmctf_step_t mctf_step(const pmctf_plane_t *src, const pmctf_plane_t *base, const pmctf_plane_t *out,
+                              const pmctf_plane_t *pred, const float *mv, int mv_n, int mv_down, float mv_sign,
+                              const float *lin_x, const float *lin_y, const float *packed, float out_mul, float sign,
+                              int lossy, int N, int H, int W)
 {
     pmctf_step_t s = blank_step(N, H, W);
     s.src_kind = PMCTF_SRC_WARP; s.mode = PMCTF_MODE_ACCUM;
-    s.src = dense(src, H, W); s.base = dense(base, H, W); s.out = dense(out, H, W);
-    if (pred) s.pred = dense(pred, H, W);
+    s.src = *src; s.base = *base; s.out = *out;
+    if (pred && pred->p) s.pred = *pred;
     s.mv = mv; s.mv_n = mv_n; s.mv_down = mv_down; s.mv_sign = mv_sign; s.lin_x = lin_x; s.lin_y = lin_y;
     s.round_src = !lossy; s.round_tmp = !lossy;
     s.pu_packed = packed; s.out_mul = lossy ? out_mul : 1.0f; s.sign = sign;
     return s;
 }
 
-int pmctf_forward_mctf(const float *ref, const float *cur, const float *mv, int mv_n, int mv_down, const float *lin_x,
-                       const float *lin_y, const pmctf_temporal_t *t, float *L, float *Hh, float *pred, float *inv,
-                       int N, int H, int W, void *stream)
+int pmctf_forward_mctf(const pmctf_plane_t *ref, const pmctf_plane_t *cur, const float *mv, int mv_n, int mv_down,
+                       const float *lin_x, const float *lin_y, const pmctf_temporal_t *t, const pmctf_plane_t *L,
+                       const pmctf_plane_t *Hh, const pmctf_plane_t *pred, const pmctf_plane_t *inv, int N, int H, int W,
+                       void *stream)
 {
-    if (!ref || !cur || !mv || !t || !L || !Hh) return PMCTF_EINVAL;
+    if (!ref || !cur || !mv || !t || !L || !Hh || !ref->p || !cur->p || !L->p || !Hh->p) return PMCTF_EINVAL;
     // H_t = cur - predict(warp(ref, mv))                 pMCTF_L.py:301-305
     pmctf_step_t s1 = mctf_step(ref, cur, Hh, pred, mv, mv_n, mv_down, 1.0f, lin_x, lin_y, t->P_t_packed, t->scale_p,
                                 -1.0f, t->lossy, N, H, W);
-    int e = run_step(s1, N, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+    int e = run_step(s1, (cudaStream_t)stream);
     if (e) return e;
     // L_t = ref + update(warp(H_t, -mv))                 pMCTF_L.py:307-311
     pmctf_step_t s2 = mctf_step(Hh, ref, L, inv, mv, mv_n, mv_down, -1.0f, lin_x, lin_y, t->U_t_packed, t->scale_u,
                                 1.0f, t->lossy, N, H, W);
-    return run_step(s2, N, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+    return run_step(s2, (cudaStream_t)stream);
 }
 
-int pmctf_inverse_mctf(const float *L, const float *Hh, const float *mv, int mv_n, int mv_down, const float *lin_x,
-                       const float *lin_y, const pmctf_temporal_t *t, float *ref, float *cur, int N, int H, int W,
-                       void *stream)
+int pmctf_inverse_mctf(const pmctf_plane_t *L, const pmctf_plane_t *Hh, const float *mv, int mv_n, int mv_down,
+                       const float *lin_x, const float *lin_y, const pmctf_temporal_t *t, const pmctf_plane_t *ref,
+                       const pmctf_plane_t *cur, int N, int H, int W, void *stream)
 {
-    if (!L || !Hh || !mv || !t || !ref || !cur) return PMCTF_EINVAL;
+    if (!L || !Hh || !mv || !t || !ref || !cur || !L->p || !Hh->p || !ref->p || !cur->p) return PMCTF_EINVAL;
     // ref = L - update(warp(H, -mv))                     pMCTF_L.py:320-324
     pmctf_step_t s1 = mctf_step(Hh, L, ref, nullptr, mv, mv_n, mv_down, -1.0f, lin_x, lin_y, t->U_t_packed, t->scale_u,
                                 -1.0f, t->lossy, N, H, W);
-    int e = run_step(s1, N, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+    int e = run_step(s1, (cudaStream_t)stream);
     if (e) return e;
     // cur = H + predict(warp(ref, mv))                   pMCTF_L.py:325-329
     pmctf_step_t s2 = mctf_step(ref, Hh, cur, nullptr, mv, mv_n, mv_down, 1.0f, lin_x, lin_y, t->P_t_packed, t->scale_p,
                                 1.0f, t->lossy, N, H, W);
-    return run_step(s2, N, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+    return run_step(s2, (cudaStream_t)stream);
 }
 
-// one spatial lifting step on logical planes: dst = (base/bd + sign*(skip + 0.1*256*PU(skip/256))) * fm
-static int spatial_step(const pmctf_iwave_t *p, int which, const pmctf_plane_t &src, float sd1, float sd2,
-                        const pmctf_plane_t &base, float bd1, float bd2, const pmctf_plane_t &out, float sign,
-                        float final_mul, const pmctf_plane_t *aux, float aux_mul, int n, int group_n, int h, int w,
-                        long long gs_src, long long gs_base, long long gs_out, long long gs_aux, cudaStream_t st,
-                        float bd1_g1 = -1.0f)
+// one spatial lifting step on logical planes: out = (base/bd1/bd2 + sign*(skip + 0.1*256*PU(skip/256))) * fm
+struct SpatialDivs {
+    float sd1 = 1.0f, sd2 = 1.0f, bd1 = 1.0f, bd2 = 1.0f;
+    int div_group_n = 0x7fffffff; // planes >= this index divide the base by bd1_g1 instead of bd1
+    float bd1_g1 = 1.0f;
+};
+
+static int spatial_step(const pmctf_iwave_t *p, int which, const pmctf_plane_t &src, const pmctf_plane_t &base,
+                        const pmctf_plane_t &out, float sign, float final_mul, const pmctf_plane_t *aux, float aux_mul,
+                        int n, int h, int w, cudaStream_t st, const SpatialDivs &dv = SpatialDivs())
 {
     pmctf_step_t s = blank_step(n, h, w);
     s.src_kind = PMCTF_SRC_SKIP3; s.mode = PMCTF_MODE_ACCUM;
-    s.src = src; s.src_div1 = sd1; s.src_div2 = sd2;
+    s.src = src; s.src_div1 = dv.sd1; s.src_div2 = dv.sd2;
     s.tap0 = p->tap[which][0]; s.tap1 = p->tap[which][1]; s.tap2 = p->tap[which][2]; s.tap_bias = p->bias[which];
     s.pu_packed = p->pu_packed + (long long)which * PMCTF_PU_PACKED_FLOATS;
     s.in_mul = 1.0f / p->dynamic_range; // exact: dynamic_range is a power of two (lifting_1d.py:62,108)
     s.post_mul = p->dynamic_range;
     s.round_tmp = !p->lossy;
-    s.base = base; s.base_div1 = bd1; s.base_div2 = bd2; s.sign = sign; s.final_mul = final_mul;
+    s.base = base; s.base_div1 = dv.bd1; s.base_div2 = dv.bd2; s.sign = sign; s.final_mul = final_mul;
     s.out = out;
     if (aux) { s.aux = *aux; s.aux_mul = aux_mul; }
-    return run_step(s, group_n, gs_src, gs_base, gs_out, 0, gs_aux, st, bd1_g1);
+    return run_step(s, st, dv.div_group_n, dv.bd1_g1);
 }
 
 static pmctf_plane_t phase(const pmctf_plane_t &x, int odd)
@@ -760,53 +774,45 @@ static pmctf_plane_t phase(const pmctf_plane_t &x, int odd)
     return p;
 }
 
-// forward_lift with explicit group strides (gs_* = element offset between the two plane groups)
-static int iwave_forward(const pmctf_plane_t &x, long long gs_x, const pmctf_iwave_t *p, const pmctf_plane_t &l,
-                         long long gs_l, const pmctf_plane_t &hh, long long gs_h, float *ws, int n, int group_n, int h2,
-                         int w, cudaStream_t st)
+static bool pow2_range(float r) { return r >= 1.0f && r <= 65536.0f && (float)(int)r == r && (((int)r) & ((int)r - 1)) == 0; }
+
+// forward_lift on logical planes; ws holds n*h2*w floats (the unscaled high band)
+static int iwave_forward(const pmctf_plane_t &x, const pmctf_iwave_t *p, const pmctf_plane_t &l, const pmctf_plane_t &hh,
+                         float *ws, int n, int h2, int w, cudaStream_t st)
 {
-    if ((float)(int)p->dynamic_range != p->dynamic_range || ((int)p->dynamic_range & ((int)p->dynamic_range - 1)))
-        return PMCTF_EINVAL;
+    if (!pow2_range(p->dynamic_range)) return PMCTF_EINVAL;
     pmctf_plane_t xe = phase(x, 0), xo = phase(x, 1);
-    pmctf_plane_t hu; // unscaled h, workspace [n, h2, w] dense
-    hu.p = ws; hu.bs = (long long)h2 * w; hu.rs = w; hu.cs = 1;
-    const long long gs_hu = (long long)group_n * hu.bs;
+    pmctf_plane_t hu = dense(ws, h2, w);
     const float sl = p->lossy ? p->scale_l : 1.0f, sh = p->lossy ? p->scale_h : 1.0f;
     int e;
     // P1: x_o += f(x_e)   lifting_1d.py:104-112
-    e = spatial_step(p, 0, xe, 1, 1, xo, 1, 1, hu, +1, 1.0f, nullptr, 1, n, group_n, h2, w, gs_x, gs_x, gs_hu, 0, st);
-    if (e) return e;
+    if ((e = spatial_step(p, 0, xe, xo, hu, +1, 1.0f, nullptr, 1, n, h2, w, st))) return e;
     // U1: x_e += f(x_o)   :114-122
-    e = spatial_step(p, 1, hu, 1, 1, xe, 1, 1, l, +1, 1.0f, nullptr, 1, n, group_n, h2, w, gs_hu, gs_x, gs_l, 0, st);
-    if (e) return e;
+    if ((e = spatial_step(p, 1, hu, xe, l, +1, 1.0f, nullptr, 1, n, h2, w, st))) return e;
     // P2                  :124-132
-    e = spatial_step(p, 2, l, 1, 1, hu, 1, 1, hu, +1, 1.0f, nullptr, 1, n, group_n, h2, w, gs_l, gs_hu, gs_hu, 0, st);
-    if (e) return e;
+    if ((e = spatial_step(p, 2, l, hu, hu, +1, 1.0f, nullptr, 1, n, h2, w, st))) return e;
     // U2 + scaling        :134-143   (l *= scale_l in the epilogue, h * scale_h copied through)
-    return spatial_step(p, 3, hu, 1, 1, l, 1, 1, l, +1, sl, &hh, sh, n, group_n, h2, w, gs_hu, gs_l, gs_l, gs_h, st);
+    return spatial_step(p, 3, hu, l, l, +1, sl, &hh, sh, n, h2, w, st);
 }
 
-static int iwave_backward(const pmctf_plane_t &l, long long gs_l, float l_div, float l_div_g1, const pmctf_plane_t &hh,
-                          long long gs_h, float h_div, const pmctf_iwave_t *p, const pmctf_plane_t &x, long long gs_x, float *ws, int n,
-                          int group_n, int h2, int w, cudaStream_t st)
+// backward_lift; ws holds 2*n*h2*w floats.  l_div / l_div_g1 / h_div: fused dequantise (pWave.py:191-202)
+static int iwave_backward(const pmctf_plane_t &l, float l_div, int div_group_n, float l_div_g1, const pmctf_plane_t &hh,
+                          float h_div, const pmctf_iwave_t *p, const pmctf_plane_t &x, float *ws, int n, int h2, int w,
+                          cudaStream_t st)
 {
+    if (!pow2_range(p->dynamic_range)) return PMCTF_EINVAL;
     pmctf_plane_t xe = phase(x, 0), xo = phase(x, 1);
-    pmctf_plane_t lw, hw;
-    lw.p = ws; lw.bs = (long long)h2 * w; lw.rs = w; lw.cs = 1;
-    hw = lw; hw.p = ws + (long long)n * lw.bs;
-    const long long gs_w = (long long)group_n * lw.bs;
+    pmctf_plane_t lw = dense(ws, h2, w), hw = dense(ws + (long long)n * h2 * w, h2, w);
     const float sl = p->lossy ? p->scale_l : 1.0f, sh = p->lossy ? p->scale_h : 1.0f;
     int e;
-    // l = l/scale_l - f(h/scale_h)      lifting_1d.py:148-159   (l_div/h_div: fused dequantise, pWave.py:191-202)
-    e = spatial_step(p, 3, hh, h_div, sh, l, l_div, sl, lw, -1, 1.0f, &hw, 1.0f, n, group_n, h2, w, gs_h, gs_l, gs_w, gs_w, st,
-                     l_div_g1);
-    if (e) return e;
-    e = spatial_step(p, 2, lw, 1, 1, hw, 1, 1, hw, -1, 1.0f, nullptr, 1, n, group_n, h2, w, gs_w, gs_w, gs_w, 0, st); // :161-168
-    if (e) return e;
-    e = spatial_step(p, 1, hw, 1, 1, lw, 1, 1, lw, -1, 1.0f, nullptr, 1, n, group_n, h2, w, gs_w, gs_w, gs_w, 0, st); // :170-177
-    if (e) return e;
+    // l = l/scale_l - f(h/scale_h)      lifting_1d.py:148-159
+    SpatialDivs dv;
+    dv.sd1 = h_div; dv.sd2 = sh; dv.bd1 = l_div; dv.bd2 = sl; dv.div_group_n = div_group_n; dv.bd1_g1 = l_div_g1;
+    if ((e = spatial_step(p, 3, hh, l, lw, -1, 1.0f, &hw, 1.0f, n, h2, w, st, dv))) return e;
+    if ((e = spatial_step(p, 2, lw, hw, hw, -1, 1.0f, nullptr, 1, n, h2, w, st))) return e; // :161-168
+    if ((e = spatial_step(p, 1, hw, lw, lw, -1, 1.0f, nullptr, 1, n, h2, w, st))) return e; // :170-177
     // P1 + merge (:179-189, :16-22): odd rows = h - f(l), even rows = l copied through
-    return spatial_step(p, 0, lw, 1, 1, hw, 1, 1, xo, -1, 1.0f, &xe, 1.0f, n, group_n, h2, w, gs_w, gs_w, gs_x, gs_x, st);
+    return spatial_step(p, 0, lw, hw, xo, -1, 1.0f, &xe, 1.0f, n, h2, w, st);
 }
 
 int pmctf_iwave1d_forward(const pmctf_plane_t *x, const pmctf_iwave_t *p, const pmctf_plane_t *l, const pmctf_plane_t *h,
@@ -815,7 +821,7 @@ int pmctf_iwave1d_forward(const pmctf_plane_t *x, const pmctf_iwave_t *p, const 
     if (!x || !p || !l || !h || !x->p || !l->p || !h->p || !p->pu_packed || !workspace || n <= 0) return PMCTF_EINVAL;
     if (h2 < 2 || w < 1) return PMCTF_ESHAPE;
     if (workspace_floats < (long long)n * h2 * w) return PMCTF_EWORKSPACE;
-    return iwave_forward(*x, 0, p, *l, 0, *h, 0, workspace, n, n, h2, w, (cudaStream_t)stream);
+    return iwave_forward(*x, p, *l, *h, workspace, n, h2, w, (cudaStream_t)stream);
 }
 
 int pmctf_iwave1d_backward(const pmctf_plane_t *l, const pmctf_plane_t *h, const pmctf_iwave_t *p, const pmctf_plane_t *x,
@@ -824,16 +830,16 @@ int pmctf_iwave1d_backward(const pmctf_plane_t *l, const pmctf_plane_t *h, const
     if (!x || !p || !l || !h || !x->p || !l->p || !h->p || !p->pu_packed || !workspace || n <= 0) return PMCTF_EINVAL;
     if (h2 < 2 || w < 1) return PMCTF_ESHAPE;
     if (workspace_floats < 2LL * n * h2 * w) return PMCTF_EWORKSPACE;
-    return iwave_backward(*l, 0, 1.0f, 1.0f, *h, 0, 1.0f, p, *x, 0, workspace, n, n, h2, w, (cudaStream_t)stream);
+    return iwave_backward(*l, 1.0f, 0x7fffffff, 1.0f, *h, 1.0f, p, *x, workspace, n, h2, w, (cudaStream_t)stream);
 }
 
 long long pmctf_lift2d_workspace(int N, int H, int W) { return 2LL * N * H * W; }
 
 // transposed logical view of a dense [n, rows, cols] buffer: logical (y', x') = physical (x', y')
-static pmctf_plane_t transposed(float *p, int rows, int cols)
+static pmctf_plane_t transposed(const float *p, int rows, int cols)
 {
-    pmctf_plane_t t;
-    t.p = p; t.bs = (long long)rows * cols; t.rs = 1; t.cs = cols;
+    pmctf_plane_t t = {};
+    t.p = const_cast<float *>(p); t.bs = (long long)rows * cols; t.rs = 1; t.cs = cols;
     return t;
 }
 
@@ -849,14 +855,13 @@ int pmctf_lift2d_forward(const float *x, const pmctf_iwave_t *p, float *ll, floa
     float *ws0 = workspace, *lbuf = l_out ? l_out : workspace + half, *hbuf = h_out ? h_out : workspace + 2 * half;
     float *ws1 = workspace + 3 * half;
     // rows: wavelet_transform.py:29
-    pmctf_plane_t xin = dense(x, H, W);
-    int e = iwave_forward(xin, 0, p, dense(lbuf, h2, W), 0, dense(hbuf, h2, W), 0, ws0, N, N, h2, W, st);
+    int e = iwave_forward(dense(x, H, W), p, dense(lbuf, h2, W), dense(hbuf, h2, W), ws0, N, h2, W, st);
     if (e) return e;
-    // columns of l and of h in one batch of 2N logical planes [W, h2] (transposed views, :32-40):
+    // columns of l and of h as ONE batch of 2N transposed logical planes [W, h2] (:32-40):
     // group 0 = l -> (ll, lh), group 1 = h -> (hl, hh)
-    pmctf_plane_t xt = transposed(lbuf, h2, W);
-    pmctf_plane_t lo = transposed(ll, h2, w2), ho = transposed(lh, h2, w2);
-    return iwave_forward(xt, hbuf - lbuf, p, lo, hl - ll, ho, hh - lh, ws1, 2 * N, N, w2, h2, st);
+    pmctf_plane_t xt = two_groups(transposed(lbuf, h2, W), hbuf, N);
+    pmctf_plane_t lo = two_groups(transposed(ll, h2, w2), hl, N), ho = two_groups(transposed(lh, h2, w2), hh, N);
+    return iwave_forward(xt, p, lo, ho, ws1, 2 * N, w2, h2, st);
 }
 
 int pmctf_lift2d_backward_q(const float *ll, const float *lh, const float *hl, const float *hh, float ll_div, float q,
@@ -874,12 +879,12 @@ int pmctf_lift2d_backward_q(const float *ll, const float *lh, const float *hl, c
     // columns (wavelet_transform.py:46-54) as ONE batch of 2N transposed logical planes:
     // group 0 = (ll, lh) -> l, group 1 = (hl, hh) -> h.  The fused dequantise (pWave.py:191-202)
     // divides ll by ll_div and the three detail bands by q.
-    pmctf_plane_t li = transposed(const_cast<float *>(ll), h2, w2), hi = transposed(const_cast<float *>(lh), h2, w2);
-    pmctf_plane_t xt = transposed(lbuf, h2, W);
-    int e = iwave_backward(li, hl - ll, ll_div, q, hi, hh - lh, q, p, xt, hbuf - lbuf, ws, 2 * N, N, w2, h2, st);
+    pmctf_plane_t li = two_groups(transposed(ll, h2, w2), hl, N), hi = two_groups(transposed(lh, h2, w2), hh, N);
+    pmctf_plane_t xt = two_groups(transposed(lbuf, h2, W), hbuf, N);
+    int e = iwave_backward(li, ll_div, N, q, hi, q, p, xt, ws, 2 * N, w2, h2, st);
     if (e) return e;
     // rows (:56)
-    return iwave_backward(dense(lbuf, h2, W), 0, 1.0f, 1.0f, dense(hbuf, h2, W), 0, 1.0f, p, dense(x, H, W), 0, ws, N, N,
+    return iwave_backward(dense(lbuf, h2, W), 1.0f, 0x7fffffff, 1.0f, dense(hbuf, h2, W), 1.0f, p, dense(x, H, W), ws, N,
                           h2, W, st);
 }
 
@@ -891,8 +896,8 @@ int pmctf_lift2d_backward(const float *ll, const float *lh, const float *hl, con
 
 int pmctf_quantize(const float *s, float q, float clip, int lossy, int do_round, float *out, long long n, void *stream)
 {
-    if (!s || !out || n < 0) return PMCTF_EINVAL;
     if (n == 0) return 0;
+    if (!s || !out || n < 0) return PMCTF_EINVAL;
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     quantize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s, q, clip, lossy, do_round, out, n);
@@ -901,8 +906,8 @@ int pmctf_quantize(const float *s, float q, float clip, int lossy, int do_round,
 
 int pmctf_dequantize(const float *s_hat, float q, int lossy, float *out, long long n, void *stream)
 {
-    if (!s_hat || !out || n < 0) return PMCTF_EINVAL;
     if (n == 0) return 0;
+    if (!s_hat || !out || n < 0) return PMCTF_EINVAL;
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     dequantize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s_hat, q, lossy, out, n);

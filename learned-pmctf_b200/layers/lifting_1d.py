@@ -123,7 +123,7 @@ class iWave1D(nn.Module):
                     d.tap[i][j] = vals[4 * i + j]
                 d.bias[i] = vals[4 * i + 3]
             d.pu_packed = packed.data_ptr()
-            d.scale_l, d.scale_h = float(self.scale_l), float(self.scale_h)
+            d.scale_l, d.scale_h = float(self.scale_l.detach()), float(self.scale_h.detach())
             d.dynamic_range = self.dynamic_range
             d.lossy = int(self.lossy)
             self._tap_key, self._desc = key, d

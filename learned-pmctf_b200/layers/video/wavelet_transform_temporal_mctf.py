@@ -27,7 +27,7 @@ class TemporalLifting(nn.Module):
         packed = self._pack.get([self.P_t, self.U_t])
         self._keep = packed
         return nat.Temporal(packed.data_ptr(), packed.data_ptr() + 4 * nat.PU_PACKED_FLOATS,
-                            float(self.scale_p), float(self.scale_u), int(self.lossy))
+                            float(self.scale_p.detach()), float(self.scale_u.detach()), int(self.lossy))
 
     def predict_filter(self, x):
         """(x + 0.1 * P_t(x)) * scale_p   (:27-35)"""

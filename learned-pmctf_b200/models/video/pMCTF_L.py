@@ -42,15 +42,15 @@ class MCTFMixin:
     def _temporal(self, stage_idx):
         return self.temporal_filtering[min(self.num_me_stages - 1, stage_idx)].descriptor()
 
-    def forward_MCTF(self, ref_frame, cur_frame, mv_hat, stage_idx=0, mv_down=False, want_pred=True):
+    def forward_MCTF(self, ref_frame, cur_frame, mv_hat, stage_idx=0, mv_down=False, want_pred=True, **out):
         """H = cur - P(warp(ref, mv)); L = ref + U(warp(H, -mv)) -> (L_t, H_t, pred, inv)  (pMCTF_L.py:297-312).
         Two launches: each fuses warp + PredictUpdate CNN + lifting arithmetic.  `mv_down=True`
         takes the luma motion field and applies the chroma 2x2-mean/2 on the fly (pMCTF_L.py:401)."""
-        return ops.forward_mctf(ref_frame, cur_frame, mv_hat, self._temporal(stage_idx), mv_down, want_pred)
+        return ops.forward_mctf(ref_frame, cur_frame, mv_hat, self._temporal(stage_idx), mv_down, want_pred, **out)
 
-    def inverse_MCTF(self, L_t, H_t, mv_hat, downscale=False, stage_idx=0):
+    def inverse_MCTF(self, L_t, H_t, mv_hat, downscale=False, stage_idx=0, **out):
         """ref = L - U(warp(H, -mv)); cur = H + P(warp(ref, mv))  (pMCTF_L.py:314-330)."""
-        return ops.inverse_mctf(L_t, H_t, mv_hat, self._temporal(stage_idx), downscale)
+        return ops.inverse_mctf(L_t, H_t, mv_hat, self._temporal(stage_idx), downscale, **out)
 
 
 class pMCTF(MCTFMixin, nn.Module):

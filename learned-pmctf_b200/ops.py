@@ -75,9 +75,17 @@ def workspace(floats: int, device, tag: str = "") -> torch.Tensor:
 
 
 def plane_of(t: torch.Tensor) -> nat.Plane:
-    """[N,1,H,W] tensor (any strides) -> strided plane descriptor."""
-    assert t.dim() == 4 and t.size(1) == 1
-    return nat.Plane(t.data_ptr(), t.stride(0), t.stride(2), t.stride(3))
+    """[N,1,H,W] or [G,K,1,H,W] tensor (any strides, no copy) -> strided plane descriptor."""
+    if t.dim() == 4 and t.size(1) == 1:
+        return nat.Plane(t.data_ptr(), t.stride(0), t.stride(2), t.stride(3), 0, 0)
+    if t.dim() == 5 and t.size(2) == 1:
+        return nat.Plane(t.data_ptr(), t.stride(1), t.stride(3), t.stride(4), t.stride(0), t.size(1))
+    raise RuntimeError(f"expected single-channel planes [N,1,H,W] or [G,K,1,H,W], got {tuple(t.shape)}")
+
+
+def _planes_shape(t: torch.Tensor):
+    """-> (number of planes, H, W)"""
+    return (t.size(0) if t.dim() == 4 else t.size(0) * t.size(1)), t.size(-2), t.size(-1)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -146,46 +154,61 @@ def temporal_filter(x: torch.Tensor, t: nat.Temporal, which: int):
 
 
 def _mv_args(frame: torch.Tensor, mv: torch.Tensor, mv_down: bool):
-    N, Cc, H, W = frame.shape
-    if Cc != 1:
-        raise RuntimeError("MCTF planes are single-channel ([N,1,H,W]; chroma is batched over N, test_pMCTF_flex.py:153-164)")
+    if frame.dim() not in (4, 5) or frame.size(-3) != 1:
+        raise RuntimeError("MCTF planes are single-channel ([N,1,H,W] or [G,K,1,H,W]; chroma is batched over N, "
+                           "test_pMCTF_flex.py:153-164)")
+    N, H, W = _planes_shape(frame)
     exp = (2, 2 * H, 2 * W) if mv_down else (2, H, W)
-    if tuple(mv.shape[1:]) != exp or N % mv.shape[0]:
+    if mv.dim() != 4 or tuple(mv.shape[1:]) != exp or N % mv.shape[0]:
         raise RuntimeError(f"mv shape {tuple(mv.shape)} does not match frame {tuple(frame.shape)} (mv_down={mv_down})")
     return N, H, W
 
 
-def forward_mctf(ref, cur, mv, t: nat.Temporal, mv_down=False, want_pred=True, lin_x=None, lin_y=None):
-    """pMCTF.forward_MCTF: pMCTF_L.py:297-312 -> (L_t, H_t, pred, inv)."""
+def _out_like(ref: torch.Tensor, out: Optional[torch.Tensor], name: str) -> torch.Tensor:
+    if out is None:
+        return torch.empty(ref.shape, dtype=torch.float32, device=ref.device)
+    _chk(out, name)
+    if out.shape != ref.shape:
+        raise RuntimeError(f"{name}: shape {tuple(out.shape)} != {tuple(ref.shape)}")
+    return out
+
+
+def forward_mctf(ref, cur, mv, t: nat.Temporal, mv_down=False, want_pred=True, lin_x=None, lin_y=None,
+                 out_L=None, out_H=None):
+    """pMCTF.forward_MCTF: pMCTF_L.py:297-312 -> (L_t, H_t, pred, inv).  ref / cur (and the optional
+    preallocated out_L / out_H) may be arbitrary strided views: no copies are made."""
     _no_grad_only(ref, cur, mv)
-    ref, cur, mv = _chk(ref, "ref", 4).contiguous(), _chk(cur, "cur", 4).contiguous(), _chk(mv, "mv", 4).contiguous()
+    ref, cur, mv = _chk(ref, "ref"), _chk(cur, "cur"), _chk(mv, "mv", 4).contiguous()
     if ref.shape != cur.shape:
         raise RuntimeError("ref and cur must have the same shape")
     N, H, W = _mv_args(ref, mv, mv_down)
     lx = linspace_table(W, ref.device) if lin_x is None else lin_x
     ly = linspace_table(H, ref.device) if lin_y is None else lin_y
-    L, Hh = torch.empty_like(ref), torch.empty_like(ref)
-    pred = torch.empty_like(ref) if want_pred else None
-    inv = torch.empty_like(ref) if want_pred else None
-    nat.check(nat.lib().pmctf_forward_mctf(ref.data_ptr(), cur.data_ptr(), mv.data_ptr(), mv.shape[0], int(mv_down),
-                                           lx.data_ptr(), ly.data_ptr(), C.byref(t), L.data_ptr(), Hh.data_ptr(),
-                                           pred.data_ptr() if want_pred else None, inv.data_ptr() if want_pred else None,
+    L, Hh = _out_like(ref, out_L, "out_L"), _out_like(ref, out_H, "out_H")
+    pred = torch.empty(ref.shape, dtype=torch.float32, device=ref.device) if want_pred else None
+    inv = torch.empty(ref.shape, dtype=torch.float32, device=ref.device) if want_pred else None
+    pr, pc, pL, pH = plane_of(ref), plane_of(cur), plane_of(L), plane_of(Hh)
+    pp, pi = (plane_of(pred), plane_of(inv)) if want_pred else (None, None)
+    nat.check(nat.lib().pmctf_forward_mctf(C.byref(pr), C.byref(pc), mv.data_ptr(), mv.shape[0], int(mv_down),
+                                           lx.data_ptr(), ly.data_ptr(), C.byref(t), C.byref(pL), C.byref(pH),
+                                           C.byref(pp) if want_pred else None, C.byref(pi) if want_pred else None,
                                            N, H, W, _stream()), "forward_mctf")
     return L, Hh, pred, inv
 
 
-def inverse_mctf(L, Hh, mv, t: nat.Temporal, mv_down=False, lin_x=None, lin_y=None):
-    """pMCTF.inverse_MCTF: pMCTF_L.py:314-330 -> (ref, cur)."""
+def inverse_mctf(L, Hh, mv, t: nat.Temporal, mv_down=False, lin_x=None, lin_y=None, out_ref=None, out_cur=None):
+    """pMCTF.inverse_MCTF: pMCTF_L.py:314-330 -> (ref, cur); strided views accepted as in forward_mctf."""
     _no_grad_only(L, Hh, mv)
-    L, Hh, mv = _chk(L, "L_t", 4).contiguous(), _chk(Hh, "H_t", 4).contiguous(), _chk(mv, "mv", 4).contiguous()
+    L, Hh, mv = _chk(L, "L_t"), _chk(Hh, "H_t"), _chk(mv, "mv", 4).contiguous()
     if L.shape != Hh.shape:
         raise RuntimeError("L_t and H_t must have the same shape")
     N, H, W = _mv_args(L, mv, mv_down)
     lx = linspace_table(W, L.device) if lin_x is None else lin_x
     ly = linspace_table(H, L.device) if lin_y is None else lin_y
-    ref, cur = torch.empty_like(L), torch.empty_like(L)
-    nat.check(nat.lib().pmctf_inverse_mctf(L.data_ptr(), Hh.data_ptr(), mv.data_ptr(), mv.shape[0], int(mv_down),
-                                           lx.data_ptr(), ly.data_ptr(), C.byref(t), ref.data_ptr(), cur.data_ptr(),
+    ref, cur = _out_like(L, out_ref, "out_ref"), _out_like(L, out_cur, "out_cur")
+    pL, pH, pr, pc = plane_of(L), plane_of(Hh), plane_of(ref), plane_of(cur)
+    nat.check(nat.lib().pmctf_inverse_mctf(C.byref(pL), C.byref(pH), mv.data_ptr(), mv.shape[0], int(mv_down),
+                                           lx.data_ptr(), ly.data_ptr(), C.byref(t), C.byref(pr), C.byref(pc),
                                            N, H, W, _stream()), "inverse_mctf")
     return ref, cur
 
@@ -276,6 +299,8 @@ def quantize(s: torch.Tensor, q: float, clip: float = 8192.0, lossy: bool = True
     _no_grad_only(s)
     s = _chk(s, "subband").contiguous()
     out = torch.empty_like(s)
+    if s.numel() == 0:
+        return out
     nat.check(nat.lib().pmctf_quantize(s.data_ptr(), q, clip, int(lossy), int(do_round), out.data_ptr(), s.numel(), _stream()),
               "quantize")
     return out
@@ -286,5 +311,7 @@ def dequantize(s_hat: torch.Tensor, q: float, lossy: bool = True):
     _no_grad_only(s_hat)
     s_hat = _chk(s_hat, "subband").contiguous()
     out = torch.empty_like(s_hat)
+    if s_hat.numel() == 0:
+        return out
     nat.check(nat.lib().pmctf_dequantize(s_hat.data_ptr(), q, int(lossy), out.data_ptr(), s_hat.numel(), _stream()), "dequantize")
     return out
