@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- 1080p GOP-16 MCTF hot-path throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one synthetic 96-frame 1080p 4:2:0 sequence per GPU (6 GOPs of 16 frames) through the
+whole hot path: MCTF analysis -> pWave++ analysis -> quantise -> dequantise -> pWave++ synthesis ->
+MCTF synthesis, plus the per-frame statistics and their NCCL gather.  Prints ONE JSON line on rank 0.
+
+  value     frames/s, inputs resident in HBM (fp32 padded frames + motion fields), CUDA events
+  e2e       frames/s through GopCodec.code_sequence_host: 8-bit frames + fp32 motion fields start in
+            pinned HOST memory, statistics end on the host; copies inside the timed region
+  roofline  the dominant kernel (lift_step_kernel: warp/skip + PredictUpdate CNN + lifting accumulate),
+            timed live with CUDA events around its launches inside the timed region
+  cpu_baseline / --impl reference   the CPU oracle (oracle/, C + OpenMP port of the reference path) on a
+            bounded sample (one 1080p GOP-2: 2 frames), all host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "1080p GOP-16 MCTF frames/s"
+H0, W0, GOP, FRAMES = 1080, 1920, 16, 96
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "tf_burst": float(p["bf16_tflops"]),
+                "tf_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML; nvidia-smi as a fallback)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                     "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+            get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._halt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = get(h)
+                self.reasons |= {k for k, bit in names.items() if r & bit}
+                time.sleep(0.1)
+        except Exception:
+            import subprocess
+            while not self._halt.is_set():
+                try:
+                    o = subprocess.run(["nvidia-smi", f"--id={self.index}", "--format=csv,noheader,nounits",
+                                        "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                                        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                                        "clocks_event_reasons.sw_power_cap"], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in o.strip().split(",")]
+                    self.samples.append(int(f[0]))
+                    self.max_mhz = int(f[1])
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+def oracle_gop2(threads=None):
+    """The CPU leg: one 1080p (padded 1152x1920, 4:2:0) GOP-2 through the oracle port of the hot path: forward MCTF,
+    hp_coder on H, lp_coder on L (transform + quantise + dequantise + inverse transform), inverse MCTF."""
+    import numpy as np
+
+    from oracle import oracle as orc
+    orc.build()
+    g = np.random.default_rng(0)
+    w = {}
+
+    def pu(prefix):
+        for i, (co, ci) in enumerate(((16, 1), (16, 16), (16, 16), (1, 16)), 1):
+            w[f"{prefix}conv{i}.weight"] = g.normal(0, 0.05, (co, ci, 3, 3)).astype(np.float32)
+            w[f"{prefix}conv{i}.bias"] = g.normal(0, 0.05, (co,)).astype(np.float32)
+        return orc.PU(w, prefix)
+
+    Pt, Ut = pu("P_t."), pu("U_t.")
+    for n, taps in (("conv_P1", [0, -1.586, -1.586]), ("conv_U1", [-0.053, -0.053, 0]), ("conv_P2", [0, 0.883, 0.883]),
+                    ("conv_U2", [0.4435, 0.4435, 0])):
+        w[f"iw.{n}.weight"] = np.array(taps, np.float32).reshape(1, 1, 3, 1)
+        w[f"iw.{n}.bias"] = np.zeros(1, np.float32)
+    for n in ("P_1", "U_1", "P_2", "U_2"):
+        pu(f"iw.{n}.")
+    iw = orc.IWave(w, "iw.")
+    hp, wp = 1152, 1920
+    y = np.round(g.random((2, 1, hp, wp)) * 255).astype(np.float32)
+    c = np.round(g.random((2, 2, 1, hp // 2, wp // 2)) * 255).astype(np.float32)
+    mv = g.normal(0, 3, (1, 2, hp, wp)).astype(np.float32)
+
+    def run():
+        t0 = time.perf_counter()
+        L, Hh, _, _ = orc.forward_mctf(y[0:1], y[1:2], mv, Pt, Ut)
+        mvc = orc.chroma_mv_down(mv)
+        Lc, Hc, _, _ = orc.forward_mctf(c[0], c[1], mvc, Pt, Ut)
+        Hh_hat, _ = orc.spatial_wavelet_dec(Hh, iw, 0.25, 0.5)
+        Hc_hat, _ = orc.spatial_wavelet_dec(Hc, iw, 0.25, 0.5)
+        L_hat, _ = orc.spatial_wavelet_dec(L, iw, 0.0625, 0.0625)
+        Lc_hat, _ = orc.spatial_wavelet_dec(Lc, iw, 0.0625, 0.0625)
+        orc.inverse_mctf(L_hat, Hh_hat, mv, Pt, Ut)
+        orc.inverse_mctf(Lc_hat, Hc_hat, mv, Pt, Ut, downscale=True)
+        return time.perf_counter() - t0
+
+    return run
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+CPU_SAMPLE = ("one 1080p (padded 1152x1920, 4:2:0) GOP-2 = 2 frames: forward MCTF, hp/lp pWave++ analysis + quantise + "
+              "dequantise + synthesis, inverse MCTF; oracle C port (OpenMP, fp32), random weights")
+
+
+def run_reference(args):
+    """--impl reference: the reference path's CPU implementation.  The reference is Python/torch and does not travel
+    to the GPU box, so this times the oracle port of it (oracle/pmctf_oracle.c) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    run = oracle_gop2()
+    for _ in range(min(args.warmup, 1)):
+        run()
+    steps = max(1, min(args.steps, 8))
+    ts = [run() for _ in range(steps)]
+    t = sum(ts) / len(ts)
+    v = 2.0 / t
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[2] hot path, bounded CPU sample", "sample": CPU_SAMPLE},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cpu_cores(), "kind": "port", "sample": CPU_SAMPLE},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def build_model(pkg, dev):
+    """Random-init pMCTF(num_me_stages=4) made non-degenerate (SURVEY.md 'Random-init degeneracy'): 3x3 conv weights
+    ~ N(0, 0.08), 16-channel biases ~ N(0, 0.05), skip taps left at their bior4.4 values, QP / QP_ll endpoints (1/32, 1/2), hp_q_scale
+    endpoints (1.0, 0.7 - 0.1*stage)."""
+    import torch
+    torch.manual_seed(0)
+    m = pkg.pMCTF(num_me_stages=4).to(dev).eval()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() == 4 and p.shape[-1] == 3:
+                p.normal_(0, 0.08)
+            elif p.dim() == 1 and p.numel() > 1:
+                p.normal_(0, 0.05)
+        for c in (m.lp_coder, m.hp_coder):
+            c.QP.copy_(torch.tensor([1 / 32, 1 / 2]).view(2, 1, 1, 1))
+            c.QP_ll.copy_(torch.tensor([1 / 16, 1.0]).view(2, 1, 1, 1))
+        for i, p in enumerate(m.hp_q_scale):
+            p.copy_(torch.tensor([1.0, 0.7 - 0.1 * i]).view(2, 1, 1, 1))
+    return m
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--q-index", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    import learned_pmctf_b200 as pkg
+    from learned_pmctf_b200 import gop as G
+    from learned_pmctf_b200 import parallel as par
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the pMCTF hot path has no CPU fallback")
+    rank, world, local = par.init_from_env()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    nat = pkg._native
+    W_ = max(args.warmup, 3)
+    K = max(args.steps, 1)
+    n_frames = (args.frames // GOP) * GOP
+    n_gops = n_frames // GOP
+
+    model = build_model(pkg, dev)
+    codec = G.GopCodec(model, GOP, q_index=args.q_index)
+    _, pr, _, pb = G.get_padding_size(H0, W0, 128)
+    hp, wp = H0 + pb, W0 + pr
+
+    # --- synthetic sequence of this rank, resident in HBM --------------------------------------------
+    y_u8, c_u8 = G.synthetic_sequence(rank, n_frames, H0, W0, dev)
+    Y = pkg.ops.unpack_u8(y_u8, hp, wp)
+    C = pkg.ops.unpack_u8(c_u8.view(-1, H0 // 2, W0 // 2), hp // 2, wp // 2).view(n_frames, 2, 1, hp // 2, wp // 2)
+    mvs = [G.synthetic_motion(rank, g, GOP, hp, wp, dev) for g in range(n_gops)]
+    items = par.work_items([args.q_index], world, n_gops)  # one sequence per rank: weak scaling
+
+    def step():
+        st = []
+        for g in range(n_gops):
+            sl = slice(g * GOP, (g + 1) * GOP)
+            _, _, s = codec.code_gop(Y[sl], C[sl], mvs[g], y_u8[sl], c_u8[sl])
+            st.append(s)
+        local_stats = torch.stack(st)
+        if world > 1:  # rank r owns sequence r: gather every rank's [gops, 16, fields] block
+            out = torch.empty((world,) + tuple(local_stats.shape), dtype=local_stats.dtype, device=dev)
+            torch.distributed.all_gather_into_tensor(out, local_stats)
+            return out
+        return local_stats[None]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W_):
+        stats = step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    timer = pkg.ops.KernelTimer()
+    l0 = nat.lib().pmctf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    with timer:
+        for _ in range(K):
+            stats = step()
+    e1.record()
+    barrier()
+    launches = int(nat.lib().pmctf_launch_count() - l0)
+    clocks = sampler.stop()
+    ms_step = par.max_over_ranks(e0.elapsed_time(e1) / K, dev)
+    value = world * n_frames / (ms_step * 1e-3)
+    ks = timer.summary()
+
+    # --- end to end through the public host-buffer API --------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        yh, ch = y_u8.cpu().pin_memory(), c_u8.cpu().pin_memory()
+        mvh = [[t.cpu().pin_memory() for t in g] for g in mvs]
+        h2d = yh.numel() + ch.numel() + sum(t.numel() * 4 for g in mvh for t in g)
+        d2h = n_frames * G.N_STATS * 8
+        codec.code_sequence_host(yh, ch, mvh)
+        ke = max(1, min(K, 3))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            host_stats = codec.code_sequence_host(yh, ch, mvh)
+        torch.cuda.synchronize()
+        t_e2e = (time.perf_counter() - t0) / ke
+        t_e2e = par.max_over_ranks(t_e2e * 1e3, dev) * 1e-3
+        e2e = {"value": world * n_frames / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": ke, "ms_per_step": 1e3 * t_e2e, "timing": "host wall clock around the public call incl. final D2H sync, max over ranks"}
+        assert torch.equal(host_stats.to(torch.float64)[:, :6], stats[rank].reshape(-1, G.N_STATS).cpu()[:, :6]), \
+            "host-buffer path and resident path disagree"
+
+    if rank != 0:
+        return
+    pk = peaks()
+    # --- roofline of the dominant kernel -------------------------------------------------------------------
+    flops = ks["pixels"] * pkg.ops.PU_FLOPS_PER_PX
+    k_ms = ks["ms"]
+    tf = flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    # algorithmic HBM bytes of the same launches: 20 B/px temporal step, 12 B/px spatial step (src 4 + base 4 + out 4)
+    roofline = {"kernel": "lift_step_kernel<PLANE|WARP|SKIP3> (warp/skip + PredictUpdate CNN + lifting accumulate, fp32 FFMA)",
+                "bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": tf / pk["tf_sustained"], "traffic": None, "peak_source": f"{pk['source']} bf16 dense, sustained",
+                "launches": ks["launches"], "avg_launch_ms": k_ms / max(ks["launches"], 1),
+                "share_of_step": k_ms / (ms_step * K), "algorithmic_flops_per_px": pkg.ops.PU_FLOPS_PER_PX,
+                "fp32_cuda_core_peak_tflops": 148 * 128 * 2 * (clocks["sm_mhz"] or 1965) * 1e6 / 1e12,
+                "note": "the CNN is computed with fp32 FMA chains on the CUDA cores (bit-exact contract), so the fraction of the "
+                        "bf16 tensor peak is bounded by fp32_cuda_core_peak / tensor peak"}
+    roofline["frac_of_fp32_cuda_core_peak"] = tf / roofline["fp32_cuda_core_peak_tflops"]
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        run = oracle_gop2()
+        run()
+        t = min(run(), run())
+        cpu = {"value": 2.0 / t, "unit": "frames/s", "cores": cpu_cores(), "kind": "port", "sample": CPU_SAMPLE,
+               "seconds_per_sample": t}
+    psnr = stats[0].reshape(-1, G.N_STATS)[:, 6]
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W_,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "configs[2]: pMCTF-L GOP-16 hot path (4 dyadic levels, num_me_stages=4; MCTF analysis -> pWave++ "
+                                   "analysis -> quantise -> dequantise -> pWave++ synthesis -> MCTF synthesis) on one synthetic "
+                                   f"{n_frames}-frame 1080p 4:2:0 sequence per GPU, injected motion fields, random-init weights",
+                       "frames_per_step_per_gpu": n_frames, "gop_size": GOP, "padded": [hp, wp], "q_index": args.q_index,
+                       "l2": "inputs larger than L2: one GOP of fp32 frames + motion fields = 477 MB > 126 MB, 6 distinct GOPs per step",
+                       "parallelism": f"gop-sharded dp{world}, all_gather of per-frame statistics per step"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "quality": {"mean_psnr_yuv_db": float(psnr[torch.isfinite(psnr)].mean()), "frames": int(psnr.numel())}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

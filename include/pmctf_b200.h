@@ -107,6 +107,8 @@ typedef struct {
 
 int pmctf_abi_version(void);
 const char *pmctf_error_string(int code);
+/* Number of CUDA kernels launched by this library so far in this process (instrumentation for bench.py). */
+unsigned long long pmctf_launch_count(void);
 
 /* Repack one PredictUpdate's 8 tensors (OIHW, as in the state_dict) into the kernel layout.
  * Replaces nothing in the reference; run once per weight version. */
@@ -182,6 +184,24 @@ int pmctf_lift2d_backward_q(const float *ll, const float *lh, const float *hl, c
 int pmctf_quantize(const float *s, float q, float clip, int lossy, int do_round, float *out,
                    long long n, void *stream);
 int pmctf_dequantize(const float *s_hat, float q, int lossy, float *out, long long n, void *stream);
+
+/* quantize_subbands (pWave.py:168-182) on `planes` dense planes of `plane_elems` coefficients with
+ * the rate statistics of the symbols accumulated on the fly: stats[2*p] += sum |sym|,
+ * stats[2*p+1] += #nonzero (unsigned 64-bit, caller zeroes them).  These exact integer counters are
+ * what the GOP-sharded run gathers over NCCL in place of the entropy model's bit estimate
+ * (the entropy model itself is out of scope, section 8f). */
+int pmctf_quantize_stats(const float *s, float q, float clip, int lossy, float *out, int planes,
+                         long long plane_elems, unsigned long long *stats, void *stream);
+
+/* 8-bit planes [n,h0,w0] (HOST-visible layout of one YUV plane batch, already on the device) ->
+ * fp32 planes [n,hp,wp], zero padded bottom/right: np_image_to_tensor + F.pad,
+ * test_pMCTF_flex.py:151-192 (padding rule: pMCTF/utils/stream_helper.py:23-32). wp % 4 == 0. */
+int pmctf_unpack_u8(const unsigned char *src, float *dst, int n, int h0, int w0, int hp, int wp, void *stream);
+
+/* sse[p] += sum over the un-padded h0 x w0 area of (round(clamp(rec,0,255)) - orig)^2: the PSNR
+ * numerators of test_pMCTF_flex.py:300-310 as exact integers (caller zeroes sse). */
+int pmctf_frame_sse(const float *rec, const unsigned char *orig, int n, int h0, int w0, int hp, int wp,
+                    unsigned long long *sse, void *stream);
 
 #ifdef __cplusplus
 }

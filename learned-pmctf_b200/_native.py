@@ -53,6 +53,7 @@ _I, _LL, _P = C.c_int, C.c_longlong, C.c_void_p
 SIGNATURES = {
     "pmctf_abi_version": [],
     "pmctf_error_string": [_I],
+    "pmctf_launch_count": [],
     "pmctf_pack_pu_weights": [_P] * 10,
     "pmctf_flow_warp": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _f, _I, _P],
     "pmctf_chroma_mv_down": [_P, _P, _I, _I, _I, _P],
@@ -71,8 +72,12 @@ SIGNATURES = {
     "pmctf_lift2d_backward_q": [_P, _P, _P, _P, _f, _f, C.POINTER(IWave), _P, _I, _I, _I, _P, _LL, _P],
     "pmctf_quantize": [_P, _f, _f, _I, _I, _P, _LL, _P],
     "pmctf_dequantize": [_P, _f, _I, _P, _LL, _P],
+    "pmctf_quantize_stats": [_P, _f, _f, _I, _P, _I, _LL, _P, _P],
+    "pmctf_unpack_u8": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "pmctf_frame_sse": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
 }
-_RESTYPES = {"pmctf_error_string": C.c_char_p, "pmctf_lift2d_workspace": C.c_longlong}
+_RESTYPES = {"pmctf_error_string": C.c_char_p, "pmctf_lift2d_workspace": C.c_longlong,
+             "pmctf_launch_count": C.c_ulonglong}
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

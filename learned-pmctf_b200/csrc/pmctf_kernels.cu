@@ -18,6 +18,10 @@
 
 namespace pmctf {
 
+// number of kernels this library has launched (process-wide; bench.py reports the delta over its timed region)
+static unsigned long long g_launches = 0;
+#define PMCTF_LAUNCHED() (++pmctf::g_launches, (int)cudaGetLastError())
+
 // ------------------------------------------------------------------------------------------
 // tile geometry (logical coordinates: what the reference's conv2d sees)
 constexpr int TH = 32, TW = 32;
@@ -508,6 +512,76 @@ __global__ void __launch_bounds__(256) dequantize_kernel(const float *__restrict
         out[i] = lossy ? s[i] / q : s[i];
 }
 
+// quantise with per-plane integer statistics of the symbols (sum |sym|, #nonzero): exact u64
+// arithmetic, so the rate statistics gathered across GPUs do not depend on reduction order.
+__global__ void __launch_bounds__(256) quantize_stats_kernel(const float *__restrict__ s, float q, float clip, int lossy,
+                                                             float *__restrict__ out, long long plane_elems,
+                                                             unsigned long long *__restrict__ stats)
+{
+    const int plane = blockIdx.y;
+    const float *sp = s + (long long)plane * plane_elems;
+    float *op = out + (long long)plane * plane_elems;
+    unsigned long long sum = 0, nnz = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < plane_elems; i += (long long)gridDim.x * blockDim.x) {
+        float v = lossy ? sp[i] * q : sp[i];
+        v = rintf(fminf(fmaxf(v, -clip), clip));
+        op[i] = v;
+        const long long iv = (long long)fabsf(v);
+        sum += (unsigned long long)iv;
+        nnz += iv != 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+        nnz += __shfl_down_sync(0xffffffffu, nnz, o);
+    }
+    if ((threadIdx.x & 31) == 0 && (sum | nnz)) {
+        atomicAdd(stats + 2 * plane, sum);
+        atomicAdd(stats + 2 * plane + 1, nnz);
+    }
+}
+
+// 8-bit samples -> fp32 planes, zero-padded bottom/right (np_image_to_tensor + F.pad, test_pMCTF_flex.py:151-192)
+__global__ void __launch_bounds__(256) unpack_u8_kernel(const unsigned char *__restrict__ src, float *__restrict__ dst,
+                                                        int h0, int w0, int hp, int wp)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    const long long n = blockIdx.z;
+    if (x4 >= wp) return;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y < h0) {
+        const unsigned char *sp = src + (n * h0 + y) * (long long)w0;
+        if (x4 + 3 < w0 && (w0 & 3) == 0) {
+            const uchar4 u = *reinterpret_cast<const uchar4 *>(sp + x4);
+            v = make_float4(u.x, u.y, u.z, u.w);
+        } else {
+            if (x4 + 0 < w0) v.x = sp[x4 + 0];
+            if (x4 + 1 < w0) v.y = sp[x4 + 1];
+            if (x4 + 2 < w0) v.z = sp[x4 + 2];
+            if (x4 + 3 < w0) v.w = sp[x4 + 3];
+        }
+    }
+    *reinterpret_cast<float4 *>(dst + (n * hp + y) * (long long)wp + x4) = v;
+}
+
+// sum over the un-padded area of (round(clamp(rec, 0, 255)) - orig)^2 per plane: the PSNR numerators of
+// test_pMCTF_flex.py:300-310, as exact integers
+__global__ void __launch_bounds__(256) frame_sse_kernel(const float *__restrict__ rec, const unsigned char *__restrict__ orig,
+                                                        int h0, int w0, int hp, int wp, unsigned long long *__restrict__ sse)
+{
+    const int y = blockIdx.y;
+    const long long n = blockIdx.z;
+    unsigned long long acc = 0;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w0; x += gridDim.x * blockDim.x) {
+        float r = rintf(fminf(fmaxf(rec[(n * hp + y) * (long long)wp + x], 0.0f), 255.0f));
+        const int d = (int)r - (int)orig[(n * h0 + y) * (long long)w0 + x];
+        acc += (unsigned long long)(d * d);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sse + n, acc);
+}
+
+
 __global__ void pack_pu_kernel(const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
                                const float *b3, const float *w4, const float *b4, float *packed)
 {
@@ -554,7 +628,7 @@ static int launch_step(const StepD &d, int src_kind, cudaStream_t st)
     case PMCTF_SRC_SKIP3: lift_step_kernel<PMCTF_SRC_SKIP3><<<grid, NT, SMEM_BYTES, st>>>(d); break;
     default: return PMCTF_EINVAL;
     }
-    return (int)cudaGetLastError();
+    return PMCTF_LAUNCHED();
 }
 
 // validated conversion of the public step descriptor
@@ -623,6 +697,8 @@ extern "C" {
 
 int pmctf_abi_version(void) { return PMCTF_ABI_VERSION; }
 
+unsigned long long pmctf_launch_count(void) { return pmctf::g_launches; }
+
 const char *pmctf_error_string(int code)
 {
     switch (code) {
@@ -639,7 +715,7 @@ int pmctf_pack_pu_weights(const float *w1, const float *b1, const float *w2, con
 {
     if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !w4 || !b4 || !packed) return PMCTF_EINVAL;
     pack_pu_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(w1, b1, w2, b2, w3, b3, w4, b4, packed);
-    return (int)cudaGetLastError();
+    return PMCTF_LAUNCHED();
 }
 
 int pmctf_flow_warp(const float *im, const float *flow, const float *lin_x, const float *lin_y, float *out, int N,
@@ -651,7 +727,7 @@ int pmctf_flow_warp(const float *im, const float *flow, const float *lin_x, cons
     flow_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(im, flow, lin_x, lin_y, out, N, C, H, W, flowN, sign,
                                                             (float)(((double)W - 1.0) / 2.0),
                                                             (float)(((double)H - 1.0) / 2.0), round_out);
-    return (int)cudaGetLastError();
+    return PMCTF_LAUNCHED();
 }
 
 int pmctf_chroma_mv_down(const float *mv, float *out, int N, int H, int W, void *stream)
@@ -660,7 +736,7 @@ int pmctf_chroma_mv_down(const float *mv, float *out, int N, int H, int W, void 
     if (H < 2 || W < 2 || (H & 1) || (W & 1) || H / 2 > 65535 || 2 * N > 65535) return PMCTF_ESHAPE;
     dim3 grid((W / 2 + 255) / 256, H / 2, 2 * N);
     chroma_mv_down_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mv, out, 2 * N, H, W);
-    return (int)cudaGetLastError();
+    return PMCTF_LAUNCHED();
 }
 
 int pmctf_lift_step(const pmctf_step_t *step, void *stream)
@@ -901,7 +977,7 @@ int pmctf_quantize(const float *s, float q, float clip, int lossy, int do_round,
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     quantize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s, q, clip, lossy, do_round, out, n);
-    return (int)cudaGetLastError();
+    return PMCTF_LAUNCHED();
 }
 
 int pmctf_dequantize(const float *s_hat, float q, int lossy, float *out, long long n, void *stream)
@@ -911,7 +987,38 @@ int pmctf_dequantize(const float *s_hat, float q, int lossy, float *out, long lo
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     dequantize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s_hat, q, lossy, out, n);
-    return (int)cudaGetLastError();
+    return PMCTF_LAUNCHED();
+}
+
+int pmctf_quantize_stats(const float *s, float q, float clip, int lossy, float *out, int planes, long long plane_elems,
+                         unsigned long long *stats, void *stream)
+{
+    if (planes == 0 || plane_elems == 0) return 0;
+    if (!s || !out || !stats || planes < 0 || plane_elems < 0 || planes > 65535) return PMCTF_EINVAL;
+    long long bx = (plane_elems + 255) / 256;
+    const long long cap = (148 * 16 + planes - 1) / planes;
+    if (bx > cap) bx = cap;
+    quantize_stats_kernel<<<dim3((unsigned)bx, planes), 256, 0, (cudaStream_t)stream>>>(s, q, clip, lossy, out, plane_elems, stats);
+    return PMCTF_LAUNCHED();
+}
+
+int pmctf_unpack_u8(const unsigned char *src, float *dst, int n, int h0, int w0, int hp, int wp, void *stream)
+{
+    if (n == 0) return 0;
+    if (!src || !dst || n < 0 || h0 <= 0 || w0 <= 0) return PMCTF_EINVAL;
+    if (hp < h0 || wp < w0 || (wp & 3) || hp > 65535 || n > 65535) return PMCTF_ESHAPE;
+    unpack_u8_kernel<<<dim3((wp / 4 + 255) / 256, hp, n), 256, 0, (cudaStream_t)stream>>>(src, dst, h0, w0, hp, wp);
+    return PMCTF_LAUNCHED();
+}
+
+int pmctf_frame_sse(const float *rec, const unsigned char *orig, int n, int h0, int w0, int hp, int wp,
+                    unsigned long long *sse, void *stream)
+{
+    if (n == 0) return 0;
+    if (!rec || !orig || !sse || n < 0 || h0 <= 0 || w0 <= 0) return PMCTF_EINVAL;
+    if (hp < h0 || wp < w0 || h0 > 65535 || n > 65535) return PMCTF_ESHAPE;
+    frame_sse_kernel<<<dim3((w0 + 255) / 256, h0, n), 256, 0, (cudaStream_t)stream>>>(rec, orig, h0, w0, hp, wp, sse);
+    return PMCTF_LAUNCHED();
 }
 
 } // extern "C"

@@ -141,6 +141,22 @@ class pWaveTransform:
     def dequantize_subband(self, subband, q_scale):
         return ops.dequantize(subband, self._q_float(q_scale), self.lossy)
 
+    def code_planes(self, x, q: float, qll: float):
+        """spatial_wavelet_dec (pWave.py:314-349, without PostProcess) on a batch of planes [P,1,H,W] with the
+        symbol statistics gathered by the quantise kernel.  -> (x_hat, int64 [P,2] = sum|sym|, #nonzero)."""
+        P = x.size(0)
+        y = self.encode_bands(x)
+        top = self.decomp_levels - 1
+        stats = torch.zeros((3 * self.decomp_levels + 1, P, 2), dtype=torch.int64, device=x.device)
+        hat, i = {}, 0
+        for lvl in range(top, -1, -1):
+            hat[lvl] = {}
+            for b in (("ll",) + BANDS if lvl == top else BANDS):
+                hat[lvl][b] = ops.quantize_stats(y[lvl][b], qll if b == "ll" else q, stats[i], self.clip_value, self.lossy)
+                i += 1
+        x_hat = self.decode_dequant(hat, q, qll)
+        return x_hat, stats.sum(0)
+
     # --- the reference's transform-only loop (pWave.py:314-349) --------------------------------
     def spatial_wavelet_dec(self, x, q_scale=None, q_scale_ll=None, post_process=True, return_symbols=False):
         """encode -> round(clamp(s*q)) on every band -> dequantise -> decode [-> PostProcess].

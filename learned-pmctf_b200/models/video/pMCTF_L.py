@@ -86,7 +86,7 @@ class pMCTF(MCTFMixin, nn.Module):
 
 
 _PWAVE_METHODS = ("encode", "decode", "decode_dequant", "encode_bands", "quantize_subband", "quantize_subbands",
-                  "dequantize_subbands", "dequantize_subband", "spatial_wavelet_dec", "_q_float")
+                  "dequantize_subbands", "dequantize_subband", "spatial_wavelet_dec", "_q_float", "code_planes")
 _MCTF_METHODS = ("motion_compensation", "forward_MCTF", "inverse_MCTF", "_temporal")
 
 

@@ -41,6 +41,51 @@ def _no_grad_only(*ts):
 
 
 # ---------------------------------------------------------------------------------------------
+# Optional live timing of the fused lifting-step launches (bench.py's roofline): while a KernelTimer is
+# active every call that launches lift_step_kernel is bracketed by CUDA events on the launching stream.
+PU_FLOPS_PER_PX = 9792  # 2*MAC of conv1..conv4
+
+
+class KernelTimer:
+    def __init__(self):
+        self.records = []  # (start_event, end_event, launches, pixels_through_PU)
+
+    def __enter__(self):
+        global _TIMER
+        _TIMER = self
+        return self
+
+    def __exit__(self, *exc):
+        global _TIMER
+        _TIMER = None
+
+    def summary(self):
+        """-> dict(launches, pixels, ms) after the stream has been synchronised."""
+        ms = sum(a.elapsed_time(b) for a, b, _, _ in self.records)
+        return {"launches": sum(r[2] for r in self.records), "pixels": sum(r[3] for r in self.records), "ms": ms}
+
+
+_TIMER: Optional[KernelTimer] = None
+
+
+class _timed:
+    __slots__ = ("launches", "pixels", "ev")
+
+    def __init__(self, launches: int, pixels: int):
+        self.launches, self.pixels = launches, pixels
+
+    def __enter__(self):
+        if _TIMER is not None:
+            self.ev = torch.cuda.Event(enable_timing=True)
+            self.ev.record()
+
+    def __exit__(self, *exc):
+        if _TIMER is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            _TIMER.records.append((self.ev, e, self.launches, self.pixels))
+
+
 _LIN_CACHE: dict = {}
 
 
@@ -189,10 +234,11 @@ def forward_mctf(ref, cur, mv, t: nat.Temporal, mv_down=False, want_pred=True, l
     inv = torch.empty(ref.shape, dtype=torch.float32, device=ref.device) if want_pred else None
     pr, pc, pL, pH = plane_of(ref), plane_of(cur), plane_of(L), plane_of(Hh)
     pp, pi = (plane_of(pred), plane_of(inv)) if want_pred else (None, None)
-    nat.check(nat.lib().pmctf_forward_mctf(C.byref(pr), C.byref(pc), mv.data_ptr(), mv.shape[0], int(mv_down),
-                                           lx.data_ptr(), ly.data_ptr(), C.byref(t), C.byref(pL), C.byref(pH),
-                                           C.byref(pp) if want_pred else None, C.byref(pi) if want_pred else None,
-                                           N, H, W, _stream()), "forward_mctf")
+    with _timed(2, 2 * N * H * W):
+        nat.check(nat.lib().pmctf_forward_mctf(C.byref(pr), C.byref(pc), mv.data_ptr(), mv.shape[0], int(mv_down),
+                                               lx.data_ptr(), ly.data_ptr(), C.byref(t), C.byref(pL), C.byref(pH),
+                                               C.byref(pp) if want_pred else None, C.byref(pi) if want_pred else None,
+                                               N, H, W, _stream()), "forward_mctf")
     return L, Hh, pred, inv
 
 
@@ -207,9 +253,10 @@ def inverse_mctf(L, Hh, mv, t: nat.Temporal, mv_down=False, lin_x=None, lin_y=No
     ly = linspace_table(H, L.device) if lin_y is None else lin_y
     ref, cur = _out_like(L, out_ref, "out_ref"), _out_like(L, out_cur, "out_cur")
     pL, pH, pr, pc = plane_of(L), plane_of(Hh), plane_of(ref), plane_of(cur)
-    nat.check(nat.lib().pmctf_inverse_mctf(C.byref(pL), C.byref(pH), mv.data_ptr(), mv.shape[0], int(mv_down),
-                                           lx.data_ptr(), ly.data_ptr(), C.byref(t), C.byref(pr), C.byref(pc),
-                                           N, H, W, _stream()), "inverse_mctf")
+    with _timed(2, 2 * N * H * W):
+        nat.check(nat.lib().pmctf_inverse_mctf(C.byref(pL), C.byref(pH), mv.data_ptr(), mv.shape[0], int(mv_down),
+                                               lx.data_ptr(), ly.data_ptr(), C.byref(t), C.byref(pr), C.byref(pc),
+                                               N, H, W, _stream()), "inverse_mctf")
     return ref, cur
 
 
@@ -264,11 +311,12 @@ def lift2d_forward(x: torch.Tensor, p: nat.IWave, want_lh_rows: bool = False):
     bands = torch.empty((4, N, 1, H // 2, W // 2), dtype=torch.float32, device=x.device)
     rows = torch.empty((2, N, 1, H // 2, W), dtype=torch.float32, device=x.device) if want_lh_rows else None
     ws = workspace(2 * N * H * W, x.device, "l2d")
-    nat.check(nat.lib().pmctf_lift2d_forward(x.data_ptr(), C.byref(p), bands[0].data_ptr(), bands[1].data_ptr(),
-                                             bands[2].data_ptr(), bands[3].data_ptr(),
-                                             rows[0].data_ptr() if want_lh_rows else None,
-                                             rows[1].data_ptr() if want_lh_rows else None,
-                                             N, H, W, ws.data_ptr(), ws.numel(), _stream()), "lift2d_forward")
+    with _timed(8, 4 * N * H * W):  # 4 row steps on N*H/2*W px + 4 column steps on 2N*W/2*H/2 px
+        nat.check(nat.lib().pmctf_lift2d_forward(x.data_ptr(), C.byref(p), bands[0].data_ptr(), bands[1].data_ptr(),
+                                                 bands[2].data_ptr(), bands[3].data_ptr(),
+                                                 rows[0].data_ptr() if want_lh_rows else None,
+                                                 rows[1].data_ptr() if want_lh_rows else None,
+                                                 N, H, W, ws.data_ptr(), ws.numel(), _stream()), "lift2d_forward")
     d = {"ll": bands[0], "lh": bands[1], "hl": bands[2], "hh": bands[3]}
     if want_lh_rows:  # the reference returns the transposed views (wavelet_transform.py:32,37,42)
         d["l"], d["h"] = rows[0].permute(0, 1, 3, 2), rows[1].permute(0, 1, 3, 2)
@@ -288,9 +336,10 @@ def lift2d_backward(ll, lh, hl, hh, p: nat.IWave, ll_div: float = 1.0, q: float 
     H, W = 2 * h2, 2 * w2
     x = torch.empty((N, 1, H, W), dtype=torch.float32, device=ts[0].device)
     ws = workspace(2 * N * H * W, x.device, "l2d")
-    nat.check(nat.lib().pmctf_lift2d_backward_q(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(),
-                                                ll_div, q, C.byref(p), x.data_ptr(), N, H, W, ws.data_ptr(), ws.numel(),
-                                                _stream()), "lift2d_backward")
+    with _timed(8, 4 * N * H * W):
+        nat.check(nat.lib().pmctf_lift2d_backward_q(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(),
+                                                    ll_div, q, C.byref(p), x.data_ptr(), N, H, W, ws.data_ptr(), ws.numel(),
+                                                    _stream()), "lift2d_backward")
     return x
 
 
@@ -315,3 +364,49 @@ def dequantize(s_hat: torch.Tensor, q: float, lossy: bool = True):
         return out
     nat.check(nat.lib().pmctf_dequantize(s_hat.data_ptr(), q, int(lossy), out.data_ptr(), s_hat.numel(), _stream()), "dequantize")
     return out
+
+
+def quantize_stats(s: torch.Tensor, q: float, stats: torch.Tensor, clip: float = 8192.0, lossy: bool = True):
+    """round(clamp(s*q)) on [P, ...] planes; stats (int64 [P,2], caller-zeroed) accumulates sum|sym| and #nonzero."""
+    _no_grad_only(s)
+    s = _chk(s, "subband").contiguous()
+    out = torch.empty_like(s)
+    planes = s.size(0) if s.dim() > 0 else 0
+    if s.numel() == 0:
+        return out
+    if stats.dtype != torch.int64 or not stats.is_cuda or not stats.is_contiguous() or stats.numel() < 2 * planes:
+        raise RuntimeError("stats must be a contiguous CUDA int64 tensor with 2 entries per plane")
+    nat.check(nat.lib().pmctf_quantize_stats(s.data_ptr(), q, clip, int(lossy), out.data_ptr(), planes, s.numel() // planes,
+                                             stats.data_ptr(), _stream()), "quantize_stats")
+    return out
+
+
+def unpack_u8(src: torch.Tensor, hp: int, wp: int, out: Optional[torch.Tensor] = None):
+    """uint8 planes [n,h0,w0] -> fp32 [n,1,hp,wp], zero padded bottom/right (test_pMCTF_flex.py:151-192)."""
+    if not src.is_cuda or src.dtype != torch.uint8 or src.dim() != 3:
+        raise RuntimeError("unpack_u8 expects a CUDA uint8 tensor [n,h0,w0]")
+    src = src.contiguous()
+    n, h0, w0 = src.shape
+    if out is None:
+        out = torch.empty((n, 1, hp, wp), dtype=torch.float32, device=src.device)
+    elif out.numel() != n * hp * wp or not out.is_contiguous() or out.dtype != torch.float32:
+        raise RuntimeError("unpack_u8: bad output buffer")
+    nat.check(nat.lib().pmctf_unpack_u8(src.data_ptr(), out.data_ptr(), n, h0, w0, hp, wp, _stream()), "unpack_u8")
+    return out
+
+
+def frame_sse(rec: torch.Tensor, orig_u8: torch.Tensor, sse: Optional[torch.Tensor] = None):
+    """Exact per-plane sum of (round(clamp(rec,0,255)) - orig)^2 over the un-padded area (test_pMCTF_flex.py:300-310)."""
+    rec = _chk(rec, "rec").contiguous()
+    if not orig_u8.is_cuda or orig_u8.dtype != torch.uint8 or orig_u8.dim() != 3:
+        raise RuntimeError("frame_sse expects the originals as a CUDA uint8 tensor [n,h0,w0]")
+    orig_u8 = orig_u8.contiguous()
+    n, h0, w0 = orig_u8.shape
+    hp, wp = rec.size(-2), rec.size(-1)
+    if rec.numel() != n * hp * wp:
+        raise RuntimeError(f"frame_sse: {tuple(rec.shape)} does not hold {n} planes")
+    if sse is None:
+        sse = torch.zeros(n, dtype=torch.int64, device=rec.device)
+    nat.check(nat.lib().pmctf_frame_sse(rec.data_ptr(), orig_u8.data_ptr(), n, h0, w0, hp, wp, sse.data_ptr(), _stream()),
+              "frame_sse")
+    return sse

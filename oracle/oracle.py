@@ -264,3 +264,76 @@ def one_q_scale(q_scale, q_index, qp_num=21):
     lo, hi = np.log(q_scale[0]), np.log(q_scale[1])
     step = np.float32((hi - lo) / np.float32(qp_num - 1))
     return float(np.exp(np.float32(lo + step * np.float32(q_index))))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Host-side pieces of the GOP loop (numpy: byte / integer arithmetic)
+def unpack_u8(src, hp, wp):
+    """np_image_to_tensor + zero pad bottom/right (test_pMCTF_flex.py:151-192)."""
+    src = np.asarray(src, np.uint8)
+    out = np.zeros(src.shape[:-2] + (hp, wp), np.float32)
+    out[..., : src.shape[-2], : src.shape[-1]] = src
+    return out
+
+
+def frame_sse(rec, orig_u8):
+    """Per-plane sum of (round(clamp(rec,0,255)) - orig)^2 over the un-padded area (test_pMCTF_flex.py:300-310)."""
+    orig = np.asarray(orig_u8)
+    h0, w0 = orig.shape[-2:]
+    r = np.rint(np.clip(_a(rec), 0, 255))[..., :h0, :w0].astype(np.int64)
+    return ((r.reshape(orig.shape) - orig.astype(np.int64)) ** 2).sum((-2, -1))
+
+
+def symbol_stats(hat):
+    """(sum |sym|, #nonzero) per plane over every coded band of one spatial_wavelet_dec call."""
+    n = next(iter(hat[0].values())).shape[0]
+    st = np.zeros((n, 2), np.int64)
+    for lvl in hat:
+        for v in hat[lvl].values():
+            a = np.abs(v.reshape(n, -1)).astype(np.int64)
+            st[:, 0] += a.sum(1)
+            st[:, 1] += (a != 0).sum(1)
+    return st
+
+
+def code_gop(Y, C, mvs, temporal, hp_w: IWave, lp_w: IWave, q_hp, q_lp, num_me_stages=4):
+    """The reference's GOP loop restricted to the hot path, one pair at a time in its own order
+    (test_pMCTF_flex.py:131-291): stage s pairs frame g*2^(s+1) with +2^s; H frames are coded with the hp
+    transform (step pair q_hp[s]), the final L with the lp transform; temporal decoding in reverse.
+    Y [G,1,H,W]; C [G,2,1,h,w]; mvs[s] [pairs,2,H,W]; temporal[i] = (P_t, U_t).
+    -> (rec_Y, rec_C, sym_stats int64 [G,2])."""
+    Y, C = _a(Y).copy(), _a(C).copy()
+    G = Y.shape[0]
+    S = int(round(math.log2(G)))
+    coded = {}
+    sym = np.zeros((G, 2), np.int64)
+    fy = {i: Y[i:i + 1] for i in range(G)}
+    fc = {i: C[i] for i in range(G)}
+    for s in range(S):
+        step = 2 ** s
+        P, U = temporal[min(num_me_stages - 1, s)]
+        for g in range(G // (2 * step)):
+            r, c = g * 2 * step, g * 2 * step + step
+            mv = _a(mvs[s][g:g + 1])
+            L, Hh, _, _ = forward_mctf(fy[r], fy[c], mv, P, U)
+            Lc, Hc, _, _ = forward_mctf(fc[r], fc[c], chroma_mv_down(mv), P, U)
+            q, qll = q_hp[s]
+            Hh_hat, hat = spatial_wavelet_dec(Hh, hp_w, q, qll)
+            Hc_hat, hatc = spatial_wavelet_dec(Hc, hp_w, q, qll)
+            sym[c] += symbol_stats(hat)[0] + symbol_stats(hatc).sum(0)
+            fy[r], fc[r] = L, Lc
+            coded[c] = (Hh_hat, Hc_hat, mv)
+    q, qll = q_lp
+    L_hat, hat = spatial_wavelet_dec(fy[0], lp_w, q, qll)
+    Lc_hat, hatc = spatial_wavelet_dec(fc[0], lp_w, q, qll)
+    sym[0] += symbol_stats(hat)[0] + symbol_stats(hatc).sum(0)
+    ry, rc = {0: L_hat}, {0: Lc_hat}
+    for s in range(S - 1, -1, -1):
+        step = 2 ** s
+        P, U = temporal[min(num_me_stages - 1, s)]
+        for g in reversed(range(G // (2 * step))):
+            r, c = g * 2 * step, g * 2 * step + step
+            Hh_hat, Hc_hat, mv = coded[c]
+            ry[r], ry[c] = inverse_mctf(ry[r], Hh_hat, mv, P, U)
+            rc[r], rc[c] = inverse_mctf(rc[r], Hc_hat, mv, P, U, downscale=True)
+    return np.concatenate([ry[i] for i in range(G)]), np.stack([rc[i] for i in range(G)]), sym

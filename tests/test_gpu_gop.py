@@ -1,0 +1,142 @@
+"""GPU parity of the batched GOP pipeline and the host-format kernels against the oracle's pair-by-pair
+restatement of the reference loop (test_pMCTF_flex.py:131-310).  Bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import sub_sd
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import learned_pmctf_b200 as pkg
+    assert torch.cuda.is_available()
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def model(P, weights):
+    m = P.pMCTF(num_me_stages=4).cuda().eval()
+    m.load_reference_state_dict({k: torch.from_numpy(v) for k, v in weights.items()} |
+                                {k.replace("lift_h", "lift_v"): torch.from_numpy(v) for k, v in weights.items() if "lift_h" in k})
+    with torch.no_grad():  # distinct steps per temporal level / q_index (random init leaves them degenerate)
+        for c in (m.lp_coder, m.hp_coder):
+            c.QP.copy_(torch.tensor([1 / 32, 1 / 2]).view(2, 1, 1, 1))
+            c.QP_ll.copy_(torch.tensor([1 / 16, 1.0]).view(2, 1, 1, 1))
+        for i, p in enumerate(m.hp_q_scale):
+            p.copy_(torch.tensor([1.0, 0.7 - 0.1 * i]).view(2, 1, 1, 1))
+    return m
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_unpack_u8_and_sse(P):
+    g = np.random.default_rng(1)
+    for (n, h0, w0, hp, wp) in ((3, 10, 12, 16, 16), (2, 30, 50, 32, 64), (1, 7, 9, 8, 12)):
+        u = g.integers(0, 256, (n, h0, w0), dtype=np.uint8)
+        got = P.ops.unpack_u8(cu(u), hp, wp)
+        assert np.array_equal(got.cpu().numpy()[:, 0], orc.unpack_u8(u, hp, wp))
+        rec = got + torch.randn_like(got) * 3
+        sse = P.ops.frame_sse(rec, cu(u))
+        assert sse.cpu().tolist() == orc.frame_sse(rec.cpu().numpy()[:, 0], u).tolist()
+    with pytest.raises(RuntimeError):
+        P.ops.unpack_u8(cu(np.zeros((1, 8, 8), np.uint8)), 8, 6)  # padded width must be a multiple of 4 and >= w0
+
+
+def test_quantize_stats(P):
+    g = np.random.default_rng(2)
+    s = (g.normal(0, 300, (5, 1, 18, 22))).astype(np.float32)
+    s[0, 0, 0, :4] = [0.5, 1.5, -2.5, 1e6]
+    st = torch.zeros((5, 2), dtype=torch.int64, device="cuda")
+    out = P.ops.quantize_stats(cu(s), 0.37, st)
+    want = orc.quantize(s, 0.37)
+    assert np.array_equal(out.cpu().numpy(), want)
+    a = np.abs(want.reshape(5, -1)).astype(np.int64)
+    assert st.cpu().tolist() == np.stack([a.sum(1), (a != 0).sum(1)], 1).tolist()
+
+
+def _inputs(G, H, W, seed):
+    g = np.random.default_rng(seed)
+    base = g.random((H + 64, W + 64)) * 255
+    k = np.ones((5, 5)) / 25
+    from numpy.lib.stride_tricks import sliding_window_view
+    base = (sliding_window_view(np.pad(base, 2, mode="edge"), (5, 5)) * k).sum((-1, -2))
+    y = np.stack([np.clip(base[8 + f:8 + f + H, 8 + 2 * f:8 + 2 * f + W] + g.normal(0, 2, (H, W)), 0, 255) for f in range(G)])
+    y = np.rint(y).astype(np.uint8)
+    c = np.rint(np.clip(g.random((G, 2, H // 2, W // 2)) * 64 + 96, 0, 255)).astype(np.uint8)
+    mvs, n = [], G
+    while n > 1:
+        n //= 2
+        mvs.append((g.normal(0, 2.5, (n, 2, H, W))).astype(np.float32))
+    return y, c, mvs
+
+
+@pytest.mark.parametrize("gop,h0,w0", [(4, 120, 190), (2, 128, 128), (8, 64, 64)])
+def test_code_gop_vs_oracle(P, model, weights, gop, h0, w0):
+    from learned_pmctf_b200 import gop as Gm
+    q_index = 12
+    codec = Gm.GopCodec(model, gop, q_index=q_index)
+    _, pr, _, pb = Gm.get_padding_size(h0, w0, 128)
+    hp, wp = h0 + pb, w0 + pr
+    y, c, mvs = _inputs(gop, h0, w0, 7)
+    mvs = [np.ascontiguousarray(np.pad(m, ((0, 0), (0, 0), (0, hp - h0), (0, wp - w0)))) for m in mvs]
+    yd, cd = cu(y), cu(c)
+    Y = P.ops.unpack_u8(yd, hp, wp)
+    C = P.ops.unpack_u8(cd.view(-1, h0 // 2, w0 // 2), hp // 2, wp // 2).view(gop, 2, 1, hp // 2, wp // 2)
+    rec_y, rec_c, st = codec.code_gop(Y, C, [cu(m) for m in mvs], yd, cd)
+    # oracle: pair by pair in the reference's order
+    temporal = [(orc.PU(sub_sd(weights, f"temporal_filtering.{i}.P_t.")), orc.PU(sub_sd(weights, f"temporal_filtering.{i}.U_t.")))
+                for i in range(4)]
+    hp_w = orc.IWave(sub_sd(weights, "hp_coder.wavelet_transform.lift_h."))
+    lp_w = orc.IWave(sub_sd(weights, "lp_coder.wavelet_transform.lift_h."))
+    S = Gm.num_stages(gop)
+    q_hp = [codec.q_pair("hp", s) for s in range(S)]
+    assert len(set(q_hp)) == min(S, 4), "temporal-layer-adaptive steps must differ per stage"
+    oy, oc, osym = orc.code_gop(orc.unpack_u8(y, hp, wp)[:, None], orc.unpack_u8(c, hp // 2, wp // 2)[:, :, None], mvs, temporal,
+                                hp_w, lp_w, q_hp, codec.q_pair("lp", 0))
+    assert np.array_equal(rec_y.cpu().numpy(), oy), f"luma: max diff {np.abs(rec_y.cpu().numpy() - oy).max()}"
+    assert np.array_equal(rec_c.cpu().numpy(), oc)
+    st = st.cpu().numpy()
+    assert np.array_equal(st[:, 1:3].astype(np.int64), osym)
+    assert np.array_equal(st[:, 3].astype(np.int64), orc.frame_sse(oy[:, 0], y))
+    assert np.array_equal(st[:, 4:6].astype(np.int64), orc.frame_sse(oc[:, :, 0], c))
+    assert st[0, 0] == 0 and np.all(st[1:, 0] == 1) and np.all(st[:, 7] == h0 * w0)
+    px = h0 * w0
+    mse = np.stack([st[:, 3] / px, st[:, 4] / (px // 4), st[:, 5] / (px // 4)], 1)
+    psnr = 10 * np.log10(255.0 ** 2 / mse)
+    assert np.allclose(st[:, 6], (6 * psnr[:, 0] + psnr[:, 1] + psnr[:, 2]) / 8, rtol=1e-12)
+    # the host-buffer entry point gives the same statistics
+    host = codec.code_sequence_host(torch.from_numpy(y).pin_memory(), torch.from_numpy(c).pin_memory(),
+                                    [[torch.from_numpy(m).pin_memory() for m in mvs]])
+    assert np.array_equal(host.numpy(), st)
+
+
+def test_gop16_1080p_properties(P, model):
+    """BASELINE.json full size (C3): one 1080p GOP-16.  Size-independent properties: with a very fine quantiser the
+    whole analysis -> code -> synthesis chain is near-lossless, statistics are consistent, and coarser steps
+    give fewer symbols and more distortion."""
+    from learned_pmctf_b200 import gop as Gm
+    y, c = Gm.synthetic_sequence(0, 16, 1080, 1920, "cuda")
+    Y = P.ops.unpack_u8(y, 1152, 1920)
+    C = P.ops.unpack_u8(c.view(-1, 540, 960), 576, 960).view(16, 2, 1, 576, 960)
+    mvs = Gm.synthetic_motion(0, 0, 16, 1152, 1920, "cuda")
+    assert [m.shape[0] for m in mvs] == [8, 4, 2, 1]
+    res = {}
+    for qi in (0, 20):
+        codec = Gm.GopCodec(model, 16, q_index=qi)
+        ry, rc, st = codec.code_gop(Y, C, mvs, y, c)
+        assert ry.shape == Y.shape and rc.shape == C.shape and torch.isfinite(ry).all() and torch.isfinite(rc).all()
+        res[qi] = st.cpu().numpy()
+    assert res[20][:, 2].sum() > res[0][:, 2].sum()          # finer step -> more nonzero symbols
+    assert res[20][:, 3].sum() < res[0][:, 3].sum()          # ... and less distortion
+    assert np.all(res[20][:, 6] > res[0][:, 6])
+    # transform chain alone (no quantiser) reconstructs: analysis -> synthesis
+    codec = Gm.GopCodec(model, 16, q_index=20)
+    Ly, Lc, Hs = codec.analysis(Y, C, mvs)
+    ry, rc = codec.synthesis(Ly, Lc, Hs, mvs)
+    assert float((ry - Y).abs().max()) <= 2e-3 and float((rc - C).abs().max()) <= 2e-3
