@@ -173,7 +173,7 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 def build_model(pkg, dev):
     """Random-init pMCTF(num_me_stages=4) made non-degenerate (SURVEY.md 'Random-init degeneracy'): 3x3 conv weights
-    ~ N(0, 0.08), 16-channel biases ~ N(0, 0.05), skip taps left at their bior4.4 values, QP / QP_ll endpoints (1/32, 1/2), hp_q_scale
+    ~ N(0, 0.08), 16-channel biases ~ N(0, 0.05), skip taps left at their bior4.4 values, QP endpoints (1/32, 1/2), QP_ll endpoints (1/16, 1/2), hp_q_scale
     endpoints (1.0, 0.7 - 0.1*stage)."""
     import torch
     torch.manual_seed(0)
@@ -186,7 +186,7 @@ def build_model(pkg, dev):
                 p.normal_(0, 0.05)
         for c in (m.lp_coder, m.hp_coder):
             c.QP.copy_(torch.tensor([1 / 32, 1 / 2]).view(2, 1, 1, 1))
-            c.QP_ll.copy_(torch.tensor([1 / 16, 1.0]).view(2, 1, 1, 1))
+            c.QP_ll.copy_(torch.tensor([1 / 16, 1 / 2]).view(2, 1, 1, 1))  # LL x q_ll must stay below clip_value 8192
         for i, p in enumerate(m.hp_q_scale):
             p.copy_(torch.tensor([1.0, 0.7 - 0.1 * i]).view(2, 1, 1, 1))
     return m

@@ -25,7 +25,7 @@ def model(P, weights):
     with torch.no_grad():  # distinct steps per temporal level / q_index (random init leaves them degenerate)
         for c in (m.lp_coder, m.hp_coder):
             c.QP.copy_(torch.tensor([1 / 32, 1 / 2]).view(2, 1, 1, 1))
-            c.QP_ll.copy_(torch.tensor([1 / 16, 1.0]).view(2, 1, 1, 1))
+            c.QP_ll.copy_(torch.tensor([1 / 16, 1 / 2]).view(2, 1, 1, 1))  # LL x q_ll must stay below clip_value 8192
         for i, p in enumerate(m.hp_q_scale):
             p.copy_(torch.tensor([1.0, 0.7 - 0.1 * i]).view(2, 1, 1, 1))
     return m
