@@ -35,7 +35,14 @@ extern "C" {
 #define PMCTF_ESHAPE (-2)   /* shape not supported (odd split size, plane too small for reflection) */
 #define PMCTF_EWORKSPACE (-3) /* workspace too small */
 
-#define PMCTF_PU_PACKED_FLOATS 5000 /* size of one packed PredictUpdate weight block */
+#define PMCTF_PU_PACKED_FLOATS 8848 /* size of one packed PredictUpdate weight block (fp32 taps + int8 tensor-core operands) */
+
+/* How the two 16->16 convolutions of PredictUpdate (lifting_1d.py:40-44) are evaluated (DESIGN.md "Numerics"):
+ *   PMCTF_CONV_TENSOR  exact fixed-point implicit GEMM on the tcgen05 tensor cores (default)
+ *   PMCTF_CONV_FFMA    sequential fp32 FMA chains on the CUDA cores
+ * Each mode is bit-exact against the oracle run in the same mode. */
+#define PMCTF_CONV_FFMA 0
+#define PMCTF_CONV_TENSOR 1
 #define PMCTF_IWAVE_PACKED_FLOATS (4 * PMCTF_PU_PACKED_FLOATS)
 
 /* A strided view of a batch of single-channel planes (strides in elements).  Element (n, y, x)
@@ -109,6 +116,11 @@ int pmctf_abi_version(void);
 const char *pmctf_error_string(int code);
 /* Number of CUDA kernels launched by this library so far in this process (instrumentation for bench.py). */
 unsigned long long pmctf_launch_count(void);
+/* Process-wide selection of the convolution arithmetic (see PMCTF_CONV_*); returns 0 or PMCTF_EINVAL. */
+int pmctf_set_conv_mode(int mode);
+int pmctf_get_conv_mode(void);
+/* Non-zero if a tensor-core kernel gave up waiting for an MMA (synchronises the device; for tests). */
+int pmctf_tc_error_flag(void);
 
 /* Repack one PredictUpdate's 8 tensors (OIHW, as in the state_dict) into the kernel layout.
  * Replaces nothing in the reference; run once per weight version. */
@@ -202,6 +214,20 @@ int pmctf_unpack_u8(const unsigned char *src, float *dst, int n, int h0, int w0,
  * numerators of test_pMCTF_flex.py:300-310 as exact integers (caller zeroes sse). */
 int pmctf_frame_sse(const float *rec, const unsigned char *orig, int n, int h0, int w0, int hp, int wp,
                     unsigned long long *sse, void *stream);
+
+/* Unit test / timing probe of the tcgen05 (5th-generation tensor core) conventions the lifting convolutions are built
+ * on: runs `n_ops` kind::i8 MMAs (M = 128, K = 32, s8 x s8 -> s32 in TMEM) per 128-row block on operands copied to
+ * shared memory and returns the raw accumulators out[block][128][out_cols].  Offsets are bytes relative to the staged
+ * A / B images; rows are 16-byte records at (r%8)*16 + (r/8)*sbo + chunk*lbo (K-major, no swizzle).  No reference
+ * counterpart (the reference calls cuDNN).  err receives 1+block if an MMA never completed. */
+typedef struct {
+    unsigned a_off, a_lbo, a_sbo;
+    unsigned b_off, b_lbo, b_sbo;
+    unsigned n, d_col, accumulate;
+} pmctf_umma_op_t;
+int pmctf_umma_selftest(const signed char *A, int a_bytes, const signed char *B, int b_bytes, const pmctf_umma_op_t *ops,
+                        int n_ops, int n_blocks, int block_stride_bytes, int out_cols, int *out, int repeat,
+                        long long *cycles, int *err, void *stream);
 
 #ifdef __cplusplus
 }

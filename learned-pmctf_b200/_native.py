@@ -11,10 +11,13 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "lib", "libpmctf_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", "pmctf_kernels.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", "pmctf_kernels.cu"), os.path.join(_HERE, "csrc", "pmctf_umma_test.cu"),
+           os.path.join(_HERE, "csrc", "pmctf_lift_tc.cu")]
+HEADERS = [os.path.join(_HERE, "csrc", "pmctf_umma.cuh"), os.path.join(_HERE, "csrc", "pmctf_common.cuh")]
 INCLUDE = os.path.join(ROOT, "include")
 
-PU_PACKED_FLOATS = 5000
+PU_PACKED_FLOATS = 8848
+CONV_FFMA, CONV_TENSOR = 0, 1
 SRC_PLANE, SRC_WARP, SRC_SKIP3 = 0, 1, 2
 MODE_ACCUM, MODE_FILTER, MODE_PU = 0, 1, 2
 
@@ -43,6 +46,10 @@ class IWave(C.Structure):
                 ("dynamic_range", _f), ("lossy", C.c_int)]
 
 
+class UmmaOp(C.Structure):
+    _fields_ = [(n, C.c_uint) for n in ("a_off", "a_lbo", "a_sbo", "b_off", "b_lbo", "b_sbo", "n", "d_col", "accumulate")]
+
+
 class Temporal(C.Structure):
     _fields_ = [("P_t_packed", _fp), ("U_t_packed", _fp), ("scale_p", _f), ("scale_u", _f), ("lossy", C.c_int)]
 
@@ -54,6 +61,9 @@ SIGNATURES = {
     "pmctf_abi_version": [],
     "pmctf_error_string": [_I],
     "pmctf_launch_count": [],
+    "pmctf_set_conv_mode": [_I],
+    "pmctf_get_conv_mode": [],
+    "pmctf_tc_error_flag": [],
     "pmctf_pack_pu_weights": [_P] * 10,
     "pmctf_flow_warp": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _f, _I, _P],
     "pmctf_chroma_mv_down": [_P, _P, _I, _I, _I, _P],
@@ -75,6 +85,7 @@ SIGNATURES = {
     "pmctf_quantize_stats": [_P, _f, _f, _I, _P, _I, _LL, _P, _P],
     "pmctf_unpack_u8": [_P, _P, _I, _I, _I, _I, _I, _P],
     "pmctf_frame_sse": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "pmctf_umma_selftest": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P],
 }
 _RESTYPES = {"pmctf_error_string": C.c_char_p, "pmctf_lift2d_workspace": C.c_longlong,
              "pmctf_launch_count": C.c_ulonglong}
@@ -86,7 +97,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA sources for sm_100a into lib/libpmctf_b200.so (in-tree, so the built file
     travels with the repository snapshot to the GPU box)."""
-    newest = max(os.path.getmtime(p) for p in SOURCES + [os.path.join(INCLUDE, "pmctf_b200.h")])
+    newest = max(os.path.getmtime(p) for p in SOURCES + HEADERS + [os.path.join(INCLUDE, "pmctf_b200.h")])
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

@@ -1,0 +1,117 @@
+// pmctf_common.cuh -- device helpers shared by the lifting-step kernels (FFMA and tensor-core versions).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pmctf_b200.h"
+
+namespace pmctf {
+
+// ------------------------------------------------------------------------------------------
+// deterministic tanh (same specification as oracle/pmctf_oracle.c: IEEE +,*,fma,/,rint only)
+__device__ __forceinline__ float tanh_det(float x)
+{
+    float ax = fminf(fabsf(x), 10.0f);
+    float z = ax + ax;
+    float kf = rintf(z * 1.44269504f);
+    float r = fmaf(kf, -0.693145752f, z);
+    r = fmaf(kf, -1.42860677e-06f, r);
+    float q = 1.98412698e-4f;
+    q = fmaf(q, r, 1.38888889e-3f);
+    q = fmaf(q, r, 8.33333333e-3f);
+    q = fmaf(q, r, 4.16666667e-2f);
+    q = fmaf(q, r, 1.66666667e-1f);
+    q = fmaf(q, r, 0.5f);
+    float r2 = r * r;
+    float p = fmaf(q, r2, r);
+    int k = (int)kf;
+    float s = __int_as_float((k + 127) << 23);
+    float em1 = fmaf(s, p, s - 1.0f);
+    float t = em1 / (em1 + 2.0f);
+    return copysignf(t, x);
+}
+
+struct PlaneD {
+    float *p;
+    long long gs, bs, rs, cs;
+    int group_n; // 0: single level (n * bs)
+};
+
+__device__ __forceinline__ long long plane_off(const PlaneD &pl, int n)
+{
+    if (pl.group_n <= 0) return (long long)n * pl.bs;
+    const int g = n / pl.group_n;
+    return (long long)g * pl.gs + (long long)(n - g * pl.group_n) * pl.bs;
+}
+
+struct StepD {
+    int n, div_group_n, h, w; // div_group_n: planes >= this index use base_div1_g1
+    int mode;
+    PlaneD src;
+    float src_div1, src_div2;
+    const float *mv;
+    int mv_share, mv_down, mv_h, mv_w; // mv_share = n / mv_n
+    float mv_sign, sx, sy;
+    const float *lin_x, *lin_y;
+    int round_src;
+    float tap0, tap1, tap2, tap_bias;
+    const float *pu_packed;
+    float in_mul, post_mul, out_mul;
+    int round_tmp;
+    PlaneD base;
+    float base_div1, base_div1_g1, base_div2, sign, final_mul; // base_div1_g1: divisor for plane group >= 1
+    PlaneD out, pred, aux;
+    float aux_mul;
+};
+
+// bilinear border-clamped backward warp of one sample: video_net.py:42-50 + ATen grid_sampler_2d
+// (align_corners=True, padding_mode=border), op for op as in oracle/pmctf_oracle.c:orc_flow_warp
+__device__ __forceinline__ float warp_sample(const float *__restrict__ im, long long rs, long long cs, int H, int W,
+                                             float lx, float ly, float fx, float fy, float sx, float sy)
+{
+    float gx = lx + fx / sx;
+    float gy = ly + fy / sy;
+    float ix = (gx + 1.0f) * sx;
+    float iy = (gy + 1.0f) * sy;
+    ix = fminf(fmaxf(ix, 0.0f), (float)(W - 1));
+    iy = fminf(fmaxf(iy, 0.0f), (float)(H - 1));
+    float x0 = floorf(ix), y0 = floorf(iy);
+    float w = ix - x0, e = 1.0f - w, nn = iy - y0, s = 1.0f - nn;
+    float nw = s * e, ne = s * w, sw = nn * e, se = nn * w;
+    int x0i = (int)x0, y0i = (int)y0;
+    bool x1ok = x0i + 1 <= W - 1, y1ok = y0i + 1 <= H - 1;
+    const float *p = im + (long long)y0i * rs + (long long)x0i * cs;
+    float vnw = __ldg(p);
+    float vne = x1ok ? __ldg(p + cs) : 0.0f;
+    float vsw = y1ok ? __ldg(p + rs) : 0.0f;
+    float vse = (x1ok && y1ok) ? __ldg(p + rs + cs) : 0.0f;
+    float acc = vnw * nw;
+    acc = fmaf(vne, ne, acc);
+    acc = fmaf(vsw, sw, acc);
+    acc = fmaf(vse, se, acc);
+    return acc;
+}
+
+// motion vector at (y, x) of plane n; mv_down fuses bilineardownsacling(mv)/2 (video_net.py:66-71)
+__device__ __forceinline__ void load_mv(const float *__restrict__ mv, int mv_share, int mv_down, int mv_h, int mv_w, int n,
+                                        int y, int x, float sign, float &fx, float &fy)
+{
+    const long long plane = (long long)mv_h * mv_w;
+    const float *b = mv + (long long)(n / mv_share) * 2 * plane; // mv_share consecutive planes use one field
+    if (!mv_down) {
+        fx = sign * __ldg(b + (long long)y * mv_w + x);
+        fy = sign * __ldg(b + plane + (long long)y * mv_w + x);
+    } else {
+        const float *a = b + (long long)(2 * y) * mv_w + 2 * x;
+        float2 r0 = __ldg(reinterpret_cast<const float2 *>(a));
+        float2 r1 = __ldg(reinterpret_cast<const float2 *>(a + mv_w));
+        fx = sign * ((((r0.x * 0.25f + r0.y * 0.25f) + r1.x * 0.25f) + r1.y * 0.25f) / 2.0f);
+        a += plane;
+        r0 = __ldg(reinterpret_cast<const float2 *>(a));
+        r1 = __ldg(reinterpret_cast<const float2 *>(a + mv_w));
+        fy = sign * ((((r0.x * 0.25f + r0.y * 0.25f) + r1.x * 0.25f) + r1.y * 0.25f) / 2.0f);
+    }
+}
+
+
+} // namespace pmctf

@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include "pmctf_b200.h"
+#include "pmctf_common.cuh"
 
 namespace pmctf {
 
@@ -41,8 +42,11 @@ constexpr int W3_OFF = 2480;
 constexpr int B3_OFF = 4784;
 constexpr int W4_OFF = 4800;   // [16 ci][12] (9 used)
 constexpr int B4_OFF = 4992;
-constexpr int WPACK = PMCTF_PU_PACKED_FLOATS;
-static_assert(WPACK == 5000, "header and kernel disagree on the packed size");
+constexpr int WPACK = 5000;        // fp32 part of the packed block
+constexpr int Q_OFF = 5000;        // int8 tensor-core operand images of conv2 / conv3 (2 x 7680 bytes)
+constexpr int QBYTES = 7680;
+constexpr int SC_OFF = 8840;       // 2^-(22+Sw) of conv2, conv3
+static_assert(PMCTF_PU_PACKED_FLOATS == 8848 && SC_OFF + 8 == PMCTF_PU_PACKED_FLOATS, "header and kernel disagree on the packed size");
 
 // shared memory carve-up (floats)
 constexpr int SM_W = 0;
@@ -57,112 +61,6 @@ static_assert(16 * A3_ROWS * A3_P <= 16 * A1_ROWS * A1_P, "a3 aliases a1");
 static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit the 227 KB per-CTA limit");
 
 constexpr int NT = 672; // 21 warps, <= 96 registers each, one CTA per SM
-
-// ------------------------------------------------------------------------------------------
-// deterministic tanh (same specification as oracle/pmctf_oracle.c: IEEE +,*,fma,/,rint only)
-__device__ __forceinline__ float tanh_det(float x)
-{
-    float ax = fminf(fabsf(x), 10.0f);
-    float z = ax + ax;
-    float kf = rintf(z * 1.44269504f);
-    float r = fmaf(kf, -0.693145752f, z);
-    r = fmaf(kf, -1.42860677e-06f, r);
-    float q = 1.98412698e-4f;
-    q = fmaf(q, r, 1.38888889e-3f);
-    q = fmaf(q, r, 8.33333333e-3f);
-    q = fmaf(q, r, 4.16666667e-2f);
-    q = fmaf(q, r, 1.66666667e-1f);
-    q = fmaf(q, r, 0.5f);
-    float r2 = r * r;
-    float p = fmaf(q, r2, r);
-    int k = (int)kf;
-    float s = __int_as_float((k + 127) << 23);
-    float em1 = fmaf(s, p, s - 1.0f);
-    float t = em1 / (em1 + 2.0f);
-    return copysignf(t, x);
-}
-
-struct PlaneD {
-    float *p;
-    long long gs, bs, rs, cs;
-    int group_n; // 0: single level (n * bs)
-};
-
-__device__ __forceinline__ long long plane_off(const PlaneD &pl, int n)
-{
-    if (pl.group_n <= 0) return (long long)n * pl.bs;
-    const int g = n / pl.group_n;
-    return (long long)g * pl.gs + (long long)(n - g * pl.group_n) * pl.bs;
-}
-
-struct StepD {
-    int n, div_group_n, h, w; // div_group_n: planes >= this index use base_div1_g1
-    int mode;
-    PlaneD src;
-    float src_div1, src_div2;
-    const float *mv;
-    int mv_share, mv_down, mv_h, mv_w; // mv_share = n / mv_n
-    float mv_sign, sx, sy;
-    const float *lin_x, *lin_y;
-    int round_src;
-    float tap0, tap1, tap2, tap_bias;
-    const float *pu_packed;
-    float in_mul, post_mul, out_mul;
-    int round_tmp;
-    PlaneD base;
-    float base_div1, base_div1_g1, base_div2, sign, final_mul; // base_div1_g1: divisor for plane group >= 1
-    PlaneD out, pred, aux;
-    float aux_mul;
-};
-
-// bilinear border-clamped backward warp of one sample: video_net.py:42-50 + ATen grid_sampler_2d
-// (align_corners=True, padding_mode=border), op for op as in oracle/pmctf_oracle.c:orc_flow_warp
-__device__ __forceinline__ float warp_sample(const float *__restrict__ im, long long rs, long long cs, int H, int W,
-                                             float lx, float ly, float fx, float fy, float sx, float sy)
-{
-    float gx = lx + fx / sx;
-    float gy = ly + fy / sy;
-    float ix = (gx + 1.0f) * sx;
-    float iy = (gy + 1.0f) * sy;
-    ix = fminf(fmaxf(ix, 0.0f), (float)(W - 1));
-    iy = fminf(fmaxf(iy, 0.0f), (float)(H - 1));
-    float x0 = floorf(ix), y0 = floorf(iy);
-    float w = ix - x0, e = 1.0f - w, nn = iy - y0, s = 1.0f - nn;
-    float nw = s * e, ne = s * w, sw = nn * e, se = nn * w;
-    int x0i = (int)x0, y0i = (int)y0;
-    bool x1ok = x0i + 1 <= W - 1, y1ok = y0i + 1 <= H - 1;
-    const float *p = im + (long long)y0i * rs + (long long)x0i * cs;
-    float vnw = __ldg(p);
-    float vne = x1ok ? __ldg(p + cs) : 0.0f;
-    float vsw = y1ok ? __ldg(p + rs) : 0.0f;
-    float vse = (x1ok && y1ok) ? __ldg(p + rs + cs) : 0.0f;
-    float acc = vnw * nw;
-    acc = fmaf(vne, ne, acc);
-    acc = fmaf(vsw, sw, acc);
-    acc = fmaf(vse, se, acc);
-    return acc;
-}
-
-// motion vector at (y, x) of plane n; mv_down fuses bilineardownsacling(mv)/2 (video_net.py:66-71)
-__device__ __forceinline__ void load_mv(const float *__restrict__ mv, int mv_share, int mv_down, int mv_h, int mv_w, int n,
-                                        int y, int x, float sign, float &fx, float &fy)
-{
-    const long long plane = (long long)mv_h * mv_w;
-    const float *b = mv + (long long)(n / mv_share) * 2 * plane; // mv_share consecutive planes use one field
-    if (!mv_down) {
-        fx = sign * __ldg(b + (long long)y * mv_w + x);
-        fy = sign * __ldg(b + plane + (long long)y * mv_w + x);
-    } else {
-        const float *a = b + (long long)(2 * y) * mv_w + 2 * x;
-        float2 r0 = __ldg(reinterpret_cast<const float2 *>(a));
-        float2 r1 = __ldg(reinterpret_cast<const float2 *>(a + mv_w));
-        fx = sign * ((((r0.x * 0.25f + r0.y * 0.25f) + r1.x * 0.25f) + r1.y * 0.25f) / 2.0f);
-        a += plane;
-        r0 = __ldg(reinterpret_cast<const float2 *>(a));
-        r1 = __ldg(reinterpret_cast<const float2 *>(a + mv_w));
-        fy = sign * ((((r0.x * 0.25f + r0.y * 0.25f) + r1.x * 0.25f) + r1.y * 0.25f) / 2.0f);
-    }
-}
 
 // ------------------------------------------------------------------------------------------
 // 16 -> 16 channel 3x3 layer on shared-memory planes.  Each work item is CO_T output channels
@@ -582,8 +480,8 @@ __global__ void __launch_bounds__(256) frame_sse_kernel(const float *__restrict_
 }
 
 
-__global__ void pack_pu_kernel(const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
-                               const float *b3, const float *w4, const float *b4, float *packed)
+__global__ void __launch_bounds__(512) pack_pu_kernel(const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                                                      const float *b3, const float *w4, const float *b4, float *packed)
 {
     for (int i = threadIdx.x; i < WPACK; i += blockDim.x) {
         float v = 0.0f;
@@ -597,6 +495,48 @@ __global__ void pack_pu_kernel(const float *w1, const float *b1, const float *w2
         else if (i == B4_OFF) v = b4[0];
         packed[i] = v;
     }
+    // tensor-core operands of conv2 / conv3: W = rint(w * 2^Sw), Sw = 22 - e with max|w| = m * 2^e, m in [0.5, 1);
+    // three signed-byte digits W = e0*2^16 + e1*2^8 + e2; image layout per tap pair tp (tests/umma_ref.py:pack_weights):
+    //   byte [tp*1536 + chunk*768 + (digit*16 + co)*16 + ci], chunk = which tap of the pair
+    __shared__ float red[512];
+    __shared__ int s_sw[2];
+    int8_t *img = reinterpret_cast<int8_t *>(packed + Q_OFF);
+    for (int layer = 0; layer < 2; ++layer) {
+        const float *w = layer == 0 ? w2 : w3;
+        float m = 0.0f;
+        for (int i = threadIdx.x; i < 2304; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+        red[threadIdx.x] = m;
+        __syncthreads();
+        for (int o = 256; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            int e = 0;
+            if (red[0] > 0.0f) frexpf(red[0], &e);
+            s_sw[layer] = 22 - e;
+            packed[SC_OFF + layer] = ldexpf(1.0f, -(22 + (22 - e)));
+        }
+        __syncthreads();
+        const float up = ldexpf(1.0f, s_sw[layer]);
+        for (int i = threadIdx.x; i < 5 * 2 * 16 * 16; i += blockDim.x) {
+            const int ci = i & 15, co = (i >> 4) & 15, chunk = (i >> 8) & 1, tp = i >> 9;
+            // tap pairs: (0,0)(0,1) | (1,0)(1,1) | (2,0)(2,1) | (0,2)(1,2) | (2,2) -
+            int ky, kx;
+            if (tp < 3) { ky = tp; kx = chunk; }
+            else if (tp == 3) { ky = chunk; kx = 2; }
+            else { ky = 2; kx = 2; }
+            int V = 0;
+            if (!(tp == 4 && chunk == 1)) V = __float2int_rn(w[(co * 16 + ci) * 9 + ky * 3 + kx] * up);
+            const int d2 = (int)(signed char)(V & 0xFF);
+            const int V1 = (V - d2) >> 8;
+            const int d1 = (int)(signed char)(V1 & 0xFF);
+            const int d0 = (V1 - d1) >> 8;
+            int8_t *o = img + layer * QBYTES + tp * 1536 + chunk * 768 + co * 16 + ci;
+            o[0] = (int8_t)d0; o[256] = (int8_t)d1; o[512] = (int8_t)d2;
+        }
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -607,8 +547,22 @@ static PlaneD to_dev(const pmctf_plane_t &p)
     return d;
 }
 
+int launch_step_tc(const StepD &d, int src_kind, int *err_flag, cudaStream_t st); // pmctf_lift_tc.cu
+
+static int g_conv_mode = PMCTF_CONV_TENSOR;
+static int *g_tc_err = nullptr; // device flag set by a tensor-core kernel whose MMA never completed
+
 static int launch_step(const StepD &d, int src_kind, cudaStream_t st)
 {
+    if (g_conv_mode == PMCTF_CONV_TENSOR) {
+        if (!g_tc_err) {
+            if (cudaMalloc(&g_tc_err, sizeof(int)) != cudaSuccess) return (int)cudaGetLastError();
+            cudaMemset(g_tc_err, 0, sizeof(int));
+        }
+        const int e = launch_step_tc(d, src_kind, g_tc_err, st);
+        if (e == 0) ++g_launches;
+        return e;
+    }
     static bool configured = false;
     if (!configured) {
         cudaError_t e;
@@ -698,6 +652,22 @@ extern "C" {
 int pmctf_abi_version(void) { return PMCTF_ABI_VERSION; }
 
 unsigned long long pmctf_launch_count(void) { return pmctf::g_launches; }
+
+int pmctf_set_conv_mode(int mode)
+{
+    if (mode != PMCTF_CONV_FFMA && mode != PMCTF_CONV_TENSOR) return PMCTF_EINVAL;
+    pmctf::g_conv_mode = mode;
+    return 0;
+}
+
+int pmctf_get_conv_mode(void) { return pmctf::g_conv_mode; }
+
+int pmctf_tc_error_flag(void)
+{
+    int v = 0;
+    if (pmctf::g_tc_err && cudaMemcpy(&v, pmctf::g_tc_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return v;
+}
 
 const char *pmctf_error_string(int code)
 {

@@ -1,0 +1,472 @@
+// pmctf_lift_tc.cu -- the fused lifting step with its two 16->16 convolutions on the sm_100a tensor cores.
+//
+// Same step as lift_step_kernel (pmctf_kernels.cu): {plane | flow warp | 3-tap skip} -> PredictUpdate CNN ->
+// lifting accumulate, one HBM pass.  conv1 (1->16, K = 9) and conv4 (16->1) stay fp32 FMA chains on the CUDA
+// cores; conv2 and conv3 (94 % of the FLOPs) are implicit GEMMs on tcgen05 in EXACT integer arithmetic:
+//
+//   * their inputs are tanh outputs in [-1, 1]: V = rint(a * 2^22), split into three signed-byte digits
+//     V = d0*2^16 + d1*2^8 + d2; weights likewise W = rint(w * 2^Sw) = e0*2^16 + e1*2^8 + e2 (Sw per layer);
+//   * a pixel's 16 channels of one digit are one 16-byte record of a K-major, un-swizzled UMMA operand, the
+//     tile is a linear pixel array with pitch 38, so a filter tap is only a different descriptor start
+//     address and two taps form the K = 32 of one kind::i8 MMA (leading byte offset = tap distance);
+//   * digit products of equal weight share a TMEM accumulator group: 5 groups x 16 columns of s32 per
+//     128-pixel block hold o_k = sum_{i+j=k} d_i e_j, every |o_k| < 2^24, and
+//     S = sum_k o_k 2^(32-8k) = sum A*W exactly -- independent of the tensor core's summation order;
+//   * conv = fma((float)S, 2^-(22+Sw), bias): one rounding.  oracle/pmctf_oracle.c states the same contract.
+//
+// CTA = one 32x32 output tile, 17 warps: warps 0-15 are four epilogue groups (a warp reads TMEM lanes
+// 32*(warp%4)..+31), warp 16 issues the MMAs; 6 accumulator slots of 80 TMEM columns pipeline MMA and epilogue
+// through full/empty mbarriers.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pmctf_b200.h"
+#include "pmctf_common.cuh"
+#include "pmctf_umma.cuh"
+
+namespace pmctf {
+namespace tc {
+
+constexpr int TH = 32, TW = 32;
+constexpr int P = 38;                                // pixel pitch of the digit arrays (= conv1 output width)
+constexpr int NBLK = 11;                             // 128-pixel blocks per layer (conv2: 36*38 px, conv3: 34*38-4 px)
+constexpr int NPIX = 1488;                           // >= 10*128 + 127 + 2*P + 2 + 1
+constexpr int PLANE = NPIX * 16;                     // bytes of one digit plane
+constexpr int S_ROWS = TH + 8, S_COLS = TW + 8, S_P = 41;
+constexpr int T_ROWS = TH + 10, T_P = 41;
+constexpr int A1_N = TH + 6, A2_N = TH + 4, A3_N = TH + 2, A3_P = 36;
+constexpr int O_P = 33;
+constexpr int NSLOT = 6, SLOT_COLS = 80;
+static_assert(A1_N == P && A1_N * P <= NPIX, "pitch");
+static_assert((NBLK - 1) * 128 + 127 + 2 * P + 2 < NPIX, "operand reads stay inside the plane");
+static_assert(NBLK * 128 >= (A2_N - 1) * P + A2_N && NBLK * 128 >= (A3_N - 1) * P + A3_N, "blocks cover the layer outputs");
+
+// packed parameter block (floats, see pack_pu_kernel)
+constexpr int W1_OFF = 0, B1_OFF = 144, B2_OFF = 2464, B3_OFF = 4784, W4_OFF = 4800, B4_OFF = 4992;
+constexpr int Q_OFF = 5000, QBYTES = 7680, SC_OFF = 8840;
+static_assert(PMCTF_PU_PACKED_FLOATS == 8848, "header and kernel disagree on the packed size");
+
+// shared memory (bytes)
+constexpr int SM_WB = 0;                              // 2 x 7680 B operand images
+constexpr int SM_F = SM_WB + 2 * QBYTES;              // fp32 parameters
+constexpr int F_W1 = 0, F_B1 = 144, F_B2 = 160, F_B3 = 176, F_W4 = 192, F_B4 = 384, F_SC2 = 385, F_SC3 = 386;
+constexpr int SM_S = SM_F + 1664;
+constexpr int SM_T = SM_S + 6656;
+constexpr int SM_A1 = SM_T + 6912;
+constexpr int A1_BYTES = 16 * A3_N * A3_P * 4;        // a3 (fp32, conv4 input) aliases the A1 digit planes
+static_assert(A1_BYTES >= 3 * PLANE && A1_BYTES % 128 == 0, "a3 alias");
+constexpr int SM_A2 = SM_A1 + A1_BYTES;
+constexpr int SM_BAR = SM_A2 + 3 * PLANE;
+constexpr int SMEM_BYTES = SM_BAR + 128;
+static_assert(SM_S % 128 == 0 && SM_T % 128 == 0 && SM_A1 % 128 == 0 && SM_A2 % 128 == 0 && SM_BAR % 128 == 0, "alignment");
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+
+constexpr int NT = 544;       // 16 epilogue warps + 1 MMA warp
+constexpr int NEPI = 512;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+// the 18 MMAs of one 128-pixel block: digit d of the activations times weight digits e0..e0+ne-1 lands in
+// accumulator groups d+e0.. (tests/umma_ref.py:conv_ops is the executable specification of this list)
+__device__ __forceinline__ void issue_block(uint32_t a_saddr, uint32_t b_saddr, uint32_t d_tmem)
+{
+#pragma unroll
+    for (int tp = 0; tp < 5; ++tp) {
+        const int t0 = (tp < 3) ? tp * P : (tp == 3 ? 2 : 2 * P + 2);          // first tap of the pair (pixels)
+        const int lbo = (tp < 3) ? 16 : (tp == 3 ? P * 16 : 16);                 // byte distance to the second tap
+        const uint32_t b = b_saddr + tp * 1536;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const uint64_t ad = umma::smem_desc(a_saddr + d * PLANE + t0 * 16, lbo, 128);
+            if (tp == 0 && d > 0) {
+                // first touch of groups 3 and 4 must not accumulate: split the N = 48 MMA
+                umma::mma_s8(d_tmem + 16 * d, ad, umma::smem_desc(b, 768, 128), umma::idesc_s8(16 * (3 - d)), 1u);
+                if (d == 1) {
+                    umma::mma_s8(d_tmem + 48, ad, umma::smem_desc(b + 512, 768, 128), umma::idesc_s8(16), 0u);
+                } else {
+                    umma::mma_s8(d_tmem + 48, ad, umma::smem_desc(b + 256, 768, 128), umma::idesc_s8(16), 1u);
+                    umma::mma_s8(d_tmem + 64, ad, umma::smem_desc(b + 512, 768, 128), umma::idesc_s8(16), 0u);
+                }
+            } else {
+                umma::mma_s8(d_tmem + 16 * d, ad, umma::smem_desc(b, 768, 128), umma::idesc_s8(48), (tp == 0) ? 0u : 1u);
+            }
+        }
+    }
+}
+
+// exact integer dot product from the five accumulator groups, rounded once to fp32
+__device__ __forceinline__ float combine(uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3, uint32_t o4)
+{
+    const long long S = ((long long)(int)o0 << 32) + (long long)((int)o1 * 256 + (int)o2) * 65536 + (long long)((int)o3 * 256 + (int)o4);
+    return (float)S;
+}
+
+// V = rint(a * 2^22) -> three signed-byte digits, appended to the byte lanes of w0/w1/w2
+__device__ __forceinline__ void push_digits(float a, int lane_byte, uint32_t &w0, uint32_t &w1, uint32_t &w2)
+{
+    const int V = __float2int_rn(a * 4194304.0f);
+    const int d2 = (int)(signed char)(V & 0xFF);
+    const int V1 = (V - d2) >> 8;
+    const int d1 = (int)(signed char)(V1 & 0xFF);
+    const int d0 = (V1 - d1) >> 8;
+    w0 |= (uint32_t)(d0 & 0xFF) << (8 * lane_byte);
+    w1 |= (uint32_t)(d1 & 0xFF) << (8 * lane_byte);
+    w2 |= (uint32_t)(d2 & 0xFF) << (8 * lane_byte);
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_constant__ StepD a, int *__restrict__ err)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    float *sf = reinterpret_cast<float *>(smem + SM_F);
+    float *ss = reinterpret_cast<float *>(smem + SM_S);
+    float *stile = reinterpret_cast<float *>(smem + SM_T);
+    uint8_t *A1 = smem + SM_A1;
+    uint8_t *A2 = smem + SM_A2;
+    float *a3 = reinterpret_cast<float *>(smem + SM_A1);
+    float *so = reinterpret_cast<float *>(smem + SM_A2);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);      // full[6], empty[6]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_BAR + 96);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = blockIdx.z;
+    const int y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+    const int H = a.h, W = a.w;
+
+    // ---- setup: parameters, barriers, TMEM ------------------------------------------------------------
+    {
+        const int4 *g = reinterpret_cast<const int4 *>(a.pu_packed + Q_OFF);
+        int4 *d = reinterpret_cast<int4 *>(smem + SM_WB);
+        for (int i = tid; i < 2 * QBYTES / 16; i += NT) d[i] = __ldg(g + i);
+        for (int i = tid; i < 144 + 16; i += NT) sf[F_W1 + i] = __ldg(a.pu_packed + W1_OFF + i);
+        if (tid < 16) {
+            sf[F_B2 + tid] = __ldg(a.pu_packed + B2_OFF + tid);
+            sf[F_B3 + tid] = __ldg(a.pu_packed + B3_OFF + tid);
+        }
+        for (int i = tid; i < 192; i += NT) sf[F_W4 + i] = __ldg(a.pu_packed + W4_OFF + i);
+        if (tid == 0) {
+            sf[F_B4] = __ldg(a.pu_packed + B4_OFF);
+            sf[F_SC2] = __ldg(a.pu_packed + SC_OFF);
+            sf[F_SC3] = __ldg(a.pu_packed + SC_OFF + 1);
+            for (int i = 0; i < NSLOT; ++i) {
+                umma::mbar_init(umma::smem_u32(bars + i), 1);
+                umma::mbar_init(umma::smem_u32(bars + NSLOT + i), 128);
+            }
+            umma::fence_mbar_init();
+        }
+        if (warp == 16) umma::tmem_alloc(tmem_slot, 512);
+    }
+
+    // ---- source tile ------------------------------------------------------------------------------------
+    const bool xfast_src = a.src.cs <= a.src.rs;
+    if (SRC == PMCTF_SRC_PLANE || SRC == PMCTF_SRC_SKIP3) {
+        constexpr int ROWS = (SRC == PMCTF_SRC_SKIP3) ? T_ROWS : S_ROWS;
+        constexpr int ROFF = (SRC == PMCTF_SRC_SKIP3) ? 5 : 4;
+        float *dst = (SRC == PMCTF_SRC_SKIP3) ? stile : ss;
+        const float *sp = a.src.p + plane_off(a.src, n);
+        const bool dodiv = (a.src_div1 != 1.0f) || (a.src_div2 != 1.0f);
+        for (int i = tid; i < ROWS * S_COLS; i += NT) {
+            int r, c;
+            if (xfast_src) { r = i / S_COLS; c = i - r * S_COLS; }
+            else { c = i / ROWS; r = i - c * ROWS; }
+            const int gy = y0 - ROFF + r, gx = x0 - 4 + c;
+            float v = 0.0f;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                v = __ldg(sp + (long long)gy * a.src.rs + (long long)gx * a.src.cs);
+                if (dodiv) v = (v / a.src_div1) / a.src_div2;
+            }
+            dst[r * S_P + c] = v;
+        }
+    } else {
+        const float *sp = a.src.p + plane_off(a.src, n);
+        for (int i = tid; i < S_ROWS * S_COLS; i += NT) {
+            const int r = i / S_COLS, c = i - r * S_COLS;
+            const int gy = y0 - 4 + r, gx = x0 - 4 + c;
+            float v = 0.0f;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                float fx, fy;
+                load_mv(a.mv, a.mv_share, a.mv_down, a.mv_h, a.mv_w, n, gy, gx, a.mv_sign, fx, fy);
+                v = warp_sample(sp, a.src.rs, a.src.cs, H, W, __ldg(a.lin_x + gx), __ldg(a.lin_y + gy), fx, fy, a.sx, a.sy);
+                if (a.round_src) v = rintf(v);
+            }
+            ss[r * S_P + c] = v;
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+    if (SRC == PMCTF_SRC_SKIP3) {
+        for (int i = tid; i < S_ROWS * S_COLS; i += NT) {
+            const int r = i / S_COLS, c = i - r * S_COLS;
+            const int gy = y0 - 4 + r, gx = x0 - 4 + c;
+            float v = 0.0f;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                const int ym = (gy == 0) ? 1 : gy - 1;
+                const int yp = (gy == H - 1) ? H - 2 : gy + 1;
+                const int base = y0 - 5;
+                v = a.tap_bias;
+                v = fmaf(a.tap0, stile[(ym - base) * T_P + c], v);
+                v = fmaf(a.tap1, stile[(gy - base) * T_P + c], v);
+                v = fmaf(a.tap2, stile[(yp - base) * T_P + c], v);
+            }
+            ss[r * S_P + c] = v;
+        }
+        __syncthreads();
+    }
+
+    // ---- conv1 (1 -> 16) + tanh -> digits of A1 (origin (-3,-3), pitch 38) -------------------------------
+    {
+        const float in_mul = a.in_mul;
+        for (int it = tid; it < 4 * A1_N * A1_N; it += NT) {
+            const int px = it >> 2, cq = it & 3;
+            const int r = px / P, c = px - r * P;
+            const int gy = y0 - 3 + r, gx = x0 - 3 + c;
+            uint32_t w0 = 0, w1 = 0, w2 = 0;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                const float4 b = *reinterpret_cast<const float4 *>(sf + F_B1 + cq * 4);
+                float acc0 = b.x, acc1 = b.y, acc2 = b.z, acc3 = b.w;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const int ky = k / 3, kx = k - ky * 3;
+                    const float v = ss[(r + ky) * S_P + c + kx] * in_mul;
+                    const float4 wv = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + cq * 4);
+                    acc0 = fmaf(wv.x, v, acc0); acc1 = fmaf(wv.y, v, acc1);
+                    acc2 = fmaf(wv.z, v, acc2); acc3 = fmaf(wv.w, v, acc3);
+                }
+                push_digits(tanh_det(acc0), 0, w0, w1, w2);
+                push_digits(tanh_det(acc1), 1, w0, w1, w2);
+                push_digits(tanh_det(acc2), 2, w0, w1, w2);
+                push_digits(tanh_det(acc3), 3, w0, w1, w2);
+            }
+            uint8_t *d = A1 + px * 16 + cq * 4;
+            *reinterpret_cast<uint32_t *>(d) = w0;
+            *reinterpret_cast<uint32_t *>(d + PLANE) = w1;
+            *reinterpret_cast<uint32_t *>(d + 2 * PLANE) = w2;
+        }
+    }
+    umma::fence_proxy_async();
+    __syncthreads();
+
+    const uint32_t full0 = umma::smem_u32(bars), empty0 = umma::smem_u32(bars + NSLOT);
+    bool ok = true;
+
+    // ---- conv2 / conv3 on the tensor core ---------------------------------------------------------------
+#pragma unroll 1
+    for (int layer = 0; layer < 2; ++layer) {
+        const uint32_t a_saddr = umma::smem_u32(layer == 0 ? A1 : A2);
+        const uint32_t b_saddr = umma::smem_u32(smem + SM_WB + layer * QBYTES);
+        if (warp == 16) {
+            if (lane == 0) {
+                umma::fence_after_sync();
+#pragma unroll 1
+                for (int blk = 0; blk < NBLK; ++blk) {
+                    const int slot = blk % NSLOT;
+                    if (blk >= NSLOT) { // the slot's previous accumulators must have been drained
+                        ok = umma::mbar_wait(empty0 + 8 * slot, 0u);
+                        if (!ok) break;
+                        umma::fence_after_sync();
+                    }
+                    issue_block(a_saddr + blk * 2048, b_saddr, tbase + slot * SLOT_COLS);
+                    umma::commit(full0 + 8 * slot);
+                }
+            }
+            __syncwarp();
+        } else {
+            const int grp = warp >> 2, quarter = warp & 3;
+            const float scale = sf[layer == 0 ? F_SC2 : F_SC3];
+            const float *bias = sf + (layer == 0 ? F_B2 : F_B3);
+#pragma unroll 1
+            for (int blk = grp; blk < NBLK; blk += 4) {
+                const int slot = blk % NSLOT;
+                const int uses = (slot < NSLOT - 1) ? 2 : 1;
+                const uint32_t parity = (uint32_t)(layer * uses + blk / NSLOT) & 1u;
+                ok = umma::mbar_wait(full0 + 8 * slot, parity);
+                if (!ok) break;
+                umma::fence_after_sync();
+                const int m = blk * 128 + quarter * 32 + lane;
+                const int r = m / P, c = m - r * P;
+                const uint32_t taddr = tbase + ((uint32_t)(quarter * 32) << 16) + slot * SLOT_COLS;
+                if (layer == 0) {
+                    const int gy = y0 - 2 + r, gx = x0 - 2 + c;
+                    const bool valid = r < A2_N && c < A2_N && gy >= 0 && gy < H && gx >= 0 && gx < W;
+                    uint32_t w[3][4];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t o[5][8];
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) tmem_ld8(taddr + 16 * k + 8 * h, o[k]);
+                        umma::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            uint32_t w0 = 0, w1 = 0, w2 = 0;
+                            if (valid) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const int ch = 4 * j + q;
+                                    const float v = fmaf(combine(o[0][ch], o[1][ch], o[2][ch], o[3][ch], o[4][ch]), scale, bias[8 * h + ch]);
+                                    push_digits(tanh_det(v), q, w0, w1, w2);
+                                }
+                            }
+                            w[0][2 * h + j] = w0; w[1][2 * h + j] = w1; w[2][2 * h + j] = w2;
+                        }
+                    }
+                    umma::fence_before_sync();
+                    mbar_arrive(empty0 + 8 * slot);
+                    uint8_t *d = A2 + m * 16;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        *reinterpret_cast<uint4 *>(d + k * PLANE) = make_uint4(w[k][0], w[k][1], w[k][2], w[k][3]);
+                } else {
+                    const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+                    const bool inside = r < A3_N && c < A3_N;
+                    const bool valid = inside && gy >= 0 && gy < H && gx >= 0 && gx < W;
+                    const float in_mul = a.in_mul;
+                    float sv[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) sv[k] = inside ? ss[(r + 2 + k / 3) * S_P + c + 2 + (k % 3)] * in_mul : 0.0f;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t o[5][8];
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) tmem_ld8(taddr + 16 * k + 8 * h, o[k]);
+                        umma::tmem_ld_wait();
+#pragma unroll
+                        for (int ch = 0; ch < 8; ++ch) {
+                            // conv1 at this position, the identical fma chain (lifting_1d.py:45 residual)
+                            float c1 = sf[F_B1 + 8 * h + ch];
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) c1 = fmaf(sf[F_W1 + k * 16 + 8 * h + ch], sv[k], c1);
+                            const float v = fmaf(combine(o[0][ch], o[1][ch], o[2][ch], o[3][ch], o[4][ch]), scale, bias[8 * h + ch]);
+                            if (inside) a3[(8 * h + ch) * (A3_N * A3_P) + r * A3_P + c] = valid ? (c1 + v) : 0.0f;
+                        }
+                    }
+                    umma::fence_before_sync();
+                    mbar_arrive(empty0 + 8 * slot);
+                }
+            }
+        }
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+    }
+    if (!ok && err) atomicExch(err, 1);
+
+    // ---- conv4 (16 -> 1) -> so ---------------------------------------------------------------------------
+    for (int it = tid; it < TH * (TW / 2); it += NT) {
+        const int r = it / (TW / 2), st = it - r * (TW / 2);
+        float acc0 = sf[F_B4], acc1 = acc0;
+        const float *ip = a3 + r * A3_P + st * 2;
+        const float *wc = sf + F_W4;
+#pragma unroll 4
+        for (int ci = 0; ci < 16; ++ci) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(wc);
+            const float4 w1 = *reinterpret_cast<const float4 *>(wc + 4);
+            const float w8 = wc[8];
+            const float wk[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w8};
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const float2 p0 = *reinterpret_cast<const float2 *>(ip + ky * A3_P);
+                const float2 p1 = *reinterpret_cast<const float2 *>(ip + ky * A3_P + 2);
+                const float pv[4] = {p0.x, p0.y, p1.x, p1.y};
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    acc0 = fmaf(wk[ky * 3 + kx], pv[kx], acc0);
+                    acc1 = fmaf(wk[ky * 3 + kx], pv[kx + 1], acc1);
+                }
+            }
+            ip += A3_N * A3_P;
+            wc += 12;
+        }
+        so[r * O_P + st * 2] = acc0;
+        so[r * O_P + st * 2 + 1] = acc1;
+    }
+    __syncthreads();
+
+    // ---- lifting arithmetic + stores -----------------------------------------------------------------------
+    {
+        const bool xfast = a.out.cs <= a.out.rs;
+        const long long o_off = plane_off(a.out, n);
+        const long long b_off = a.base.p ? plane_off(a.base, n) : 0;
+        const long long p_off = a.pred.p ? plane_off(a.pred, n) : 0;
+        const long long x_off = a.aux.p ? plane_off(a.aux, n) : 0;
+        const float bd1 = (n >= a.div_group_n) ? a.base_div1_g1 : a.base_div1;
+        const bool bdiv = (bd1 != 1.0f) || (a.base_div2 != 1.0f);
+        for (int i = tid; i < TH * TW; i += NT) {
+            int r, c;
+            if (xfast) { r = i / TW; c = i - r * TW; }
+            else { c = i / TH; r = i - c * TH; }
+            const int gy = y0 + r, gx = x0 + c;
+            if (gy >= H || gx >= W) continue;
+            const float pu = so[r * O_P + c];
+            float res;
+            if (a.mode == PMCTF_MODE_PU) {
+                res = pu;
+            } else {
+                const float s = ss[(r + 4) * S_P + c + 4];
+                const float t = pu * a.post_mul;
+                float tmp = s + t * 0.1f;
+                if (a.round_tmp) tmp = rintf(tmp);
+                const float rr = tmp * a.out_mul;
+                if (a.pred.p) a.pred.p[p_off + (long long)gy * a.pred.rs + (long long)gx * a.pred.cs] = rr;
+                if (a.mode == PMCTF_MODE_FILTER) {
+                    res = rr;
+                } else {
+                    float b = __ldg(a.base.p + b_off + (long long)gy * a.base.rs + (long long)gx * a.base.cs);
+                    if (bdiv) b = (b / bd1) / a.base_div2;
+                    res = (a.sign > 0.0f) ? b + rr : b - rr;
+                    res = res * a.final_mul;
+                }
+            }
+            a.out.p[o_off + (long long)gy * a.out.rs + (long long)gx * a.out.cs] = res;
+            if (a.aux.p) {
+                const float raw = (SRC == PMCTF_SRC_SKIP3) ? stile[(r + 5) * T_P + c + 4] : ss[(r + 4) * S_P + c + 4];
+                a.aux.p[x_off + (long long)gy * a.aux.rs + (long long)gx * a.aux.cs] = raw * a.aux_mul;
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 16) umma::tmem_dealloc(tbase, 512);
+}
+
+} // namespace tc
+
+// host side: called by launch_step() in pmctf_kernels.cu
+int launch_step_tc(const StepD &d, int src_kind, int *err_flag, cudaStream_t st)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e;
+        e = cudaFuncSetAttribute(tc::lift_step_tc_kernel<PMCTF_SRC_PLANE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(tc::lift_step_tc_kernel<PMCTF_SRC_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(tc::lift_step_tc_kernel<PMCTF_SRC_SKIP3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    dim3 grid((d.w + tc::TW - 1) / tc::TW, (d.h + tc::TH - 1) / tc::TH, d.n);
+    if (grid.y > 65535 || grid.z > 65535) return PMCTF_ESHAPE;
+    switch (src_kind) {
+    case PMCTF_SRC_PLANE: tc::lift_step_tc_kernel<PMCTF_SRC_PLANE><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(d, err_flag); break;
+    case PMCTF_SRC_WARP: tc::lift_step_tc_kernel<PMCTF_SRC_WARP><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(d, err_flag); break;
+    case PMCTF_SRC_SKIP3: tc::lift_step_tc_kernel<PMCTF_SRC_SKIP3><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(d, err_flag); break;
+    default: return PMCTF_EINVAL;
+    }
+    return (int)cudaGetLastError();
+}
+
+} // namespace pmctf

@@ -19,6 +19,16 @@ SCALE_P = float(np.float32(1 / math.sqrt(2)))   # wavelet_transform_temporal_mct
 SCALE_U = 0.5
 
 
+def set_conv_mode(mode: str) -> None:
+    """'tensor' (default): conv2/conv3 of PredictUpdate as exact fixed-point implicit GEMMs on the tcgen05 tensor cores;
+    'ffma': sequential fp32 FMA chains on the CUDA cores.  Process-wide (include/pmctf_b200.h PMCTF_CONV_*)."""
+    nat.check(nat.lib().pmctf_set_conv_mode({"ffma": nat.CONV_FFMA, "tensor": nat.CONV_TENSOR}[mode]), "set_conv_mode")
+
+
+def get_conv_mode() -> str:
+    return "tensor" if nat.lib().pmctf_get_conv_mode() == nat.CONV_TENSOR else "ffma"
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

@@ -51,6 +51,15 @@ def lib():
     return _lib
 
 
+def set_conv_mode(mode: str) -> None:
+    """'ffma': conv2/conv3 as sequential fp32 FMA chains; 'tensor': exact fixed-point (see pmctf_oracle.c)."""
+    lib().orc_set_conv_mode({"ffma": 0, "tensor": 1}[mode])
+
+
+def get_conv_mode() -> str:
+    return "tensor" if lib().orc_get_conv_mode() == 1 else "ffma"
+
+
 def _a(x) -> np.ndarray:
     return np.ascontiguousarray(x, dtype=np.float32)
 

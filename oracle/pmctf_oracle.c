@@ -190,6 +190,54 @@ static void conv3x3_band(const float *in, int cin, int rows_in, const float *wgt
             }
 }
 
+/* ---- "exact" convolution mode (PMCTF_CONV_TENSOR of include/pmctf_b200.h) ----------------------------------
+ * conv2 / conv3 of PredictUpdate take tanh outputs in [-1, 1].  In this mode they are evaluated in exact integer
+ * arithmetic, which makes the result independent of any summation order (so a tensor-core implementation can be
+ * bit-identical):  V = rint(a * 2^22);  Wq = rint(w * 2^Sw) with Sw = 22 - e, max|w| = m * 2^e, m in [0.5, 1);
+ * S = sum V * Wq (exact, |S| < 2^52);  out = fma((float)S, 2^-(22+Sw), bias)   -- (float)S is one RN rounding.     */
+static int g_conv_mode = 0;
+ORC_API void orc_set_conv_mode(int mode) { g_conv_mode = mode; }
+ORC_API int orc_get_conv_mode(void) { return g_conv_mode; }
+
+typedef struct {
+    int32_t w[NCH * NCH * 9];
+    float down;
+} orc_qconv_t;
+
+static void quantise_weights(const float *wgt, orc_qconv_t *q)
+{
+    float m = 0.0f;
+    for (int i = 0; i < NCH * NCH * 9; ++i) m = fmaxf(m, fabsf(wgt[i]));
+    int e = 0;
+    if (m > 0.0f) frexpf(m, &e);
+    const int sw = 22 - e;
+    const float up = ldexpf(1.0f, sw);
+    for (int i = 0; i < NCH * NCH * 9; ++i) q->w[i] = (int32_t)rintf(wgt[i] * up);
+    q->down = ldexpf(1.0f, -(22 + sw));
+}
+
+/* same band geometry as conv3x3_band, 16 -> 16 channels */
+static void conv3x3_band_exact(const float *in, int rows_in, const orc_qconv_t *q, const float *bias, float *out,
+                               int rows_out, int W, int Wp, int32_t *vin)
+{
+    const size_t nin = (size_t)NCH * rows_in * Wp;
+    for (size_t i = 0; i < nin; ++i) vin[i] = (int32_t)rintf(in[i] * 4194304.0f);
+    for (int co = 0; co < NCH; ++co)
+        for (int r = 0; r < rows_out; ++r) {
+            float *o = out + ((size_t)co * rows_out + r) * Wp + 1;
+            for (int x = 0; x < W; ++x) {
+                int64_t S = 0;
+                for (int ci = 0; ci < NCH; ++ci)
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int32_t *row = vin + ((size_t)ci * rows_in + r + ky) * Wp + x;
+                        const int32_t *wq = q->w + ((co * NCH + ci) * 3 + ky) * 3;
+                        S += (int64_t)row[0] * wq[0] + (int64_t)row[1] * wq[1] + (int64_t)row[2] * wq[2];
+                    }
+                o[x] = __builtin_fmaf((float)S, q->down, bias[co]);
+            }
+        }
+}
+
 static void band_fix(float *buf, int ch, int rows, int Wp, int W, int row0_img, int H, int do_tanh)
 {
     /* zero padding semantics of every layer: rows outside the image and the two border columns
@@ -215,8 +263,15 @@ ORC_API void orc_predict_update(const float *x, const orc_pu_t *pu, float *out, 
 {
     const int Wp = W + 2;
     const int nb = (H + BAND - 1) / BAND;
+    const int exact = g_conv_mode == 1;
+    orc_qconv_t q2, q3;
+    if (exact) {
+        quantise_weights(pu->w2, &q2);
+        quantise_weights(pu->w3, &q3);
+    }
 #pragma omp parallel
     {
+        int32_t *vin = exact ? (int32_t *)malloc(sizeof(int32_t) * NCH * (BAND + 6) * Wp) : NULL;
         float *xin = (float *)malloc(sizeof(float) * (BAND + 8) * Wp);
         float *c1 = (float *)malloc(sizeof(float) * NCH * (BAND + 6) * Wp);
         float *a1 = (float *)malloc(sizeof(float) * NCH * (BAND + 6) * Wp);
@@ -246,9 +301,11 @@ ORC_API void orc_predict_update(const float *x, const orc_pu_t *pu, float *out, 
                 memcpy(a1, c1, sizeof(float) * NCH * (rows + 6) * Wp);
                 band_fix(c1, NCH, rows + 6, Wp, W, y0 - 3, H, 0);
                 band_fix(a1, NCH, rows + 6, Wp, W, y0 - 3, H, 1); /* tanh(conv1) */
-                conv3x3_band(a1, NCH, rows + 6, pu->w2, pu->b2, a2, NCH, rows + 4, W, Wp);
+                if (exact) conv3x3_band_exact(a1, rows + 6, &q2, pu->b2, a2, rows + 4, W, Wp, vin);
+                else conv3x3_band(a1, NCH, rows + 6, pu->w2, pu->b2, a2, NCH, rows + 4, W, Wp);
                 band_fix(a2, NCH, rows + 4, Wp, W, y0 - 2, H, 1); /* tanh(conv2) */
-                conv3x3_band(a2, NCH, rows + 4, pu->w3, pu->b3, a3, NCH, rows + 2, W, Wp);
+                if (exact) conv3x3_band_exact(a2, rows + 4, &q3, pu->b3, a3, rows + 2, W, Wp, vin);
+                else conv3x3_band(a2, NCH, rows + 4, pu->w3, pu->b3, a3, NCH, rows + 2, W, Wp);
                 /* x = conv1 + conv3   lifting_1d.py:45 */
                 for (int c = 0; c < NCH; ++c)
                     for (int r = 0; r < rows + 2; ++r) {
@@ -261,7 +318,7 @@ ORC_API void orc_predict_update(const float *x, const orc_pu_t *pu, float *out, 
                 for (int r = 0; r < rows; ++r)
                     memcpy(out + (size_t)n * H * W + (size_t)(y0 + r) * W, o4 + (size_t)r * Wp + 1, sizeof(float) * W);
             }
-        free(xin); free(c1); free(a1); free(a2); free(a3); free(o4);
+        free(xin); free(c1); free(a1); free(a2); free(a3); free(o4); free(vin);
     }
 }
 

@@ -29,3 +29,20 @@ def weights(golden):
 def sub_sd(sd, prefix):
     """Strip `prefix` from a state-dict style mapping."""
     return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+@pytest.fixture(autouse=True, params=["tensor", "ffma"])
+def conv_mode(request):
+    """Every parity test runs in both convolution arithmetics (include/pmctf_b200.h PMCTF_CONV_*): the oracle and,
+    for GPU tests, the CUDA library are switched together and must agree bit for bit in each."""
+    from oracle import oracle as orc
+    orc.set_conv_mode(request.param)
+    gpu = request.node.get_closest_marker("gpu") is not None
+    if gpu:
+        import learned_pmctf_b200 as pkg
+        pkg.ops.set_conv_mode(request.param)
+    yield request.param
+    orc.set_conv_mode("ffma")
+    if gpu:
+        import learned_pmctf_b200 as pkg
+        assert pkg._native.lib().pmctf_tc_error_flag() == 0, "a tensor-core kernel timed out waiting for an MMA"

@@ -1,0 +1,87 @@
+"""numpy emulation of the tcgen05 kind::i8 op lists executed by pmctf_umma_selftest, and the builder of the op list
+the lifting convolution uses (3 signed-byte digits per operand, 5 tap pairs, 5 accumulator groups).  Test infrastructure."""
+import numpy as np
+
+TAP_PAIRS = [((0, 0), (0, 1)), ((1, 0), (1, 1)), ((2, 0), (2, 1)), ((0, 2), (1, 2)), ((2, 2), None)]
+
+
+def emulate(A, B, ops, n_blocks, block_stride, out_cols):
+    """A, B: int8 byte images; ops: dicts with the pmctf_umma_op_t fields.  -> int64 [n_blocks, 128, out_cols]."""
+    A = np.asarray(A, np.int8).astype(np.int64)
+    B = np.asarray(B, np.int8).astype(np.int64)
+    out = np.zeros((n_blocks, 128, out_cols), np.int64)
+    r = np.arange(128)
+    for blk in range(n_blocks):
+        for op in ops:
+            n = op["n"]
+            arow = op["a_off"] + blk * block_stride + (r % 8) * 16 + (r // 8) * op["a_sbo"]
+            rn = np.arange(n)
+            brow = op["b_off"] + (rn % 8) * 16 + (rn // 8) * op["b_sbo"]
+            acc = np.zeros((128, n), np.int64)
+            for c in range(2):
+                a = A[(arow + c * op["a_lbo"])[:, None] + np.arange(16)[None, :]]
+                b = B[(brow + c * op["b_lbo"])[:, None] + np.arange(16)[None, :]]
+                acc += a @ b.T
+            sl = slice(op["d_col"], op["d_col"] + n)
+            out[blk, :, sl] = acc + (out[blk, :, sl] if op["accumulate"] else 0)
+    return out
+
+
+def split_digits(v):
+    """int (|v| <= 2^22) -> three signed-byte digits d0, d1, d2 with v = d0*65536 + d1*256 + d2."""
+    v = np.asarray(v, np.int64)
+    d2 = ((v + 128) & 0xFF) - 128
+    v1 = (v - d2) >> 8
+    d1 = ((v1 + 128) & 0xFF) - 128
+    d0 = (v1 - d1) >> 8
+    assert np.all(np.abs(d0) <= 127) and np.all(d0 * 65536 + d1 * 256 + d2 == v)
+    return d0.astype(np.int8), d1.astype(np.int8), d2.astype(np.int8)
+
+
+def pack_weights(W):
+    """W int [16 co, 16 ci, 3, 3] (|W| <= 2^22) -> int8 image: per tap pair a [2 chunks][48 rows = (digit, co)][16 ci] block."""
+    d = split_digits(W)
+    out = np.zeros((5, 2, 48, 16), np.int8)
+    for tp, pair in enumerate(TAP_PAIRS):
+        for c, tap in enumerate(pair):
+            if tap is None:
+                continue
+            for j in range(3):
+                out[tp, c, j * 16:(j + 1) * 16, :] = d[j][:, :, tap[0], tap[1]]
+    return out.reshape(-1)
+
+
+def conv_ops(pitch, plane_bytes):
+    """Op list of one 128-pixel block of the 16->16 3x3 convolution: D columns [16*i, 16*i+16) accumulate the
+    digit products of order i (weight 2^(32-8i)): a_d x w_e lands in group d+e."""
+    ops = []
+    for tp, (t0, t1) in enumerate(TAP_PAIRS):
+        a_off = (t0[0] * pitch + t0[1]) * 16
+        lbo = ((t1[0] * pitch + t1[1]) - (t0[0] * pitch + t0[1])) * 16 if t1 is not None else 16
+        boff = tp * 1536
+
+        def op(d, e0, ne, acc):
+            return dict(a_off=d * plane_bytes + a_off, a_lbo=lbo, a_sbo=128, b_off=boff + e0 * 256, b_lbo=768, b_sbo=128,
+                        n=16 * ne, d_col=16 * (d + e0), accumulate=acc)
+        if tp == 0:  # first touch of every accumulator group must not accumulate
+            ops += [op(0, 0, 3, 0), op(1, 0, 2, 1), op(1, 2, 1, 0), op(2, 0, 1, 1), op(2, 1, 1, 1), op(2, 2, 1, 0)]
+        else:
+            ops += [op(0, 0, 3, 1), op(1, 0, 3, 1), op(2, 0, 3, 1)]
+    return ops
+
+
+def conv_exact(Aint, Wint, pitch, n_out):
+    """Direct integer convolution on the linearised pixel array: out[m, co] = sum_{ci,ky,kx} A[m + ky*pitch + kx, ci] W[co,ci,ky,kx]."""
+    Aint = np.asarray(Aint, np.int64)
+    Wint = np.asarray(Wint, np.int64)
+    out = np.zeros((n_out, 16), np.int64)
+    for ky in range(3):
+        for kx in range(3):
+            out += Aint[ky * pitch + kx: ky * pitch + kx + n_out] @ Wint[:, :, ky, kx].T
+    return out
+
+
+def combine_orders(o):
+    """[.., 80] accumulator groups -> exact integer sum  o0*2^32 + o1*2^24 + o2*2^16 + o3*2^8 + o4."""
+    o = np.asarray(o, np.int64).reshape(o.shape[:-1] + (5, 16))
+    return sum(o[..., i, :] << (32 - 8 * i) for i in range(5))
