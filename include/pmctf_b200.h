@@ -121,6 +121,14 @@ int pmctf_set_conv_mode(int mode);
 int pmctf_get_conv_mode(void);
 /* Non-zero if a tensor-core kernel gave up waiting for an MMA (synchronises the device; for tests). */
 int pmctf_tc_error_flag(void);
+/* clock64 stamps of the phases of one CTA of the most recent tensor-core launches (profiling aid; synchronises):
+ * [0..6] start, source ready, conv1 done, conv2 done, conv3 done, conv4 done, end; [8..11] MMA issue begin/end of
+ * conv2, conv3; [12..13] cycles an epilogue warp waited for accumulators. */
+int pmctf_tc_debug_times(long long *out16);
+/* MMA throughput probe on an otherwise idle SM: issues reps x 18 kind::i8 MMAs (variant 0: the convolution's block
+ * pattern; 1/2/3: N = 16/48/96 with overlapping K chunks; 4: N = 48, disjoint K chunks) and writes
+ * {issue cycles, issue+completion cycles, #MMAs} to out3_device. */
+int pmctf_tc_mma_probe(int variant, int reps, long long *out3_device, void *stream);
 
 /* Repack one PredictUpdate's 8 tensors (OIHW, as in the state_dict) into the kernel layout.
  * Replaces nothing in the reference; run once per weight version. */

@@ -64,6 +64,8 @@ SIGNATURES = {
     "pmctf_set_conv_mode": [_I],
     "pmctf_get_conv_mode": [],
     "pmctf_tc_error_flag": [],
+    "pmctf_tc_debug_times": [_P],
+    "pmctf_tc_mma_probe": [_I, _I, _P, _P],
     "pmctf_pack_pu_weights": [_P] * 10,
     "pmctf_flow_warp": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _f, _I, _P],
     "pmctf_chroma_mv_down": [_P, _P, _I, _I, _I, _P],

@@ -556,8 +556,8 @@ static int launch_step(const StepD &d, int src_kind, cudaStream_t st)
 {
     if (g_conv_mode == PMCTF_CONV_TENSOR) {
         if (!g_tc_err) {
-            if (cudaMalloc(&g_tc_err, sizeof(int)) != cudaSuccess) return (int)cudaGetLastError();
-            cudaMemset(g_tc_err, 0, sizeof(int));
+            if (cudaMalloc(&g_tc_err, 256) != cudaSuccess) return (int)cudaGetLastError();
+            cudaMemset(g_tc_err, 0, 256);
         }
         const int e = launch_step_tc(d, src_kind, g_tc_err, st);
         if (e == 0) ++g_launches;
@@ -661,6 +661,16 @@ int pmctf_set_conv_mode(int mode)
 }
 
 int pmctf_get_conv_mode(void) { return pmctf::g_conv_mode; }
+
+int pmctf_tc_debug_times(long long *out16)
+{
+    if (!out16) return PMCTF_EINVAL;
+    for (int i = 0; i < 16; ++i) out16[i] = 0;
+    if (!pmctf::g_tc_err) return 0;
+    if (cudaMemcpy(out16, pmctf::g_tc_err + 2, 16 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return (int)cudaGetLastError();
+    cudaMemset(pmctf::g_tc_err + 2, 0, 16 * sizeof(long long));
+    return 0;
+}
 
 int pmctf_tc_error_flag(void)
 {

@@ -139,10 +139,15 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);      // full[6], empty[6]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_BAR + 96);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0); // warp-uniform for the compiler
     const int n = blockIdx.z;
     const int y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
     const int H = a.h, W = a.w;
+    // optional phase timing of CTA (1,1,0): err[2..] as long long stamps (debug / profiling aid)
+    long long *dbg = (err && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) ? reinterpret_cast<long long *>(err + 2) : nullptr;
+#define STAMP(i) do { if (dbg && tid == 0) dbg[i] = clock64(); } while (0)
+    STAMP(0);
 
     // ---- setup: parameters, barriers, TMEM ------------------------------------------------------------
     {
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
+    STAMP(1);
     const uint32_t tbase = *tmem_slot;
     if (SRC == PMCTF_SRC_SKIP3) {
         for (int i = tid; i < S_ROWS * S_COLS; i += NT) {
@@ -258,6 +264,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
     }
     umma::fence_proxy_async();
     __syncthreads();
+    STAMP(2);
 
     const uint32_t full0 = umma::smem_u32(bars), empty0 = umma::smem_u32(bars + NSLOT);
     bool ok = true;
@@ -268,21 +275,23 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
         const uint32_t a_saddr = umma::smem_u32(layer == 0 ? A1 : A2);
         const uint32_t b_saddr = umma::smem_u32(smem + SM_WB + layer * QBYTES);
         if (warp == 16) {
-            if (lane == 0) {
-                umma::fence_after_sync();
+            if (dbg && lane == 0) dbg[8 + 2 * layer] = clock64();
+            // the whole warp walks the (uniform) loop; one elected lane issues
 #pragma unroll 1
-                for (int blk = 0; blk < NBLK; ++blk) {
-                    const int slot = blk % NSLOT;
-                    if (blk >= NSLOT) { // the slot's previous accumulators must have been drained
-                        ok = umma::mbar_wait(empty0 + 8 * slot, 0u);
-                        if (!ok) break;
-                        umma::fence_after_sync();
-                    }
+            for (int blk = 0; blk < NBLK; ++blk) {
+                const int slot = blk % NSLOT;
+                if (blk >= NSLOT) { // the slot's previous accumulators must have been drained
+                    ok = __shfl_sync(0xffffffffu, (int)umma::mbar_wait(empty0 + 8 * slot, 0u), 0) != 0;
+                    if (!ok) break;
+                    umma::fence_after_sync();
+                }
+                if (umma::elect_one()) {
                     issue_block(a_saddr + blk * 2048, b_saddr, tbase + slot * SLOT_COLS);
                     umma::commit(full0 + 8 * slot);
                 }
+                __syncwarp();
             }
-            __syncwarp();
+            if (dbg && lane == 0) dbg[9 + 2 * layer] = clock64();
         } else {
             const int grp = warp >> 2, quarter = warp & 3;
             const float scale = sf[layer == 0 ? F_SC2 : F_SC3];
@@ -292,7 +301,9 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
                 const int slot = blk % NSLOT;
                 const int uses = (slot < NSLOT - 1) ? 2 : 1;
                 const uint32_t parity = (uint32_t)(layer * uses + blk / NSLOT) & 1u;
+                const long long tw = (dbg && tid == 0) ? clock64() : 0;
                 ok = umma::mbar_wait(full0 + 8 * slot, parity);
+                if (dbg && tid == 0) dbg[12 + layer] += clock64() - tw;
                 if (!ok) break;
                 umma::fence_after_sync();
                 const int m = blk * 128 + quarter * 32 + lane;
@@ -361,6 +372,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
         umma::fence_before_sync();
         __syncthreads();
         umma::fence_after_sync();
+        STAMP(3 + layer);
     }
     if (!ok && err) atomicExch(err, 1);
 
@@ -394,6 +406,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
         so[r * O_P + st * 2 + 1] = acc1;
     }
     __syncthreads();
+    STAMP(5);
 
     // ---- lifting arithmetic + stores -----------------------------------------------------------------------
     {
@@ -439,7 +452,59 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
     }
     umma::fence_before_sync();
     __syncthreads();
+    STAMP(6);
     if (warp == 16) umma::tmem_dealloc(tbase, 512);
+}
+
+// ---- timing probe: MMA throughput of the production operand layout with nothing else running on the SM ------
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int variant, int reps, long long *__restrict__ out)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tslot;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    for (int i = tid; i < (SM_BAR) / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u * (uint32_t)(i & 3);
+    if (tid == 0) {
+        umma::mbar_init(umma::smem_u32(&bar), 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(&tslot, 512);
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tbase = tslot;
+    const uint32_t a_s = umma::smem_u32(smem + SM_A1), b_s = umma::smem_u32(smem + SM_WB);
+    if (warp == 0) {
+        long long t0 = clock64();
+        int n_mma = 0;
+        for (int r = 0; r < reps; ++r) {
+            if (umma::elect_one()) {
+                if (variant == 0) {
+                    issue_block(a_s + (r % NBLK) * 2048, b_s, tbase + (r % NSLOT) * SLOT_COLS);
+                } else {
+                    const int nn = variant == 1 ? 16 : (variant == 2 ? 48 : (variant == 3 ? 96 : 48));
+                    const int lbo = variant == 4 ? 2048 : 16;
+#pragma unroll
+                    for (int i = 0; i < 18; ++i)
+                        umma::mma_s8(tbase + (r % 4) * 96, umma::smem_desc(a_s + (r % NBLK) * 2048 + i * 160, lbo, 128),
+                                     umma::smem_desc(b_s + (i % 5) * 1536, 768, 128), umma::idesc_s8(nn), 1u);
+                }
+            }
+            __syncwarp();
+            n_mma += 18;
+        }
+        if (umma::elect_one()) umma::commit(umma::smem_u32(&bar));
+        __syncwarp();
+        const long long t1 = clock64();
+        umma::mbar_wait(umma::smem_u32(&bar), 0u);
+        const long long t2 = clock64();
+        if (tid == 0) { out[0] = t1 - t0; out[1] = t2 - t0; out[2] = n_mma; }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tbase, 512);
 }
 
 } // namespace tc
@@ -470,3 +535,12 @@ int launch_step_tc(const StepD &d, int src_kind, int *err_flag, cudaStream_t st)
 }
 
 } // namespace pmctf
+
+extern "C" int pmctf_tc_mma_probe(int variant, int reps, long long *out3_device, void *stream)
+{
+    if (!out3_device || reps <= 0 || variant < 0 || variant > 4) return PMCTF_EINVAL;
+    cudaError_t e = cudaFuncSetAttribute(pmctf::tc::mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pmctf::tc::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    pmctf::tc::mma_probe_kernel<<<1, 128, pmctf::tc::SMEM_BYTES, (cudaStream_t)stream>>>(variant, reps, out3_device);
+    return (int)cudaGetLastError();
+}

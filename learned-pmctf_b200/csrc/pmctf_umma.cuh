@@ -45,6 +45,20 @@ __device__ __forceinline__ void mma_s8(uint32_t d_tmem, uint64_t adesc, uint64_t
         : "memory");
 }
 
+// one lane of a converged warp (the values feeding the MMA stay in uniform registers this way)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // all previously issued MMAs of this thread arrive on the mbarrier when they have completed
 __device__ __forceinline__ void commit(uint32_t mbar_saddr)
 {

@@ -1,0 +1,25 @@
+"""Phase timing of the tensor-core lifting step (one CTA) on a 1080p luma plane."""
+import ctypes as C, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import learned_pmctf_b200 as P
+m = P.pMCTF(num_me_stages=4).cuda().eval()
+x = torch.rand(1, 1, 1152, 1920, device="cuda") * 255
+mv = torch.randn(1, 2, 1152, 1920, device="cuda") * 3
+lib = P._native.lib()
+out = (C.c_longlong * 16)()
+for name, fn in (("temporal fwd", lambda: m.forward_MCTF(x, x, mv, 0, want_pred=False)),
+                 ("lift2d fwd", lambda: m.hp_coder.wavelet_transform.forward_lift_2d_bands(x))):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize(); lib.pmctf_tc_debug_times(out)
+    fn(); torch.cuda.synchronize(); lib.pmctf_tc_debug_times(out)
+    t = list(out)
+    print(name, "phases (cycles): setup+src %d | conv1 %d | conv2 %d | conv3 %d | conv4 %d | final %d | total %d" %
+          (t[1]-t[0], t[2]-t[1], t[3]-t[2], t[4]-t[3], t[5]-t[4], t[6]-t[5], t[6]-t[0]))
+    print("   MMA issue conv2 %d conv3 %d cycles; epilogue warp0 waited %d / %d cycles" % (t[9]-t[8], t[11]-t[10], t[12], t[13]))
+o = torch.zeros(3, dtype=torch.int64, device="cuda")
+for v, name in ((0, "conv block pattern"), (1, "N=16"), (2, "N=48"), (3, "N=96"), (4, "N=48 disjoint chunks")):
+    lib.pmctf_tc_mma_probe(v, 64, o.data_ptr(), None); torch.cuda.synchronize()
+    a, b, n = o.tolist()
+    print(f"probe {name:24s}: issue {a/n:6.1f} cyc/MMA, complete {b/n:6.1f} cyc/MMA ({n} MMAs)")
