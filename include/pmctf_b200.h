@@ -35,7 +35,7 @@ extern "C" {
 #define PMCTF_ESHAPE (-2)   /* shape not supported (odd split size, plane too small for reflection) */
 #define PMCTF_EWORKSPACE (-3) /* workspace too small */
 
-#define PMCTF_PU_PACKED_FLOATS 8848 /* size of one packed PredictUpdate weight block (fp32 taps + int8 tensor-core operands) */
+#define PMCTF_PU_PACKED_FLOATS 10128 /* size of one packed PredictUpdate weight block (fp32 taps + int8 tensor-core operands) */
 
 /* How the two 16->16 convolutions of PredictUpdate (lifting_1d.py:40-44) are evaluated (DESIGN.md "Numerics"):
  *   PMCTF_CONV_TENSOR  exact fixed-point implicit GEMM on the tcgen05 tensor cores (default)

@@ -16,7 +16,7 @@ SOURCES = [os.path.join(_HERE, "csrc", "pmctf_kernels.cu"), os.path.join(_HERE, 
 HEADERS = [os.path.join(_HERE, "csrc", "pmctf_umma.cuh"), os.path.join(_HERE, "csrc", "pmctf_common.cuh")]
 INCLUDE = os.path.join(ROOT, "include")
 
-PU_PACKED_FLOATS = 8848
+PU_PACKED_FLOATS = 10128
 CONV_FFMA, CONV_TENSOR = 0, 1
 SRC_PLANE, SRC_WARP, SRC_SKIP3 = 0, 1, 2
 MODE_ACCUM, MODE_FILTER, MODE_PU = 0, 1, 2

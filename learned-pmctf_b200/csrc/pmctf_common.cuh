@@ -4,31 +4,33 @@
 #include <stdint.h>
 
 #include "pmctf_b200.h"
+#include "pmctf_tanh_table.h"
 
 namespace pmctf {
 
 // ------------------------------------------------------------------------------------------
-// deterministic tanh (same specification as oracle/pmctf_oracle.c: IEEE +,*,fma,/,rint only)
-__device__ __forceinline__ float tanh_det(float x)
+// deterministic tanh (arithmetic contract: table include/pmctf_tanh_table.h, routine specified in
+// tools/gen_tanh_table.py, restated independently in oracle/pmctf_oracle.c): third-order expansion around the
+// nearest multiple of 1/32, derivatives from T = tanh(node); one 4-byte shared-memory lookup per evaluation
+__device__ const unsigned int g_tanh_bits[PMCTF_TANH_ENTRIES] = {PMCTF_TANH_TABLE_VALUES};
+constexpr int TANH_SMEM_BYTES = ((PMCTF_TANH_ENTRIES * 4 + 127) / 128) * 128;
+
+__device__ __forceinline__ void load_tanh_table(float *tab_smem, int tid, int nthreads)
 {
-    float ax = fminf(fabsf(x), 10.0f);
-    float z = ax + ax;
-    float kf = rintf(z * 1.44269504f);
-    float r = fmaf(kf, -0.693145752f, z);
-    r = fmaf(kf, -1.42860677e-06f, r);
-    float q = 1.98412698e-4f;
-    q = fmaf(q, r, 1.38888889e-3f);
-    q = fmaf(q, r, 8.33333333e-3f);
-    q = fmaf(q, r, 4.16666667e-2f);
-    q = fmaf(q, r, 1.66666667e-1f);
-    q = fmaf(q, r, 0.5f);
-    float r2 = r * r;
-    float p = fmaf(q, r2, r);
-    int k = (int)kf;
-    float s = __int_as_float((k + 127) << 23);
-    float em1 = fmaf(s, p, s - 1.0f);
-    float t = em1 / (em1 + 2.0f);
-    return copysignf(t, x);
+    for (int i = tid; i < PMCTF_TANH_ENTRIES; i += nthreads) tab_smem[i] = __uint_as_float(g_tanh_bits[i]);
+}
+
+__device__ __forceinline__ float tanh_det(float x, const float *__restrict__ tab)
+{
+    const float ax = fminf(fabsf(x), PMCTF_TANH_XMAX);
+    const float fi = rintf(ax * 32.0f);
+    const float d = fmaf(fi, -0.03125f, ax);
+    const float T = tab[(int)fi];
+    const float D1 = fmaf(-T, T, 1.0f);
+    const float D2 = -(T * D1);
+    const float D3 = (D1 * fmaf(-3.0f * T, T, 1.0f)) * -0.333333343f;
+    const float y = fmaf(fmaf(fmaf(D3, d, D2), d, D1), d, T);
+    return copysignf(y, x);
 }
 
 struct PlaneD {

@@ -43,10 +43,10 @@ constexpr int B3_OFF = 4784;
 constexpr int W4_OFF = 4800;   // [16 ci][12] (9 used)
 constexpr int B4_OFF = 4992;
 constexpr int WPACK = 5000;        // fp32 part of the packed block
-constexpr int Q_OFF = 5000;        // int8 tensor-core operand images of conv2 / conv3 (2 x 7680 bytes)
-constexpr int QBYTES = 7680;
-constexpr int SC_OFF = 8840;       // 2^-(22+Sw) of conv2, conv3
-static_assert(PMCTF_PU_PACKED_FLOATS == 8848 && SC_OFF + 8 == PMCTF_PU_PACKED_FLOATS, "header and kernel disagree on the packed size");
+constexpr int Q_OFF = 5000;        // int8 tensor-core operand images of conv2 / conv3 (2 x 10240 bytes)
+constexpr int QBYTES = 10240;      // 5 tap pairs x 1536 B, then the 80-row (zero padded) image of tap pair 0 at +7680
+constexpr int SC_OFF = 10120;      // 2^-(22+Sw) of conv2, conv3
+static_assert(PMCTF_PU_PACKED_FLOATS == 10128 && SC_OFF + 8 == PMCTF_PU_PACKED_FLOATS, "header and kernel disagree on the packed size");
 
 // shared memory carve-up (floats)
 constexpr int SM_W = 0;
@@ -55,8 +55,9 @@ constexpr int SM_T = SM_S + S_ROWS * S_P;          // + 1640
 constexpr int SM_A1 = SM_T + 1724;                 // T tile 42*41 = 1722, padded for 16 B alignment
 constexpr int SM_A2 = SM_A1 + 16 * A1_ROWS * A1_P; // + 24320
 constexpr int SM_END = SM_A2 + 16 * A2_ROWS * A2_P;
-constexpr int SMEM_BYTES = SM_END * 4;
-static_assert((SM_A1 * 4) % 16 == 0 && (SM_A2 * 4) % 16 == 0, "activation planes must be 16 B aligned");
+constexpr int SM_TANH_B = SM_END * 4;              // byte offset of the tanh table
+constexpr int SMEM_BYTES = SM_TANH_B + TANH_SMEM_BYTES;
+static_assert(SM_TANH_B % 16 == 0 && (SM_A1 * 4) % 16 == 0 && (SM_A2 * 4) % 16 == 0, "activation planes must be 16 B aligned");
 static_assert(16 * A3_ROWS * A3_P <= 16 * A1_ROWS * A1_P, "a3 aliases a1");
 static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit the 227 KB per-CTA limit");
 
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_kernel(const __grid_constant_
     float *a2 = smem + SM_A2;
     float *a3 = a1;   // a1 is dead once conv2 has been computed
     float *so = a2;   // a2 is dead once conv3 has been computed
+    const float *ttab = reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(smem) + SM_TANH_B);
 
     const int tid = threadIdx.x;
     const int n = blockIdx.z;
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_kernel(const __grid_constant_
         const float4 *g = reinterpret_cast<const float4 *>(a.pu_packed);
         float4 *d = reinterpret_cast<float4 *>(sw);
         for (int i = tid; i < WPACK / 4; i += NT) d[i] = __ldg(g + i);
+        load_tanh_table(reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(smem) + SM_TANH_B), tid, NT);
     }
     const bool xfast_src = a.src.cs <= a.src.rs;
     if (SRC == PMCTF_SRC_PLANE || SRC == PMCTF_SRC_SKIP3) {
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_kernel(const __grid_constant_
                     acc0 = fmaf(wv.x, v, acc0); acc1 = fmaf(wv.y, v, acc1);
                     acc2 = fmaf(wv.z, v, acc2); acc3 = fmaf(wv.w, v, acc3);
                 }
-                o = make_float4(tanh_det(acc0), tanh_det(acc1), tanh_det(acc2), tanh_det(acc3));
+                o = make_float4(tanh_det(acc0, ttab), tanh_det(acc1, ttab), tanh_det(acc2, ttab), tanh_det(acc3, ttab));
             }
             float *d = a1 + (cq * 4) * (A1_ROWS * A1_P) + r * A1_P + c;
             d[0] = o.x; d[A1_ROWS * A1_P] = o.y; d[2 * A1_ROWS * A1_P] = o.z; d[3 * A1_ROWS * A1_P] = o.w;
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_kernel(const __grid_constant_
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     const int gx = x0 - 2 + st * 4 + p;
-                    v[p] = (rowin && gx >= 0 && gx < W) ? tanh_det(acc[co][p]) : 0.0f;
+                    v[p] = (rowin && gx >= 0 && gx < W) ? tanh_det(acc[co][p], ttab) : 0.0f;
                 }
                 *reinterpret_cast<float4 *>(a2 + (cg * 8 + co) * (A2_ROWS * A2_P) + r * A2_P + st * 4) =
                     make_float4(v[0], v[1], v[2], v[3]);
@@ -534,6 +537,10 @@ __global__ void __launch_bounds__(512) pack_pu_kernel(const float *w1, const flo
             const int d0 = (V1 - d1) >> 8;
             int8_t *o = img + layer * QBYTES + tp * 1536 + chunk * 768 + co * 16 + ci;
             o[0] = (int8_t)d0; o[256] = (int8_t)d1; o[512] = (int8_t)d2;
+            if (tp == 0) { // 80-row copy: [chunk][80 rows][16], rows 48..79 zero
+                int8_t *z = img + layer * QBYTES + 7680 + chunk * 1280 + co * 16 + ci;
+                z[0] = (int8_t)d0; z[256] = (int8_t)d1; z[512] = (int8_t)d2; z[768] = 0; z[1024] = 0;
+            }
         }
         __syncthreads();
     }
@@ -556,8 +563,9 @@ static int launch_step(const StepD &d, int src_kind, cudaStream_t st)
 {
     if (g_conv_mode == PMCTF_CONV_TENSOR) {
         if (!g_tc_err) {
-            if (cudaMalloc(&g_tc_err, 256) != cudaSuccess) return (int)cudaGetLastError();
-            cudaMemset(g_tc_err, 0, 256);
+            // [0] error flag, [2..33] phase stamps, [64..319] per-SM arrival counters of the tensor-core kernel
+            if (cudaMalloc(&g_tc_err, 2048) != cudaSuccess) return (int)cudaGetLastError();
+            cudaMemset(g_tc_err, 0, 2048);
         }
         const int e = launch_step_tc(d, src_kind, g_tc_err, st);
         if (e == 0) ++g_launches;

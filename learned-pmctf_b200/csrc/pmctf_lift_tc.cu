@@ -14,9 +14,10 @@
 //     S = sum_k o_k 2^(32-8k) = sum A*W exactly -- independent of the tensor core's summation order;
 //   * conv = fma((float)S, 2^-(22+Sw), bias): one rounding.  oracle/pmctf_oracle.c states the same contract.
 //
-// CTA = one 32x32 output tile, 17 warps: warps 0-15 are four epilogue groups (a warp reads TMEM lanes
-// 32*(warp%4)..+31), warp 16 issues the MMAs; 6 accumulator slots of 80 TMEM columns pipeline MMA and epilogue
-// through full/empty mbarriers.
+// CTA = one 16x32 output tile, 9 warps: warps 0-7 are two epilogue groups (a warp reads TMEM lanes
+// 32*(warp%4)..+31), warp 8 issues the MMAs; 3 accumulator slots of 80 TMEM columns pipeline MMA and epilogue
+// through full/empty mbarriers.  Two CTAs are resident per SM (105 KB shared memory, 256 TMEM columns each), so
+// the CUDA-core phases of one tile overlap the tensor-core phases of the other.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -27,42 +28,48 @@
 namespace pmctf {
 namespace tc {
 
-constexpr int TH = 32, TW = 32;
+constexpr int TH = 16, TW = 32;                      // output tile; two CTAs share an SM (smem <= 113 KB, 256 TMEM columns each)
 constexpr int P = 38;                                // pixel pitch of the digit arrays (= conv1 output width)
-constexpr int NBLK = 11;                             // 128-pixel blocks per layer (conv2: 36*38 px, conv3: 34*38-4 px)
-constexpr int NPIX = 1488;                           // >= 10*128 + 127 + 2*P + 2 + 1
+constexpr int NBLK = 6;                              // 128-pixel blocks per layer (conv2: 20 rows x 38, conv3: 18 rows x 38)
+constexpr int NPIX = 848;                            // >= (NBLK-1)*128 + 127 + 2*P + 2 + 1
 constexpr int PLANE = NPIX * 16;                     // bytes of one digit plane
 constexpr int S_ROWS = TH + 8, S_COLS = TW + 8, S_P = 41;
 constexpr int T_ROWS = TH + 10, T_P = 41;
-constexpr int A1_N = TH + 6, A2_N = TH + 4, A3_N = TH + 2, A3_P = 36;
+constexpr int A1_R = TH + 6, A1_C = TW + 6;          // tanh(conv1): origin (-3,-3)
+constexpr int A2_R = TH + 4, A2_C = TW + 4;          // tanh(conv2): origin (-2,-2)
+constexpr int A3_R = TH + 2, A3_C = TW + 2, A3_P = 36; // conv1 + conv3: origin (-1,-1), fp32 planar
 constexpr int O_P = 33;
-constexpr int NSLOT = 6, SLOT_COLS = 80;
-static_assert(A1_N == P && A1_N * P <= NPIX, "pitch");
+constexpr int NSLOT = 3, SLOT_COLS = 80, TMEM_COLS = 256;
+constexpr int NGRP = 2;                              // epilogue groups of 4 warps
+static_assert(A1_C == P && A1_R * P <= NPIX, "pitch");
 static_assert((NBLK - 1) * 128 + 127 + 2 * P + 2 < NPIX, "operand reads stay inside the plane");
-static_assert(NBLK * 128 >= (A2_N - 1) * P + A2_N && NBLK * 128 >= (A3_N - 1) * P + A3_N, "blocks cover the layer outputs");
+static_assert(NBLK * 128 >= (A2_R - 1) * P + A2_C && NBLK * 128 >= (A3_R - 1) * P + A3_C, "blocks cover the layer outputs");
+static_assert(NBLK == 2 * NSLOT && NSLOT * SLOT_COLS <= TMEM_COLS, "every accumulator slot is used exactly twice per layer");
 
 // packed parameter block (floats, see pack_pu_kernel)
 constexpr int W1_OFF = 0, B1_OFF = 144, B2_OFF = 2464, B3_OFF = 4784, W4_OFF = 4800, B4_OFF = 4992;
-constexpr int Q_OFF = 5000, QBYTES = 7680, SC_OFF = 8840;
-static_assert(PMCTF_PU_PACKED_FLOATS == 8848, "header and kernel disagree on the packed size");
+constexpr int Q_OFF = 5000, QBYTES = 10240, Q0_OFF = 7680, SC_OFF = 10120; // Q0: 80-row image of tap pair 0
+static_assert(PMCTF_PU_PACKED_FLOATS == 10128, "header and kernel disagree on the packed size");
 
 // shared memory (bytes)
-constexpr int SM_WB = 0;                              // 2 x 7680 B operand images
+constexpr int SM_WB = 0;                              // 2 x 10240 B operand images
 constexpr int SM_F = SM_WB + 2 * QBYTES;              // fp32 parameters
 constexpr int F_W1 = 0, F_B1 = 144, F_B2 = 160, F_B3 = 176, F_W4 = 192, F_B4 = 384, F_SC2 = 385, F_SC3 = 386;
 constexpr int SM_S = SM_F + 1664;
-constexpr int SM_T = SM_S + 6656;
-constexpr int SM_A1 = SM_T + 6912;
-constexpr int A1_BYTES = 16 * A3_N * A3_P * 4;        // a3 (fp32, conv4 input) aliases the A1 digit planes
-static_assert(A1_BYTES >= 3 * PLANE && A1_BYTES % 128 == 0, "a3 alias");
+constexpr int SM_T = SM_S + ((S_ROWS * S_P * 4 + 127) / 128) * 128;
+constexpr int SM_A1 = SM_T + ((T_ROWS * T_P * 4 + 127) / 128) * 128;
+constexpr int A3_BYTES = 16 * A3_R * A3_P * 4;        // a3 (fp32, conv4 input) aliases the A1 digit planes
+constexpr int A1_BYTES = ((A3_BYTES > 3 * PLANE ? A3_BYTES : 3 * PLANE) + 127) / 128 * 128;
 constexpr int SM_A2 = SM_A1 + A1_BYTES;
-constexpr int SM_BAR = SM_A2 + 3 * PLANE;
+constexpr int SM_TANH = SM_A2 + 3 * PLANE;
+constexpr int SM_BAR = SM_TANH + TANH_SMEM_BYTES;
 constexpr int SMEM_BYTES = SM_BAR + 128;
 static_assert(SM_S % 128 == 0 && SM_T % 128 == 0 && SM_A1 % 128 == 0 && SM_A2 % 128 == 0 && SM_BAR % 128 == 0, "alignment");
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 
-constexpr int NT = 544;       // 16 epilogue warps + 1 MMA warp
-constexpr int NEPI = 512;
+constexpr long long STAGGER_CYCLES = 11000;
+constexpr int MMA_WARP = 4 * NGRP;
+constexpr int NT = 32 * (MMA_WARP + 1);   // 8 epilogue warps + 1 MMA warp
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
@@ -77,8 +84,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
                  : "memory");
 }
 
-// the 18 MMAs of one 128-pixel block: digit d of the activations times weight digits e0..e0+ne-1 lands in
-// accumulator groups d+e0.. (tests/umma_ref.py:conv_ops is the executable specification of this list)
+// the 15 MMAs of one 128-pixel block: activation digit d times the stacked weight digits [w0; w1; w2] (N = 48)
+// lands in accumulator groups d, d+1, d+2.  The very first MMA uses the 80-row image of tap pair 0 (rows 48..79
+// are zero) with accumulate = 0, which initialises all five groups at once.
 __device__ __forceinline__ void issue_block(uint32_t a_saddr, uint32_t b_saddr, uint32_t d_tmem)
 {
 #pragma unroll
@@ -89,44 +97,37 @@ __device__ __forceinline__ void issue_block(uint32_t a_saddr, uint32_t b_saddr, 
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             const uint64_t ad = umma::smem_desc(a_saddr + d * PLANE + t0 * 16, lbo, 128);
-            if (tp == 0 && d > 0) {
-                // first touch of groups 3 and 4 must not accumulate: split the N = 48 MMA
-                umma::mma_s8(d_tmem + 16 * d, ad, umma::smem_desc(b, 768, 128), umma::idesc_s8(16 * (3 - d)), 1u);
-                if (d == 1) {
-                    umma::mma_s8(d_tmem + 48, ad, umma::smem_desc(b + 512, 768, 128), umma::idesc_s8(16), 0u);
-                } else {
-                    umma::mma_s8(d_tmem + 48, ad, umma::smem_desc(b + 256, 768, 128), umma::idesc_s8(16), 1u);
-                    umma::mma_s8(d_tmem + 64, ad, umma::smem_desc(b + 512, 768, 128), umma::idesc_s8(16), 0u);
-                }
-            } else {
-                umma::mma_s8(d_tmem + 16 * d, ad, umma::smem_desc(b, 768, 128), umma::idesc_s8(48), (tp == 0) ? 0u : 1u);
-            }
+            if (tp == 0 && d == 0)
+                umma::mma_s8(d_tmem, ad, umma::smem_desc(b_saddr + Q0_OFF, 1280, 128), umma::idesc_s8(80), 0u);
+            else
+                umma::mma_s8(d_tmem + 16 * d, ad, umma::smem_desc(b, 768, 128), umma::idesc_s8(48), 1u);
         }
     }
 }
 
-// exact integer dot product from the five accumulator groups, rounded once to fp32
+// exact integer dot product S = o0*2^32 + (o1*256 + o2)*2^16 + (o3*256 + o4) from the five accumulator groups
+// (64-bit integer arithmetic), rounded once to fp32.  (An fp64 formulation was measured 15 % slower on B200.)
 __device__ __forceinline__ float combine(uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3, uint32_t o4)
 {
     const long long S = ((long long)(int)o0 << 32) + (long long)((int)o1 * 256 + (int)o2) * 65536 + (long long)((int)o3 * 256 + (int)o4);
     return (float)S;
 }
 
-// V = rint(a * 2^22) -> three signed-byte digits, appended to the byte lanes of w0/w1/w2
-__device__ __forceinline__ void push_digits(float a, int lane_byte, uint32_t &w0, uint32_t &w1, uint32_t &w2)
+// V = rint(a * 2^22) of four channels -> the three signed-byte digit words (V = d0*2^16 + d1*2^8 + d2 with
+// d2 = (int8)V, V1 = (V + 128) >> 8, d1 = (int8)V1, d0 = (V1 + 128) >> 8), channel q in byte q of each word
+__device__ __forceinline__ void push_digits4(float a0, float a1, float a2, float a3, uint32_t &w0, uint32_t &w1, uint32_t &w2)
 {
-    const int V = __float2int_rn(a * 4194304.0f);
-    const int d2 = (int)(signed char)(V & 0xFF);
-    const int V1 = (V - d2) >> 8;
-    const int d1 = (int)(signed char)(V1 & 0xFF);
-    const int d0 = (V1 - d1) >> 8;
-    w0 |= (uint32_t)(d0 & 0xFF) << (8 * lane_byte);
-    w1 |= (uint32_t)(d1 & 0xFF) << (8 * lane_byte);
-    w2 |= (uint32_t)(d2 & 0xFF) << (8 * lane_byte);
+    const int Va = __float2int_rn(a0 * 4194304.0f), Vb = __float2int_rn(a1 * 4194304.0f);
+    const int Vc = __float2int_rn(a2 * 4194304.0f), Vd = __float2int_rn(a3 * 4194304.0f);
+    const int Va1 = (Va + 128) >> 8, Vb1 = (Vb + 128) >> 8, Vc1 = (Vc + 128) >> 8, Vd1 = (Vd + 128) >> 8;
+    const int Va2 = (Va1 + 128) >> 8, Vb2 = (Vb1 + 128) >> 8, Vc2 = (Vc1 + 128) >> 8, Vd2 = (Vd1 + 128) >> 8;
+    w2 = __byte_perm(__byte_perm(Va, Vb, 0x0040), __byte_perm(Vc, Vd, 0x0040), 0x5410);
+    w1 = __byte_perm(__byte_perm(Va1, Vb1, 0x0040), __byte_perm(Vc1, Vd1, 0x0040), 0x5410);
+    w0 = __byte_perm(__byte_perm(Va2, Vb2, 0x0040), __byte_perm(Vc2, Vd2, 0x0040), 0x5410);
 }
 
 template <int SRC>
-__global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_constant__ StepD a, int *__restrict__ err)
+__global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_constant__ StepD a, int *__restrict__ err)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     float *sf = reinterpret_cast<float *>(smem + SM_F);
@@ -136,24 +137,28 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
     uint8_t *A2 = smem + SM_A2;
     float *a3 = reinterpret_cast<float *>(smem + SM_A1);
     float *so = reinterpret_cast<float *>(smem + SM_A2);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);      // full[6], empty[6]
+    float *ttab = reinterpret_cast<float *>(smem + SM_TANH);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);      // full[NSLOT], empty[NSLOT]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_BAR + 96);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0); // warp-uniform for the compiler
-    const int n = blockIdx.z;
-    const int y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
     const int H = a.h, W = a.w;
-    // optional phase timing of CTA (1,1,0): err[2..] as long long stamps (debug / profiling aid)
-    long long *dbg = (err && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) ? reinterpret_cast<long long *>(err + 2) : nullptr;
+    const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+    const int n_tiles = tiles_x * tiles_y * a.n;
+    // optional phase timing of the 5th tile (or the only one) of CTA 1: err[2..] as long long stamps (profiling aid)
+    long long *dbg_cta = (err && blockIdx.x == 1) ? reinterpret_cast<long long *>(err + 2) : nullptr;
+    long long *dbg = nullptr;
+    const long long t_cta0 = clock64();
+    int tiles_done = 0;
 #define STAMP(i) do { if (dbg && tid == 0) dbg[i] = clock64(); } while (0)
-    STAMP(0);
 
     // ---- setup: parameters, barriers, TMEM ------------------------------------------------------------
     {
         const int4 *g = reinterpret_cast<const int4 *>(a.pu_packed + Q_OFF);
         int4 *d = reinterpret_cast<int4 *>(smem + SM_WB);
         for (int i = tid; i < 2 * QBYTES / 16; i += NT) d[i] = __ldg(g + i);
+        load_tanh_table(ttab, tid, NT);
         for (int i = tid; i < 144 + 16; i += NT) sf[F_W1 + i] = __ldg(a.pu_packed + W1_OFF + i);
         if (tid < 16) {
             sf[F_B2 + tid] = __ldg(a.pu_packed + B2_OFF + tid);
@@ -170,49 +175,104 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
             }
             umma::fence_mbar_init();
         }
-        if (warp == 16) umma::tmem_alloc(tmem_slot, 512);
+        if (warp == MMA_WARP) umma::tmem_alloc(tmem_slot, TMEM_COLS);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t full0 = umma::smem_u32(bars), empty0 = umma::smem_u32(bars + NSLOT);
+    bool ok = true;
+    const bool xfast_src = a.src.cs <= a.src.rs;
+
+    // Two CTAs share an SM.  Launched together they would run in lockstep (both on the CUDA cores, then both on the
+    // tensor core); the second CTA to arrive on an SM therefore starts half a tile period late, so that one CTA's
+    // CUDA-core phases overlap the other's tensor-core phases for the rest of the persistent loop.
+    if (err && n_tiles > (int)gridDim.x) {
+        if (tid == 0) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const int order = atomicAdd(err + 64 + (smid & 255), 1);
+            if (order & 1) {
+                const long long t0 = clock64();
+                while (clock64() - t0 < STAGGER_CYCLES) { }
+            }
+        }
+        __syncthreads();
     }
 
+    // ---- persistent loop over tiles: every accumulator slot completes exactly twice per layer, so the mbarrier
+    //      parities are the same for every tile ------------------------------------------------------------------
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int n = tile / (tiles_x * tiles_y);
+    const int trem = tile - n * (tiles_x * tiles_y);
+    const int ty = trem / tiles_x;
+    const int y0 = ty * TH, x0 = (trem - ty * tiles_x) * TW;
+    dbg = (tiles_done == 4 || n_tiles <= (int)gridDim.x * 4) ? dbg_cta : nullptr;
+    if (dbg && tid == 0) dbg[12] = dbg[13] = 0;
+    STAMP(0);
+
     // ---- source tile ------------------------------------------------------------------------------------
-    const bool xfast_src = a.src.cs <= a.src.rs;
     if (SRC == PMCTF_SRC_PLANE || SRC == PMCTF_SRC_SKIP3) {
         constexpr int ROWS = (SRC == PMCTF_SRC_SKIP3) ? T_ROWS : S_ROWS;
         constexpr int ROFF = (SRC == PMCTF_SRC_SKIP3) ? 5 : 4;
         float *dst = (SRC == PMCTF_SRC_SKIP3) ? stile : ss;
         const float *sp = a.src.p + plane_off(a.src, n);
         const bool dodiv = (a.src_div1 != 1.0f) || (a.src_div2 != 1.0f);
-        for (int i = tid; i < ROWS * S_COLS; i += NT) {
+        constexpr int NIT = (ROWS * S_COLS + NT - 1) / NT;   // fixed trip count: all loads of a thread are in flight together
+        float v[NIT];
+#pragma unroll
+        for (int k = 0; k < NIT; ++k) {
+            const int i = tid + k * NT;
             int r, c;
             if (xfast_src) { r = i / S_COLS; c = i - r * S_COLS; }
             else { c = i / ROWS; r = i - c * ROWS; }
             const int gy = y0 - ROFF + r, gx = x0 - 4 + c;
-            float v = 0.0f;
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                v = __ldg(sp + (long long)gy * a.src.rs + (long long)gx * a.src.cs);
-                if (dodiv) v = (v / a.src_div1) / a.src_div2;
-            }
-            dst[r * S_P + c] = v;
+            v[k] = 0.0f;
+            if (i < ROWS * S_COLS && gy >= 0 && gy < H && gx >= 0 && gx < W)
+                v[k] = __ldg(sp + (long long)gy * a.src.rs + (long long)gx * a.src.cs);
+        }
+#pragma unroll
+        for (int k = 0; k < NIT; ++k) {
+            const int i = tid + k * NT;
+            int r, c;
+            if (xfast_src) { r = i / S_COLS; c = i - r * S_COLS; }
+            else { c = i / ROWS; r = i - c * ROWS; }
+            if (i < ROWS * S_COLS) dst[r * S_P + c] = dodiv ? (v[k] / a.src_div1) / a.src_div2 : v[k];
         }
     } else {
         const float *sp = a.src.p + plane_off(a.src, n);
-        for (int i = tid; i < S_ROWS * S_COLS; i += NT) {
+        constexpr int NIT = (S_ROWS * S_COLS + NT - 1) / NT;
+        float fx[NIT], fy[NIT], lx[NIT], ly[NIT];
+        bool in[NIT];
+#pragma unroll
+        for (int k = 0; k < NIT; ++k) {   // motion vectors and grid tables of all items first ...
+            const int i = tid + k * NT;
             const int r = i / S_COLS, c = i - r * S_COLS;
             const int gy = y0 - 4 + r, gx = x0 - 4 + c;
+            in[k] = i < S_ROWS * S_COLS && gy >= 0 && gy < H && gx >= 0 && gx < W;
+            fx[k] = fy[k] = lx[k] = ly[k] = 0.0f;
+            if (in[k]) {
+                load_mv(a.mv, a.mv_share, a.mv_down, a.mv_h, a.mv_w, n, gy, gx, a.mv_sign, fx[k], fy[k]);
+                lx[k] = __ldg(a.lin_x + gx);
+                ly[k] = __ldg(a.lin_y + gy);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NIT; ++k) {   // ... then the gathers
+            const int i = tid + k * NT;
+            const int r = i / S_COLS, c = i - r * S_COLS;
             float v = 0.0f;
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                float fx, fy;
-                load_mv(a.mv, a.mv_share, a.mv_down, a.mv_h, a.mv_w, n, gy, gx, a.mv_sign, fx, fy);
-                v = warp_sample(sp, a.src.rs, a.src.cs, H, W, __ldg(a.lin_x + gx), __ldg(a.lin_y + gy), fx, fy, a.sx, a.sy);
+            if (in[k]) {
+                v = warp_sample(sp, a.src.rs, a.src.cs, H, W, lx[k], ly[k], fx[k], fy[k], a.sx, a.sy);
                 if (a.round_src) v = rintf(v);
             }
-            ss[r * S_P + c] = v;
+            if (i < S_ROWS * S_COLS) ss[r * S_P + c] = v;
         }
     }
-    umma::fence_before_sync();
     __syncthreads();
-    umma::fence_after_sync();
     STAMP(1);
-    const uint32_t tbase = *tmem_slot;
     if (SRC == PMCTF_SRC_SKIP3) {
         for (int i = tid; i < S_ROWS * S_COLS; i += NT) {
             const int r = i / S_COLS, c = i - r * S_COLS;
@@ -234,27 +294,28 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
 
     // ---- conv1 (1 -> 16) + tanh -> digits of A1 (origin (-3,-3), pitch 38) -------------------------------
     {
+        // item = (pixel, channel quarter); NT % 4 == 0, so a thread keeps its quarter: weights live in registers
         const float in_mul = a.in_mul;
-        for (int it = tid; it < 4 * A1_N * A1_N; it += NT) {
-            const int px = it >> 2, cq = it & 3;
+        const int cq = tid & 3;
+        float4 wv[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wv[k] = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + cq * 4);
+        const float4 b = *reinterpret_cast<const float4 *>(sf + F_B1 + cq * 4);
+        for (int it = tid; it < 4 * A1_R * A1_C; it += NT) {
+            const int px = it >> 2;
             const int r = px / P, c = px - r * P;
             const int gy = y0 - 3 + r, gx = x0 - 3 + c;
             uint32_t w0 = 0, w1 = 0, w2 = 0;
             if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                const float4 b = *reinterpret_cast<const float4 *>(sf + F_B1 + cq * 4);
                 float acc0 = b.x, acc1 = b.y, acc2 = b.z, acc3 = b.w;
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
                     const int ky = k / 3, kx = k - ky * 3;
                     const float v = ss[(r + ky) * S_P + c + kx] * in_mul;
-                    const float4 wv = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + cq * 4);
-                    acc0 = fmaf(wv.x, v, acc0); acc1 = fmaf(wv.y, v, acc1);
-                    acc2 = fmaf(wv.z, v, acc2); acc3 = fmaf(wv.w, v, acc3);
+                    acc0 = fmaf(wv[k].x, v, acc0); acc1 = fmaf(wv[k].y, v, acc1);
+                    acc2 = fmaf(wv[k].z, v, acc2); acc3 = fmaf(wv[k].w, v, acc3);
                 }
-                push_digits(tanh_det(acc0), 0, w0, w1, w2);
-                push_digits(tanh_det(acc1), 1, w0, w1, w2);
-                push_digits(tanh_det(acc2), 2, w0, w1, w2);
-                push_digits(tanh_det(acc3), 3, w0, w1, w2);
+                push_digits4(tanh_det(acc0, ttab), tanh_det(acc1, ttab), tanh_det(acc2, ttab), tanh_det(acc3, ttab), w0, w1, w2);
             }
             uint8_t *d = A1 + px * 16 + cq * 4;
             *reinterpret_cast<uint32_t *>(d) = w0;
@@ -266,21 +327,18 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
     __syncthreads();
     STAMP(2);
 
-    const uint32_t full0 = umma::smem_u32(bars), empty0 = umma::smem_u32(bars + NSLOT);
-    bool ok = true;
-
     // ---- conv2 / conv3 on the tensor core ---------------------------------------------------------------
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
         const uint32_t a_saddr = umma::smem_u32(layer == 0 ? A1 : A2);
         const uint32_t b_saddr = umma::smem_u32(smem + SM_WB + layer * QBYTES);
-        if (warp == 16) {
+        if (warp == MMA_WARP) {
             if (dbg && lane == 0) dbg[8 + 2 * layer] = clock64();
             // the whole warp walks the (uniform) loop; one elected lane issues
 #pragma unroll 1
             for (int blk = 0; blk < NBLK; ++blk) {
                 const int slot = blk % NSLOT;
-                if (blk >= NSLOT) { // the slot's previous accumulators must have been drained
+                if (blk >= NSLOT) { // the slot's previous accumulators (drain 2*layer of this slot) must be gone
                     ok = __shfl_sync(0xffffffffu, (int)umma::mbar_wait(empty0 + 8 * slot, 0u), 0) != 0;
                     if (!ok) break;
                     umma::fence_after_sync();
@@ -297,10 +355,9 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
             const float scale = sf[layer == 0 ? F_SC2 : F_SC3];
             const float *bias = sf + (layer == 0 ? F_B2 : F_B3);
 #pragma unroll 1
-            for (int blk = grp; blk < NBLK; blk += 4) {
+            for (int blk = grp; blk < NBLK; blk += NGRP) {
                 const int slot = blk % NSLOT;
-                const int uses = (slot < NSLOT - 1) ? 2 : 1;
-                const uint32_t parity = (uint32_t)(layer * uses + blk / NSLOT) & 1u;
+                const uint32_t parity = (uint32_t)(blk / NSLOT) & 1u; // completion 2*layer + blk/NSLOT of this slot
                 const long long tw = (dbg && tid == 0) ? clock64() : 0;
                 ok = umma::mbar_wait(full0 + 8 * slot, parity);
                 if (dbg && tid == 0) dbg[12 + layer] += clock64() - tw;
@@ -311,7 +368,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
                 const uint32_t taddr = tbase + ((uint32_t)(quarter * 32) << 16) + slot * SLOT_COLS;
                 if (layer == 0) {
                     const int gy = y0 - 2 + r, gx = x0 - 2 + c;
-                    const bool valid = r < A2_N && c < A2_N && gy >= 0 && gy < H && gx >= 0 && gx < W;
+                    const bool valid = r < A2_R && c < A2_C && gy >= 0 && gy < H && gx >= 0 && gx < W;
                     uint32_t w[3][4];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -323,12 +380,15 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
                         for (int j = 0; j < 2; ++j) {
                             uint32_t w0 = 0, w1 = 0, w2 = 0;
                             if (valid) {
+                                const float4 bv = *reinterpret_cast<const float4 *>(bias + 8 * h + 4 * j);
+                                const float bq[4] = {bv.x, bv.y, bv.z, bv.w};
+                                float t[4];
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     const int ch = 4 * j + q;
-                                    const float v = fmaf(combine(o[0][ch], o[1][ch], o[2][ch], o[3][ch], o[4][ch]), scale, bias[8 * h + ch]);
-                                    push_digits(tanh_det(v), q, w0, w1, w2);
+                                    t[q] = tanh_det(fmaf(combine(o[0][ch], o[1][ch], o[2][ch], o[3][ch], o[4][ch]), scale, bq[q]), ttab);
                                 }
+                                push_digits4(t[0], t[1], t[2], t[3], w0, w1, w2);
                             }
                             w[0][2 * h + j] = w0; w[1][2 * h + j] = w1; w[2][2 * h + j] = w2;
                         }
@@ -341,7 +401,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
                         *reinterpret_cast<uint4 *>(d + k * PLANE) = make_uint4(w[k][0], w[k][1], w[k][2], w[k][3]);
                 } else {
                     const int gy = y0 - 1 + r, gx = x0 - 1 + c;
-                    const bool inside = r < A3_N && c < A3_N;
+                    const bool inside = r < A3_R && c < A3_C;
                     const bool valid = inside && gy >= 0 && gy < H && gx >= 0 && gx < W;
                     const float in_mul = a.in_mul;
                     float sv[9];
@@ -353,14 +413,27 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
 #pragma unroll
                         for (int k = 0; k < 5; ++k) tmem_ld8(taddr + 16 * k + 8 * h, o[k]);
                         umma::tmem_ld_wait();
+                        // conv1 at this position, the identical fma chains (lifting_1d.py:45 residual), 8 channels
+                        float c1[8];
+                        {
+                            const float4 b0 = *reinterpret_cast<const float4 *>(sf + F_B1 + 8 * h);
+                            const float4 b1 = *reinterpret_cast<const float4 *>(sf + F_B1 + 8 * h + 4);
+                            c1[0] = b0.x; c1[1] = b0.y; c1[2] = b0.z; c1[3] = b0.w; c1[4] = b1.x; c1[5] = b1.y; c1[6] = b1.z; c1[7] = b1.w;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) {
+                            const float4 u0 = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + 8 * h);
+                            const float4 u1 = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + 8 * h + 4);
+                            c1[0] = fmaf(u0.x, sv[k], c1[0]); c1[1] = fmaf(u0.y, sv[k], c1[1]); c1[2] = fmaf(u0.z, sv[k], c1[2]);
+                            c1[3] = fmaf(u0.w, sv[k], c1[3]); c1[4] = fmaf(u1.x, sv[k], c1[4]); c1[5] = fmaf(u1.y, sv[k], c1[5]);
+                            c1[6] = fmaf(u1.z, sv[k], c1[6]); c1[7] = fmaf(u1.w, sv[k], c1[7]);
+                        }
+                        const float4 bv0 = *reinterpret_cast<const float4 *>(bias + 8 * h), bv1 = *reinterpret_cast<const float4 *>(bias + 8 * h + 4);
+                        const float bq[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
 #pragma unroll
                         for (int ch = 0; ch < 8; ++ch) {
-                            // conv1 at this position, the identical fma chain (lifting_1d.py:45 residual)
-                            float c1 = sf[F_B1 + 8 * h + ch];
-#pragma unroll
-                            for (int k = 0; k < 9; ++k) c1 = fmaf(sf[F_W1 + k * 16 + 8 * h + ch], sv[k], c1);
-                            const float v = fmaf(combine(o[0][ch], o[1][ch], o[2][ch], o[3][ch], o[4][ch]), scale, bias[8 * h + ch]);
-                            if (inside) a3[(8 * h + ch) * (A3_N * A3_P) + r * A3_P + c] = valid ? (c1 + v) : 0.0f;
+                            const float v = fmaf(combine(o[0][ch], o[1][ch], o[2][ch], o[3][ch], o[4][ch]), scale, bq[ch]);
+                            if (inside) a3[(8 * h + ch) * (A3_R * A3_P) + r * A3_P + c] = valid ? (c1[ch] + v) : 0.0f;
                         }
                     }
                     umma::fence_before_sync();
@@ -374,7 +447,10 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
         umma::fence_after_sync();
         STAMP(3 + layer);
     }
-    if (!ok && err) atomicExch(err, 1);
+    if (!ok) {
+        if (err) atomicExch(err, 1);
+        break;
+    }
 
     // ---- conv4 (16 -> 1) -> so ---------------------------------------------------------------------------
     for (int it = tid; it < TH * (TW / 2); it += NT) {
@@ -399,7 +475,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
                     acc1 = fmaf(wk[ky * 3 + kx], pv[kx + 1], acc1);
                 }
             }
-            ip += A3_N * A3_P;
+            ip += A3_R * A3_P;
             wc += 12;
         }
         so[r * O_P + st * 2] = acc0;
@@ -450,10 +526,14 @@ __global__ void __launch_bounds__(NT, 1) lift_step_tc_kernel(const __grid_consta
             }
         }
     }
+    __syncthreads();   // the tile's shared-memory arrays are reused by the next tile
+    STAMP(6);
+    ++tiles_done;
+    } // tile loop
+    if (dbg_cta && tid == 0) { dbg_cta[14] = clock64() - t_cta0; dbg_cta[15] = tiles_done; }
     umma::fence_before_sync();
     __syncthreads();
-    STAMP(6);
-    if (warp == 16) umma::tmem_dealloc(tbase, 512);
+    if (warp == MMA_WARP) umma::tmem_dealloc(tbase, TMEM_COLS);
 }
 
 // ---- timing probe: MMA throughput of the production operand layout with nothing else running on the SM ------
@@ -469,7 +549,7 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int variant, int reps
         umma::mbar_init(umma::smem_u32(&bar), 1);
         umma::fence_mbar_init();
     }
-    if (warp == 0) umma::tmem_alloc(&tslot, 512);
+    if (warp == 0) umma::tmem_alloc(&tslot, TMEM_COLS);
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
@@ -488,7 +568,7 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int variant, int reps
                     const int lbo = variant == 4 ? 2048 : 16;
 #pragma unroll
                     for (int i = 0; i < 18; ++i)
-                        umma::mma_s8(tbase + (r % 4) * 96, umma::smem_desc(a_s + (r % NBLK) * 2048 + i * 160, lbo, 128),
+                        umma::mma_s8(tbase + (r % 2) * 96, umma::smem_desc(a_s + (r % NBLK) * 2048 + i * 160, lbo, 128),
                                      umma::smem_desc(b_s + (i % 5) * 1536, 768, 128), umma::idesc_s8(nn), 1u);
                 }
             }
@@ -504,7 +584,7 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int variant, int reps
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tbase, 512);
+    if (warp == 0) umma::tmem_dealloc(tbase, TMEM_COLS);
 }
 
 } // namespace tc
@@ -523,8 +603,15 @@ int launch_step_tc(const StepD &d, int src_kind, int *err_flag, cudaStream_t st)
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    dim3 grid((d.w + tc::TW - 1) / tc::TW, (d.h + tc::TH - 1) / tc::TH, d.n);
-    if (grid.y > 65535 || grid.z > 65535) return PMCTF_ESHAPE;
+    static int resident = 0; // CTAs that fit the device at two per SM
+    if (!resident) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return (int)cudaGetLastError();
+        resident = 2 * sms;
+    }
+    const long long tiles = (long long)((d.w + tc::TW - 1) / tc::TW) * ((d.h + tc::TH - 1) / tc::TH) * d.n;
+    if (tiles > 0x7fffffffLL) return PMCTF_ESHAPE;
+    dim3 grid((unsigned)(tiles < resident ? tiles : resident));
     switch (src_kind) {
     case PMCTF_SRC_PLANE: tc::lift_step_tc_kernel<PMCTF_SRC_PLANE><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(d, err_flag); break;
     case PMCTF_SRC_WARP: tc::lift_step_tc_kernel<PMCTF_SRC_WARP><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(d, err_flag); break;

@@ -58,28 +58,23 @@ typedef struct {
 } orc_iwave_t;
 
 /* ------------------------------------------------------------------------------------------ */
-/* deterministic tanh: tanh(x) = em1/(em1+2), em1 = expm1(2|x|), built from IEEE ops only      */
+/* deterministic tanh (arithmetic contract; table include/pmctf_tanh_table.h, routine specified in
+ * tools/gen_tanh_table.py): third-order expansion around the nearest multiple of 1/32 with the derivatives
+ * expressed through T = tanh(node).  Absolute error <= 1.2e-7; exact 0 at 0; odd; saturates at |x| >= 9.        */
+#include "../include/pmctf_tanh_table.h"
+static const uint32_t tanh_bits[PMCTF_TANH_ENTRIES] = {PMCTF_TANH_TABLE_VALUES};
 static inline float tanh_det(float x)
 {
-    float ax = fminf(fabsf(x), 10.0f); /* tanh(10) rounds to 1.0f */
-    float z = ax + ax;
-    float kf = rintf(z * 1.44269504f);
-    float r = fmaf(kf, -0.693145752f, z);
-    r = fmaf(kf, -1.42860677e-06f, r);
-    float q = 1.98412698e-4f;
-    q = fmaf(q, r, 1.38888889e-3f);
-    q = fmaf(q, r, 8.33333333e-3f);
-    q = fmaf(q, r, 4.16666667e-2f);
-    q = fmaf(q, r, 1.66666667e-1f);
-    q = fmaf(q, r, 0.5f);
-    float r2 = r * r;
-    float p = fmaf(q, r2, r);
-    int32_t k = (int32_t)kf;
-    union { int32_t i; float f; } s;
-    s.i = (k + 127) << 23;
-    float em1 = fmaf(s.f, p, s.f - 1.0f);
-    float t = em1 / (em1 + 2.0f);
-    return copysignf(t, x);
+    const float *tab = (const float *)tanh_bits;
+    float ax = fminf(fabsf(x), PMCTF_TANH_XMAX);
+    float fi = rintf(ax * 32.0f);
+    float d = fmaf(fi, -0.03125f, ax);
+    float T = tab[(int32_t)fi];
+    float D1 = fmaf(-T, T, 1.0f);
+    float D2 = -(T * D1);
+    float D3 = (D1 * fmaf(-3.0f * T, T, 1.0f)) * -0.333333343f;
+    float y = fmaf(fmaf(fmaf(D3, d, D2), d, D1), d, T);
+    return copysignf(y, x);
 }
 
 ORC_API void orc_tanh(const float *x, float *y, long n)

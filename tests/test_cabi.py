@@ -49,7 +49,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(n.Plane) == 48
     assert ctypes.sizeof(n.Temporal) == 32
     assert ctypes.sizeof(n.IWave) == 4 * 3 * 4 + 4 * 4 + 8 + 4 * 4
-    assert n.PU_PACKED_FLOATS == 8848
+    assert n.PU_PACKED_FLOATS == 10128
 
 
 def test_no_cpu_fallback():

@@ -65,7 +65,8 @@ def test_accumulate_and_column_offsets():
     B = g.integers(-128, 128, 2 * 48 * 16, dtype=np.int8)
     mk = lambda a_off, b_off, n, col, acc: dict(a_off=a_off, a_lbo=16, a_sbo=128, b_off=b_off, b_lbo=768, b_sbo=128, n=n,  # noqa: E731
                                                 d_col=col, accumulate=acc)
-    ops = [mk(0, 0, 48, 0, 0), mk(160, 0, 32, 16, 1), mk(160, 512, 16, 48, 0), mk(320, 256, 16, 48, 1), mk(32, 0, 48, 32, 1)]
+    ops = [mk(0, 0, 48, 0, 0), mk(160, 0, 32, 16, 1), mk(160, 512, 16, 48, 0), mk(320, 256, 16, 48, 1), mk(64, 256, 16, 64, 0),
+           mk(32, 0, 48, 32, 1)]  # every column group is initialised (accumulate=0) before it is accumulated into
     got, _ = run(A, B, ops, 1, 0, 80)
     assert np.array_equal(got, U.emulate(A, B, ops, 1, 0, 80))
 
@@ -84,7 +85,7 @@ def test_digit_split_convolution_and_timing():
     assert np.array_equal(U.combine_orders(got).reshape(-1, 16), U.conv_exact(Aint, Wint, pitch, n_blocks * 128))
     _, cyc = run(A, B, ops, n_blocks, 2048, 80, repeat=64)
     per_mma = float(np.median(cyc)) / (64 * len(ops))
-    print(f"\ntcgen05 kind::i8 M=128 conv op list: {np.median(cyc1):.0f} cycles per 18-MMA block (issue+commit+wait), "
+    print(f"\ntcgen05 kind::i8 M=128 conv op list: {np.median(cyc1):.0f} cycles per 15-MMA block (issue+commit+wait), "
           f"{per_mma:.1f} cycles per MMA steady state (N mix 48/32/16)")
     for n in (16, 32, 48, 96):
         o = [dict(a_off=32 * i, a_lbo=16, a_sbo=128, b_off=0, b_lbo=768 if n <= 48 else 1536, b_sbo=128, n=n, d_col=0, accumulate=1)

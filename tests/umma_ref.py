@@ -39,7 +39,8 @@ def split_digits(v):
 
 
 def pack_weights(W):
-    """W int [16 co, 16 ci, 3, 3] (|W| <= 2^22) -> int8 image: per tap pair a [2 chunks][48 rows = (digit, co)][16 ci] block."""
+    """W int [16 co, 16 ci, 3, 3] (|W| <= 2^22) -> int8 image (10240 B): per tap pair a [2 chunks][48 rows = (digit, co)][16 ci]
+    block (5 x 1536 B), followed by the 80-row copy of tap pair 0 ([2][80][16], rows 48..79 zero) at byte 7680."""
     d = split_digits(W)
     out = np.zeros((5, 2, 48, 16), np.int8)
     for tp, pair in enumerate(TAP_PAIRS):
@@ -48,25 +49,25 @@ def pack_weights(W):
                 continue
             for j in range(3):
                 out[tp, c, j * 16:(j + 1) * 16, :] = d[j][:, :, tap[0], tap[1]]
-    return out.reshape(-1)
+    first = np.zeros((2, 80, 16), np.int8)
+    first[:, :48] = out[0]
+    return np.concatenate([out.reshape(-1), first.reshape(-1)])
 
 
 def conv_ops(pitch, plane_bytes):
-    """Op list of one 128-pixel block of the 16->16 3x3 convolution: D columns [16*i, 16*i+16) accumulate the
-    digit products of order i (weight 2^(32-8i)): a_d x w_e lands in group d+e."""
+    """Op list of one 128-pixel block of the 16->16 3x3 convolution (15 MMAs): D columns [16*i, 16*i+16) accumulate the
+    digit products of order i (weight 2^(32-8i)): a_d x [w0; w1; w2] lands in groups d, d+1, d+2.  The first MMA uses the
+    80-row image (zero rows 48..79) without accumulation and thereby initialises all five groups."""
     ops = []
     for tp, (t0, t1) in enumerate(TAP_PAIRS):
         a_off = (t0[0] * pitch + t0[1]) * 16
         lbo = ((t1[0] * pitch + t1[1]) - (t0[0] * pitch + t0[1])) * 16 if t1 is not None else 16
-        boff = tp * 1536
-
-        def op(d, e0, ne, acc):
-            return dict(a_off=d * plane_bytes + a_off, a_lbo=lbo, a_sbo=128, b_off=boff + e0 * 256, b_lbo=768, b_sbo=128,
-                        n=16 * ne, d_col=16 * (d + e0), accumulate=acc)
-        if tp == 0:  # first touch of every accumulator group must not accumulate
-            ops += [op(0, 0, 3, 0), op(1, 0, 2, 1), op(1, 2, 1, 0), op(2, 0, 1, 1), op(2, 1, 1, 1), op(2, 2, 1, 0)]
-        else:
-            ops += [op(0, 0, 3, 1), op(1, 0, 3, 1), op(2, 0, 3, 1)]
+        for d in range(3):
+            if tp == 0 and d == 0:
+                ops.append(dict(a_off=a_off, a_lbo=lbo, a_sbo=128, b_off=7680, b_lbo=1280, b_sbo=128, n=80, d_col=0, accumulate=0))
+            else:
+                ops.append(dict(a_off=d * plane_bytes + a_off, a_lbo=lbo, a_sbo=128, b_off=tp * 1536, b_lbo=768, b_sbo=128,
+                                n=48, d_col=16 * d, accumulate=1))
     return ops
 
 
