@@ -51,6 +51,12 @@ def lib():
     return _lib
 
 
+def set_threads(n: int) -> None:
+    """Number of OpenMP threads the oracle uses (torchrun exports OMP_NUM_THREADS=1, which would silently serialise it)."""
+    lib()
+    C.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+
+
 def set_conv_mode(mode: str) -> None:
     """'ffma': conv2/conv3 as sequential fp32 FMA chains; 'tensor': exact fixed-point (see pmctf_oracle.c)."""
     lib().orc_set_conv_mode({"ffma": 0, "tensor": 1}[mode])
