@@ -452,34 +452,43 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
         break;
     }
 
-    // ---- conv4 (16 -> 1) -> so ---------------------------------------------------------------------------
-    for (int it = tid; it < TH * (TW / 2); it += NT) {
-        const int r = it / (TW / 2), st = it - r * (TW / 2);
-        float acc0 = sf[F_B4], acc1 = acc0;
-        const float *ip = a3 + r * A3_P + st * 2;
-        const float *wc = sf + F_W4;
-#pragma unroll 4
+    // ---- conv4 (16 -> 1) -> so: 2 rows x 4 columns per thread; shared-memory bandwidth is what limits this kernel,
+    //      and the register tile halves the bytes read per output -------------------------------------------------
+    for (int it = tid; it < (TH / 2) * (TW / 4); it += NT) {
+        const int r = 2 * (it / (TW / 4)), c = 4 * (it % (TW / 4));
+        float acc[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = sf[F_B4];
+#pragma unroll 2
         for (int ci = 0; ci < 16; ++ci) {
+            const float *ip = a3 + ci * (A3_R * A3_P) + r * A3_P + c;
+            const float *wc = sf + F_W4 + ci * 12;
             const float4 w0 = *reinterpret_cast<const float4 *>(wc);
             const float4 w1 = *reinterpret_cast<const float4 *>(wc + 4);
-            const float w8 = wc[8];
-            const float wk[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w8};
+            const float wk[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, wc[8]};
+            float pv[4][6];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const float2 p0 = *reinterpret_cast<const float2 *>(ip + ky * A3_P);
-                const float2 p1 = *reinterpret_cast<const float2 *>(ip + ky * A3_P + 2);
-                const float pv[4] = {p0.x, p0.y, p1.x, p1.y};
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    acc0 = fmaf(wk[ky * 3 + kx], pv[kx], acc0);
-                    acc1 = fmaf(wk[ky * 3 + kx], pv[kx + 1], acc1);
-                }
+            for (int rr = 0; rr < 4; ++rr) {
+                const float4 p0 = *reinterpret_cast<const float4 *>(ip + rr * A3_P);
+                const float2 p1 = *reinterpret_cast<const float2 *>(ip + rr * A3_P + 4);
+                pv[rr][0] = p0.x; pv[rr][1] = p0.y; pv[rr][2] = p0.z; pv[rr][3] = p0.w; pv[rr][4] = p1.x; pv[rr][5] = p1.y;
             }
-            ip += A3_R * A3_P;
-            wc += 12;
+            // every output stays one sequential chain in (ci, ky, kx) order
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wk[ky * 3 + kx], pv[i + ky][j + kx], acc[i][j]);
         }
-        so[r * O_P + st * 2] = acc0;
-        so[r * O_P + st * 2 + 1] = acc1;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) so[(r + i) * O_P + c + j] = acc[i][j];
     }
     __syncthreads();
     STAMP(5);
