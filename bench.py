@@ -325,6 +325,10 @@ def main():
         roofline.update({
             "kernel": "lift_step_tc_kernel<PLANE|WARP|SKIP3>: warp/skip + PredictUpdate CNN + lifting accumulate; conv2/conv3 as exact "
                       "int8 digit-split implicit GEMMs on tcgen05 (UTCIMMA, accumulators in TMEM), conv1/conv4/tanh on CUDA cores",
+            "traffic": 35.6e6,
+            "traffic_note": "dram__bytes_read+write of ONE launch from ncu --set full (profiles/r1c_lift_step_tc_ncu.txt): the 1080p luma "
+                            "temporal step, 2.21 Mpx, algorithmic 44.2 MB (20 B/px); outputs stay in the 126 MB L2, so DRAM traffic is "
+                            "below the algorithmic bytes -- no wasted re-reads.  Not measured live.",
             "executed_int8_tops": ks["pixels"] * ops_per_px / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
             "executed_int8_ops_per_px": ops_per_px, "int8_dense_peak_tops_nominal": 4500.0,
             "note": "9 digit products per MAC (3 signed-byte digits per operand) make the convolution exact, so executed tensor work is "

@@ -192,8 +192,9 @@ class GopCodec:
     def code_sequence_host(self, y_u8: torch.Tensor, c_u8: torch.Tensor, mvs_host: List[Sequence[torch.Tensor]],
                            psize: int = 128):
         """End-to-end entry point on HOST buffers: y_u8 [F,h0,w0], c_u8 [F,2,h0/2,w0/2] uint8 (pinned for
-        speed) and per-GOP host motion fields; frames are uploaded GOP by GOP, unpacked + zero padded on the
-        device, coded, and the [F, N_STATS] statistics are returned on the host."""
+        speed) and per-GOP host motion fields; frames are uploaded GOP by GOP on a copy stream (overlapping the
+        previous GOP's kernels), unpacked + zero padded on the device, coded, and the [F, N_STATS] statistics are
+        returned on the host."""
         G = self.gop_size
         F_, h0, w0 = y_u8.shape
         if F_ % G:
@@ -201,11 +202,26 @@ class GopCodec:
         _, pr, _, pb = get_padding_size(h0, w0, psize)
         hp, wp = h0 + pb, w0 + pr
         dev = next(self.m.parameters()).device
+        cur = torch.cuda.current_stream(dev)
+        copy = self._copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(dev)
+
+        def upload(g):  # H2D of GOP g on the copy stream, overlapping the kernels of GOP g-1
+            with torch.cuda.stream(copy):
+                t = (y_u8[g * G:(g + 1) * G].to(dev, non_blocking=True), c_u8[g * G:(g + 1) * G].to(dev, non_blocking=True),
+                     [m.to(dev, non_blocking=True) for m in mvs_host[g]])
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return t, ev
+
         out = []
+        nxt = upload(0)
         for g in range(F_ // G):
-            yd = y_u8[g * G:(g + 1) * G].to(dev, non_blocking=True)
-            cd = c_u8[g * G:(g + 1) * G].to(dev, non_blocking=True)
-            mvd = [t.to(dev, non_blocking=True) for t in mvs_host[g]]
+            (yd, cd, mvd), ev = nxt
+            cur.wait_event(ev)
+            for t in [yd, cd] + mvd:
+                t.record_stream(cur)
+            if g + 1 < F_ // G:
+                nxt = upload(g + 1)
             Y = ops.unpack_u8(yd, hp, wp)
             C = ops.unpack_u8(cd.view(-1, h0 // 2, w0 // 2), hp // 2, wp // 2).view(G, 2, 1, hp // 2, wp // 2)
             _, _, st = self.code_gop(Y, C, mvd, yd, cd)

@@ -140,3 +140,64 @@ def test_gop16_1080p_properties(P, model):
     Ly, Lc, Hs = codec.analysis(Y, C, mvs)
     ry, rc = codec.synthesis(Ly, Lc, Hs, mvs)
     assert float((ry - Y).abs().max()) <= 2e-3 and float((rc - C).abs().max()) <= 2e-3
+
+
+# ---- BASELINE.json configs as parity cases at their own sizes ---------------------------------------------------
+def _oracle_weights(weights):
+    temporal = [(orc.PU(sub_sd(weights, f"temporal_filtering.{i}.P_t.")), orc.PU(sub_sd(weights, f"temporal_filtering.{i}.U_t.")))
+                for i in range(4)]
+    return temporal, orc.IWave(sub_sd(weights, "hp_coder.wavelet_transform.lift_h.")), orc.IWave(sub_sd(weights, "lp_coder.wavelet_transform.lift_h."))
+
+
+def test_config0_gop2_256x448_vs_oracle(P, model, weights):
+    """configs[0]: pMCTF-L GOP-2 forward (flow warp + one temporal lifting level + pWave++ on the subbands) on a synthetic
+    2-frame 256x448 clip (padded to 256x512 as test_pMCTF_flex.py does), bit-exact against the oracle."""
+    from learned_pmctf_b200 import gop as Gm
+    h0, w0, gop = 256, 448, 2
+    codec = Gm.GopCodec(model, gop, q_index=8)
+    _, pr, _, pb = Gm.get_padding_size(h0, w0, 128)
+    hp, wp = h0 + pb, w0 + pr
+    assert (hp, wp) == (256, 512)
+    y, c, mvs = _inputs(gop, h0, w0, 11)
+    mvs = [np.ascontiguousarray(np.pad(m, ((0, 0), (0, 0), (0, hp - h0), (0, wp - w0)))) for m in mvs]
+    yd, cd = cu(y), cu(c)
+    Y = P.ops.unpack_u8(yd, hp, wp)
+    C = P.ops.unpack_u8(cd.view(-1, h0 // 2, w0 // 2), hp // 2, wp // 2).view(gop, 2, 1, hp // 2, wp // 2)
+    rec_y, rec_c, st = codec.code_gop(Y, C, [cu(m) for m in mvs], yd, cd)
+    temporal, hp_w, lp_w = _oracle_weights(weights)
+    oy, oc, osym = orc.code_gop(orc.unpack_u8(y, hp, wp)[:, None], orc.unpack_u8(c, hp // 2, wp // 2)[:, :, None], mvs, temporal,
+                                hp_w, lp_w, [codec.q_pair("hp", 0)], codec.q_pair("lp", 0))
+    assert np.array_equal(rec_y.cpu().numpy(), oy) and np.array_equal(rec_c.cpu().numpy(), oc)
+    assert np.array_equal(st.cpu().numpy()[:, 1:3].astype(np.int64), osym)
+
+
+def test_config1_pwave_1080p_six_q_points_vs_oracle(P, model, weights, conv_mode):
+    """configs[1]: pWave++ analysis + quantise + dequantise + synthesis of one 1920x1080 frame (padded 1152x1920) at the
+    6 q_index points of test_pMCTF_flex.py:436-443 -- every quantised symbol and the reconstruction bit-exact vs the oracle."""
+    if conv_mode == "ffma":
+        pytest.skip("full-size oracle run once (tensor mode); the ffma mode is covered at the smaller sizes")
+    from learned_pmctf_b200 import gop as Gm
+    y, _ = Gm.synthetic_sequence(3, 1, 1080, 1920, "cuda")
+    X = P.ops.unpack_u8(y, 1152, 1920)
+    x_np = X.cpu().numpy()
+    _, _, lp_w = _oracle_weights(weights)
+    y_or = orc.pwave_encode(x_np, lp_w)          # analysis once; quantisation per q point
+    coder = model.lp_coder
+    enc = coder.encode_bands(X)
+    for lvl in range(4):
+        for b in ("ll", "lh", "hl", "hh"):
+            assert np.array_equal(enc[lvl][b].cpu().numpy(), y_or[lvl][b]), (lvl, b)
+    nsym = 0
+    for qi in (0, 4, 8, 12, 16, 20):
+        q, qll = coder.q_pair(qi)
+        q, qll = float(q.detach().reshape(-1)[0].cpu()), float(qll.detach().reshape(-1)[0].cpu())
+        x_hat, hat = coder.spatial_wavelet_dec(X, q, qll, post_process=False, return_symbols=True)
+        for lvl in hat:
+            for b, v in hat[lvl].items():
+                want = orc.quantize(y_or[lvl][b], qll if b == "ll" else q)
+                assert np.array_equal(v.cpu().numpy(), want), f"q_index {qi} level {lvl} band {b}"
+                nsym += want.size
+        if qi in (0, 20):  # full synthesis vs the oracle at the two end points
+            rec = {lvl: {b: orc.dequantize(v.cpu().numpy(), qll if b == "ll" else q) for b, v in hat[lvl].items()} for lvl in hat}
+            assert np.array_equal(x_hat.cpu().numpy(), orc.pwave_decode(rec, lp_w))
+    assert nsym == 6 * 1152 * 1920
