@@ -195,6 +195,50 @@ def build_model(pkg, dev):
     return m
 
 
+def run_train(args, pkg, G, par, dev, rank, world):
+    """BASELINE configs[4]: hot-path training step (forward + backward through warp, lifting and convs + AdamW), batch 8 of
+    synthetic 256x256 GOP-8 luma clips per GPU, on the training kernels (csrc/pmctf_train.cu).  Secondary line."""
+    import torch
+    model = build_model(pkg, dev).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
+    B, GOP8, H, W = 8, 8, 256, 256
+    g = torch.Generator(device=dev)
+    g.manual_seed(7 + rank)
+    base = torch.nn.functional.avg_pool2d(torch.rand((B, 1, H + 16, W + 32), device=dev, generator=g), 5, 1, 2) * 255
+    clips = torch.stack([base[:, :, 8 + f:8 + f + H, 2 * f:2 * f + W] for f in range(GOP8)], 1).contiguous()
+    mvs = [torch.randn((B * (GOP8 >> (s + 1)), 2, H, W), device=dev, generator=g) * 1.5 for s in range(3)]
+    yh = clips.cpu().pin_memory()
+
+    def step():
+        x = yh.to(dev, non_blocking=True)
+        opt.zero_grad(set_to_none=True)
+        loss, dist = G.training_loss_hot_path(model, x, mvs, q_index=args.q_index)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)   # train_pMCTF_L.py:247-251
+        opt.step()
+        return float(loss)                                        # D2H read of the step's result
+
+    W_, K = max(args.warmup, 3), max(args.steps, 1)
+    for _ in range(W_):
+        loss = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = par.max_over_ranks(e0.elapsed_time(e1) / K, dev)
+    if rank == 0:
+        print(json.dumps({"metric": "pMCTF-L hot-path training clips/s (GOP-8 256x256 luma, batch 8)", "value": world * B / (ms * 1e-3),
+                          "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "configs[4]: training step (forward + backward + grad clip + AdamW) on the hot path, batch 8 "
+                                                 "x GOP-8 x 256x256, injected motion fields, un-fused fp32 training kernels", "loss": loss}}), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -206,6 +250,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--conv-mode", default="tensor", choices=["tensor", "ffma"])
+    ap.add_argument("--workload", default="gop16", choices=["gop16", "train"],
+                    help="gop16: the headline metric (default); train: BASELINE configs[4] training step (not the headline)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -230,6 +276,8 @@ def main():
     n_gops = n_frames // GOP
 
     pkg.ops.set_conv_mode(args.conv_mode)
+    if args.workload == "train":
+        return run_train(args, pkg, G, par, dev, rank, world)
     model = build_model(pkg, dev)
     codec = G.GopCodec(model, GOP, q_index=args.q_index)
     _, pr, _, pb = G.get_padding_size(H0, W0, 128)

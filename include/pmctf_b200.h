@@ -237,6 +237,18 @@ int pmctf_umma_selftest(const signed char *A, int a_bytes, const signed char *B,
                         int n_ops, int n_blocks, int block_stride_bytes, int out_cols, int *out, int repeat,
                         long long *cycles, int *err, void *stream);
 
+/* ---- training path (BASELINE.json configs[4]): differentiable fp32 primitives composed by autograd ---------------------
+ * Under autograd the modules compose these un-fused kernels the way the reference composes conv2d / grid_sample.
+ * conv3x3: nn.Conv2d(cin, cout, 3, padding=1) forward (pMCTF/layers/layers.py:54-56), x [N,cin,H,W], w [cout,cin,3,3], b [cout]
+ * or NULL, (cin, cout) in {(1,16), (16,16), (16,1), (1,1)}; its data gradient is the same call with w transposed and flipped.
+ * conv3x3_wgrad: gw[cout,cin,3,3] += dL/dw, gb[cout] += dL/db (caller zeroes; gb may be NULL).
+ * flow_warp_bwd: adjoint of pmctf_flow_warp; gim [N,C,H,W] += dL/dim, gflow [flowN,2,H,W] += dL/dflow (caller zeroes; either
+ * may be NULL). */
+int pmctf_conv3x3(const float *x, const float *w, const float *b, float *y, int N, int cin, int cout, int H, int W, void *stream);
+int pmctf_conv3x3_wgrad(const float *x, const float *g, float *gw, float *gb, int N, int cin, int cout, int H, int W, void *stream);
+int pmctf_flow_warp_bwd(const float *gout, const float *im, const float *flow, const float *lin_x, const float *lin_y, float *gim,
+                        float *gflow, int N, int C, int H, int W, int flowN, float sign, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

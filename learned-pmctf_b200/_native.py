@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "lib", "libpmctf_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "pmctf_kernels.cu"), os.path.join(_HERE, "csrc", "pmctf_umma_test.cu"),
-           os.path.join(_HERE, "csrc", "pmctf_lift_tc.cu")]
+           os.path.join(_HERE, "csrc", "pmctf_lift_tc.cu"), os.path.join(_HERE, "csrc", "pmctf_train.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "pmctf_umma.cuh"), os.path.join(_HERE, "csrc", "pmctf_common.cuh")]
 INCLUDE = os.path.join(ROOT, "include")
 
@@ -87,6 +87,9 @@ SIGNATURES = {
     "pmctf_quantize_stats": [_P, _f, _f, _I, _P, _I, _LL, _P, _P],
     "pmctf_unpack_u8": [_P, _P, _I, _I, _I, _I, _I, _P],
     "pmctf_frame_sse": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "pmctf_conv3x3": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pmctf_conv3x3_wgrad": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pmctf_flow_warp_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _f, _P],
     "pmctf_umma_selftest": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P],
 }
 _RESTYPES = {"pmctf_error_string": C.c_char_p, "pmctf_lift2d_workspace": C.c_longlong,

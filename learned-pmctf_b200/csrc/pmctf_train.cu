@@ -1,0 +1,188 @@
+// pmctf_train.cu -- differentiable primitives of the TRAINING path (BASELINE.json configs[4]: forward + backward through
+// warp, lifting and convs).  Evaluation uses the fused tensor-core lifting step (pmctf_lift_tc.cu); under autograd the
+// modules compose these un-fused fp32 kernels instead, exactly like the reference composes conv2d / grid_sample:
+//
+//   conv3x3_kernel<CIN,COUT>   y = conv3x3(x, w) + b, zero padding, NCHW (layers.py:54-56).  The data gradient is the
+//                              same kernel run with the transposed, flipped weights.
+//   wgrad3x3_kernel<CIN,COUT>  dL/dw[co][ci][ky][kx] = sum g[co](p) x[ci](p + k), dL/db[co] = sum g[co]   (atomics)
+//   flow_warp_bwd_kernel       adjoint of flow_warp (video_net.py:32-55 / ATen grid_sampler_2d backward, bilinear, border,
+//                              align_corners=True): scatter-add into dL/dim, dL/dflow
+// Floating-point, tolerance-tested against torch autograd (tests/test_gpu_train.py); no exactness contract here.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pmctf_b200.h"
+
+namespace pmctf {
+namespace train {
+
+constexpr int TX = 32, TY = 8; // output tile per CTA, one thread per pixel
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(TX * TY) conv3x3_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
+                                                          float *__restrict__ y, int H, int W)
+{
+    __shared__ float xs[CIN][TY + 2][TX + 2];
+    __shared__ __align__(16) float ws[CIN * 9][COUT]; // [ci*9 + k][co]
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    const int n = blockIdx.z, y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
+    for (int i = tid; i < CIN * 9 * COUT; i += TX * TY) {
+        const int co = i % COUT, r = i / COUT; // r = ci*9 + k
+        ws[r][co] = w[(co * CIN + r / 9) * 9 + r % 9];
+    }
+    const float *xp = x + (long long)n * CIN * H * W;
+    for (int i = tid; i < CIN * (TY + 2) * (TX + 2); i += TX * TY) {
+        const int ci = i / ((TY + 2) * (TX + 2)), rem = i % ((TY + 2) * (TX + 2));
+        const int r = rem / (TX + 2), c = rem % (TX + 2);
+        const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+        xs[ci][r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? xp[((long long)ci * H + gy) * W + gx] : 0.0f;
+    }
+    __syncthreads();
+    const int gy = y0 + threadIdx.y, gx = x0 + threadIdx.x;
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = b ? b[co] : 0.0f;
+#pragma unroll 1
+    for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const float v = xs[ci][threadIdx.y + k / 3][threadIdx.x + k % 3];
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[co] = fmaf(ws[ci * 9 + k][co], v, acc[co]);
+        }
+    }
+    if (gy < H && gx < W) {
+        float *yp = y + (long long)n * COUT * H * W + (long long)gy * W + gx;
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) yp[(long long)co * H * W] = acc[co];
+    }
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) wgrad3x3_kernel(const float *__restrict__ x, const float *__restrict__ g, float *__restrict__ gw,
+                                                       float *__restrict__ gb, int H, int W)
+{
+    __shared__ float xs[CIN][TY + 2][TX + 2];
+    __shared__ float gs[COUT][TY][TX];
+    const int tid = threadIdx.x;
+    const int n = blockIdx.z, y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
+    const float *xp = x + (long long)n * CIN * H * W;
+    const float *gp = g + (long long)n * COUT * H * W;
+    for (int i = tid; i < CIN * (TY + 2) * (TX + 2); i += 256) {
+        const int ci = i / ((TY + 2) * (TX + 2)), rem = i % ((TY + 2) * (TX + 2));
+        const int r = rem / (TX + 2), c = rem % (TX + 2);
+        const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+        xs[ci][r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? xp[((long long)ci * H + gy) * W + gx] : 0.0f;
+    }
+    for (int i = tid; i < COUT * TY * TX; i += 256) {
+        const int co = i / (TY * TX), rem = i % (TY * TX);
+        const int r = rem / TX, c = rem % TX;
+        const int gy = y0 + r, gx = x0 + c;
+        gs[co][r][c] = (gy < H && gx < W) ? gp[((long long)co * H + gy) * W + gx] : 0.0f;
+    }
+    __syncthreads();
+    // one (co, ci) pair per thread, the tile's pixels split over the remaining threads
+    constexpr int PAIRS = CIN * COUT, SPLIT = 256 / PAIRS;
+    const int pair = tid % PAIRS, part = tid / PAIRS;
+    const int co = pair / CIN, ci = pair % CIN;
+    float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, bsum = 0.0f;
+    for (int p = part; p < TY * TX; p += SPLIT) {
+        const int r = p / TX, c = p % TX;
+        const float gv = gs[co][r][c];
+        bsum += gv;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[k] = fmaf(gv, xs[ci][r + k / 3][c + k % 3], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) atomicAdd(gw + (co * CIN + ci) * 9 + k, acc[k]);
+    if (gb && ci == 0) atomicAdd(gb + co, bsum);
+}
+
+__global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ im,
+                                                            const float *__restrict__ flow, const float *__restrict__ lin_x,
+                                                            const float *__restrict__ lin_y, float *__restrict__ gim,
+                                                            float *__restrict__ gflow, int N, int C, int H, int W, int flowN, float sign,
+                                                            float sx, float sy)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, n = blockIdx.z;
+    if (x >= W) return;
+    const long long plane = (long long)H * W;
+    const int fn = n / (N / flowN);
+    const float *fb = flow + (long long)fn * 2 * plane + (long long)y * W + x;
+    const float fx = sign * fb[0], fy = sign * fb[plane];
+    // forward coordinate arithmetic of flow_warp_kernel
+    const float gxn = lin_x[x] + fx / sx, gyn = lin_y[y] + fy / sy;
+    const float ixu = (gxn + 1.0f) * sx, iyu = (gyn + 1.0f) * sy;
+    const float ix = fminf(fmaxf(ixu, 0.0f), (float)(W - 1)), iy = fminf(fmaxf(iyu, 0.0f), (float)(H - 1));
+    const float mx = (ixu >= 0.0f && ixu <= (float)(W - 1)) ? 1.0f : 0.0f; // clip_coordinates_set_grad
+    const float my = (iyu >= 0.0f && iyu <= (float)(H - 1)) ? 1.0f : 0.0f;
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float wx = ix - x0f, wy = iy - y0f;
+    const int x0i = (int)x0f, y0i = (int)y0f;
+    const bool x1ok = x0i + 1 <= W - 1, y1ok = y0i + 1 <= H - 1;
+    float gix = 0.0f, giy = 0.0f;
+    for (int c = 0; c < C; ++c) {
+        const long long base = ((long long)n * C + c) * plane;
+        const float go = gout[base + (long long)y * W + x];
+        const float *p = im + base + (long long)y0i * W + x0i;
+        const float vnw = p[0], vne = x1ok ? p[1] : 0.0f, vsw = y1ok ? p[W] : 0.0f, vse = (x1ok && y1ok) ? p[W + 1] : 0.0f;
+        if (gim) {
+            float *q = gim + base + (long long)y0i * W + x0i;
+            atomicAdd(q, go * (1.0f - wx) * (1.0f - wy));
+            if (x1ok) atomicAdd(q + 1, go * wx * (1.0f - wy));
+            if (y1ok) atomicAdd(q + W, go * (1.0f - wx) * wy);
+            if (x1ok && y1ok) atomicAdd(q + W + 1, go * wx * wy);
+        }
+        gix += go * ((vne - vnw) * (1.0f - wy) + (vse - vsw) * wy);
+        giy += go * ((vsw - vnw) * (1.0f - wx) + (vse - vne) * wx);
+    }
+    if (gflow) { // d ix / d fx = 1 inside the image, 0 where the coordinate was clipped
+        float *gf = gflow + (long long)fn * 2 * plane + (long long)y * W + x;
+        atomicAdd(gf, sign * gix * mx);
+        atomicAdd(gf + plane, sign * giy * my);
+    }
+}
+
+} // namespace train
+} // namespace pmctf
+
+using namespace pmctf::train;
+
+extern "C" int pmctf_conv3x3(const float *x, const float *w, const float *b, float *y, int N, int cin, int cout, int H, int W, void *stream)
+{
+    if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0) return PMCTF_EINVAL;
+    dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY, N), block(TX, TY);
+    if (grid.y > 65535 || grid.z > 65535) return PMCTF_ESHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cin == 1 && cout == 16) conv3x3_kernel<1, 16><<<grid, block, 0, st>>>(x, w, b, y, H, W);
+    else if (cin == 16 && cout == 16) conv3x3_kernel<16, 16><<<grid, block, 0, st>>>(x, w, b, y, H, W);
+    else if (cin == 16 && cout == 1) conv3x3_kernel<16, 1><<<grid, block, 0, st>>>(x, w, b, y, H, W);
+    else if (cin == 1 && cout == 1) conv3x3_kernel<1, 1><<<grid, block, 0, st>>>(x, w, b, y, H, W);
+    else return PMCTF_ESHAPE;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int pmctf_conv3x3_wgrad(const float *x, const float *g, float *gw, float *gb, int N, int cin, int cout, int H, int W, void *stream)
+{
+    if (!x || !g || !gw || N <= 0 || H <= 0 || W <= 0) return PMCTF_EINVAL;
+    dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY, N);
+    if (grid.y > 65535 || grid.z > 65535) return PMCTF_ESHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cin == 1 && cout == 16) wgrad3x3_kernel<1, 16><<<grid, 256, 0, st>>>(x, g, gw, gb, H, W);
+    else if (cin == 16 && cout == 16) wgrad3x3_kernel<16, 16><<<grid, 256, 0, st>>>(x, g, gw, gb, H, W);
+    else if (cin == 16 && cout == 1) wgrad3x3_kernel<16, 1><<<grid, 256, 0, st>>>(x, g, gw, gb, H, W);
+    else return PMCTF_ESHAPE;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int pmctf_flow_warp_bwd(const float *gout, const float *im, const float *flow, const float *lin_x, const float *lin_y, float *gim,
+                                   float *gflow, int N, int C, int H, int W, int flowN, float sign, void *stream)
+{
+    if (!gout || !im || !flow || !lin_x || !lin_y || N <= 0 || C <= 0) return PMCTF_EINVAL;
+    if (H < 2 || W < 2 || flowN < 1 || (N % flowN) || H > 65535 || N > 65535) return PMCTF_ESHAPE;
+    dim3 grid((W + 255) / 256, H, N);
+    flow_warp_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gout, im, flow, lin_x, lin_y, gim, gflow, N, C, H, W, flowN, sign,
+                                                                (float)(((double)W - 1.0) / 2.0), (float)(((double)H - 1.0) / 2.0));
+    return (int)cudaGetLastError();
+}

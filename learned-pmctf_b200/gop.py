@@ -230,6 +230,41 @@ class GopCodec:
 
 
 # -------------------------------------------------------------------------------------------------
+def training_loss_hot_path(model, clips: torch.Tensor, mvs: Optional[Sequence[torch.Tensor]] = None, q_index: int = 8,
+                           lmbda: float = 0.05):
+    """The hot-path part of one training iteration (train_pMCTF_L.py:161-226, luma only as :137): dyadic MCTF analysis of a
+    batch of clips [B,G,1,H,W] (pairs of a stage batched along N), hp/lp pWave++ transform with the straight-through
+    quantiser, synthesis, inverse MCTF, and a rate-proxy + distortion loss.  Differentiable: under model.train() every op
+    runs on the training kernels (train.py).  mvs[s]: [B * pairs_s, 2, H, W] motion fields (zeros if None; the reference
+    gets them from SpyNet + MV codec, out of scope)."""
+    B, G, _, H, W = clips.shape
+    S = num_stages(G)
+    level = [clips[:, f] for f in range(G)]                     # each [B,1,H,W]
+    coded, rate = [], 0.0
+    for s in range(S):
+        n = len(level) // 2
+        ref = torch.cat(level[0::2], 0)                          # [n*B,1,H,W], pair-major
+        cur = torch.cat(level[1::2], 0)
+        mv = mvs[s] if mvs is not None else torch.zeros((n * B, 2, H, W), dtype=torch.float32, device=clips.device)
+        me = min(model.num_me_stages - 1, s)
+        L, Hh, _, _ = model.forward_MCTF(ref, cur, mv, stage_idx=me)
+        q, qll = model.hp_coder.q_pair(q_index, model.hp_qp_scale(me, q_index))
+        x_hat, hat = model.hp_coder.spatial_wavelet_dec(Hh, q, qll, post_process=False, return_symbols=True)
+        rate = rate + sum(v.abs().mean() for lvl in hat for v in hat[lvl].values())
+        coded.append((x_hat, mv, me))
+        level = list(L.split(B, 0))
+    q, qll = model.lp_coder.q_pair(q_index)
+    L_hat, hat = model.lp_coder.spatial_wavelet_dec(level[0], q, qll, post_process=False, return_symbols=True)
+    rate = rate + sum(v.abs().mean() for lvl in hat for v in hat[lvl].values())
+    rec = [L_hat]
+    for s in range(S - 1, -1, -1):
+        x_hat, mv, me = coded[s]
+        r, c = model.inverse_MCTF(torch.cat(rec, 0), x_hat, mv, stage_idx=me)
+        rec = [t for pair in zip(r.split(B, 0), c.split(B, 0)) for t in pair]
+    dist = sum(((a - clips[:, f]) ** 2).mean() for f, a in enumerate(rec)) / G
+    return dist + lmbda * rate, dist
+
+
 def synthetic_sequence(seq_id: int, n_frames: int, h0: int = 1080, w0: int = 1920, device="cuda"):
     """SURVEY.md section 8d synthetic input: band-limited noise (3x 9x9 box blur, rescaled to 16..235) translated by a
     per-sequence constant velocity, plus N(0, 2^2) per-frame noise, rounded to 8 bits.

@@ -71,6 +71,9 @@ class PredictUpdate(nn.Module):
         return self._pack.get([self])
 
     def forward(self, x):
+        from .. import train
+        if train.needs_grad(x, self):  # autograd: differentiable conv kernels (csrc/pmctf_train.cu)
+            return train.predict_update(self, x)
         return ops.predict_update(x, self.packed())
 
 
@@ -130,7 +133,13 @@ class iWave1D(nn.Module):
         return self._desc
 
     def forward_lift(self, x):
+        from .. import train
+        if train.needs_grad(x, self):
+            return train.iwave1d_forward(self, x)
         return ops.iwave1d_forward(x, self.descriptor())
 
     def backward_lift(self, l, h):
+        from .. import train
+        if train.needs_grad(l, h, self):
+            return train.iwave1d_backward(self, l, h)
         return ops.iwave1d_backward(l, h, self.descriptor())

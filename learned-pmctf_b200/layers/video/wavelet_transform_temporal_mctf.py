@@ -31,8 +31,14 @@ class TemporalLifting(nn.Module):
 
     def predict_filter(self, x):
         """(x + 0.1 * P_t(x)) * scale_p   (:27-35)"""
+        from ... import train
+        if train.needs_grad(x, self):
+            return train.temporal_filter(self, x, 0)
         return ops.temporal_filter(x, self.descriptor(), 0)
 
     def update_filter(self, x):
         """(x + 0.1 * U_t(x)) * scale_u   (:37-45)"""
+        from ... import train
+        if train.needs_grad(x, self):
+            return train.temporal_filter(self, x, 1)
         return ops.temporal_filter(x, self.descriptor(), 1)

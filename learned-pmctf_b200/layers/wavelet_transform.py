@@ -23,13 +23,23 @@ class LiftingScheme2D(nn.Module):
 
     def forward_lift_2d(self, x):
         """-> {'ll','lh','hl','hh','l','h'} (wavelet_transform.py:25-43)."""
+        from .. import train
+        if train.needs_grad(x, self):
+            return train.lift2d_forward(self, x)
         return ops.lift2d_forward(x, self.lift_h.descriptor(), want_lh_rows=True)
 
     def forward_lift_2d_bands(self, x):
         """Same without materialising the row-pass 'l'/'h' entries (nothing reads them)."""
+        from .. import train
+        if train.needs_grad(x, self):
+            return train.lift2d_forward(self, x)
         return ops.lift2d_forward(x, self.lift_h.descriptor(), want_lh_rows=False)
 
     def backward_lift_2d(self, subbands, ll_div=1.0, q=1.0):
         """wavelet_transform.py:45-57; ll_div / q fuse dequantize_subbands (pWave.py:191-202)."""
+        from .. import train
+        if train.needs_grad(subbands["ll"], subbands["lh"], subbands["hl"], subbands["hh"], self):
+            sb = {"ll": subbands["ll"] / ll_div, "lh": subbands["lh"] / q, "hl": subbands["hl"] / q, "hh": subbands["hh"] / q}
+            return train.lift2d_backward(self, sb)
         return ops.lift2d_backward(subbands["ll"], subbands["lh"], subbands["hl"], subbands["hh"],
                                    self.lift_h.descriptor(), ll_div, q)

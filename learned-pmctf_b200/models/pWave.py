@@ -105,6 +105,8 @@ class pWaveTransform:
     def decode_dequant(self, subbands_hat, q_scale, q_scale_ll):
         """dequantize_subbands (pWave.py:191-202) + decode (:150-157) with the divisions fused into
         the first loads of each inverse level."""
+        if self._train(subbands_hat[0]["lh"], q_scale, q_scale_ll):
+            return self.decode(self.dequantize_subbands(subbands_hat, q_scale, q_scale_ll))
         q = self._q_float(q_scale) if self.lossy else 1.0
         qll = self._q_float(q_scale_ll) if self.lossy else 1.0
         top = self.decomp_levels - 1
@@ -116,22 +118,41 @@ class pWaveTransform:
         return ll
 
     # --- quantisation (pWave.py:168-202) -------------------------------------------------------
+    def _train(self, *ts):
+        from .. import train
+        return train.needs_grad(*ts, self)
+
     def quantize_subband(self, subband, q_scale):
         """clamp(s * q, +-clip), not rounded (pWave.py:184-189)."""
+        if self._train(subband, q_scale):
+            from .. import train
+            return train.quantize(subband, q_scale, self.clip_value, self.lossy, do_round=False)
         return ops.quantize(subband, self._q_float(q_scale), self.clip_value, self.lossy, do_round=False)
 
     def quantize_subbands(self, subbands, q_scale, q_scale_ll):
         """round(clamp(s * q)) for every coded band (pWave.py:168-182)."""
-        q, qll = self._q_float(q_scale), self._q_float(q_scale_ll)
+        train_mode = self._train(subbands[0]["lh"], q_scale, q_scale_ll)
+        if train_mode:
+            from .. import train
+            q, qll = q_scale, q_scale_ll     # tensors stay in the graph: QP / QP_ll / hp_q_scale receive gradients
+        else:
+            q, qll = self._q_float(q_scale), self._q_float(q_scale_ll)
         out = {}
         for lvl in range(self.decomp_levels - 1, -1, -1):
             out[lvl] = {}
             for b in (("ll",) + BANDS if lvl == self.decomp_levels - 1 else BANDS):
-                out[lvl][b] = ops.quantize(subbands[lvl][b], qll if b == "ll" else q, self.clip_value, self.lossy,
-                                           do_round=self.lossy)
+                if train_mode:
+                    out[lvl][b] = train.quantize(subbands[lvl][b], qll if b == "ll" else q, self.clip_value, self.lossy, self.lossy)
+                else:
+                    out[lvl][b] = ops.quantize(subbands[lvl][b], qll if b == "ll" else q, self.clip_value, self.lossy,
+                                               do_round=self.lossy)
         return out
 
     def dequantize_subbands(self, subbands_hat, q_scale, q_scale_ll):
+        if self._train(next(iter(subbands_hat[0].values())), q_scale, q_scale_ll):
+            if not self.lossy:
+                return {lvl: dict(v) for lvl, v in subbands_hat.items()}
+            return {lvl: {b: v / (q_scale_ll if b == "ll" else q_scale) for b, v in subbands_hat[lvl].items()} for lvl in subbands_hat}
         q, qll = self._q_float(q_scale), self._q_float(q_scale_ll)
         out = {}
         for lvl in range(self.decomp_levels - 1, -1, -1):
@@ -139,6 +160,8 @@ class pWaveTransform:
         return out
 
     def dequantize_subband(self, subband, q_scale):
+        if self._train(subband, q_scale):
+            return subband / q_scale if self.lossy else subband
         return ops.dequantize(subband, self._q_float(q_scale), self.lossy)
 
     def code_planes(self, x, q: float, qll: float):

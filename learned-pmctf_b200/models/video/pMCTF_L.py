@@ -46,10 +46,19 @@ class MCTFMixin:
         """H = cur - P(warp(ref, mv)); L = ref + U(warp(H, -mv)) -> (L_t, H_t, pred, inv)  (pMCTF_L.py:297-312).
         Two launches: each fuses warp + PredictUpdate CNN + lifting arithmetic.  `mv_down=True`
         takes the luma motion field and applies the chroma 2x2-mean/2 on the fly (pMCTF_L.py:401)."""
+        from ... import train
+        if train.needs_grad(ref_frame, cur_frame, mv_hat, self.temporal_filtering):
+            return train.forward_mctf(self, ref_frame, cur_frame, mv_hat, stage_idx, mv_down)
         return ops.forward_mctf(ref_frame, cur_frame, mv_hat, self._temporal(stage_idx), mv_down, want_pred, **out)
 
     def inverse_MCTF(self, L_t, H_t, mv_hat, downscale=False, stage_idx=0, **out):
         """ref = L - U(warp(H, -mv)); cur = H + P(warp(ref, mv))  (pMCTF_L.py:314-330)."""
+        from ... import train
+        if train.needs_grad(L_t, H_t, mv_hat, self.temporal_filtering):
+            ref, cur = train.inverse_mctf(self, L_t, H_t, mv_hat, downscale, stage_idx)
+            if out.get("out_ref") is not None:  # caller-provided strided outputs (GopCodec.synthesis)
+                out["out_ref"].copy_(ref), out["out_cur"].copy_(cur)
+            return ref, cur
         return ops.inverse_mctf(L_t, H_t, mv_hat, self._temporal(stage_idx), downscale, **out)
 
 
