@@ -250,6 +250,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--conv-mode", default="tensor", choices=["tensor", "ffma"])
+    ap.add_argument("--torch-baseline", action="store_true",
+                    help="also time the same hot path written with stock torch ops (cuDNN / grid_sample) on this GPU; informational")
     ap.add_argument("--workload", default="gop16", choices=["gop16", "train"],
                     help="gop16: the headline metric (default); train: BASELINE configs[4] training step (not the headline)")
     args = ap.parse_args()
@@ -350,6 +352,29 @@ def main():
         assert torch.equal(host_stats.to(torch.float64)[:, :6], stats[rank].reshape(-1, G.N_STATS).cpu()[:, :6]), \
             "host-buffer path and resident path disagree"
 
+    torch_gpu = None
+    if args.torch_baseline and rank == 0:
+        # what the reference dispatches to on this GPU: stock ATen / cuDNN ops (PyTorch default: TF32 convolutions allowed)
+        from baseline import torch_stock as TS
+        Yb = pkg.ops.unpack_u8(y_u8[:GOP], hp, wp)
+        Cb = pkg.ops.unpack_u8(c_u8[:GOP].reshape(-1, H0 // 2, W0 // 2), hp // 2, wp // 2).view(GOP, 2, 1, hp // 2, wp // 2)
+        res = {}
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(2):
+                ty, tc_ = TS.code_gop(model, codec, Yb, Cb, mvs[0])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                ty, tc_ = TS.code_gop(model, codec, Yb, Cb, mvs[0])
+            torch.cuda.synchronize()
+            res["tf32" if tf32 else "fp32"] = GOP / ((time.perf_counter() - t0) / 2)
+        oy, oc, _ = codec.code_gop(Yb, Cb, mvs[0], want_stats=False)
+        torch_gpu = {"frames_per_s_cudnn_tf32": res["tf32"], "frames_per_s_cudnn_fp32": res["fp32"], "sample": "one 1080p GOP-16",
+                     "mean_abs_diff_vs_ours_luma": float((ty - oy).abs().mean()),
+                     "frac_luma_px_differing_by_more_than_0.5": float(((ty - oy).abs() > 0.5).float().mean()),
+                     "note": "same hot path with F.conv2d / F.grid_sample / ATen element-wise ops (baseline/torch_stock.py), no statistics; "
+                             "outputs differ from ours only where fp32 round-off flips a quantised symbol (diff columns are vs the fp32 run)"}
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -406,6 +431,7 @@ def main():
                        "conv_mode": mode,
                        "parallelism": f"gop-sharded dp{world}, all_gather of per-frame statistics per step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "torch_gpu_baseline": torch_gpu,
             "quality": {"mean_psnr_yuv_db": float(psnr[torch.isfinite(psnr)].mean()), "frames": int(psnr.numel())}}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -10,7 +10,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "lib", "libpmctf_b200.so")
+LIB_PATH = os.environ.get("PMCTF_LIB") or os.path.join(_HERE, "lib", "libpmctf_b200.so")  # PMCTF_LIB: profiling builds only
 SOURCES = [os.path.join(_HERE, "csrc", "pmctf_kernels.cu"), os.path.join(_HERE, "csrc", "pmctf_umma_test.cu"),
            os.path.join(_HERE, "csrc", "pmctf_lift_tc.cu"), os.path.join(_HERE, "csrc", "pmctf_train.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "pmctf_umma.cuh"), os.path.join(_HERE, "csrc", "pmctf_common.cuh")]

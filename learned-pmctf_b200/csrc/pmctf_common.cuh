@@ -25,7 +25,11 @@ __device__ __forceinline__ float tanh_det(float x, const float *__restrict__ tab
     const float ax = fminf(fabsf(x), PMCTF_TANH_XMAX);
     const float fi = rintf(ax * 32.0f);
     const float d = fmaf(fi, -0.03125f, ax);
+#if defined(PMCTF_WHATIF) && (PMCTF_WHATIF & 2)
+    const float T = fi * 0.003f;
+#else
     const float T = tab[(int)fi];
+#endif
     const float D1 = fmaf(-T, T, 1.0f);
     const float D2 = -(T * D1);
     const float D3 = (D1 * fmaf(-3.0f * T, T, 1.0f)) * -0.333333343f;

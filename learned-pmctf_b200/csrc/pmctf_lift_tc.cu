@@ -25,6 +25,10 @@
 #include "pmctf_common.cuh"
 #include "pmctf_umma.cuh"
 
+#ifndef PMCTF_WHATIF
+#define PMCTF_WHATIF 0   // timing experiments only (bit 0: no conv1 residual recompute, bit 1: no tanh table lookup, bit 2: no MMAs)
+#endif
+
 namespace pmctf {
 namespace tc {
 
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     umma::fence_after_sync();
                 }
                 if (umma::elect_one()) {
-                    issue_block(a_saddr + blk * 2048, b_saddr, tbase + slot * SLOT_COLS);
+                    if (!(PMCTF_WHATIF & 4)) issue_block(a_saddr + blk * 2048, b_saddr, tbase + slot * SLOT_COLS);
                     umma::commit(full0 + 8 * slot);
                 }
                 __syncwarp();
@@ -421,7 +425,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                             c1[0] = b0.x; c1[1] = b0.y; c1[2] = b0.z; c1[3] = b0.w; c1[4] = b1.x; c1[5] = b1.y; c1[6] = b1.z; c1[7] = b1.w;
                         }
 #pragma unroll
-                        for (int k = 0; k < 9; ++k) {
+                        for (int k = 0; k < (PMCTF_WHATIF & 1 ? 0 : 9); ++k) {
                             const float4 u0 = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + 8 * h);
                             const float4 u1 = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + 8 * h + 4);
                             c1[0] = fmaf(u0.x, sv[k], c1[0]); c1[1] = fmaf(u0.y, sv[k], c1[1]); c1[2] = fmaf(u0.z, sv[k], c1[2]);
