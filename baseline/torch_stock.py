@@ -113,3 +113,50 @@ def code_gop(model, codec, Y, C, mvs):
         n = r.size(0) // 2
         Lc = torch.stack([r.reshape(n, 2, *r.shape[-2:]), c.reshape(n, 2, *r.shape[-2:])], 1).reshape(-1, 1, *r.shape[-2:])
     return Ly, Lc.reshape(-1, 2, 1, *Lc.shape[-2:])
+
+
+class _StockCoder:
+    def __init__(self, coder):
+        self.c = coder
+
+    def q_pair(self, *a, **k):
+        return self.c.q_pair(*a, **k)
+
+    def spatial_wavelet_dec(self, x, q, qll, post_process=False, return_symbols=False):
+        """Differentiable version (straight-through round / clamp) of spatial_wavelet_dec above."""
+        w = self.c.wavelet_transform.lift_h
+        T = lambda t: t.permute(0, 1, 3, 2)  # noqa: E731
+        ll, bands = x, []
+        for _ in range(4):
+            l, h = fwd1d(w, ll)
+            a, b = fwd1d(w, T(l))
+            c, d = fwd1d(w, T(h))
+            bands.append((T(b), T(c), T(d)))
+            ll = T(a)
+        ste = lambda v: v + (torch.round(v.clamp(-8192, 8192)) - v).detach()  # noqa: E731
+        hat = {3: {"ll": ste(ll * qll)}}
+        for lvl in range(4):
+            hat.setdefault(lvl, {}).update({k: ste(v * q) for k, v in zip(("lh", "hl", "hh"), bands[lvl])})
+        y = hat[3]["ll"] / qll
+        for lvl in range(3, -1, -1):
+            y = bwd1d(w, T(bwd1d(w, T(y), T(hat[lvl]["lh"] / q))), T(bwd1d(w, T(hat[lvl]["hl"] / q), T(hat[lvl]["hh"] / q))))
+        return (y, hat) if return_symbols else y
+
+
+class StockModel:
+    """Adapter with the method surface gop.training_loss_hot_path uses, on stock torch ops (baseline for the training step)."""
+
+    def __init__(self, model):
+        self.m = model
+        self.num_me_stages = model.num_me_stages
+        self.hp_coder, self.lp_coder = _StockCoder(model.hp_coder), _StockCoder(model.lp_coder)
+
+    def hp_qp_scale(self, *a):
+        return self.m.hp_qp_scale(*a)
+
+    def forward_MCTF(self, ref, cur, mv, stage_idx=0):
+        L, Hh = forward_mctf(self.m.temporal_filtering[stage_idx], ref, cur, mv)
+        return L, Hh, None, None
+
+    def inverse_MCTF(self, L, Hh, mv, stage_idx=0):
+        return inverse_mctf(self.m.temporal_filtering[stage_idx], L, Hh, mv)

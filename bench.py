@@ -196,11 +196,11 @@ def build_model(pkg, dev):
 
 
 def run_train(args, pkg, G, par, dev, rank, world):
-    """BASELINE configs[4]: hot-path training step (forward + backward through warp, lifting and convs + AdamW), batch 8 of
-    synthetic 256x256 GOP-8 luma clips per GPU, on the training kernels (csrc/pmctf_train.cu).  Secondary line."""
+    """BASELINE configs[4]: hot-path training step (forward + backward through warp, lifting and convs + grad clip + AdamW), batch 8
+    of synthetic 256x256 GOP-8 luma clips per GPU, on the training kernels (csrc/pmctf_train.cu).  Secondary line.  The step is
+    captured once in a CUDA graph (whole-network capture: static input buffer, capturable AdamW) and replayed, because the
+    un-fused training kernels are otherwise launch-bound; `eager_ms_per_step` is the same step launched from Python."""
     import torch
-    model = build_model(pkg, dev).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
     B, GOP8, H, W = 8, 8, 256, 256
     g = torch.Generator(device=dev)
     g.manual_seed(7 + rank)
@@ -208,33 +208,82 @@ def run_train(args, pkg, G, par, dev, rank, world):
     clips = torch.stack([base[:, :, 8 + f:8 + f + H, 2 * f:2 * f + W] for f in range(GOP8)], 1).contiguous()
     mvs = [torch.randn((B * (GOP8 >> (s + 1)), 2, H, W), device=dev, generator=g) * 1.5 for s in range(3)]
     yh = clips.cpu().pin_memory()
-
-    def step():
-        x = yh.to(dev, non_blocking=True)
-        opt.zero_grad(set_to_none=True)
-        loss, dist = G.training_loss_hot_path(model, x, mvs, q_index=args.q_index)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)   # train_pMCTF_L.py:247-251
-        opt.step()
-        return float(loss)                                        # D2H read of the step's result
-
     W_, K = max(args.warmup, 3), max(args.steps, 1)
-    for _ in range(W_):
-        loss = step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        loss = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = par.max_over_ranks(e0.elapsed_time(e1) / K, dev)
+
+    def make(stock):
+        model = build_model(pkg, dev).train()
+        net = model
+        if stock:
+            from baseline import torch_stock as TS
+            net = TS.StockModel(model)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-5, capturable=True)
+        x_static = torch.empty_like(clips)
+        loss_static = torch.zeros((), device=dev)
+
+        def body():
+            opt.zero_grad(set_to_none=False)
+            loss, _ = G.training_loss_hot_path(net, x_static, mvs, q_index=args.q_index)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)   # train_pMCTF_L.py:247-251
+            opt.step()
+            loss_static.copy_(loss.detach())
+
+        def eager_step():
+            x_static.copy_(yh, non_blocking=True)
+            body()
+            return float(loss_static)                                 # D2H read of the step's result
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                                  # warm-up on a side stream, as graph capture requires
+            for _ in range(3):
+                eager_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            eager_step()
+        torch.cuda.synchronize()
+        eager_ms = 1e3 * (time.perf_counter() - t0) / 2
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+
+        def step():
+            x_static.copy_(yh, non_blocking=True)
+            graph.replay()
+            return float(loss_static)
+
+        for _ in range(W_):
+            loss = step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / K, eager_ms, loss
+
+    ms, eager_ms, loss = make(False)
+    ms = par.max_over_ranks(ms, dev)
+    stock = None
+    if args.torch_baseline and rank == 0:  # the same step on stock torch ops (cuDNN convs, grid_sample autograd), also graphed
+        res = {}
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            m2, e2, _ = make(True)
+            res["tf32" if tf32 else "fp32"] = (m2, e2)
+        stock = {"ms_per_step_cudnn_tf32_graphed": res["tf32"][0], "ms_per_step_cudnn_fp32_graphed": res["fp32"][0],
+                 "ms_per_step_cudnn_tf32_eager": res["tf32"][1], "ms_per_step_cudnn_fp32_eager": res["fp32"][1]}
     if rank == 0:
         print(json.dumps({"metric": "pMCTF-L hot-path training clips/s (GOP-8 256x256 luma, batch 8)", "value": world * B / (ms * 1e-3),
-                          "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms, "eager_ms_per_step": eager_ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "torch_gpu_baseline": stock,
                           "config": {"workload": "configs[4]: training step (forward + backward + grad clip + AdamW) on the hot path, batch 8 "
-                                                 "x GOP-8 x 256x256, injected motion fields, un-fused fp32 training kernels", "loss": loss}}), flush=True)
+                                                 "x GOP-8 x 256x256, injected motion fields, un-fused fp32 training kernels, CUDA-graph replay",
+                                     "loss": loss}}), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
