@@ -283,9 +283,14 @@ def test_errors(P, model):
         P.flow_warp(torch.zeros(1, 1, 8, 8).cuda().half(), torch.zeros(1, 2, 8, 8).cuda())
     with pytest.raises(RuntimeError):
         model.hp_coder.wavelet_transform.forward_lift_2d(torch.zeros(1, 1, 9, 8).cuda())  # odd height
+    # the fused kernels have no backward: the raw ops refuse tensors that require grad, while the modules switch to the
+    # differentiable training kernels (tests/test_gpu_train.py)
+    xg = torch.zeros(1, 1, 8, 8, device="cuda", requires_grad=True)
     with pytest.raises(NotImplementedError, match="backward"):
         with torch.enable_grad():
-            model.temporal_filtering[0].predict_filter(torch.zeros(1, 1, 8, 8, device="cuda", requires_grad=True))
+            P.ops.temporal_filter(xg, model.temporal_filtering[0].descriptor(), 0)
+    with torch.enable_grad():
+        assert model.temporal_filtering[0].predict_filter(xg).grad_fn is not None
     s = P._native.Step()
     assert P._native.lib().pmctf_lift_step(s, None) == -1  # EINVAL, nothing launched
 
