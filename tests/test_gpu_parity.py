@@ -323,3 +323,30 @@ def test_full_size_1080p_properties(model):
             q = 0.5 if b == "ll" else 0.25
             assert float((v - (y[lvl][b] * q).clamp(-8192, 8192)).abs().max()) <= 0.5 + 1e-3
     assert torch.isfinite(x_hat).all()
+
+
+# ---- randomised shape sweep: tile-boundary and ragged cases of the fused step (both conv modes) ------------------
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shapes_vs_oracle(P, model, weights, seed):
+    g = np.random.default_rng(100 + seed)
+    n = int(g.integers(1, 4))
+    h, w = int(g.integers(2, 75)), int(g.integers(2, 99))
+    x = rnd((n, 1, h, w), seed, -300, 300)
+    pu = orc.PU(sub_sd(weights, "temporal_filtering.1.U_t."))
+    assert_bitexact(npy(model.temporal_filtering[1].U_t(cu(x))), orc.predict_update(x, pu), f"PU {x.shape}")
+    if h >= 2 and w >= 2:
+        mv = smooth_flow(1, h, w, seed)
+        ref, cur = rnd((n, 1, h, w), seed + 50), rnd((n, 1, h, w), seed + 60)
+        Pt = orc.PU(sub_sd(weights, "temporal_filtering.1.P_t."))
+        got = model.forward_MCTF(cu(ref), cu(cur), cu(mv), stage_idx=1)
+        want = orc.forward_mctf(ref, cur, mv, Pt, pu)
+        for a, b, name in zip(got, want, ("L", "H", "pred", "inv")):
+            assert_bitexact(npy(a), b, f"forward_MCTF {name} {ref.shape}")
+    h2, w2 = 2 * int(g.integers(2, 40)), 2 * int(g.integers(2, 50))
+    xs = rnd((n, 1, h2, w2), seed + 7, -120, 130)
+    iw = orc.IWave(sub_sd(weights, "lp_coder.wavelet_transform.lift_h."))
+    d = model.lp_coder.wavelet_transform.forward_lift_2d(cu(xs))
+    wd = orc.lift2d_forward(xs, iw)
+    for k in ("ll", "lh", "hl", "hh"):
+        assert_bitexact(npy(d[k]), wd[k], f"lift2d {k} {xs.shape}")
+    assert_bitexact(npy(model.lp_coder.wavelet_transform.backward_lift_2d(d)), orc.lift2d_backward(wd, iw), f"lift2d inverse {xs.shape}")
