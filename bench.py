@@ -239,6 +239,7 @@ def run_train(args, pkg, G, par, dev, rank, world):
             for _ in range(3):
                 eager_step()
         torch.cuda.current_stream().wait_stream(side)
+        eager_step()                                                  # first step on this stream fills its allocator pool
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(2):

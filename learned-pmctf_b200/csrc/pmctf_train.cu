@@ -60,42 +60,66 @@ __global__ void __launch_bounds__(TX * TY) conv3x3_kernel(const float *__restric
 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(256) wgrad3x3_kernel(const float *__restrict__ x, const float *__restrict__ g, float *__restrict__ gw,
-                                                       float *__restrict__ gb, int H, int W)
+                                                       float *__restrict__ gb, int N, int H, int W)
 {
+    // persistent CTAs: each walks its share of the 32x8 tiles keeping the partial sums in registers, so the global atomics
+    // (which all land on the same few hundred addresses) are paid once per CTA instead of once per tile
+    constexpr int PAIRS = CIN * COUT, SPLIT = 256 / PAIRS;
     __shared__ float xs[CIN][TY + 2][TX + 2];
     __shared__ float gs[COUT][TY][TX];
+    __shared__ float red[(SPLIT > 1) ? 256 * 10 : 1];
     const int tid = threadIdx.x;
-    const int n = blockIdx.z, y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
-    const float *xp = x + (long long)n * CIN * H * W;
-    const float *gp = g + (long long)n * COUT * H * W;
-    for (int i = tid; i < CIN * (TY + 2) * (TX + 2); i += 256) {
-        const int ci = i / ((TY + 2) * (TX + 2)), rem = i % ((TY + 2) * (TX + 2));
-        const int r = rem / (TX + 2), c = rem % (TX + 2);
-        const int gy = y0 - 1 + r, gx = x0 - 1 + c;
-        xs[ci][r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? xp[((long long)ci * H + gy) * W + gx] : 0.0f;
-    }
-    for (int i = tid; i < COUT * TY * TX; i += 256) {
-        const int co = i / (TY * TX), rem = i % (TY * TX);
-        const int r = rem / TX, c = rem % TX;
-        const int gy = y0 + r, gx = x0 + c;
-        gs[co][r][c] = (gy < H && gx < W) ? gp[((long long)co * H + gy) * W + gx] : 0.0f;
-    }
-    __syncthreads();
-    // one (co, ci) pair per thread, the tile's pixels split over the remaining threads
-    constexpr int PAIRS = CIN * COUT, SPLIT = 256 / PAIRS;
-    const int pair = tid % PAIRS, part = tid / PAIRS;
+    const int pair = tid % PAIRS, part = tid / PAIRS;   // one (co, ci) pair per thread, a tile's pixels split over `SPLIT` parts
     const int co = pair / CIN, ci = pair % CIN;
+    const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY;
+    const int per_img = tiles_x * tiles_y, total = per_img * N;
     float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, bsum = 0.0f;
-    for (int p = part; p < TY * TX; p += SPLIT) {
-        const int r = p / TX, c = p % TX;
-        const float gv = gs[co][r][c];
-        bsum += gv;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int n = t / per_img, rem = t - n * per_img;
+        const int y0 = (rem / tiles_x) * TY, x0 = (rem % tiles_x) * TX;
+        const float *xp = x + (long long)n * CIN * H * W;
+        const float *gp = g + (long long)n * COUT * H * W;
+        __syncthreads();
+        for (int i = tid; i < CIN * (TY + 2) * (TX + 2); i += 256) {
+            const int c_ = i / ((TY + 2) * (TX + 2)), r2 = i % ((TY + 2) * (TX + 2));
+            const int r = r2 / (TX + 2), c = r2 % (TX + 2);
+            const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+            xs[c_][r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? xp[((long long)c_ * H + gy) * W + gx] : 0.0f;
+        }
+        for (int i = tid; i < COUT * TY * TX; i += 256) {
+            const int c_ = i / (TY * TX), r2 = i % (TY * TX);
+            const int r = r2 / TX, c = r2 % TX;
+            const int gy = y0 + r, gx = x0 + c;
+            gs[c_][r][c] = (gy < H && gx < W) ? gp[((long long)c_ * H + gy) * W + gx] : 0.0f;
+        }
+        __syncthreads();
+        for (int p = part; p < TY * TX; p += SPLIT) {
+            const int r = p / TX, c = p % TX;
+            const float gv = gs[co][r][c];
+            bsum += gv;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) acc[k] = fmaf(gv, xs[ci][r + k / 3][c + k % 3], acc[k]);
+            for (int k = 0; k < 9; ++k) acc[k] = fmaf(gv, xs[ci][r + k / 3][c + k % 3], acc[k]);
+        }
     }
+    if (SPLIT > 1) { // fold the parts of a pair inside the CTA
+        __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 9; ++k) atomicAdd(gw + (co * CIN + ci) * 9 + k, acc[k]);
-    if (gb && ci == 0) atomicAdd(gb + co, bsum);
+        for (int k = 0; k < 9; ++k) red[tid * 10 + k] = acc[k];
+        red[tid * 10 + 9] = bsum;
+        __syncthreads();
+        if (part == 0) {
+            for (int q = 1; q < SPLIT; ++q) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc[k] += red[(pair + q * PAIRS) * 10 + k];
+                bsum += red[(pair + q * PAIRS) * 10 + 9];
+            }
+        }
+    }
+    if (part == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) atomicAdd(gw + (co * CIN + ci) * 9 + k, acc[k]);
+        if (gb && ci == 0) atomicAdd(gb + co, bsum);
+    }
 }
 
 __global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ im,
@@ -166,12 +190,13 @@ extern "C" int pmctf_conv3x3(const float *x, const float *w, const float *b, flo
 extern "C" int pmctf_conv3x3_wgrad(const float *x, const float *g, float *gw, float *gb, int N, int cin, int cout, int H, int W, void *stream)
 {
     if (!x || !g || !gw || N <= 0 || H <= 0 || W <= 0) return PMCTF_EINVAL;
-    dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY, N);
-    if (grid.y > 65535 || grid.z > 65535) return PMCTF_ESHAPE;
+    const long long tiles = (long long)((W + TX - 1) / TX) * ((H + TY - 1) / TY) * N;
+    if (tiles > 0x7fffffffLL) return PMCTF_ESHAPE;
+    const unsigned grid = (unsigned)(tiles < 592 ? tiles : 592); // 4 CTAs per SM on 148 SMs
     cudaStream_t st = (cudaStream_t)stream;
-    if (cin == 1 && cout == 16) wgrad3x3_kernel<1, 16><<<grid, 256, 0, st>>>(x, g, gw, gb, H, W);
-    else if (cin == 16 && cout == 16) wgrad3x3_kernel<16, 16><<<grid, 256, 0, st>>>(x, g, gw, gb, H, W);
-    else if (cin == 16 && cout == 1) wgrad3x3_kernel<16, 1><<<grid, 256, 0, st>>>(x, g, gw, gb, H, W);
+    if (cin == 1 && cout == 16) wgrad3x3_kernel<1, 16><<<grid, 256, 0, st>>>(x, g, gw, gb, N, H, W);
+    else if (cin == 16 && cout == 16) wgrad3x3_kernel<16, 16><<<grid, 256, 0, st>>>(x, g, gw, gb, N, H, W);
+    else if (cin == 16 && cout == 1) wgrad3x3_kernel<16, 1><<<grid, 256, 0, st>>>(x, g, gw, gb, N, H, W);
     else return PMCTF_ESHAPE;
     return (int)cudaGetLastError();
 }
