@@ -37,6 +37,54 @@ __device__ __forceinline__ float tanh_det(float x, const float *__restrict__ tab
     return copysignf(y, x);
 }
 
+// two independent IEEE fp32 FMAs in one instruction (sm_100 FFMA2): acc.x = fma(a.x, b, acc.x), acc.y = fma(a.y, b, acc.y).
+// Bit-identical to two fmaf() calls; it only halves the issue slots of the CUDA-core convolution chains.
+__device__ __forceinline__ float2 ffma2(float2 a, float b, float2 acc)
+{
+    unsigned long long d;
+    const float2 bb = make_float2(b, b);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long *>(&a)), "l"(*reinterpret_cast<const unsigned long long *>(&bb)),
+          "l"(*reinterpret_cast<const unsigned long long *>(&acc)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+
+__device__ __forceinline__ float2 fma2v(float2 a, float2 b, float2 c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long *>(&a)), "l"(*reinterpret_cast<const unsigned long long *>(&b)),
+          "l"(*reinterpret_cast<const unsigned long long *>(&c)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+__device__ __forceinline__ float2 mul2v(float2 a, float2 b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long *>(&a)), "l"(*reinterpret_cast<const unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+
+// tanh_det of two values at once on the packed fp32x2 pipe: the same operations in the same order per element
+__device__ __forceinline__ float2 tanh_det2(float2 x, const float *__restrict__ tab)
+{
+    const float2 ax = make_float2(fminf(fabsf(x.x), PMCTF_TANH_XMAX), fminf(fabsf(x.y), PMCTF_TANH_XMAX));
+    const float2 t = mul2v(ax, make_float2(32.0f, 32.0f));
+    const float2 fi = make_float2(rintf(t.x), rintf(t.y));
+    const float2 d = fma2v(fi, make_float2(-0.03125f, -0.03125f), ax);
+    const float2 T = make_float2(tab[(int)fi.x], tab[(int)fi.y]);
+    const float2 nT = make_float2(-T.x, -T.y);
+    const float2 D1 = fma2v(nT, T, make_float2(1.0f, 1.0f));
+    const float2 D2 = mul2v(nT, D1);                                             // -(T * D1)
+    const float2 u = fma2v(mul2v(T, make_float2(-3.0f, -3.0f)), T, make_float2(1.0f, 1.0f));
+    const float2 D3 = mul2v(mul2v(D1, u), make_float2(-0.333333343f, -0.333333343f));
+    const float2 y = fma2v(fma2v(fma2v(D3, d, D2), d, D1), d, T);
+    return make_float2(copysignf(y.x, x.x), copysignf(y.y, x.y));
+}
+
 struct PlaneD {
     float *p;
     long long gs, bs, rs, cs;

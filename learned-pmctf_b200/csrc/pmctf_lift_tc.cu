@@ -71,7 +71,6 @@ constexpr int SMEM_BYTES = SM_BAR + 128;
 static_assert(SM_S % 128 == 0 && SM_T % 128 == 0 && SM_A1 % 128 == 0 && SM_A2 % 128 == 0 && SM_BAR % 128 == 0, "alignment");
 static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 
-constexpr long long STAGGER_CYCLES = 11000;
 constexpr int MMA_WARP = 4 * NGRP;
 constexpr int NT = 32 * (MMA_WARP + 1);   // 8 epilogue warps + 1 MMA warp
 
@@ -189,22 +188,6 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     bool ok = true;
     const bool xfast_src = a.src.cs <= a.src.rs;
 
-    // Two CTAs share an SM.  Launched together they would run in lockstep (both on the CUDA cores, then both on the
-    // tensor core); the second CTA to arrive on an SM therefore starts half a tile period late, so that one CTA's
-    // CUDA-core phases overlap the other's tensor-core phases for the rest of the persistent loop.
-    if (err && n_tiles > (int)gridDim.x) {
-        if (tid == 0) {
-            uint32_t smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            const int order = atomicAdd(err + 64 + (smid & 255), 1);
-            if (order & 1) {
-                const long long t0 = clock64();
-                while (clock64() - t0 < STAGGER_CYCLES) { }
-            }
-        }
-        __syncthreads();
-    }
-
     // ---- persistent loop over tiles: every accumulator slot completes exactly twice per layer, so the mbarrier
     //      parities are the same for every tile ------------------------------------------------------------------
 #pragma unroll 1
@@ -311,15 +294,16 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
             const int gy = y0 - 3 + r, gx = x0 - 3 + c;
             uint32_t w0 = 0, w1 = 0, w2 = 0;
             if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                float acc0 = b.x, acc1 = b.y, acc2 = b.z, acc3 = b.w;
+                float2 a01 = make_float2(b.x, b.y), a23 = make_float2(b.z, b.w);
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
                     const int ky = k / 3, kx = k - ky * 3;
                     const float v = ss[(r + ky) * S_P + c + kx] * in_mul;
-                    acc0 = fmaf(wv[k].x, v, acc0); acc1 = fmaf(wv[k].y, v, acc1);
-                    acc2 = fmaf(wv[k].z, v, acc2); acc3 = fmaf(wv[k].w, v, acc3);
+                    a01 = ffma2(make_float2(wv[k].x, wv[k].y), v, a01);
+                    a23 = ffma2(make_float2(wv[k].z, wv[k].w), v, a23);
                 }
-                push_digits4(tanh_det(acc0, ttab), tanh_det(acc1, ttab), tanh_det(acc2, ttab), tanh_det(acc3, ttab), w0, w1, w2);
+                const float2 t01 = tanh_det2(a01, ttab), t23 = tanh_det2(a23, ttab);
+                push_digits4(t01.x, t01.y, t23.x, t23.y, w0, w1, w2);
             }
             uint8_t *d = A1 + px * 16 + cq * 4;
             *reinterpret_cast<uint32_t *>(d) = w0;
@@ -386,12 +370,14 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                             if (valid) {
                                 const float4 bv = *reinterpret_cast<const float4 *>(bias + 8 * h + 4 * j);
                                 const float bq[4] = {bv.x, bv.y, bv.z, bv.w};
-                                float t[4];
+                                float u[4];
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     const int ch = 4 * j + q;
-                                    t[q] = tanh_det(fmaf(combine(o[0][ch], o[1][ch], o[2][ch], o[3][ch], o[4][ch]), scale, bq[q]), ttab);
+                                    u[q] = fmaf(combine(o[0][ch], o[1][ch], o[2][ch], o[3][ch], o[4][ch]), scale, bq[q]);
                                 }
+                                const float2 t01 = tanh_det2(make_float2(u[0], u[1]), ttab), t23 = tanh_det2(make_float2(u[2], u[3]), ttab);
+                                const float t[4] = {t01.x, t01.y, t23.x, t23.y};
                                 push_digits4(t[0], t[1], t[2], t[3], w0, w1, w2);
                             }
                             w[0][2 * h + j] = w0; w[1][2 * h + j] = w1; w[2][2 * h + j] = w2;
@@ -418,20 +404,21 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                         for (int k = 0; k < 5; ++k) tmem_ld8(taddr + 16 * k + 8 * h, o[k]);
                         umma::tmem_ld_wait();
                         // conv1 at this position, the identical fma chains (lifting_1d.py:45 residual), 8 channels
-                        float c1[8];
+                        float2 c1p[4];
                         {
                             const float4 b0 = *reinterpret_cast<const float4 *>(sf + F_B1 + 8 * h);
                             const float4 b1 = *reinterpret_cast<const float4 *>(sf + F_B1 + 8 * h + 4);
-                            c1[0] = b0.x; c1[1] = b0.y; c1[2] = b0.z; c1[3] = b0.w; c1[4] = b1.x; c1[5] = b1.y; c1[6] = b1.z; c1[7] = b1.w;
+                            c1p[0] = make_float2(b0.x, b0.y); c1p[1] = make_float2(b0.z, b0.w);
+                            c1p[2] = make_float2(b1.x, b1.y); c1p[3] = make_float2(b1.z, b1.w);
                         }
 #pragma unroll
                         for (int k = 0; k < (PMCTF_WHATIF & 1 ? 0 : 9); ++k) {
                             const float4 u0 = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + 8 * h);
                             const float4 u1 = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + 8 * h + 4);
-                            c1[0] = fmaf(u0.x, sv[k], c1[0]); c1[1] = fmaf(u0.y, sv[k], c1[1]); c1[2] = fmaf(u0.z, sv[k], c1[2]);
-                            c1[3] = fmaf(u0.w, sv[k], c1[3]); c1[4] = fmaf(u1.x, sv[k], c1[4]); c1[5] = fmaf(u1.y, sv[k], c1[5]);
-                            c1[6] = fmaf(u1.z, sv[k], c1[6]); c1[7] = fmaf(u1.w, sv[k], c1[7]);
+                            c1p[0] = ffma2(make_float2(u0.x, u0.y), sv[k], c1p[0]); c1p[1] = ffma2(make_float2(u0.z, u0.w), sv[k], c1p[1]);
+                            c1p[2] = ffma2(make_float2(u1.x, u1.y), sv[k], c1p[2]); c1p[3] = ffma2(make_float2(u1.z, u1.w), sv[k], c1p[3]);
                         }
+                        const float c1[8] = {c1p[0].x, c1p[0].y, c1p[1].x, c1p[1].y, c1p[2].x, c1p[2].y, c1p[3].x, c1p[3].y};
                         const float4 bv0 = *reinterpret_cast<const float4 *>(bias + 8 * h), bv1 = *reinterpret_cast<const float4 *>(bias + 8 * h + 4);
                         const float bq[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
 #pragma unroll
