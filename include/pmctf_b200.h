@@ -232,6 +232,7 @@ typedef struct {
     unsigned a_off, a_lbo, a_sbo;
     unsigned b_off, b_lbo, b_sbo;
     unsigned n, d_col, accumulate;
+    unsigned a_unsigned; /* 1: the A bytes are unsigned (u8 x s8), 0: signed */
 } pmctf_umma_op_t;
 int pmctf_umma_selftest(const signed char *A, int a_bytes, const signed char *B, int b_bytes, const pmctf_umma_op_t *ops,
                         int n_ops, int n_blocks, int block_stride_bytes, int out_cols, int *out, int repeat,

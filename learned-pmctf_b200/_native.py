@@ -47,7 +47,7 @@ class IWave(C.Structure):
 
 
 class UmmaOp(C.Structure):
-    _fields_ = [(n, C.c_uint) for n in ("a_off", "a_lbo", "a_sbo", "b_off", "b_lbo", "b_sbo", "n", "d_col", "accumulate")]
+    _fields_ = [(n, C.c_uint) for n in ("a_off", "a_lbo", "a_sbo", "b_off", "b_lbo", "b_sbo", "n", "d_col", "accumulate", "a_unsigned")]
 
 
 class Temporal(C.Structure):

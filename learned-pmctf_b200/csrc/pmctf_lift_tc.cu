@@ -4,8 +4,9 @@
 // lifting accumulate, one HBM pass.  conv1 (1->16, K = 9) and conv4 (16->1) stay fp32 FMA chains on the CUDA
 // cores; conv2 and conv3 (94 % of the FLOPs) are implicit GEMMs on tcgen05 in EXACT integer arithmetic:
 //
-//   * their inputs are tanh outputs in [-1, 1]: V = rint(a * 2^22), split into three signed-byte digits
-//     V = d0*2^16 + d1*2^8 + d2; weights likewise W = rint(w * 2^Sw) = e0*2^16 + e1*2^8 + e2 (Sw per layer);
+//   * their inputs are tanh outputs in [-1, 1]: V = rint(a * 2^22) is split into its two's complement bytes
+//     V = d0*2^16 + u1*2^8 + u2 (d0 signed, u1/u2 unsigned: s8 and u8 MMA operands); the weights W = rint(w * 2^Sw)
+//     into three signed-byte digits e0*2^16 + e1*2^8 + e2 (Sw per layer);
 //   * a pixel's 16 channels of one digit are one 16-byte record of a K-major, un-swizzled UMMA operand, the
 //     tile is a linear pixel array with pitch 38, so a filter tap is only a different descriptor start
 //     address and two taps form the K = 32 of one kind::i8 MMA (leading byte offset = tap distance);
@@ -103,7 +104,7 @@ __device__ __forceinline__ void issue_block(uint32_t a_saddr, uint32_t b_saddr, 
             if (tp == 0 && d == 0)
                 umma::mma_s8(d_tmem, ad, umma::smem_desc(b_saddr + Q0_OFF, 1280, 128), umma::idesc_s8(80), 0u);
             else
-                umma::mma_s8(d_tmem + 16 * d, ad, umma::smem_desc(b, 768, 128), umma::idesc_s8(48), 1u);
+                umma::mma_s8(d_tmem + 16 * d, ad, umma::smem_desc(b, 768, 128), umma::idesc_s8(48, d > 0), 1u);
         }
     }
 }
@@ -116,17 +117,16 @@ __device__ __forceinline__ float combine(uint32_t o0, uint32_t o1, uint32_t o2, 
     return (float)S;
 }
 
-// V = rint(a * 2^22) of four channels -> the three signed-byte digit words (V = d0*2^16 + d1*2^8 + d2 with
-// d2 = (int8)V, V1 = (V + 128) >> 8, d1 = (int8)V1, d0 = (V1 + 128) >> 8), channel q in byte q of each word
+// V = rint(a * 2^22) of four channels -> the three digit words, channel q in byte q of each word.  The digits are simply the
+// two's complement bytes of V: V = d0*2^16 + u1*2^8 + u2 with d0 = V >> 16 signed and u1, u2 in [0, 255]; the MMAs read
+// plane 0 as s8 and planes 1, 2 as u8 (the weight digits stay signed), so no carry arithmetic is needed here.
 __device__ __forceinline__ void push_digits4(float a0, float a1, float a2, float a3, uint32_t &w0, uint32_t &w1, uint32_t &w2)
 {
     const int Va = __float2int_rn(a0 * 4194304.0f), Vb = __float2int_rn(a1 * 4194304.0f);
     const int Vc = __float2int_rn(a2 * 4194304.0f), Vd = __float2int_rn(a3 * 4194304.0f);
-    const int Va1 = (Va + 128) >> 8, Vb1 = (Vb + 128) >> 8, Vc1 = (Vc + 128) >> 8, Vd1 = (Vd + 128) >> 8;
-    const int Va2 = (Va1 + 128) >> 8, Vb2 = (Vb1 + 128) >> 8, Vc2 = (Vc1 + 128) >> 8, Vd2 = (Vd1 + 128) >> 8;
     w2 = __byte_perm(__byte_perm(Va, Vb, 0x0040), __byte_perm(Vc, Vd, 0x0040), 0x5410);
-    w1 = __byte_perm(__byte_perm(Va1, Vb1, 0x0040), __byte_perm(Vc1, Vd1, 0x0040), 0x5410);
-    w0 = __byte_perm(__byte_perm(Va2, Vb2, 0x0040), __byte_perm(Vc2, Vd2, 0x0040), 0x5410);
+    w1 = __byte_perm(__byte_perm(Va, Vb, 0x0051), __byte_perm(Vc, Vd, 0x0051), 0x5410);
+    w0 = __byte_perm(__byte_perm(Va, Vb, 0x0062), __byte_perm(Vc, Vd, 0x0062), 0x5410);
 }
 
 template <int SRC>

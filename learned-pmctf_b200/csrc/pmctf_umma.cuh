@@ -27,10 +27,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
-// 32-bit instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 128, N = n
-__host__ __device__ __forceinline__ constexpr uint32_t idesc_s8(uint32_t n)
+// 32-bit instruction descriptor: D = s32, B = signed int8, A = signed (default) or unsigned int8, both K-major, M = 128, N = n
+__host__ __device__ __forceinline__ constexpr uint32_t idesc_s8(uint32_t n, bool a_unsigned = false)
 {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+    return (2u << 4) | ((a_unsigned ? 0u : 1u) << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread on behalf of the CTA

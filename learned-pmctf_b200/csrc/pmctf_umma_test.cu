@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const int8_t *__r
         s_ad[tid] = umma::smem_desc(a0 + op.a_off, op.a_lbo, op.a_sbo);
         s_bd[tid] = umma::smem_desc(b0 + op.b_off, op.b_lbo, op.b_sbo);
         s_dcol[tid] = tbase + op.d_col;
-        s_idesc[tid] = umma::idesc_s8(op.n);
+        s_idesc[tid] = umma::idesc_s8(op.n, op.a_unsigned != 0);
         s_acc[tid] = op.accumulate;
     }
     __syncthreads();

@@ -20,7 +20,7 @@ def run(A, B, ops, n_blocks, block_stride, out_cols, repeat=1):
     pad = lambda x: np.concatenate([x, np.zeros((-x.size) % 16, np.int8)])  # noqa: E731
     A, B = pad(A), pad(B)
     dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
-    arr = (nat.UmmaOp * len(ops))(*[nat.UmmaOp(**o) for o in ops])
+    arr = (nat.UmmaOp * len(ops))(*[nat.UmmaOp(**{"a_unsigned": 0, **o}) for o in ops])
     dops = torch.from_numpy(np.frombuffer(bytes(arr), np.uint8).copy()).cuda()
     out = torch.zeros((n_blocks, 128, out_cols), dtype=torch.int32, device="cuda")
     cyc = torch.zeros(n_blocks, dtype=torch.int64, device="cuda")
@@ -69,6 +69,24 @@ def test_accumulate_and_column_offsets():
            mk(32, 0, 48, 32, 1)]  # every column group is initialised (accumulate=0) before it is accumulated into
     got, _ = run(A, B, ops, 1, 0, 80)
     assert np.array_equal(got, U.emulate(A, B, ops, 1, 0, 80))
+
+
+def test_mixed_sign_u8_times_s8():
+    """kind::i8 with an unsigned A operand and a signed B operand (instruction descriptor a_format = 0, b_format = 1)."""
+    g = np.random.default_rng(21)
+    A = g.integers(-128, 128, 2 * 128 * 16, dtype=np.int8)
+    B = g.integers(-128, 128, 2 * 48 * 16, dtype=np.int8)
+    for au in (0, 1):
+        ops = [dict(a_off=0, a_lbo=128 * 16, a_sbo=128, b_off=0, b_lbo=48 * 16, b_sbo=128, n=48, d_col=0, accumulate=0, a_unsigned=au)]
+        got, _ = run(A, B, ops, 1, 0, 48)
+        assert np.array_equal(got, U.emulate(A, B, ops, 1, 0, 48)), f"a_unsigned={au}"
+    pitch, n_blocks = 38, 3
+    npix = n_blocks * 128 + 2 * pitch + 2 + 8
+    Aint = g.integers(-2 ** 22, 2 ** 22 + 1, (npix, 16))
+    Wint = g.integers(-2 ** 22, 2 ** 22 + 1, (16, 16, 3, 3))
+    Ab = np.concatenate([d.reshape(-1) for d in U.split_digits_twos(Aint)])
+    got, _ = run(Ab, U.pack_weights(Wint), U.conv_ops(pitch, npix * 16, twos=True), n_blocks, 2048, 80)
+    assert np.array_equal(U.combine_orders(got).reshape(-1, 16), U.conv_exact(Aint, Wint, pitch, n_blocks * 128))
 
 
 def test_digit_split_convolution_and_timing():

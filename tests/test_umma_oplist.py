@@ -28,3 +28,17 @@ def test_conv_oplist_is_exact():
     assert np.abs(out).max() < 2 ** 31, "accumulator groups must fit int32"
     got = U.combine_orders(out).reshape(n_blocks * 128, 16)
     assert np.array_equal(got, U.conv_exact(Aint, Wint, pitch, n_blocks * 128))
+
+
+def test_conv_oplist_twos_complement_activation_digits():
+    """Activation digits as plain two's complement bytes (plane 0 signed, planes 1 and 2 unsigned: u8 x s8 MMAs)."""
+    g = np.random.default_rng(1)
+    pitch, n_blocks = 38, 2
+    npix = n_blocks * 128 + 2 * pitch + 2 + 8
+    Aint = g.integers(-2 ** 22, 2 ** 22 + 1, (npix, 16))
+    Wint = g.integers(-2 ** 22, 2 ** 22 + 1, (16, 16, 3, 3))
+    Aint[3, 5], Aint[4, 6] = 2 ** 22, -2 ** 22
+    A = np.concatenate([d.reshape(-1) for d in U.split_digits_twos(Aint)])
+    out = U.emulate(A, U.pack_weights(Wint), U.conv_ops(pitch, npix * 16, twos=True), n_blocks, 128 * 16, 80)
+    assert np.abs(out).max() < 2 ** 31
+    assert np.array_equal(U.combine_orders(out).reshape(n_blocks * 128, 16), U.conv_exact(Aint, Wint, pitch, n_blocks * 128))

@@ -7,7 +7,8 @@ TAP_PAIRS = [((0, 0), (0, 1)), ((1, 0), (1, 1)), ((2, 0), (2, 1)), ((0, 2), (1, 
 
 def emulate(A, B, ops, n_blocks, block_stride, out_cols):
     """A, B: int8 byte images; ops: dicts with the pmctf_umma_op_t fields.  -> int64 [n_blocks, 128, out_cols]."""
-    A = np.asarray(A, np.int8).astype(np.int64)
+    A_s = np.asarray(A, np.int8).astype(np.int64)
+    A_u = np.asarray(A, np.int8).view(np.uint8).astype(np.int64)
     B = np.asarray(B, np.int8).astype(np.int64)
     out = np.zeros((n_blocks, 128, out_cols), np.int64)
     r = np.arange(128)
@@ -18,6 +19,7 @@ def emulate(A, B, ops, n_blocks, block_stride, out_cols):
             rn = np.arange(n)
             brow = op["b_off"] + (rn % 8) * 16 + (rn // 8) * op["b_sbo"]
             acc = np.zeros((128, n), np.int64)
+            A = A_u if op.get("a_unsigned") else A_s
             for c in range(2):
                 a = A[(arow + c * op["a_lbo"])[:, None] + np.arange(16)[None, :]]
                 b = B[(brow + c * op["b_lbo"])[:, None] + np.arange(16)[None, :]]
@@ -38,6 +40,15 @@ def split_digits(v):
     return d0.astype(np.int8), d1.astype(np.int8), d2.astype(np.int8)
 
 
+def split_digits_twos(v):
+    """int (|v| <= 2^22) -> two's complement byte digits: d0 = v >> 16 (signed), u1, u2 in [0, 255] with
+    v = d0*65536 + u1*256 + u2 -- what the kernel stores for the activations (plane 0 signed, planes 1, 2 unsigned)."""
+    v = np.asarray(v, np.int64)
+    u2, u1, d0 = v & 0xFF, (v >> 8) & 0xFF, v >> 16
+    assert np.all(np.abs(d0) <= 127) and np.all(d0 * 65536 + u1 * 256 + u2 == v)
+    return d0.astype(np.int8), u1.astype(np.uint8).view(np.int8), u2.astype(np.uint8).view(np.int8)
+
+
 def pack_weights(W):
     """W int [16 co, 16 ci, 3, 3] (|W| <= 2^22) -> int8 image (10240 B): per tap pair a [2 chunks][48 rows = (digit, co)][16 ci]
     block (5 x 1536 B), followed by the 80-row copy of tap pair 0 ([2][80][16], rows 48..79 zero) at byte 7680."""
@@ -54,7 +65,7 @@ def pack_weights(W):
     return np.concatenate([out.reshape(-1), first.reshape(-1)])
 
 
-def conv_ops(pitch, plane_bytes):
+def conv_ops(pitch, plane_bytes, twos=False):
     """Op list of one 128-pixel block of the 16->16 3x3 convolution (15 MMAs): D columns [16*i, 16*i+16) accumulate the
     digit products of order i (weight 2^(32-8i)): a_d x [w0; w1; w2] lands in groups d, d+1, d+2.  The first MMA uses the
     80-row image (zero rows 48..79) without accumulation and thereby initialises all five groups."""
@@ -64,10 +75,11 @@ def conv_ops(pitch, plane_bytes):
         lbo = ((t1[0] * pitch + t1[1]) - (t0[0] * pitch + t0[1])) * 16 if t1 is not None else 16
         for d in range(3):
             if tp == 0 and d == 0:
-                ops.append(dict(a_off=a_off, a_lbo=lbo, a_sbo=128, b_off=7680, b_lbo=1280, b_sbo=128, n=80, d_col=0, accumulate=0))
+                ops.append(dict(a_off=a_off, a_lbo=lbo, a_sbo=128, b_off=7680, b_lbo=1280, b_sbo=128, n=80, d_col=0, accumulate=0,
+                                a_unsigned=0))
             else:
                 ops.append(dict(a_off=d * plane_bytes + a_off, a_lbo=lbo, a_sbo=128, b_off=tp * 1536, b_lbo=768, b_sbo=128,
-                                n=48, d_col=16 * d, accumulate=1))
+                                n=48, d_col=16 * d, accumulate=1, a_unsigned=int(twos and d > 0)))
     return ops
 
 
