@@ -449,7 +449,7 @@ def main():
             "kernel": "lift_step_tc_kernel<PLANE|WARP|SKIP3>: warp/skip + PredictUpdate CNN + lifting accumulate; conv2/conv3 as exact "
                       "int8 digit-split implicit GEMMs on tcgen05 (UTCIMMA, accumulators in TMEM), conv1/conv4/tanh on CUDA cores",
             "traffic": 35.6e6,
-            "traffic_note": "dram__bytes_read+write of ONE launch from ncu --set full (profiles/r1c_lift_step_tc_ncu.txt): the 1080p luma "
+            "traffic_note": "dram__bytes_read+write of ONE launch from ncu --set full (profiles/r1g_lift_step_tc_ncu.txt): the 1080p luma "
                             "temporal step, 2.21 Mpx, algorithmic 44.2 MB (20 B/px); outputs stay in the 126 MB L2, so DRAM traffic is "
                             "below the algorithmic bytes -- no wasted re-reads.  Not measured live.",
             "executed_int8_tops": ks["pixels"] * ops_per_px / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
