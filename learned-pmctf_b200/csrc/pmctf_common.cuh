@@ -68,14 +68,26 @@ __device__ __forceinline__ float2 mul2v(float2 a, float2 b)
     return *reinterpret_cast<float2 *>(&d);
 }
 
-// tanh_det of two values at once on the packed fp32x2 pipe: the same operations in the same order per element
+__device__ __forceinline__ float2 add2v(float2 a, float2 b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long *>(&a)), "l"(*reinterpret_cast<const unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+
+// tanh_det of two values at once on the packed fp32x2 pipe: the same values per element.  rint(ax * 32) and the table index come
+// from the 1.5 * 2^23 trick (fma(ax, 32, M) = M + rint(ax * 32) exactly, ties to even like rintf) instead of FRND + F2I, which
+// keeps the conversion (XU) pipe out of the hot loop.
 __device__ __forceinline__ float2 tanh_det2(float2 x, const float *__restrict__ tab)
 {
+    constexpr float M = 12582912.0f; // 1.5 * 2^23
     const float2 ax = make_float2(fminf(fabsf(x.x), PMCTF_TANH_XMAX), fminf(fabsf(x.y), PMCTF_TANH_XMAX));
-    const float2 t = mul2v(ax, make_float2(32.0f, 32.0f));
-    const float2 fi = make_float2(rintf(t.x), rintf(t.y));
+    const float2 tm = fma2v(ax, make_float2(32.0f, 32.0f), make_float2(M, M));
+    const float2 fi = add2v(tm, make_float2(-M, -M));
     const float2 d = fma2v(fi, make_float2(-0.03125f, -0.03125f), ax);
-    const float2 T = make_float2(tab[(int)fi.x], tab[(int)fi.y]);
+    const float2 T = make_float2(tab[__float_as_int(tm.x) & 0x1FF], tab[__float_as_int(tm.y) & 0x1FF]);
     const float2 nT = make_float2(-T.x, -T.y);
     const float2 D1 = fma2v(nT, T, make_float2(1.0f, 1.0f));
     const float2 D2 = mul2v(nT, D1);                                             // -(T * D1)

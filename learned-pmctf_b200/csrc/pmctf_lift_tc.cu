@@ -122,8 +122,12 @@ __device__ __forceinline__ float combine(uint32_t o0, uint32_t o1, uint32_t o2, 
 // plane 0 as s8 and planes 1, 2 as u8 (the weight digits stay signed), so no carry arithmetic is needed here.
 __device__ __forceinline__ void push_digits4(float a0, float a1, float a2, float a3, uint32_t &w0, uint32_t &w1, uint32_t &w2)
 {
-    const int Va = __float2int_rn(a0 * 4194304.0f), Vb = __float2int_rn(a1 * 4194304.0f);
-    const int Vc = __float2int_rn(a2 * 4194304.0f), Vd = __float2int_rn(a3 * 4194304.0f);
+    // V = rint(a * 2^22) via fma(a, 2^22, 1.5 * 2^23): the sum lies in [2^23, 2^24], where floats are the integers, so the
+    // mantissa bits hold 2^22 + V exactly (ties to even, as cvt.rni would) -- no conversion instruction needed
+    constexpr float M = 12582912.0f;
+    constexpr int MB = 0x4B400000;
+    const int Va = __float_as_int(fmaf(a0, 4194304.0f, M)) - MB, Vb = __float_as_int(fmaf(a1, 4194304.0f, M)) - MB;
+    const int Vc = __float_as_int(fmaf(a2, 4194304.0f, M)) - MB, Vd = __float_as_int(fmaf(a3, 4194304.0f, M)) - MB;
     w2 = __byte_perm(__byte_perm(Va, Vb, 0x0040), __byte_perm(Vc, Vd, 0x0040), 0x5410);
     w1 = __byte_perm(__byte_perm(Va, Vb, 0x0051), __byte_perm(Vc, Vd, 0x0051), 0x5410);
     w0 = __byte_perm(__byte_perm(Va, Vb, 0x0062), __byte_perm(Vc, Vd, 0x0062), 0x5410);
