@@ -78,12 +78,14 @@ __device__ __forceinline__ void conv16_layer(const float *__restrict__ in, const
         const int rem = it - cg * PER_CG;
         const int r = rem / OUT_STRIPS;
         const int st = rem - r * OUT_STRIPS;
-        float acc[CO_T][4];
+        // accumulators as (co, co+1) pairs: one packed fp32x2 FMA (FFMA2) updates two output channels with the same input
+        // value -- bit-identical to two fmaf() chains, half the issue slots
+        float2 acc2[CO_T / 2][4];
 #pragma unroll
-        for (int co = 0; co < CO_T; ++co) {
-            const float b = bias[cg * CO_T + co];
+        for (int c2 = 0; c2 < CO_T / 2; ++c2) {
+            const float2 b = make_float2(bias[cg * CO_T + 2 * c2], bias[cg * CO_T + 2 * c2 + 1]);
 #pragma unroll
-            for (int p = 0; p < 4; ++p) acc[co][p] = b;
+            for (int p = 0; p < 4; ++p) acc2[c2][p] = b;
         }
         const float *ip = in + r * IN_P + st * 4;
         const float *wc = wp + cg * CO_T;
@@ -99,21 +101,27 @@ __device__ __forceinline__ void conv16_layer(const float *__restrict__ in, const
             }
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                float wv[CO_T];
+                float2 wv[CO_T / 2];
 #pragma unroll
                 for (int c4 = 0; c4 < CO_T / 4; ++c4) {
                     const float4 t = *reinterpret_cast<const float4 *>(wc + k * 16 + c4 * 4);
-                    wv[c4 * 4 + 0] = t.x; wv[c4 * 4 + 1] = t.y; wv[c4 * 4 + 2] = t.z; wv[c4 * 4 + 3] = t.w;
+                    wv[c4 * 2] = make_float2(t.x, t.y);
+                    wv[c4 * 2 + 1] = make_float2(t.z, t.w);
                 }
                 const int ky = k / 3, kx = k - ky * 3;
 #pragma unroll
-                for (int co = 0; co < CO_T; ++co)
+                for (int c2 = 0; c2 < CO_T / 2; ++c2)
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) acc[co][p] = fmaf(wv[co], patch[ky][kx + p], acc[co][p]);
+                    for (int p = 0; p < 4; ++p) acc2[c2][p] = ffma2(wv[c2], patch[ky][kx + p], acc2[c2][p]);
             }
             ip += in_plane;
             wc += 144;
         }
+        float acc[CO_T][4];
+#pragma unroll
+        for (int c2 = 0; c2 < CO_T / 2; ++c2)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) { acc[2 * c2][p] = acc2[c2][p].x; acc[2 * c2 + 1][p] = acc2[c2][p].y; }
         epi(cg, r, st, acc);
     }
 }
