@@ -15,10 +15,17 @@
 //     S = sum_k o_k 2^(32-8k) = sum A*W exactly -- independent of the tensor core's summation order;
 //   * conv = fma((float)S, 2^-(22+Sw), bias): one rounding.  oracle/pmctf_oracle.c states the same contract.
 //
+//   * conv4 (16 -> 1) is evaluated as per-tap partial sums T_k(p) = sum_ci w4[ci][k] a3[ci][p] (one fma chain over
+//     ci, from 0) inside the conv3 epilogue, where a pixel's 16 channels are already in registers, followed by
+//     out = ((b4 + T_0) + T_1) + ... + T_8 over the 3x3 neighbourhood -- the conv4 contract of the tensor mode.
+//
 // CTA = one 16x32 output tile, 9 warps: warps 0-7 are two epilogue groups (a warp reads TMEM lanes
 // 32*(warp%4)..+31), warp 8 issues the MMAs; 3 accumulator slots of 80 TMEM columns pipeline MMA and epilogue
-// through full/empty mbarriers.  Two CTAs are resident per SM (105 KB shared memory, 256 TMEM columns each), so
-// the CUDA-core phases of one tile overlap the tensor-core phases of the other.
+// through full/empty mbarriers.  One set of digit planes serves both layers: the conv2 epilogue writes tanh(conv2)
+// over the tanh(conv1) records of its own (finished) block, and the conv3 epilogue writes the conv4 partials over
+// them again; conv1's pre-activation outputs (the residual) are kept in shared memory instead of being recomputed.
+// Two CTAs are resident per SM (112 KB shared memory, 256 TMEM columns each), so the CUDA-core phases of one tile
+// overlap the tensor-core phases of the other.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -42,8 +49,10 @@ constexpr int S_ROWS = TH + 8, S_COLS = TW + 8, S_P = 41;
 constexpr int T_ROWS = TH + 10, T_P = 41;
 constexpr int A1_R = TH + 6, A1_C = TW + 6;          // tanh(conv1): origin (-3,-3)
 constexpr int A2_R = TH + 4, A2_C = TW + 4;          // tanh(conv2): origin (-2,-2)
-constexpr int A3_R = TH + 2, A3_C = TW + 2, A3_P = 36; // conv1 + conv3: origin (-1,-1), fp32 planar
+constexpr int A3_R = TH + 2, A3_C = TW + 2, A3_P = 36; // conv1 + conv3: origin (-1,-1); pitch of the conv1 stash
 constexpr int O_P = 33;
+constexpr int C1Q_BYTES = ((A3_R * A3_P * 16 + 127) / 128) * 128 + 32; // one float4 plane per channel quarter; +32: the four
+                                                                        // quarters of two pixels hit eight different bank groups
 constexpr int NSLOT = 3, SLOT_COLS = 80, TMEM_COLS = 256;
 constexpr int NGRP = 2;                              // epilogue groups of 4 warps
 static_assert(A1_C == P && A1_R * P <= NPIX, "pitch");
@@ -59,17 +68,16 @@ static_assert(PMCTF_PU_PACKED_FLOATS == 10128, "header and kernel disagree on th
 // shared memory (bytes)
 constexpr int SM_WB = 0;                              // 2 x 10240 B operand images
 constexpr int SM_F = SM_WB + 2 * QBYTES;              // fp32 parameters
-constexpr int F_W1 = 0, F_B1 = 144, F_B2 = 160, F_B3 = 176, F_W4 = 192, F_B4 = 384, F_SC2 = 385, F_SC3 = 386;
+constexpr int F_W1 = 0, F_B1 = 144, F_B2 = 160, F_B3 = 176, F_W4 = 192, F_W48 = 320, F_B4 = 384, F_SC2 = 385, F_SC3 = 386; // W4: [ci][8] taps 0..7, W48: [ci] tap 8
 constexpr int SM_S = SM_F + 1664;
 constexpr int SM_T = SM_S + ((S_ROWS * S_P * 4 + 127) / 128) * 128;
 constexpr int SM_A1 = SM_T + ((T_ROWS * T_P * 4 + 127) / 128) * 128;
-constexpr int A3_BYTES = 16 * A3_R * A3_P * 4;        // a3 (fp32, conv4 input) aliases the A1 digit planes
-constexpr int A1_BYTES = ((A3_BYTES > 3 * PLANE ? A3_BYTES : 3 * PLANE) + 127) / 128 * 128;
-constexpr int SM_A2 = SM_A1 + A1_BYTES;
-constexpr int SM_TANH = SM_A2 + 3 * PLANE;
+constexpr int SM_C1 = SM_A1 + 3 * PLANE;              // conv1 stash (4 quarter planes); the conv4 sums of the tile alias it later
+constexpr int SM_TANH = SM_C1 + 4 * C1Q_BYTES;
 constexpr int SM_BAR = SM_TANH + TANH_SMEM_BYTES;
 constexpr int SMEM_BYTES = SM_BAR + 128;
-static_assert(SM_S % 128 == 0 && SM_T % 128 == 0 && SM_A1 % 128 == 0 && SM_A2 % 128 == 0 && SM_BAR % 128 == 0, "alignment");
+static_assert(SM_S % 128 == 0 && SM_T % 128 == 0 && SM_A1 % 128 == 0 && SM_C1 % 128 == 0 && SM_TANH % 128 == 0 && SM_BAR % 128 == 0, "alignment");
+static_assert(C1Q_BYTES % 128 == 32 && TH * O_P * 4 <= C1Q_BYTES, "conv1 stash planes");
 static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 
 constexpr int MMA_WARP = 4 * NGRP;
@@ -140,10 +148,9 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     float *sf = reinterpret_cast<float *>(smem + SM_F);
     float *ss = reinterpret_cast<float *>(smem + SM_S);
     float *stile = reinterpret_cast<float *>(smem + SM_T);
-    uint8_t *A1 = smem + SM_A1;
-    uint8_t *A2 = smem + SM_A2;
-    float *a3 = reinterpret_cast<float *>(smem + SM_A1);
-    float *so = reinterpret_cast<float *>(smem + SM_A2);
+    uint8_t *A1 = smem + SM_A1;                 // digit planes of tanh(conv1), then (in place) tanh(conv2), then the conv4 partials
+    uint8_t *c1q = smem + SM_C1;                // conv1 pre-activations of the (TH+2) x (TW+2) region, one float4 plane per channel quarter
+    float *so = reinterpret_cast<float *>(smem + SM_C1); // conv4 output of the tile (after the stash is consumed)
     float *ttab = reinterpret_cast<float *>(smem + SM_TANH);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);      // full[NSLOT], empty[NSLOT]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_BAR + 96);
@@ -171,7 +178,10 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
             sf[F_B2 + tid] = __ldg(a.pu_packed + B2_OFF + tid);
             sf[F_B3 + tid] = __ldg(a.pu_packed + B3_OFF + tid);
         }
-        for (int i = tid; i < 192; i += NT) sf[F_W4 + i] = __ldg(a.pu_packed + W4_OFF + i);
+        for (int i = tid; i < 144; i += NT) {   // packed [ci][12] (9 used) -> taps 0..7 as [ci][8], tap 8 as [ci]
+            const int ci = i / 9, k = i - ci * 9;
+            sf[k < 8 ? F_W4 + ci * 8 + k : F_W48 + ci] = __ldg(a.pu_packed + W4_OFF + ci * 12 + k);
+        }
         if (tid == 0) {
             sf[F_B4] = __ldg(a.pu_packed + B4_OFF);
             sf[F_SC2] = __ldg(a.pu_packed + SC_OFF);
@@ -306,6 +316,8 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     a01 = ffma2(make_float2(wv[k].x, wv[k].y), v, a01);
                     a23 = ffma2(make_float2(wv[k].z, wv[k].w), v, a23);
                 }
+                if (r >= 2 && r < 2 + A3_R && c >= 2 && c < 2 + A3_C)   // residual operand of lifting_1d.py:45
+                    *reinterpret_cast<float4 *>(c1q + cq * C1Q_BYTES + ((r - 2) * A3_P + (c - 2)) * 16) = make_float4(a01.x, a01.y, a23.x, a23.y);
                 const float2 t01 = tanh_det2(a01, ttab), t23 = tanh_det2(a23, ttab);
                 push_digits4(t01.x, t01.y, t23.x, t23.y, w0, w1, w2);
             }
@@ -322,7 +334,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     // ---- conv2 / conv3 on the tensor core ---------------------------------------------------------------
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
-        const uint32_t a_saddr = umma::smem_u32(layer == 0 ? A1 : A2);
+        const uint32_t a_saddr = umma::smem_u32(A1);
         const uint32_t b_saddr = umma::smem_u32(smem + SM_WB + layer * QBYTES);
         if (warp == MMA_WARP) {
             if (dbg && lane == 0) dbg[8 + 2 * layer] = clock64();
@@ -389,7 +401,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     }
                     umma::fence_before_sync();
                     mbar_arrive(empty0 + 8 * slot);
-                    uint8_t *d = A2 + m * 16;
+                    uint8_t *d = A1 + m * 16;   // in place: every MMA that reads these records has completed (full barrier of this block)
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
                         *reinterpret_cast<uint4 *>(d + k * PLANE) = make_uint4(w[k][0], w[k][1], w[k][2], w[k][3]);
@@ -397,42 +409,44 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     const int gy = y0 - 1 + r, gx = x0 - 1 + c;
                     const bool inside = r < A3_R && c < A3_C;
                     const bool valid = inside && gy >= 0 && gy < H && gx >= 0 && gx < W;
-                    const float in_mul = a.in_mul;
-                    float sv[9];
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) sv[k] = inside ? ss[(r + 2 + k / 3) * S_P + c + 2 + (k % 3)] * in_mul : 0.0f;
+                    float2 tp[4] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+                    float t8 = 0.0f;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         uint32_t o[5][8];
 #pragma unroll
                         for (int k = 0; k < 5; ++k) tmem_ld8(taddr + 16 * k + 8 * h, o[k]);
+                        float c1[8];
+                        {   // conv1 at this position (stashed by the conv1 phase), 8 channels
+                            float4 q0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), q1 = q0;
+                            if (valid) {
+                                q0 = *reinterpret_cast<const float4 *>(c1q + (2 * h) * C1Q_BYTES + (r * A3_P + c) * 16);
+                                q1 = *reinterpret_cast<const float4 *>(c1q + (2 * h + 1) * C1Q_BYTES + (r * A3_P + c) * 16);
+                            }
+                            c1[0] = q0.x; c1[1] = q0.y; c1[2] = q0.z; c1[3] = q0.w; c1[4] = q1.x; c1[5] = q1.y; c1[6] = q1.z; c1[7] = q1.w;
+                        }
                         umma::tmem_ld_wait();
-                        // conv1 at this position, the identical fma chains (lifting_1d.py:45 residual), 8 channels
-                        float2 c1p[4];
-                        {
-                            const float4 b0 = *reinterpret_cast<const float4 *>(sf + F_B1 + 8 * h);
-                            const float4 b1 = *reinterpret_cast<const float4 *>(sf + F_B1 + 8 * h + 4);
-                            c1p[0] = make_float2(b0.x, b0.y); c1p[1] = make_float2(b0.z, b0.w);
-                            c1p[2] = make_float2(b1.x, b1.y); c1p[3] = make_float2(b1.z, b1.w);
-                        }
-#pragma unroll
-                        for (int k = 0; k < (PMCTF_WHATIF & 1 ? 0 : 9); ++k) {
-                            const float4 u0 = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + 8 * h);
-                            const float4 u1 = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + 8 * h + 4);
-                            c1p[0] = ffma2(make_float2(u0.x, u0.y), sv[k], c1p[0]); c1p[1] = ffma2(make_float2(u0.z, u0.w), sv[k], c1p[1]);
-                            c1p[2] = ffma2(make_float2(u1.x, u1.y), sv[k], c1p[2]); c1p[3] = ffma2(make_float2(u1.z, u1.w), sv[k], c1p[3]);
-                        }
-                        const float c1[8] = {c1p[0].x, c1p[0].y, c1p[1].x, c1p[1].y, c1p[2].x, c1p[2].y, c1p[3].x, c1p[3].y};
                         const float4 bv0 = *reinterpret_cast<const float4 *>(bias + 8 * h), bv1 = *reinterpret_cast<const float4 *>(bias + 8 * h + 4);
                         const float bq[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
 #pragma unroll
                         for (int ch = 0; ch < 8; ++ch) {
                             const float v = fmaf(combine(o[0][ch], o[1][ch], o[2][ch], o[3][ch], o[4][ch]), scale, bq[ch]);
-                            if (inside) a3[(8 * h + ch) * (A3_R * A3_P) + r * A3_P + c] = valid ? (c1[ch] + v) : 0.0f;
+                            const float a3v = valid ? (c1[ch] + v) : 0.0f;   // zero padding of conv4's input outside the image
+                            // conv4 partials of this pixel: T_k += w4[ci][k] * a3[ci], ci ascending (taps pairwise on the fp32x2 pipe)
+                            const float4 wa = *reinterpret_cast<const float4 *>(sf + F_W4 + (8 * h + ch) * 8);
+                            const float4 wb = *reinterpret_cast<const float4 *>(sf + F_W4 + (8 * h + ch) * 8 + 4);
+                            tp[0] = ffma2(make_float2(wa.x, wa.y), a3v, tp[0]); tp[1] = ffma2(make_float2(wa.z, wa.w), a3v, tp[1]);
+                            tp[2] = ffma2(make_float2(wb.x, wb.y), a3v, tp[2]); tp[3] = ffma2(make_float2(wb.z, wb.w), a3v, tp[3]);
+                            t8 = fmaf(sf[F_W48 + 8 * h + ch], a3v, t8);
                         }
                     }
                     umma::fence_before_sync();
                     mbar_arrive(empty0 + 8 * slot);
+                    // the partials replace the pixel's own digit records (their last reader, this block's MMAs, is done)
+                    uint8_t *d = A1 + m * 16;
+                    *reinterpret_cast<float4 *>(d) = make_float4(tp[0].x, tp[0].y, tp[1].x, tp[1].y);
+                    *reinterpret_cast<float4 *>(d + PLANE) = make_float4(tp[2].x, tp[2].y, tp[3].x, tp[3].y);
+                    *reinterpret_cast<float *>(d + 2 * PLANE) = t8;
                 }
             }
         }
@@ -447,43 +461,16 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
         break;
     }
 
-    // ---- conv4 (16 -> 1) -> so: 2 rows x 4 columns per thread; shared-memory bandwidth is what limits this kernel,
-    //      and the register tile halves the bytes read per output -------------------------------------------------
-    for (int it = tid; it < (TH / 2) * (TW / 4); it += NT) {
-        const int r = 2 * (it / (TW / 4)), c = 4 * (it % (TW / 4));
-        float acc[2][4];
+    // ---- conv4 (16 -> 1): out = ((b4 + T_0) + T_1) + ... + T_8 over the 3x3 neighbourhood of partials -> so -----------
+    for (int i = tid; i < TH * TW; i += NT) {
+        const int r = i / TW, c = i - r * TW;
+        float acc = sf[F_B4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = sf[F_B4];
-#pragma unroll 2
-        for (int ci = 0; ci < 16; ++ci) {
-            const float *ip = a3 + ci * (A3_R * A3_P) + r * A3_P + c;
-            const float *wc = sf + F_W4 + ci * 12;
-            const float4 w0 = *reinterpret_cast<const float4 *>(wc);
-            const float4 w1 = *reinterpret_cast<const float4 *>(wc + 4);
-            const float wk[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, wc[8]};
-            float pv[4][6];
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                const float4 p0 = *reinterpret_cast<const float4 *>(ip + rr * A3_P);
-                const float2 p1 = *reinterpret_cast<const float2 *>(ip + rr * A3_P + 4);
-                pv[rr][0] = p0.x; pv[rr][1] = p0.y; pv[rr][2] = p0.z; pv[rr][3] = p0.w; pv[rr][4] = p1.x; pv[rr][5] = p1.y;
-            }
-            // every output stays one sequential chain in (ci, ky, kx) order
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wk[ky * 3 + kx], pv[i + ky][j + kx], acc[i][j]);
+        for (int k = 0; k < 9; ++k) {
+            const int m = (r + k / 3) * P + c + (k % 3);   // conv3 pixel index (origin (-1,-1)) of the neighbour
+            acc = acc + *reinterpret_cast<const float *>(A1 + (k >> 2) * PLANE + m * 16 + (k & 3) * 4);
         }
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) so[(r + i) * O_P + c + j] = acc[i][j];
+        so[r * O_P + c] = acc;
     }
     __syncthreads();
     STAMP(5);

@@ -189,7 +189,8 @@ static void conv3x3_band(const float *in, int cin, int rows_in, const float *wgt
  * conv2 / conv3 of PredictUpdate take tanh outputs in [-1, 1].  In this mode they are evaluated in exact integer
  * arithmetic, which makes the result independent of any summation order (so a tensor-core implementation can be
  * bit-identical):  V = rint(a * 2^22);  Wq = rint(w * 2^Sw) with Sw = 22 - e, max|w| = m * 2^e, m in [0.5, 1);
- * S = sum V * Wq (exact, |S| < 2^52);  out = fma((float)S, 2^-(22+Sw), bias)   -- (float)S is one RN rounding.     */
+ * S = sum V * Wq (exact, |S| < 2^52);  out = fma((float)S, 2^-(22+Sw), bias)   -- (float)S is one RN rounding.
+ * conv4 of this mode sums per-tap partials (conv4_partials_band below).                                          */
 static int g_conv_mode = 0;
 ORC_API void orc_set_conv_mode(int mode) { g_conv_mode = mode; }
 ORC_API int orc_get_conv_mode(void) { return g_conv_mode; }
@@ -231,6 +232,28 @@ static void conv3x3_band_exact(const float *in, int rows_in, const orc_qconv_t *
                 o[x] = __builtin_fmaf((float)S, q->down, bias[co]);
             }
         }
+}
+
+/* conv4 (16 -> 1) of the exact mode: per-tap partial sums T_k(p) = sum_ci w4[ci][k] * a3[ci][p] (one fma chain over ci,
+ * starting from 0), then out = ((b4 + T_0) + T_1) + ... + T_8 over the 3x3 neighbourhood, k = 3*ky + kx.  The order
+ * is a specification of this mode (the tensor-core kernel forms the partials where a pixel's 16 channels sit in
+ * registers); the reference's own summation order is unspecified.  Band geometry as conv3x3_band.                  */
+static void conv4_partials_band(const float *in, int rows_in, const float *w4, float b4, float *out, int rows_out, int W, int Wp)
+{
+    for (int r = 0; r < rows_out; ++r) {
+        float *o = out + (size_t)r * Wp + 1;
+        for (int x = 0; x < W; ++x) {
+            float acc = b4;
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx) {
+                    float t = 0.0f;
+                    for (int ci = 0; ci < NCH; ++ci)
+                        t = __builtin_fmaf(w4[(ci * 3 + ky) * 3 + kx], in[((size_t)ci * rows_in + r + ky) * Wp + x + kx], t);
+                    acc = acc + t;
+                }
+            o[x] = acc;
+        }
+    }
 }
 
 static void band_fix(float *buf, int ch, int rows, int Wp, int W, int row0_img, int H, int do_tanh)
@@ -309,7 +332,8 @@ ORC_API void orc_predict_update(const float *x, const orc_pu_t *pu, float *out, 
                         for (int xx = 1; xx <= W; ++xx) p3[xx] = p1[xx] + p3[xx];
                     }
                 band_fix(a3, NCH, rows + 2, Wp, W, y0 - 1, H, 0);
-                conv3x3_band(a3, NCH, rows + 2, pu->w4, pu->b4, o4, 1, rows, W, Wp);
+                if (exact) conv4_partials_band(a3, rows + 2, pu->w4, pu->b4[0], o4, rows, W, Wp);
+                else conv3x3_band(a3, NCH, rows + 2, pu->w4, pu->b4, o4, 1, rows, W, Wp);
                 for (int r = 0; r < rows; ++r)
                     memcpy(out + (size_t)n * H * W + (size_t)(y0 + r) * W, o4 + (size_t)r * Wp + 1, sizeof(float) * W);
             }
