@@ -295,36 +295,39 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
 
     // ---- conv1 (1 -> 16) + tanh -> digits of A1 (origin (-3,-3), pitch 38) -------------------------------
     {
-        // item = (pixel, channel quarter); NT % 4 == 0, so a thread keeps its quarter: weights live in registers
+        // one thread = one pixel, all 16 channels (a quarter at a time); the weights are warp-uniform 128-bit shared loads
         const float in_mul = a.in_mul;
-        const int cq = tid & 3;
-        float4 wv[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) wv[k] = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + cq * 4);
-        const float4 b = *reinterpret_cast<const float4 *>(sf + F_B1 + cq * 4);
-        for (int it = tid; it < 4 * A1_R * A1_C; it += NT) {
-            const int px = it >> 2;
+        for (int px = tid; px < A1_R * A1_C; px += NT) {
             const int r = px / P, c = px - r * P;
             const int gy = y0 - 3 + r, gx = x0 - 3 + c;
-            uint32_t w0 = 0, w1 = 0, w2 = 0;
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                float2 a01 = make_float2(b.x, b.y), a23 = make_float2(b.z, b.w);
+            uint32_t w[3][4];
 #pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    const int ky = k / 3, kx = k - ky * 3;
-                    const float v = ss[(r + ky) * S_P + c + kx] * in_mul;
-                    a01 = ffma2(make_float2(wv[k].x, wv[k].y), v, a01);
-                    a23 = ffma2(make_float2(wv[k].z, wv[k].w), v, a23);
+            for (int q = 0; q < 4; ++q) w[0][q] = w[1][q] = w[2][q] = 0u;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                float v[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) v[k] = ss[(r + k / 3) * S_P + c + (k % 3)] * in_mul;
+                const bool stash = r >= 2 && r < 2 + A3_R && c >= 2 && c < 2 + A3_C;   // residual operand of lifting_1d.py:45
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b = *reinterpret_cast<const float4 *>(sf + F_B1 + q * 4);
+                    float2 a01 = make_float2(b.x, b.y), a23 = make_float2(b.z, b.w);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        const float4 wk = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + q * 4);
+                        a01 = ffma2(make_float2(wk.x, wk.y), v[k], a01);
+                        a23 = ffma2(make_float2(wk.z, wk.w), v[k], a23);
+                    }
+                    if (stash)
+                        *reinterpret_cast<float4 *>(c1q + q * C1Q_BYTES + ((r - 2) * A3_P + (c - 2)) * 16) = make_float4(a01.x, a01.y, a23.x, a23.y);
+                    const float2 t01 = tanh_det2(a01, ttab), t23 = tanh_det2(a23, ttab);
+                    push_digits4(t01.x, t01.y, t23.x, t23.y, w[0][q], w[1][q], w[2][q]);
                 }
-                if (r >= 2 && r < 2 + A3_R && c >= 2 && c < 2 + A3_C)   // residual operand of lifting_1d.py:45
-                    *reinterpret_cast<float4 *>(c1q + cq * C1Q_BYTES + ((r - 2) * A3_P + (c - 2)) * 16) = make_float4(a01.x, a01.y, a23.x, a23.y);
-                const float2 t01 = tanh_det2(a01, ttab), t23 = tanh_det2(a23, ttab);
-                push_digits4(t01.x, t01.y, t23.x, t23.y, w0, w1, w2);
             }
-            uint8_t *d = A1 + px * 16 + cq * 4;
-            *reinterpret_cast<uint32_t *>(d) = w0;
-            *reinterpret_cast<uint32_t *>(d + PLANE) = w1;
-            *reinterpret_cast<uint32_t *>(d + 2 * PLANE) = w2;
+            uint8_t *d = A1 + px * 16;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                *reinterpret_cast<uint4 *>(d + k * PLANE) = make_uint4(w[k][0], w[k][1], w[k][2], w[k][3]);
         }
     }
     umma::fence_proxy_async();
