@@ -10,8 +10,8 @@ namespace pmctf {
 
 // ------------------------------------------------------------------------------------------
 // deterministic tanh (arithmetic contract: table include/pmctf_tanh_table.h, routine specified in
-// tools/gen_tanh_table.py, restated independently in oracle/pmctf_oracle.c): third-order expansion around the
-// nearest multiple of 1/32, derivatives from T = tanh(node); one 4-byte shared-memory lookup per evaluation
+// tools/gen_tanh_table.py, restated independently in oracle/pmctf_oracle.c): second-order expansion around the
+// nearest multiple of 1/128, derivatives from T = tanh(node); one 4-byte shared-memory lookup per evaluation
 __device__ const unsigned int g_tanh_bits[PMCTF_TANH_ENTRIES] = {PMCTF_TANH_TABLE_VALUES};
 constexpr int TANH_SMEM_BYTES = ((PMCTF_TANH_ENTRIES * 4 + 127) / 128) * 128;
 
@@ -22,18 +22,18 @@ __device__ __forceinline__ void load_tanh_table(float *tab_smem, int tid, int nt
 
 __device__ __forceinline__ float tanh_det(float x, const float *__restrict__ tab)
 {
-    const float ax = fminf(fabsf(x), PMCTF_TANH_XMAX);
-    const float fi = rintf(ax * 32.0f);
-    const float d = fmaf(fi, -0.03125f, ax);
+    const float m = fmaxf(-fabsf(x), -PMCTF_TANH_XMAX);
+    const float fi = rintf(m * -PMCTF_TANH_STEPS);
+    const float e = fmaf(fi, 1.0f / PMCTF_TANH_STEPS, m);
 #if defined(PMCTF_WHATIF) && (PMCTF_WHATIF & 2)
-    const float T = fi * 0.003f;
+    const float T = fi * 0.0008f;
 #else
     const float T = tab[(int)fi];
 #endif
-    const float D1 = fmaf(-T, T, 1.0f);
-    const float D2 = -(T * D1);
-    const float D3 = (D1 * fmaf(-3.0f * T, T, 1.0f)) * -0.333333343f;
-    const float y = fmaf(fmaf(fmaf(D3, d, D2), d, D1), d, T);
+    const float Q = fmaf(T, T, -1.0f);
+    const float R = T * Q;
+    const float G = fmaf(e, R, Q);
+    const float y = fmaf(e, G, T);
     return copysignf(y, x);
 }
 
@@ -77,23 +77,21 @@ __device__ __forceinline__ float2 add2v(float2 a, float2 b)
     return *reinterpret_cast<float2 *>(&d);
 }
 
-// tanh_det of two values at once on the packed fp32x2 pipe: the same values per element.  rint(ax * 32) and the table index come
-// from the 1.5 * 2^23 trick (fma(ax, 32, M) = M + rint(ax * 32) exactly, ties to even like rintf) instead of FRND + F2I, which
-// keeps the conversion (XU) pipe out of the hot loop.
+// tanh_det of two values at once on the packed fp32x2 pipe: the same values per element.  rint(128 |x|) and the table index come
+// from the 1.5 * 2^23 trick (fma(m, -128, M) = M + rint(128 |x|) exactly, ties to even like rintf) instead of FRND + F2I, which
+// keeps the conversion (XU) pipe out of the hot loop; the sign arrangement of the contract needs no packed negation.
 __device__ __forceinline__ float2 tanh_det2(float2 x, const float *__restrict__ tab)
 {
     constexpr float M = 12582912.0f; // 1.5 * 2^23
-    const float2 ax = make_float2(fminf(fabsf(x.x), PMCTF_TANH_XMAX), fminf(fabsf(x.y), PMCTF_TANH_XMAX));
-    const float2 tm = fma2v(ax, make_float2(32.0f, 32.0f), make_float2(M, M));
+    const float2 m = make_float2(fmaxf(-fabsf(x.x), -PMCTF_TANH_XMAX), fmaxf(-fabsf(x.y), -PMCTF_TANH_XMAX));
+    const float2 tm = fma2v(m, make_float2(-PMCTF_TANH_STEPS, -PMCTF_TANH_STEPS), make_float2(M, M));
     const float2 fi = add2v(tm, make_float2(-M, -M));
-    const float2 d = fma2v(fi, make_float2(-0.03125f, -0.03125f), ax);
-    const float2 T = make_float2(tab[__float_as_int(tm.x) & 0x1FF], tab[__float_as_int(tm.y) & 0x1FF]);
-    const float2 nT = make_float2(-T.x, -T.y);
-    const float2 D1 = fma2v(nT, T, make_float2(1.0f, 1.0f));
-    const float2 D2 = mul2v(nT, D1);                                             // -(T * D1)
-    const float2 u = fma2v(mul2v(T, make_float2(-3.0f, -3.0f)), T, make_float2(1.0f, 1.0f));
-    const float2 D3 = mul2v(mul2v(D1, u), make_float2(-0.333333343f, -0.333333343f));
-    const float2 y = fma2v(fma2v(fma2v(D3, d, D2), d, D1), d, T);
+    const float2 e = fma2v(fi, make_float2(1.0f / PMCTF_TANH_STEPS, 1.0f / PMCTF_TANH_STEPS), m);
+    const float2 T = make_float2(tab[__float_as_int(tm.x) & 0x7FF], tab[__float_as_int(tm.y) & 0x7FF]);
+    const float2 Q = fma2v(T, T, make_float2(-1.0f, -1.0f));
+    const float2 R = mul2v(T, Q);
+    const float2 G = fma2v(e, R, Q);
+    const float2 y = fma2v(e, G, T);
     return make_float2(copysignf(y.x, x.x), copysignf(y.y, x.y));
 }
 

@@ -51,7 +51,8 @@ constexpr int A1_R = TH + 6, A1_C = TW + 6;          // tanh(conv1): origin (-3,
 constexpr int A2_R = TH + 4, A2_C = TW + 4;          // tanh(conv2): origin (-2,-2)
 constexpr int A3_R = TH + 2, A3_C = TW + 2, A3_P = 36; // conv1 + conv3: origin (-1,-1); pitch of the conv1 stash
 constexpr int O_P = 33;
-constexpr int C1Q_BYTES = ((A3_R * A3_P * 16 + 127) / 128) * 128 + 32; // one float4 plane per channel quarter; +32: the four
+constexpr int C1_P = A3_C;                            // pitch of the conv1 stash
+constexpr int C1Q_BYTES = ((A3_R * C1_P * 16 - 32 + 127) / 128) * 128 + 32; // one float4 plane per channel quarter; +32: the four
                                                                         // quarters of two pixels hit eight different bank groups
 constexpr int NSLOT = 3, SLOT_COLS = 80, TMEM_COLS = 256;
 constexpr int NGRP = 2;                              // epilogue groups of 4 warps
@@ -77,7 +78,7 @@ constexpr int SM_TANH = SM_C1 + 4 * C1Q_BYTES;
 constexpr int SM_BAR = SM_TANH + TANH_SMEM_BYTES;
 constexpr int SMEM_BYTES = SM_BAR + 128;
 static_assert(SM_S % 128 == 0 && SM_T % 128 == 0 && SM_A1 % 128 == 0 && SM_C1 % 128 == 0 && SM_TANH % 128 == 0 && SM_BAR % 128 == 0, "alignment");
-static_assert(C1Q_BYTES % 128 == 32 && TH * O_P * 4 <= C1Q_BYTES, "conv1 stash planes");
+static_assert(C1Q_BYTES % 128 == 32 && C1Q_BYTES >= A3_R * C1_P * 16 && TH * O_P * 4 <= C1Q_BYTES, "conv1 stash planes");
 static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 
 constexpr int MMA_WARP = 4 * NGRP;
@@ -128,16 +129,19 @@ __device__ __forceinline__ float combine(uint32_t o0, uint32_t o1, uint32_t o2, 
 // V = rint(a * 2^22) of four channels -> the three digit words, channel q in byte q of each word.  The digits are simply the
 // two's complement bytes of V: V = d0*2^16 + u1*2^8 + u2 with d0 = V >> 16 signed and u1, u2 in [0, 255]; the MMAs read
 // plane 0 as s8 and planes 1, 2 as u8 (the weight digits stay signed), so no carry arithmetic is needed here.
-__device__ __forceinline__ void push_digits4(float a0, float a1, float a2, float a3, uint32_t &w0, uint32_t &w1, uint32_t &w2)
+__device__ __forceinline__ void push_digits4(float2 a01, float2 a23, uint32_t &w0, uint32_t &w1, uint32_t &w2)
 {
     // V = rint(a * 2^22) via fma(a, 2^22, 1.5 * 2^23): the sum lies in [2^23, 2^24], where floats are the integers, so the
     // mantissa bits hold 2^22 + V exactly (ties to even, as cvt.rni would) -- no conversion instruction needed
     constexpr float M = 12582912.0f;
     constexpr int MB = 0x4B400000;
-    const int Va = __float_as_int(fmaf(a0, 4194304.0f, M)) - MB, Vb = __float_as_int(fmaf(a1, 4194304.0f, M)) - MB;
-    const int Vc = __float_as_int(fmaf(a2, 4194304.0f, M)) - MB, Vd = __float_as_int(fmaf(a3, 4194304.0f, M)) - MB;
-    w2 = __byte_perm(__byte_perm(Va, Vb, 0x0040), __byte_perm(Vc, Vd, 0x0040), 0x5410);
-    w1 = __byte_perm(__byte_perm(Va, Vb, 0x0051), __byte_perm(Vc, Vd, 0x0051), 0x5410);
+    const float2 f01 = fma2v(a01, make_float2(4194304.0f, 4194304.0f), make_float2(M, M));
+    const float2 f23 = fma2v(a23, make_float2(4194304.0f, 4194304.0f), make_float2(M, M));
+    const int Va = __float_as_int(f01.x) - MB, Vb = __float_as_int(f01.y) - MB;
+    const int Vc = __float_as_int(f23.x) - MB, Vd = __float_as_int(f23.y) - MB;
+    const uint32_t ab = __byte_perm(Va, Vb, 0x5140), cd = __byte_perm(Vc, Vd, 0x5140);   // (a0, b0, a1, b1), (c0, d0, c1, d1)
+    w2 = __byte_perm(ab, cd, 0x5410);
+    w1 = __byte_perm(ab, cd, 0x7632);
     w0 = __byte_perm(__byte_perm(Va, Vb, 0x0062), __byte_perm(Vc, Vd, 0x0062), 0x5410);
 }
 
@@ -319,9 +323,9 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                         a23 = ffma2(make_float2(wk.z, wk.w), v[k], a23);
                     }
                     if (stash)
-                        *reinterpret_cast<float4 *>(c1q + q * C1Q_BYTES + ((r - 2) * A3_P + (c - 2)) * 16) = make_float4(a01.x, a01.y, a23.x, a23.y);
+                        *reinterpret_cast<float4 *>(c1q + q * C1Q_BYTES + ((r - 2) * C1_P + (c - 2)) * 16) = make_float4(a01.x, a01.y, a23.x, a23.y);
                     const float2 t01 = tanh_det2(a01, ttab), t23 = tanh_det2(a23, ttab);
-                    push_digits4(t01.x, t01.y, t23.x, t23.y, w[0][q], w[1][q], w[2][q]);
+                    push_digits4(t01, t23, w[0][q], w[1][q], w[2][q]);
                 }
             }
             uint8_t *d = A1 + px * 16;
@@ -396,8 +400,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                                     u[q] = fmaf(combine(o[0][ch], o[1][ch], o[2][ch], o[3][ch], o[4][ch]), scale, bq[q]);
                                 }
                                 const float2 t01 = tanh_det2(make_float2(u[0], u[1]), ttab), t23 = tanh_det2(make_float2(u[2], u[3]), ttab);
-                                const float t[4] = {t01.x, t01.y, t23.x, t23.y};
-                                push_digits4(t[0], t[1], t[2], t[3], w0, w1, w2);
+                                push_digits4(t01, t23, w0, w1, w2);
                             }
                             w[0][2 * h + j] = w0; w[1][2 * h + j] = w1; w[2][2 * h + j] = w2;
                         }
@@ -423,8 +426,8 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                         {   // conv1 at this position (stashed by the conv1 phase), 8 channels
                             float4 q0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), q1 = q0;
                             if (valid) {
-                                q0 = *reinterpret_cast<const float4 *>(c1q + (2 * h) * C1Q_BYTES + (r * A3_P + c) * 16);
-                                q1 = *reinterpret_cast<const float4 *>(c1q + (2 * h + 1) * C1Q_BYTES + (r * A3_P + c) * 16);
+                                q0 = *reinterpret_cast<const float4 *>(c1q + (2 * h) * C1Q_BYTES + (r * C1_P + c) * 16);
+                                q1 = *reinterpret_cast<const float4 *>(c1q + (2 * h + 1) * C1Q_BYTES + (r * C1_P + c) * 16);
                             }
                             c1[0] = q0.x; c1[1] = q0.y; c1[2] = q0.z; c1[3] = q0.w; c1[4] = q1.x; c1[5] = q1.y; c1[6] = q1.z; c1[7] = q1.w;
                         }

@@ -59,21 +59,21 @@ typedef struct {
 
 /* ------------------------------------------------------------------------------------------ */
 /* deterministic tanh (arithmetic contract; table include/pmctf_tanh_table.h, routine specified in
- * tools/gen_tanh_table.py): third-order expansion around the nearest multiple of 1/32 with the derivatives
+ * tools/gen_tanh_table.py): second-order expansion around the nearest multiple of 1/128 with the derivatives
  * expressed through T = tanh(node).  Absolute error <= 1.2e-7; exact 0 at 0; odd; saturates at |x| >= 9.        */
 #include "../include/pmctf_tanh_table.h"
 static const uint32_t tanh_bits[PMCTF_TANH_ENTRIES] = {PMCTF_TANH_TABLE_VALUES};
 static inline float tanh_det(float x)
 {
     const float *tab = (const float *)tanh_bits;
-    float ax = fminf(fabsf(x), PMCTF_TANH_XMAX);
-    float fi = rintf(ax * 32.0f);
-    float d = fmaf(fi, -0.03125f, ax);
+    float m = fmaxf(-fabsf(x), -PMCTF_TANH_XMAX);
+    float fi = rintf(m * -PMCTF_TANH_STEPS);            /* rint(128 |x|), ties to even */
+    float e = fmaf(fi, 1.0f / PMCTF_TANH_STEPS, m);     /* node - |x|, exact */
     float T = tab[(int32_t)fi];
-    float D1 = fmaf(-T, T, 1.0f);
-    float D2 = -(T * D1);
-    float D3 = (D1 * fmaf(-3.0f * T, T, 1.0f)) * -0.333333343f;
-    float y = fmaf(fmaf(fmaf(D3, d, D2), d, D1), d, T);
+    float Q = fmaf(T, T, -1.0f);
+    float R = T * Q;
+    float G = fmaf(e, R, Q);
+    float y = fmaf(e, G, T);
     return copysignf(y, x);
 }
 
