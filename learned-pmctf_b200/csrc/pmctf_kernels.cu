@@ -563,6 +563,7 @@ static PlaneD to_dev(const pmctf_plane_t &p)
 }
 
 int launch_step_tc(const StepD &d, int src_kind, int *err_flag, cudaStream_t st); // pmctf_lift_tc.cu
+int register_packed_weights(const float *packed, cudaStream_t st);                 // pmctf_lift_tc.cu
 
 static int g_conv_mode = PMCTF_CONV_TENSOR;
 static int *g_tc_err = nullptr; // device flag set by a tensor-core kernel whose MMA never completed
@@ -711,7 +712,11 @@ int pmctf_pack_pu_weights(const float *w1, const float *b1, const float *w2, con
 {
     if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !w4 || !b4 || !packed) return PMCTF_EINVAL;
     pack_pu_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(w1, b1, w2, b2, w3, b3, w4, b4, packed);
-    return PMCTF_LAUNCHED();
+    const int e = PMCTF_LAUNCHED();
+    if (e) return e;
+    // the tensor-core kernel takes the small fp32 parameters as kernel arguments: keep a host copy per packed block
+    // (one 40 KB read-back and stream synchronisation per weight version)
+    return pmctf::register_packed_weights(packed, (cudaStream_t)stream);
 }
 
 int pmctf_flow_warp(const float *im, const float *flow, const float *lin_x, const float *lin_y, float *out, int N,

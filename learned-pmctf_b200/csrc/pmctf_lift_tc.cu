@@ -29,6 +29,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
 #include "pmctf_b200.h"
 #include "pmctf_common.cuh"
 #include "pmctf_umma.cuh"
@@ -68,9 +72,7 @@ static_assert(PMCTF_PU_PACKED_FLOATS == 10128, "header and kernel disagree on th
 
 // shared memory (bytes)
 constexpr int SM_WB = 0;                              // 2 x 10240 B operand images
-constexpr int SM_F = SM_WB + 2 * QBYTES;              // fp32 parameters
-constexpr int F_W1 = 0, F_B1 = 144, F_B2 = 160, F_B3 = 176, F_W4 = 192, F_W48 = 320, F_B4 = 384, F_SC2 = 385, F_SC3 = 386; // W4: [ci][8] taps 0..7, W48: [ci] tap 8
-constexpr int SM_S = SM_F + 1664;
+constexpr int SM_S = SM_WB + 2 * QBYTES;
 constexpr int SM_T = SM_S + ((S_ROWS * S_P * 4 + 127) / 128) * 128;
 constexpr int SM_A1 = SM_T + ((T_ROWS * T_P * 4 + 127) / 128) * 128;
 constexpr int SM_C1 = SM_A1 + 3 * PLANE;              // conv1 stash (4 quarter planes); the conv4 sums of the tile alias it later
@@ -84,6 +86,16 @@ static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 constexpr int MMA_WARP = 4 * NGRP;
 constexpr int NT = 32 * (MMA_WARP + 1);   // 8 epilogue warps + 1 MMA warp
 
+// The small fp32 parameters travel as kernel arguments: warp-uniform constant-bank operands cost no shared-memory
+// bandwidth (the bound of this kernel).  Filled on the host from the copy pmctf_pack_pu_weights() registers.
+struct TcW {
+    float w1[144];     // conv1 [k][co]
+    float b1[16], b2[16], b3[16];
+    float w4[16][8];   // conv4 taps 0..7 per input channel
+    float w48[16];     // conv4 tap 8
+    float b4, sc2, sc3;
+};
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
@@ -93,6 +105,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
                  : "r"(taddr)
                  : "memory");
 }
@@ -146,10 +166,9 @@ __device__ __forceinline__ void push_digits4(float2 a01, float2 a23, uint32_t &w
 }
 
 template <int SRC>
-__global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_constant__ StepD a, int *__restrict__ err)
+__global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_constant__ StepD a, const __grid_constant__ TcW cw, int *__restrict__ err)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    float *sf = reinterpret_cast<float *>(smem + SM_F);
     float *ss = reinterpret_cast<float *>(smem + SM_S);
     float *stile = reinterpret_cast<float *>(smem + SM_T);
     uint8_t *A1 = smem + SM_A1;                 // digit planes of tanh(conv1), then (in place) tanh(conv2), then the conv4 partials
@@ -177,19 +196,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
         int4 *d = reinterpret_cast<int4 *>(smem + SM_WB);
         for (int i = tid; i < 2 * QBYTES / 16; i += NT) d[i] = __ldg(g + i);
         load_tanh_table(ttab, tid, NT);
-        for (int i = tid; i < 144 + 16; i += NT) sf[F_W1 + i] = __ldg(a.pu_packed + W1_OFF + i);
-        if (tid < 16) {
-            sf[F_B2 + tid] = __ldg(a.pu_packed + B2_OFF + tid);
-            sf[F_B3 + tid] = __ldg(a.pu_packed + B3_OFF + tid);
-        }
-        for (int i = tid; i < 144; i += NT) {   // packed [ci][12] (9 used) -> taps 0..7 as [ci][8], tap 8 as [ci]
-            const int ci = i / 9, k = i - ci * 9;
-            sf[k < 8 ? F_W4 + ci * 8 + k : F_W48 + ci] = __ldg(a.pu_packed + W4_OFF + ci * 12 + k);
-        }
         if (tid == 0) {
-            sf[F_B4] = __ldg(a.pu_packed + B4_OFF);
-            sf[F_SC2] = __ldg(a.pu_packed + SC_OFF);
-            sf[F_SC3] = __ldg(a.pu_packed + SC_OFF + 1);
             for (int i = 0; i < NSLOT; ++i) {
                 umma::mbar_init(umma::smem_u32(bars + i), 1);
                 umma::mbar_init(umma::smem_u32(bars + NSLOT + i), 128);
@@ -314,13 +321,11 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                 const bool stash = r >= 2 && r < 2 + A3_R && c >= 2 && c < 2 + A3_C;   // residual operand of lifting_1d.py:45
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float4 b = *reinterpret_cast<const float4 *>(sf + F_B1 + q * 4);
-                    float2 a01 = make_float2(b.x, b.y), a23 = make_float2(b.z, b.w);
+                    float2 a01 = make_float2(cw.b1[q * 4], cw.b1[q * 4 + 1]), a23 = make_float2(cw.b1[q * 4 + 2], cw.b1[q * 4 + 3]);
 #pragma unroll
                     for (int k = 0; k < 9; ++k) {
-                        const float4 wk = *reinterpret_cast<const float4 *>(sf + F_W1 + k * 16 + q * 4);
-                        a01 = ffma2(make_float2(wk.x, wk.y), v[k], a01);
-                        a23 = ffma2(make_float2(wk.z, wk.w), v[k], a23);
+                        a01 = ffma2(make_float2(cw.w1[k * 16 + q * 4], cw.w1[k * 16 + q * 4 + 1]), v[k], a01);
+                        a23 = ffma2(make_float2(cw.w1[k * 16 + q * 4 + 2], cw.w1[k * 16 + q * 4 + 3]), v[k], a23);
                     }
                     if (stash)
                         *reinterpret_cast<float4 *>(c1q + q * C1Q_BYTES + ((r - 2) * C1_P + (c - 2)) * 16) = make_float4(a01.x, a01.y, a23.x, a23.y);
@@ -363,8 +368,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
             if (dbg && lane == 0) dbg[9 + 2 * layer] = clock64();
         } else {
             const int grp = warp >> 2, quarter = warp & 3;
-            const float scale = sf[layer == 0 ? F_SC2 : F_SC3];
-            const float *bias = sf + (layer == 0 ? F_B2 : F_B3);
+            const float scale = layer == 0 ? cw.sc2 : cw.sc3;
 #pragma unroll 1
             for (int blk = grp; blk < NBLK; blk += NGRP) {
                 const int slot = blk % NSLOT;
@@ -381,29 +385,27 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     const int gy = y0 - 2 + r, gx = x0 - 2 + c;
                     const bool valid = r < A2_R && c < A2_C && gy >= 0 && gy < H && gx >= 0 && gx < W;
                     uint32_t w[3][4];
+                    uint32_t o[2][5][4];   // four channels at a time, the next quad's TMEM loads in flight behind the arithmetic
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t o[5][8];
+                    for (int k = 0; k < 5; ++k) tmem_ld4(taddr + 16 * k, o[0][k]);
 #pragma unroll
-                        for (int k = 0; k < 5; ++k) tmem_ld8(taddr + 16 * k + 8 * h, o[k]);
+                    for (int q = 0; q < 4; ++q) {
                         umma::tmem_ld_wait();
+                        if (q < 3) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            uint32_t w0 = 0, w1 = 0, w2 = 0;
-                            if (valid) {
-                                const float4 bv = *reinterpret_cast<const float4 *>(bias + 8 * h + 4 * j);
-                                const float bq[4] = {bv.x, bv.y, bv.z, bv.w};
-                                float u[4];
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const int ch = 4 * j + q;
-                                    u[q] = fmaf(combine(o[0][ch], o[1][ch], o[2][ch], o[3][ch], o[4][ch]), scale, bq[q]);
-                                }
-                                const float2 t01 = tanh_det2(make_float2(u[0], u[1]), ttab), t23 = tanh_det2(make_float2(u[2], u[3]), ttab);
-                                push_digits4(t01, t23, w0, w1, w2);
-                            }
-                            w[0][2 * h + j] = w0; w[1][2 * h + j] = w1; w[2][2 * h + j] = w2;
+                            for (int k = 0; k < 5; ++k) tmem_ld4(taddr + 16 * k + 4 * (q + 1), o[(q + 1) & 1][k]);
                         }
+                        uint32_t w0 = 0, w1 = 0, w2 = 0;
+                        if (valid) {
+                            const float bq[4] = {cw.b2[4 * q], cw.b2[4 * q + 1], cw.b2[4 * q + 2], cw.b2[4 * q + 3]};
+                            float u[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                u[j] = fmaf(combine(o[q & 1][0][j], o[q & 1][1][j], o[q & 1][2][j], o[q & 1][3][j], o[q & 1][4][j]), scale, bq[j]);
+                            const float2 t01 = tanh_det2(make_float2(u[0], u[1]), ttab), t23 = tanh_det2(make_float2(u[2], u[3]), ttab);
+                            push_digits4(t01, t23, w0, w1, w2);
+                        }
+                        w[0][q] = w0; w[1][q] = w1; w[2][q] = w2;
                     }
                     umma::fence_before_sync();
                     mbar_arrive(empty0 + 8 * slot);
@@ -417,33 +419,30 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     const bool valid = inside && gy >= 0 && gy < H && gx >= 0 && gx < W;
                     float2 tp[4] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
                     float t8 = 0.0f;
+                    uint32_t o[2][5][4];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t o[5][8];
+                    for (int k = 0; k < 5; ++k) tmem_ld4(taddr + 16 * k, o[0][k]);
 #pragma unroll
-                        for (int k = 0; k < 5; ++k) tmem_ld8(taddr + 16 * k + 8 * h, o[k]);
-                        float c1[8];
-                        {   // conv1 at this position (stashed by the conv1 phase), 8 channels
-                            float4 q0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), q1 = q0;
-                            if (valid) {
-                                q0 = *reinterpret_cast<const float4 *>(c1q + (2 * h) * C1Q_BYTES + (r * C1_P + c) * 16);
-                                q1 = *reinterpret_cast<const float4 *>(c1q + (2 * h + 1) * C1Q_BYTES + (r * C1_P + c) * 16);
-                            }
-                            c1[0] = q0.x; c1[1] = q0.y; c1[2] = q0.z; c1[3] = q0.w; c1[4] = q1.x; c1[5] = q1.y; c1[6] = q1.z; c1[7] = q1.w;
-                        }
+                    for (int q = 0; q < 4; ++q) {
+                        // conv1 at this position (stashed by the conv1 phase), 4 channels
+                        float4 cq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (valid) cq = *reinterpret_cast<const float4 *>(c1q + q * C1Q_BYTES + (r * C1_P + c) * 16);
+                        const float c1[4] = {cq.x, cq.y, cq.z, cq.w};
+                        const float bq[4] = {cw.b3[4 * q], cw.b3[4 * q + 1], cw.b3[4 * q + 2], cw.b3[4 * q + 3]};
                         umma::tmem_ld_wait();
-                        const float4 bv0 = *reinterpret_cast<const float4 *>(bias + 8 * h), bv1 = *reinterpret_cast<const float4 *>(bias + 8 * h + 4);
-                        const float bq[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
+                        if (q < 3) {
 #pragma unroll
-                        for (int ch = 0; ch < 8; ++ch) {
-                            const float v = fmaf(combine(o[0][ch], o[1][ch], o[2][ch], o[3][ch], o[4][ch]), scale, bq[ch]);
-                            const float a3v = valid ? (c1[ch] + v) : 0.0f;   // zero padding of conv4's input outside the image
+                            for (int k = 0; k < 5; ++k) tmem_ld4(taddr + 16 * k + 4 * (q + 1), o[(q + 1) & 1][k]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float v = fmaf(combine(o[q & 1][0][j], o[q & 1][1][j], o[q & 1][2][j], o[q & 1][3][j], o[q & 1][4][j]), scale, bq[j]);
+                            const float a3v = valid ? (c1[j] + v) : 0.0f;   // zero padding of conv4's input outside the image
                             // conv4 partials of this pixel: T_k += w4[ci][k] * a3[ci], ci ascending (taps pairwise on the fp32x2 pipe)
-                            const float4 wa = *reinterpret_cast<const float4 *>(sf + F_W4 + (8 * h + ch) * 8);
-                            const float4 wb = *reinterpret_cast<const float4 *>(sf + F_W4 + (8 * h + ch) * 8 + 4);
-                            tp[0] = ffma2(make_float2(wa.x, wa.y), a3v, tp[0]); tp[1] = ffma2(make_float2(wa.z, wa.w), a3v, tp[1]);
-                            tp[2] = ffma2(make_float2(wb.x, wb.y), a3v, tp[2]); tp[3] = ffma2(make_float2(wb.z, wb.w), a3v, tp[3]);
-                            t8 = fmaf(sf[F_W48 + 8 * h + ch], a3v, t8);
+                            const float *wc = cw.w4[4 * q + j];
+                            tp[0] = ffma2(make_float2(wc[0], wc[1]), a3v, tp[0]); tp[1] = ffma2(make_float2(wc[2], wc[3]), a3v, tp[1]);
+                            tp[2] = ffma2(make_float2(wc[4], wc[5]), a3v, tp[2]); tp[3] = ffma2(make_float2(wc[6], wc[7]), a3v, tp[3]);
+                            t8 = fmaf(cw.w48[4 * q + j], a3v, t8);
                         }
                     }
                     umma::fence_before_sync();
@@ -467,10 +466,29 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
         break;
     }
 
+    // the base operand of this thread's output pixels: issued here so that the gather below hides the global-load latency
+    constexpr int NFIN = (TH * TW + NT - 1) / NT;
+    float bpre[NFIN];
+    const bool xfast_out = a.out.cs <= a.out.rs;
+    {
+        const bool want = a.mode == PMCTF_MODE_ACCUM;
+        const long long b_off = want ? plane_off(a.base, n) : 0;
+#pragma unroll
+        for (int k = 0; k < NFIN; ++k) {
+            const int i = tid + k * NT;
+            int r, c;
+            if (xfast_out) { r = i / TW; c = i - r * TW; }
+            else { c = i / TH; r = i - c * TH; }
+            const int gy = y0 + r, gx = x0 + c;
+            bpre[k] = 0.0f;
+            if (want && i < TH * TW && gy < H && gx < W) bpre[k] = __ldg(a.base.p + b_off + (long long)gy * a.base.rs + (long long)gx * a.base.cs);
+        }
+    }
+
     // ---- conv4 (16 -> 1): out = ((b4 + T_0) + T_1) + ... + T_8 over the 3x3 neighbourhood of partials -> so -----------
     for (int i = tid; i < TH * TW; i += NT) {
         const int r = i / TW, c = i - r * TW;
-        float acc = sf[F_B4];
+        float acc = cw.b4;
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
             const int m = (r + k / 3) * P + c + (k % 3);   // conv3 pixel index (origin (-1,-1)) of the neighbour
@@ -483,14 +501,16 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
 
     // ---- lifting arithmetic + stores -----------------------------------------------------------------------
     {
-        const bool xfast = a.out.cs <= a.out.rs;
+        const bool xfast = xfast_out;
         const long long o_off = plane_off(a.out, n);
-        const long long b_off = a.base.p ? plane_off(a.base, n) : 0;
         const long long p_off = a.pred.p ? plane_off(a.pred, n) : 0;
         const long long x_off = a.aux.p ? plane_off(a.aux, n) : 0;
         const float bd1 = (n >= a.div_group_n) ? a.base_div1_g1 : a.base_div1;
         const bool bdiv = (bd1 != 1.0f) || (a.base_div2 != 1.0f);
-        for (int i = tid; i < TH * TW; i += NT) {
+#pragma unroll
+        for (int k = 0; k < NFIN; ++k) {
+            const int i = tid + k * NT;
+            if (i >= TH * TW) break;
             int r, c;
             if (xfast) { r = i / TW; c = i - r * TW; }
             else { c = i / TH; r = i - c * TH; }
@@ -510,7 +530,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                 if (a.mode == PMCTF_MODE_FILTER) {
                     res = rr;
                 } else {
-                    float b = __ldg(a.base.p + b_off + (long long)gy * a.base.rs + (long long)gx * a.base.cs);
+                    float b = bpre[k];
                     if (bdiv) b = (b / bd1) / a.base_div2;
                     res = (a.sign > 0.0f) ? b + rr : b - rr;
                     res = res * a.final_mul;
@@ -586,7 +606,37 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int variant, int reps
 
 } // namespace tc
 
-// host side: called by launch_step() in pmctf_kernels.cu
+// ---- host side ---------------------------------------------------------------------------------------------------
+// Registry of the small fp32 parameters per packed block (keyed by its device address): pmctf_pack_pu_weights() reads the
+// freshly packed block back once (40 KB, one synchronisation per weight version) so that every later launch can pass
+// conv1 / conv4 / the biases as kernel arguments.
+static std::mutex g_w_mutex;
+static std::unordered_map<const float *, tc::TcW> g_w_registry;
+
+int register_packed_weights(const float *packed, cudaStream_t st)
+{
+    std::vector<float> h(PMCTF_PU_PACKED_FLOATS);
+    cudaError_t e = cudaMemcpyAsync(h.data(), packed, sizeof(float) * PMCTF_PU_PACKED_FLOATS, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return (int)e;
+    tc::TcW w;
+    for (int i = 0; i < 144; ++i) w.w1[i] = h[tc::W1_OFF + i];
+    for (int i = 0; i < 16; ++i) {
+        w.b1[i] = h[tc::B1_OFF + i];
+        w.b2[i] = h[tc::B2_OFF + i];
+        w.b3[i] = h[tc::B3_OFF + i];
+        for (int k = 0; k < 8; ++k) w.w4[i][k] = h[tc::W4_OFF + i * 12 + k];
+        w.w48[i] = h[tc::W4_OFF + i * 12 + 8];
+    }
+    w.b4 = h[tc::B4_OFF];
+    w.sc2 = h[tc::SC_OFF];
+    w.sc3 = h[tc::SC_OFF + 1];
+    std::lock_guard<std::mutex> lk(g_w_mutex);
+    g_w_registry[packed] = w;
+    return 0;
+}
+
+// called by launch_step() in pmctf_kernels.cu
 int launch_step_tc(const StepD &d, int src_kind, int *err_flag, cudaStream_t st)
 {
     static bool configured = false;
@@ -606,13 +656,20 @@ int launch_step_tc(const StepD &d, int src_kind, int *err_flag, cudaStream_t st)
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return (int)cudaGetLastError();
         resident = 2 * sms;
     }
+    tc::TcW w;
+    {
+        std::lock_guard<std::mutex> lk(g_w_mutex);
+        auto it = g_w_registry.find(d.pu_packed);
+        if (it == g_w_registry.end()) return PMCTF_EINVAL;   // block was not produced by pmctf_pack_pu_weights()
+        w = it->second;
+    }
     const long long tiles = (long long)((d.w + tc::TW - 1) / tc::TW) * ((d.h + tc::TH - 1) / tc::TH) * d.n;
     if (tiles > 0x7fffffffLL) return PMCTF_ESHAPE;
     dim3 grid((unsigned)(tiles < resident ? tiles : resident));
     switch (src_kind) {
-    case PMCTF_SRC_PLANE: tc::lift_step_tc_kernel<PMCTF_SRC_PLANE><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(d, err_flag); break;
-    case PMCTF_SRC_WARP: tc::lift_step_tc_kernel<PMCTF_SRC_WARP><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(d, err_flag); break;
-    case PMCTF_SRC_SKIP3: tc::lift_step_tc_kernel<PMCTF_SRC_SKIP3><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(d, err_flag); break;
+    case PMCTF_SRC_PLANE: tc::lift_step_tc_kernel<PMCTF_SRC_PLANE><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(d, w, err_flag); break;
+    case PMCTF_SRC_WARP: tc::lift_step_tc_kernel<PMCTF_SRC_WARP><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(d, w, err_flag); break;
+    case PMCTF_SRC_SKIP3: tc::lift_step_tc_kernel<PMCTF_SRC_SKIP3><<<grid, tc::NT, tc::SMEM_BYTES, st>>>(d, w, err_flag); break;
     default: return PMCTF_EINVAL;
     }
     return (int)cudaGetLastError();
