@@ -447,11 +447,13 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     }
                     umma::fence_before_sync();
                     mbar_arrive(empty0 + 8 * slot);
-                    // the partials replace the pixel's own digit records (their last reader, this block's MMAs, is done)
-                    uint8_t *d = A1 + m * 16;
-                    *reinterpret_cast<float4 *>(d) = make_float4(tp[0].x, tp[0].y, tp[1].x, tp[1].y);
-                    *reinterpret_cast<float4 *>(d + PLANE) = make_float4(tp[2].x, tp[2].y, tp[3].x, tp[3].y);
-                    *reinterpret_cast<float *>(d + 2 * PLANE) = t8;
+                    // the partials go over the digit records of this (finished) block, tap-planar inside the block so that the
+                    // stores and the gather below are free of bank conflicts: T_k[m] at plane k/4, block, sub-plane k%4, word m%128
+                    float *d = reinterpret_cast<float *>(A1 + blk * 2048) + (m & 127);
+                    constexpr int PW = PLANE / 4;
+                    d[0] = tp[0].x; d[128] = tp[0].y; d[256] = tp[1].x; d[384] = tp[1].y;
+                    d[PW] = tp[2].x; d[PW + 128] = tp[2].y; d[PW + 256] = tp[3].x; d[PW + 384] = tp[3].y;
+                    d[2 * PW] = t8;
                 }
             }
         }
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
             const int m = (r + k / 3) * P + c + (k % 3);   // conv3 pixel index (origin (-1,-1)) of the neighbour
-            acc = acc + *reinterpret_cast<const float *>(A1 + (k >> 2) * PLANE + m * 16 + (k & 3) * 4);
+            acc = acc + *reinterpret_cast<const float *>(A1 + (k >> 2) * PLANE + (m >> 7) * 2048 + (k & 3) * 512 + (m & 127) * 4);
         }
         so[r * O_P + c] = acc;
     }
