@@ -507,8 +507,10 @@ __global__ void __launch_bounds__(512) pack_pu_kernel(const float *w1, const flo
         packed[i] = v;
     }
     // tensor-core operands of conv2 / conv3: W = rint(w * 2^Sw), Sw = 22 - e with max|w| = m * 2^e, m in [0.5, 1);
-    // three signed-byte digits W = e0*2^16 + e1*2^8 + e2; image layout per tap pair tp (tests/umma_ref.py:pack_weights):
-    //   byte [tp*1536 + chunk*768 + (digit*16 + co)*16 + ci], chunk = which tap of the pair
+    // three signed-byte digits W = e0*2^16 + e1*2^8 + e2; image layout (tests/umma_ref.py:pack_weights):
+    //   tap pairs tp = 0..3 and tap 8 alone (tp = 4, second chunk zero): byte [tp*1536 + chunk*768 + (digit*16 + co)*16 + ci];
+    //   tap 8 against the activation digit pair (d1 | d2): byte [7680 + chunk*1024 + (row block*16 + co)*16 + ci], weight digit j
+    //   in row block j of chunk 0 and row block j + 1 of chunk 1 (the other row blocks zero)
     __shared__ float red[512];
     __shared__ int s_sw[2];
     int8_t *img = reinterpret_cast<int8_t *>(packed + Q_OFF);
@@ -545,9 +547,10 @@ __global__ void __launch_bounds__(512) pack_pu_kernel(const float *w1, const flo
             const int d0 = (V1 - d1) >> 8;
             int8_t *o = img + layer * QBYTES + tp * 1536 + chunk * 768 + co * 16 + ci;
             o[0] = (int8_t)d0; o[256] = (int8_t)d1; o[512] = (int8_t)d2;
-            if (tp == 0) { // 80-row copy: [chunk][80 rows][16], rows 48..79 zero
-                int8_t *z = img + layer * QBYTES + 7680 + chunk * 1280 + co * 16 + ci;
-                z[0] = (int8_t)d0; z[256] = (int8_t)d1; z[512] = (int8_t)d2; z[768] = 0; z[1024] = 0;
+            if (tp == 4 && chunk == 0) {
+                int8_t *z = img + layer * QBYTES + 7680 + co * 16 + ci;
+                z[0] = (int8_t)d0; z[256] = (int8_t)d1; z[512] = (int8_t)d2; z[768] = 0;
+                z[1024] = 0; z[1024 + 256] = (int8_t)d0; z[1024 + 512] = (int8_t)d1; z[1024 + 768] = (int8_t)d2;
             }
         }
         __syncthreads();

@@ -67,12 +67,13 @@ static_assert(NBLK == 2 * NSLOT && NSLOT * SLOT_COLS <= TMEM_COLS, "every accumu
 
 // packed parameter block (floats, see pack_pu_kernel)
 constexpr int W1_OFF = 0, B1_OFF = 144, B2_OFF = 2464, B3_OFF = 4784, W4_OFF = 4800, B4_OFF = 4992;
-constexpr int Q_OFF = 5000, QBYTES = 10240, Q0_OFF = 7680, SC_OFF = 10120; // Q0: 80-row image of tap pair 0
+constexpr int Q_OFF = 5000, QBYTES = 10240, QIMG = 9728, QL_OFF = 7680, SC_OFF = 10120; // QBYTES: stride of the two layers in
+                                                  // the packed block, QIMG: bytes used (copied to shared memory), QL: digit-pair image of tap 8
 static_assert(PMCTF_PU_PACKED_FLOATS == 10128, "header and kernel disagree on the packed size");
 
 // shared memory (bytes)
-constexpr int SM_WB = 0;                              // 2 x 10240 B operand images
-constexpr int SM_S = SM_WB + 2 * QBYTES;
+constexpr int SM_WB = 0;                              // 2 x 9728 B operand images
+constexpr int SM_S = SM_WB + 2 * QIMG;
 constexpr int SM_T = SM_S + ((S_ROWS * S_P * 4 + 127) / 128) * 128;
 constexpr int SM_A1 = SM_T + ((T_ROWS * T_P * 4 + 127) / 128) * 128;
 constexpr int SM_C1 = SM_A1 + 3 * PLANE;              // conv1 stash (4 quarter planes); the conv4 sums of the tile alias it later
@@ -117,25 +118,27 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
                  : "memory");
 }
 
-// the 15 MMAs of one 128-pixel block: activation digit d times the stacked weight digits [w0; w1; w2] (N = 48)
-// lands in accumulator groups d, d+1, d+2.  The very first MMA uses the 80-row image of tap pair 0 (rows 48..79
-// are zero) with accumulate = 0, which initialises all five groups at once.
+// the 14 MMAs of one 128-pixel block: activation digit d times the stacked weight digits [w0; w1; w2] (N = 48)
+// lands in accumulator groups d, d+1, d+2.  Taps 0..7 go pairwise (K = 2 taps x 16 channels); tap 8 goes once for
+// digit 0 (second K half against zero weights) and once for the digit PAIR d1 | d2 (K = 2 digits x 16 channels: the
+// two K chunks are one plane apart, N = 64 -> groups 1..4).  The very first MMA does not accumulate and thereby
+// initialises groups 0..2; groups 3 and 4 were zeroed by the epilogue that drained this slot before.
 __device__ __forceinline__ void issue_block(uint32_t a_saddr, uint32_t b_saddr, uint32_t d_tmem)
 {
 #pragma unroll
-    for (int tp = 0; tp < 5; ++tp) {
-        const int t0 = (tp < 3) ? tp * P : (tp == 3 ? 2 : 2 * P + 2);          // first tap of the pair (pixels)
-        const int lbo = (tp < 3) ? 16 : (tp == 3 ? P * 16 : 16);                 // byte distance to the second tap
-        const uint32_t b = b_saddr + tp * 1536;
+    for (int tp = 0; tp < 4; ++tp) {
+        const int t0 = (tp < 3) ? tp * P : 2;                                    // first tap of the pair (pixels)
+        const int lbo = (tp < 3) ? 16 : P * 16;                                  // byte distance to the second tap
+        const uint64_t bd = umma::smem_desc(b_saddr + tp * 1536, 768, 128);
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const uint64_t ad = umma::smem_desc(a_saddr + d * PLANE + t0 * 16, lbo, 128);
-            if (tp == 0 && d == 0)
-                umma::mma_s8(d_tmem, ad, umma::smem_desc(b_saddr + Q0_OFF, 1280, 128), umma::idesc_s8(80), 0u);
-            else
-                umma::mma_s8(d_tmem + 16 * d, ad, umma::smem_desc(b, 768, 128), umma::idesc_s8(48, d > 0), 1u);
-        }
+        for (int d = 0; d < 3; ++d)
+            umma::mma_s8(d_tmem + 16 * d, umma::smem_desc(a_saddr + d * PLANE + t0 * 16, lbo, 128), bd, umma::idesc_s8(48, d > 0),
+                         (tp == 0 && d == 0) ? 0u : 1u);
     }
+    constexpr int T8 = (2 * P + 2) * 16;
+    umma::mma_s8(d_tmem, umma::smem_desc(a_saddr + T8, 16, 128), umma::smem_desc(b_saddr + 4 * 1536, 768, 128), umma::idesc_s8(48), 1u);
+    umma::mma_s8(d_tmem + 16, umma::smem_desc(a_saddr + PLANE + T8, PLANE, 128), umma::smem_desc(b_saddr + QL_OFF, 1024, 128),
+                 umma::idesc_s8(64, true), 1u);
 }
 
 // exact integer dot product S = o0*2^32 + (o1*256 + o2)*2^16 + (o3*256 + o4) from the five accumulator groups
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     {
         const int4 *g = reinterpret_cast<const int4 *>(a.pu_packed + Q_OFF);
         int4 *d = reinterpret_cast<int4 *>(smem + SM_WB);
-        for (int i = tid; i < 2 * QBYTES / 16; i += NT) d[i] = __ldg(g + i);
+        for (int i = tid; i < 2 * QIMG / 16; i += NT) d[i] = __ldg(g + (i / (QIMG / 16)) * (QBYTES / 16) + i % (QIMG / 16));
         load_tanh_table(ttab, tid, NT);
         if (tid == 0) {
             for (int i = 0; i < NSLOT; ++i) {
@@ -211,6 +214,17 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     const uint32_t tbase = *tmem_slot;
     const uint32_t full0 = umma::smem_u32(bars), empty0 = umma::smem_u32(bars + NSLOT);
     bool ok = true;
+    if (warp < 4) {   // accumulator groups 3 and 4 of every slot start at zero (later each epilogue re-zeroes the slot it drained)
+#pragma unroll
+        for (int sl = 0; sl < NSLOT; ++sl) {
+            umma::tmem_zero16(tbase + ((uint32_t)(warp * 32) << 16) + sl * SLOT_COLS + 48);
+            umma::tmem_zero16(tbase + ((uint32_t)(warp * 32) << 16) + sl * SLOT_COLS + 64);
+        }
+        umma::tmem_st_wait();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
     const bool xfast_src = a.src.cs <= a.src.rs;
 
     // ---- persistent loop over tiles: every accumulator slot completes exactly twice per layer, so the mbarrier
@@ -347,7 +361,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
         const uint32_t a_saddr = umma::smem_u32(A1);
-        const uint32_t b_saddr = umma::smem_u32(smem + SM_WB + layer * QBYTES);
+        const uint32_t b_saddr = umma::smem_u32(smem + SM_WB + layer * QIMG);
         if (warp == MMA_WARP) {
             if (dbg && lane == 0) dbg[8 + 2 * layer] = clock64();
             // the whole warp walks the (uniform) loop; one elected lane issues
@@ -407,6 +421,9 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                         }
                         w[0][q] = w0; w[1][q] = w1; w[2][q] = w2;
                     }
+                    umma::tmem_zero16(taddr + 48);   // groups 3, 4 are accumulate-only for the MMAs: hand the slot back zeroed
+                    umma::tmem_zero16(taddr + 64);
+                    umma::tmem_st_wait();
                     umma::fence_before_sync();
                     mbar_arrive(empty0 + 8 * slot);
                     uint8_t *d = A1 + m * 16;   // in place: every MMA that reads these records has completed (full barrier of this block)
@@ -445,6 +462,9 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                             t8 = fmaf(cw.w48[4 * q + j], a3v, t8);
                         }
                     }
+                    umma::tmem_zero16(taddr + 48);   // groups 3, 4 are accumulate-only for the MMAs: hand the slot back zeroed
+                    umma::tmem_zero16(taddr + 64);
+                    umma::tmem_st_wait();
                     umma::fence_before_sync();
                     mbar_arrive(empty0 + 8 * slot);
                     // the partials go over the digit records of this (finished) block, tap-planar inside the block so that the

@@ -93,6 +93,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// zero 16 consecutive 32-bit columns of this warp's 32 lanes (thread i owns lane 32*(warp%4)+i, as for the loads)
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr)
+{
+    const uint32_t z = 0u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint32_t mbar_saddr, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_saddr), "r"(count) : "memory");

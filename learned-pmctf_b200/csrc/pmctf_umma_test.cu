@@ -54,6 +54,12 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const int8_t *__r
     uint32_t phase = 0;
     bool ok = true;
     for (int blk = 0; blk < n_blocks && ok; ++blk) {
+        // accumulators start at zero (op lists may initialise only part of the columns with their first MMA)
+        for (int c0 = 0; c0 < out_cols; c0 += 16) umma::tmem_zero16(tbase + ((uint32_t)(warp * 32) << 16) + c0);
+        umma::tmem_st_wait();
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
         long long t0 = 0;
         if (tid == 0) {
             t0 = clock64();

@@ -23,7 +23,7 @@ def test_conv_oplist_is_exact():
     A = np.concatenate([d.reshape(-1) for d in U.split_digits(Aint)])
     B = U.pack_weights(Wint)
     ops = U.conv_ops(pitch, plane)
-    assert len(ops) == 15
+    assert len(ops) == 14
     out = U.emulate(A, B, ops, n_blocks, 128 * 16, 80)
     assert np.abs(out).max() < 2 ** 31, "accumulator groups must fit int32"
     got = U.combine_orders(out).reshape(n_blocks * 128, 16)

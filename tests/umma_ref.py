@@ -1,5 +1,6 @@
 """numpy emulation of the tcgen05 kind::i8 op lists executed by pmctf_umma_selftest, and the builder of the op list
-the lifting convolution uses (3 signed-byte digits per operand, 5 tap pairs, 5 accumulator groups).  Test infrastructure."""
+the lifting convolution uses (3 byte digits per operand, 4 tap pairs + tap 8 as a digit pair, 5 accumulator groups).
+Test infrastructure."""
 import numpy as np
 
 TAP_PAIRS = [((0, 0), (0, 1)), ((1, 0), (1, 1)), ((2, 0), (2, 1)), ((0, 2), (1, 2)), ((2, 2), None)]
@@ -50,8 +51,11 @@ def split_digits_twos(v):
 
 
 def pack_weights(W):
-    """W int [16 co, 16 ci, 3, 3] (|W| <= 2^22) -> int8 image (10240 B): per tap pair a [2 chunks][48 rows = (digit, co)][16 ci]
-    block (5 x 1536 B), followed by the 80-row copy of tap pair 0 ([2][80][16], rows 48..79 zero) at byte 7680."""
+    """W int [16 co, 16 ci, 3, 3] (|W| <= 2^22) -> int8 image (10240 B, 9728 used):
+      * per tap pair tp = 0..3 a [2 chunks][48 rows = (digit, co)][16 ci] block at tp*1536;
+      * tap 8 (ky = kx = 2) for the most significant activation digit: the same block format at 6144, second chunk zero;
+      * tap 8 for the activation digit PAIR (d1 | d2): [2 chunks][64 rows = (group - 1, co)][16 ci] at 7680: chunk 0
+        (times d1) holds weight digit j in row block j, chunk 1 (times d2) holds weight digit j in row block j + 1."""
     d = split_digits(W)
     out = np.zeros((5, 2, 48, 16), np.int8)
     for tp, pair in enumerate(TAP_PAIRS):
@@ -60,26 +64,30 @@ def pack_weights(W):
                 continue
             for j in range(3):
                 out[tp, c, j * 16:(j + 1) * 16, :] = d[j][:, :, tap[0], tap[1]]
-    first = np.zeros((2, 80, 16), np.int8)
-    first[:, :48] = out[0]
-    return np.concatenate([out.reshape(-1), first.reshape(-1)])
+    last = np.zeros((2, 64, 16), np.int8)
+    for j in range(3):
+        last[0, j * 16:(j + 1) * 16, :] = d[j][:, :, 2, 2]
+        last[1, (j + 1) * 16:(j + 2) * 16, :] = d[j][:, :, 2, 2]
+    return np.concatenate([out.reshape(-1), last.reshape(-1), np.zeros(512, np.int8)])
 
 
 def conv_ops(pitch, plane_bytes, twos=False):
-    """Op list of one 128-pixel block of the 16->16 3x3 convolution (15 MMAs): D columns [16*i, 16*i+16) accumulate the
-    digit products of order i (weight 2^(32-8i)): a_d x [w0; w1; w2] lands in groups d, d+1, d+2.  The first MMA uses the
-    80-row image (zero rows 48..79) without accumulation and thereby initialises all five groups."""
+    """Op list of one 128-pixel block of the 16->16 3x3 convolution (14 MMAs): D columns [16*i, 16*i+16) accumulate the
+    digit products of order i (weight 2^(32-8i)): a_d x [w0; w1; w2] lands in groups d, d+1, d+2.  Taps 0..7 go pairwise
+    (K = 2 taps x 16 channels) per activation digit; tap 8 goes once for digit 0 (second K half against zero weights) and
+    once for the digit pair (d1 | d2) (K = 2 digits x 16 channels, N = 64 -> groups 1..4).  The first MMA does not
+    accumulate and initialises groups 0..2; groups 3, 4 are zeroed by whoever drained the accumulators before."""
     ops = []
-    for tp, (t0, t1) in enumerate(TAP_PAIRS):
+    for tp, (t0, t1) in enumerate(TAP_PAIRS[:4]):
         a_off = (t0[0] * pitch + t0[1]) * 16
-        lbo = ((t1[0] * pitch + t1[1]) - (t0[0] * pitch + t0[1])) * 16 if t1 is not None else 16
+        lbo = ((t1[0] * pitch + t1[1]) - (t0[0] * pitch + t0[1])) * 16
         for d in range(3):
-            if tp == 0 and d == 0:
-                ops.append(dict(a_off=a_off, a_lbo=lbo, a_sbo=128, b_off=7680, b_lbo=1280, b_sbo=128, n=80, d_col=0, accumulate=0,
-                                a_unsigned=0))
-            else:
-                ops.append(dict(a_off=d * plane_bytes + a_off, a_lbo=lbo, a_sbo=128, b_off=tp * 1536, b_lbo=768, b_sbo=128,
-                                n=48, d_col=16 * d, accumulate=1, a_unsigned=int(twos and d > 0)))
+            ops.append(dict(a_off=d * plane_bytes + a_off, a_lbo=lbo, a_sbo=128, b_off=tp * 1536, b_lbo=768, b_sbo=128,
+                            n=48, d_col=16 * d, accumulate=int(not (tp == 0 and d == 0)), a_unsigned=int(twos and d > 0)))
+    t8 = (2 * pitch + 2) * 16
+    ops.append(dict(a_off=t8, a_lbo=16, a_sbo=128, b_off=6144, b_lbo=768, b_sbo=128, n=48, d_col=0, accumulate=1, a_unsigned=0))
+    ops.append(dict(a_off=plane_bytes + t8, a_lbo=plane_bytes, a_sbo=128, b_off=7680, b_lbo=1024, b_sbo=128, n=64, d_col=16,
+                    accumulate=1, a_unsigned=int(twos)))
     return ops
 
 
