@@ -443,20 +443,21 @@ def main():
                 "achieved_definition": "sum over timed launches of (pixels through PredictUpdate x 9792 FLOP) / sum of CUDA-event time "
                                        "around those launches (events on the launching stream inside the timed region)"}
     if mode == "tensor":
-        # executed int8 tensor-core work: per 16x32 tile 12 blocks x (1 MMA 128x80x32 + 14 MMAs 128x48x32), 2 ops per MAC
-        ops_per_px = 12 * (128 * 80 * 32 + 14 * 128 * 48 * 32) * 2 / 512.0
+        # executed int8 tensor-core work: per 16x32 tile 12 blocks x (13 MMAs 128x48x32 + 1 MMA 128x64x32), 2 ops per MAC
+        ops_per_px = 12 * (13 * 128 * 48 * 32 + 128 * 64 * 32) * 2 / 512.0
         roofline.update({
             "kernel": "lift_step_tc_kernel<PLANE|WARP|SKIP3>: warp/skip + PredictUpdate CNN + lifting accumulate; conv2/conv3 as exact "
                       "int8 digit-split implicit GEMMs on tcgen05 (UTCIMMA, accumulators in TMEM), conv1/conv4/tanh on CUDA cores",
-            "traffic": 35.6e6,
-            "traffic_note": "dram__bytes_read+write of ONE launch from ncu --set full (profiles/r1g_lift_step_tc_ncu.txt): the 1080p luma "
+            "traffic": 35.5e6,
+            "traffic_note": "dram__bytes_read+write of ONE launch from ncu --set full (profiles/r1s_lift_step_tc_ncu.txt): the 1080p luma "
                             "temporal step, 2.21 Mpx, algorithmic 44.2 MB (20 B/px); outputs stay in the 126 MB L2, so DRAM traffic is "
                             "below the algorithmic bytes -- no wasted re-reads.  Not measured live.",
             "executed_int8_tops": ks["pixels"] * ops_per_px / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
             "executed_int8_ops_per_px": ops_per_px, "int8_dense_peak_tops_nominal": 4500.0,
-            "note": "9 digit products per MAC (3 signed-byte digits per operand) make the convolution exact, so executed tensor work is "
-                    "~15x the algorithmic FLOPs; with N = 48 the MMA rate is set by the A-operand fetch from shared memory (~47 cycles per "
-                    "128x48x32 MMA measured), and the kernel as a whole by shared-memory bandwidth + CUDA-core issue (profiles/)"})
+            "note": "9 digit products per MAC (3 byte digits per operand) make the convolution exact, so executed tensor work is "
+                    "~13.5x the algorithmic FLOPs; with N = 48 the MMA rate is set by the operand fetch from shared memory (~42 cycles per "
+                    "128x48x32 MMA measured), and the kernel as a whole by the shared-memory data pipe, which the tensor-core operand "
+                    "fetch and the CUDA-core loads/stores share (~90 % busy, profiles/r1s_lift_step_tc_ncu.txt)"})
     else:
         roofline.update({
             "kernel": "lift_step_kernel<PLANE|WARP|SKIP3> (warp/skip + PredictUpdate CNN + lifting accumulate, fp32 FFMA chains on CUDA cores)",

@@ -131,7 +131,10 @@ int pmctf_tc_debug_times(long long *out16);
 int pmctf_tc_mma_probe(int variant, int reps, long long *out3_device, void *stream);
 
 /* Repack one PredictUpdate's 8 tensors (OIHW, as in the state_dict) into the kernel layout.
- * Replaces nothing in the reference; run once per weight version. */
+ * Replaces nothing in the reference; run once per weight version.  The call also reads the packed block back once
+ * (40 KB, synchronises `stream`) and registers its small fp32 parameters (conv1, conv4, biases) under the address of
+ * `packed`: the tensor-core step kernel takes them as kernel arguments.  A step launched with a `pu_packed` block that
+ * did not come from this call (e.g. a device-side copy of one) is rejected with PMCTF_EINVAL in tensor mode. */
 int pmctf_pack_pu_weights(const float *w1, const float *b1, const float *w2, const float *b2,
                           const float *w3, const float *b3, const float *w4, const float *b4,
                           float *packed, void *stream);
