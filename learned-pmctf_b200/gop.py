@@ -65,12 +65,17 @@ class GopCodec:
     """MCTF analysis -> pWave++ analysis -> quantise -> dequantise -> pWave++ synthesis -> MCTF synthesis
     for whole GOPs.  `model` is a learned_pmctf_b200.pMCTF (or an accelerate()d reference model)."""
 
-    def __init__(self, model, gop_size: int = 16, q_index: Optional[int] = None):
+    def __init__(self, model, gop_size: int = 16, q_index: Optional[int] = None, concurrent_chroma: bool = True):
         self.m = model
         self.gop_size = gop_size
         self.stages = num_stages(gop_size)
         self.q_index = q_index
         self._qcache = {}
+        # luma and chroma never meet on the path (the motion field is read-only), so code_gop() runs the chroma chain on a
+        # side stream: the tail of every persistent launch (CTAs that run out of tiles) and the small launches of the deep
+        # wavelet levels are filled by the other chain's kernels
+        self.concurrent_chroma = concurrent_chroma
+        self._side = {}
 
     # step sizes exactly as forward_one_stage derives them (pMCTF_L.py:343-349, pWave.py:231-238)
     def q_pair(self, coder: str, stage: int):
@@ -141,6 +146,37 @@ class GopCodec:
             Ly, Lc = by, bc
         return Ly, Lc
 
+    def _stream_for(self, key, device):
+        st = self._side.get(key)
+        if st is None:
+            st = self._side[key] = torch.cuda.Stream(device)
+        return st
+
+    def _chain(self, X, mvs, chroma: bool, want_stats: bool):
+        """analysis -> code -> synthesis of ONE plane type (luma [G,1,H,W] or chroma [G,2,1,h,w]), everything on the
+        current stream.  Same calls in the same order as analysis() / code() / synthesis() make for that plane type."""
+        m = self.m
+        L, Hs = X, []
+        for s in range(self.stages):
+            me = min(m.num_me_stages - 1, s)
+            if mvs[s].size(0) != L.size(0) // 2:
+                raise RuntimeError(f"stage {s}: expected {L.size(0) // 2} motion fields, got {mvs[s].size(0)}")
+            L, H, _, _ = m.forward_MCTF(L[0::2], L[1::2], mvs[s], stage_idx=me, mv_down=chroma, want_pred=False)
+            Hs.append(H)
+        st = [] if want_stats else None
+        Hhat = []
+        for s, H in enumerate(Hs):
+            q, qll = self.q_pair("hp", s)
+            Hhat.append(self._code(m.hp_coder, H, q, qll, st))
+        q, qll = self.q_pair("lp", 0)
+        L = self._code(m.lp_coder, L, q, qll, st)
+        for s in range(self.stages - 1, -1, -1):
+            me = min(m.num_me_stages - 1, s)
+            b = torch.empty((2 * L.size(0),) + tuple(L.shape[1:]), dtype=torch.float32, device=L.device)
+            m.inverse_MCTF(L, Hhat[s], mvs[s], downscale=chroma, stage_idx=me, out_ref=b[0::2], out_cur=b[1::2])
+            L = b
+        return L, st
+
     # ---------------------------------------------------------------------------------------
     def _frame_of_plane(self):
         """GOP frame index of every coded plane in the order `code` emits statistics."""
@@ -158,9 +194,22 @@ class GopCodec:
         G = self.gop_size
         if Y.size(0) != G or C.size(0) != G:
             raise RuntimeError(f"expected {G} frames, got {Y.size(0)} / {C.size(0)}")
-        Ly, Lc, Hs = self.analysis(Y, C, mvs)
-        Ly_hat, Lc_hat, Hhat, sy, sc = self.code(Ly, Lc, Hs, want_stats)
-        rec_y, rec_c = self.synthesis(Ly_hat, Lc_hat, Hhat, mvs)
+        for s in range(self.stages):   # resolve the quantisation steps (host scalars) before any stream forks
+            self.q_pair("hp", s)
+        self.q_pair("lp", 0)
+        if self.concurrent_chroma and Y.is_cuda:
+            cur = torch.cuda.current_stream(Y.device)
+            side = self._stream_for((Y.device, "chroma", cur.cuda_stream), Y.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                rec_c, sc = self._chain(C, mvs, True, want_stats)
+            rec_y, sy = self._chain(Y, mvs, False, want_stats)
+            cur.wait_stream(side)
+            for t in [rec_c] + (sc or []):
+                t.record_stream(cur)
+        else:
+            rec_y, sy = self._chain(Y, mvs, False, want_stats)
+            rec_c, sc = self._chain(C, mvs, True, want_stats)
         if not want_stats:
             return rec_y, rec_c, None
         dev = Y.device
@@ -188,13 +237,55 @@ class GopCodec:
         return rec_y, rec_c, st
 
     # ---------------------------------------------------------------------------------------
+    # GOPs in flight (GOPs are independent: test_pMCTF_flex.py:131-134); each lane = a luma + a chroma stream.  Measured on B200:
+    # the luma | chroma overlap of one GOP already fills the launch tails (145 -> 162 frames/s); a second lane adds nothing (160).
+    GOP_LANES = 1
+
+    def _lane(self, device, g: int):
+        cur = torch.cuda.current_stream(device)
+        if not self.concurrent_chroma or self.GOP_LANES <= 1:
+            return cur
+        return self._stream_for((device, "lane", cur.cuda_stream, g % self.GOP_LANES), device)
+
+    @torch.no_grad()
+    def code_sequence(self, Y, C, mvs_per_gop, y_u8=None, c_u8=None):
+        """Whole GOPs of a device-resident sequence: Y [F,1,H,W], C [F,2,1,H/2,W/2], mvs_per_gop[g] as code_gop takes them.
+        Consecutive GOPs alternate between GOP_LANES stream pairs, so that the serial tail of one GOP's launch chain is
+        covered by another GOP's kernels.  -> fp64 statistics [F/G, G, N_STATS] on the device, ordered on the current stream."""
+        G = self.gop_size
+        n_gops = Y.size(0) // G
+        if Y.size(0) % G or len(mvs_per_gop) != n_gops:
+            raise RuntimeError("frame count must be a multiple of the GOP size, one motion-field list per GOP")
+        dev = Y.device
+        cur = torch.cuda.current_stream(dev)
+        out, lanes = [], []
+        for g in range(n_gops):
+            lane = self._lane(dev, g)
+            sl = slice(g * G, (g + 1) * G)
+            if lane is not cur:
+                if lane not in lanes:
+                    lanes.append(lane)
+                    lane.wait_stream(cur)
+                with torch.cuda.stream(lane):
+                    _, _, st = self.code_gop(Y[sl], C[sl], mvs_per_gop[g], None if y_u8 is None else y_u8[sl],
+                                             None if c_u8 is None else c_u8[sl])
+            else:
+                _, _, st = self.code_gop(Y[sl], C[sl], mvs_per_gop[g], None if y_u8 is None else y_u8[sl],
+                                         None if c_u8 is None else c_u8[sl])
+            out.append(st)
+        for lane in lanes:
+            cur.wait_stream(lane)
+        for st in out:
+            st.record_stream(cur)
+        return torch.stack(out)
+
     @torch.no_grad()
     def code_sequence_host(self, y_u8: torch.Tensor, c_u8: torch.Tensor, mvs_host: List[Sequence[torch.Tensor]],
                            psize: int = 128):
         """End-to-end entry point on HOST buffers: y_u8 [F,h0,w0], c_u8 [F,2,h0/2,w0/2] uint8 (pinned for
         speed) and per-GOP host motion fields; frames are uploaded GOP by GOP on a copy stream (overlapping the
-        previous GOP's kernels), unpacked + zero padded on the device, coded, and the [F, N_STATS] statistics are
-        returned on the host."""
+        kernels of earlier GOPs), unpacked + zero padded on the device, coded (GOPs alternating between GOP_LANES stream
+        pairs), and the [F, N_STATS] statistics are returned on the host."""
         G = self.gop_size
         F_, h0, w0 = y_u8.shape
         if F_ % G:
@@ -203,9 +294,10 @@ class GopCodec:
         hp, wp = h0 + pb, w0 + pr
         dev = next(self.m.parameters()).device
         cur = torch.cuda.current_stream(dev)
-        copy = self._copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(dev)
+        copy = self._stream_for((dev, "copy"), dev)
+        copy.wait_stream(cur)
 
-        def upload(g):  # H2D of GOP g on the copy stream, overlapping the kernels of GOP g-1
+        def upload(g):  # H2D of GOP g on the copy stream, overlapping the kernels of the GOPs before it
             with torch.cuda.stream(copy):
                 t = (y_u8[g * G:(g + 1) * G].to(dev, non_blocking=True), c_u8[g * G:(g + 1) * G].to(dev, non_blocking=True),
                      [m.to(dev, non_blocking=True) for m in mvs_host[g]])
@@ -213,19 +305,28 @@ class GopCodec:
                 ev.record(copy)
             return t, ev
 
-        out = []
+        out, lanes = [], []
         nxt = upload(0)
         for g in range(F_ // G):
             (yd, cd, mvd), ev = nxt
-            cur.wait_event(ev)
+            lane = self._lane(dev, g)
+            if lane is not cur and lane not in lanes:
+                lanes.append(lane)
+                lane.wait_stream(cur)
+            lane.wait_event(ev)
             for t in [yd, cd] + mvd:
-                t.record_stream(cur)
+                t.record_stream(lane)
             if g + 1 < F_ // G:
                 nxt = upload(g + 1)
-            Y = ops.unpack_u8(yd, hp, wp)
-            C = ops.unpack_u8(cd.view(-1, h0 // 2, w0 // 2), hp // 2, wp // 2).view(G, 2, 1, hp // 2, wp // 2)
-            _, _, st = self.code_gop(Y, C, mvd, yd, cd)
+            with torch.cuda.stream(lane):
+                Y = ops.unpack_u8(yd, hp, wp)
+                C = ops.unpack_u8(cd.view(-1, h0 // 2, w0 // 2), hp // 2, wp // 2).view(G, 2, 1, hp // 2, wp // 2)
+                _, _, st = self.code_gop(Y, C, mvd, yd, cd)
             out.append(st)
+        for lane in lanes:
+            cur.wait_stream(lane)
+        for st in out:
+            st.record_stream(cur)
         return torch.cat(out).cpu()
 
 

@@ -201,3 +201,59 @@ def test_config1_pwave_1080p_six_q_points_vs_oracle(P, model, weights, conv_mode
             rec = {lvl: {b: orc.dequantize(v.cpu().numpy(), qll if b == "ll" else q) for b, v in hat[lvl].items()} for lvl in hat}
             assert np.array_equal(x_hat.cpu().numpy(), orc.pwave_decode(rec, lp_w))
     assert nsym == 6 * 1152 * 1920
+
+
+@pytest.mark.parametrize("gop,h0,w0", [(4, 120, 190), (8, 256, 320), (16, 64, 96)])
+def test_concurrent_chroma_equals_single_stream(P, model, gop, h0, w0):
+    """GopCodec runs the chroma chain on a side stream (luma and chroma never meet on the path).  The two-stream run must be
+    bit-identical to the single-stream one, repeatedly (a cross-stream race would show up as a flaky difference), and the
+    public analysis()/code()/synthesis() trio must agree with both."""
+    from learned_pmctf_b200 import gop as Gm
+    _, pr, _, pb = Gm.get_padding_size(h0, w0, 128)
+    hp, wp = h0 + pb, w0 + pr
+    y, c, mvs = _inputs(gop, h0, w0, 23)
+    mvs = [cu(np.ascontiguousarray(np.pad(m, ((0, 0), (0, 0), (0, hp - h0), (0, wp - w0))))) for m in mvs]
+    yd, cd = cu(y), cu(c)
+    Y = P.ops.unpack_u8(yd, hp, wp)
+    C = P.ops.unpack_u8(cd.view(-1, h0 // 2, w0 // 2), hp // 2, wp // 2).view(gop, 2, 1, hp // 2, wp // 2)
+    serial = Gm.GopCodec(model, gop, q_index=12, concurrent_chroma=False)
+    ry, rc, st = serial.code_gop(Y, C, mvs, yd, cd)
+    torch.cuda.synchronize()
+    Ly, Lc, Hs = serial.analysis(Y, C, mvs)
+    Lyh, Lch, Hh, _, _ = serial.code(Ly, Lc, Hs)
+    ty, tc = serial.synthesis(Lyh, Lch, Hh, mvs)
+    assert torch.equal(ty, ry) and torch.equal(tc, rc)
+    both = Gm.GopCodec(model, gop, q_index=12)
+    assert both.concurrent_chroma
+    for _ in range(4):
+        by, bc, bst = both.code_gop(Y, C, mvs, yd, cd)
+        by2, bc2, _ = both.code_gop(Y, C, mvs, yd, cd)     # back to back: the second GOP forks while the first still runs
+        torch.cuda.synchronize()
+        assert torch.equal(by, ry) and torch.equal(bc, rc) and torch.equal(bst, st)
+        assert torch.equal(by2, ry) and torch.equal(bc2, rc)
+
+
+def test_code_sequence_lanes_equal_gop_by_gop(P, model):
+    """code_sequence() alternates GOPs between stream-pair lanes; its statistics must equal the GOP-by-GOP single-stream run."""
+    from learned_pmctf_b200 import gop as Gm
+    gop, h0, w0, n_gops = 4, 120, 190, 5
+    _, pr, _, pb = Gm.get_padding_size(h0, w0, 128)
+    hp, wp = h0 + pb, w0 + pr
+    ys, cs, mvl = [], [], []
+    for g in range(n_gops):
+        y, c, mvs = _inputs(gop, h0, w0, 31 + g)
+        ys.append(y), cs.append(c)
+        mvl.append([cu(np.ascontiguousarray(np.pad(m, ((0, 0), (0, 0), (0, hp - h0), (0, wp - w0))))) for m in mvs])
+    yd, cd = cu(np.concatenate(ys)), cu(np.concatenate(cs))
+    Y = P.ops.unpack_u8(yd, hp, wp)
+    C = P.ops.unpack_u8(cd.view(-1, h0 // 2, w0 // 2), hp // 2, wp // 2).view(gop * n_gops, 2, 1, hp // 2, wp // 2)
+    serial = Gm.GopCodec(model, gop, q_index=12, concurrent_chroma=False)
+    want = torch.stack([serial.code_gop(Y[g * gop:(g + 1) * gop], C[g * gop:(g + 1) * gop], mvl[g], yd[g * gop:(g + 1) * gop],
+                                        cd[g * gop:(g + 1) * gop])[2] for g in range(n_gops)])
+    assert torch.equal(serial.code_sequence(Y, C, mvl, yd, cd), want)
+    lanes = Gm.GopCodec(model, gop, q_index=12)
+    lanes.GOP_LANES = 2
+    for _ in range(3):
+        assert torch.equal(lanes.code_sequence(Y, C, mvl, yd, cd), want)
+    host = lanes.code_sequence_host(yd.cpu().pin_memory(), cd.cpu().pin_memory(), [[m.cpu().pin_memory() for m in g] for g in mvl])
+    assert torch.equal(host, want.reshape(-1, want.size(-1)).cpu())
