@@ -436,7 +436,11 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     const bool valid = inside && gy >= 0 && gy < H && gx >= 0 && gx < W;
                     float2 tp[4] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
                     float t8 = 0.0f;
+                    // warps whose 32 pixels all lie below the (TH+2)-row region have nothing to produce (the gather never reads
+                    // their partials); they only hand the slot back
+                    const bool warp_has_work = blk * 128 + quarter * 32 < A3_R * P;
                     uint32_t o[2][5][4];
+                    if (warp_has_work) {
 #pragma unroll
                     for (int k = 0; k < 5; ++k) tmem_ld4(taddr + 16 * k, o[0][k]);
 #pragma unroll
@@ -462,6 +466,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                             t8 = fmaf(cw.w48[4 * q + j], a3v, t8);
                         }
                     }
+                    }
                     umma::tmem_zero16(taddr + 48);   // groups 3, 4 are accumulate-only for the MMAs: hand the slot back zeroed
                     umma::tmem_zero16(taddr + 64);
                     umma::tmem_st_wait();
@@ -471,9 +476,11 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     // stores and the gather below are free of bank conflicts: T_k[m] at plane k/4, block, sub-plane k%4, word m%128
                     float *d = reinterpret_cast<float *>(A1 + blk * 2048) + (m & 127);
                     constexpr int PW = PLANE / 4;
+                    if (warp_has_work) {
                     d[0] = tp[0].x; d[128] = tp[0].y; d[256] = tp[1].x; d[384] = tp[1].y;
                     d[PW] = tp[2].x; d[PW + 128] = tp[2].y; d[PW + 256] = tp[3].x; d[PW + 384] = tp[3].y;
                     d[2 * PW] = t8;
+                    }
                 }
             }
         }
