@@ -99,19 +99,21 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-shared", "-Xcompiler", "-fPIC"]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
     """Compile the CUDA sources for sm_100a into lib/libpmctf_b200.so (in-tree, so the built file
-    travels with the repository snapshot to the GPU box)."""
+    travels with the repository snapshot to the GPU box).  `defines` / `out`: profiling variants (e.g.
+    ("PMCTF_TC_TIMING=1",) -> lib/libpmctf_b200_timing.so, loaded by setting PMCTF_LIB)."""
+    out = out or LIB_PATH
     newest = max(os.path.getmtime(p) for p in SOURCES + HEADERS + [os.path.join(INCLUDE, "pmctf_b200.h")])
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
-        return LIB_PATH
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= newest:
+        return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB_PATH, *SOURCES]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", INCLUDE, "-o", out, *SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)
-    return LIB_PATH
+    return out
 
 
 _lib = None

@@ -37,6 +37,9 @@
 #include "pmctf_common.cuh"
 #include "pmctf_umma.cuh"
 
+#ifndef PMCTF_TC_TIMING
+#define PMCTF_TC_TIMING 0   // 1: clock64 stamps of the phases of one CTA (pmctf_tc_debug_times, scratch/tc_phases.py); profiling builds only
+#endif
 #ifndef PMCTF_WHATIF
 #define PMCTF_WHATIF 0   // timing experiments only (bit 0: no conv1 residual recompute, bit 1: no tanh table lookup, bit 2: no MMAs)
 #endif
@@ -187,11 +190,19 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
     const int n_tiles = tiles_x * tiles_y * a.n;
     // optional phase timing of the 5th tile (or the only one) of CTA 1: err[2..] as long long stamps (profiling aid)
+#if PMCTF_TC_TIMING
     long long *dbg_cta = (err && blockIdx.x == 1) ? reinterpret_cast<long long *>(err + 2) : nullptr;
+#else
+    constexpr long long *dbg_cta = nullptr;
+#endif
     long long *dbg = nullptr;
     const long long t_cta0 = clock64();
     int tiles_done = 0;
+#if PMCTF_TC_TIMING
 #define STAMP(i) do { if (dbg && tid == 0) dbg[i] = clock64(); } while (0)
+#else
+#define STAMP(i) do { } while (0)
+#endif
 
     // ---- setup: parameters, barriers, TMEM ------------------------------------------------------------
     {
@@ -235,8 +246,10 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     const int trem = tile - n * (tiles_x * tiles_y);
     const int ty = trem / tiles_x;
     const int y0 = ty * TH, x0 = (trem - ty * tiles_x) * TW;
+#if PMCTF_TC_TIMING
     dbg = (tiles_done == 4 || n_tiles <= (int)gridDim.x * 4) ? dbg_cta : nullptr;
     if (dbg && tid == 0) dbg[12] = dbg[13] = 0;
+#endif
     STAMP(0);
 
     // ---- source tile ------------------------------------------------------------------------------------
@@ -363,7 +376,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
         const uint32_t a_saddr = umma::smem_u32(A1);
         const uint32_t b_saddr = umma::smem_u32(smem + SM_WB + layer * QIMG);
         if (warp == MMA_WARP) {
-            if (dbg && lane == 0) dbg[8 + 2 * layer] = clock64();
+            if (PMCTF_TC_TIMING && dbg && lane == 0) dbg[8 + 2 * layer] = clock64();
             // the whole warp walks the (uniform) loop; one elected lane issues
 #pragma unroll 1
             for (int blk = 0; blk < NBLK; ++blk) {
@@ -379,7 +392,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                 }
                 __syncwarp();
             }
-            if (dbg && lane == 0) dbg[9 + 2 * layer] = clock64();
+            if (PMCTF_TC_TIMING && dbg && lane == 0) dbg[9 + 2 * layer] = clock64();
         } else {
             const int grp = warp >> 2, quarter = warp & 3;
             const float scale = layer == 0 ? cw.sc2 : cw.sc3;
@@ -387,9 +400,9 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
             for (int blk = grp; blk < NBLK; blk += NGRP) {
                 const int slot = blk % NSLOT;
                 const uint32_t parity = (uint32_t)(blk / NSLOT) & 1u; // completion 2*layer + blk/NSLOT of this slot
-                const long long tw = (dbg && tid == 0) ? clock64() : 0;
+                const long long tw = (PMCTF_TC_TIMING && dbg && tid == 0) ? clock64() : 0;
                 ok = umma::mbar_wait(full0 + 8 * slot, parity);
-                if (dbg && tid == 0) dbg[12 + layer] += clock64() - tw;
+                if (PMCTF_TC_TIMING && dbg && tid == 0) dbg[12 + layer] += clock64() - tw;
                 if (!ok) break;
                 umma::fence_after_sync();
                 const int m = blk * 128 + quarter * 32 + lane;
@@ -576,7 +589,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     STAMP(6);
     ++tiles_done;
     } // tile loop
-    if (dbg_cta && tid == 0) { dbg_cta[14] = clock64() - t_cta0; dbg_cta[15] = tiles_done; }
+    if (PMCTF_TC_TIMING && dbg_cta && tid == 0) { dbg_cta[14] = clock64() - t_cta0; dbg_cta[15] = tiles_done; }
     umma::fence_before_sync();
     __syncthreads();
     if (warp == MMA_WARP) umma::tmem_dealloc(tbase, TMEM_COLS);

@@ -1,6 +1,11 @@
-"""Phase timing of the tensor-core lifting step (one CTA) on a 1080p luma plane."""
+"""Phase timing of the tensor-core lifting step (one CTA) on a 1080p luma plane.  Needs the timing variant of the library
+(clock64 stamps compiled in): build it in the build container first,
+    python -c "import learned_pmctf_b200 as P; P._native.build(True, defines=('PMCTF_TC_TIMING=1',), out=P._native.LIB_PATH.replace('.so', '_timing.so'))"
+"""
 import ctypes as C, sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["PMCTF_LIB"] = os.path.join(ROOT, "learned-pmctf_b200", "lib", "libpmctf_b200_timing.so")
 import torch
 import learned_pmctf_b200 as P
 m = P.pMCTF(num_me_stages=4).cuda().eval()
