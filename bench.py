@@ -170,7 +170,7 @@ def run_reference(args):
             "config": {"workload": "configs[2] hot path, bounded CPU sample per step", "sample": CPU_SAMPLE},
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cpu_cores(), "kind": "port", "sample": CPU_SAMPLE},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -278,18 +278,42 @@ def run_train(args, pkg, G, par, dev, rank, world):
         stock = {"ms_per_step_cudnn_tf32_graphed": res["tf32"][0], "ms_per_step_cudnn_fp32_graphed": res["fp32"][0],
                  "ms_per_step_cudnn_tf32_eager": res["tf32"][1], "ms_per_step_cudnn_fp32_eager": res["fp32"][1]}
     if rank == 0:
-        print(json.dumps({"metric": "pMCTF-L hot-path training clips/s (GOP-8 256x256 luma, batch 8)", "value": world * B / (ms * 1e-3),
+        emit({"metric": "pMCTF-L hot-path training clips/s (GOP-8 256x256 luma, batch 8)", "value": world * B / (ms * 1e-3),
                           "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms, "eager_ms_per_step": eager_ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "torch_gpu_baseline": stock,
                           "config": {"workload": "configs[4]: training step (forward + backward + grad clip + AdamW) on the hot path, batch 8 "
                                                  "x GOP-8 x 256x256, injected motion fields, un-fused fp32 training kernels, CUDA-graph replay",
-                                     "loss": loss}}), flush=True)
+                                     "loss": loss}})
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def quiet_stdout():
+    """Libraries chat on stdout (NCCL prints its version banner there when NCCL_DEBUG is set): point fd 1 at stderr for the
+    run and keep the original for emit(), so that stdout carries exactly one JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -461,7 +485,7 @@ def main():
             "kernel": "lift_step_tc_kernel<PLANE|WARP|SKIP3>: warp/skip + PredictUpdate CNN + lifting accumulate; conv2/conv3 as exact "
                       "int8 digit-split implicit GEMMs on tcgen05 (UTCIMMA, accumulators in TMEM), conv1/conv4/tanh on CUDA cores",
             "traffic": 35.5e6,
-            "traffic_note": "dram__bytes_read+write of ONE launch from ncu --set full (profiles/r1s_lift_step_tc_ncu.txt): the 1080p luma "
+            "traffic_note": "dram__bytes_read+write of ONE launch from ncu --set full (profiles/r1z_lift_step_tc_ncu.txt): the 1080p luma "
                             "temporal step, 2.21 Mpx, algorithmic 44.2 MB (20 B/px); outputs stay in the 126 MB L2, so DRAM traffic is "
                             "below the algorithmic bytes -- no wasted re-reads.  Not measured live.",
             "executed_int8_tops": ks["pixels"] * ops_per_px / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
@@ -469,7 +493,7 @@ def main():
             "note": "9 digit products per MAC (3 byte digits per operand) make the convolution exact, so executed tensor work is "
                     "~13.5x the algorithmic FLOPs; with N = 48 the MMA rate is set by the operand fetch from shared memory (~42 cycles per "
                     "128x48x32 MMA measured), and the kernel as a whole by the shared-memory data pipe, which the tensor-core operand "
-                    "fetch and the CUDA-core loads/stores share (~90 % busy, profiles/r1s_lift_step_tc_ncu.txt)"})
+                    "fetch and the CUDA-core loads/stores share (~90 % busy, profiles/r1z_lift_step_tc_ncu.txt)"})
     else:
         roofline.update({
             "kernel": "lift_step_kernel<PLANE|WARP|SKIP3> (warp/skip + PredictUpdate CNN + lifting accumulate, fp32 FFMA chains on CUDA cores)",
@@ -497,7 +521,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "torch_gpu_baseline": torch_gpu,
             "quality": {"mean_psnr_yuv_db": float(psnr[torch.isfinite(psnr)].mean()), "frames": int(psnr.numel())}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
