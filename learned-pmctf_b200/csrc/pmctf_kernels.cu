@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(NT, 1) lift_step_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
-// flow_warp (video_net.py:32-55): one thread per output pixel, all C channels
+// flow_warp (video_net.py:32-55): one thread per output pixel, all C channels (any W / alignment)
 __global__ void __launch_bounds__(256) flow_warp_kernel(const float *__restrict__ im, const float *__restrict__ flow,
                                                         const float *__restrict__ lin_x, const float *__restrict__ lin_y,
                                                         float *__restrict__ out, int N, int C, int H, int W, int flowN,
@@ -389,6 +389,46 @@ __global__ void __launch_bounds__(256) flow_warp_kernel(const float *__restrict_
     }
 }
 
+// the same with four pixels per thread, one in each of four consecutive rows: every load and store of a warp stays coalesced
+// (consecutive lanes = consecutive x) while the 8 motion-vector loads and then the 16 gathers of a thread are in flight together
+// (the one-pixel form is bound by memory latency); no index divisions
+__global__ void __launch_bounds__(128) flow_warp4_kernel(const float *__restrict__ im, const float *__restrict__ flow,
+                                                         const float *__restrict__ lin_x, const float *__restrict__ lin_y,
+                                                         float *__restrict__ out, int N, int C, int H, int W, int flowN,
+                                                         float sign, float sx, float sy, int round_out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = blockIdx.y * 4;
+    const int n = blockIdx.z;
+    if (x >= W) return;
+    const long long plane = (long long)H * W;
+    const float *fb = flow + (long long)(n / (N / flowN)) * 2 * plane + (long long)y0 * W + x;
+    const float lx = __ldg(lin_x + x);
+    float fx[4], fy[4], ly[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        fx[j] = fy[j] = ly[j] = 0.0f;
+        if (y0 + j < H) {
+            fx[j] = sign * __ldg(fb + (long long)j * W);
+            fy[j] = sign * __ldg(fb + plane + (long long)j * W);
+            ly[j] = __ldg(lin_y + y0 + j);
+        }
+    }
+    for (int c = 0; c < C; ++c) {
+        const float *ip = im + ((long long)n * C + c) * plane;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = (y0 + j < H) ? warp_sample(ip, W, 1, H, W, lx, ly[j], fx[j], fy[j], sx, sy) : 0.0f;
+            if (round_out) v[j] = rintf(v[j]);
+        }
+        float *op = out + ((long long)n * C + c) * plane + (long long)y0 * W + x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (y0 + j < H) op[(long long)j * W] = v[j];
+    }
+}
+
 __global__ void __launch_bounds__(256) chroma_mv_down_kernel(const float *__restrict__ mv, float *__restrict__ out,
                                                              int planes, int H, int W)
 {
@@ -403,49 +443,82 @@ __global__ void __launch_bounds__(256) chroma_mv_down_kernel(const float *__rest
     out[(long long)p * h2 * w2 + (long long)y * w2 + x] = v / 2.0f;
 }
 
-__global__ void __launch_bounds__(256) quantize_kernel(const float *__restrict__ s, float q, float clip, int lossy,
-                                                       int do_round, float *__restrict__ out, long long n)
+__device__ __forceinline__ float quant1(float v, float q, float clip, int lossy, int do_round)
 {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float v = lossy ? s[i] * q : s[i];
-        v = fminf(fmaxf(v, -clip), clip);
-        if (do_round) v = rintf(v);
-        out[i] = v;
+    v = lossy ? v * q : v;
+    v = fminf(fmaxf(v, -clip), clip);
+    return do_round ? rintf(v) : v;
+}
+
+// the element-wise kernels take a 128-bit path when the pointers are 16-byte aligned (vec = 1): n4 = n / 4 quads, then the tail
+__global__ void __launch_bounds__(256) quantize_kernel(const float *__restrict__ s, float q, float clip, int lossy,
+                                                       int do_round, float *__restrict__ out, long long n, int vec)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+    const long long n4 = vec ? n >> 2 : 0;
+    for (long long i = t; i < n4; i += nt) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(s) + i);
+        reinterpret_cast<float4 *>(out)[i] = make_float4(quant1(v.x, q, clip, lossy, do_round), quant1(v.y, q, clip, lossy, do_round),
+                                                         quant1(v.z, q, clip, lossy, do_round), quant1(v.w, q, clip, lossy, do_round));
     }
+    for (long long i = 4 * n4 + t; i < n; i += nt) out[i] = quant1(s[i], q, clip, lossy, do_round);
 }
 
 __global__ void __launch_bounds__(256) dequantize_kernel(const float *__restrict__ s, float q, int lossy,
-                                                         float *__restrict__ out, long long n)
+                                                         float *__restrict__ out, long long n, int vec)
 {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        out[i] = lossy ? s[i] / q : s[i];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+    const long long n4 = vec ? n >> 2 : 0;
+    for (long long i = t; i < n4; i += nt) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(s) + i);
+        reinterpret_cast<float4 *>(out)[i] = lossy ? make_float4(v.x / q, v.y / q, v.z / q, v.w / q) : v;
+    }
+    for (long long i = 4 * n4 + t; i < n; i += nt) out[i] = lossy ? s[i] / q : s[i];
 }
 
 // quantise with per-plane integer statistics of the symbols (sum |sym|, #nonzero): exact u64
 // arithmetic, so the rate statistics gathered across GPUs do not depend on reduction order.
 __global__ void __launch_bounds__(256) quantize_stats_kernel(const float *__restrict__ s, float q, float clip, int lossy,
                                                              float *__restrict__ out, long long plane_elems,
-                                                             unsigned long long *__restrict__ stats)
+                                                             unsigned long long *__restrict__ stats, int vec)
 {
     const int plane = blockIdx.y;
     const float *sp = s + (long long)plane * plane_elems;
     float *op = out + (long long)plane * plane_elems;
-    unsigned long long sum = 0, nnz = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < plane_elems; i += (long long)gridDim.x * blockDim.x) {
-        float v = lossy ? sp[i] * q : sp[i];
-        v = rintf(fminf(fmaxf(v, -clip), clip));
+    unsigned long long sum = 0;
+    unsigned int nnz = 0;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+    const long long n4 = vec ? plane_elems >> 2 : 0;
+    for (long long i = t; i < n4; i += nt) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(sp) + i);
+        const float4 r = make_float4(quant1(v.x, q, clip, lossy, 1), quant1(v.y, q, clip, lossy, 1), quant1(v.z, q, clip, lossy, 1),
+                                     quant1(v.w, q, clip, lossy, 1));
+        reinterpret_cast<float4 *>(op)[i] = r;
+        const unsigned int a0 = (unsigned int)fabsf(r.x), a1 = (unsigned int)fabsf(r.y), a2 = (unsigned int)fabsf(r.z), a3 = (unsigned int)fabsf(r.w);
+        sum += a0 + a1 + a2 + a3;
+        nnz += (a0 != 0) + (a1 != 0) + (a2 != 0) + (a3 != 0);
+    }
+    for (long long i = 4 * n4 + t; i < plane_elems; i += nt) {
+        const float v = quant1(sp[i], q, clip, lossy, 1);
         op[i] = v;
-        const long long iv = (long long)fabsf(v);
-        sum += (unsigned long long)iv;
+        const unsigned int iv = (unsigned int)fabsf(v);
+        sum += iv;
         nnz += iv != 0;
     }
+    unsigned long long s64 = sum, n64 = nnz;
     for (int o = 16; o > 0; o >>= 1) {
-        sum += __shfl_down_sync(0xffffffffu, sum, o);
-        nnz += __shfl_down_sync(0xffffffffu, nnz, o);
+        s64 += __shfl_down_sync(0xffffffffu, s64, o);
+        n64 += __shfl_down_sync(0xffffffffu, n64, o);
     }
-    if ((threadIdx.x & 31) == 0 && (sum | nnz)) {
-        atomicAdd(stats + 2 * plane, sum);
-        atomicAdd(stats + 2 * plane + 1, nnz);
+    __shared__ unsigned long long red[2][8];
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s64; red[1][threadIdx.x >> 5] = n64; }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // one pair of atomics per block
+        for (int w = 1; w < 8; ++w) { s64 += red[0][w]; n64 += red[1][w]; }
+        if (s64 | n64) {
+            atomicAdd(stats + 2 * plane, s64);
+            atomicAdd(stats + 2 * plane + 1, n64);
+        }
     }
 }
 
@@ -476,18 +549,37 @@ __global__ void __launch_bounds__(256) unpack_u8_kernel(const unsigned char *__r
 // sum over the un-padded area of (round(clamp(rec, 0, 255)) - orig)^2 per plane: the PSNR numerators of
 // test_pMCTF_flex.py:300-310, as exact integers
 __global__ void __launch_bounds__(256) frame_sse_kernel(const float *__restrict__ rec, const unsigned char *__restrict__ orig,
-                                                        int h0, int w0, int hp, int wp, unsigned long long *__restrict__ sse)
+                                                        int h0, int w0, int hp, int wp, unsigned long long *__restrict__ sse, int vec)
 {
-    const int y = blockIdx.y;
-    const long long n = blockIdx.z;
+    // a block walks rows blockIdx.x, blockIdx.x + gridDim.x, ... of plane blockIdx.y; one atomic per block
+    const long long n = blockIdx.y;
     unsigned long long acc = 0;
-    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w0; x += gridDim.x * blockDim.x) {
-        float r = rintf(fminf(fmaxf(rec[(n * hp + y) * (long long)wp + x], 0.0f), 255.0f));
-        const int d = (int)r - (int)orig[(n * h0 + y) * (long long)w0 + x];
-        acc += (unsigned long long)(d * d);
+    for (int y = blockIdx.x; y < h0; y += gridDim.x) {
+        const float *rp = rec + (n * hp + y) * (long long)wp;
+        const unsigned char *op = orig + (n * h0 + y) * (long long)w0;
+        unsigned int row = 0;   // <= 255^2 * (w0 / threads + 4) per thread
+        const int w4 = vec ? w0 >> 2 : 0;
+        for (int i = threadIdx.x; i < w4; i += blockDim.x) {
+            const float4 r = __ldg(reinterpret_cast<const float4 *>(rp) + i);
+            const uchar4 o = __ldg(reinterpret_cast<const uchar4 *>(op) + i);
+            const int d0 = (int)rintf(fminf(fmaxf(r.x, 0.0f), 255.0f)) - (int)o.x, d1 = (int)rintf(fminf(fmaxf(r.y, 0.0f), 255.0f)) - (int)o.y;
+            const int d2 = (int)rintf(fminf(fmaxf(r.z, 0.0f), 255.0f)) - (int)o.z, d3 = (int)rintf(fminf(fmaxf(r.w, 0.0f), 255.0f)) - (int)o.w;
+            row += (unsigned int)(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
+        }
+        for (int x = 4 * w4 + threadIdx.x; x < w0; x += blockDim.x) {
+            const int d = (int)rintf(fminf(fmaxf(rp[x], 0.0f), 255.0f)) - (int)op[x];
+            row += (unsigned int)(d * d);
+        }
+        acc += row;
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sse + n, acc);
+    __shared__ unsigned long long red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) acc += red[w];
+        if (acc) atomicAdd(sse + n, acc);
+    }
 }
 
 
@@ -727,10 +819,14 @@ int pmctf_flow_warp(const float *im, const float *flow, const float *lin_x, cons
 {
     if (!im || !flow || !lin_x || !lin_y || !out || N <= 0 || C <= 0) return PMCTF_EINVAL;
     if (H < 2 || W < 2 || flowN < 1 || (N % flowN) || H > 65535 || N > 65535) return PMCTF_ESHAPE;
-    dim3 grid((W + 255) / 256, H, N);
-    flow_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(im, flow, lin_x, lin_y, out, N, C, H, W, flowN, sign,
-                                                            (float)(((double)W - 1.0) / 2.0),
-                                                            (float)(((double)H - 1.0) / 2.0), round_out);
+    const float sx = (float)(((double)W - 1.0) / 2.0), sy = (float)(((double)H - 1.0) / 2.0);
+    if (H >= 8 && (H + 3) / 4 <= 65535) {
+        flow_warp4_kernel<<<dim3((W + 127) / 128, (H + 3) / 4, N), 128, 0, (cudaStream_t)stream>>>(im, flow, lin_x, lin_y, out, N, C, H, W,
+                                                                                                 flowN, sign, sx, sy, round_out);
+    } else {
+        flow_warp_kernel<<<dim3((W + 255) / 256, H, N), 256, 0, (cudaStream_t)stream>>>(im, flow, lin_x, lin_y, out, N, C, H, W, flowN, sign,
+                                                                                     sx, sy, round_out);
+    }
     return PMCTF_LAUNCHED();
 }
 
@@ -978,9 +1074,10 @@ int pmctf_quantize(const float *s, float q, float clip, int lossy, int do_round,
 {
     if (n == 0) return 0;
     if (!s || !out || n < 0) return PMCTF_EINVAL;
-    long long blocks = (n + 255) / 256;
+    const int vec = ((((uintptr_t)s | (uintptr_t)out) & 15) == 0);
+    long long blocks = ((vec ? n / 4 + 3 : n) + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    quantize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s, q, clip, lossy, do_round, out, n);
+    quantize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s, q, clip, lossy, do_round, out, n, vec);
     return PMCTF_LAUNCHED();
 }
 
@@ -988,9 +1085,10 @@ int pmctf_dequantize(const float *s_hat, float q, int lossy, float *out, long lo
 {
     if (n == 0) return 0;
     if (!s_hat || !out || n < 0) return PMCTF_EINVAL;
-    long long blocks = (n + 255) / 256;
+    const int vec = ((((uintptr_t)s_hat | (uintptr_t)out) & 15) == 0);
+    long long blocks = ((vec ? n / 4 + 3 : n) + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    dequantize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s_hat, q, lossy, out, n);
+    dequantize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s_hat, q, lossy, out, n, vec);
     return PMCTF_LAUNCHED();
 }
 
@@ -999,10 +1097,11 @@ int pmctf_quantize_stats(const float *s, float q, float clip, int lossy, float *
 {
     if (planes == 0 || plane_elems == 0) return 0;
     if (!s || !out || !stats || planes < 0 || plane_elems < 0 || planes > 65535) return PMCTF_EINVAL;
-    long long bx = (plane_elems + 255) / 256;
+    const int vec = ((((uintptr_t)s | (uintptr_t)out) & 15) == 0) && (plane_elems % 4 == 0 || planes == 1);
+    long long bx = ((vec ? plane_elems / 4 + 3 : plane_elems) + 255) / 256;
     const long long cap = (148 * 16 + planes - 1) / planes;
     if (bx > cap) bx = cap;
-    quantize_stats_kernel<<<dim3((unsigned)bx, planes), 256, 0, (cudaStream_t)stream>>>(s, q, clip, lossy, out, plane_elems, stats);
+    quantize_stats_kernel<<<dim3((unsigned)bx, planes), 256, 0, (cudaStream_t)stream>>>(s, q, clip, lossy, out, plane_elems, stats, vec);
     return PMCTF_LAUNCHED();
 }
 
@@ -1021,7 +1120,10 @@ int pmctf_frame_sse(const float *rec, const unsigned char *orig, int n, int h0, 
     if (n == 0) return 0;
     if (!rec || !orig || !sse || n < 0 || h0 <= 0 || w0 <= 0) return PMCTF_EINVAL;
     if (hp < h0 || wp < w0 || h0 > 65535 || n > 65535) return PMCTF_ESHAPE;
-    frame_sse_kernel<<<dim3((w0 + 255) / 256, h0, n), 256, 0, (cudaStream_t)stream>>>(rec, orig, h0, w0, hp, wp, sse);
+    int bx = (148 * 8 + n - 1) / n;   // about eight blocks per SM over all planes
+    if (bx > h0) bx = h0;
+    const int vec = (w0 % 4 == 0) && (wp % 4 == 0) && ((((uintptr_t)rec) & 15) == 0) && ((((uintptr_t)orig) & 3) == 0);
+    frame_sse_kernel<<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>(rec, orig, h0, w0, hp, wp, sse, vec);
     return PMCTF_LAUNCHED();
 }
 
