@@ -12,7 +12,8 @@ namespace pmctf {
 // deterministic tanh (arithmetic contract: table include/pmctf_tanh_table.h, routine specified in
 // tools/gen_tanh_table.py, restated independently in oracle/pmctf_oracle.c): second-order expansion around the
 // nearest multiple of 1/128, derivatives from T = tanh(node); one 4-byte shared-memory lookup per evaluation
-__device__ const unsigned int g_tanh_bits[PMCTF_TANH_ENTRIES] = {PMCTF_TANH_TABLE_VALUES};
+constexpr int TANH_BULK_BYTES = ((PMCTF_TANH_ENTRIES * 4 + 15) / 16) * 16;   // the table as one 16-byte-granular bulk copy
+__device__ __align__(16) const unsigned int g_tanh_bits[TANH_BULK_BYTES / 4] = {PMCTF_TANH_TABLE_VALUES};
 constexpr int TANH_SMEM_BYTES = ((PMCTF_TANH_ENTRIES * 4 + 127) / 128) * 128;
 
 __device__ __forceinline__ void load_tanh_table(float *tab_smem, int tid, int nthreads)

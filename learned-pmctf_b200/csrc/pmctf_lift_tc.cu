@@ -206,16 +206,19 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
 
     // ---- setup: parameters, barriers, TMEM ------------------------------------------------------------
     {
-        const int4 *g = reinterpret_cast<const int4 *>(a.pu_packed + Q_OFF);
-        int4 *d = reinterpret_cast<int4 *>(smem + SM_WB);
-        for (int i = tid; i < 2 * QIMG / 16; i += NT) d[i] = __ldg(g + (i / (QIMG / 16)) * (QBYTES / 16) + i % (QIMG / 16));
-        load_tanh_table(ttab, tid, NT);
         if (tid == 0) {
             for (int i = 0; i < NSLOT; ++i) {
                 umma::mbar_init(umma::smem_u32(bars + i), 1);
                 umma::mbar_init(umma::smem_u32(bars + NSLOT + i), 128);
             }
+            const uint32_t wbar = umma::smem_u32(bars + 2 * NSLOT);
+            umma::mbar_init(wbar, 1);
             umma::fence_mbar_init();
+            // the two operand images and the tanh table arrive by TMA bulk copies (one thread, no register staging)
+            umma::mbar_expect_tx(wbar, 2 * QIMG + TANH_BULK_BYTES);
+            umma::bulk_g2s(umma::smem_u32(smem + SM_WB), a.pu_packed + Q_OFF, QIMG, wbar);
+            umma::bulk_g2s(umma::smem_u32(smem + SM_WB + QIMG), a.pu_packed + Q_OFF + QBYTES / 4, QIMG, wbar);
+            umma::bulk_g2s(umma::smem_u32(ttab), g_tanh_bits, TANH_BULK_BYTES, wbar);
         }
         if (warp == MMA_WARP) umma::tmem_alloc(tmem_slot, TMEM_COLS);
     }
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     umma::fence_after_sync();
     const uint32_t tbase = *tmem_slot;
     const uint32_t full0 = umma::smem_u32(bars), empty0 = umma::smem_u32(bars + NSLOT);
-    bool ok = true;
+    bool ok = umma::mbar_wait(umma::smem_u32(bars + 2 * NSLOT), 0u);   // weights + tanh table have landed
     if (warp < 4) {   // accumulator groups 3 and 4 of every slot start at zero (later each epilogue re-zeroes the slot it drained)
 #pragma unroll
         for (int sl = 0; sl < NSLOT; ++sl) {
@@ -240,8 +243,9 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
 
     // ---- persistent loop over tiles: every accumulator slot completes exactly twice per layer, so the mbarrier
     //      parities are the same for every tile ------------------------------------------------------------------
+    if (!ok && err) atomicExch(err, 1);   // the bulk copies never completed: report, process nothing
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int tile = ok ? (int)blockIdx.x : n_tiles; tile < n_tiles; tile += gridDim.x) {
     const int n = tile / (tiles_x * tiles_y);
     const int trem = tile - n * (tiles_x * tiles_y);
     const int ty = trem / tiles_x;

@@ -107,6 +107,19 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar_saddr, uint32_t count)
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// TMA bulk copy (1-D, no tensor map): global -> shared, completion counted in bytes on an mbarrier.  dst / src 16-byte aligned,
+// bytes a multiple of 16.  Issued by one thread after mbar_expect_tx() announced the total.
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar_saddr, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void *src_global, uint32_t bytes, uint32_t mbar_saddr)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_saddr),
+                 "l"(__cvta_generic_to_global(src_global)), "r"(bytes), "r"(mbar_saddr)
+                 : "memory");
+}
+
 // bounded wait (never hangs the GPU: returns false when the phase did not complete in time)
 __device__ __forceinline__ bool mbar_wait(uint32_t mbar_saddr, uint32_t parity, int max_tries = 1 << 22)
 {
