@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     umma::fence_after_sync();
     const uint32_t tbase = *tmem_slot;
     const uint32_t full0 = umma::smem_u32(bars), empty0 = umma::smem_u32(bars + NSLOT);
-    bool ok = umma::mbar_wait(umma::smem_u32(bars + 2 * NSLOT), 0u);   // weights + tanh table have landed
+    bool ok = true;
+    bool staged = false;   // weights + tanh table have landed (waited for after the first tile's source load)
     if (warp < 4) {   // accumulator groups 3 and 4 of every slot start at zero (later each epilogue re-zeroes the slot it drained)
 #pragma unroll
         for (int sl = 0; sl < NSLOT; ++sl) {
@@ -243,9 +244,8 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
 
     // ---- persistent loop over tiles: every accumulator slot completes exactly twice per layer, so the mbarrier
     //      parities are the same for every tile ------------------------------------------------------------------
-    if (!ok && err) atomicExch(err, 1);   // the bulk copies never completed: report, process nothing
 #pragma unroll 1
-    for (int tile = ok ? (int)blockIdx.x : n_tiles; tile < n_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int n = tile / (tiles_x * tiles_y);
     const int trem = tile - n * (tiles_x * tiles_y);
     const int ty = trem / tiles_x;
@@ -333,6 +333,15 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
             ss[r * S_P + c] = v;
         }
         __syncthreads();
+    }
+
+    if (!staged) {   // first tile of this CTA: the TMA bulk copies of the setup ran under the source load
+        ok = umma::mbar_wait(umma::smem_u32(bars + 2 * NSLOT), 0u);
+        staged = true;
+        if (!ok) {
+            if (err) atomicExch(err, 1);
+            break;
+        }
     }
 
     // ---- conv1 (1 -> 16) + tanh -> digits of A1 (origin (-3,-3), pitch 38) -------------------------------
