@@ -84,7 +84,7 @@ constexpr int SM_TANH = SM_C1 + 4 * C1Q_BYTES;
 constexpr int SM_BAR = SM_TANH + TANH_SMEM_BYTES;
 constexpr int SMEM_BYTES = SM_BAR + 128;
 static_assert(SM_S % 128 == 0 && SM_T % 128 == 0 && SM_A1 % 128 == 0 && SM_C1 % 128 == 0 && SM_TANH % 128 == 0 && SM_BAR % 128 == 0, "alignment");
-static_assert(C1Q_BYTES % 128 == 32 && C1Q_BYTES >= A3_R * C1_P * 16 && TH * O_P * 4 <= C1Q_BYTES, "conv1 stash planes");
+static_assert(C1Q_BYTES % 128 == 32 && C1Q_BYTES >= A3_R * C1_P * 16, "conv1 stash planes");
 static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 
 constexpr int MMA_WARP = 4 * NGRP;
@@ -179,7 +179,6 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     float *stile = reinterpret_cast<float *>(smem + SM_T);
     uint8_t *A1 = smem + SM_A1;                 // digit planes of tanh(conv1), then (in place) tanh(conv2), then the conv4 partials
     uint8_t *c1q = smem + SM_C1;                // conv1 pre-activations of the (TH+2) x (TW+2) region, one float4 plane per channel quarter
-    float *so = reinterpret_cast<float *>(smem + SM_C1); // conv4 output of the tile (after the stash is consumed)
     float *ttab = reinterpret_cast<float *>(smem + SM_TANH);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);      // full[NSLOT], empty[NSLOT]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_BAR + 96);
@@ -540,20 +539,6 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
         }
     }
 
-    // ---- conv4 (16 -> 1): out = ((b4 + T_0) + T_1) + ... + T_8 over the 3x3 neighbourhood of partials -> so -----------
-    for (int i = tid; i < TH * TW; i += NT) {
-        const int r = i / TW, c = i - r * TW;
-        float acc = cw.b4;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const int m = (r + k / 3) * P + c + (k % 3);   // conv3 pixel index (origin (-1,-1)) of the neighbour
-            acc = acc + *reinterpret_cast<const float *>(A1 + (k >> 2) * PLANE + (m >> 7) * 2048 + (k & 3) * 512 + (m & 127) * 4);
-        }
-        so[r * O_P + c] = acc;
-    }
-    __syncthreads();
-    STAMP(5);
-
     // ---- lifting arithmetic + stores -----------------------------------------------------------------------
     {
         const bool xfast = xfast_out;
@@ -571,7 +556,16 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
             else { c = i / TH; r = i - c * TH; }
             const int gy = y0 + r, gx = x0 + c;
             if (gy >= H || gx >= W) continue;
-            const float pu = so[r * O_P + c];
+            // conv4 (16 -> 1): out = ((b4 + T_0) + T_1) + ... + T_8 over the 3x3 neighbourhood of partials
+            float tk[9];
+#pragma unroll
+            for (int k9 = 0; k9 < 9; ++k9) {
+                const int m = (r + k9 / 3) * P + c + (k9 % 3);   // conv3 pixel index (origin (-1,-1)) of the neighbour
+                tk[k9] = *reinterpret_cast<const float *>(A1 + (k9 >> 2) * PLANE + (m >> 7) * 2048 + (k9 & 3) * 512 + (m & 127) * 4);
+            }
+            float pu = cw.b4;
+#pragma unroll
+            for (int k9 = 0; k9 < 9; ++k9) pu = pu + tk[k9];
             float res;
             if (a.mode == PMCTF_MODE_PU) {
                 res = pu;
