@@ -288,6 +288,14 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
         constexpr int NIT = (S_ROWS * S_COLS + NT - 1) / NT;
         float fx[NIT], fy[NIT], lx[NIT], ly[NIT];
         bool in[NIT];
+        // everything that does not depend on the sample is resolved once per tile (the field of this plane, strides, scales)
+        const int mv_w = a.mv_w, mv_down = a.mv_down;
+        const long long mv_plane = (long long)a.mv_h * mv_w;
+        const float *mvb = a.mv + (long long)(n / a.mv_share) * 2 * mv_plane;   // mv_share consecutive planes use one field
+        const float msign = a.mv_sign, sx = a.sx, sy = a.sy;
+        const float *linx = a.lin_x, *liny = a.lin_y;
+        const long long srs = a.src.rs, scs = a.src.cs;
+        const int round_src = a.round_src;
 #pragma unroll
         for (int k = 0; k < NIT; ++k) {   // motion vectors and grid tables of all items first ...
             const int i = tid + k * NT;
@@ -296,9 +304,22 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
             in[k] = i < S_ROWS * S_COLS && gy >= 0 && gy < H && gx >= 0 && gx < W;
             fx[k] = fy[k] = lx[k] = ly[k] = 0.0f;
             if (in[k]) {
-                load_mv(a.mv, a.mv_share, a.mv_down, a.mv_h, a.mv_w, n, gy, gx, a.mv_sign, fx[k], fy[k]);
-                lx[k] = __ldg(a.lin_x + gx);
-                ly[k] = __ldg(a.lin_y + gy);
+                if (!mv_down) {
+                    const float *q = mvb + (long long)gy * mv_w + gx;
+                    fx[k] = msign * __ldg(q);
+                    fy[k] = msign * __ldg(q + mv_plane);
+                } else {   // bilineardownsacling(mv) / 2 fused (video_net.py:66-71), op for op as load_mv()
+                    const float *q = mvb + (long long)(2 * gy) * mv_w + 2 * gx;
+                    float2 r0 = __ldg(reinterpret_cast<const float2 *>(q));
+                    float2 r1 = __ldg(reinterpret_cast<const float2 *>(q + mv_w));
+                    fx[k] = msign * ((((r0.x * 0.25f + r0.y * 0.25f) + r1.x * 0.25f) + r1.y * 0.25f) / 2.0f);
+                    q += mv_plane;
+                    r0 = __ldg(reinterpret_cast<const float2 *>(q));
+                    r1 = __ldg(reinterpret_cast<const float2 *>(q + mv_w));
+                    fy[k] = msign * ((((r0.x * 0.25f + r0.y * 0.25f) + r1.x * 0.25f) + r1.y * 0.25f) / 2.0f);
+                }
+                lx[k] = __ldg(linx + gx);
+                ly[k] = __ldg(liny + gy);
             }
         }
 #pragma unroll
@@ -307,8 +328,8 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
             const int r = i / S_COLS, c = i - r * S_COLS;
             float v = 0.0f;
             if (in[k]) {
-                v = warp_sample(sp, a.src.rs, a.src.cs, H, W, lx[k], ly[k], fx[k], fy[k], a.sx, a.sy);
-                if (a.round_src) v = rintf(v);
+                v = warp_sample(sp, srs, scs, H, W, lx[k], ly[k], fx[k], fy[k], sx, sy);
+                if (round_src) v = rintf(v);
             }
             if (i < S_ROWS * S_COLS) ss[r * S_P + c] = v;
         }
