@@ -271,6 +271,20 @@ def test_quantize_dequantize_vs_oracle(P):
             assert_bitexact(npy(P.ops.quantize(cu(s), q, 8192.0, True, do_round)), orc.quantize(s, q, 8192.0, True, do_round), "quantize")
         assert_bitexact(npy(P.ops.dequantize(cu(s), q)), orc.dequantize(s, q), "dequantize")
     assert npy(P.ops.quantize(cu(np.zeros((0,), np.float32)), 1.0)).size == 0  # empty input
+    # the 128-bit fast paths need 16-byte aligned pointers: odd offsets and odd sizes take the scalar path / the tail loop
+    big = cu(rnd((1, 1, 41, 67), 52, -9000, 9000))
+    for off, n in ((0, 2747), (1, 2744), (3, 2001), (4, 5), (2, 3)):
+        v = big.view(-1)[off:off + n]
+        assert_bitexact(npy(P.ops.quantize(v, 0.37)), orc.quantize(npy(v), 0.37), f"quantize off {off} n {n}")
+        assert_bitexact(npy(P.ops.dequantize(v, 0.37)), orc.dequantize(npy(v), 0.37), f"dequantize off {off} n {n}")
+    for shape, off in (((3, 1, 9, 7), 0), ((2, 1, 8, 8), 1), ((1, 1, 5, 3), 2)):   # plane sizes not divisible by 4, unaligned base
+        n = int(np.prod(shape))
+        v = big.view(-1)[off:off + n].view(shape)
+        st = torch.zeros((shape[0], 2), dtype=torch.int64, device="cuda")
+        want = orc.quantize(npy(v), 0.21)
+        assert_bitexact(npy(P.ops.quantize_stats(v, 0.21, st)), want, f"quantize_stats {shape} off {off}")
+        a = np.abs(want.reshape(shape[0], -1)).astype(np.int64)
+        assert st.cpu().tolist() == np.stack([a.sum(1), (a != 0).sum(1)], 1).tolist()
 
 
 # ---- error behaviour ----------------------------------------------------------------------------
@@ -293,6 +307,14 @@ def test_errors(P, model):
         assert model.temporal_filtering[0].predict_filter(xg).grad_fn is not None
     s = P._native.Step()
     assert P._native.lib().pmctf_lift_step(s, None) == -1  # EINVAL, nothing launched
+    # tensor mode takes the small fp32 parameters from the host registry pmctf_pack_pu_weights() fills: a device-side COPY of a
+    # packed block is not a registered block and is rejected instead of running with somebody else's weights
+    if P.ops.get_conv_mode() == "tensor":
+        pu = model.temporal_filtering[0].P_t
+        x = torch.zeros(1, 1, 16, 32, device="cuda")
+        P.ops.predict_update(x, pu.packed())
+        with pytest.raises(RuntimeError, match="predict_update"):
+            P.ops.predict_update(x, pu.packed().clone())
 
 
 # ---- BASELINE.json full sizes: size-independent properties --------------------------------------
