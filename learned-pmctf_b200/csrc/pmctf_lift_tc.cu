@@ -2,14 +2,16 @@
 //
 // Same step as lift_step_kernel (pmctf_kernels.cu): {plane | flow warp | 3-tap skip} -> PredictUpdate CNN ->
 // lifting accumulate, one HBM pass.  conv1 (1->16, K = 9) and conv4 (16->1) stay fp32 FMA chains on the CUDA
-// cores; conv2 and conv3 (94 % of the FLOPs) are implicit GEMMs on tcgen05 in EXACT integer arithmetic:
+// cores (weights and biases as kernel arguments = constant-bank operands); conv2 and conv3 (94 % of the FLOPs) are
+// implicit GEMMs on tcgen05 in EXACT integer arithmetic:
 //
 //   * their inputs are tanh outputs in [-1, 1]: V = rint(a * 2^22) is split into its two's complement bytes
 //     V = d0*2^16 + u1*2^8 + u2 (d0 signed, u1/u2 unsigned: s8 and u8 MMA operands); the weights W = rint(w * 2^Sw)
 //     into three signed-byte digits e0*2^16 + e1*2^8 + e2 (Sw per layer);
 //   * a pixel's 16 channels of one digit are one 16-byte record of a K-major, un-swizzled UMMA operand, the
 //     tile is a linear pixel array with pitch 38, so a filter tap is only a different descriptor start
-//     address and two taps form the K = 32 of one kind::i8 MMA (leading byte offset = tap distance);
+//     address and two taps form the K = 32 of one kind::i8 MMA (leading byte offset = tap distance); 14 MMAs per
+//     128-pixel block (issue_block below);
 //   * digit products of equal weight share a TMEM accumulator group: 5 groups x 16 columns of s32 per
 //     128-pixel block hold o_k = sum_{i+j=k} d_i e_j, every |o_k| < 2^24, and
 //     S = sum_k o_k 2^(32-8k) = sum A*W exactly -- independent of the tensor core's summation order;
@@ -24,8 +26,10 @@
 // through full/empty mbarriers.  One set of digit planes serves both layers: the conv2 epilogue writes tanh(conv2)
 // over the tanh(conv1) records of its own (finished) block, and the conv3 epilogue writes the conv4 partials over
 // them again; conv1's pre-activation outputs (the residual) are kept in shared memory instead of being recomputed.
-// Two CTAs are resident per SM (112 KB shared memory, 256 TMEM columns each), so the CUDA-core phases of one tile
-// overlap the tensor-core phases of the other.
+// The operand images and the tanh table reach shared memory by TMA bulk copies.  Two CTAs are resident per SM (112 KB
+// shared memory, 256 TMEM columns each), so the CUDA-core phases of one tile overlap the tensor-core phases of the
+// other.  What bounds the kernel is the shared-memory data pipe, which the tensor cores' operand fetch and the CUDA
+// cores' loads/stores share.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -41,7 +45,7 @@
 #define PMCTF_TC_TIMING 0   // 1: clock64 stamps of the phases of one CTA (pmctf_tc_debug_times, scratch/tc_phases.py); profiling builds only
 #endif
 #ifndef PMCTF_WHATIF
-#define PMCTF_WHATIF 0   // timing experiments only (bit 0: no conv1 residual recompute, bit 1: no tanh table lookup, bit 2: no MMAs)
+#define PMCTF_WHATIF 0   // timing experiments only (bit 1: no tanh table lookup, bit 2: no MMAs)
 #endif
 
 namespace pmctf {
@@ -56,9 +60,8 @@ constexpr int S_ROWS = TH + 8, S_COLS = TW + 8, S_P = 41;
 constexpr int T_ROWS = TH + 10, T_P = 41;
 constexpr int A1_R = TH + 6, A1_C = TW + 6;          // tanh(conv1): origin (-3,-3)
 constexpr int A2_R = TH + 4, A2_C = TW + 4;          // tanh(conv2): origin (-2,-2)
-constexpr int A3_R = TH + 2, A3_C = TW + 2, A3_P = 36; // conv1 + conv3: origin (-1,-1); pitch of the conv1 stash
-constexpr int O_P = 33;
-constexpr int C1_P = A3_C;                            // pitch of the conv1 stash
+constexpr int A3_R = TH + 2, A3_C = TW + 2;          // conv1 + conv3 (conv4's input region): origin (-1,-1)
+constexpr int C1_P = A3_C;                           // pitch of the conv1 stash
 constexpr int C1Q_BYTES = ((A3_R * C1_P * 16 - 32 + 127) / 128) * 128 + 32; // one float4 plane per channel quarter; +32: the four
                                                                         // quarters of two pixels hit eight different bank groups
 constexpr int NSLOT = 3, SLOT_COLS = 80, TMEM_COLS = 256;
@@ -79,7 +82,7 @@ constexpr int SM_WB = 0;                              // 2 x 9728 B operand imag
 constexpr int SM_S = SM_WB + 2 * QIMG;
 constexpr int SM_T = SM_S + ((S_ROWS * S_P * 4 + 127) / 128) * 128;
 constexpr int SM_A1 = SM_T + ((T_ROWS * T_P * 4 + 127) / 128) * 128;
-constexpr int SM_C1 = SM_A1 + 3 * PLANE;              // conv1 stash (4 quarter planes); the conv4 sums of the tile alias it later
+constexpr int SM_C1 = SM_A1 + 3 * PLANE;              // conv1 stash (4 quarter planes)
 constexpr int SM_TANH = SM_C1 + 4 * C1Q_BYTES;
 constexpr int SM_BAR = SM_TANH + TANH_SMEM_BYTES;
 constexpr int SMEM_BYTES = SM_BAR + 128;
@@ -103,14 +106,6 @@ struct TcW {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr)
-                 : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
