@@ -251,7 +251,52 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     STAMP(0);
 
     // ---- source tile ------------------------------------------------------------------------------------
-    if (SRC == PMCTF_SRC_PLANE || SRC == PMCTF_SRC_SKIP3) {
+    bool skip_done = false;
+    if (SRC == PMCTF_SRC_SKIP3 && xfast_src) {
+        // row-major source view: one thread per (column, 4-row segment) loads the six raw rows it needs straight from global
+        // memory (lanes = columns, coalesced) and applies the reflect-padded 3-tap skip filter from registers -- the same
+        // values and the same fma chains as the generic path below, a tenth of its instructions, one barrier less
+        constexpr int SEG = 4, NSEG = S_ROWS / SEG;
+        static_assert(S_ROWS % SEG == 0 && NSEG * S_COLS <= NT && T_ROWS == S_ROWS + 2, "segment mapping");
+        if (tid < NSEG * S_COLS) {
+            const int seg = tid / S_COLS, c = tid - seg * S_COLS;
+            const int gx = x0 - 4 + c;
+            const bool colin = gx >= 0 && gx < W;
+            const float *sp = a.src.p + plane_off(a.src, n) + (long long)gx * a.src.cs;
+            const float d1 = a.src_div1, d2 = a.src_div2;
+            const bool dodiv = (d1 != 1.0f) || (d2 != 1.0f);
+            float raw[SEG + 2];
+#pragma unroll
+            for (int j = 0; j < SEG + 2; ++j) {
+                const int gyr = y0 - 5 + seg * SEG + j;
+                raw[j] = 0.0f;
+                if (colin && gyr >= 0 && gyr < H) raw[j] = __ldg(sp + (long long)gyr * a.src.rs);
+            }
+#pragma unroll
+            for (int j = 0; j < SEG + 2; ++j) {
+                if (dodiv) raw[j] = (raw[j] / d1) / d2;
+                // raw rows for the aux output of the final phase: every row of the tile is stored by exactly one segment
+                if ((j >= 1 && j <= SEG) || (j == 0 && seg == 0) || (j == SEG + 1 && seg == NSEG - 1))
+                    stile[(seg * SEG + j) * T_P + c] = raw[j];
+            }
+            const float t0 = a.tap0, t1 = a.tap1, t2 = a.tap2, tb = a.tap_bias;
+#pragma unroll
+            for (int q = 0; q < SEG; ++q) {
+                const int r = seg * SEG + q, gy = y0 - 4 + r;
+                float v = 0.0f;
+                if (colin && gy >= 0 && gy < H) {
+                    const float vm = (gy == 0) ? raw[q + 2] : raw[q];          // row-reflect padding (lifting_1d.py:91): row -1 -> row 1
+                    const float vp = (gy == H - 1) ? raw[q] : raw[q + 2];      // row H -> row H-2
+                    v = tb;
+                    v = fmaf(t0, vm, v);
+                    v = fmaf(t1, raw[q + 1], v);
+                    v = fmaf(t2, vp, v);
+                }
+                ss[r * S_P + c] = v;
+            }
+        }
+        skip_done = true;
+    } else if (SRC == PMCTF_SRC_PLANE || SRC == PMCTF_SRC_SKIP3) {
         constexpr int ROWS = (SRC == PMCTF_SRC_SKIP3) ? T_ROWS : S_ROWS;
         constexpr int ROFF = (SRC == PMCTF_SRC_SKIP3) ? 5 : 4;
         float *dst = (SRC == PMCTF_SRC_SKIP3) ? stile : ss;
@@ -331,7 +376,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     }
     __syncthreads();
     STAMP(1);
-    if (SRC == PMCTF_SRC_SKIP3) {
+    if (SRC == PMCTF_SRC_SKIP3 && !skip_done) {
         for (int i = tid; i < S_ROWS * S_COLS; i += NT) {
             const int r = i / S_COLS, c = i - r * S_COLS;
             const int gy = y0 - 4 + r, gx = x0 - 4 + c;
