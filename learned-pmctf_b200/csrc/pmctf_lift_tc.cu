@@ -251,7 +251,6 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     STAMP(0);
 
     // ---- source tile ------------------------------------------------------------------------------------
-    bool skip_done = false;
     if (SRC == PMCTF_SRC_SKIP3 && xfast_src) {
         // row-major source view: one thread per (column, 4-row segment) loads the six raw rows it needs straight from global
         // memory (lanes = columns, coalesced) and applies the reflect-padded 3-tap skip filter from registers -- the same
@@ -295,11 +294,50 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                 ss[r * S_P + c] = v;
             }
         }
-        skip_done = true;
-    } else if (SRC == PMCTF_SRC_PLANE || SRC == PMCTF_SRC_SKIP3) {
-        constexpr int ROWS = (SRC == PMCTF_SRC_SKIP3) ? T_ROWS : S_ROWS;
-        constexpr int ROFF = (SRC == PMCTF_SRC_SKIP3) ? 5 : 4;
-        float *dst = (SRC == PMCTF_SRC_SKIP3) ? stile : ss;
+    } else if (SRC == PMCTF_SRC_SKIP3) {
+        // transposed source view (column pass: memory runs along the view's rows): lanes = the 26 raw rows of the tile, a warp
+        // walks columns; the filter's row neighbours come from the neighbouring lanes by shuffle
+        constexpr int NW = NT / 32, NCOL = (S_COLS + NW - 1) / NW;
+        static_assert(T_ROWS <= 32, "one lane per raw row");
+        const int t = lane, gyr = y0 - 5 + t;
+        const bool rowin = t < T_ROWS && gyr >= 0 && gyr < H;
+        const float *sp = a.src.p + plane_off(a.src, n) + (long long)gyr * a.src.rs;
+        const long long scs = a.src.cs;
+        const float d1 = a.src_div1, d2 = a.src_div2;
+        const bool dodiv = (d1 != 1.0f) || (d2 != 1.0f);
+        const float t0 = a.tap0, t1 = a.tap1, t2 = a.tap2, tb = a.tap_bias;
+        float v[NCOL];
+#pragma unroll
+        for (int k = 0; k < NCOL; ++k) {
+            const int c = warp + k * NW, gx = x0 - 4 + c;
+            v[k] = 0.0f;
+            if (rowin && c < S_COLS && gx >= 0 && gx < W) v[k] = __ldg(sp + (long long)gx * scs);
+        }
+#pragma unroll
+        for (int k = 0; k < NCOL; ++k) {
+            const int c = warp + k * NW, gx = x0 - 4 + c;
+            if (c < S_COLS) {   // warp-uniform
+                if (dodiv) v[k] = (v[k] / d1) / d2;
+                if (t < T_ROWS) stile[t * T_P + c] = v[k];
+                const float up = __shfl_up_sync(0xffffffffu, v[k], 1);     // raw row t - 1
+                const float dn = __shfl_down_sync(0xffffffffu, v[k], 1);   // raw row t + 1
+                if (t >= 1 && t <= S_ROWS) {   // this lane's raw row is the centre of output row t - 1
+                    float o = 0.0f;
+                    if (gyr >= 0 && gyr < H && gx >= 0 && gx < W) {
+                        const float vm = (gyr == 0) ? dn : up;          // row-reflect padding (lifting_1d.py:91)
+                        const float vp = (gyr == H - 1) ? up : dn;
+                        o = tb;
+                        o = fmaf(t0, vm, o);
+                        o = fmaf(t1, v[k], o);
+                        o = fmaf(t2, vp, o);
+                    }
+                    ss[(t - 1) * S_P + c] = o;
+                }
+            }
+        }
+    } else if (SRC == PMCTF_SRC_PLANE) {
+        constexpr int ROWS = S_ROWS, ROFF = 4;
+        float *dst = ss;
         const float *sp = a.src.p + plane_off(a.src, n);
         const bool dodiv = (a.src_div1 != 1.0f) || (a.src_div2 != 1.0f);
         constexpr int NIT = (ROWS * S_COLS + NT - 1) / NT;   // fixed trip count: all loads of a thread are in flight together
@@ -376,25 +414,6 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     }
     __syncthreads();
     STAMP(1);
-    if (SRC == PMCTF_SRC_SKIP3 && !skip_done) {
-        for (int i = tid; i < S_ROWS * S_COLS; i += NT) {
-            const int r = i / S_COLS, c = i - r * S_COLS;
-            const int gy = y0 - 4 + r, gx = x0 - 4 + c;
-            float v = 0.0f;
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                const int ym = (gy == 0) ? 1 : gy - 1;
-                const int yp = (gy == H - 1) ? H - 2 : gy + 1;
-                const int base = y0 - 5;
-                v = a.tap_bias;
-                v = fmaf(a.tap0, stile[(ym - base) * T_P + c], v);
-                v = fmaf(a.tap1, stile[(gy - base) * T_P + c], v);
-                v = fmaf(a.tap2, stile[(yp - base) * T_P + c], v);
-            }
-            ss[r * S_P + c] = v;
-        }
-        __syncthreads();
-    }
-
     if (!staged) {   // first tile of this CTA: the TMA bulk copies of the setup ran under the source load
         ok = umma::mbar_wait(umma::smem_u32(bars + 2 * NSLOT), 0u);
         staged = true;
