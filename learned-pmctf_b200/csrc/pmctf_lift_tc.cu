@@ -95,7 +95,7 @@ constexpr int NT = 32 * (MMA_WARP + 1);   // 8 epilogue warps + 1 MMA warp
 
 // The small fp32 parameters travel as kernel arguments: warp-uniform constant-bank operands cost no shared-memory
 // bandwidth (the bound of this kernel).  Filled on the host from the copy pmctf_pack_pu_weights() registers.
-struct TcW {
+struct alignas(16) TcW {
     float w1[144];     // conv1 [k][co]
     float b1[16], b2[16], b3[16];
     float w4[16][8];   // conv4 taps 0..7 per input channel
@@ -451,8 +451,9 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     float2 a01 = make_float2(cw.b1[q * 4], cw.b1[q * 4 + 1]), a23 = make_float2(cw.b1[q * 4 + 2], cw.b1[q * 4 + 3]);
 #pragma unroll
                     for (int k = 0; k < 9; ++k) {
-                        a01 = ffma2(make_float2(cw.w1[k * 16 + q * 4], cw.w1[k * 16 + q * 4 + 1]), v[k], a01);
-                        a23 = ffma2(make_float2(cw.w1[k * 16 + q * 4 + 2], cw.w1[k * 16 + q * 4 + 3]), v[k], a23);
+                        const float4 wk = *reinterpret_cast<const float4 *>(&cw.w1[k * 16 + q * 4]);   // one 128-bit constant load
+                        a01 = ffma2(make_float2(wk.x, wk.y), v[k], a01);
+                        a23 = ffma2(make_float2(wk.z, wk.w), v[k], a23);
                     }
                     if (stash)
                         *reinterpret_cast<float4 *>(c1q + q * C1Q_BYTES + ((r - 2) * C1_P + (c - 2)) * 16) = make_float4(a01.x, a01.y, a23.x, a23.y);
@@ -573,9 +574,10 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                             const float v = fmaf(combine(o[q & 1][0][j], o[q & 1][1][j], o[q & 1][2][j], o[q & 1][3][j], o[q & 1][4][j]), scale, bq[j]);
                             const float a3v = valid ? (c1[j] + v) : 0.0f;   // zero padding of conv4's input outside the image
                             // conv4 partials of this pixel: T_k += w4[ci][k] * a3[ci], ci ascending (taps pairwise on the fp32x2 pipe)
-                            const float *wc = cw.w4[4 * q + j];
-                            tp[0] = ffma2(make_float2(wc[0], wc[1]), a3v, tp[0]); tp[1] = ffma2(make_float2(wc[2], wc[3]), a3v, tp[1]);
-                            tp[2] = ffma2(make_float2(wc[4], wc[5]), a3v, tp[2]); tp[3] = ffma2(make_float2(wc[6], wc[7]), a3v, tp[3]);
+                            const float4 wa = *reinterpret_cast<const float4 *>(&cw.w4[4 * q + j][0]);
+                            const float4 wb = *reinterpret_cast<const float4 *>(&cw.w4[4 * q + j][4]);
+                            tp[0] = ffma2(make_float2(wa.x, wa.y), a3v, tp[0]); tp[1] = ffma2(make_float2(wa.z, wa.w), a3v, tp[1]);
+                            tp[2] = ffma2(make_float2(wb.x, wb.y), a3v, tp[2]); tp[3] = ffma2(make_float2(wb.z, wb.w), a3v, tp[3]);
                             t8 = fmaf(cw.w48[4 * q + j], a3v, t8);
                         }
                     }
