@@ -661,17 +661,26 @@ int launch_step_tc(const StepD &d, int src_kind, int *err_flag, cudaStream_t st)
 int register_packed_weights(const float *packed, cudaStream_t st);                 // pmctf_lift_tc.cu
 
 static int g_conv_mode = PMCTF_CONV_TENSOR;
-static int *g_tc_err = nullptr; // device flag set by a tensor-core kernel whose MMA never completed
+static int *g_tc_err_of[64] = {nullptr}; // per device: flag set by a tensor-core kernel whose MMA never completed (+ timing stamps)
+
+static int *tc_err_buffer(bool create)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!g_tc_err_of[dev] && create) {
+        // [0] error flag, [2..33] phase stamps of the timing build
+        if (cudaMalloc(&g_tc_err_of[dev], 2048) != cudaSuccess) return nullptr;
+        cudaMemset(g_tc_err_of[dev], 0, 2048);
+    }
+    return g_tc_err_of[dev];
+}
 
 static int launch_step(const StepD &d, int src_kind, cudaStream_t st)
 {
     if (g_conv_mode == PMCTF_CONV_TENSOR) {
-        if (!g_tc_err) {
-            // [0] error flag, [2..33] phase stamps, [64..319] per-SM arrival counters of the tensor-core kernel
-            if (cudaMalloc(&g_tc_err, 2048) != cudaSuccess) return (int)cudaGetLastError();
-            cudaMemset(g_tc_err, 0, 2048);
-        }
-        const int e = launch_step_tc(d, src_kind, g_tc_err, st);
+        int *err = tc_err_buffer(true);
+        if (!err) return (int)cudaGetLastError();
+        const int e = launch_step_tc(d, src_kind, err, st);
         if (e == 0) ++g_launches;
         return e;
     }
@@ -778,16 +787,18 @@ int pmctf_tc_debug_times(long long *out16)
 {
     if (!out16) return PMCTF_EINVAL;
     for (int i = 0; i < 16; ++i) out16[i] = 0;
-    if (!pmctf::g_tc_err) return 0;
-    if (cudaMemcpy(out16, pmctf::g_tc_err + 2, 16 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return (int)cudaGetLastError();
-    cudaMemset(pmctf::g_tc_err + 2, 0, 16 * sizeof(long long));
+    int *err = pmctf::tc_err_buffer(false);
+    if (!err) return 0;
+    if (cudaMemcpy(out16, err + 2, 16 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return (int)cudaGetLastError();
+    cudaMemset(err + 2, 0, 16 * sizeof(long long));
     return 0;
 }
 
 int pmctf_tc_error_flag(void)
 {
     int v = 0;
-    if (pmctf::g_tc_err && cudaMemcpy(&v, pmctf::g_tc_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    int *err = pmctf::tc_err_buffer(false);
+    if (err && cudaMemcpy(&v, err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return v;
 }
 

@@ -778,8 +778,12 @@ int register_packed_weights(const float *packed, cudaStream_t st)
 // called by launch_step() in pmctf_kernels.cu
 int launch_step_tc(const StepD &d, int src_kind, int *err_flag, cudaStream_t st)
 {
-    static bool configured = false;
-    if (!configured) {
+    // per-device one-time setup: the dynamic shared-memory limit of the three instantiations, and the resident-CTA count
+    static int resident_of[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
+    if (dev < 0 || dev >= 64) return PMCTF_EINVAL;
+    if (!resident_of[dev]) {
         cudaError_t e;
         e = cudaFuncSetAttribute(tc::lift_step_tc_kernel<PMCTF_SRC_PLANE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
@@ -787,14 +791,11 @@ int launch_step_tc(const StepD &d, int src_kind, int *err_flag, cudaStream_t st)
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(tc::lift_step_tc_kernel<PMCTF_SRC_SKIP3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return (int)cudaGetLastError();
+        resident_of[dev] = 2 * sms;   // CTAs that fit the device at two per SM
     }
-    static int resident = 0; // CTAs that fit the device at two per SM
-    if (!resident) {
-        int dev = 0, sms = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return (int)cudaGetLastError();
-        resident = 2 * sms;
-    }
+    const int resident = resident_of[dev];
     tc::TcW w;
     {
         std::lock_guard<std::mutex> lk(g_w_mutex);
