@@ -108,6 +108,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
@@ -513,27 +521,28 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     const int gy = y0 - 2 + r, gx = x0 - 2 + c;
                     const bool valid = r < A2_R && c < A2_C && gy >= 0 && gy < H && gx >= 0 && gx < W;
                     uint32_t w[3][4];
-                    uint32_t o[2][5][4];   // four channels at a time, the next quad's TMEM loads in flight behind the arithmetic
+                    uint32_t o[5][8];   // eight channels per round of TMEM loads (measured: better here than four with the next
+                                        // quad in flight, which is what the conv3 epilogue below does -- there it is the other way round)
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) tmem_ld4(taddr + 16 * k, o[0][k]);
+                    for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                        for (int k = 0; k < 5; ++k) tmem_ld8(taddr + 16 * k + 8 * h, o[k]);
                         umma::tmem_ld_wait();
-                        if (q < 3) {
 #pragma unroll
-                            for (int k = 0; k < 5; ++k) tmem_ld4(taddr + 16 * k + 4 * (q + 1), o[(q + 1) & 1][k]);
-                        }
-                        uint32_t w0 = 0, w1 = 0, w2 = 0;
-                        if (valid) {
-                            const float bq[4] = {cw.b2[4 * q], cw.b2[4 * q + 1], cw.b2[4 * q + 2], cw.b2[4 * q + 3]};
-                            float u[4];
+                        for (int jq = 0; jq < 2; ++jq) {
+                            const int q = 2 * h + jq;
+                            uint32_t w0 = 0, w1 = 0, w2 = 0;
+                            if (valid) {
+                                const float bq[4] = {cw.b2[4 * q], cw.b2[4 * q + 1], cw.b2[4 * q + 2], cw.b2[4 * q + 3]};
+                                float u[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                u[j] = fmaf(combine(o[q & 1][0][j], o[q & 1][1][j], o[q & 1][2][j], o[q & 1][3][j], o[q & 1][4][j]), scale, bq[j]);
-                            const float2 t01 = tanh_det2(make_float2(u[0], u[1]), ttab), t23 = tanh_det2(make_float2(u[2], u[3]), ttab);
-                            push_digits4(t01, t23, w0, w1, w2);
+                                for (int j = 0; j < 4; ++j)
+                                    u[j] = fmaf(combine(o[0][4 * jq + j], o[1][4 * jq + j], o[2][4 * jq + j], o[3][4 * jq + j], o[4][4 * jq + j]), scale, bq[j]);
+                                const float2 t01 = tanh_det2(make_float2(u[0], u[1]), ttab), t23 = tanh_det2(make_float2(u[2], u[3]), ttab);
+                                push_digits4(t01, t23, w0, w1, w2);
+                            }
+                            w[0][q] = w0; w[1][q] = w1; w[2][q] = w2;
                         }
-                        w[0][q] = w0; w[1][q] = w1; w[2][q] = w2;
                     }
                     umma::tmem_zero16(taddr + 48);   // groups 3, 4 are accumulate-only for the MMAs: hand the slot back zeroed
                     umma::tmem_zero16(taddr + 64);
