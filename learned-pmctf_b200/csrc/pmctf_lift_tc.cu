@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float v = fmaf(combine(o[q & 1][0][j], o[q & 1][1][j], o[q & 1][2][j], o[q & 1][3][j], o[q & 1][4][j]), scale, bq[j]);
-                            const float a3v = valid ? (c1[j] + v) : 0.0f;   // zero padding of conv4's input outside the image
+                            const float a3v = c1[j] + v;
                             // conv4 partials of this pixel: T_k += w4[ci][k] * a3[ci], ci ascending (taps pairwise on the fp32x2 pipe)
                             const float4 wa = *reinterpret_cast<const float4 *>(&cw.w4[4 * q + j][0]);
                             const float4 wb = *reinterpret_cast<const float4 *>(&cw.w4[4 * q + j][4]);
@@ -601,6 +601,10 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     float *d = reinterpret_cast<float *>(A1 + blk * 2048) + (m & 127);
                     constexpr int PW = PLANE / 4;
                     if (warp_has_work) {
+                    if (!valid) {   // zero padding of conv4's input outside the image (and the junk columns): no contribution
+                        tp[0] = tp[1] = tp[2] = tp[3] = make_float2(0.0f, 0.0f);
+                        t8 = 0.0f;
+                    }
                     d[0] = tp[0].x; d[128] = tp[0].y; d[256] = tp[1].x; d[384] = tp[1].y;
                     d[PW] = tp[2].x; d[PW + 128] = tp[2].y; d[PW + 256] = tp[3].x; d[PW + 384] = tp[3].y;
                     d[2 * PW] = t8;
