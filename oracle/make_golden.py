@@ -40,9 +40,9 @@ def is_hot(k):
         or k.endswith(".QP") or k.endswith(".QP_ll")
 
 
-def build_model():
+def build_model(lossy=True):
     torch.manual_seed(0)
-    m = pMCTF(num_me_stages=4).eval()
+    m = pMCTF(lossy=lossy, num_me_stages=4).eval()
     g = torch.Generator().manual_seed(1234)
     bior = [-1.586134342059924, -0.052980118572961, 0.882911075530934, 0.443506852043971]
     with torch.no_grad():
@@ -197,5 +197,52 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+@torch.no_grad()
+def main_lossless():
+    """tests/golden/lossless.npz: the lossless variant of the path (pMCTF(lossy=False): the warp output, 0.1 * PU and every
+    lifting update are rounded, no subband scaling -- lifting_1d.py:110-148, wavelet_transform_temporal_mctf.py:30-43,
+    pMCTF_L.py:302-326).  Integer frames in, integer subbands out, perfect reconstruction.  The model's own hot-path weights
+    are stored in the file (prefix `w.`): the lossless model is a separate construction."""
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    m = build_model(lossy=False)
+    c = {"w." + k: npy(v) for k, v in m.state_dict().items() if is_hot(k)}
+    meta = f"torch {torch.__version__}; cpu capability {torch.backends.cpu.get_cpu_capability()}; threads 8"
+    H, W = 64, 96
+    fr = frames(2, H, W, 71)
+    ch = frames(4, H // 2, W // 2, 72)
+    mvh = flows(1, H, W, 73)
+    c["lin_x"], c["lin_y"] = npy(torch.linspace(-1.0, 1.0, W)), npy(torch.linspace(-1.0, 1.0, H))
+    c["lin_xc"], c["lin_yc"] = npy(torch.linspace(-1.0, 1.0, W // 2)), npy(torch.linspace(-1.0, 1.0, H // 2))
+    c["ref"], c["cur"], c["ref_c"], c["cur_c"], c["mv"] = npy(fr[0:1]), npy(fr[1:2]), npy(ch[0:2]), npy(ch[2:4]), npy(mvh)
+    for s in (0, 2):
+        L, Hh, pred, inv = m.forward_MCTF(fr[0:1], fr[1:2], mvh, stage_idx=s)
+        c[f"s{s}.L"], c[f"s{s}.H"], c[f"s{s}.pred"], c[f"s{s}.inv"] = npy(L), npy(Hh), npy(pred), npy(inv)
+        r, cu = m.inverse_MCTF(L, Hh, mvh, stage_idx=s)
+        c[f"s{s}.ref_rec"], c[f"s{s}.cur_rec"] = npy(r), npy(cu)
+        mvc = bilineardownsacling(mvh) / 2
+        Lc, Hc, _, _ = m.forward_MCTF(ch[0:2], ch[2:4], mvc, stage_idx=s)
+        c[f"s{s}.Lc"], c[f"s{s}.Hc"] = npy(Lc), npy(Hc)
+    coder = m.lp_coder
+    lift = coder.wavelet_transform
+    x = frames(2, 32, 48, 74) - 60.0
+    l, h = lift.lift_h.forward_lift(x)
+    c["x1d"], c["l1d"], c["h1d"] = npy(x), npy(l), npy(h)
+    c["x1d_rec"] = npy(lift.lift_h.backward_lift(l, h))
+    x = frames(1, 64, 96, 75)
+    c["x"] = npy(x)
+    y = coder.encode(x)
+    for lvl in range(4):
+        for k in ("ll", "lh", "hl", "hh"):
+            c[f"enc.{lvl}.{k}"] = npy(y[lvl][k].contiguous())
+    c["dec"] = npy(coder.decode({lvl: dict(y[lvl]) for lvl in range(4)}))
+    np.savez_compressed(os.path.join(OUT, "lossless.npz"), meta=meta, **c)
+    print("lossless.npz", os.path.getsize(os.path.join(OUT, "lossless.npz")),
+          "perfect reconstruction in the reference:", bool((c["dec"] == c["x"]).all()), bool((c["s0.ref_rec"] == c["ref"]).all()))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "lossless":
+        main_lossless()
+    else:
+        main()
