@@ -127,3 +127,27 @@ def test_cuda_lossless_perfect_reconstruction_1080p(model):
         assert torch.equal(coder.decode({lvl: dict(y[lvl]) for lvl in range(4)}), x)
     r, c = model.inverse_MCTF(L, Hh, mv, stage_idx=1)
     assert torch.equal(r, ref) and torch.equal(c, cur)
+
+
+@pytest.mark.gpu
+def test_cuda_lossless_gop_is_exact(model):
+    """A whole GOP through the batched pipeline in lossless mode: no quantisation step is applied (pWave.py:184-202 with
+    lossy=False), the symbols ARE the integer subbands, and the reconstruction equals the input frames exactly."""
+    import learned_pmctf_b200 as P
+    from learned_pmctf_b200 import gop as Gm
+    gop, h0, w0 = 8, 128, 192
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    y_u8 = torch.randint(0, 256, (gop, h0, w0), device="cuda", generator=gen, dtype=torch.uint8)
+    c_u8 = torch.randint(0, 256, (gop, 2, h0 // 2, w0 // 2), device="cuda", generator=gen, dtype=torch.uint8)
+    Y = P.ops.unpack_u8(y_u8, h0, w0)
+    C = P.ops.unpack_u8(c_u8.view(-1, h0 // 2, w0 // 2), h0 // 2, w0 // 2).view(gop, 2, 1, h0 // 2, w0 // 2)
+    mvs, n = [], gop
+    while n > 1:
+        n //= 2
+        mvs.append(torch.randn(n, 2, h0, w0, device="cuda", generator=gen) * 2.5)
+    codec = Gm.GopCodec(model, gop, q_index=12)
+    rec_y, rec_c, st = codec.code_gop(Y, C, mvs, y_u8, c_u8)
+    assert torch.equal(rec_y, Y) and torch.equal(rec_c, C)
+    assert float(st[:, 3:6].abs().max()) == 0.0          # zero squared error on every plane
+    s = P.ops.quantize(Y, 0.37, lossy=False)              # lossless quantise / dequantise leave integers alone
+    assert torch.equal(s, Y) and torch.equal(P.ops.dequantize(s, 0.37, lossy=False), Y)
