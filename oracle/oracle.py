@@ -94,7 +94,7 @@ class PU:
 class IWave:
     """iWave1D parameters (lifting_1d.py:52-101)."""
 
-    def __init__(self, sd, prefix="", lossy=True):
+    def __init__(self, sd, prefix="", lossy=True, dynamic_range=256.0):
         self.pus = [PU(sd, f"{prefix}{n}.") for n in ("P_1", "U_1", "P_2", "U_2")]
         c = _IWave()
         for i, n in enumerate(("conv_P1", "conv_U1", "conv_P2", "conv_U2")):
@@ -103,7 +103,7 @@ class IWave:
                 c.tap[i][j] = float(w[j])
             c.bias[i] = float(_a(sd[f"{prefix}{n}.bias"]).reshape(1)[0])
             c.pu[i] = self.pus[i].c
-        c.scale_l, c.scale_h, c.dynamic_range, c.lossy = SCALE_L, SCALE_H, 256.0, int(lossy)
+        c.scale_l, c.scale_h, c.dynamic_range, c.lossy = SCALE_L, SCALE_H, float(dynamic_range), int(lossy)  # 2 ** bitdepth, lifting_1d.py:62
         self.c = c
         self.lossy = lossy
 

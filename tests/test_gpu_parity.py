@@ -287,6 +287,31 @@ def test_quantize_dequantize_vs_oracle(P):
         assert st.cpu().tolist() == np.stack([a.sum(1), (a != 0).sum(1)], 1).tolist()
 
 
+@pytest.mark.parametrize("bitdepth,levels", [(8, 2), (10, 3), (8, 1)])
+def test_pwave_other_depths_and_levels(P, bitdepth, levels):
+    """Constructor arguments the reference exposes but its scripts never vary: decomp_levels (pWave.py:36,139-157) and bitdepth
+    (dynamic_range = 2 ** bitdepth of the lifting steps, lifting_1d.py:62,108)."""
+    torch.manual_seed(7)
+    coder = P.pWave(bitdepth=bitdepth, decomp_levels=levels, lossy=True).cuda().eval()
+    with torch.no_grad():
+        for p in coder.wavelet_transform.parameters():
+            if p.dim() == 4 and p.shape[-1] == 3:
+                p.normal_(0, 0.08)
+            elif p.dim() == 1:
+                p.normal_(0, 0.05)
+    sd = {k: v.detach().cpu().numpy() for k, v in coder.state_dict().items()}
+    w = orc.IWave(sub_sd(sd, "wavelet_transform.lift_h."), dynamic_range=float(2 ** bitdepth))
+    x = rnd((2, 1, 48, 80), 71, 0, 2 ** bitdepth - 1)
+    y = orc.pwave_encode(x, w, levels=levels)
+    enc = coder.encode_bands(cu(x))
+    assert sorted(enc) == list(range(levels))
+    for lvl in range(levels):
+        for b in ("ll", "lh", "hl", "hh"):
+            assert_bitexact(npy(enc[lvl][b]), y[lvl][b], f"bitdepth {bitdepth} levels {levels}: {lvl}.{b}")
+    dec = coder.decode({lvl: dict(enc[lvl]) for lvl in range(levels)})
+    assert_bitexact(npy(dec), orc.pwave_decode({lvl: dict(y[lvl]) for lvl in range(levels)}, w, levels=levels), "decode")
+
+
 # ---- error behaviour ----------------------------------------------------------------------------
 def test_errors(P, model):
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
