@@ -119,6 +119,8 @@ def oracle_gop2(threads=None):
         pu(f"iw.{n}.")
     iw = orc.IWave(w, "iw.")
     hp, wp = 1152, 1920
+    if os.environ.get("PMCTF_BENCH_REF_HW"):   # tests only: a smaller sample so that the JSON contract can be checked in seconds
+        hp, wp = (int(v) for v in os.environ["PMCTF_BENCH_REF_HW"].split("x"))
     y = np.round(g.random((2, 1, hp, wp)) * 255).astype(np.float32)
     c = np.round(g.random((2, 2, 1, hp // 2, wp // 2)) * 255).astype(np.float32)
     mv = g.normal(0, 3, (1, 2, hp, wp)).astype(np.float32)
