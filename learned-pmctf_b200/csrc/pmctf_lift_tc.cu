@@ -809,6 +809,7 @@ int launch_step_tc(const StepD &d, int src_kind, int *err_flag, cudaStream_t st)
         resident_of[dev] = 2 * sms;   // CTAs that fit the device at two per SM
     }
     const int resident = resident_of[dev];
+    if (((uintptr_t)d.pu_packed & 15) != 0) return PMCTF_EINVAL;   // the operand images are fetched by 16-byte-granular TMA bulk copies
     tc::TcW w;
     {
         std::lock_guard<std::mutex> lk(g_w_mutex);
