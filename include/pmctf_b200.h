@@ -131,7 +131,8 @@ int pmctf_tc_debug_times(long long *out16);
 int pmctf_tc_mma_probe(int variant, int reps, long long *out3_device, void *stream);
 
 /* Repack one PredictUpdate's 8 tensors (OIHW, as in the state_dict) into the kernel layout.
- * Replaces nothing in the reference; run once per weight version.  The call also reads the packed block back once
+ * Replaces nothing in the reference; run once per weight version.  `packed` holds PMCTF_PU_PACKED_FLOATS floats and must be
+ * 16-byte aligned.  The call also reads the packed block back once
  * (40 KB, synchronises `stream`) and registers its small fp32 parameters (conv1, conv4, biases) under the address of
  * `packed`: the tensor-core step kernel takes them as kernel arguments.  A step launched with a `pu_packed` block that
  * did not come from this call (e.g. a device-side copy of one) is rejected with PMCTF_EINVAL in tensor mode. */

@@ -817,6 +817,7 @@ int pmctf_pack_pu_weights(const float *w1, const float *b1, const float *w2, con
                           const float *b3, const float *w4, const float *b4, float *packed, void *stream)
 {
     if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !w4 || !b4 || !packed) return PMCTF_EINVAL;
+    if (((uintptr_t)packed & 15) != 0) return PMCTF_EINVAL;   // the tensor-core kernel fetches the operand images by TMA bulk copies
     pack_pu_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(w1, b1, w2, b2, w3, b3, w4, b4, packed);
     const int e = PMCTF_LAUNCHED();
     if (e) return e;
