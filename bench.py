@@ -478,6 +478,8 @@ def main():
                 "timed_in": "a single-stream pass of the same K steps right after the timed region (there the luma and chroma chains "
                             "overlap on two streams, which fills the tail of every persistent launch; per-launch event brackets "
                             "would overlap)", "single_stream_ms_per_step": ms_step_serial,
+                "step_level_tflops_two_streams": flops / K / (ms_step * 1e-3) / 1e12,
+                "step_level_frac_two_streams": flops / K / (ms_step * 1e-3) / 1e12 / pk["tf_sustained"],
                 "achieved_definition": "sum over timed launches of (pixels through PredictUpdate x 9792 FLOP) / sum of CUDA-event time "
                                        "around those launches (events on the launching stream inside the timed region)"}
     if mode == "tensor":
