@@ -29,20 +29,25 @@
 extern "C" {
 #endif
 
-#define PMCTF_ABI_VERSION 1
+#define PMCTF_ABI_VERSION 2
 
 #define PMCTF_EINVAL (-1)   /* null pointer / non-positive size / unsupported flag */
 #define PMCTF_ESHAPE (-2)   /* shape not supported (odd split size, plane too small for reflection) */
 #define PMCTF_EWORKSPACE (-3) /* workspace too small */
+#define PMCTF_ETIMEOUT (-4) /* an earlier tensor-core launch on this device gave up waiting for its MMAs; nothing was launched */
 
 #define PMCTF_PU_PACKED_FLOATS 10128 /* size of one packed PredictUpdate weight block (fp32 taps + int8 tensor-core operands) */
 
 /* How the two 16->16 convolutions of PredictUpdate (lifting_1d.py:40-44) are evaluated (DESIGN.md "Numerics"):
  *   PMCTF_CONV_TENSOR  exact fixed-point implicit GEMM on the tcgen05 tensor cores (default)
  *   PMCTF_CONV_FFMA    sequential fp32 FMA chains on the CUDA cores
- * Each mode is bit-exact against the oracle run in the same mode. */
-#define PMCTF_CONV_FFMA 0
-#define PMCTF_CONV_TENSOR 1
+ * Each mode is bit-exact against the oracle run in the same mode.
+ * Every descriptor that reaches a PredictUpdate (pmctf_step_t, pmctf_iwave_t, pmctf_temporal_t) carries a conv_mode
+ * field: PMCTF_CONV_DEFAULT (= 0, what a zeroed struct holds) follows the process-wide default set by
+ * pmctf_set_conv_mode(); the other two values select the arithmetic for that call only. */
+#define PMCTF_CONV_DEFAULT 0
+#define PMCTF_CONV_FFMA 1
+#define PMCTF_CONV_TENSOR 2
 #define PMCTF_IWAVE_PACKED_FLOATS (4 * PMCTF_PU_PACKED_FLOATS)
 
 /* A strided view of a batch of single-channel planes (strides in elements).  Element (n, y, x)
@@ -93,6 +98,7 @@ typedef struct {
     float base_div1, base_div2, sign, final_mul;
     pmctf_plane_t out, pred, aux;
     float aux_mul;
+    int conv_mode;        /* PMCTF_CONV_* for this call (0 = process default) */
 } pmctf_step_t;
 
 /* iWave1D parameters (lifting_1d.py:52-101) */
@@ -103,6 +109,7 @@ typedef struct {
     float scale_l, scale_h; /* lifting_1d.py:98-101 */
     float dynamic_range;    /* 256: lifting_1d.py:62 */
     int lossy;
+    int conv_mode;          /* PMCTF_CONV_* for calls with this descriptor (0 = process default) */
 } pmctf_iwave_t;
 
 /* TemporalLifting parameters (wavelet_transform_temporal_mctf.py:11-25) */
@@ -110,17 +117,25 @@ typedef struct {
     const float *P_t_packed, *U_t_packed;
     float scale_p, scale_u; /* 1/sqrt(2), 0.5 */
     int lossy;
+    int conv_mode;          /* PMCTF_CONV_* for calls with this descriptor (0 = process default) */
 } pmctf_temporal_t;
 
 int pmctf_abi_version(void);
 const char *pmctf_error_string(int code);
 /* Number of CUDA kernels launched by this library so far in this process (instrumentation for bench.py). */
 unsigned long long pmctf_launch_count(void);
-/* Process-wide selection of the convolution arithmetic (see PMCTF_CONV_*); returns 0 or PMCTF_EINVAL. */
+/* Process-wide DEFAULT of the convolution arithmetic (PMCTF_CONV_FFMA or PMCTF_CONV_TENSOR; used by descriptors whose
+ * conv_mode is PMCTF_CONV_DEFAULT); returns 0 or PMCTF_EINVAL.  Atomic; the per-descriptor field is the re-entrant way. */
 int pmctf_set_conv_mode(int mode);
 int pmctf_get_conv_mode(void);
-/* Non-zero if a tensor-core kernel gave up waiting for an MMA (synchronises the device; for tests). */
+/* Tensor-core watchdog.  Every mbarrier wait inside the tensor-core step kernel is bounded; a kernel that gives up sets an
+ * error word in mapped pinned host memory (per device) and ALL its CTAs leave together.  From then on every call that would
+ * launch a tensor-core step on that device -- and pmctf_pack_pu_weights -- returns PMCTF_ETIMEOUT without launching, until
+ * pmctf_tc_clear_error().  pmctf_tc_error_flag() reads the word of the current device (no copy, no synchronisation: call it
+ * after synchronising the streams whose kernels should be covered); pmctf_tc_inject_timeout() sets it (tests). */
 int pmctf_tc_error_flag(void);
+int pmctf_tc_clear_error(void);
+int pmctf_tc_inject_timeout(void);
 /* clock64 stamps of the phases of one CTA of the most recent tensor-core launches (profiling aid; synchronises):
  * [0..6] start, source ready, conv1 done, conv2 done, conv3 done, conv4 done, end; [8..11] MMA issue begin/end of
  * conv2, conv3; [12..13] cycles an epilogue warp waited for accumulators. */
@@ -139,6 +154,9 @@ int pmctf_tc_mma_probe(int variant, int reps, long long *out3_device, void *stre
 int pmctf_pack_pu_weights(const float *w1, const float *b1, const float *w2, const float *b2,
                           const float *w3, const float *b3, const float *w4, const float *b4,
                           float *packed, void *stream);
+/* Forget the parameters registered for `packed` (call before freeing or reusing the block's memory): a later launch that names
+ * the address without a fresh pmctf_pack_pu_weights() is rejected with PMCTF_EINVAL instead of running with stale values. */
+int pmctf_release_pu_weights(const float *packed);
 
 /* flow_warp(im, flow): pMCTF/layers/video/video_net.py:32-55.
  * im [N,C,H,W], flow [flowN,2,H,W] in pixels (flowN divides N), out [N,C,H,W]. */
@@ -154,7 +172,7 @@ int pmctf_lift_step(const pmctf_step_t *step, void *stream);
 
 /* PredictUpdate.forward: lifting_1d.py:36-49.  x, out dense [N,1,H,W]. */
 int pmctf_predict_update(const float *x, const float *pu_packed, float in_mul, float *out,
-                         int N, int H, int W, void *stream);
+                         int N, int H, int W, int conv_mode, void *stream);
 
 /* TemporalLifting.predict_filter / update_filter: wavelet_transform_temporal_mctf.py:27-45
  * (which = 0 predict, 1 update). */

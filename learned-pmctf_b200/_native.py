@@ -17,7 +17,8 @@ HEADERS = [os.path.join(_HERE, "csrc", "pmctf_umma.cuh"), os.path.join(_HERE, "c
 INCLUDE = os.path.join(ROOT, "include")
 
 PU_PACKED_FLOATS = 10128
-CONV_FFMA, CONV_TENSOR = 0, 1
+CONV_DEFAULT, CONV_FFMA, CONV_TENSOR = 0, 1, 2
+E_TIMEOUT = -4
 SRC_PLANE, SRC_WARP, SRC_SKIP3 = 0, 1, 2
 MODE_ACCUM, MODE_FILTER, MODE_PU = 0, 1, 2
 
@@ -38,12 +39,12 @@ class Step(C.Structure):
                 ("tap0", _f), ("tap1", _f), ("tap2", _f), ("tap_bias", _f),
                 ("pu_packed", _fp), ("in_mul", _f), ("post_mul", _f), ("out_mul", _f), ("round_tmp", C.c_int),
                 ("base", Plane), ("base_div1", _f), ("base_div2", _f), ("sign", _f), ("final_mul", _f),
-                ("out", Plane), ("pred", Plane), ("aux", Plane), ("aux_mul", _f)]
+                ("out", Plane), ("pred", Plane), ("aux", Plane), ("aux_mul", _f), ("conv_mode", C.c_int)]
 
 
 class IWave(C.Structure):
     _fields_ = [("tap", (_f * 3) * 4), ("bias", _f * 4), ("pu_packed", _fp), ("scale_l", _f), ("scale_h", _f),
-                ("dynamic_range", _f), ("lossy", C.c_int)]
+                ("dynamic_range", _f), ("lossy", C.c_int), ("conv_mode", C.c_int)]
 
 
 class UmmaOp(C.Structure):
@@ -51,7 +52,8 @@ class UmmaOp(C.Structure):
 
 
 class Temporal(C.Structure):
-    _fields_ = [("P_t_packed", _fp), ("U_t_packed", _fp), ("scale_p", _f), ("scale_u", _f), ("lossy", C.c_int)]
+    _fields_ = [("P_t_packed", _fp), ("U_t_packed", _fp), ("scale_p", _f), ("scale_u", _f), ("lossy", C.c_int),
+                ("conv_mode", C.c_int)]
 
 
 # name -> argtypes; every entry returns int except the ones listed in _RESTYPES.  This table is
@@ -64,13 +66,16 @@ SIGNATURES = {
     "pmctf_set_conv_mode": [_I],
     "pmctf_get_conv_mode": [],
     "pmctf_tc_error_flag": [],
+    "pmctf_tc_clear_error": [],
+    "pmctf_tc_inject_timeout": [],
+    "pmctf_release_pu_weights": [_P],
     "pmctf_tc_debug_times": [_P],
     "pmctf_tc_mma_probe": [_I, _I, _P, _P],
     "pmctf_pack_pu_weights": [_P] * 10,
     "pmctf_flow_warp": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _f, _I, _P],
     "pmctf_chroma_mv_down": [_P, _P, _I, _I, _I, _P],
     "pmctf_lift_step": [C.POINTER(Step), _P],
-    "pmctf_predict_update": [_P, _P, _f, _P, _I, _I, _I, _P],
+    "pmctf_predict_update": [_P, _P, _f, _P, _I, _I, _I, _I, _P],
     "pmctf_temporal_filter": [_P, C.POINTER(Temporal), _I, _P, _I, _I, _I, _P],
     "pmctf_forward_mctf": [C.POINTER(Plane), C.POINTER(Plane), _P, _I, _I, _P, _P, C.POINTER(Temporal),
                            C.POINTER(Plane), C.POINTER(Plane), C.POINTER(Plane), C.POINTER(Plane), _I, _I, _I, _P],
@@ -130,13 +135,15 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if L.pmctf_abi_version() != 1:
+        if L.pmctf_abi_version() != 2:
             raise RuntimeError("libpmctf_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
 
 
 def check(code: int, what: str):
+    """Raise RuntimeError for a non-zero return of the C ABI (PMCTF_ETIMEOUT included: a tensor-core kernel on this device
+    gave up earlier and its outputs are incomplete; ops.clear_tc_error() re-arms the device)."""
     if code != 0:
         msg = lib().pmctf_error_string(code)
         raise RuntimeError(f"{what} failed ({code}): {msg.decode() if msg else '?'}")

@@ -14,14 +14,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "pmctf_b200.h"
 #include "pmctf_common.cuh"
 
 namespace pmctf {
 
 // number of kernels this library has launched (process-wide; bench.py reports the delta over its timed region)
-static unsigned long long g_launches = 0;
-#define PMCTF_LAUNCHED() (++pmctf::g_launches, (int)cudaGetLastError())
+static std::atomic<unsigned long long> g_launches{0};
+#define PMCTF_LAUNCHED() (pmctf::g_launches.fetch_add(1, std::memory_order_relaxed), (int)cudaGetLastError())
 
 // ------------------------------------------------------------------------------------------
 // tile geometry (logical coordinates: what the reference's conv2d sees)
@@ -659,29 +661,64 @@ static PlaneD to_dev(const pmctf_plane_t &p)
 
 int launch_step_tc(const StepD &d, int src_kind, int *err_flag, cudaStream_t st); // pmctf_lift_tc.cu
 int register_packed_weights(const float *packed, cudaStream_t st);                 // pmctf_lift_tc.cu
+int release_packed_weights(const float *packed);                                   // pmctf_lift_tc.cu
 
-static int g_conv_mode = PMCTF_CONV_TENSOR;
-static int *g_tc_err_of[64] = {nullptr}; // per device: flag set by a tensor-core kernel whose MMA never completed (+ timing stamps)
+// process-wide DEFAULT of the convolution arithmetic; descriptors may name a mode per call (conv_mode fields)
+static std::atomic<int> g_conv_mode{PMCTF_CONV_TENSOR};
 
-static int *tc_err_buffer(bool create)
+// Per device: the error word a tensor-core kernel sets when one of its bounded mbarrier waits gave up (+ the phase stamps of the
+// timing build).  It lives in MAPPED PINNED host memory: the kernel writes it through the device alias, the host reads it
+// without any copy or synchronisation -- every launch checks it first, so a timed-out kernel makes all later calls on that
+// device fail with PMCTF_ETIMEOUT until pmctf_tc_clear_error().
+static volatile int *g_tc_err_host[64] = {nullptr};
+static int *g_tc_err_dev[64] = {nullptr};
+static std::atomic<int> g_tc_err_state[64];   // 0 none, 1 being created, 2 ready
+
+static int tc_err_buffer(bool create, volatile int **host, int **devp)
 {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!g_tc_err_of[dev] && create) {
-        // [0] error flag, [2..33] phase stamps of the timing build
-        if (cudaMalloc(&g_tc_err_of[dev], 2048) != cudaSuccess) return nullptr;
-        cudaMemset(g_tc_err_of[dev], 0, 2048);
+    if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
+    if (dev < 0 || dev >= 64) return PMCTF_EINVAL;
+    if (g_tc_err_state[dev].load(std::memory_order_acquire) != 2) {
+        if (!create) { *host = nullptr; *devp = nullptr; return 0; }
+        int expect = 0;
+        if (g_tc_err_state[dev].compare_exchange_strong(expect, 1)) {
+            void *h = nullptr, *d = nullptr;   // [0] error flag, [2..33] phase stamps of the timing build
+            cudaError_t e = cudaHostAlloc(&h, 2048, cudaHostAllocMapped | cudaHostAllocPortable);
+            if (e == cudaSuccess) e = cudaHostGetDevicePointer(&d, h, 0);
+            if (e != cudaSuccess) { g_tc_err_state[dev].store(0); return (int)e; }
+            for (int i = 0; i < 512; ++i) ((int *)h)[i] = 0;
+            g_tc_err_host[dev] = (volatile int *)h;
+            g_tc_err_dev[dev] = (int *)d;
+            g_tc_err_state[dev].store(2, std::memory_order_release);
+        } else {
+            while (g_tc_err_state[dev].load(std::memory_order_acquire) == 1) { }
+            if (g_tc_err_state[dev].load(std::memory_order_acquire) != 2) return PMCTF_EINVAL;
+        }
     }
-    return g_tc_err_of[dev];
+    *host = g_tc_err_host[dev];
+    *devp = g_tc_err_dev[dev];
+    return 0;
 }
 
-static int launch_step(const StepD &d, int src_kind, cudaStream_t st)
+static int resolve_conv_mode(int requested)
 {
-    if (g_conv_mode == PMCTF_CONV_TENSOR) {
-        int *err = tc_err_buffer(true);
-        if (!err) return (int)cudaGetLastError();
-        const int e = launch_step_tc(d, src_kind, err, st);
-        if (e == 0) ++g_launches;
+    if (requested == PMCTF_CONV_DEFAULT) return g_conv_mode.load(std::memory_order_relaxed);
+    return requested;
+}
+
+static int launch_step(const StepD &d, int src_kind, int conv_mode, cudaStream_t st)
+{
+    conv_mode = resolve_conv_mode(conv_mode);
+    if (conv_mode != PMCTF_CONV_TENSOR && conv_mode != PMCTF_CONV_FFMA) return PMCTF_EINVAL;
+    if (conv_mode == PMCTF_CONV_TENSOR) {
+        volatile int *herr = nullptr;
+        int *derr = nullptr;
+        int e = tc_err_buffer(true, &herr, &derr);
+        if (e) return e;
+        if (herr[0] != 0) return PMCTF_ETIMEOUT;   // an earlier tensor-core launch on this device gave up: its outputs are incomplete
+        e = launch_step_tc(d, src_kind, derr, st);
+        if (e == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
         return e;
     }
     static bool configured = false;
@@ -709,6 +746,7 @@ static int launch_step(const StepD &d, int src_kind, cudaStream_t st)
 // validated conversion of the public step descriptor
 static int run_step(const pmctf_step_t &s, cudaStream_t st, int div_group_n = 0x7fffffff, float base_div1_g1 = 1.0f)
 {
+    if (s.conv_mode != PMCTF_CONV_DEFAULT && s.conv_mode != PMCTF_CONV_FFMA && s.conv_mode != PMCTF_CONV_TENSOR) return PMCTF_EINVAL;
     if (s.n <= 0 || s.h <= 0 || s.w <= 0 || !s.pu_packed || !s.out.p || !s.src.p) return PMCTF_EINVAL;
     if (s.mode < 0 || s.mode > 2) return PMCTF_EINVAL;
     if (s.mode == PMCTF_MODE_ACCUM && !s.base.p) return PMCTF_EINVAL;
@@ -735,7 +773,7 @@ static int run_step(const pmctf_step_t &s, cudaStream_t st, int div_group_n = 0x
     d.sign = s.sign; d.final_mul = s.final_mul;
     d.out = to_dev(s.out); d.pred = to_dev(s.pred); d.aux = to_dev(s.aux);
     d.aux_mul = s.aux_mul;
-    return launch_step(d, s.src_kind, st);
+    return launch_step(d, s.src_kind, s.conv_mode, st);
 }
 
 static pmctf_plane_t dense(const float *p, int H, int W)
@@ -772,34 +810,61 @@ extern "C" {
 
 int pmctf_abi_version(void) { return PMCTF_ABI_VERSION; }
 
-unsigned long long pmctf_launch_count(void) { return pmctf::g_launches; }
+unsigned long long pmctf_launch_count(void) { return pmctf::g_launches.load(std::memory_order_relaxed); }
 
 int pmctf_set_conv_mode(int mode)
 {
     if (mode != PMCTF_CONV_FFMA && mode != PMCTF_CONV_TENSOR) return PMCTF_EINVAL;
-    pmctf::g_conv_mode = mode;
+    pmctf::g_conv_mode.store(mode, std::memory_order_relaxed);
     return 0;
 }
 
-int pmctf_get_conv_mode(void) { return pmctf::g_conv_mode; }
+int pmctf_get_conv_mode(void) { return pmctf::g_conv_mode.load(std::memory_order_relaxed); }
 
 int pmctf_tc_debug_times(long long *out16)
 {
     if (!out16) return PMCTF_EINVAL;
     for (int i = 0; i < 16; ++i) out16[i] = 0;
-    int *err = pmctf::tc_err_buffer(false);
-    if (!err) return 0;
-    if (cudaMemcpy(out16, err + 2, 16 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return (int)cudaGetLastError();
-    cudaMemset(err + 2, 0, 16 * sizeof(long long));
+    volatile int *herr = nullptr;
+    int *derr = nullptr;
+    if (pmctf::tc_err_buffer(false, &herr, &derr) || !herr) return 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return (int)cudaGetLastError();
+    volatile long long *t = reinterpret_cast<volatile long long *>(herr + 2);
+    for (int i = 0; i < 16; ++i) { out16[i] = t[i]; t[i] = 0; }
     return 0;
 }
 
 int pmctf_tc_error_flag(void)
 {
-    int v = 0;
-    int *err = pmctf::tc_err_buffer(false);
-    if (err && cudaMemcpy(&v, err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    return v;
+    volatile int *herr = nullptr;
+    int *derr = nullptr;
+    if (pmctf::tc_err_buffer(false, &herr, &derr)) return -1;
+    return herr ? herr[0] : 0;
+}
+
+int pmctf_tc_clear_error(void)
+{
+    volatile int *herr = nullptr;
+    int *derr = nullptr;
+    if (pmctf::tc_err_buffer(false, &herr, &derr)) return PMCTF_EINVAL;
+    if (herr) herr[0] = 0;
+    return 0;
+}
+
+int pmctf_tc_inject_timeout(void)
+{
+    volatile int *herr = nullptr;
+    int *derr = nullptr;
+    const int e = pmctf::tc_err_buffer(true, &herr, &derr);
+    if (e) return e;
+    herr[0] = 1;
+    return 0;
+}
+
+int pmctf_release_pu_weights(const float *packed)
+{
+    if (!packed) return PMCTF_EINVAL;
+    return pmctf::release_packed_weights(packed);
 }
 
 const char *pmctf_error_string(int code)
@@ -809,6 +874,7 @@ const char *pmctf_error_string(int code)
     case PMCTF_EINVAL: return "pmctf: invalid argument (null pointer, non-positive size or bad flag)";
     case PMCTF_ESHAPE: return "pmctf: unsupported shape";
     case PMCTF_EWORKSPACE: return "pmctf: workspace too small";
+    case PMCTF_ETIMEOUT: return "pmctf: a tensor-core kernel on this device gave up waiting for its MMAs (outputs of that launch are incomplete); pmctf_tc_clear_error() re-arms the device";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "pmctf: unknown error";
     }
 }
@@ -818,6 +884,7 @@ int pmctf_pack_pu_weights(const float *w1, const float *b1, const float *w2, con
 {
     if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !w4 || !b4 || !packed) return PMCTF_EINVAL;
     if (((uintptr_t)packed & 15) != 0) return PMCTF_EINVAL;   // the tensor-core kernel fetches the operand images by TMA bulk copies
+    if (pmctf_tc_error_flag() != 0) return PMCTF_ETIMEOUT;
     pack_pu_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(w1, b1, w2, b2, w3, b3, w4, b4, packed);
     const int e = PMCTF_LAUNCHED();
     if (e) return e;
@@ -858,10 +925,11 @@ int pmctf_lift_step(const pmctf_step_t *step, void *stream)
 }
 
 int pmctf_predict_update(const float *x, const float *pu_packed, float in_mul, float *out, int N, int H, int W,
-                         void *stream)
+                         int conv_mode, void *stream)
 {
     if (!x || !out || !pu_packed) return PMCTF_EINVAL;
     pmctf_step_t s = blank_step(N, H, W);
+    s.conv_mode = conv_mode;
     s.src_kind = PMCTF_SRC_PLANE; s.mode = PMCTF_MODE_PU;
     s.src = dense(x, H, W); s.out = dense(out, H, W);
     s.pu_packed = pu_packed; s.in_mul = in_mul;
@@ -873,6 +941,7 @@ int pmctf_temporal_filter(const float *x, const pmctf_temporal_t *t, int which, 
 {
     if (!x || !out || !t || (which != 0 && which != 1)) return PMCTF_EINVAL;
     pmctf_step_t s = blank_step(N, H, W);
+    s.conv_mode = t->conv_mode;
     s.src_kind = PMCTF_SRC_PLANE; s.mode = PMCTF_MODE_FILTER;
     s.src = dense(x, H, W); s.out = dense(out, H, W);
     s.pu_packed = which == 0 ? t->P_t_packed : t->U_t_packed;
@@ -884,9 +953,10 @@ int pmctf_temporal_filter(const float *x, const pmctf_temporal_t *t, int which, 
 static pmctf_step_t mctf_step(const pmctf_plane_t *src, const pmctf_plane_t *base, const pmctf_plane_t *out,
                               const pmctf_plane_t *pred, const float *mv, int mv_n, int mv_down, float mv_sign,
                               const float *lin_x, const float *lin_y, const float *packed, float out_mul, float sign,
-                              int lossy, int N, int H, int W)
+                              int lossy, int N, int H, int W, int conv_mode)
 {
     pmctf_step_t s = blank_step(N, H, W);
+    s.conv_mode = conv_mode;
     s.src_kind = PMCTF_SRC_WARP; s.mode = PMCTF_MODE_ACCUM;
     s.src = *src; s.base = *base; s.out = *out;
     if (pred && pred->p) s.pred = *pred;
@@ -904,12 +974,12 @@ int pmctf_forward_mctf(const pmctf_plane_t *ref, const pmctf_plane_t *cur, const
     if (!ref || !cur || !mv || !t || !L || !Hh || !ref->p || !cur->p || !L->p || !Hh->p) return PMCTF_EINVAL;
     // H_t = cur - predict(warp(ref, mv))                 pMCTF_L.py:301-305
     pmctf_step_t s1 = mctf_step(ref, cur, Hh, pred, mv, mv_n, mv_down, 1.0f, lin_x, lin_y, t->P_t_packed, t->scale_p,
-                                -1.0f, t->lossy, N, H, W);
+                                -1.0f, t->lossy, N, H, W, t->conv_mode);
     int e = run_step(s1, (cudaStream_t)stream);
     if (e) return e;
     // L_t = ref + update(warp(H_t, -mv))                 pMCTF_L.py:307-311
     pmctf_step_t s2 = mctf_step(Hh, ref, L, inv, mv, mv_n, mv_down, -1.0f, lin_x, lin_y, t->U_t_packed, t->scale_u,
-                                1.0f, t->lossy, N, H, W);
+                                1.0f, t->lossy, N, H, W, t->conv_mode);
     return run_step(s2, (cudaStream_t)stream);
 }
 
@@ -920,12 +990,12 @@ int pmctf_inverse_mctf(const pmctf_plane_t *L, const pmctf_plane_t *Hh, const fl
     if (!L || !Hh || !mv || !t || !ref || !cur || !L->p || !Hh->p || !ref->p || !cur->p) return PMCTF_EINVAL;
     // ref = L - update(warp(H, -mv))                     pMCTF_L.py:320-324
     pmctf_step_t s1 = mctf_step(Hh, L, ref, nullptr, mv, mv_n, mv_down, -1.0f, lin_x, lin_y, t->U_t_packed, t->scale_u,
-                                -1.0f, t->lossy, N, H, W);
+                                -1.0f, t->lossy, N, H, W, t->conv_mode);
     int e = run_step(s1, (cudaStream_t)stream);
     if (e) return e;
     // cur = H + predict(warp(ref, mv))                   pMCTF_L.py:325-329
     pmctf_step_t s2 = mctf_step(ref, Hh, cur, nullptr, mv, mv_n, mv_down, 1.0f, lin_x, lin_y, t->P_t_packed, t->scale_p,
-                                1.0f, t->lossy, N, H, W);
+                                1.0f, t->lossy, N, H, W, t->conv_mode);
     return run_step(s2, (cudaStream_t)stream);
 }
 
@@ -941,6 +1011,7 @@ static int spatial_step(const pmctf_iwave_t *p, int which, const pmctf_plane_t &
                         int n, int h, int w, cudaStream_t st, const SpatialDivs &dv = SpatialDivs())
 {
     pmctf_step_t s = blank_step(n, h, w);
+    s.conv_mode = p->conv_mode;
     s.src_kind = PMCTF_SRC_SKIP3; s.mode = PMCTF_MODE_ACCUM;
     s.src = src; s.src_div1 = dv.sd1; s.src_div2 = dv.sd2;
     s.tap0 = p->tap[which][0]; s.tap1 = p->tap[which][1]; s.tap2 = p->tap[which][2]; s.tap_bias = p->bias[which];

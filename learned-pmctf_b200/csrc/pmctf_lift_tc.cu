@@ -45,7 +45,7 @@
 #define PMCTF_TC_TIMING 0   // 1: clock64 stamps of the phases of one CTA (pmctf_tc_debug_times, scratch/tc_phases.py); profiling builds only
 #endif
 #ifndef PMCTF_WHATIF
-#define PMCTF_WHATIF 0   // timing experiments only (bit 1: no tanh table lookup, bit 2: no MMAs)
+#define PMCTF_WHATIF 0   // timing experiments only (2: no tanh table lookup, 4: no MMAs, 8: no TMEM reads, 16: third-order tanh on a 1/32 grid)
 #endif
 
 namespace pmctf {
@@ -110,6 +110,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
 {
+#if PMCTF_WHATIF & 8   // timing experiment: no TMEM reads
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = taddr + i;
+    return;
+#endif
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr)
@@ -118,6 +123,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
 
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
 {
+#if PMCTF_WHATIF & 8
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = taddr + i;
+    return;
+#endif
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
                  : "r"(taddr)
@@ -433,8 +443,8 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     if (!staged) {   // first tile of this CTA: the TMA bulk copies of the setup ran under the source load
         ok = umma::mbar_wait(umma::smem_u32(bars + 2 * NSLOT), 0u);
         staged = true;
-        if (!ok) {
-            if (err) atomicExch(err, 1);
+        if (__syncthreads_or(!ok)) {   // CTA-uniform: either every thread goes on or all of them leave
+            ok = false;
             break;
         }
     }
@@ -510,7 +520,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                 const int slot = blk % NSLOT;
                 const uint32_t parity = (uint32_t)(blk / NSLOT) & 1u; // completion 2*layer + blk/NSLOT of this slot
                 const long long tw = (PMCTF_TC_TIMING && dbg && tid == 0) ? clock64() : 0;
-                ok = umma::mbar_wait(full0 + 8 * slot, parity);
+                ok = __all_sync(0xffffffffu, (int)umma::mbar_wait(full0 + 8 * slot, parity)) != 0;   // warp-uniform: the TMEM loads below are .sync.aligned
                 if (PMCTF_TC_TIMING && dbg && tid == 0) dbg[12 + layer] += clock64() - tw;
                 if (!ok) break;
                 umma::fence_after_sync();
@@ -614,14 +624,15 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
         }
         umma::fence_proxy_async();
         umma::fence_before_sync();
-        __syncthreads();
+        const int bad = __syncthreads_or(!ok);   // a bounded wait gave up somewhere in the CTA: all warps leave together
         umma::fence_after_sync();
         STAMP(3 + layer);
+        if (bad) {
+            ok = false;
+            break;
+        }
     }
-    if (!ok) {
-        if (err) atomicExch(err, 1);
-        break;
-    }
+    if (!ok) break;   // CTA-uniform (set from __syncthreads_or)
 
     // the base operand of this thread's output pixels: issued here so that the gather below hides the global-load latency
     constexpr int NFIN = (TH * TW + NT - 1) / NT;
@@ -700,6 +711,10 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     ++tiles_done;
     } // tile loop
     if (PMCTF_TC_TIMING && dbg_cta && tid == 0) { dbg_cta[14] = clock64() - t_cta0; dbg_cta[15] = tiles_done; }
+    if (!ok && tid == 0 && err) {   // watchdog word in mapped pinned host memory: later launches on this device are refused (PMCTF_ETIMEOUT)
+        *reinterpret_cast<volatile int *>(err) = 1;
+        __threadfence_system();
+    }
     umma::fence_before_sync();
     __syncthreads();
     if (warp == MMA_WARP) umma::tmem_dealloc(tbase, TMEM_COLS);
@@ -784,7 +799,16 @@ int register_packed_weights(const float *packed, cudaStream_t st)
     w.sc2 = h[tc::SC_OFF];
     w.sc3 = h[tc::SC_OFF + 1];
     std::lock_guard<std::mutex> lk(g_w_mutex);
-    g_w_registry[packed] = w;
+    g_w_registry[packed] = w;   // a repack at the same address replaces the entry
+    return 0;
+}
+
+// the owner of a packed block frees it (or is about to reuse the memory for something else): forget its parameters, so that a
+// later launch naming this address without a fresh pmctf_pack_pu_weights() is rejected instead of running with stale values
+int release_packed_weights(const float *packed)
+{
+    std::lock_guard<std::mutex> lk(g_w_mutex);
+    g_w_registry.erase(packed);
     return 0;
 }
 

@@ -78,8 +78,19 @@ class GopCodec:
         self._side = {}
 
     # step sizes exactly as forward_one_stage derives them (pMCTF_L.py:343-349, pWave.py:231-238)
+    def _q_params(self, coder: str, stage: int):
+        m = self.m
+        if coder == "hp":
+            ps = [m.hp_coder.QP, m.hp_coder.QP_ll]
+            if self.q_index is not None and m.quant_stage:
+                ps.append(m.hp_q_scale[min(m.num_me_stages - 1, stage)])
+            return ps
+        return [m.lp_coder.QP, m.lp_coder.QP_ll]
+
     def q_pair(self, coder: str, stage: int):
-        key = (coder, stage, self.q_index)
+        """Host scalars of the quantisation steps, cached per (coder, stage, q_index) AND per version of the parameters they
+        derive from, so that load_state_dict / an optimiser step is seen."""
+        key = (coder, stage, self.q_index) + tuple((p.data_ptr(), p._version) for p in self._q_params(coder, stage))
         v = self._qcache.get(key)
         if v is None:
             m = self.m
@@ -90,6 +101,8 @@ class GopCodec:
             else:
                 q, qll = m.lp_coder.q_pair(self.q_index)
             v = (float(q.detach().reshape(-1)[0].cpu()), float(qll.detach().reshape(-1)[0].cpu()))
+            if len(self._qcache) > 256:
+                self._qcache.clear()
             self._qcache[key] = v
         return v
 
@@ -327,7 +340,9 @@ class GopCodec:
             cur.wait_stream(lane)
         for st in out:
             st.record_stream(cur)
-        return torch.cat(out).cpu()
+        res = torch.cat(out).cpu()              # synchronises: every kernel of the sequence has finished
+        ops.check_tc_error(dev, "GopCodec.code_sequence_host")
+        return res
 
 
 # -------------------------------------------------------------------------------------------------

@@ -29,26 +29,88 @@ def merge(x_e, x_o):
 
 
 class _PackedWeights:
-    """Device-side repack of PredictUpdate weights, refreshed when any parameter changes
-    (keyed on tensor version counters and storage addresses)."""
+    """Device-side repack of PredictUpdate weights, refreshed when any parameter changes.  The key is (storage address,
+    tensor version, device) per parameter.  Writes that bypass the version counter (`p.data.copy_(...)`, as some EMA /
+    checkpoint code does) are not visible to it: call `invalidate()` (or the owning module's `invalidate_packed()`, which
+    load_state_dict does automatically) after such a write.  The block registered with the C library is released before its
+    memory is dropped (pmctf_release_pu_weights), so a recycled address can never be launched with stale parameters."""
 
     def __init__(self):
         self.key = None
         self.buf = None
+        self.blocks = 0
+
+    def invalidate(self):
+        self.key = None
+
+    def _release(self):
+        if self.buf is not None:
+            try:
+                ops.release_pu(self.buf, self.blocks)
+            except Exception:   # interpreter shutdown: the library may be gone already
+                pass
+            self.buf = None
+
+    def __del__(self):
+        self._release()
+
+    # caches hold device pointers: never pickled / deep-copied (torch.save(model), copy.deepcopy(model))
+    def __getstate__(self):
+        return {"packed": None}   # non-empty: pickle skips __setstate__ for a falsy state
+
+    def __setstate__(self, state):
+        self.key, self.buf, self.blocks = None, None, 0
+
+    def __deepcopy__(self, memo):
+        return _PackedWeights()
 
     def get(self, pus):
         params = [p for pu in pus for p in pu.ordered_params()]
         key = tuple((p.data_ptr(), p._version, str(p.device)) for p in params)
         if key != self.key:
             dev = params[0].device
-            buf = torch.empty(len(pus) * nat.PU_PACKED_FLOATS, dtype=torch.float32, device=dev)
-            for i, pu in enumerate(pus):
-                ops.pack_pu(pu.ordered_params(), buf[i * nat.PU_PACKED_FLOATS:(i + 1) * nat.PU_PACKED_FLOATS])
-            self.key, self.buf = key, buf
+            if self.buf is not None and (self.buf.device != dev or self.blocks != len(pus)):
+                self._release()
+            if self.buf is None:
+                self.buf = torch.empty(len(pus) * nat.PU_PACKED_FLOATS, dtype=torch.float32, device=dev)
+                self.blocks = len(pus)
+            for i, pu in enumerate(pus):   # a repack at the same address replaces the registered parameters
+                ops.pack_pu(pu.ordered_params(), self.buf[i * nat.PU_PACKED_FLOATS:(i + 1) * nat.PU_PACKED_FLOATS])
+            self.key = key
         return self.buf
 
 
-class PredictUpdate(nn.Module):
+class _HotPathModule(nn.Module):
+    """Shared plumbing of the modules that own packed weights: `conv_mode` (None = process default, 'ffma' | 'tensor' =
+    this module's calls only), cache invalidation on load_state_dict, and pickling without device pointers."""
+
+    conv_mode = None
+
+    def invalidate_packed(self):
+        for m in self.modules():
+            pk = m.__dict__.get("_pack")
+            if pk is not None:
+                pk.invalidate()
+            if "_desc" in m.__dict__:
+                m.__dict__["_desc"] = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        pk = self.__dict__.get("_pack")
+        if pk is not None:
+            pk.invalidate()
+        if "_desc" in self.__dict__:
+            self.__dict__["_desc"] = None
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        if "_desc" in st:
+            st["_desc"] = None      # ctypes struct with device pointers
+        st.pop("_keep", None)
+        return st
+
+
+class PredictUpdate(_HotPathModule):
     """conv1 -> tanh -> conv2 -> tanh -> conv3, + conv1, -> conv4; 1-16-16-16-1 channels (lifting_1d.py:25-49)."""
 
     def __init__(self, in_ch):
@@ -74,7 +136,7 @@ class PredictUpdate(nn.Module):
         from .. import train
         if train.needs_grad(x, self):  # autograd: differentiable conv kernels (csrc/pmctf_train.cu)
             return train.predict_update(self, x)
-        return ops.predict_update(x, self.packed())
+        return ops.predict_update(x, self.packed(), conv_mode=self.conv_mode)
 
 
 def _skip_conv(init):
@@ -85,7 +147,7 @@ def _skip_conv(init):
     return conv
 
 
-class iWave1D(nn.Module):
+class iWave1D(_HotPathModule):
     """Prediction-first learned lifting along rows with bior4.4-initialised skip taps (lifting_1d.py:52-189)."""
 
     def __init__(self, in_channels=1, bitdepth=8, lossy=True):
@@ -118,7 +180,8 @@ class iWave1D(nn.Module):
         skips = [self.conv_P1, self.conv_U1, self.conv_P2, self.conv_U2]
         key = tuple((m.weight.data_ptr(), m.weight._version, m.bias.data_ptr(), m.bias._version) for m in skips)
         packed = self._pack.get([self.P_1, self.U_1, self.P_2, self.U_2])  # application order
-        if key != self._tap_key or self._desc is None or self._desc.pu_packed != packed.data_ptr():
+        mode = ops.conv_mode_code(self.conv_mode)
+        if key != self._tap_key or self._desc is None or self._desc.pu_packed != packed.data_ptr() or self._desc.conv_mode != mode:
             vals = torch.cat([torch.cat([m.weight.detach().reshape(3), m.bias.detach().reshape(1)]) for m in skips]).tolist()
             d = nat.IWave()
             for i in range(4):
@@ -129,6 +192,7 @@ class iWave1D(nn.Module):
             d.scale_l, d.scale_h = float(self.scale_l.detach()), float(self.scale_h.detach())
             d.dynamic_range = self.dynamic_range
             d.lossy = int(self.lossy)
+            d.conv_mode = mode
             self._tap_key, self._desc = key, d
         return self._desc
 

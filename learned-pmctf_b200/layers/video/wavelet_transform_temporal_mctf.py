@@ -6,10 +6,10 @@ import torch.nn as nn
 
 from ... import _native as nat
 from ... import ops
-from ..lifting_1d import PredictUpdate, _PackedWeights
+from ..lifting_1d import PredictUpdate, _HotPathModule, _PackedWeights
 
 
-class TemporalLifting(nn.Module):
+class TemporalLifting(_HotPathModule):
     def __init__(self, bitdepth=8, lossy=True, in_channels=1):
         super().__init__()
         self.bitdepth = bitdepth
@@ -27,7 +27,8 @@ class TemporalLifting(nn.Module):
         packed = self._pack.get([self.P_t, self.U_t])
         self._keep = packed
         return nat.Temporal(packed.data_ptr(), packed.data_ptr() + 4 * nat.PU_PACKED_FLOATS,
-                            float(self.scale_p.detach()), float(self.scale_u.detach()), int(self.lossy))
+                            float(self.scale_p.detach()), float(self.scale_u.detach()), int(self.lossy),
+                            ops.conv_mode_code(self.conv_mode))
 
     def predict_filter(self, x):
         """(x + 0.1 * P_t(x)) * scale_p   (:27-35)"""

@@ -68,11 +68,22 @@ class pWaveTransform:
         return self.get_one_q_scale(q_scale, q_index)
 
     def _q_float(self, q) -> float:
-        """Scalar value of a [1,1,1,1] step tensor (or a float)."""
+        """Scalar value of a [1,1,1,1] step tensor (or a float).  The reference's forward_one_channel passes the SAME step
+        tensor to quantize_subband for every band (pWave.py:255,278) and again to dequantize_subbands (:291): the device ->
+        host read is done once per tensor object and version (a small identity cache that keeps the tensor alive, so an id
+        can not be recycled), not once per subband."""
         if isinstance(q, torch.Tensor):
             if q.numel() != 1:
                 raise NotImplementedError("per-sample q_index lists are not supported on the fused path (batch shares one step)")
-            return float(q.detach().reshape(()).to("cpu"))
+            cache = self.__dict__.setdefault("_q_seen", [])
+            for t, ver, val in cache:
+                if t is q and ver == q._version:
+                    return val
+            val = float(q.detach().reshape(()).to("cpu"))
+            cache.append((q, q._version, val))
+            if len(cache) > 8:
+                del cache[0]
+            return val
         return float(q)
 
     # --- transform (pWave.py:139-157) ---------------------------------------------------------
@@ -121,6 +132,22 @@ class pWaveTransform:
     def _train(self, *ts):
         from .. import train
         return train.needs_grad(*ts, self)
+
+    def _round(self, s):
+        """RoundNoGradient (layers.py:71-80) on a clamped band: the fused kernel with q = 1 on the evaluation path."""
+        if self._train(s):
+            from ..layers import RoundNoGradient
+            return RoundNoGradient.apply(s) if self.lossy else s
+        return ops.quantize(s, 1.0, self.clip_value, self.lossy, do_round=self.lossy)
+
+    def q_pair(self, q_index=None, qp_scale=None):
+        """(q, q_ll) as the reference derives them in forward/compress (pWave.py:231-238,383-392)."""
+        if q_index is None:
+            return self.QP[-1], self.QP_ll[-1]
+        q, qll = self.get_curr_q(self.QP, q_index), self.get_curr_q(self.QP_ll, q_index)
+        if qp_scale is not None:
+            q, qll = q * qp_scale, qll * qp_scale
+        return q, qll
 
     def quantize_subband(self, subband, q_scale):
         """clamp(s * q, +-clip), not rounded (pWave.py:184-189)."""
@@ -211,18 +238,32 @@ class pWave(pWaveTransform, nn.Module):
         self.QP_ll = nn.Parameter(torch.ones((2, 1, 1, 1), dtype=torch.float) * 1 / 16)
         self._qc = _QCache()
 
-    def q_pair(self, q_index=None, qp_scale=None):
-        """(q, q_ll) as the reference derives them in forward/compress (pWave.py:231-238,383-392)."""
-        if q_index is None:
-            return self.QP[-1], self.QP_ll[-1]
-        q, qll = self.get_curr_q(self.QP, q_index), self.get_curr_q(self.QP_ll, q_index)
-        if qp_scale is not None:
-            q, qll = q * qp_scale, qll * qp_scale
-        return q, qll
-
     def forward(self, x, q_index=None, qp_scale=None):
-        """Transform-only forward: returns what the reference's forward_one_channel computes up to
-        the entropy model (pWave.py:240-257, 293-296): x_hat (pre-PostProcess) and the symbols."""
-        q, qll = self.q_pair(q_index, qp_scale)
-        x_hat, hat = self.spatial_wavelet_dec(x, q, qll, post_process=False, return_symbols=True)
-        return {"x_hat": x_hat, "subbands": hat}
+        """pWave.forward (pWave.py:231-242): same signature, same step derivation, then forward_one_channel."""
+        if q_index is not None:
+            q, qll = self.q_pair(q_index, qp_scale)
+            return self.forward_one_channel(x, q, qll)
+        return self.forward_one_channel(x)
+
+    def forward_one_channel(self, x, q_scale=None, q_scale_ll=None):
+        """pWave.forward_one_channel (pWave.py:244-312) with the reference's own call sequence on the hot path -- encode ->
+        quantize_subband(ll, q_ll) -> round -> per band (coarsest level first, lh/hl/hh) quantize_subband(s, q) -> symbols ->
+        dequantize_subbands -> decode -- and the reference's return keys.  The entropy-parameter networks and the
+        PostProcess net are SURVEY.md section 8f rows (not built yet): the symbols are the zero-mean ones
+        (round(clamp(s*q)), which is what spatial_wavelet_dec, pWave.py:314-349, defines), `x_hat` is the synthesis output
+        before PostProcess, and the keys that only the entropy model can fill (`bits`, `likelihoods`, `bits_total`,
+        `bpp_total`) are NaN / None instead of invented numbers."""
+        if q_scale is None:
+            q_scale, q_scale_ll = self.QP[-1], self.QP_ll[-1]
+        top = self.decomp_levels - 1
+        y = self.encode(x)
+        subbands_hat = {lvl: {} for lvl in range(self.decomp_levels)}
+        ll = self.quantize_subband(y[top]["ll"], q_scale_ll)
+        subbands_hat[top]["ll"] = self._round(ll)
+        for lvl in range(top, -1, -1):
+            for b in BANDS:
+                subbands_hat[lvl][b] = self._round(self.quantize_subband(y[lvl][b], q_scale))
+        x_hat = self.decode(self.dequantize_subbands(subbands_hat, q_scale, q_scale_ll))
+        nan = torch.full((), float("nan"), device=x.device)
+        return {"x_hat": x_hat, "bits": None, "likelihoods": None, "subbands": subbands_hat, "bpp_total": nan, "bits_total": nan,
+                "mse": torch.mean((x - x_hat) ** 2)}

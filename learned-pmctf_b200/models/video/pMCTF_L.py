@@ -42,6 +42,48 @@ class MCTFMixin:
     def _temporal(self, stage_idx):
         return self.temporal_filtering[min(self.num_me_stages - 1, stage_idx)].descriptor()
 
+    def hp_qp_scale(self, stage_idx, q_index):
+        """Temporal-layer-adaptive step scaling (pMCTF_L.py:343-347,404-408)."""
+        if not self.quant_stage:
+            return None
+        return self.get_curr_q(self.hp_q_scale[stage_idx], q_index)
+
+    @staticmethod
+    def mse(x, y):
+        return torch.mean((x - y) ** 2)
+
+    # --- entry points (pMCTF_L.py:294, 332-379) ------------------------------------------------------------
+    def forward(self, ref_frame, cur_frame, q_index, code_lt, dpb, stage_idx=0):
+        return self.forward_one_stage(ref_frame, cur_frame, q_index, code_lt, dpb, stage_idx=stage_idx)
+
+    def forward_one_stage(self, ref_frame, cur_frame, q_index, code_lt, dpb, mv_hat=None, stage_idx=0, me_downsample=1):
+        """pMCTF.forward_one_stage (pMCTF_L.py:332-379), same signature and return keys, for the hot path: the motion field is
+        an INPUT here (`mv_hat=`; the reference's own signature already accepts it and then skips SpyNet + the MV codec,
+        :333-336 -- note that it halves and 2x2-averages a given field exactly as below).  The keys that only the MV
+        codec / entropy model can fill are None / NaN (see pWave.forward_one_channel)."""
+        if mv_hat is None:
+            raise NotImplementedError("motion estimation + MV coding (SpyNet, SURVEY.md section 8f row 4) are not part of the hot path: "
+                                      "pass mv_hat= (the reference's forward_one_stage accepts it, pMCTF_L.py:333-336)")
+        bpp_mv_y, bpp_mv_z = None, None
+        ref_mv = {"mv_feature": None, "mv_y_hat": None}
+        mv_hat = bilineardownsacling(mv_hat) / 2                      # pMCTF_L.py:336
+        L_t, H_t, pred_frame, inv_pred_frame = self.forward_MCTF(ref_frame, cur_frame, mv_hat, stage_idx)
+        qp_scale = self.get_curr_q(self.hp_q_scale[stage_idx], q_index) if self.quant_stage else None
+        res_H = self.hp_coder.forward(H_t, q_index, qp_scale=qp_scale)
+        ret = {"bpp_mv_y": bpp_mv_y, "bpp_mv_z": bpp_mv_z, "bpp_me": None, "me_mse": self.mse(pred_frame, cur_frame),
+               "bpp": res_H["bpp_total"], "bpp_H": res_H["bpp_total"], "bit_H": res_H["bits_total"], "bit_ME": None,
+               "mse_H": res_H["mse"], "mv_hat": mv_hat, "dpb": {"mv_feature": ref_mv["mv_feature"], "ref_mv_y": ref_mv["mv_y_hat"]},
+               "H_t": res_H["x_hat"]}
+        if code_lt:
+            res_L = self.lp_coder.forward(L_t, q_index)
+            ret["bpp_L"], ret["bit_L"], ret["mse_L"] = res_L["bpp_total"], res_L["bits_total"], res_L["mse"]
+            ret["me_mse_inv"] = self.mse(inv_pred_frame, ref_frame)
+            ret["L_t"] = res_L["x_hat"]
+        else:
+            ret["L_t"] = L_t
+        ret["bit"] = ret["bpp"] * (ref_frame.size(2) * ref_frame.size(3))
+        return ret
+
     def forward_MCTF(self, ref_frame, cur_frame, mv_hat, stage_idx=0, mv_down=False, want_pred=True, **out):
         """H = cur - P(warp(ref, mv)); L = ref + U(warp(H, -mv)) -> (L_t, H_t, pred, inv)  (pMCTF_L.py:297-312).
         Two launches: each fuses warp + PredictUpdate CNN + lifting arithmetic.  `mv_down=True`
@@ -78,12 +120,6 @@ class pMCTF(MCTFMixin, nn.Module):
         self.two_stage_me = two_stage_me
         self.num_me_stages = num_me_stages
 
-    def hp_qp_scale(self, stage_idx, q_index):
-        """Temporal-layer-adaptive step scaling (pMCTF_L.py:343-347,404-408)."""
-        if not self.quant_stage:
-            return None
-        return self.get_curr_q(self.hp_q_scale[stage_idx], q_index)
-
     def load_reference_state_dict(self, sd):
         """Load the hot-path entries of a full reference checkpoint (3224 keys for num_me_stages=4);
         every key this model owns must be present."""
@@ -94,9 +130,13 @@ class pMCTF(MCTFMixin, nn.Module):
         return self.load_state_dict({k: sd[k] for k in own}, strict=True)
 
 
+# grafted onto the reference's objects by accelerate(): the hot-path methods and the helpers they (and GopCodec) call.  The
+# reference's own forward / forward_one_channel / forward_one_stage / compress / decompress bodies stay: they sequence the
+# out-of-scope networks around these.
 _PWAVE_METHODS = ("encode", "decode", "decode_dequant", "encode_bands", "quantize_subband", "quantize_subbands",
-                  "dequantize_subbands", "dequantize_subband", "spatial_wavelet_dec", "_q_float", "code_planes")
-_MCTF_METHODS = ("motion_compensation", "forward_MCTF", "inverse_MCTF", "_temporal")
+                  "dequantize_subbands", "dequantize_subband", "spatial_wavelet_dec", "_q_float", "code_planes", "_train", "_round",
+                  "q_pair")
+_MCTF_METHODS = ("motion_compensation", "forward_MCTF", "inverse_MCTF", "_temporal", "hp_qp_scale")
 
 
 def accelerate(ref_model):

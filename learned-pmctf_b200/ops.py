@@ -19,9 +19,14 @@ SCALE_P = float(np.float32(1 / math.sqrt(2)))   # wavelet_transform_temporal_mct
 SCALE_U = 0.5
 
 
+_MODES = {"default": nat.CONV_DEFAULT, "ffma": nat.CONV_FFMA, "tensor": nat.CONV_TENSOR}
+
+
 def set_conv_mode(mode: str) -> None:
     """'tensor' (default): conv2/conv3 of PredictUpdate as exact fixed-point implicit GEMMs on the tcgen05 tensor cores;
-    'ffma': sequential fp32 FMA chains on the CUDA cores.  Process-wide (include/pmctf_b200.h PMCTF_CONV_*)."""
+    'ffma': sequential fp32 FMA chains on the CUDA cores.  This is the process-wide DEFAULT (include/pmctf_b200.h
+    PMCTF_CONV_*); a module can pin its own arithmetic with `module.conv_mode = "ffma" | "tensor"`, which travels in the
+    conv_mode field of its descriptor and overrides the default for that module's calls only."""
     nat.check(nat.lib().pmctf_set_conv_mode({"ffma": nat.CONV_FFMA, "tensor": nat.CONV_TENSOR}[mode]), "set_conv_mode")
 
 
@@ -29,8 +34,79 @@ def get_conv_mode() -> str:
     return "tensor" if nat.lib().pmctf_get_conv_mode() == nat.CONV_TENSOR else "ffma"
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def conv_mode_code(mode) -> int:
+    """'default' | 'ffma' | 'tensor' | None -> PMCTF_CONV_* value of a descriptor's conv_mode field."""
+    return _MODES[mode or "default"]
+
+
+def tc_error_flag() -> int:
+    """Watchdog word of the current device: non-zero once a tensor-core step kernel gave up waiting for its MMAs.  Read it
+    after synchronising; every later launch on that device fails with PMCTF_ETIMEOUT until clear_tc_error()."""
+    return int(nat.lib().pmctf_tc_error_flag())
+
+
+def check_tc_error(device=None, what: str = "tensor-core lifting step") -> None:
+    """Raise if a tensor-core kernel on `device` timed out (its outputs are incomplete).  Called by GopCodec at its
+    synchronisation points; cheap (reads one word of pinned host memory)."""
+    with _guard(device):
+        if tc_error_flag() != 0:
+            raise RuntimeError(f"{what}: a tensor-core kernel gave up waiting for its MMAs on {device or 'the current device'}; "
+                               "results since the last check are incomplete (ops.clear_tc_error() re-arms the device)")
+
+
+def clear_tc_error(device=None) -> None:
+    with _guard(device):
+        nat.check(nat.lib().pmctf_tc_clear_error(), "tc_clear_error")
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOGUARD = _NoGuard()
+
+
+def _guard(device):
+    """Device guard like the one ATen ops carry: the C ABI keys its per-device state on the CURRENT device and launches
+    on the stream it is given, so a call on tensors of another device must switch to it first.  No-op (no allocation) when
+    the tensors already live on the current device."""
+    if device is None:
+        return _NOGUARD
+    device = torch.device(device)
+    if device.type != "cuda":
+        return _NOGUARD
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx == torch.cuda.current_device():
+        return _NOGUARD
+    return torch.cuda.device(idx)
+
+
+def _same_device(*ts):
+    """All CUDA operands of one call must share a device (the kernels dereference raw pointers)."""
+    dev = None
+    for t in ts:
+        if isinstance(t, torch.Tensor):
+            if dev is None:
+                dev = t.device
+            elif t.device != dev:
+                raise RuntimeError(f"operands live on different devices: {dev} and {t.device}")
+    return dev
+
+
+def _launch(device, what: str, fn, *args) -> None:
+    """One C-ABI call on `device`: device guard, the current stream of THAT device as the trailing stream argument,
+    non-zero return -> RuntimeError."""
+    with _guard(device):
+        nat.check(fn(*args, _stream(device)), what)
+
+
+def _stream(device=None) -> int:
+    """Handle of torch's current stream ON THE OPERANDS' DEVICE (not of the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def _chk(t: torch.Tensor, name: str, ndim: Optional[int] = None) -> torch.Tensor:
@@ -79,20 +155,20 @@ _TIMER: Optional[KernelTimer] = None
 
 
 class _timed:
-    __slots__ = ("launches", "pixels", "ev")
+    __slots__ = ("launches", "pixels", "ev", "dev")
 
-    def __init__(self, launches: int, pixels: int):
-        self.launches, self.pixels = launches, pixels
+    def __init__(self, launches: int, pixels: int, device=None):
+        self.launches, self.pixels, self.dev = launches, pixels, device
 
     def __enter__(self):
         if _TIMER is not None:
             self.ev = torch.cuda.Event(enable_timing=True)
-            self.ev.record()
+            self.ev.record(torch.cuda.current_stream(self.dev))
 
     def __exit__(self, *exc):
         if _TIMER is not None:
             e = torch.cuda.Event(enable_timing=True)
-            e.record()
+            e.record(torch.cuda.current_stream(self.dev))
             _TIMER.records.append((self.ev, e, self.launches, self.pixels))
 
 
@@ -120,13 +196,26 @@ _WS_CACHE: dict = {}
 
 def workspace(floats: int, device, tag: str = "") -> torch.Tensor:
     """Grow-only per-(device, stream, tag) scratch buffer; stream-ordered reuse is safe because
-    every consumer is launched on the same stream."""
-    key = (str(device), _stream(), tag)
+    every consumer is launched on the same stream.  release_workspaces() drops them."""
+    device = torch.device(device)
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device(), _stream(device), tag)
     t = _WS_CACHE.get(key)
     if t is None or t.numel() < floats:
         t = torch.empty(max(floats, 1), dtype=torch.float32, device=device)
         _WS_CACHE[key] = t
     return t
+
+
+def release_workspaces(device=None) -> None:
+    """Drop the cached scratch buffers (of one device, or all): they are otherwise kept for the life of the process, keyed on
+    (device, stream), so a program that cycles through many streams should call this when a stream is retired."""
+    if device is None:
+        _WS_CACHE.clear()
+        return
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    for k in [k for k in _WS_CACHE if k[1] == idx]:
+        del _WS_CACHE[k]
 
 
 def plane_of(t: torch.Tensor) -> nat.Plane:
@@ -152,8 +241,15 @@ def pack_pu(params, out: torch.Tensor):
         if tuple(p.shape) != s:
             raise RuntimeError(f"PredictUpdate parameter has shape {tuple(p.shape)}, expected {s} (lifting_1d.py:28-34)")
     assert out.numel() == nat.PU_PACKED_FLOATS and out.is_contiguous()
-    nat.check(nat.lib().pmctf_pack_pu_weights(*[p.data_ptr() for p in ps], out.data_ptr(), _stream()), "pack_pu_weights")
+    _dev = _same_device(out, *ps)
+    _launch(_dev, "pack_pu_weights", nat.lib().pmctf_pack_pu_weights, *[p.data_ptr() for p in ps], out.data_ptr())
     return ps  # keep alive until the stream has consumed them
+
+
+def release_pu(packed: torch.Tensor, blocks: int = 1) -> None:
+    """Forget the parameters registered for `blocks` consecutive packed blocks (the owner is about to free or rewrite them)."""
+    for i in range(blocks):
+        nat.lib().pmctf_release_pu_weights(packed.data_ptr() + 4 * i * nat.PU_PACKED_FLOATS)
 
 
 def flow_warp(im: torch.Tensor, flow: torch.Tensor, sign: float = 1.0, lin_x=None, lin_y=None, round_out=False):
@@ -166,8 +262,9 @@ def flow_warp(im: torch.Tensor, flow: torch.Tensor, sign: float = 1.0, lin_x=Non
     lx = linspace_table(W, im.device) if lin_x is None else _chk(lin_x, "lin_x")
     ly = linspace_table(H, im.device) if lin_y is None else _chk(lin_y, "lin_y")
     out = torch.empty_like(im)
-    nat.check(nat.lib().pmctf_flow_warp(im.data_ptr(), flow.data_ptr(), lx.data_ptr(), ly.data_ptr(), out.data_ptr(),
-                                        N, Cc, H, W, flow.shape[0], sign, int(round_out), _stream()), "flow_warp")
+    _dev = _same_device(im, flow, lx, ly)
+    _launch(_dev, "flow_warp", nat.lib().pmctf_flow_warp, im.data_ptr(), flow.data_ptr(), lx.data_ptr(), ly.data_ptr(), out.data_ptr(),
+                                        N, Cc, H, W, flow.shape[0], sign, int(round_out))
     return out
 
 
@@ -179,20 +276,22 @@ def chroma_mv_down(mv: torch.Tensor):
     if two != 2:
         raise RuntimeError("mv must be [N,2,H,W]")
     out = torch.empty((N, 2, H // 2, W // 2), dtype=torch.float32, device=mv.device)
-    nat.check(nat.lib().pmctf_chroma_mv_down(mv.data_ptr(), out.data_ptr(), N, H, W, _stream()), "chroma_mv_down")
+    _dev = mv.device
+    _launch(_dev, "chroma_mv_down", nat.lib().pmctf_chroma_mv_down, mv.data_ptr(), out.data_ptr(), N, H, W)
     return out
 
 
-def predict_update(x: torch.Tensor, packed: torch.Tensor, in_mul: float = 1.0):
-    """PredictUpdate.forward: lifting_1d.py:36-49."""
+def predict_update(x: torch.Tensor, packed: torch.Tensor, in_mul: float = 1.0, conv_mode=None):
+    """PredictUpdate.forward: lifting_1d.py:36-49.  conv_mode: None/'default' | 'ffma' | 'tensor' for this call."""
     _no_grad_only(x)
     x = _chk(x, "x", 4).contiguous()
     N, Cc, H, W = x.shape
     if Cc != 1:
         raise RuntimeError("PredictUpdate on the hot path is single-channel (in_ch=1)")
     out = torch.empty_like(x)
-    nat.check(nat.lib().pmctf_predict_update(x.data_ptr(), packed.data_ptr(), in_mul, out.data_ptr(), N, H, W, _stream()),
-              "predict_update")
+    _dev = _same_device(x, packed)
+    _launch(_dev, "predict_update", nat.lib().pmctf_predict_update, x.data_ptr(), packed.data_ptr(), in_mul, out.data_ptr(), N, H, W,
+            conv_mode_code(conv_mode))
     return out
 
 
@@ -203,8 +302,8 @@ def temporal_filter(x: torch.Tensor, t: nat.Temporal, which: int):
     if Cc != 1:
         raise RuntimeError("TemporalLifting is single-channel")
     out = torch.empty_like(x)
-    nat.check(nat.lib().pmctf_temporal_filter(x.data_ptr(), C.byref(t), which, out.data_ptr(), N, H, W, _stream()),
-              "temporal_filter")
+    _dev = x.device
+    _launch(_dev, "temporal_filter", nat.lib().pmctf_temporal_filter, x.data_ptr(), C.byref(t), which, out.data_ptr(), N, H, W)
     return out
 
 
@@ -244,11 +343,12 @@ def forward_mctf(ref, cur, mv, t: nat.Temporal, mv_down=False, want_pred=True, l
     inv = torch.empty(ref.shape, dtype=torch.float32, device=ref.device) if want_pred else None
     pr, pc, pL, pH = plane_of(ref), plane_of(cur), plane_of(L), plane_of(Hh)
     pp, pi = (plane_of(pred), plane_of(inv)) if want_pred else (None, None)
-    with _timed(2, 2 * N * H * W):
-        nat.check(nat.lib().pmctf_forward_mctf(C.byref(pr), C.byref(pc), mv.data_ptr(), mv.shape[0], int(mv_down),
+    _dev = _same_device(ref, cur, mv, L, Hh, lx, ly)
+    with _timed(2, 2 * N * H * W, _dev):
+        _launch(_dev, "forward_mctf", nat.lib().pmctf_forward_mctf, C.byref(pr), C.byref(pc), mv.data_ptr(), mv.shape[0], int(mv_down),
                                                lx.data_ptr(), ly.data_ptr(), C.byref(t), C.byref(pL), C.byref(pH),
                                                C.byref(pp) if want_pred else None, C.byref(pi) if want_pred else None,
-                                               N, H, W, _stream()), "forward_mctf")
+                                               N, H, W)
     return L, Hh, pred, inv
 
 
@@ -263,10 +363,11 @@ def inverse_mctf(L, Hh, mv, t: nat.Temporal, mv_down=False, lin_x=None, lin_y=No
     ly = linspace_table(H, L.device) if lin_y is None else lin_y
     ref, cur = _out_like(L, out_ref, "out_ref"), _out_like(L, out_cur, "out_cur")
     pL, pH, pr, pc = plane_of(L), plane_of(Hh), plane_of(ref), plane_of(cur)
-    with _timed(2, 2 * N * H * W):
-        nat.check(nat.lib().pmctf_inverse_mctf(C.byref(pL), C.byref(pH), mv.data_ptr(), mv.shape[0], int(mv_down),
+    _dev = _same_device(L, Hh, mv, ref, cur, lx, ly)
+    with _timed(2, 2 * N * H * W, _dev):
+        _launch(_dev, "inverse_mctf", nat.lib().pmctf_inverse_mctf, C.byref(pL), C.byref(pH), mv.data_ptr(), mv.shape[0], int(mv_down),
                                                lx.data_ptr(), ly.data_ptr(), C.byref(t), C.byref(pr), C.byref(pc),
-                                               N, H, W, _stream()), "inverse_mctf")
+                                               N, H, W)
     return ref, cur
 
 
@@ -288,8 +389,9 @@ def iwave1d_forward(x: torch.Tensor, p: nat.IWave):
         h = torch.empty((N, 1, W, h2), dtype=torch.float32, device=x.device).permute(0, 1, 3, 2)
     ws = workspace(N * h2 * W, x.device, "iw1d")
     px, pl, ph = plane_of(x), plane_of(l), plane_of(h)
-    nat.check(nat.lib().pmctf_iwave1d_forward(C.byref(px), C.byref(p), C.byref(pl), C.byref(ph), N, h2, W,
-                                              ws.data_ptr(), ws.numel(), _stream()), "iwave1d_forward")
+    _dev = x.device
+    _launch(_dev, "iwave1d_forward", nat.lib().pmctf_iwave1d_forward, C.byref(px), C.byref(p), C.byref(pl), C.byref(ph), N, h2, W,
+                                              ws.data_ptr(), ws.numel())
     return l, h
 
 
@@ -306,8 +408,9 @@ def iwave1d_backward(l: torch.Tensor, h: torch.Tensor, p: nat.IWave):
         x = torch.empty((N, 1, W, 2 * h2), dtype=torch.float32, device=l.device).permute(0, 1, 3, 2)
     ws = workspace(2 * N * h2 * W, l.device, "iw1d")
     pl, ph, px = plane_of(l), plane_of(h), plane_of(x)
-    nat.check(nat.lib().pmctf_iwave1d_backward(C.byref(pl), C.byref(ph), C.byref(p), C.byref(px), N, h2, W,
-                                               ws.data_ptr(), ws.numel(), _stream()), "iwave1d_backward")
+    _dev = _same_device(l, h)
+    _launch(_dev, "iwave1d_backward", nat.lib().pmctf_iwave1d_backward, C.byref(pl), C.byref(ph), C.byref(p), C.byref(px), N, h2, W,
+                                               ws.data_ptr(), ws.numel())
     return x
 
 
@@ -321,12 +424,13 @@ def lift2d_forward(x: torch.Tensor, p: nat.IWave, want_lh_rows: bool = False):
     bands = torch.empty((4, N, 1, H // 2, W // 2), dtype=torch.float32, device=x.device)
     rows = torch.empty((2, N, 1, H // 2, W), dtype=torch.float32, device=x.device) if want_lh_rows else None
     ws = workspace(2 * N * H * W, x.device, "l2d")
-    with _timed(8, 4 * N * H * W):  # 4 row steps on N*H/2*W px + 4 column steps on 2N*W/2*H/2 px
-        nat.check(nat.lib().pmctf_lift2d_forward(x.data_ptr(), C.byref(p), bands[0].data_ptr(), bands[1].data_ptr(),
+    _dev = x.device
+    with _timed(8, 4 * N * H * W, _dev):  # 4 row steps on N*H/2*W px + 4 column steps on 2N*W/2*H/2 px
+        _launch(_dev, "lift2d_forward", nat.lib().pmctf_lift2d_forward, x.data_ptr(), C.byref(p), bands[0].data_ptr(), bands[1].data_ptr(),
                                                  bands[2].data_ptr(), bands[3].data_ptr(),
                                                  rows[0].data_ptr() if want_lh_rows else None,
                                                  rows[1].data_ptr() if want_lh_rows else None,
-                                                 N, H, W, ws.data_ptr(), ws.numel(), _stream()), "lift2d_forward")
+                                                 N, H, W, ws.data_ptr(), ws.numel())
     d = {"ll": bands[0], "lh": bands[1], "hl": bands[2], "hh": bands[3]}
     if want_lh_rows:  # the reference returns the transposed views (wavelet_transform.py:32,37,42)
         d["l"], d["h"] = rows[0].permute(0, 1, 3, 2), rows[1].permute(0, 1, 3, 2)
@@ -346,10 +450,10 @@ def lift2d_backward(ll, lh, hl, hh, p: nat.IWave, ll_div: float = 1.0, q: float 
     H, W = 2 * h2, 2 * w2
     x = torch.empty((N, 1, H, W), dtype=torch.float32, device=ts[0].device)
     ws = workspace(2 * N * H * W, x.device, "l2d")
-    with _timed(8, 4 * N * H * W):
-        nat.check(nat.lib().pmctf_lift2d_backward_q(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(),
-                                                    ll_div, q, C.byref(p), x.data_ptr(), N, H, W, ws.data_ptr(), ws.numel(),
-                                                    _stream()), "lift2d_backward")
+    _dev = _same_device(*ts)
+    with _timed(8, 4 * N * H * W, _dev):
+        _launch(_dev, "lift2d_backward", nat.lib().pmctf_lift2d_backward_q, ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(),
+                                                    ll_div, q, C.byref(p), x.data_ptr(), N, H, W, ws.data_ptr(), ws.numel())
     return x
 
 
@@ -360,8 +464,8 @@ def quantize(s: torch.Tensor, q: float, clip: float = 8192.0, lossy: bool = True
     out = torch.empty_like(s)
     if s.numel() == 0:
         return out
-    nat.check(nat.lib().pmctf_quantize(s.data_ptr(), q, clip, int(lossy), int(do_round), out.data_ptr(), s.numel(), _stream()),
-              "quantize")
+    _dev = s.device
+    _launch(_dev, "quantize", nat.lib().pmctf_quantize, s.data_ptr(), q, clip, int(lossy), int(do_round), out.data_ptr(), s.numel())
     return out
 
 
@@ -372,7 +476,8 @@ def dequantize(s_hat: torch.Tensor, q: float, lossy: bool = True):
     out = torch.empty_like(s_hat)
     if s_hat.numel() == 0:
         return out
-    nat.check(nat.lib().pmctf_dequantize(s_hat.data_ptr(), q, int(lossy), out.data_ptr(), s_hat.numel(), _stream()), "dequantize")
+    _dev = s_hat.device
+    _launch(_dev, "dequantize", nat.lib().pmctf_dequantize, s_hat.data_ptr(), q, int(lossy), out.data_ptr(), s_hat.numel())
     return out
 
 
@@ -386,8 +491,9 @@ def quantize_stats(s: torch.Tensor, q: float, stats: torch.Tensor, clip: float =
         return out
     if stats.dtype != torch.int64 or not stats.is_cuda or not stats.is_contiguous() or stats.numel() < 2 * planes:
         raise RuntimeError("stats must be a contiguous CUDA int64 tensor with 2 entries per plane")
-    nat.check(nat.lib().pmctf_quantize_stats(s.data_ptr(), q, clip, int(lossy), out.data_ptr(), planes, s.numel() // planes,
-                                             stats.data_ptr(), _stream()), "quantize_stats")
+    _dev = _same_device(s, stats)
+    _launch(_dev, "quantize_stats", nat.lib().pmctf_quantize_stats, s.data_ptr(), q, clip, int(lossy), out.data_ptr(), planes, s.numel() // planes,
+                                             stats.data_ptr())
     return out
 
 
@@ -401,7 +507,8 @@ def unpack_u8(src: torch.Tensor, hp: int, wp: int, out: Optional[torch.Tensor] =
         out = torch.empty((n, 1, hp, wp), dtype=torch.float32, device=src.device)
     elif out.numel() != n * hp * wp or not out.is_contiguous() or out.dtype != torch.float32:
         raise RuntimeError("unpack_u8: bad output buffer")
-    nat.check(nat.lib().pmctf_unpack_u8(src.data_ptr(), out.data_ptr(), n, h0, w0, hp, wp, _stream()), "unpack_u8")
+    _dev = _same_device(src, out)
+    _launch(_dev, "unpack_u8", nat.lib().pmctf_unpack_u8, src.data_ptr(), out.data_ptr(), n, h0, w0, hp, wp)
     return out
 
 
@@ -417,6 +524,6 @@ def frame_sse(rec: torch.Tensor, orig_u8: torch.Tensor, sse: Optional[torch.Tens
         raise RuntimeError(f"frame_sse: {tuple(rec.shape)} does not hold {n} planes")
     if sse is None:
         sse = torch.zeros(n, dtype=torch.int64, device=rec.device)
-    nat.check(nat.lib().pmctf_frame_sse(rec.data_ptr(), orig_u8.data_ptr(), n, h0, w0, hp, wp, sse.data_ptr(), _stream()),
-              "frame_sse")
+    _dev = _same_device(rec, orig_u8, sse)
+    _launch(_dev, "frame_sse", nat.lib().pmctf_frame_sse, rec.data_ptr(), orig_u8.data_ptr(), n, h0, w0, hp, wp, sse.data_ptr())
     return sse

@@ -39,8 +39,8 @@ def _conv_raw(x, w, b):
     if tuple(w.shape) != (cout, cin, 3, 3):
         raise RuntimeError(f"conv3x3: weight {tuple(w.shape)} does not match input channels {cin}")
     y = torch.empty((N, cout, H, W), dtype=torch.float32, device=x.device)
-    nat.check(nat.lib().pmctf_conv3x3(x.data_ptr(), w.data_ptr(), b.contiguous().data_ptr() if b is not None else None, y.data_ptr(),
-                                      N, cin, cout, H, W, ops._stream()), "conv3x3")
+    ops._launch(ops._same_device(x, w, b), "conv3x3", nat.lib().pmctf_conv3x3, x.data_ptr(), w.data_ptr(),
+                b.contiguous().data_ptr() if b is not None else None, y.data_ptr(), N, cin, cout, H, W)
     return y
 
 
@@ -65,9 +65,8 @@ class _Conv3x3(torch.autograd.Function):
             cout = w.size(0)
             gw = torch.zeros_like(w)
             gb = torch.zeros(cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
-            nat.check(nat.lib().pmctf_conv3x3_wgrad(x.contiguous().data_ptr(), g.data_ptr(), gw.data_ptr(),
-                                                    gb.data_ptr() if gb is not None else None, N, cin, cout, H, W, ops._stream()),
-                      "conv3x3_wgrad")
+            ops._launch(ops._same_device(x, g), "conv3x3_wgrad", nat.lib().pmctf_conv3x3_wgrad, x.contiguous().data_ptr(), g.data_ptr(),
+                        gw.data_ptr(), gb.data_ptr() if gb is not None else None, N, cin, cout, H, W)
         return gx, gw, gb
 
 
@@ -93,9 +92,9 @@ class _FlowWarp(torch.autograd.Function):
         gim = torch.zeros_like(im) if ctx.needs_input_grad[0] else None
         gfl = torch.zeros_like(flow) if ctx.needs_input_grad[1] else None
         lx, ly = ops.linspace_table(W, im.device), ops.linspace_table(H, im.device)
-        nat.check(nat.lib().pmctf_flow_warp_bwd(g.data_ptr(), im.data_ptr(), flow.data_ptr(), lx.data_ptr(), ly.data_ptr(),
-                                                gim.data_ptr() if gim is not None else None, gfl.data_ptr() if gfl is not None else None,
-                                                N, Cc, H, W, flow.size(0), 1.0, ops._stream()), "flow_warp_bwd")
+        ops._launch(ops._same_device(g, im, flow), "flow_warp_bwd", nat.lib().pmctf_flow_warp_bwd, g.data_ptr(), im.data_ptr(),
+                    flow.data_ptr(), lx.data_ptr(), ly.data_ptr(), gim.data_ptr() if gim is not None else None,
+                    gfl.data_ptr() if gfl is not None else None, N, Cc, H, W, flow.size(0), 1.0)
         return gim, gfl
 
 

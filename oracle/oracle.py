@@ -311,12 +311,13 @@ def symbol_stats(hat):
     return st
 
 
-def code_gop(Y, C, mvs, temporal, hp_w: IWave, lp_w: IWave, q_hp, q_lp, num_me_stages=4):
+def code_gop(Y, C, mvs, temporal, hp_w: IWave, lp_w: IWave, q_hp, q_lp, num_me_stages=4, trace=None):
     """The reference's GOP loop restricted to the hot path, one pair at a time in its own order
     (test_pMCTF_flex.py:131-291): stage s pairs frame g*2^(s+1) with +2^s; H frames are coded with the hp
     transform (step pair q_hp[s]), the final L with the lp transform; temporal decoding in reverse.
     Y [G,1,H,W]; C [G,2,1,h,w]; mvs[s] [pairs,2,H,W]; temporal[i] = (P_t, U_t).
-    -> (rec_Y, rec_C, sym_stats int64 [G,2])."""
+    -> (rec_Y, rec_C, sym_stats int64 [G,2]).  `trace` (a dict) receives the temporal subbands before coding:
+    trace["H"][frame] = (H_y, H_c) of every high-pass frame, trace["L"] = (L_y, L_c) of the final low-pass frame."""
     Y, C = _a(Y).copy(), _a(C).copy()
     G = Y.shape[0]
     S = int(round(math.log2(G)))
@@ -338,7 +339,11 @@ def code_gop(Y, C, mvs, temporal, hp_w: IWave, lp_w: IWave, q_hp, q_lp, num_me_s
             sym[c] += symbol_stats(hat)[0] + symbol_stats(hatc).sum(0)
             fy[r], fc[r] = L, Lc
             coded[c] = (Hh_hat, Hc_hat, mv)
+            if trace is not None:
+                trace.setdefault("H", {})[c] = (Hh, Hc)
     q, qll = q_lp
+    if trace is not None:
+        trace["L"] = (fy[0], fc[0])
     L_hat, hat = spatial_wavelet_dec(fy[0], lp_w, q, qll)
     Lc_hat, hatc = spatial_wavelet_dec(fc[0], lp_w, q, qll)
     sym[0] += symbol_stats(hat)[0] + symbol_stats(hatc).sum(0)

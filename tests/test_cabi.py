@@ -38,17 +38,20 @@ def test_library_exports_every_declared_symbol():
         assert name in pkg._native.SIGNATURES, f"{name} has no ctypes signature"
         assert len(pkg._native.SIGNATURES[name]) == nargs, f"{name}: header has {nargs} args, binding has {len(pkg._native.SIGNATURES[name])}"
     assert set(pkg._native.SIGNATURES) == set(fns), "binding table and header disagree"
-    assert lib.pmctf_abi_version() == 1
+    assert lib.pmctf_abi_version() == 2
     lib.pmctf_error_string.restype = ctypes.c_char_p
     assert b"invalid argument" in lib.pmctf_error_string(-1)
+    assert b"gave up" in lib.pmctf_error_string(-4)          # PMCTF_ETIMEOUT
 
 
 def test_struct_layouts_match_header():
     # sizes implied by the header's field lists on LP64
     n = pkg._native
     assert ctypes.sizeof(n.Plane) == 48
-    assert ctypes.sizeof(n.Temporal) == 32
-    assert ctypes.sizeof(n.IWave) == 4 * 3 * 4 + 4 * 4 + 8 + 4 * 4
+    assert ctypes.sizeof(n.Temporal) == 32                   # 2 pointers, 2 floats, lossy, conv_mode
+    assert ctypes.sizeof(n.IWave) == 4 * 3 * 4 + 4 * 4 + 8 + 4 * 4 + 8   # + conv_mode (+ tail padding)
+    assert n.Step.conv_mode.offset == n.Step.aux_mul.offset + 4 and n.IWave.conv_mode.offset == 88 and n.Temporal.conv_mode.offset == 28
+    assert (n.CONV_DEFAULT, n.CONV_FFMA, n.CONV_TENSOR) == (0, 1, 2)   # a zeroed descriptor means "process default"
     assert n.PU_PACKED_FLOATS == 10128
 
 

@@ -117,7 +117,8 @@ def test_code_gop_vs_oracle(P, model, weights, gop, h0, w0):
 
 
 def test_gop16_1080p_properties(P, model):
-    """BASELINE.json full size (C3): one 1080p GOP-16.  Size-independent properties: with a very fine quantiser the
+    """BASELINE.json full size (C3): one 1080p GOP-16, PROPERTY checks only (the parity test proper is
+    test_config2_gop16_1080p_vs_oracle below).  Size-independent properties: with a very fine quantiser the
     whole analysis -> code -> synthesis chain is near-lossless, statistics are consistent, and coarser steps
     give fewer symbols and more distortion."""
     from learned_pmctf_b200 import gop as Gm
@@ -140,6 +141,92 @@ def test_gop16_1080p_properties(P, model):
     Ly, Lc, Hs = codec.analysis(Y, C, mvs)
     ry, rc = codec.synthesis(Ly, Lc, Hs, mvs)
     assert float((ry - Y).abs().max()) <= 2e-3 and float((rc - C).abs().max()) <= 2e-3
+
+
+def _adversarial_motion(mvs):
+    """SURVEY.md section 8d (ii) on top of the N(0, 4^2) fields: saturated +-32 px blocks, and 64 px vectors pointing out of the
+    frame along all four borders (border clamping of the warp, video_net.py:47-50)."""
+    mvs = [m.clone() for m in mvs]
+    f = mvs[0]
+    f[0, 0, :, :96] = -64.0          # left border, pointing left
+    f[0, 0, :, -96:] = 64.0          # right border, pointing right
+    f[1, 1, :96, :] = -64.0          # top border, pointing up
+    f[1, 1, -96:, :] = 64.0          # bottom border (inside the zero padding rows), pointing down
+    f[2, :, 300:600, 500:900] = 32.0
+    f[3, :, 300:600, 500:900] = -32.0
+    mvs[-1][0, 0, 200:400, 100:1800] = 32.0       # coarsest stage (temporal module set 3)
+    mvs[-1][0, 1, 700:1100, 100:1800] = -64.0
+    return mvs
+
+
+def test_config2_gop16_1080p_vs_oracle(P, model, weights, conv_mode):
+    """configs[2] at its own size: ONE 1080p GOP-16 (1152x1920 luma, [16,2,1,576,960] chroma, 8/4/2/1 motion fields incl. the
+    +-32 px and out-of-frame cases, all four temporal module sets, q_index 12) through GopCodec -- every temporal subband frame
+    (H of each stage, final L), the reconstruction and the symbol / distortion statistics BIT-EXACT against the oracle's
+    pair-by-pair restatement of test_pMCTF_flex.py:131-291 / pMCTF_L.py:297-330."""
+    if conv_mode == "ffma":
+        pytest.skip("full-size oracle run once (tensor mode = the default contract); ffma is covered at the smaller sizes")
+    from learned_pmctf_b200 import gop as Gm
+    G, h0, w0, hp, wp = 16, 1080, 1920, 1152, 1920
+    y, c = Gm.synthetic_sequence(0, G, h0, w0, "cuda")
+    mvs = _adversarial_motion(Gm.synthetic_motion(0, 0, G, hp, wp, "cuda"))
+    assert [m.shape[0] for m in mvs] == [8, 4, 2, 1] and float(mvs[0].abs().max()) == 64.0
+    Y = P.ops.unpack_u8(y, hp, wp)
+    C = P.ops.unpack_u8(c.view(-1, h0 // 2, w0 // 2), hp // 2, wp // 2).view(G, 2, 1, hp // 2, wp // 2)
+    codec = Gm.GopCodec(model, G, q_index=12)
+    assert model.num_me_stages == 4 and codec.stages == 4
+    Ly, Lc, Hs = codec.analysis(Y, C, mvs)                       # the temporal subbands as coded
+    rec_y, rec_c, st = codec.code_gop(Y, C, mvs, y, c)
+    torch.cuda.synchronize()
+    temporal, hp_w, lp_w = _oracle_weights(weights)
+    q_hp = [codec.q_pair("hp", s) for s in range(4)]
+    assert len(set(q_hp)) == 4
+    trace = {}
+    y_np, c_np = y.cpu().numpy(), c.cpu().numpy()
+    oy, oc, osym = orc.code_gop(orc.unpack_u8(y_np, hp, wp)[:, None], orc.unpack_u8(c_np, hp // 2, wp // 2)[:, :, None],
+                                [m.cpu().numpy() for m in mvs], temporal, hp_w, lp_w, q_hp, codec.q_pair("lp", 0), trace=trace)
+    # temporal analysis: every H frame of every stage, and the final low-pass frame
+    for s, pairs in enumerate(Gm.dyadic_schedule(G)):
+        Hy, Hc = Hs[s]
+        for g, (_, cur) in enumerate(pairs):
+            assert np.array_equal(Hy[g:g + 1].cpu().numpy(), trace["H"][cur][0]), f"H luma, stage {s} pair {g}"
+            assert np.array_equal(Hc[g].cpu().numpy(), trace["H"][cur][1]), f"H chroma, stage {s} pair {g}"
+    assert np.array_equal(Ly.cpu().numpy(), trace["L"][0]) and np.array_equal(Lc[0].cpu().numpy(), trace["L"][1])
+    # reconstruction + statistics
+    assert np.array_equal(rec_y.cpu().numpy(), oy), f"luma: max diff {np.abs(rec_y.cpu().numpy() - oy).max()}"
+    assert np.array_equal(rec_c.cpu().numpy(), oc), f"chroma: max diff {np.abs(rec_c.cpu().numpy() - oc).max()}"
+    st = st.cpu().numpy()
+    assert np.array_equal(st[:, 1:3].astype(np.int64), osym)
+    assert np.array_equal(st[:, 3].astype(np.int64), orc.frame_sse(oy[:, 0], y_np))
+    assert np.array_equal(st[:, 4:6].astype(np.int64), orc.frame_sse(oc[:, :, 0], c_np))
+
+
+def test_mctf_1080p_standalone_vs_oracle(P, model, weights, conv_mode):
+    """forward_MCTF / inverse_MCTF on one 1152x1920 luma pair and one [2,1,576,960] chroma pair (mv_down: the fused 2x2-mean/2 of
+    the luma field) with out-of-frame vectors, incl. the pred / inv outputs -- bit-exact vs the oracle (pMCTF_L.py:297-330)."""
+    if conv_mode == "ffma":
+        pytest.skip("full-size oracle run once (tensor mode)")
+    from learned_pmctf_b200 import gop as Gm
+    hp, wp = 1152, 1920
+    y, c = Gm.synthetic_sequence(1, 2, 1080, 1920, "cuda")
+    Y = P.ops.unpack_u8(y, hp, wp)
+    C = P.ops.unpack_u8(c.view(-1, 540, 960), hp // 2, wp // 2).view(2, 2, 1, hp // 2, wp // 2)
+    mv = _adversarial_motion(Gm.synthetic_motion(1, 0, 16, hp, wp, "cuda"))[0][:1].contiguous()
+    Pt, Ut = _oracle_weights(weights)[0][2]
+    L, H, pred, inv = model.forward_MCTF(Y[0:1], Y[1:2], mv, stage_idx=2)
+    oL, oH, opred, oinv = orc.forward_mctf(Y[0:1].cpu().numpy(), Y[1:2].cpu().numpy(), mv.cpu().numpy(), Pt, Ut)
+    for a, b, n in ((L, oL, "L"), (H, oH, "H"), (pred, opred, "pred"), (inv, oinv, "inv")):
+        assert np.array_equal(a.cpu().numpy(), b), n
+    r, cu_ = model.inverse_MCTF(L, H, mv, stage_idx=2)
+    orr, occ = orc.inverse_mctf(oL, oH, mv.cpu().numpy(), Pt, Ut)
+    assert np.array_equal(r.cpu().numpy(), orr) and np.array_equal(cu_.cpu().numpy(), occ)
+    Lc, Hc, _, _ = model.forward_MCTF(C[0], C[1], mv, stage_idx=2, mv_down=True)
+    omv = orc.chroma_mv_down(mv.cpu().numpy())
+    oLc, oHc, _, _ = orc.forward_mctf(C[0].cpu().numpy(), C[1].cpu().numpy(), omv, Pt, Ut)
+    assert np.array_equal(Lc.cpu().numpy(), oLc) and np.array_equal(Hc.cpu().numpy(), oHc)
+    rc, cc = model.inverse_MCTF(Lc, Hc, mv, downscale=True, stage_idx=2)
+    orc_, occ_ = orc.inverse_mctf(oLc, oHc, mv.cpu().numpy(), Pt, Ut, downscale=True)
+    assert np.array_equal(rc.cpu().numpy(), orc_) and np.array_equal(cc.cpu().numpy(), occ_)
 
 
 # ---- BASELINE.json configs as parity cases at their own sizes ---------------------------------------------------
