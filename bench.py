@@ -175,6 +175,113 @@ def run_reference(args):
     emit(line)
 
 
+def measure_int8_peak(dev, seconds=2.0):
+    """Dense int8 tensor-core peak of THIS GPU, measured the way MEASURED_PEAKS.json measures bf16: torch._int_mm (cuBLASLt) on
+    8192^3, best of 10 (burst) and back to back for `seconds` (sustained).  TOPS = 2 N^3 / t.  Library call = the yardstick,
+    nothing on the hot path uses it."""
+    import torch
+    try:
+        n = 8192
+        a = torch.randint(-128, 127, (n, n), dtype=torch.int8, device=dev)
+        b = torch.randint(-128, 127, (n, n), dtype=torch.int8, device=dev)
+        for _ in range(3):
+            torch._int_mm(a, b)
+        torch.cuda.synchronize(dev)
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps, t0 = 0, time.perf_counter()
+        e0.record()
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(20):
+                torch._int_mm(a, b)
+            reps += 20
+            torch.cuda.synchronize(dev)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return {"burst_tops": 2 * n ** 3 / (best * 1e-3) / 1e12, "sustained_tops": reps * 2 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                "how": "torch._int_mm int8 8192^3 on this GPU inside bench.py: best of 10 (burst), back to back for 2 s (sustained)"}
+    except Exception as ex:   # no int8 GEMM in this torch build: say so instead of quoting a nominal figure as if measured
+        return {"burst_tops": None, "sustained_tops": None, "how": f"unavailable: {ex}"}
+
+
+def profiled_traffic():
+    """dram bytes per launch of the dominant kernel from THIS round's ncu --set full capture (tools/refresh_profiles.sh writes
+    profiles/<tag>_traffic.json beside the summary it was read from).  None when no such artifact exists."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        for f in sorted(os.listdir(pdir)):
+            if f.endswith("_traffic.json") and f.startswith("r2"):
+                best = os.path.join(pdir, f)
+        if best:
+            with open(best) as fh:
+                d = json.load(fh)
+            d["artifact"] = os.path.relpath(best, ROOT)
+            return d
+    except Exception:
+        pass
+    return None
+
+
+def run_uvg(args, pkg, G, par, model, dev, rank, world):
+    """BASELINE configs[3] as written: 7 synthetic 1080p sequences x 96 frames (6 GOP-16s each) x the q_index list of
+    test_pMCTF_flex.py:436-443, FLATTENED into 252 work items (q_index, sequence, gop), sharded round-robin over the ranks
+    (parallel.shard), no data-path collective, ONE gather of the per-frame statistics at the end (parallel.gather_stats,
+    test_pMCTF_flex.py:455-498).  Strong scaling: the total work is fixed.  8-bit frames and motion fields are resident on
+    the device; unpack + padding is inside the timed region."""
+    import torch
+    n_seq, q_list = args.uvg_sequences, [0, 4, 8, 12, 16, 20]
+    n_gops = FRAMES // GOP
+    items = par.work_items(q_list, n_seq, n_gops)
+    mine = par.shard(items, rank, world)
+    _, pr, _, pb = G.get_padding_size(H0, W0, 128)
+    hp, wp = H0 + pb, W0 + pr
+    seqs = {s: G.synthetic_sequence(s, FRAMES, H0, W0, dev) for s in sorted({s for _, s, _ in mine})}
+    mvs = {(s, g): G.synthetic_motion(s, g, GOP, hp, wp, dev) for s, g in sorted({(s, g) for _, s, g in mine})}
+    codecs = {q: G.GopCodec(model, GOP, q_index=q, concurrent_chroma=not args.single_stream) for q in q_list}
+
+    def one(item):
+        q, s, g = item
+        y, c = seqs[s]
+        yd, cd = y[g * GOP:(g + 1) * GOP], c[g * GOP:(g + 1) * GOP]
+        Y = pkg.ops.unpack_u8(yd, hp, wp)
+        C = pkg.ops.unpack_u8(cd.reshape(-1, H0 // 2, W0 // 2), hp // 2, wp // 2).view(GOP, 2, 1, hp // 2, wp // 2)
+        return codecs[q].code_gop(Y, C, mvs[(s, g)], yd, cd)[2]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    if mine:
+        one(mine[0])   # warm-up (allocator pools of this shape are already warm from the headline run)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    local = [one(it) for it in mine]
+    local = torch.stack(local) if local else torch.zeros((0, GOP, G.N_STATS), dtype=torch.float64, device=dev)
+    allst = par.gather_stats(local, len(items), rank, world)          # the ONE collective of the run
+    e1.record()
+    barrier()
+    pkg.ops.check_tc_error(dev, "uvg workload")
+    ms = par.max_over_ranks(e0.elapsed_time(e1), dev)
+    cap = par.max_items_per_rank(len(items), world)
+    psnr = allst[:, :, 6]
+    return {"workload": f"configs[3]: {n_seq} synthetic 1080p sequences x {FRAMES} frames, GOP-16, q_index {q_list} flattened into "
+                        f"{len(items)} items (q, sequence, gop), round-robin over {world} GPU(s), one gather of [items,16,{G.N_STATS}] fp64 at the end",
+            "frames_per_s": len(items) * GOP / (ms * 1e-3), "unit": "frames/s", "scaling": "strong", "seconds": ms * 1e-3,
+            "items": len(items), "items_max_per_rank": cap, "load_balance": len(items) / (world * cap),
+            "mean_psnr_yuv_db_by_q_index": {str(q): float(psnr[[i for i, it in enumerate(items) if it[0] == q]][torch.isfinite(
+                psnr[[i for i, it in enumerate(items) if it[0] == q]])].mean()) for q in q_list}}
+
+
 # --------------------------------------------------------------------------------------------------
 def build_model(pkg, dev):
     """Random-init pMCTF(num_me_stages=4) made non-degenerate (SURVEY.md 'Random-init degeneracy'): 3x3 conv weights
@@ -327,8 +434,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--single-stream", action="store_true", help="luma and chroma chains on one stream (ncu launch lists, A/B runs)")
     ap.add_argument("--conv-mode", default="tensor", choices=["tensor", "ffma"])
-    ap.add_argument("--torch-baseline", action="store_true",
-                    help="also time the same hot path written with stock torch ops (cuDNN / grid_sample) on this GPU; informational")
+    ap.add_argument("--torch-baseline", action="store_true", help="(kept for compatibility: the stock-torch GPU baseline is part of the default line now)")
+    ap.add_argument("--no-torch-baseline", action="store_true",
+                    help="skip timing the same hot path written with stock torch ops (cuDNN TF32 / fp32, grid_sample) on this GPU")
+    ap.add_argument("--no-uvg", action="store_true", help="skip the configs[3] block (7 sequences x 6 GOPs x 6 q_index points, strong scaling)")
+    ap.add_argument("--uvg-sequences", type=int, default=7)
+    ap.add_argument("--no-int8-peak", action="store_true", help="skip measuring the int8 dense peak of this GPU")
     ap.add_argument("--workload", default="gop16", choices=["gop16", "train"],
                     help="gop16: the headline metric (default); train: BASELINE configs[4] training step (not the headline)")
     args = ap.parse_args()
@@ -422,23 +533,31 @@ def main():
         yh, ch = y_u8.cpu().pin_memory(), c_u8.cpu().pin_memory()
         mvh = [[t.cpu().pin_memory() for t in g] for g in mvs]
         h2d = yh.numel() + ch.numel() + sum(t.numel() * 4 for g in mvh for t in g)
-        d2h = n_frames * G.N_STATS * 8
-        codec.code_sequence_host(yh, ch, mvh)
+        # the path's product comes back to the host: per-frame statistics AND the int16 symbols of every coded plane (what the
+        # reference hands to its entropy coder, entropy_models.py:37-40), copied GOP by GOP into pinned buffers
+        d2h = n_frames * G.N_STATS * 8 + n_frames * (hp * wp + 2 * (hp // 2) * (wp // 2)) * 2
+        codec.code_sequence_host(yh, ch, mvh, return_symbols=True)
         ke = max(1, min(K, 3))
         barrier()
         t0 = time.perf_counter()
         for _ in range(ke):
-            host_stats = codec.code_sequence_host(yh, ch, mvh)
+            host_stats, host_sym = codec.code_sequence_host(yh, ch, mvh, return_symbols=True)
         torch.cuda.synchronize()
         t_e2e = (time.perf_counter() - t0) / ke
         t_e2e = par.max_over_ranks(t_e2e * 1e3, dev) * 1e-3
         e2e = {"value": world * n_frames / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "steps": ke, "ms_per_step": 1e3 * t_e2e, "timing": "host wall clock around the public call incl. final D2H sync, max over ranks"}
+               "steps": ke, "ms_per_step": 1e3 * t_e2e, "timing": "host wall clock around the public call incl. final D2H sync, max over ranks",
+               "returns": "per-frame statistics + int16 quantised symbols of every coded plane in pinned host memory",
+               "symbols_nonzero_on_host": int((host_sym["y"][:GOP] != 0).sum())}
         assert torch.equal(host_stats.to(torch.float64)[:, :6], stats[rank].reshape(-1, G.N_STATS).cpu()[:, :6]), \
             "host-buffer path and resident path disagree"
 
+    uvg = None
+    if not args.no_uvg and args.frames == FRAMES:
+        uvg = run_uvg(args, pkg, G, par, model, dev, rank, world)
+    pkg.ops.check_tc_error(dev, "bench.py")
     torch_gpu = None
-    if args.torch_baseline and rank == 0:
+    if not args.no_torch_baseline and world == 1 and args.workload == "gop16":   # like cpu_baseline: at N = 1 only
         # what the reference dispatches to on this GPU: stock ATen / cuDNN ops (PyTorch default: TF32 convolutions allowed)
         from baseline import torch_stock as TS
         Yb = pkg.ops.unpack_u8(y_u8[:GOP], hp, wp)
@@ -484,20 +603,36 @@ def main():
                                        "around those launches (events on the launching stream inside the timed region)"}
     if mode == "tensor":
         # executed int8 tensor-core work: per 16x32 tile 12 blocks x (13 MMAs 128x48x32 + 1 MMA 128x64x32), 2 ops per MAC
+        # (continuation tiles run 10 blocks; the figure below is the upper one of a first-of-column tile)
         ops_per_px = 12 * (13 * 128 * 48 * 32 + 128 * 64 * 32) * 2 / 512.0
+        tr = profiled_traffic()
+        if tr is not None:
+            roofline["traffic"] = tr.get("dram_bytes_per_launch")
+            roofline["traffic_note"] = (f"dram__bytes_read.sum + dram__bytes_write.sum of one launch, read from {tr['artifact']} (this round's ncu --set "
+                                        f"full capture: {tr.get('what', '')}); algorithmic bytes of that launch {tr.get('algorithmic_bytes')}")
+        else:
+            roofline["traffic_note"] = "null: no ncu capture of this round under profiles/ (never a constant copied from an older run)"
+        i8 = None if (args.no_int8_peak or world > 1) else measure_int8_peak(dev)
         roofline.update({
             "kernel": "lift_step_tc_kernel<PLANE|WARP|SKIP3>: warp/skip + PredictUpdate CNN + lifting accumulate; conv2/conv3 as exact "
                       "int8 digit-split implicit GEMMs on tcgen05 (UTCIMMA, accumulators in TMEM), conv1/conv4/tanh on CUDA cores",
-            "traffic": 35.5e6,
-            "traffic_note": "dram__bytes_read+write of ONE launch from ncu --set full (profiles/r1z_lift_step_tc_ncu.txt): the 1080p luma "
-                            "temporal step, 2.21 Mpx, algorithmic 44.2 MB (20 B/px); outputs stay in the 126 MB L2, so DRAM traffic is "
-                            "below the algorithmic bytes -- no wasted re-reads.  Not measured live.",
             "executed_int8_tops": ks["pixels"] * ops_per_px / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
-            "executed_int8_ops_per_px": ops_per_px, "int8_dense_peak_tops_nominal": 4500.0,
+            "executed_int8_ops_per_px": ops_per_px,
+            "int8_dense_peak_tops_measured": i8,
+            "executed_int8_frac_of_measured_sustained": (ks["pixels"] * ops_per_px / (k_ms * 1e-3) / 1e12 / i8["sustained_tops"])
+            if (i8 and i8.get("sustained_tops") and k_ms > 0) else None,
+            "exactness_ceiling": {"digit_products_per_mac": 9, "executed_over_algorithmic": ops_per_px / pkg.ops.PU_FLOPS_PER_PX,
+                                  "max_algorithmic_tflops_at_measured_int8_peak": (i8["sustained_tops"] / (ops_per_px / pkg.ops.PU_FLOPS_PER_PX))
+                                  if (i8 and i8.get("sustained_tops")) else None,
+                                  "max_frac_of_bf16_peak": (i8["sustained_tops"] / (ops_per_px / pkg.ops.PU_FLOPS_PER_PX) / pk["tf_sustained"])
+                                  if (i8 and i8.get("sustained_tops")) else None,
+                                  "note": "the bit-exact contract evaluates every 16->16 MAC as 9 int8 digit products (plus the tile halo), so even a "
+                                          "kernel that ran the tensor cores at their measured int8 peak could not exceed this algorithmic rate; "
+                                          "`frac` is quoted against the bf16 peak as SURVEY.md section 8d prescribes"},
             "note": "9 digit products per MAC (3 byte digits per operand) make the convolution exact, so executed tensor work is "
                     "~13.5x the algorithmic FLOPs; with N = 48 the MMA rate is set by the operand fetch from shared memory (~42 cycles per "
-                    "128x48x32 MMA measured), and the kernel as a whole by the shared-memory data pipe, which the tensor-core operand "
-                    "fetch and the CUDA-core loads/stores share (~90 % busy, profiles/r1z_lift_step_tc_ncu.txt)"})
+                    "128x48x32 MMA measured); what bounds the kernel is the CUDA-core work around the MMAs (tanh, digit split, exact "
+                    "recombination): a build WITHOUT the MMAs is only 22 % faster (profiles/r2_whatif.txt)"})
     else:
         roofline.update({
             "kernel": "lift_step_kernel<PLANE|WARP|SKIP3> (warp/skip + PredictUpdate CNN + lifting accumulate, fp32 FFMA chains on CUDA cores)",
@@ -523,7 +658,7 @@ def main():
                        "streams": "1" if args.single_stream else "2 per GPU: luma chain | chroma chain (independent on the path)",
                        "parallelism": f"gop-sharded dp{world}, all_gather of per-frame statistics per step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "torch_gpu_baseline": torch_gpu,
+            "torch_gpu_baseline": torch_gpu, "uvg": uvg,
             "quality": {"mean_psnr_yuv_db": float(psnr[torch.isfinite(psnr)].mean()), "frames": int(psnr.numel())}}
     emit(line)
     if world > 1:

@@ -235,6 +235,15 @@ int pmctf_dequantize(const float *s_hat, float q, int lossy, float *out, long lo
 int pmctf_quantize_stats(const float *s, float q, float clip, int lossy, float *out, int planes,
                          long long plane_elems, unsigned long long *stats, void *stream);
 
+/* The coder step of a batch of planes with PER-PLANE steps (the H frames of all temporal levels of a GOP coded together;
+ * hp_q_scale differs per level, pMCTF_L.py:343-347): sym = rint(clamp(s * q[p], +-clip)).  q_per_plane: DEVICE array of
+ * `planes` floats.  out (fp32) receives the symbols, or with dequant != 0 the dequantised values sym / q[p]
+ * (dequantize_subbands, pWave.py:191-202).  sym16 (may be NULL): the symbols as int16 at sym16[p * sym16_plane_stride + i]
+ * -- what the reference copies to the host for the entropy coder (entropy_models.py:37-40); 8-byte aligned.  stats (may be
+ * NULL) as in pmctf_quantize_stats. */
+int pmctf_quantize_code(const float *s, const float *q_per_plane, float clip, int lossy, int dequant, float *out, short *sym16,
+                        long long sym16_plane_stride, int planes, long long plane_elems, unsigned long long *stats, void *stream);
+
 /* 8-bit planes [n,h0,w0] (HOST-visible layout of one YUV plane batch, already on the device) ->
  * fp32 planes [n,hp,wp], zero padded bottom/right: np_image_to_tensor + F.pad,
  * test_pMCTF_flex.py:151-192 (padding rule: pMCTF/utils/stream_helper.py:23-32). wp % 4 == 0. */

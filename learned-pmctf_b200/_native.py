@@ -90,6 +90,7 @@ SIGNATURES = {
     "pmctf_quantize": [_P, _f, _f, _I, _I, _P, _LL, _P],
     "pmctf_dequantize": [_P, _f, _I, _P, _LL, _P],
     "pmctf_quantize_stats": [_P, _f, _f, _I, _P, _I, _LL, _P, _P],
+    "pmctf_quantize_code": [_P, _P, _f, _I, _I, _P, _P, _LL, _I, _LL, _P, _P],
     "pmctf_unpack_u8": [_P, _P, _I, _I, _I, _I, _I, _P],
     "pmctf_frame_sse": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "pmctf_conv3x3": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

@@ -524,6 +524,61 @@ __global__ void __launch_bounds__(256) quantize_stats_kernel(const float *__rest
     }
 }
 
+// The coder's per-band step for a batch of planes that do NOT share a quantisation step (the H frames of all temporal levels of
+// a GOP coded as one batch: hp_q_scale differs per level, pMCTF_L.py:343-347): sym = rint(clamp(s * q[p], +-clip)); the fp32
+// output is the symbol or, with `dequant`, already sym / q[p] (dequantize_subbands, pWave.py:191-202 -- the same single
+// division the fused inverse-lifting loads would do); optional int16 copy of the symbols at sym16[p * stride + i] (what the
+// reference hands to the entropy coder, entropy_models.py:37-40) and the exact per-plane statistics.
+__global__ void __launch_bounds__(256) quantize_code_kernel(const float *__restrict__ s, const float *__restrict__ q_tab, float clip,
+                                                            int lossy, int dequant, float *__restrict__ out, short *__restrict__ sym16,
+                                                            long long sym16_stride, long long plane_elems,
+                                                            unsigned long long *__restrict__ stats, int vec)
+{
+    const int plane = blockIdx.y;
+    const float q = __ldg(q_tab + plane);
+    const float *sp = s + (long long)plane * plane_elems;
+    float *op = out + (long long)plane * plane_elems;
+    short *yp = sym16 ? sym16 + (long long)plane * sym16_stride : nullptr;
+    const bool div = dequant && lossy;
+    unsigned long long sum = 0;
+    unsigned int nnz = 0;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+    const long long n4 = vec ? plane_elems >> 2 : 0;
+    for (long long i = t; i < n4; i += nt) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(sp) + i);
+        const float4 r = make_float4(quant1(v.x, q, clip, lossy, 1), quant1(v.y, q, clip, lossy, 1), quant1(v.z, q, clip, lossy, 1),
+                                     quant1(v.w, q, clip, lossy, 1));
+        reinterpret_cast<float4 *>(op)[i] = div ? make_float4(r.x / q, r.y / q, r.z / q, r.w / q) : r;
+        if (yp) reinterpret_cast<short4 *>(yp)[i] = make_short4((short)(int)r.x, (short)(int)r.y, (short)(int)r.z, (short)(int)r.w);
+        const unsigned int a0 = (unsigned int)fabsf(r.x), a1 = (unsigned int)fabsf(r.y), a2 = (unsigned int)fabsf(r.z), a3 = (unsigned int)fabsf(r.w);
+        sum += a0 + a1 + a2 + a3;
+        nnz += (a0 != 0) + (a1 != 0) + (a2 != 0) + (a3 != 0);
+    }
+    for (long long i = 4 * n4 + t; i < plane_elems; i += nt) {
+        const float v = quant1(sp[i], q, clip, lossy, 1);
+        op[i] = div ? v / q : v;
+        if (yp) yp[i] = (short)(int)v;
+        const unsigned int iv = (unsigned int)fabsf(v);
+        sum += iv;
+        nnz += iv != 0;
+    }
+    unsigned long long s64 = sum, n64 = nnz;
+    for (int o = 16; o > 0; o >>= 1) {
+        s64 += __shfl_down_sync(0xffffffffu, s64, o);
+        n64 += __shfl_down_sync(0xffffffffu, n64, o);
+    }
+    __shared__ unsigned long long red[2][8];
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s64; red[1][threadIdx.x >> 5] = n64; }
+    __syncthreads();
+    if (threadIdx.x == 0 && stats) {   // one pair of atomics per block
+        for (int w = 1; w < 8; ++w) { s64 += red[0][w]; n64 += red[1][w]; }
+        if (s64 | n64) {
+            atomicAdd(stats + 2 * plane, s64);
+            atomicAdd(stats + 2 * plane + 1, n64);
+        }
+    }
+}
+
 // 8-bit samples -> fp32 planes, zero-padded bottom/right (np_image_to_tensor + F.pad, test_pMCTF_flex.py:151-192)
 __global__ void __launch_bounds__(256) unpack_u8_kernel(const unsigned char *__restrict__ src, float *__restrict__ dst,
                                                         int h0, int w0, int hp, int wp)
@@ -1185,6 +1240,23 @@ int pmctf_quantize_stats(const float *s, float q, float clip, int lossy, float *
     const long long cap = (148 * 16 + planes - 1) / planes;
     if (bx > cap) bx = cap;
     quantize_stats_kernel<<<dim3((unsigned)bx, planes), 256, 0, (cudaStream_t)stream>>>(s, q, clip, lossy, out, plane_elems, stats, vec);
+    return PMCTF_LAUNCHED();
+}
+
+int pmctf_quantize_code(const float *s, const float *q_per_plane, float clip, int lossy, int dequant, float *out, short *sym16,
+                        long long sym16_plane_stride, int planes, long long plane_elems, unsigned long long *stats, void *stream)
+{
+    if (planes == 0 || plane_elems == 0) return 0;
+    if (!s || !out || !q_per_plane || planes < 0 || plane_elems < 0 || planes > 65535) return PMCTF_EINVAL;
+    if (sym16 && sym16_plane_stride < plane_elems) return PMCTF_EINVAL;
+    if (clip > 32767.0f && sym16) return PMCTF_EINVAL;   // the symbols must fit the int16 the entropy coder takes (pWave.py:55-58)
+    int vec = ((((uintptr_t)s | (uintptr_t)out) & 15) == 0) && (plane_elems % 4 == 0 || planes == 1);
+    if (sym16 && ((((uintptr_t)sym16) & 7) != 0 || (sym16_plane_stride % 4 != 0 && planes > 1))) vec = 0;
+    long long bx = ((vec ? plane_elems / 4 + 3 : plane_elems) + 255) / 256;
+    const long long cap = (148 * 16 + planes - 1) / planes;
+    if (bx > cap) bx = cap;
+    quantize_code_kernel<<<dim3((unsigned)bx, planes), 256, 0, (cudaStream_t)stream>>>(s, q_per_plane, clip, lossy, dequant, out, sym16,
+                                                                                      sym16_plane_stride, plane_elems, stats, vec);
     return PMCTF_LAUNCHED();
 }
 

@@ -85,7 +85,8 @@ constexpr int SM_A1 = SM_T + ((T_ROWS * T_P * 4 + 127) / 128) * 128;
 constexpr int SM_C1 = SM_A1 + 3 * PLANE;              // conv1 stash (4 quarter planes)
 constexpr int SM_TANH = SM_C1 + 4 * C1Q_BYTES;
 constexpr int SM_BAR = SM_TANH + TANH_SMEM_BYTES;
-constexpr int SMEM_BYTES = SM_BAR + 128;
+constexpr int NC1BAR = 4, NC2BAR = NBLK;              // "conv1 pass k written" / "conv2 block j written" barriers (operand readiness for the MMA warp)
+constexpr int SMEM_BYTES = SM_BAR + 256;              // full[3], empty[3], weights, c1r[4], c2r[6] (8 B each), TMEM base at +240
 static_assert(SM_S % 128 == 0 && SM_T % 128 == 0 && SM_A1 % 128 == 0 && SM_C1 % 128 == 0 && SM_TANH % 128 == 0 && SM_BAR % 128 == 0, "alignment");
 static_assert(C1Q_BYTES % 128 == 32 && C1Q_BYTES >= A3_R * C1_P * 16, "conv1 stash planes");
 static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
@@ -201,8 +202,9 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     uint8_t *A1 = smem + SM_A1;                 // digit planes of tanh(conv1), then (in place) tanh(conv2), then the conv4 partials
     uint8_t *c1q = smem + SM_C1;                // conv1 pre-activations of the (TH+2) x (TW+2) region, one float4 plane per channel quarter
     float *ttab = reinterpret_cast<float *>(smem + SM_TANH);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);      // full[NSLOT], empty[NSLOT]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_BAR + 96);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);      // full[2 layers][NSLOT], empty[NSLOT], weights, c1r[NC1BAR], c2r[NC2BAR]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_BAR + 240);
+    static_assert((3 * NSLOT + 1 + NC1BAR + NC2BAR) * 8 <= 240, "barrier area");
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0); // warp-uniform for the compiler
@@ -229,10 +231,13 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
         if (tid == 0) {
             for (int i = 0; i < NSLOT; ++i) {
                 umma::mbar_init(umma::smem_u32(bars + i), 1);
-                umma::mbar_init(umma::smem_u32(bars + NSLOT + i), 128);
+                umma::mbar_init(umma::smem_u32(bars + NSLOT + i), 1);
+                umma::mbar_init(umma::smem_u32(bars + 2 * NSLOT + i), 128);
             }
-            const uint32_t wbar = umma::smem_u32(bars + 2 * NSLOT);
+            const uint32_t wbar = umma::smem_u32(bars + 3 * NSLOT);
             umma::mbar_init(wbar, 1);
+            for (int i = 0; i < NC1BAR; ++i) umma::mbar_init(umma::smem_u32(bars + 3 * NSLOT + 1 + i), 32 * MMA_WARP);
+            for (int i = 0; i < NC2BAR; ++i) umma::mbar_init(umma::smem_u32(bars + 3 * NSLOT + 1 + NC1BAR + i), 128);
             umma::fence_mbar_init();
             // the two operand images and the tanh table arrive by TMA bulk copies (one thread, no register staging)
             umma::mbar_expect_tx(wbar, 2 * QIMG + TANH_BULK_BYTES);
@@ -246,7 +251,10 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tbase = *tmem_slot;
-    const uint32_t full0 = umma::smem_u32(bars), empty0 = umma::smem_u32(bars + NSLOT);
+    // "accumulators complete": one barrier per (layer, slot) -- a parity wait can only tell completion u from u - 1, and with one
+    // barrier per slot an epilogue group could be asked for conv3's completion before it has seen conv2's last one
+    const uint32_t full0 = umma::smem_u32(bars), empty0 = umma::smem_u32(bars + 2 * NSLOT);
+    const uint32_t c1r0 = umma::smem_u32(bars + 3 * NSLOT + 1), c2r0 = umma::smem_u32(bars + 3 * NSLOT + 1 + NC1BAR);
     bool ok = true;
     bool staged = false;   // weights + tanh table have landed (waited for after the first tile's source load)
     if (warp < 4) {   // accumulator groups 3 and 4 of every slot start at zero (later each epilogue re-zeroes the slot it drained)
@@ -262,14 +270,50 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     umma::fence_after_sync();
     const bool xfast_src = a.src.cs <= a.src.rs;
 
-    // ---- persistent loop over tiles: every accumulator slot completes exactly twice per layer, so the mbarrier
-    //      parities are the same for every tile ------------------------------------------------------------------
+    // ---- persistent loop over tiles.  Tiles are numbered column-major (plane, column strip, row), every CTA takes one contiguous
+    //      range, so it walks DOWN a column strip.  A tile whose upper neighbour was the previous tile of this CTA is a
+    //      CONTINUATION tile: the rows the two tiles share are not recomputed -- tanh(conv2) of the two shared rows and the conv4
+    //      partials of the two shared conv3 rows travel across the tile boundary in the registers of the threads that produced
+    //      them -- so conv1 runs on 18 instead of 22 rows and conv2 / conv3 on 16 rows = 5 instead of 6 128-pixel blocks.
+    //      Same values either way (the arithmetic of a pixel does not depend on the tile it is computed in).
+    const int t_per = n_tiles / (int)gridDim.x, t_rem = n_tiles - t_per * (int)gridDim.x;
+    const int t_begin = (int)blockIdx.x * t_per + min((int)blockIdx.x, t_rem);
+    const int t_end = t_begin + t_per + ((int)blockIdx.x < t_rem ? 1 : 0);
+    uint32_t c1pm = 0, c2pm = 0;          // bit i: phase parity of barrier c1r[i] / c2r[i] (they complete once per tile that uses them)
+    uint32_t pm = 0;                      // bit s: phase parity of full[layer][s] at the start of the tile (the same for both layers)
+    uint4 carry_d[3];                     // tanh(conv2) digits of this thread's pixel in the two rows the next tile shares
+    float carry_p[9];                     // conv4 partials of this thread's pixel in the two conv3 rows the next tile shares
+    int carry_dm = -1, carry_pm = -1;     // their pixel indices in the NEXT tile's frame (-1: none)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) carry_d[k] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) carry_p[k] = 0.0f;
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int n = tile / (tiles_x * tiles_y);
-    const int trem = tile - n * (tiles_x * tiles_y);
-    const int ty = trem / tiles_x;
-    const int y0 = ty * TH, x0 = (trem - ty * tiles_x) * TW;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+    const int strip = tile / tiles_y;
+    const int ty = tile - strip * tiles_y;
+    const int n = strip / tiles_x;
+    const int y0 = ty * TH, x0 = (strip - n * tiles_x) * TW;
+    const bool cont = tile > t_begin && ty > 0;                 // the previous tile of this CTA was (strip, ty - 1)
+    const bool next_cont = tile + 1 < t_end && ty + 1 < tiles_y;
+    const int row_lo = cont ? 4 : 0;                           // first source row / conv1 row of this tile that is computed
+    const int c2s = cont ? 4 * P : 0, c3s = cont ? 2 * P : 0;  // first pixel record of the conv2 / conv3 blocks
+    const int nblk = cont ? NBLK - 1 : NBLK;
+    if (cont) {
+        // what the previous tile left in registers: its conv2 rows 18, 19 are this tile's rows 2, 3 (records 76..151), and the
+        // partials of its conv3 rows 16, 17 are those of rows 0, 1 here; they go to the (otherwise unused) records 0..75:
+        // tap k at plane k / 4, byte (k % 4) * 4 * 2P + 4 m
+        if (carry_dm >= 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) *reinterpret_cast<uint4 *>(A1 + k * PLANE + carry_dm * 16) = carry_d[k];
+        }
+        if (carry_pm >= 0) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                *reinterpret_cast<float *>(A1 + (k >> 2) * PLANE + (k & 3) * (8 * P) + carry_pm * 4) = carry_p[k];
+        }
+    }
+    carry_dm = carry_pm = -1;
 #if PMCTF_TC_TIMING
     dbg = (tiles_done == 4 || n_tiles <= (int)gridDim.x * 4) ? dbg_cta : nullptr;
     if (dbg && tid == 0) dbg[12] = dbg[13] = 0;
@@ -283,7 +327,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
         // values and the same fma chains as the generic path below, a tenth of its instructions, one barrier less
         constexpr int SEG = 4, NSEG = S_ROWS / SEG;
         static_assert(S_ROWS % SEG == 0 && NSEG * S_COLS <= NT && T_ROWS == S_ROWS + 2, "segment mapping");
-        if (tid < NSEG * S_COLS) {
+        if (tid < NSEG * S_COLS && tid >= (row_lo / SEG) * S_COLS) {   // continuation tiles need source rows >= 4 only
             const int seg = tid / S_COLS, c = tid - seg * S_COLS;
             const int gx = x0 - 4 + c;
             const bool colin = gx >= 0 && gx < W;
@@ -400,12 +444,13 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
         const float *linx = a.lin_x, *liny = a.lin_y;
         const long long srs = a.src.rs, scs = a.src.cs;
         const int round_src = a.round_src;
+        const int n_src = (S_ROWS - row_lo) * S_COLS;   // continuation tiles: rows >= 4 only
 #pragma unroll
         for (int k = 0; k < NIT; ++k) {   // motion vectors and grid tables of all items first ...
             const int i = tid + k * NT;
-            const int r = i / S_COLS, c = i - r * S_COLS;
+            const int r = row_lo + i / S_COLS, c = i - (i / S_COLS) * S_COLS;
             const int gy = y0 - 4 + r, gx = x0 - 4 + c;
-            in[k] = i < S_ROWS * S_COLS && gy >= 0 && gy < H && gx >= 0 && gx < W;
+            in[k] = i < n_src && gy >= 0 && gy < H && gx >= 0 && gx < W;
             fx[k] = fy[k] = lx[k] = ly[k] = 0.0f;
             if (in[k]) {
                 if (!mv_down) {
@@ -429,19 +474,19 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
 #pragma unroll
         for (int k = 0; k < NIT; ++k) {   // ... then the gathers
             const int i = tid + k * NT;
-            const int r = i / S_COLS, c = i - r * S_COLS;
+            const int r = row_lo + i / S_COLS, c = i - (i / S_COLS) * S_COLS;
             float v = 0.0f;
             if (in[k]) {
                 v = warp_sample(sp, srs, scs, H, W, lx[k], ly[k], fx[k], fy[k], sx, sy);
                 if (round_src) v = rintf(v);
             }
-            if (i < S_ROWS * S_COLS) ss[r * S_P + c] = v;
+            if (i < n_src) ss[r * S_P + c] = v;
         }
     }
     __syncthreads();
     STAMP(1);
     if (!staged) {   // first tile of this CTA: the TMA bulk copies of the setup ran under the source load
-        ok = umma::mbar_wait(umma::smem_u32(bars + 2 * NSLOT), 0u);
+        ok = umma::mbar_wait(umma::smem_u32(bars + 3 * NSLOT), 0u);
         staged = true;
         if (__syncthreads_or(!ok)) {   // CTA-uniform: either every thread goes on or all of them leave
             ok = false;
@@ -452,8 +497,16 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     // ---- conv1 (1 -> 16) + tanh -> digits of A1 (origin (-3,-3), pitch 38) -------------------------------
     {
         // one thread = one pixel, all 16 channels (a quarter at a time); the weights are warp-uniform 128-bit shared loads
+        // The eight epilogue warps do this phase, 256 pixels per pass, and announce every finished pass on its own mbarrier: the
+        // MMA warp starts conv2's first blocks while the later passes are still being computed (block b only reads the
+        // records of the passes up to (128 b + 205) / 256).
         const float in_mul = a.in_mul;
-        for (int px = tid; px < A1_R * A1_C; px += NT) {
+        constexpr int NE = 32 * MMA_WARP;
+        const int n_pass = (A1_R * A1_C - row_lo * P + NE - 1) / NE;
+        if (warp != MMA_WARP)
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int px = row_lo * P + pass * NE + tid;
+            if (px < A1_R * A1_C) {
             const int r = px / P, c = px - r * P;
             const int gy = y0 - 3 + r, gx = x0 - 3 + c;
             uint32_t w[3][4];
@@ -483,31 +536,57 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 *reinterpret_cast<uint4 *>(d + k * PLANE) = make_uint4(w[k][0], w[k][1], w[k][2], w[k][3]);
+            }
+            umma::fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's operand fetch
+            mbar_arrive(c1r0 + 8 * pass);
         }
     }
-    umma::fence_proxy_async();
-    __syncthreads();
     STAMP(2);
 
     // ---- conv2 / conv3 on the tensor core ---------------------------------------------------------------
+    // No CTA barrier between conv1, conv2 and conv3: the MMA warp follows the producers through mbarriers (conv1 passes, conv2
+    // blocks: conv3's block b reads conv2's blocks <= b + 1), the epilogue warps follow the MMAs through the accumulator
+    // slots' full / empty barriers.  Uses of a slot per tile are even (two layers with the same block count), so the parity of
+    // a use only depends on its position inside the tile.
+    int c1_waited = 0, c2_waited = 0;
+    const int n_pass_t = (A1_R * A1_C - row_lo * P + 32 * MMA_WARP - 1) / (32 * MMA_WARP);
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
+        if (!ok) break;
         const uint32_t a_saddr = umma::smem_u32(A1);
         const uint32_t b_saddr = umma::smem_u32(smem + SM_WB + layer * QIMG);
         if (warp == MMA_WARP) {
             if (PMCTF_TC_TIMING && dbg && lane == 0) dbg[8 + 2 * layer] = clock64();
             // the whole warp walks the (uniform) loop; one elected lane issues
+            const uint32_t a_first = a_saddr + (uint32_t)(layer == 0 ? c2s : c3s) * 16u;
 #pragma unroll 1
-            for (int blk = 0; blk < NBLK; ++blk) {
+            for (int blk = 0; blk < nblk; ++blk) {
                 const int slot = blk % NSLOT;
-                if (blk >= NSLOT) { // the slot's previous accumulators (drain 2*layer of this slot) must be gone
-                    ok = __shfl_sync(0xffffffffu, (int)umma::mbar_wait(empty0 + 8 * slot, 0u), 0) != 0;
-                    if (!ok) break;
-                    umma::fence_after_sync();
+                // operands written?
+                if (layer == 0) {
+                    const int need = min((128 * blk + 205) / (32 * MMA_WARP), n_pass_t - 1);
+                    while (ok && c1_waited <= need) {
+                        ok = __shfl_sync(0xffffffffu, (int)umma::mbar_wait(c1r0 + 8 * c1_waited, (c1pm >> c1_waited) & 1u), 0) != 0;
+                        ++c1_waited;
+                    }
+                } else {
+                    const int need = min(blk + 1, nblk - 1);
+                    while (ok && c2_waited <= need) {
+                        ok = __shfl_sync(0xffffffffu, (int)umma::mbar_wait(c2r0 + 8 * c2_waited, (c2pm >> c2_waited) & 1u), 0) != 0;
+                        ++c2_waited;
+                    }
                 }
+                if (!ok) break;
+                // accumulator slot drained?  (its previous use: the same layer's block blk - 3, or the layer / tile before)
+                const uint32_t use_par = (uint32_t)((layer ? (nblk - slot + NSLOT - 1) / NSLOT : 0) + blk / NSLOT) & 1u;
+                if (!(tile == t_begin && layer == 0 && blk < NSLOT)) {
+                    ok = __shfl_sync(0xffffffffu, (int)umma::mbar_wait(empty0 + 8 * slot, use_par ^ 1u), 0) != 0;
+                    if (!ok) break;
+                }
+                umma::fence_after_sync();
                 if (umma::elect_one()) {
-                    if (!(PMCTF_WHATIF & 4)) issue_block(a_saddr + blk * 2048, b_saddr, tbase + slot * SLOT_COLS);
-                    umma::commit(full0 + 8 * slot);
+                    if (!(PMCTF_WHATIF & 4)) issue_block(a_first + blk * 2048, b_saddr, tbase + slot * SLOT_COLS);
+                    umma::commit(full0 + 8 * (layer * NSLOT + slot));
                 }
                 __syncwarp();
             }
@@ -516,15 +595,15 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
             const int grp = warp >> 2, quarter = warp & 3;
             const float scale = layer == 0 ? cw.sc2 : cw.sc3;
 #pragma unroll 1
-            for (int blk = grp; blk < NBLK; blk += NGRP) {
+            for (int blk = grp; blk < nblk; blk += NGRP) {
                 const int slot = blk % NSLOT;
-                const uint32_t parity = (uint32_t)(blk / NSLOT) & 1u; // completion 2*layer + blk/NSLOT of this slot
+                const uint32_t parity = ((pm >> slot) ^ (uint32_t)(blk / NSLOT)) & 1u;   // this layer's use count of the slot before this block
                 const long long tw = (PMCTF_TC_TIMING && dbg && tid == 0) ? clock64() : 0;
-                ok = __all_sync(0xffffffffu, (int)umma::mbar_wait(full0 + 8 * slot, parity)) != 0;   // warp-uniform: the TMEM loads below are .sync.aligned
+                ok = __all_sync(0xffffffffu, (int)umma::mbar_wait(full0 + 8 * (layer * NSLOT + slot), parity)) != 0;   // warp-uniform: the TMEM loads below are .sync.aligned
                 if (PMCTF_TC_TIMING && dbg && tid == 0) dbg[12 + layer] += clock64() - tw;
                 if (!ok) break;
                 umma::fence_after_sync();
-                const int m = blk * 128 + quarter * 32 + lane;
+                const int m = (layer == 0 ? c2s : c3s) + blk * 128 + quarter * 32 + lane;
                 const int r = m / P, c = m - r * P;
                 const uint32_t taddr = tbase + ((uint32_t)(quarter * 32) << 16) + slot * SLOT_COLS;
                 if (layer == 0) {
@@ -563,6 +642,13 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
                         *reinterpret_cast<uint4 *>(d + k * PLANE) = make_uint4(w[k][0], w[k][1], w[k][2], w[k][3]);
+                    umma::fence_proxy_async();
+                    mbar_arrive(c2r0 + 8 * blk);   // conv3's MMAs may read this block's records now
+                    if (next_cont && m >= TH * P + 2 * P && m < TH * P + 4 * P) {   // rows 18, 19 = rows 2, 3 of the tile below
+                        carry_dm = m - TH * P;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) carry_d[k] = make_uint4(w[k][0], w[k][1], w[k][2], w[k][3]);
+                    }
                 } else {
                     const int gy = y0 - 1 + r, gx = x0 - 1 + c;
                     const bool inside = r < A3_R && c < A3_C;
@@ -571,7 +657,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     float t8 = 0.0f;
                     // warps whose 32 pixels all lie below the (TH+2)-row region have nothing to produce (the gather never reads
                     // their partials); they only hand the slot back
-                    const bool warp_has_work = blk * 128 + quarter * 32 < A3_R * P;
+                    const bool warp_has_work = c3s + blk * 128 + quarter * 32 < A3_R * P;
                     uint32_t o[2][5][4];
                     if (warp_has_work) {
 #pragma unroll
@@ -608,7 +694,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     mbar_arrive(empty0 + 8 * slot);
                     // the partials go over the digit records of this (finished) block, tap-planar inside the block so that the
                     // stores and the gather below are free of bank conflicts: T_k[m] at plane k/4, block, sub-plane k%4, word m%128
-                    float *d = reinterpret_cast<float *>(A1 + blk * 2048) + (m & 127);
+                    float *d = reinterpret_cast<float *>(A1 + c3s * 16 + blk * 2048) + quarter * 32 + lane;
                     constexpr int PW = PLANE / 4;
                     if (warp_has_work) {
                     if (!valid) {   // zero padding of conv4's input outside the image (and the junk columns): no contribution
@@ -618,21 +704,30 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                     d[0] = tp[0].x; d[128] = tp[0].y; d[256] = tp[1].x; d[384] = tp[1].y;
                     d[PW] = tp[2].x; d[PW + 128] = tp[2].y; d[PW + 256] = tp[3].x; d[PW + 384] = tp[3].y;
                     d[2 * PW] = t8;
+                    if (next_cont && m >= TH * P && m < TH * P + 2 * P) {   // conv3 rows 16, 17 = rows 0, 1 of the tile below
+                        carry_pm = m - TH * P;
+                        carry_p[0] = tp[0].x; carry_p[1] = tp[0].y; carry_p[2] = tp[1].x; carry_p[3] = tp[1].y;
+                        carry_p[4] = tp[2].x; carry_p[5] = tp[2].y; carry_p[6] = tp[3].x; carry_p[7] = tp[3].y;
+                        carry_p[8] = t8;
+                    }
                     }
                 }
             }
         }
-        umma::fence_proxy_async();
-        umma::fence_before_sync();
+    }
+    c1pm ^= (1u << n_pass_t) - 1u;   // every barrier used by this tile completed one phase
+    c2pm ^= (1u << nblk) - 1u;
+    if (nblk < NBLK) pm ^= 1u << (NSLOT - 1);   // five blocks: the last slot was used once per layer, the others twice
+    umma::fence_before_sync();
+    {
         const int bad = __syncthreads_or(!ok);   // a bounded wait gave up somewhere in the CTA: all warps leave together
         umma::fence_after_sync();
-        STAMP(3 + layer);
+        STAMP(4);
         if (bad) {
             ok = false;
             break;
         }
     }
-    if (!ok) break;   // CTA-uniform (set from __syncthreads_or)
 
     // the base operand of this thread's output pixels: issued here so that the gather below hides the global-load latency
     constexpr int NFIN = (TH * TW + NT - 1) / NT;
@@ -675,7 +770,9 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
 #pragma unroll
             for (int k9 = 0; k9 < 9; ++k9) {
                 const int m = (r + k9 / 3) * P + c + (k9 % 3);   // conv3 pixel index (origin (-1,-1)) of the neighbour
-                tk[k9] = *reinterpret_cast<const float *>(A1 + (k9 >> 2) * PLANE + (m >> 7) * 2048 + (k9 & 3) * 512 + (m & 127) * 4);
+                const int mm = m - c3s;                          // rows 0, 1 of a continuation tile: carried partials (records 0..75)
+                const int off = mm >= 0 ? c3s * 16 + (mm >> 7) * 2048 + (k9 & 3) * 512 + (mm & 127) * 4 : (k9 & 3) * (8 * P) + m * 4;
+                tk[k9] = *reinterpret_cast<const float *>(A1 + (k9 >> 2) * PLANE + off);
             }
             float pu = cw.b4;
 #pragma unroll

@@ -71,6 +71,8 @@ class GopCodec:
         self.stages = num_stages(gop_size)
         self.q_index = q_index
         self._qcache = {}
+        self._qtab = {}
+        self._hostsym = {}
         # luma and chroma never meet on the path (the motion field is read-only), so code_gop() runs the chroma chain on a
         # side stream: the tail of every persistent launch (CTAs that run out of tiles) and the small launches of the deep
         # wavelet levels are filled by the other chain's kernels
@@ -123,12 +125,30 @@ class GopCodec:
             Ly, Lc = L2y, L2c
         return Ly, Lc, Hs
 
-    def _code(self, coder, x, q, qll, stats):
+    def _code(self, coder, x, q, qll, stats, sym16=None):
         planes = x.reshape(-1, 1, x.size(-2), x.size(-1))
-        x_hat, st = coder.code_planes(planes, q, qll)
+        x_hat, st = coder.code_planes(planes, q, qll, sym16=sym16)
         if stats is not None:
             stats.append(st)
         return x_hat.view(x.shape)
+
+    def _hp_step_tables(self, planes_per_frame: int, device):
+        """Per-plane (q, q_ll) tables of the H frames of ALL temporal levels in coding order (level 0 frames first): the step of
+        hp_coder is scaled per temporal level (pMCTF_L.py:343-347), so the frames of a GOP can share one coder batch only with
+        per-plane steps.  Cached per parameter version."""
+        pairs = [self.q_pair("hp", s) for s in range(self.stages)]
+        key = (tuple(pairs), planes_per_frame, str(device))
+        t = self._qtab.get(key)
+        if t is None:
+            q, qll = [], []
+            for s, (a, b) in enumerate(pairs):
+                n = (self.gop_size >> (s + 1)) * planes_per_frame
+                q += [a] * n
+                qll += [b] * n
+            if len(self._qtab) > 32:
+                self._qtab.clear()
+            t = self._qtab[key] = (torch.tensor(q, dtype=torch.float32, device=device), torch.tensor(qll, dtype=torch.float32, device=device))
+        return t
 
     def code(self, Ly, Lc, Hs, want_stats: bool = True):
         """Spatial coding of every temporal subband frame: hp_coder on the H frames of each stage (step scaled
@@ -165,32 +185,45 @@ class GopCodec:
             st = self._side[key] = torch.cuda.Stream(device)
         return st
 
-    def _chain(self, X, mvs, chroma: bool, want_stats: bool):
+    def _chain(self, X, mvs, chroma: bool, want_stats: bool, sym16=None):
         """analysis -> code -> synthesis of ONE plane type (luma [G,1,H,W] or chroma [G,2,1,h,w]), everything on the
-        current stream.  Same calls in the same order as analysis() / code() / synthesis() make for that plane type."""
+        current stream.  The H frames of every temporal level are written into ONE buffer (level 0 first: the coding order of
+        test_pMCTF_flex.py:138-146) and coded by hp_coder as ONE batch with per-plane steps, so the deep wavelet levels launch
+        G-1 planes at a time instead of G/2, G/4, ... 1.  sym16: optional int16 [G * planes_per_frame, coefficients] buffer that
+        receives the symbols (rows in coding order: H frames, then the final L)."""
         m = self.m
-        L, Hs = X, []
+        G = X.size(0)
+        ppf = X.numel() // (G * X.size(-2) * X.size(-1))          # planes per frame: 1 (luma) or 2 (Cb, Cr)
+        Hbuf = torch.empty((G - 1,) + tuple(X.shape[1:]), dtype=torch.float32, device=X.device)
+        L, off = X, 0
         for s in range(self.stages):
             me = min(m.num_me_stages - 1, s)
-            if mvs[s].size(0) != L.size(0) // 2:
-                raise RuntimeError(f"stage {s}: expected {L.size(0) // 2} motion fields, got {mvs[s].size(0)}")
-            L, H, _, _ = m.forward_MCTF(L[0::2], L[1::2], mvs[s], stage_idx=me, mv_down=chroma, want_pred=False)
-            Hs.append(H)
+            n = L.size(0) // 2
+            if mvs[s].size(0) != n:
+                raise RuntimeError(f"stage {s}: expected {n} motion fields, got {mvs[s].size(0)}")
+            L, _, _, _ = m.forward_MCTF(L[0::2], L[1::2], mvs[s], stage_idx=me, mv_down=chroma, want_pred=False, out_H=Hbuf[off:off + n])
+            off += n
         st = [] if want_stats else None
-        Hhat = []
-        for s, H in enumerate(Hs):
-            q, qll = self.q_pair("hp", s)
-            Hhat.append(self._code(m.hp_coder, H, q, qll, st))
+        qt, qllt = self._hp_step_tables(ppf, X.device)
+        nh = (G - 1) * ppf
+        Hhat = self._code(m.hp_coder, Hbuf, qt, qllt, st, None if sym16 is None else sym16[:nh])
         q, qll = self.q_pair("lp", 0)
-        L = self._code(m.lp_coder, L, q, qll, st)
+        L = self._code(m.lp_coder, L, q, qll, st, None if sym16 is None else sym16[nh:])
+        end = G - 1
         for s in range(self.stages - 1, -1, -1):
             me = min(m.num_me_stages - 1, s)
-            b = torch.empty((2 * L.size(0),) + tuple(L.shape[1:]), dtype=torch.float32, device=L.device)
-            m.inverse_MCTF(L, Hhat[s], mvs[s], downscale=chroma, stage_idx=me, out_ref=b[0::2], out_cur=b[1::2])
+            n = L.size(0)
+            b = torch.empty((2 * n,) + tuple(L.shape[1:]), dtype=torch.float32, device=L.device)
+            m.inverse_MCTF(L, Hhat[end - n:end], mvs[s], downscale=chroma, stage_idx=me, out_ref=b[0::2], out_cur=b[1::2])
+            end -= n
             L = b
         return L, st
 
     # ---------------------------------------------------------------------------------------
+    def coding_order(self):
+        """GOP frame index of row i of the symbol buffers / statistics: the H frames level by level, then the low-pass frame."""
+        return self._frame_of_plane()
+
     def _frame_of_plane(self):
         """GOP frame index of every coded plane in the order `code` emits statistics."""
         order = []
@@ -200,29 +233,37 @@ class GopCodec:
         return order
 
     @torch.no_grad()
-    def code_gop(self, Y, C, mvs, orig_y_u8=None, orig_c_u8=None, want_stats=True):
+    def code_gop(self, Y, C, mvs, orig_y_u8=None, orig_c_u8=None, want_stats=True, symbols=None):
         """One GOP through the whole hot path.  Returns (rec_Y, rec_C, stats) with stats an fp64 device
         tensor [G, N_STATS] (None if want_stats is False).  orig_*_u8: the un-padded 8-bit originals
-        ([G,h0,w0], [G,2,h0/2,w0/2]) for the distortion columns; without them SSE is taken against Y / C."""
+        ([G,h0,w0], [G,2,h0/2,w0/2]) for the distortion columns; without them SSE is taken against Y / C.
+        symbols: optional dict that receives the quantised symbols as int16 device tensors, "y" [G, H*W] and "c" [G*2, H*W/4]
+        (rows in CODING order -- row i belongs to frame coding_order()[i], chroma rows Cb, Cr per frame -- each row in
+        pWave.band_layout() order): what the reference copies to the host for its entropy coder (entropy_models.py:37-40)."""
         G = self.gop_size
         if Y.size(0) != G or C.size(0) != G:
             raise RuntimeError(f"expected {G} frames, got {Y.size(0)} / {C.size(0)}")
         for s in range(self.stages):   # resolve the quantisation steps (host scalars) before any stream forks
             self.q_pair("hp", s)
         self.q_pair("lp", 0)
+        sym_y = sym_c = None
+        if symbols is not None:
+            sym_y = torch.empty((G, Y.size(-2) * Y.size(-1)), dtype=torch.int16, device=Y.device)
+            sym_c = torch.empty((2 * G, C.size(-2) * C.size(-1)), dtype=torch.int16, device=Y.device)
+            symbols["y"], symbols["c"] = sym_y, sym_c
         if self.concurrent_chroma and Y.is_cuda:
             cur = torch.cuda.current_stream(Y.device)
             side = self._stream_for((Y.device, "chroma", cur.cuda_stream), Y.device)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                rec_c, sc = self._chain(C, mvs, True, want_stats)
-            rec_y, sy = self._chain(Y, mvs, False, want_stats)
+                rec_c, sc = self._chain(C, mvs, True, want_stats, sym_c)
+            rec_y, sy = self._chain(Y, mvs, False, want_stats, sym_y)
             cur.wait_stream(side)
             for t in [rec_c] + (sc or []):
                 t.record_stream(cur)
         else:
-            rec_y, sy = self._chain(Y, mvs, False, want_stats)
-            rec_c, sc = self._chain(C, mvs, True, want_stats)
+            rec_y, sy = self._chain(Y, mvs, False, want_stats, sym_y)
+            rec_c, sc = self._chain(C, mvs, True, want_stats, sym_c)
         if not want_stats:
             return rec_y, rec_c, None
         dev = Y.device
@@ -293,12 +334,27 @@ class GopCodec:
         return torch.stack(out)
 
     @torch.no_grad()
+    def _host_symbols(self, frames: int, ny: int, nc: int):
+        """Pinned host buffers that receive the int16 symbols of a sequence (allocated once per shape, reused by later calls)."""
+        key = (frames, ny, nc)
+        b = self._hostsym.get(key)
+        if b is None:
+            self._hostsym.clear()
+            b = self._hostsym[key] = (torch.empty((frames, ny), dtype=torch.int16).pin_memory(),
+                                      torch.empty((frames, 2, nc), dtype=torch.int16).pin_memory())
+        return b
+
     def code_sequence_host(self, y_u8: torch.Tensor, c_u8: torch.Tensor, mvs_host: List[Sequence[torch.Tensor]],
-                           psize: int = 128):
+                           psize: int = 128, return_symbols: bool = False):
         """End-to-end entry point on HOST buffers: y_u8 [F,h0,w0], c_u8 [F,2,h0/2,w0/2] uint8 (pinned for
         speed) and per-GOP host motion fields; frames are uploaded GOP by GOP on a copy stream (overlapping the
         kernels of earlier GOPs), unpacked + zero padded on the device, coded (GOPs alternating between GOP_LANES stream
-        pairs), and the [F, N_STATS] statistics are returned on the host."""
+        pairs), and the [F, N_STATS] statistics are returned on the host.
+        return_symbols=True additionally brings the path's PRODUCT to the host: the quantised symbols of every coded plane as
+        int16, copied GOP by GOP on a second copy stream into pinned buffers while later GOPs compute -> (stats,
+        {"y": int16 [F, Hp*Wp], "c": int16 [F, 2, Hp*Wp/4], "coding_order": frame index of each row within its GOP}); rows
+        g*G .. g*G+G-1 hold GOP g in coding order, every row in pWave.band_layout() order.  The buffers are reused by the
+        next call on the same codec."""
         G = self.gop_size
         F_, h0, w0 = y_u8.shape
         if F_ % G:
@@ -309,6 +365,8 @@ class GopCodec:
         cur = torch.cuda.current_stream(dev)
         copy = self._stream_for((dev, "copy"), dev)
         copy.wait_stream(cur)
+        d2h = self._stream_for((dev, "d2h"), dev) if return_symbols else None
+        hy, hc = self._host_symbols(F_, hp * wp, (hp // 2) * (wp // 2)) if return_symbols else (None, None)
 
         def upload(g):  # H2D of GOP g on the copy stream, overlapping the kernels of the GOPs before it
             with torch.cuda.stream(copy):
@@ -331,17 +389,28 @@ class GopCodec:
                 t.record_stream(lane)
             if g + 1 < F_ // G:
                 nxt = upload(g + 1)
+            sym = {} if return_symbols else None
             with torch.cuda.stream(lane):
                 Y = ops.unpack_u8(yd, hp, wp)
                 C = ops.unpack_u8(cd.view(-1, h0 // 2, w0 // 2), hp // 2, wp // 2).view(G, 2, 1, hp // 2, wp // 2)
-                _, _, st = self.code_gop(Y, C, mvd, yd, cd)
+                _, _, st = self.code_gop(Y, C, mvd, yd, cd, symbols=sym)
+            if return_symbols:   # device -> pinned host on its own stream, overlapping the next GOP's kernels
+                d2h.wait_stream(lane)
+                with torch.cuda.stream(d2h):
+                    hy[g * G:(g + 1) * G].copy_(sym["y"], non_blocking=True)
+                    hc[g * G:(g + 1) * G].copy_(sym["c"].view(G, 2, -1), non_blocking=True)
+                sym["y"].record_stream(d2h), sym["c"].record_stream(d2h)
             out.append(st)
         for lane in lanes:
             cur.wait_stream(lane)
         for st in out:
             st.record_stream(cur)
         res = torch.cat(out).cpu()              # synchronises: every kernel of the sequence has finished
+        if return_symbols:
+            d2h.synchronize()
         ops.check_tc_error(dev, "GopCodec.code_sequence_host")
+        if return_symbols:
+            return res, {"y": hy, "c": hc, "coding_order": self.coding_order()}
         return res
 
 

@@ -191,20 +191,49 @@ class pWaveTransform:
             return subband / q_scale if self.lossy else subband
         return ops.dequantize(subband, self._q_float(q_scale), self.lossy)
 
-    def code_planes(self, x, q: float, qll: float):
-        """spatial_wavelet_dec (pWave.py:314-349, without PostProcess) on a batch of planes [P,1,H,W] with the
-        symbol statistics gathered by the quantise kernel.  -> (x_hat, int64 [P,2] = sum|sym|, #nonzero)."""
-        P = x.size(0)
-        y = self.encode_bands(x)
+    def _step_table(self, q, planes: int, device):
+        """per-plane step table (CUDA float [P]) from a float (cached) or a tensor of P steps"""
+        if isinstance(q, torch.Tensor):
+            if q.numel() != planes:
+                raise RuntimeError(f"expected one step per plane ({planes}), got {q.numel()}")
+            return q.detach().to(device=device, dtype=torch.float32).reshape(planes).contiguous()
+        cache = self.__dict__.setdefault("_qtabs", {})
+        key = (float(q), planes, str(device))
+        t = cache.get(key)
+        if t is None:
+            if len(cache) > 64:
+                cache.clear()
+            t = cache[key] = torch.full((planes,), float(q), dtype=torch.float32, device=device)
+        return t
+
+    def band_layout(self, H: int, W: int):
+        """[(level, band, offset, elements)] of one plane's coefficients in coding order (ll of the coarsest level, then lh / hl /
+        hh from the coarsest level down: pWave.py:254-290) -- the layout of the int16 symbol rows code_planes() emits."""
+        out, off = [], 0
         top = self.decomp_levels - 1
-        stats = torch.zeros((3 * self.decomp_levels + 1, P, 2), dtype=torch.int64, device=x.device)
-        hat, i = {}, 0
         for lvl in range(top, -1, -1):
-            hat[lvl] = {}
+            n = (H >> (lvl + 1)) * (W >> (lvl + 1))
             for b in (("ll",) + BANDS if lvl == top else BANDS):
-                hat[lvl][b] = ops.quantize_stats(y[lvl][b], qll if b == "ll" else q, stats[i], self.clip_value, self.lossy)
-                i += 1
-        x_hat = self.decode_dequant(hat, q, qll)
+                out.append((lvl, b, off, n))
+                off += n
+        return out
+
+    def code_planes(self, x, q, qll, sym16=None):
+        """spatial_wavelet_dec (pWave.py:314-349, without PostProcess) on a batch of planes [P,1,H,W]: analysis, then ONE launch per
+        band that quantises (per-plane steps: q / qll are floats or CUDA tensors with P entries, so frames of different
+        temporal levels can share the batch), gathers the exact symbol statistics, optionally emits the symbols as int16
+        (sym16: CUDA int16 [P, H*W], rows in band_layout() order -- what the reference hands to its entropy coder,
+        entropy_models.py:37-40) and dequantises; then synthesis.  -> (x_hat, int64 [P,2] = sum|sym|, #nonzero)."""
+        P, _, H, W = x.shape
+        y = self.encode_bands(x)
+        qt, qllt = self._step_table(q, P, x.device), self._step_table(qll, P, x.device)
+        layout = self.band_layout(H, W)
+        stats = torch.zeros((len(layout), P, 2), dtype=torch.int64, device=x.device)
+        hat = {lvl: {} for lvl in range(self.decomp_levels)}
+        for i, (lvl, b, off, _) in enumerate(layout):
+            hat[lvl][b] = ops.quantize_code(y[lvl][b], qllt if b == "ll" else qt, stats[i], self.clip_value, self.lossy, dequant=True,
+                                            sym16=sym16, sym16_offset=off)
+        x_hat = self.decode(hat)          # the bands are dequantised already
         return x_hat, stats.sum(0)
 
     # --- the reference's transform-only loop (pWave.py:314-349) --------------------------------

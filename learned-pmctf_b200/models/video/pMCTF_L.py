@@ -135,7 +135,7 @@ class pMCTF(MCTFMixin, nn.Module):
 # out-of-scope networks around these.
 _PWAVE_METHODS = ("encode", "decode", "decode_dequant", "encode_bands", "quantize_subband", "quantize_subbands",
                   "dequantize_subbands", "dequantize_subband", "spatial_wavelet_dec", "_q_float", "code_planes", "_train", "_round",
-                  "q_pair")
+                  "q_pair", "_step_table", "band_layout")
 _MCTF_METHODS = ("motion_compensation", "forward_MCTF", "inverse_MCTF", "_temporal", "hp_qp_scale")
 
 

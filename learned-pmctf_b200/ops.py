@@ -497,6 +497,34 @@ def quantize_stats(s: torch.Tensor, q: float, stats: torch.Tensor, clip: float =
     return out
 
 
+def quantize_code(s: torch.Tensor, q_tab: torch.Tensor, stats: Optional[torch.Tensor] = None, clip: float = 8192.0, lossy: bool = True,
+                  dequant: bool = True, sym16: Optional[torch.Tensor] = None, sym16_offset: int = 0):
+    """One band of a plane batch [P, ...] with per-plane steps q_tab (CUDA float [P]): -> fp32 tensor of the dequantised symbols
+    (or the symbols, dequant=False).  sym16: int16 [P, plane_total] buffer that receives this band's symbols at column
+    `sym16_offset` of every plane's row; stats: int64 [P,2] accumulators (caller-zeroed)."""
+    _no_grad_only(s)
+    s = _chk(s, "subband").contiguous()
+    out = torch.empty_like(s)
+    planes = s.size(0) if s.dim() > 0 else 0
+    if s.numel() == 0:
+        return out
+    elems = s.numel() // planes
+    if q_tab.dtype != torch.float32 or not q_tab.is_cuda or q_tab.numel() != planes or not q_tab.is_contiguous():
+        raise RuntimeError("q_tab must be a contiguous CUDA float32 tensor with one step per plane")
+    if stats is not None and (stats.dtype != torch.int64 or not stats.is_cuda or not stats.is_contiguous() or stats.numel() < 2 * planes):
+        raise RuntimeError("stats must be a contiguous CUDA int64 tensor with 2 entries per plane")
+    sp, stride = None, 0
+    if sym16 is not None:
+        if sym16.dtype != torch.int16 or not sym16.is_cuda or sym16.dim() != 2 or sym16.size(0) != planes or sym16.stride(1) != 1 \
+                or sym16_offset + elems > sym16.size(1):
+            raise RuntimeError("sym16 must be a CUDA int16 tensor [planes, coefficients per plane] with room for this band")
+        sp, stride = sym16.data_ptr() + 2 * sym16_offset, sym16.stride(0)
+    _dev = _same_device(s, q_tab, stats, sym16)
+    _launch(_dev, "quantize_code", nat.lib().pmctf_quantize_code, s.data_ptr(), q_tab.data_ptr(), clip, int(lossy), int(dequant),
+            out.data_ptr(), sp, stride, planes, elems, stats.data_ptr() if stats is not None else None)
+    return out
+
+
 def unpack_u8(src: torch.Tensor, hp: int, wp: int, out: Optional[torch.Tensor] = None):
     """uint8 planes [n,h0,w0] -> fp32 [n,1,hp,wp], zero padded bottom/right (test_pMCTF_flex.py:151-192)."""
     if not src.is_cuda or src.dtype != torch.uint8 or src.dim() != 3:

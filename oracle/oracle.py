@@ -317,7 +317,8 @@ def code_gop(Y, C, mvs, temporal, hp_w: IWave, lp_w: IWave, q_hp, q_lp, num_me_s
     transform (step pair q_hp[s]), the final L with the lp transform; temporal decoding in reverse.
     Y [G,1,H,W]; C [G,2,1,h,w]; mvs[s] [pairs,2,H,W]; temporal[i] = (P_t, U_t).
     -> (rec_Y, rec_C, sym_stats int64 [G,2]).  `trace` (a dict) receives the temporal subbands before coding:
-    trace["H"][frame] = (H_y, H_c) of every high-pass frame, trace["L"] = (L_y, L_c) of the final low-pass frame."""
+    trace["H"][frame] = (H_y, H_c) of every high-pass frame, trace["L"] = (L_y, L_c) of the final low-pass frame,
+    trace["sym"][frame] = (luma symbols, chroma symbols) as spatial_wavelet_dec returns them."""
     Y, C = _a(Y).copy(), _a(C).copy()
     G = Y.shape[0]
     S = int(round(math.log2(G)))
@@ -341,12 +342,15 @@ def code_gop(Y, C, mvs, temporal, hp_w: IWave, lp_w: IWave, q_hp, q_lp, num_me_s
             coded[c] = (Hh_hat, Hc_hat, mv)
             if trace is not None:
                 trace.setdefault("H", {})[c] = (Hh, Hc)
+                trace.setdefault("sym", {})[c] = (hat, hatc)
     q, qll = q_lp
     if trace is not None:
         trace["L"] = (fy[0], fc[0])
     L_hat, hat = spatial_wavelet_dec(fy[0], lp_w, q, qll)
     Lc_hat, hatc = spatial_wavelet_dec(fc[0], lp_w, q, qll)
     sym[0] += symbol_stats(hat)[0] + symbol_stats(hatc).sum(0)
+    if trace is not None:
+        trace.setdefault("sym", {})[0] = (hat, hatc)
     ry, rc = {0: L_hat}, {0: Lc_hat}
     for s in range(S - 1, -1, -1):
         step = 2 ** s

@@ -20,8 +20,8 @@ for name, fn in (("temporal fwd", lambda: m.forward_MCTF(x, x, mv, 0, want_pred=
     torch.cuda.synchronize(); lib.pmctf_tc_debug_times(out)
     fn(); torch.cuda.synchronize(); lib.pmctf_tc_debug_times(out)
     t = list(out)
-    print(name, "phases (cycles): setup+src %d | conv1 %d | conv2 %d | conv3 %d | conv4 %d | final %d | total %d" %
-          (t[1]-t[0], t[2]-t[1], t[3]-t[2], t[4]-t[3], t[5]-t[4], t[6]-t[5], t[6]-t[0]))
+    print(name, "phases (cycles): setup+src %d | conv1 %d | conv2+conv3 %d | final %d | total %d" %
+          (t[1]-t[0], t[2]-t[1], t[4]-t[2], t[6]-t[4], t[6]-t[0]))
     print("   MMA issue conv2 %d conv3 %d cycles; epilogue warp0 waited %d / %d cycles; CTA total %d cycles for %d tiles = %d / tile" % (t[9]-t[8], t[11]-t[10], t[12], t[13], t[14], t[15], t[14] // max(t[15], 1)))
 o = torch.zeros(3, dtype=torch.int64, device="cuda")
 for v, name in ((0, "conv block pattern"), (1, "N=16"), (2, "N=48"), (3, "N=96"), (4, "N=48 disjoint chunks")):

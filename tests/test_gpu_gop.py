@@ -143,6 +143,65 @@ def test_gop16_1080p_properties(P, model):
     assert float((ry - Y).abs().max()) <= 2e-3 and float((rc - C).abs().max()) <= 2e-3
 
 
+def test_quantize_code_per_plane_steps(P):
+    """pmctf_quantize_code: per-plane steps, int16 symbols at a column offset of a wider row, statistics, fused dequantise."""
+    g = np.random.default_rng(5)
+    s = g.normal(0, 400, (5, 1, 18, 22)).astype(np.float32)
+    s[0, 0, 0, :4] = [0.5, 1.5, -2.5, 1e6]
+    qs = np.array([0.37, 0.05, 0.5, 0.11, 0.25], np.float32)
+    st = torch.zeros((5, 2), dtype=torch.int64, device="cuda")
+    sym16 = torch.full((5, 1000), -7, dtype=torch.int16, device="cuda")
+    out = P.ops.quantize_code(cu(s), cu(qs), st, sym16=sym16, sym16_offset=100)
+    raw = P.ops.quantize_code(cu(s), cu(qs), None, dequant=False)
+    for p in range(5):
+        want = orc.quantize(s[p], float(qs[p]))
+        assert np.array_equal(raw[p].cpu().numpy(), want)
+        assert np.array_equal(out[p].cpu().numpy(), orc.dequantize(want, float(qs[p])))
+        assert np.array_equal(sym16[p, 100:100 + 396].cpu().numpy(), want.reshape(-1).astype(np.int16))
+        a = np.abs(want.reshape(-1)).astype(np.int64)
+        assert st[p].cpu().tolist() == [int(a.sum()), int((a != 0).sum())]
+    assert bool((sym16[:, :100] == -7).all()) and bool((sym16[:, 496:] == -7).all())
+    with pytest.raises(RuntimeError):
+        P.ops.quantize_code(cu(s), cu(qs[:3]), st)
+
+
+def test_host_symbols_equal_oracle(P, model, weights):
+    """The path's product on the HOST: code_sequence_host(return_symbols=True) brings the int16 symbols of every coded plane
+    (entropy_models.py:37-40 hands exactly these to rANS) to pinned host memory; they equal the oracle's symbols, frame by
+    frame, band by band, for both GOPs of a 2-GOP sequence."""
+    from learned_pmctf_b200 import gop as Gm
+    gop, h0, w0, n_gops = 4, 120, 190, 2
+    codec = Gm.GopCodec(model, gop, q_index=12)
+    _, pr, _, pb = Gm.get_padding_size(h0, w0, 128)
+    hp, wp = h0 + pb, w0 + pr
+    ys, cs, mvl = [], [], []
+    for g in range(n_gops):
+        y, c, mvs = _inputs(gop, h0, w0, 41 + g)
+        ys.append(y), cs.append(c)
+        mvl.append([np.ascontiguousarray(np.pad(m, ((0, 0), (0, 0), (0, hp - h0), (0, wp - w0)))) for m in mvs])
+    y, c = np.concatenate(ys), np.concatenate(cs)
+    stats, sym = codec.code_sequence_host(torch.from_numpy(y).pin_memory(), torch.from_numpy(c).pin_memory(),
+                                          [[torch.from_numpy(m).pin_memory() for m in g] for g in mvl], return_symbols=True)
+    assert sym["y"].dtype == torch.int16 and sym["y"].shape == (n_gops * gop, hp * wp) and sym["c"].shape == (n_gops * gop, 2, hp * wp // 4)
+    assert sym["y"].is_pinned() and sym["coding_order"] == [1, 3, 2, 0]
+    temporal, hp_w, lp_w = _oracle_weights(weights)
+    q_hp = [codec.q_pair("hp", s) for s in range(2)]
+    lay_y, lay_c = model.hp_coder.band_layout(hp, wp), model.hp_coder.band_layout(hp // 2, wp // 2)
+    for g in range(n_gops):
+        trace = {}
+        _, _, osym = orc.code_gop(orc.unpack_u8(ys[g], hp, wp)[:, None], orc.unpack_u8(cs[g], hp // 2, wp // 2)[:, :, None], mvl[g],
+                                  temporal, hp_w, lp_w, q_hp, codec.q_pair("lp", 0), trace=trace)
+        for row, frame in enumerate(sym["coding_order"]):
+            hat_y, hat_c = trace["sym"][frame]
+            for lvl, b, off, n in lay_y:
+                assert np.array_equal(sym["y"][g * gop + row, off:off + n].numpy(), hat_y[lvl][b].reshape(-1).astype(np.int16)), (g, frame, lvl, b)
+            for lvl, b, off, n in lay_c:
+                for ch in range(2):
+                    assert np.array_equal(sym["c"][g * gop + row, ch, off:off + n].numpy(), hat_c[lvl][b][ch].reshape(-1).astype(np.int16))
+        assert np.array_equal(stats.numpy()[g * gop:(g + 1) * gop, 1:3].astype(np.int64), osym)
+    assert sum(n for *_, n in lay_y) == hp * wp
+
+
 def _adversarial_motion(mvs):
     """SURVEY.md section 8d (ii) on top of the N(0, 4^2) fields: saturated +-32 px blocks, and 64 px vectors pointing out of the
     frame along all four borders (border clamping of the warp, video_net.py:47-50)."""
