@@ -602,9 +602,10 @@ def main():
                 "achieved_definition": "sum over timed launches of (pixels through PredictUpdate x 9792 FLOP) / sum of CUDA-event time "
                                        "around those launches (events on the launching stream inside the timed region)"}
     if mode == "tensor":
-        # executed int8 tensor-core work: per 16x32 tile 12 blocks x (13 MMAs 128x48x32 + 1 MMA 128x64x32), 2 ops per MAC
-        # (continuation tiles run 10 blocks; the figure below is the upper one of a first-of-column tile)
-        ops_per_px = 12 * (13 * 128 * 48 * 32 + 128 * 64 * 32) * 2 / 512.0
+        # executed int8 tensor-core work: per 16x32 tile 10 or 12 blocks x (13 MMAs 128x48x32 + 1 MMA 128x64x32), 2 ops per MAC
+        # continuation tiles (all but the first tile of every column run of a CTA) execute 10 blocks, the others 12; the executed
+        # work is quoted with the continuation figure (a slight under-count, never an over-count)
+        ops_per_px = 10 * (13 * 128 * 48 * 32 + 128 * 64 * 32) * 2 / 512.0
         tr = profiled_traffic()
         if tr is not None:
             roofline["traffic"] = tr.get("dram_bytes_per_launch")
