@@ -261,7 +261,9 @@ def run_uvg(args, pkg, G, par, model, dev, rank, world):
         torch.cuda.synchronize()
 
     if mine:
-        one(mine[0])   # warm-up (allocator pools of this shape are already warm from the headline run)
+        w = one(mine[0])   # warm-up (allocator pools of this shape are already warm from the headline run)
+        # ... and of the collective: the first all_gather of a new shape sets up NCCL channels / protocols (seconds, once)
+        par.gather_stats(torch.stack([w] * len(mine)), len(items), rank, world)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
