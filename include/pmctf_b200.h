@@ -254,6 +254,41 @@ int pmctf_unpack_u8(const unsigned char *src, float *dst, int n, int h0, int w0,
 int pmctf_frame_sse(const float *rec, const unsigned char *orig, int n, int h0, int w0, int hp, int wp,
                     unsigned long long *sse, void *stream);
 
+/* ---- PostProcess: pMCTF/layers/postprocessing.py:20-44, applied to every reconstructed plane at
+ * pWave.py:299-300,347,455,526 as dequantModule(x_hat / 256) * 256.  15 3x3 convolutions (1 -> 64, 6 ResBlocks of two
+ * 64 -> 64 with LeakyReLU(0.2), 64 -> 64 + skip, 64 -> 1), 958 kFLOP per pixel.  The thirteen 64 -> 64 layers and the last one
+ * run as tcgen05 implicit GEMMs with bf16 operands and fp32 accumulators in TMEM; biases, skip connections and the residual
+ * stream are fp32.  Not bit-exact (the tensor core's summation order is unspecified): parity is the north-star tolerance for
+ * frames, 1e-3 on the [0,1] pixel scale, against the fp32 oracle.
+ * Weights: conv1 fp32 OIHW as in the state_dict; every other layer packed once by pmctf_pp_pack_conv (bf16 operand image,
+ * pmctf_pp_packed_bytes(co) bytes, 16-byte aligned); biases fp32. */
+typedef struct {
+    const float *conv1_w, *conv1_b;          /* [64,1,3,3], [64] */
+    const void *res_w[12];                   /* resBlocks.{0..5}.{conv1,conv2} packed (co = 64) */
+    const float *res_b[12];
+    const void *conv2_w; const float *conv2_b; /* packed (co = 64) */
+    const void *conv3_w; const float *conv3_b; /* packed (co = 1), [1] */
+} pmctf_postprocess_t;
+long long pmctf_pp_packed_bytes(int co);
+/* OIHW fp32 [co,64,3,3] (co = 64, or 1..16) -> operand image */
+int pmctf_pp_pack_conv(const float *w, int co, void *packed, void *stream);
+/* conv1: x [N,1,H,W] fp32 (scaled by in_mul) -> NHWC 64-channel feature map, fp32 and bf16 copies */
+int pmctf_pp_conv_in(const float *x, const float *w, const float *b, float in_mul, float *out_f32, void *out_bf16, int N, int H, int W,
+                     void *stream);
+/* fp32 -> bf16 (RN), n a multiple of 4 */
+int pmctf_pp_to_bf16(const float *in, void *out, long long n, void *stream);
+/* One 3x3 convolution 64 -> co on the tensor cores: in_bf16 NHWC [N,H,W,64]; co == 64: out = lrelu_slope(conv + bias [+ residual
+ * NHWC fp32]) written as fp32 and / or bf16 NHWC (either may be NULL); co == 1: y_plane[N,1,H,W] = (x_plane * in_mul + conv +
+ * bias) * out_mul (postprocessing.py:41-44 with the scaling of pWave.py:300). */
+int pmctf_pp_conv64(const void *in_bf16, const void *packed_w, const float *bias, int co, const float *residual, float lrelu_slope,
+                    float *out_f32, void *out_bf16, const float *x_plane, float in_mul, float out_mul, float *y_plane, int N, int H,
+                    int W, void *stream);
+/* The whole filter, plane by plane: y = PostProcess(x * in_mul) * out_mul on [N,1,H,W]; workspace (256-byte aligned) of
+ * pmctf_postprocess_workspace(H, W) bytes holds one plane's feature maps. */
+long long pmctf_postprocess_workspace(int H, int W);
+int pmctf_postprocess(const float *x, const pmctf_postprocess_t *p, float in_mul, float out_mul, float *y, int N, int H, int W,
+                      void *workspace, long long workspace_bytes, void *stream);
+
 /* Unit test / timing probe of the tcgen05 (5th-generation tensor core) conventions the lifting convolutions are built
  * on: runs `n_ops` kind::i8 MMAs (M = 128, K = 32, s8 x s8 -> s32 in TMEM) per 128-row block on operands copied to
  * shared memory and returns the raw accumulators out[block][128][out_cols].  Offsets are bytes relative to the staged

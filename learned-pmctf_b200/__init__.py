@@ -6,17 +6,18 @@ Layout mirrors the reference package for the modules on the path:
     layers.video.wavelet_transform_temporal_mctf TemporalLifting
     layers.lifting_1d                            PredictUpdate, iWave1D, split, merge
     layers.wavelet_transform                     LiftingScheme2D
+    layers.postprocessing                        PostProcess (de-quantisation filter)
     models.pWave                                 pWave (transform + quantiser)
     models.video.pMCTF_L                         pMCTF (forward_MCTF / inverse_MCTF), accelerate()
     gop                                          dyadic GOP schedule (test_pMCTF_flex.py:131-291)
     parallel                                     GOP sharding + NCCL stats gather
 """
 from . import _native, ops  # noqa: F401
-from .layers import LiftingScheme2D, PredictUpdate, iWave1D  # noqa: F401
+from .layers import LiftingScheme2D, PostProcess, PredictUpdate, iWave1D  # noqa: F401
 from .layers.video.video_net import bilineardownsacling, flow_warp  # noqa: F401
 from .layers.video.wavelet_transform_temporal_mctf import TemporalLifting  # noqa: F401
 from .models.pWave import pWave  # noqa: F401
 from .models.video.pMCTF_L import accelerate, pMCTF  # noqa: F401
 
-__all__ = ["flow_warp", "bilineardownsacling", "PredictUpdate", "iWave1D", "LiftingScheme2D", "TemporalLifting",
+__all__ = ["flow_warp", "bilineardownsacling", "PredictUpdate", "iWave1D", "LiftingScheme2D", "TemporalLifting", "PostProcess",
            "pWave", "pMCTF", "accelerate", "ops"]

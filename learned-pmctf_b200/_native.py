@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("PMCTF_LIB") or os.path.join(_HERE, "lib", "libpmctf_b200.so")  # PMCTF_LIB: profiling builds only
 SOURCES = [os.path.join(_HERE, "csrc", "pmctf_kernels.cu"), os.path.join(_HERE, "csrc", "pmctf_umma_test.cu"),
-           os.path.join(_HERE, "csrc", "pmctf_lift_tc.cu"), os.path.join(_HERE, "csrc", "pmctf_train.cu")]
+           os.path.join(_HERE, "csrc", "pmctf_lift_tc.cu"), os.path.join(_HERE, "csrc", "pmctf_train.cu"),
+           os.path.join(_HERE, "csrc", "pmctf_pp.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "pmctf_umma.cuh"), os.path.join(_HERE, "csrc", "pmctf_common.cuh")]
 INCLUDE = os.path.join(ROOT, "include")
 
@@ -49,6 +50,11 @@ class IWave(C.Structure):
 
 class UmmaOp(C.Structure):
     _fields_ = [(n, C.c_uint) for n in ("a_off", "a_lbo", "a_sbo", "b_off", "b_lbo", "b_sbo", "n", "d_col", "accumulate", "a_unsigned")]
+
+
+class PostProcessD(C.Structure):
+    _fields_ = [("conv1_w", _fp), ("conv1_b", _fp), ("res_w", _fp * 12), ("res_b", _fp * 12), ("conv2_w", _fp), ("conv2_b", _fp),
+                ("conv3_w", _fp), ("conv3_b", _fp)]
 
 
 class Temporal(C.Structure):
@@ -92,13 +98,21 @@ SIGNATURES = {
     "pmctf_quantize_stats": [_P, _f, _f, _I, _P, _I, _LL, _P, _P],
     "pmctf_quantize_code": [_P, _P, _f, _I, _I, _P, _P, _LL, _I, _LL, _P, _P],
     "pmctf_unpack_u8": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "pmctf_pp_packed_bytes": [_I],
+    "pmctf_pp_pack_conv": [_P, _I, _P, _P],
+    "pmctf_pp_conv_in": [_P, _P, _P, _f, _P, _P, _I, _I, _I, _P],
+    "pmctf_pp_to_bf16": [_P, _P, _LL, _P],
+    "pmctf_pp_conv64": [_P, _P, _P, _I, _P, _f, _P, _P, _P, _f, _f, _P, _I, _I, _I, _P],
+    "pmctf_postprocess_workspace": [_I, _I],
+    "pmctf_postprocess": [_P, C.POINTER(PostProcessD), _f, _f, _P, _I, _I, _I, _P, _LL, _P],
     "pmctf_frame_sse": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "pmctf_conv3x3": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pmctf_conv3x3_wgrad": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pmctf_flow_warp_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _f, _P],
     "pmctf_umma_selftest": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P],
 }
-_RESTYPES = {"pmctf_error_string": C.c_char_p, "pmctf_lift2d_workspace": C.c_longlong,
+_RESTYPES = {"pmctf_error_string": C.c_char_p, "pmctf_lift2d_workspace": C.c_longlong, "pmctf_pp_packed_bytes": C.c_longlong,
+             "pmctf_postprocess_workspace": C.c_longlong,
              "pmctf_launch_count": C.c_ulonglong}
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",

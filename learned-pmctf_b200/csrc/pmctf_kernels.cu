@@ -756,6 +756,10 @@ static int tc_err_buffer(bool create, volatile int **host, int **devp)
     return 0;
 }
 
+// used by the other translation units that launch tensor-core kernels (pmctf_pp.cu)
+int tc_watchdog(volatile int **host, int **dev) { return tc_err_buffer(true, host, dev); }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 static int resolve_conv_mode(int requested)
 {
     if (requested == PMCTF_CONV_DEFAULT) return g_conv_mode.load(std::memory_order_relaxed);

@@ -525,6 +525,50 @@ def quantize_code(s: torch.Tensor, q_tab: torch.Tensor, stats: Optional[torch.Te
     return out
 
 
+_WSB_CACHE: dict = {}
+
+
+def byte_workspace(nbytes: int, device, tag: str) -> torch.Tensor:
+    """Grow-only per-(device, stream, tag) byte buffer (256-byte aligned by the caching allocator)."""
+    device = torch.device(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream(device), tag)
+    t = _WSB_CACHE.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _WSB_CACHE[key] = t
+    return t
+
+
+def postprocess(x: torch.Tensor, desc: "nat.PostProcessD", in_mul: float = 1.0, out_mul: float = 1.0):
+    """PostProcess.forward (postprocessing.py:35-44) on [N,1,H,W]: y = PostProcess(x * in_mul) * out_mul.  The 64 -> 64 layers run
+    on the tensor cores (bf16 operands, fp32 accumulation); one plane's feature maps live in a cached workspace (1 KB / pixel)."""
+    _no_grad_only(x)
+    x = _chk(x, "x", 4).contiguous()
+    N, Cc, H, W = x.shape
+    if Cc != 1:
+        raise RuntimeError("PostProcess is single-channel (pWave.py:62)")
+    y = torch.empty_like(x)
+    need = int(nat.lib().pmctf_postprocess_workspace(H, W))
+    ws = byte_workspace(need, x.device, "pp")
+    _launch(x.device, "postprocess", nat.lib().pmctf_postprocess, x.data_ptr(), C.byref(desc), in_mul, out_mul, y.data_ptr(), N, H, W,
+            ws.data_ptr(), ws.numel())
+    return y
+
+
+def pp_conv64(x_bf16: torch.Tensor, packed_w: torch.Tensor, bias: torch.Tensor, co: int = 64, residual=None, slope: float = 1.0,
+              want_f32: bool = True, want_bf16: bool = False):
+    """One tensor-core 3x3 convolution 64 -> 64 on an NHWC bf16 tensor [N,H,W,64] (building block of PostProcess; tests)."""
+    if x_bf16.dtype != torch.bfloat16 or not x_bf16.is_cuda or x_bf16.dim() != 4 or x_bf16.size(3) != 64 or not x_bf16.is_contiguous():
+        raise RuntimeError("pp_conv64 expects a contiguous CUDA bfloat16 tensor [N,H,W,64]")
+    N, H, W, _ = x_bf16.shape
+    of = torch.empty((N, H, W, 64), dtype=torch.float32, device=x_bf16.device) if want_f32 else None
+    ob = torch.empty((N, H, W, 64), dtype=torch.bfloat16, device=x_bf16.device) if want_bf16 else None
+    _launch(x_bf16.device, "pp_conv64", nat.lib().pmctf_pp_conv64, x_bf16.data_ptr(), packed_w.data_ptr(), bias.data_ptr(), co,
+            residual.data_ptr() if residual is not None else None, slope, of.data_ptr() if of is not None else None,
+            ob.data_ptr() if ob is not None else None, None, 1.0, 1.0, None, N, H, W)
+    return of, ob
+
+
 def unpack_u8(src: torch.Tensor, hp: int, wp: int, out: Optional[torch.Tensor] = None):
     """uint8 planes [n,h0,w0] -> fp32 [n,1,hp,wp], zero padded bottom/right (test_pMCTF_flex.py:151-192)."""
     if not src.is_cuda or src.dtype != torch.uint8 or src.dim() != 3:

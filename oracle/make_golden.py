@@ -241,8 +241,41 @@ def main_lossless():
           "perfect reconstruction in the reference:", bool((c["dec"] == c["x"]).all()), bool((c["s0.ref_rec"] == c["ref"]).all()))
 
 
+def main_postprocess():
+    """tests/golden/postprocess.npz: the reference's PostProcess module (pMCTF/layers/postprocessing.py:20-44) as pWave applies it
+    (pWave.py:300: dequantModule(x_hat / 256) * 256), CPU fp32.  Weights: N(0, 0.05) for the 64 -> 64 layers (gain ~1.2 per layer,
+    so the activations stay O(1)..O(10) through the 13 layers instead of vanishing as with the 0.02 init), N(0, 0.3) for 1 -> 64,
+    N(0, 1e-4) for 64 -> 1 (a correction of a few grey levels, like a trained filter), biases N(0, 0.05); seed 4321."""
+    from pMCTF.layers.postprocessing import PostProcess
+    torch.manual_seed(7)
+    pp = PostProcess().eval()
+    g = torch.Generator().manual_seed(4321)
+    with torch.no_grad():
+        for k, p in pp.named_parameters():
+            if k.endswith("weight"):
+                std = 0.3 if p.shape[1] == 1 else (1e-4 if p.shape[0] == 1 else 0.05)
+                p.copy_(std * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+    out = {"w." + k: npy(v) for k, v in pp.state_dict().items()}
+    x = frames(2, 72, 100, 99)
+    with torch.no_grad():
+        y = pp(x / 256.0) * 256.0
+        # one 64 -> 64 layer on a real feature map, for the single-layer tests
+        feat = pp.conv1(x[:1, :, :24, :40] / 256.0)      # a small crop keeps the fixture small
+        blk = pp.resBlocks[0]
+        mid = blk.lrelu(blk.conv1(feat))
+        res = blk.conv2(mid) + feat
+    out.update({"x": npy(x), "y": npy(y), "feat": npy(feat), "mid": npy(mid), "res0": npy(res)})
+    print("postprocess: |y - x| mean %.3f max %.3f (0..255 scale); feature rms %.3f -> %.3f" %
+          (float((y - x).abs().mean()), float((y - x).abs().max()), float(feat.pow(2).mean().sqrt()), float(res.pow(2).mean().sqrt())))
+    np.savez_compressed(os.path.join(OUT, "postprocess.npz"), **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "lossless":
+    if len(sys.argv) > 1 and sys.argv[1] == "postprocess":
+        main_postprocess()
+    elif len(sys.argv) > 1 and sys.argv[1] == "lossless":
         main_lossless()
     else:
         main()

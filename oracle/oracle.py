@@ -361,3 +361,48 @@ def code_gop(Y, C, mvs, temporal, hp_w: IWave, lp_w: IWave, q_hp, q_lp, num_me_s
             ry[r], ry[c] = inverse_mctf(ry[r], Hh_hat, mv, P, U)
             rc[r], rc[c] = inverse_mctf(rc[r], Hc_hat, mv, P, U, downscale=True)
     return np.concatenate([ry[i] for i in range(G)]), np.stack([rc[i] for i in range(G)]), sym
+
+
+# ---------------------------------------------------------------------------------------------------
+# PostProcess (postprocessing.py:20-44) -- fp32 tolerance oracle of the section 8f row
+class _PostProcessC(C.Structure):
+    _fields_ = [("conv1_w", C.c_void_p), ("conv1_b", C.c_void_p), ("res_w", C.c_void_p * 12), ("res_b", C.c_void_p * 12),
+                ("conv2_w", C.c_void_p), ("conv2_b", C.c_void_p), ("conv3_w", C.c_void_p), ("conv3_b", C.c_void_p)]
+
+
+class PostProcess:
+    """Weights of a PostProcess module from a state_dict-like mapping (keys conv1.weight, resBlocks.0.conv1.weight, ...)."""
+
+    def __init__(self, sd, prefix=""):
+        g = lambda k: _a(sd[prefix + k])  # noqa: E731
+        self.keep = {k: g(k) for k in ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "conv3.weight", "conv3.bias"] +
+                     [f"resBlocks.{i}.conv{j}.{t}" for i in range(6) for j in (1, 2) for t in ("weight", "bias")]}
+        c = _PostProcessC()
+        c.conv1_w, c.conv1_b = self.keep["conv1.weight"].ctypes.data, self.keep["conv1.bias"].ctypes.data
+        c.conv2_w, c.conv2_b = self.keep["conv2.weight"].ctypes.data, self.keep["conv2.bias"].ctypes.data
+        c.conv3_w, c.conv3_b = self.keep["conv3.weight"].ctypes.data, self.keep["conv3.bias"].ctypes.data
+        for i in range(6):
+            for j in (1, 2):
+                c.res_w[2 * i + j - 1] = self.keep[f"resBlocks.{i}.conv{j}.weight"].ctypes.data
+                c.res_b[2 * i + j - 1] = self.keep[f"resBlocks.{i}.conv{j}.bias"].ctypes.data
+        self.c = c
+
+
+def postprocess(x, pp: PostProcess, in_mul=1.0 / 256.0, out_mul=256.0):
+    """dequantModule(x / 256) * 256 (pWave.py:300) on [N,1,H,W]."""
+    x = _a(x)
+    N, _, H, W = x.shape
+    y = np.empty_like(x)
+    lib().orc_postprocess(_p(x), C.byref(pp.c), C.c_float(in_mul), C.c_float(out_mul), _p(y), N, H, W)
+    return y
+
+
+def conv3x3(x, w, b, slope=1.0, res=None):
+    """nn.Conv2d(3x3, padding=1) (+ residual, + LeakyReLU) on ONE planar map [ci,H,W] -> [co,H,W]."""
+    x, w, b = _a(x), _a(w), _a(b)
+    ci, H, W = x.shape
+    co = w.shape[0]
+    out = np.empty((co, H, W), np.float32)
+    r = _a(res) if res is not None else None
+    lib().orc_conv3x3(_p(x), ci, _p(w), _p(b), co, _p(out), H, W, C.c_float(slope), _p(r) if r is not None else None)
+    return out

@@ -551,3 +551,74 @@ ORC_API void orc_dequantize(const float *s_hat, float q, int lossy, float *out, 
 {
     for (long i = 0; i < n; ++i) out[i] = lossy ? s_hat[i] / q : s_hat[i];
 }
+
+/* ---- PostProcess (pMCTF/layers/postprocessing.py:20-44) in plain fp32 ---------------------------
+ * nn.Conv2d(3x3, zero padding 1) on planar [C][H][W] maps: acc = bias, then fma over (ci, ky, kx) in that order.  The CUDA path
+ * evaluates the 64 -> 64 layers on the tensor cores with bf16 operands, so this is a TOLERANCE oracle (1e-3 on the [0,1] pixel
+ * scale), pinned to outputs of the reference's own module (tests/golden/postprocess.npz).                                      */
+static void conv3x3_planar(const float *in, int ci_n, const float *w, const float *b, int co_n, float *out, int H, int W,
+                           float slope, const float *res)
+{
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int co = 0; co < co_n; ++co)
+        for (int y = 0; y < H; ++y) {
+            float *o = out + ((size_t)co * H + y) * W;
+            for (int x = 0; x < W; ++x) o[x] = b[co];
+            for (int ci = 0; ci < ci_n; ++ci)
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int yy = y + ky - 1;
+                    if (yy < 0 || yy >= H) continue;
+                    const float *ip = in + ((size_t)ci * H + yy) * W;
+                    const float *wp = w + (((size_t)co * ci_n + ci) * 3 + ky) * 3;
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float wv = wp[kx];
+                        const int x0 = kx == 0 ? 1 : 0, x1 = kx == 2 ? W - 1 : W;
+                        for (int x = x0; x < x1; ++x) o[x] = __builtin_fmaf(wv, ip[x + kx - 1], o[x]);
+                    }
+                }
+            if (res) {
+                const float *rp = res + ((size_t)co * H + y) * W;
+                for (int x = 0; x < W; ++x) o[x] = o[x] + rp[x];
+            }
+            if (slope != 1.0f)
+                for (int x = 0; x < W; ++x) o[x] = o[x] >= 0.0f ? o[x] : o[x] * slope;
+        }
+}
+
+typedef struct {
+    const float *conv1_w, *conv1_b;     /* [64,1,3,3] */
+    const float *res_w[12], *res_b[12]; /* resBlocks.{i}.conv1 / conv2: [64,64,3,3] */
+    const float *conv2_w, *conv2_b, *conv3_w, *conv3_b;
+} orc_postprocess_t;
+
+/* y = PostProcess(x * in_mul) * out_mul on [N,1,H,W]  (pWave.py:300: in_mul = 1/256, out_mul = 256) */
+ORC_API void orc_postprocess(const float *x, const orc_postprocess_t *p, float in_mul, float out_mul, float *y, int N, int H, int W)
+{
+    const size_t px = (size_t)H * W;
+    float *xs = (float *)malloc(sizeof(float) * px), *c1 = (float *)malloc(sizeof(float) * 64 * px);
+    float *a = (float *)malloc(sizeof(float) * 64 * px), *t = (float *)malloc(sizeof(float) * 64 * px);
+    float *o = (float *)malloc(sizeof(float) * px);
+    for (int n = 0; n < N; ++n) {
+        for (size_t i = 0; i < px; ++i) xs[i] = x[n * px + i] * in_mul;
+        conv3x3_planar(xs, 1, p->conv1_w, p->conv1_b, 64, c1, H, W, 1.0f, NULL);
+        memcpy(a, c1, sizeof(float) * 64 * px);
+        for (int r = 0; r < 6; ++r) {   /* ResBlock: conv1 -> LeakyReLU(0.2) -> conv2, + input (:14-18) */
+            conv3x3_planar(a, 64, p->res_w[2 * r], p->res_b[2 * r], 64, t, H, W, 0.2f, NULL);
+            float *nx = (float *)malloc(sizeof(float) * 64 * px);
+            conv3x3_planar(t, 64, p->res_w[2 * r + 1], p->res_b[2 * r + 1], 64, nx, H, W, 1.0f, a);
+            memcpy(a, nx, sizeof(float) * 64 * px);
+            free(nx);
+        }
+        conv3x3_planar(a, 64, p->conv2_w, p->conv2_b, 64, t, H, W, 1.0f, c1);   /* conv2(tmp) + conv1 (:40) */
+        conv3x3_planar(t, 64, p->conv3_w, p->conv3_b, 1, o, H, W, 1.0f, NULL);
+        for (size_t i = 0; i < px; ++i) y[n * px + i] = (xs[i] + o[i]) * out_mul;   /* x + tmp (:43) */
+    }
+    free(xs); free(c1); free(a); free(t); free(o);
+}
+
+/* one layer, planar in / out (tests of the single tensor-core convolution) */
+ORC_API void orc_conv3x3(const float *in, int ci, const float *w, const float *b, int co, float *out, int H, int W, float slope,
+                         const float *res)
+{
+    conv3x3_planar(in, ci, w, b, co, out, H, W, slope, res);
+}
