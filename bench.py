@@ -230,6 +230,71 @@ def profiled_traffic():
     return None
 
 
+PP_FLOPS_PER_PX = 2 * 9 * (1 * 64 + 13 * 64 * 64 + 64 * 1)   # the 15 3x3 convolutions of postprocessing.py:20-44 (2 per MAC)
+
+
+def run_postprocess(pkg, dev, pk):
+    """the PostProcess filter pWave++ applies to every reconstructed plane (pWave.py:299-300), on 1080p
+    luma planes.  Secondary block: NOT part of the headline metric (north_star's path ends at the synthesis transform).  Reports
+    the whole filter (15 layers incl. the CUDA-core 1 -> 64 layer and the layout conversions) against the measured bf16 peak, and
+    the same module on stock torch ops (cuDNN, channels_last; TF32 and fp32)."""
+    import torch
+    torch.manual_seed(3)
+    m = pkg.PostProcess().to(dev).eval()
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if k.endswith("weight"):
+                p.normal_(0, 0.3 if p.shape[1] == 1 else (1e-4 if p.shape[0] == 1 else 0.05))
+            else:
+                p.normal_(0, 0.05)
+    n, hp, wp = 4, 1152, 1920
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = (torch.nn.functional.avg_pool2d(torch.rand((n, 1, hp + 4, wp + 4), device=dev, generator=g), 5, 1, 0) * 255).round().contiguous()
+
+    def timed(fn, reps):
+        for _ in range(2):
+            y = fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            y = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps, y
+
+    with torch.no_grad():
+        ms, y = timed(lambda: m(x, 1.0 / 256.0, 256.0), 5)
+        stock = {}
+        import torch.nn.functional as F
+
+        def stock_fwd():
+            xs = (x / 256.0).contiguous(memory_format=torch.channels_last)
+            c1 = m.conv1(xs)
+            t = c1
+            for b in m.resBlocks:
+                t = b.conv2(F.leaky_relu(b.conv1(t), 0.2)) + t
+            return (xs + m.conv3(m.conv2(t) + c1)) * 256.0
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            try:
+                sms, ys = timed(stock_fwd, 2)
+                stock["tf32" if tf32 else "fp32"] = {"ms_per_plane": sms / n, "max_abs_diff_vs_ours_255": float((ys - y).abs().max())}
+            except Exception as ex:   # out of memory on a small device etc.: informational only
+                stock["tf32" if tf32 else "fp32"] = {"error": str(ex)[:100]}
+        torch.backends.cudnn.allow_tf32 = True
+    px = n * hp * wp
+    tf = PP_FLOPS_PER_PX * px / (ms * 1e-3) / 1e12
+    return {"what": "PostProcess (postprocessing.py:20-44; 6 ResBlocks, 64 channels) on 4 luma planes 1152x1920: dequantModule(x/256)*256; "
+                    "64->64 layers as tcgen05 bf16 implicit GEMMs (fp32 accumulation in TMEM), fp32 residual stream",
+            "ms_per_plane": ms / n, "planes_per_s": n / (ms * 1e-3), "frames_per_s_420": n / (ms * 1e-3) / 1.5,
+            "algorithmic_flops_per_px": PP_FLOPS_PER_PX,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
+                         "peak_source": f"{pk['source']} bf16 dense, sustained",
+                         "scope": "the whole filter call (15 launches per plane incl. the 1 -> 64 CUDA-core layer and the 64 -> 1 layer padded to N = 16)"},
+            "torch_gpu_baseline": stock}
+
+
 def run_uvg(args, pkg, G, par, model, dev, rank, world):
     """BASELINE configs[3] as written: 7 synthetic 1080p sequences x 96 frames (6 GOP-16s each) x the q_index list of
     test_pMCTF_flex.py:436-443, FLATTENED into 252 work items (q_index, sequence, gop), sharded round-robin over the ranks
@@ -442,6 +507,7 @@ def main():
     ap.add_argument("--no-uvg", action="store_true", help="skip the configs[3] block (7 sequences x 6 GOPs x 6 q_index points, strong scaling)")
     ap.add_argument("--uvg-sequences", type=int, default=7)
     ap.add_argument("--no-int8-peak", action="store_true", help="skip measuring the int8 dense peak of this GPU")
+    ap.add_argument("--no-postprocess", action="store_true", help="skip the PostProcess block (section 8f row 2, secondary)")
     ap.add_argument("--workload", default="gop16", choices=["gop16", "train"],
                     help="gop16: the headline metric (default); train: BASELINE configs[4] training step (not the headline)")
     args = ap.parse_args()
@@ -586,6 +652,12 @@ def main():
             torch.distributed.destroy_process_group()
         return
     pk = peaks()
+    ppb = None
+    if world == 1 and not args.no_postprocess and args.frames == FRAMES:
+        try:
+            ppb = run_postprocess(pkg, dev, pk)
+        except Exception as ex:   # a secondary block must never take the headline line down
+            ppb = {"error": str(ex)[:200]}
     # --- roofline of the dominant kernel -------------------------------------------------------------------
     mode = pkg.ops.get_conv_mode()
     flops = ks["pixels"] * pkg.ops.PU_FLOPS_PER_PX
@@ -661,7 +733,7 @@ def main():
                        "streams": "1" if args.single_stream else "2 per GPU: luma chain | chroma chain (independent on the path)",
                        "parallelism": f"gop-sharded dp{world}, all_gather of per-frame statistics per step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "torch_gpu_baseline": torch_gpu, "uvg": uvg,
+            "torch_gpu_baseline": torch_gpu, "uvg": uvg, "postprocess": ppb,
             "quality": {"mean_psnr_yuv_db": float(psnr[torch.isfinite(psnr)].mean()), "frames": int(psnr.numel())}}
     emit(line)
     if world > 1:

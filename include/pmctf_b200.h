@@ -272,14 +272,16 @@ typedef struct {
 long long pmctf_pp_packed_bytes(int co);
 /* OIHW fp32 [co,64,3,3] (co = 64, or 1..16) -> operand image */
 int pmctf_pp_pack_conv(const float *w, int co, void *packed, void *stream);
-/* conv1: x [N,1,H,W] fp32 (scaled by in_mul) -> NHWC 64-channel feature map, fp32 and bf16 copies */
+/* Feature-map layouts between the layers (chunk-planar, so that one thread per pixel is coalesced on both sides of the tensor
+ * core): bf16 operands [N][8][H][W][8] (channel c of pixel (y,x) at ((n*8 + c/8)*H*W + y*W + x)*8 + c%8), fp32 [N][16][H][W][4].
+ * conv1: x [N,1,H,W] fp32 (scaled by in_mul) -> 64-channel feature map, fp32 and bf16 copies */
 int pmctf_pp_conv_in(const float *x, const float *w, const float *b, float in_mul, float *out_f32, void *out_bf16, int N, int H, int W,
                      void *stream);
 /* fp32 -> bf16 (RN), n a multiple of 4 */
 int pmctf_pp_to_bf16(const float *in, void *out, long long n, void *stream);
-/* One 3x3 convolution 64 -> co on the tensor cores: in_bf16 NHWC [N,H,W,64]; co == 64: out = lrelu_slope(conv + bias [+ residual
- * NHWC fp32]) written as fp32 and / or bf16 NHWC (either may be NULL); co == 1: y_plane[N,1,H,W] = (x_plane * in_mul + conv +
- * bias) * out_mul (postprocessing.py:41-44 with the scaling of pWave.py:300). */
+/* One 3x3 convolution 64 -> co on the tensor cores: in_bf16 [N][8][H][W][8]; co == 64: out = lrelu_slope(conv + bias [+ residual
+ * fp32 [N][16][H][W][4]]) written as fp32 [N][16][H][W][4] and / or bf16 [N][8][H][W][8] (either may be NULL); co == 1:
+ * y_plane[N,1,H,W] = (x_plane * in_mul + conv + bias) * out_mul (postprocessing.py:41-44 with the scaling of pWave.py:300). */
 int pmctf_pp_conv64(const void *in_bf16, const void *packed_w, const float *bias, int co, const float *residual, float lrelu_slope,
                     float *out_f32, void *out_bf16, const float *x_plane, float in_mul, float out_mul, float *y_plane, int N, int H,
                     int W, void *stream);

@@ -12,8 +12,12 @@
 // group of 8 channels, K-major / un-swizzled, so a filter tap is only a different descriptor start address; one MMA
 // (M = 128 pixels, N = 64, K = 16) consumes two planes (leading byte offset = plane size).  36 MMAs per 128-pixel block.
 //
+// Feature maps live in HBM in CHUNK-PLANAR layouts chosen so that one thread per pixel is fully coalesced on both sides of the
+// tensor core: bf16 operands as [N][C/8][H][W][8] (a pixel's 8 channels = one 16-byte operand record; a warp's 32 pixels of a
+// tile row = 512 contiguous bytes), fp32 residual stream as [N][C/4][H][W][4].
+//
 // CTA (1 per SM, persistent over tiles of 16 x 30 outputs = 4 blocks): warps 0-3 epilogue (TMEM lane quarters), warps 4-7 load
-// the next input tile (16-byte loads from the NHWC bf16 activations, zero padding), warp 8 issues the MMAs.  Two input buffers
+// the next input tile (16-byte loads of operand records, zero padding), warp 8 issues the MMAs.  Two input buffers
 // and two sets of four accumulators (all 512 TMEM columns), so the loads of tile t+1 and the epilogue of tile t-1 overlap the MMAs
 // of tile t.  All 9 x 64 x 64 weights stay resident in shared memory (72 KB, one TMA bulk copy per CTA).
 //
@@ -43,7 +47,8 @@ constexpr int WMAX = 36 * 64 * 32;                   // 73 728 B: [tap][k-step][
 constexpr int SM_W = 0;
 constexpr int SM_IN = SM_W + WMAX;
 constexpr int SM_BAR = SM_IN + 2 * INBUF;
-constexpr int SMEM_BYTES = SM_BAR + 128;
+constexpr int SM_BIAS = SM_BAR + 128;                // 64 floats
+constexpr int SMEM_BYTES = SM_BIAS + 256;
 static_assert(TH * P == NBLK * 128 && IN_R * P + 2 + 2 * P <= NPIX + 2 * P, "tile geometry");
 static_assert((NBLK - 1) * 128 + 127 + 2 * P + 2 < NPIX, "operand reads stay inside the plane");
 static_assert(SM_IN % 128 == 0 && INBUF % 16 == 0 && SM_BAR % 8 == 0 && SMEM_BYTES <= 227 * 1024, "shared memory");
@@ -75,12 +80,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 }
 
 struct ConvD {
-    const __nv_bfloat16 *in;      // NHWC bf16, 64 channels
+    const __nv_bfloat16 *in;      // bf16 [N][8][H][W][8], 64 channels
     const uint8_t *wimg;          // packed operand image (pp_pack_kernel)
     const float *bias;            // [co]
-    const float *res;             // NHWC fp32 64 channels, added after the bias (skip connection), or null
-    float *out_f32;               // NHWC fp32 64 channels, or null
-    __nv_bfloat16 *out_bf16;      // NHWC bf16 64 channels, or null
+    const float *res;             // fp32 [N][16][H][W][4], added after the bias (skip connection), or null
+    float *out_f32;               // fp32 [N][16][H][W][4], or null
+    __nv_bfloat16 *out_bf16;      // bf16 [N][8][H][W][8], or null
     const float *x_plane;         // last layer (co == 1): y = (x * in_mul + conv) * out_mul on [N,1,H,W] planes
     float *y_plane;
     float slope, in_mul, out_mul; // LeakyReLU slope (1 = identity)
@@ -114,6 +119,7 @@ __global__ void __launch_bounds__(NT, 1) pp_conv64_kernel(const __grid_constant_
         umma::bulk_g2s(umma::smem_u32(smem + SM_W), a.wimg, WBYTES, umma::smem_u32(bars + 8));
     }
     if (warp == MMA_WARP) umma::tmem_alloc(tmem_slot, 512);
+    if (tid < 64) reinterpret_cast<float *>(smem + SM_BIAS)[tid] = tid < a.co ? a.bias[tid] : 0.0f;
     // the over-read records behind the tile (they only feed junk rows of the last block) hold zeros
     for (int i = tid; i < 2 * (C / 8) * (NPIX - IN_R * P); i += NT) {
         const int buf = i / ((C / 8) * (NPIX - IN_R * P)), j = i - buf * ((C / 8) * (NPIX - IN_R * P));
@@ -142,21 +148,22 @@ __global__ void __launch_bounds__(NT, 1) pp_conv64_kernel(const __grid_constant_
             const int n = tile / (tiles_x * tiles_y), trem = tile - n * (tiles_x * tiles_y);
             const int ty = trem / tiles_x, y0 = ty * TH, x0 = (trem - ty * tiles_x) * TW;
             uint8_t *dst = smem + SM_IN + buf * INBUF;
-            const __nv_bfloat16 *src = a.in + (long long)n * H * W * C;
-            constexpr int ITEMS = IN_R * P * (C / 8), PER = (ITEMS + 32 * LOAD_WARPS - 1) / (32 * LOAD_WARPS);
+            const long long plane_px = (long long)H * W;
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.in) + (long long)n * (C / 8) * plane_px;   // one uint4 = one operand record
+            constexpr int ITEMS = IN_R * P * (C / 8), PER = ITEMS / (32 * LOAD_WARPS);
+            static_assert(ITEMS % (32 * LOAD_WARPS) == 0 && (IN_R * P) % 32 == 0, "a loader warp = 32 consecutive pixels of one chunk");
             uint4 v[PER];
 #pragma unroll
-            for (int k = 0; k < PER; ++k) {   // all loads of a thread in flight together
-                const int i = lt + k * 32 * LOAD_WARPS, px = i >> 3, ch = i & 7;
+            for (int k = 0; k < PER; ++k) {   // all loads of a thread in flight together; a warp = 32 consecutive pixels of one row and chunk
+                const int i = lt + k * 32 * LOAD_WARPS, ch = i / (IN_R * P), px = i - ch * (IN_R * P);
                 const int r = px >> 5, c = px & 31, gy = y0 - 1 + r, gx = x0 - 1 + c;
                 v[k] = make_uint4(0u, 0u, 0u, 0u);
-                if (i < ITEMS && gy >= 0 && gy < H && gx >= 0 && gx < W)
-                    v[k] = __ldg(reinterpret_cast<const uint4 *>(src + ((long long)gy * W + gx) * C + ch * 8));
+                if (gy >= 0 && gy < H && gx >= 0 && gx < W) v[k] = __ldg(src + ch * plane_px + (long long)gy * W + gx);
             }
 #pragma unroll
             for (int k = 0; k < PER; ++k) {
-                const int i = lt + k * 32 * LOAD_WARPS, px = i >> 3, ch = i & 7;
-                if (i < ITEMS) *reinterpret_cast<uint4 *>(dst + ch * PLANE + px * 16) = v[k];
+                const int i = lt + k * 32 * LOAD_WARPS, ch = i / (IN_R * P), px = i - ch * (IN_R * P);
+                *reinterpret_cast<uint4 *>(dst + ch * PLANE + px * 16) = v[k];
             }
             umma::fence_proxy_async();
             mbar_arrive(in_full + 8 * buf);
@@ -175,19 +182,21 @@ __global__ void __launch_bounds__(NT, 1) pp_conv64_kernel(const __grid_constant_
             }
             umma::fence_after_sync();
             if (umma::elect_one()) {
-                const uint32_t in_s = umma::smem_u32(smem + SM_IN + buf * INBUF), w_s = umma::smem_u32(smem + SM_W);
+                // descriptors: the start address sits in the low 14 bits (16-byte units) and never carries out of them (shared memory
+                // < 256 KB), so a tap / k-step / block is ONE 64-bit add of a constant to a base descriptor
+                const uint64_t a0 = umma::smem_desc(umma::smem_u32(smem + SM_IN + buf * INBUF), PLANE, 128);
+                const uint64_t b0 = umma::smem_desc(umma::smem_u32(smem + SM_W), CO_PAD * 16, 128);
 #pragma unroll 1
                 for (int blk = 0; blk < NBLK; ++blk) {
                     const uint32_t d = tbase + buf * ACC_COLS + blk * 64;
+                    const uint64_t ab = a0 + (uint64_t)(blk * 128);
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int off = (tap / 3) * P + (tap % 3);
 #pragma unroll
-                        for (int ks = 0; ks < C / 16; ++ks) {
-                            const uint64_t ad = umma::smem_desc(in_s + (2 * ks) * PLANE + (blk * 128 + off) * 16, PLANE, 128);
-                            const uint64_t bd = umma::smem_desc(w_s + (tap * (C / 16) + ks) * (CO_PAD * 32), CO_PAD * 16, 128);
-                            mma_bf16(d, ad, bd, idesc_bf16(CO_PAD), (tap | ks) ? 1u : 0u);
-                        }
+                        for (int ks = 0; ks < C / 16; ++ks)
+                            mma_bf16(d, ab + (uint64_t)((2 * ks) * (PLANE / 16) + off), b0 + (uint64_t)((tap * (C / 16) + ks) * (CO_PAD * 2)),
+                                     idesc_bf16(CO_PAD), (tap | ks) ? 1u : 0u);
                     }
                 }
                 umma::commit(in_empty + 8 * buf);    // input buffer free once these MMAs have completed ...
@@ -211,23 +220,34 @@ __global__ void __launch_bounds__(NT, 1) pp_conv64_kernel(const __grid_constant_
                 const int m = blk * 128 + quarter * 32 + lane;
                 const int r = m >> 5, c = m & 31, gy = y0 + r, gx = x0 + c;
                 const bool valid = c < TW && gy < H && gx < W;
-                const long long pix = ((long long)n * H + gy) * W + gx;
+                const long long plane_px = (long long)H * W, pix = (long long)gy * W + gx;
+                const float *sbias = reinterpret_cast<const float *>(smem + SM_BIAS);
                 const uint32_t taddr = tbase + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS + blk * 64;
                 if (CO_PAD == 64) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {   // 16 channels per round
                         uint32_t o[16];
                         umma::tmem_ld16(taddr + 16 * q, o);
+                        float4 rr[4];
+                        const bool use_res = a.res != nullptr && valid;
+                        if (use_res) {   // lanes = consecutive pixels: 512 contiguous bytes per load instruction
+                            const float4 *rp = reinterpret_cast<const float4 *>(a.res) + ((long long)n * 16 + 4 * q) * plane_px + pix;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) rr[j] = __ldg(rp + j * plane_px);
+                        }
                         umma::tmem_ld_wait();
                         if (valid) {
                             float v[16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(o[j]) + __ldg(a.bias + 16 * q + j);
-                            if (a.res) {
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 bb = *reinterpret_cast<const float4 *>(sbias + 16 * q + 4 * j);
+                                v[4 * j] = __uint_as_float(o[4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(o[4 * j + 1]) + bb.y;
+                                v[4 * j + 2] = __uint_as_float(o[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(o[4 * j + 3]) + bb.w;
+                            }
+                            if (use_res) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    const float4 rr = __ldg(reinterpret_cast<const float4 *>(a.res + pix * C + 16 * q) + j);
-                                    v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+                                    v[4 * j] += rr[j].x; v[4 * j + 1] += rr[j].y; v[4 * j + 2] += rr[j].z; v[4 * j + 3] += rr[j].w;
                                 }
                             }
                             if (a.slope != 1.0f) {
@@ -235,9 +255,9 @@ __global__ void __launch_bounds__(NT, 1) pp_conv64_kernel(const __grid_constant_
                                 for (int j = 0; j < 16; ++j) v[j] = v[j] >= 0.0f ? v[j] : v[j] * a.slope;
                             }
                             if (a.out_f32) {
+                                float4 *op = reinterpret_cast<float4 *>(a.out_f32) + ((long long)n * 16 + 4 * q) * plane_px + pix;
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    reinterpret_cast<float4 *>(a.out_f32 + pix * C + 16 * q)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                                for (int j = 0; j < 4; ++j) op[j * plane_px] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                             }
                             if (a.out_bf16) {
                                 uint32_t pk[8];
@@ -246,9 +266,9 @@ __global__ void __launch_bounds__(NT, 1) pp_conv64_kernel(const __grid_constant_
                                     const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
                                     pk[j] = *reinterpret_cast<const uint32_t *>(&b2);
                                 }
-                                uint4 *op = reinterpret_cast<uint4 *>(a.out_bf16 + pix * C + 16 * q);
+                                uint4 *op = reinterpret_cast<uint4 *>(a.out_bf16) + ((long long)n * 8 + 2 * q) * plane_px + pix;
                                 op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                                op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                                op[plane_px] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                             }
                         }
                     }
@@ -257,8 +277,8 @@ __global__ void __launch_bounds__(NT, 1) pp_conv64_kernel(const __grid_constant_
                     umma::tmem_ld16(taddr, o);
                     umma::tmem_ld_wait();
                     if (valid) {
-                        const float t = __uint_as_float(o[0]) + __ldg(a.bias);
-                        a.y_plane[pix] = (__ldg(a.x_plane + pix) * a.in_mul + t) * a.out_mul;
+                        const float t = __uint_as_float(o[0]) + sbias[0];
+                        a.y_plane[(long long)n * plane_px + pix] = (__ldg(a.x_plane + (long long)n * plane_px + pix) * a.in_mul + t) * a.out_mul;
                     }
                 }
             }
@@ -287,13 +307,13 @@ __global__ void __launch_bounds__(256) pp_conv_in_kernel(const float *__restrict
     for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
     if (threadIdx.x < 64) sb[threadIdx.x] = b[threadIdx.x];
     __syncthreads();
-    const long long total = (long long)N * H * W * 4;   // one thread = one pixel x 16 channels
+    const long long plane_px = (long long)H * W, all_px = (long long)N * plane_px, total = all_px * 4;   // one thread = one pixel x 16 channels
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int q = (int)(i & 3);
-        const long long pix = i >> 2;
-        const int gx = (int)(pix % W), gy = (int)((pix / W) % H);
-        const long long n = pix / ((long long)W * H);
-        const float *xp = x + n * H * W;
+        const int q = (int)(i / all_px);                 // consecutive threads = consecutive pixels (coalesced both ways)
+        const long long apix = i - q * all_px;
+        const long long n = apix / plane_px, pix = apix - n * plane_px;
+        const int gx = (int)(pix % W), gy = (int)(pix / W);
+        const float *xp = x + n * plane_px;
         float v[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
@@ -308,18 +328,18 @@ __global__ void __launch_bounds__(256) pp_conv_in_kernel(const float *__restrict
             for (int k = 0; k < 9; ++k) acc = fmaf(sw[(16 * q + j) * 9 + k], v[k], acc);
             o[j] = acc;
         }
+        float4 *of = reinterpret_cast<float4 *>(out_f32) + (n * 16 + 4 * q) * plane_px + pix;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            reinterpret_cast<float4 *>(out_f32 + pix * 64 + 16 * q)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) of[j * plane_px] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const __nv_bfloat162 b2 = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
             pk[j] = *reinterpret_cast<const uint32_t *>(&b2);
         }
-        uint4 *op = reinterpret_cast<uint4 *>(out_bf16 + pix * 64 + 16 * q);
+        uint4 *op = reinterpret_cast<uint4 *>(out_bf16) + (n * 8 + 2 * q) * plane_px + pix;
         op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        op[plane_px] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
 }
 
@@ -335,7 +355,7 @@ __global__ void pp_pack_kernel(const float *__restrict__ w, int co, int co_pad, 
     }
 }
 
-// plain fp32 NHWC -> bf16 NHWC (operand copy of an fp32 tensor that was produced elsewhere)
+// fp32 -> bf16 element-wise (RN); layout conversions are the caller's business
 __global__ void __launch_bounds__(256) pp_to_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, long long n4)
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {

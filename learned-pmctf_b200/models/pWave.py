@@ -133,6 +133,14 @@ class pWaveTransform:
         from .. import train
         return train.needs_grad(*ts, self)
 
+    def post_process(self, x_hat):
+        """dequantModule(x_hat / 256) * 256 (pWave.py:299-300): the scaling is fused into our PostProcess kernels; a stock torch
+        module (the reference's own, or a test double) is called the reference's way."""
+        from ..layers.postprocessing import PostProcess
+        if isinstance(self.dequantModule, PostProcess):
+            return self.dequantModule(x_hat, 1.0 / self.dynamic_range, self.dynamic_range)
+        return self.dequantModule(x_hat / self.dynamic_range) * self.dynamic_range
+
     def _round(self, s):
         """RoundNoGradient (layers.py:71-80) on a clamped band: the fused kernel with q = 1 on the evaluation path."""
         if self._train(s):
@@ -246,7 +254,7 @@ class pWaveTransform:
         hat = self.quantize_subbands(y, q_scale, q_scale_ll)
         x_hat = self.decode_dequant(hat, q_scale, q_scale_ll)
         if post_process and self.lossy and hasattr(self, "dequantModule"):
-            x_hat = self.dequantModule(x_hat / self.dynamic_range) * self.dynamic_range
+            x_hat = self.post_process(x_hat)
         return (x_hat, hat) if return_symbols else x_hat
 
 
@@ -254,7 +262,7 @@ class pWave(pWaveTransform, nn.Module):
     """Stand-alone hot-path subset of the reference's pWave (pWave.py:26-98): same constructor,
     same parameter names for the transform and the quantiser."""
 
-    def __init__(self, bitdepth=8, decomp_levels=4, lossy=True):
+    def __init__(self, bitdepth=8, decomp_levels=4, lossy=True, postprocess=False):
         super().__init__()
         self.bitdepth = 8
         self.dynamic_range = float(2 ** bitdepth)
@@ -266,6 +274,9 @@ class pWave(pWaveTransform, nn.Module):
         self.QP = nn.Parameter(torch.ones((2, 1, 1, 1), dtype=torch.float) * 1 / 16)      # pWave.py:84-85
         self.QP_ll = nn.Parameter(torch.ones((2, 1, 1, 1), dtype=torch.float) * 1 / 16)
         self._qc = _QCache()
+        if postprocess and lossy:   # pWave.py:61-62; optional here so that hot-path-only checkpoints keep loading
+            from ..layers.postprocessing import PostProcess
+            self.dequantModule = PostProcess(in_channels=1, out_channels=1)
 
     def forward(self, x, q_index=None, qp_scale=None):
         """pWave.forward (pWave.py:231-242): same signature, same step derivation, then forward_one_channel."""
@@ -293,6 +304,8 @@ class pWave(pWaveTransform, nn.Module):
             for b in BANDS:
                 subbands_hat[lvl][b] = self._round(self.quantize_subband(y[lvl][b], q_scale))
         x_hat = self.decode(self.dequantize_subbands(subbands_hat, q_scale, q_scale_ll))
+        if self.lossy and hasattr(self, "dequantModule"):          # pWave.py:298-300
+            x_hat = self.post_process(x_hat)
         nan = torch.full((), float("nan"), device=x.device)
         return {"x_hat": x_hat, "bits": None, "likelihoods": None, "subbands": subbands_hat, "bpp_total": nan, "bits_total": nan,
                 "mse": torch.mean((x - x_hat) ** 2)}

@@ -106,13 +106,13 @@ class MCTFMixin:
 
 class pMCTF(MCTFMixin, nn.Module):
     def __init__(self, bitdepth=8, decomp_levels=4, lossy=True, two_stage_me=True, num_me_stages=2, quant_stage=True,
-                 **kwargs):
+                 postprocess=False, **kwargs):
         super().__init__()
         self.bitdepth = bitdepth
         self.dynamic_range = 2 ** bitdepth - 1
         self.lossy = lossy
-        self.lp_coder = pWave(bitdepth, decomp_levels, lossy)
-        self.hp_coder = pWave(bitdepth, decomp_levels, lossy)
+        self.lp_coder = pWave(bitdepth, decomp_levels, lossy, postprocess=postprocess)
+        self.hp_coder = pWave(bitdepth, decomp_levels, lossy, postprocess=postprocess)
         self.temporal_filtering = nn.ModuleList([TemporalLifting(lossy=lossy) for _ in range(num_me_stages)])
         self.quant_stage = quant_stage
         if quant_stage:
@@ -133,7 +133,7 @@ class pMCTF(MCTFMixin, nn.Module):
 # grafted onto the reference's objects by accelerate(): the hot-path methods and the helpers they (and GopCodec) call.  The
 # reference's own forward / forward_one_channel / forward_one_stage / compress / decompress bodies stay: they sequence the
 # out-of-scope networks around these.
-_PWAVE_METHODS = ("encode", "decode", "decode_dequant", "encode_bands", "quantize_subband", "quantize_subbands",
+_PWAVE_METHODS = ("post_process", "encode", "decode", "decode_dequant", "encode_bands", "quantize_subband", "quantize_subbands",
                   "dequantize_subbands", "dequantize_subband", "spatial_wavelet_dec", "_q_float", "code_planes", "_train", "_round",
                   "q_pair", "_step_table", "band_layout")
 _MCTF_METHODS = ("motion_compensation", "forward_MCTF", "inverse_MCTF", "_temporal", "hp_qp_scale")
@@ -162,6 +162,10 @@ def accelerate(ref_model):
         wt = coder.wavelet_transform
         new = LiftingScheme2D(bitdepth=coder.bitdepth, lossy=coder.lossy).to(next(wt.parameters()).device)
         coder.wavelet_transform = adopt(new, wt)
+        dq = getattr(coder, "dequantModule", None)
+        if dq is not None and all(hasattr(dq, n) for n in ("resBlocks", "conv1", "conv2", "conv3")):   # the reference's PostProcess
+            from ...layers.postprocessing import PostProcess
+            coder.dequantModule = adopt(PostProcess().to(next(dq.parameters()).device), dq)
         for m in _PWAVE_METHODS:
             setattr(coder, m, types.MethodType(getattr(pWaveTransform, m), coder))
     for m in _MCTF_METHODS:

@@ -555,14 +555,34 @@ def postprocess(x: torch.Tensor, desc: "nat.PostProcessD", in_mul: float = 1.0, 
     return y
 
 
+def pp_layout_bf16(x: torch.Tensor) -> torch.Tensor:
+    """[N,64,H,W] float -> the operand layout of the PostProcess kernels: bf16 [N,8,H,W,8] (a pixel's 8 channels = one 16-byte record)."""
+    N, Cc, H, W = x.shape
+    return x.reshape(N, Cc // 8, 8, H, W).permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16)
+
+
+def pp_layout_f32(x: torch.Tensor) -> torch.Tensor:
+    """[N,64,H,W] float -> fp32 [N,16,H,W,4] (residual stream layout)."""
+    N, Cc, H, W = x.shape
+    return x.reshape(N, Cc // 4, 4, H, W).permute(0, 1, 3, 4, 2).contiguous().float()
+
+
+def pp_unlayout(t: torch.Tensor) -> torch.Tensor:
+    """[N,G,H,W,g] (either layout) -> [N,G*g,H,W] fp32."""
+    N, G, H, W, g = t.shape
+    return t.permute(0, 1, 4, 2, 3).reshape(N, G * g, H, W).float()
+
+
 def pp_conv64(x_bf16: torch.Tensor, packed_w: torch.Tensor, bias: torch.Tensor, co: int = 64, residual=None, slope: float = 1.0,
               want_f32: bool = True, want_bf16: bool = False):
-    """One tensor-core 3x3 convolution 64 -> 64 on an NHWC bf16 tensor [N,H,W,64] (building block of PostProcess; tests)."""
-    if x_bf16.dtype != torch.bfloat16 or not x_bf16.is_cuda or x_bf16.dim() != 4 or x_bf16.size(3) != 64 or not x_bf16.is_contiguous():
-        raise RuntimeError("pp_conv64 expects a contiguous CUDA bfloat16 tensor [N,H,W,64]")
-    N, H, W, _ = x_bf16.shape
-    of = torch.empty((N, H, W, 64), dtype=torch.float32, device=x_bf16.device) if want_f32 else None
-    ob = torch.empty((N, H, W, 64), dtype=torch.bfloat16, device=x_bf16.device) if want_bf16 else None
+    """One tensor-core 3x3 convolution 64 -> 64 on a bf16 feature map in operand layout [N,8,H,W,8] (building block of
+    PostProcess; tests).  residual / fp32 output: [N,16,H,W,4]."""
+    if x_bf16.dtype != torch.bfloat16 or not x_bf16.is_cuda or x_bf16.dim() != 5 or x_bf16.size(1) != 8 or x_bf16.size(4) != 8 \
+            or not x_bf16.is_contiguous():
+        raise RuntimeError("pp_conv64 expects a contiguous CUDA bfloat16 tensor [N,8,H,W,8] (ops.pp_layout_bf16)")
+    N, _, H, W, _ = x_bf16.shape
+    of = torch.empty((N, 16, H, W, 4), dtype=torch.float32, device=x_bf16.device) if want_f32 else None
+    ob = torch.empty((N, 8, H, W, 8), dtype=torch.bfloat16, device=x_bf16.device) if want_bf16 else None
     _launch(x_bf16.device, "pp_conv64", nat.lib().pmctf_pp_conv64, x_bf16.data_ptr(), packed_w.data_ptr(), bias.data_ptr(), co,
             residual.data_ptr() if residual is not None else None, slope, of.data_ptr() if of is not None else None,
             ob.data_ptr() if ob is not None else None, None, 1.0, 1.0, None, N, H, W)

@@ -1,0 +1,15 @@
+"""PostProcess on one 1080p luma plane for ncu."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import learned_pmctf_b200 as P
+torch.manual_seed(3)
+m = P.PostProcess().cuda().eval()
+with torch.no_grad():
+    for k, p in m.named_parameters():
+        p.normal_(0, 0.05)
+    x = (torch.rand(1, 1, 1152, 1920, device="cuda") * 255).round()
+    for _ in range(2):
+        y = m(x, 1 / 256.0, 256.0)
+torch.cuda.synchronize()
+print("done")

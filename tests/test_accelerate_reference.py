@@ -36,7 +36,8 @@ def test_accelerate_keeps_state_dict_and_swaps_hot_path(ref_model):
     for coder in (m.lp_coder, m.hp_coder):
         assert type(coder.wavelet_transform).__module__.startswith("learned_pmctf_b200")
         assert coder.wavelet_transform.lift_v is coder.wavelet_transform.lift_h
-        assert type(coder.dequantModule).__module__.startswith("pMCTF.")
+        assert type(coder.dequantModule).__module__.startswith("learned_pmctf_b200")      # PostProcess (section 8f row 2) is ours now
+        assert type(coder.context_fusion).__module__.startswith(("pMCTF.", "torch."))      # the entropy-parameter nets are not
         assert coder.encode.__func__ is sys.modules["learned_pmctf_b200.models.pWave"].pWaveTransform.encode
     assert type(m.optic_flow).__module__.startswith("pMCTF.") if hasattr(m, "optic_flow") else True
     assert m.forward_MCTF.__func__ is sys.modules["learned_pmctf_b200.models.video.pMCTF_L"].MCTFMixin.forward_MCTF
