@@ -291,6 +291,36 @@ long long pmctf_postprocess_workspace(int H, int W);
 int pmctf_postprocess(const float *x, const pmctf_postprocess_t *p, float in_mul, float out_mul, float *y, int N, int H, int W,
                       void *workspace, long long workspace_bytes, void *stream);
 
+/* ---- entropy-coder boundary ----------------------------------------------------------------
+ * HOST functions (plain host pointers, no stream): the 64-bit rANS coder of pMCTF/cpp/rans/rans.cpp:76-168,272-331 behind the
+ * sub-stream container of pMCTF/cpp/py_rans/py_rans.cpp:22-225 (what the reference binds as MLCodec_rans.RansEncoder /
+ * RansDecoder), and pmf_to_quantized_cdf of pMCTF/cpp/ops/ops.cpp:24-82 (MLCodec_CXX).  The rANS primitives are a restatement
+ * of rygorous/ryg_rans rans64.h @ c9d162d9 (un-vendored dependency of the reference); streams are byte-identical to the
+ * reference's.  cdfs: [cdf_num][cdf_stride] int32 rows, cdfs_sizes[i] valid entries each (the last interval is the escape to
+ * 4-bit bypass digits), offsets[i] = value of the first table entry.  Symbols with a negative index are skipped by the encoder.
+ * With multi_thread != 0 or stream_part > 1 every sub-stream has its own worker thread: encode / flush return at once and
+ * pmctf_rans_encoded_size / pmctf_rans_get_encoded_stream wait for the queued work. */
+int pmctf_pmf_to_quantized_cdf(const float *pmf, int n, int precision, unsigned *cdf /* n + 1 */);
+int pmctf_rans_encoder_create(int multi_thread, int stream_part, void **enc);
+int pmctf_rans_encoder_destroy(void *enc);
+int pmctf_rans_encoder_reset(void *enc);
+int pmctf_rans_encode_with_indexes(void *enc, const short *symbols, const short *indexes, long long n, const int *cdfs, int cdf_num,
+                                   int cdf_stride, const int *cdfs_sizes, const int *offsets);
+int pmctf_rans_encoder_flush(void *enc);
+long long pmctf_rans_encoded_size(void *enc);
+int pmctf_rans_get_encoded_stream(void *enc, unsigned char *out, long long capacity);
+int pmctf_rans_decoder_create(int stream_part, void **dec);
+int pmctf_rans_decoder_destroy(void *dec);
+int pmctf_rans_decoder_set_stream(void *dec, const unsigned char *bytes, long long n);
+int pmctf_rans_decode_stream(void *dec, const short *indexes, long long n, const int *cdfs, int cdf_num, int cdf_stride,
+                             const int *cdfs_sizes, const int *offsets, short *out);
+/* DEVICE: what entropy_models.py:37-40 and GaussianEncoder.build_indexes (:266-270) do with two blocking copies per coded step,
+ * in one pass: sym16 = int16(clamp(symbols, +-30000)), idx16 = int16(clamp((log(max(scales, 1e-5)) - log_scale_min) /
+ * log_scale_step, 0, scale_levels - 1)).  symbols / sym16 may both be NULL (decoder side: indexes only).  Inputs 16-byte,
+ * outputs 8-byte aligned. */
+int pmctf_gaussian_symbolize(const float *symbols, const float *scales, long long n, float log_scale_min, float log_scale_step,
+                             int scale_levels, short *sym16, short *idx16, void *stream);
+
 /* Unit test / timing probe of the tcgen05 (5th-generation tensor core) conventions the lifting convolutions are built
  * on: runs `n_ops` kind::i8 MMAs (M = 128, K = 32, s8 x s8 -> s32 in TMEM) per 128-row block on operands copied to
  * shared memory and returns the raw accumulators out[block][128][out_cols].  Offsets are bytes relative to the staged

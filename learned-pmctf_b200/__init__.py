@@ -7,6 +7,9 @@ Layout mirrors the reference package for the modules on the path:
     layers.lifting_1d                            PredictUpdate, iWave1D, split, merge
     layers.wavelet_transform                     LiftingScheme2D
     layers.postprocessing                        PostProcess (de-quantisation filter)
+    entropy_models.entropy_models                EntropyCoder, GaussianEncoder (rANS boundary)
+    entropy_models.gaussian_model                CompressionModel
+    models.MLCodec_rans / models.MLCodec_CXX     drop-ins for the reference's two pybind11 extensions (native coder behind the C ABI)
     models.pWave                                 pWave (transform + quantiser)
     models.video.pMCTF_L                         pMCTF (forward_MCTF / inverse_MCTF), accelerate()
     gop                                          dyadic GOP schedule (test_pMCTF_flex.py:131-291)

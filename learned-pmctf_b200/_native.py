@@ -13,7 +13,7 @@ ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("PMCTF_LIB") or os.path.join(_HERE, "lib", "libpmctf_b200.so")  # PMCTF_LIB: profiling builds only
 SOURCES = [os.path.join(_HERE, "csrc", "pmctf_kernels.cu"), os.path.join(_HERE, "csrc", "pmctf_umma_test.cu"),
            os.path.join(_HERE, "csrc", "pmctf_lift_tc.cu"), os.path.join(_HERE, "csrc", "pmctf_train.cu"),
-           os.path.join(_HERE, "csrc", "pmctf_pp.cu")]
+           os.path.join(_HERE, "csrc", "pmctf_pp.cu"), os.path.join(_HERE, "csrc", "pmctf_rans.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "pmctf_umma.cuh"), os.path.join(_HERE, "csrc", "pmctf_common.cuh")]
 INCLUDE = os.path.join(ROOT, "include")
 
@@ -105,6 +105,19 @@ SIGNATURES = {
     "pmctf_pp_conv64": [_P, _P, _P, _I, _P, _f, _P, _P, _P, _f, _f, _P, _I, _I, _I, _P],
     "pmctf_postprocess_workspace": [_I, _I],
     "pmctf_postprocess": [_P, C.POINTER(PostProcessD), _f, _f, _P, _I, _I, _I, _P, _LL, _P],
+    "pmctf_pmf_to_quantized_cdf": [_P, _I, _I, _P],
+    "pmctf_rans_encoder_create": [_I, _I, _P],
+    "pmctf_rans_encoder_destroy": [_P],
+    "pmctf_rans_encoder_reset": [_P],
+    "pmctf_rans_encode_with_indexes": [_P, _P, _P, _LL, _P, _I, _I, _P, _P],
+    "pmctf_rans_encoder_flush": [_P],
+    "pmctf_rans_encoded_size": [_P],
+    "pmctf_rans_get_encoded_stream": [_P, _P, _LL],
+    "pmctf_rans_decoder_create": [_I, _P],
+    "pmctf_rans_decoder_destroy": [_P],
+    "pmctf_rans_decoder_set_stream": [_P, _P, _LL],
+    "pmctf_rans_decode_stream": [_P, _P, _LL, _P, _I, _I, _P, _P, _P],
+    "pmctf_gaussian_symbolize": [_P, _P, _LL, _f, _f, _I, _P, _P, _P],
     "pmctf_frame_sse": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "pmctf_conv3x3": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pmctf_conv3x3_wgrad": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
@@ -112,7 +125,7 @@ SIGNATURES = {
     "pmctf_umma_selftest": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P],
 }
 _RESTYPES = {"pmctf_error_string": C.c_char_p, "pmctf_lift2d_workspace": C.c_longlong, "pmctf_pp_packed_bytes": C.c_longlong,
-             "pmctf_postprocess_workspace": C.c_longlong,
+             "pmctf_postprocess_workspace": C.c_longlong, "pmctf_rans_encoded_size": C.c_longlong,
              "pmctf_launch_count": C.c_ulonglong}
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
