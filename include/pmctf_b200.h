@@ -291,6 +291,57 @@ long long pmctf_postprocess_workspace(int H, int W);
 int pmctf_postprocess(const float *x, const pmctf_postprocess_t *p, float in_mul, float out_mul, float *y, int N, int H, int W,
                       void *workspace, long long workspace_bytes, void *stream);
 
+/* ---- four-step entropy-parameter network: pMCTF/layers/context_fusion_4step.py:23-249 ----------
+ * ContextFusionFourStep(num_features = 112) is evaluated once per coded subband (pWave.py:259-290, 405-421, 500-512): 22 dense
+ * 112 -> 112 3x3 convolutions and one 1x1 per subband (4.97 MFLOP per coefficient).  Those run as tcgen05 CTA-pair implicit GEMMs
+ * (cta_group::2, M = 256, N = 112, bf16 operands, fp32 accumulators in TMEM, inputs by TMA tensor loads, all weights of a layer
+ * resident in shared memory, half per CTA); the small layers around them are CUDA-core kernels.  Feature maps between the layers
+ * are chunk-planar: bf16 operands [N][14][H][W][8], fp32 [N][28][H][W][4].  Not bit-exact against fp32 (bf16 operands): the
+ * tests report parameter errors and final-symbol mismatch counts against the fp32 oracle. */
+long long pmctf_ctx_packed_bytes(int taps);
+/* OIHW fp32 [112,112,k,k] (taps = k*k = 9 or 1) -> bf16 operand images of both CTAs of a pair */
+int pmctf_ctx_pack_conv(const float *w, int taps, void *packed, void *stream);
+/* nn.Conv2d(1 or 2 -> 112, 3x3, padding 1) on single-channel planes x0 (and x1, or NULL): conv1_context (:47), y_spatial_prior_k.0
+ * (:62-86); w [112,cin,3,3]; writes the fp32 map and its bf16 operand copy */
+int pmctf_ctx_conv_in(const float *x0, const float *x1, const float *w, const float *b, float *out_f32, void *out_bf16, int N, int H, int W,
+                      void *stream);
+/* One 112 -> 112 convolution on the tensor cores (ContextResidual.conv1 / conv2 :12-14, DepthConv.conv1 with taps = 1):
+ * out = lrelu_slope(conv(in) + bias [+ res] [+ res2]) as fp32 and / or bf16 (either may be NULL) */
+int pmctf_ctx_conv112(const void *in_bf16, const void *packed_w, int taps, const float *bias, const float *res, const float *res2,
+                      float lrelu_slope, float *out_f32, void *out_bf16, int N, int H, int W, void *stream);
+/* lower_level_subband (:49-52): nearest x2 upsampling of prev [N,1,h,w] + nn.Conv2d(1 -> 1, 3x3) -> out [N,1,2h,2w] */
+int pmctf_ctx_lower_subband(const float *prev, const float *w, const float *b, float *out, int N, int h, int w_, void *stream);
+/* DepthConvBlock(112, 2) behind its first 1x1 convolution (pMCTF/layers/video/layers.py:113-172): t1 = LeakyReLU_0.01(conv1(ctx))
+ * (a pmctf_ctx_conv112 call with taps = 1) -> depthwise 3x3 -> 1x1 to 2 channels + adaptor(ctx) -> ConvFFN; all weights fp32 in
+ * their state_dict layouts.  scales / means: [N,1,H,W] (chunk(2, dim=1) of the block's output, :172) */
+typedef struct {
+    const float *dw_w, *dw_b;   /* block.0.depth_conv  [112,1,3,3], [112] */
+    const float *pw_w, *pw_b;   /* block.0.conv2       [2,112,1,1], [2] */
+    const float *ad_w, *ad_b;   /* block.0.adaptor     [2,112,1,1], [2] */
+    const float *f1_w, *f1_b;   /* block.1.conv.0      [8,2,1,1], [8] */
+    const float *f2_w, *f2_b;   /* block.1.conv.2      [2,8,1,1], [2] */
+} pmctf_ctx_dcb_t;
+int pmctf_ctx_dcb_tail(const float *t1, const float *ctx_f32, const pmctf_ctx_dcb_t *p, float *scales, float *means, int N, int H, int W,
+                       void *stream);
+/* the 112 -> 2 1x1 convolution that ends y_spatial_prior_k_out (:66-70) on an fp32 map; w [2,112,1,1] */
+int pmctf_ctx_head(const float *feat, const float *w, const float *b, float *scales, float *means, int N, int H, int W, void *stream);
+/* process_with_mask (:115-125) of step `step` (0..3, mask = pixels with 2*(y&1) + (x&1) == step): on the mask
+ * x_q = rint(x - mean), x_hat = x_q + mean, s_hat = scale, x_res = x - mean, written into the running planes (step 0 zeroes the
+ * rest; x_q / x_res may be NULL).  Decoder form (:209-247): x == NULL and dec_sym = the step's decoded symbols (int16, full
+ * plane); x == NULL and dec_sym == NULL: nothing but idx16 is written (what the decoder needs BEFORE it can read the step's
+ * symbols).  idx16 / sym16 (may be NULL): the step's full planes as GaussianEncoder.encode derives them from the masked planes
+ * (entropy_models.py:37-40,266-275) -- symbol and scale-table index on the mask, 0 and the index of scale 1e-5 elsewhere. */
+typedef struct {
+    const float *x;
+    const short *dec_sym;
+    const float *scales, *means;
+    float *x_hat, *x_q, *s_hat, *x_res;
+    short *sym16, *idx16;
+    float log_scale_min, log_scale_step;
+    int scale_levels, step, lossy, N, H, W;
+} pmctf_ctx_step_t;
+int pmctf_ctx_mask_step(const pmctf_ctx_step_t *s, void *stream);
+
 /* ---- entropy-coder boundary ----------------------------------------------------------------
  * HOST functions (plain host pointers, no stream): the 64-bit rANS coder of pMCTF/cpp/rans/rans.cpp:76-168,272-331 behind the
  * sub-stream container of pMCTF/cpp/py_rans/py_rans.cpp:22-225 (what the reference binds as MLCodec_rans.RansEncoder /

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("PMCTF_LIB") or os.path.join(_HERE, "lib", "libpmctf_b200.so")  # PMCTF_LIB: profiling builds only
 SOURCES = [os.path.join(_HERE, "csrc", "pmctf_kernels.cu"), os.path.join(_HERE, "csrc", "pmctf_umma_test.cu"),
            os.path.join(_HERE, "csrc", "pmctf_lift_tc.cu"), os.path.join(_HERE, "csrc", "pmctf_train.cu"),
-           os.path.join(_HERE, "csrc", "pmctf_pp.cu"), os.path.join(_HERE, "csrc", "pmctf_rans.cu")]
+           os.path.join(_HERE, "csrc", "pmctf_pp.cu"), os.path.join(_HERE, "csrc", "pmctf_rans.cu"), os.path.join(_HERE, "csrc", "pmctf_ctx.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "pmctf_umma.cuh"), os.path.join(_HERE, "csrc", "pmctf_common.cuh")]
 INCLUDE = os.path.join(ROOT, "include")
 
@@ -55,6 +55,16 @@ class UmmaOp(C.Structure):
 class PostProcessD(C.Structure):
     _fields_ = [("conv1_w", _fp), ("conv1_b", _fp), ("res_w", _fp * 12), ("res_b", _fp * 12), ("conv2_w", _fp), ("conv2_b", _fp),
                 ("conv3_w", _fp), ("conv3_b", _fp)]
+
+
+class CtxDcb(C.Structure):
+    _fields_ = [(n, _fp) for n in ("dw_w", "dw_b", "pw_w", "pw_b", "ad_w", "ad_b", "f1_w", "f1_b", "f2_w", "f2_b")]
+
+
+class CtxStep(C.Structure):
+    _fields_ = [("x", _fp), ("dec_sym", C.c_void_p), ("scales", _fp), ("means", _fp), ("x_hat", _fp), ("x_q", _fp), ("s_hat", _fp),
+                ("x_res", _fp), ("sym16", C.c_void_p), ("idx16", C.c_void_p), ("log_scale_min", _f), ("log_scale_step", _f),
+                ("scale_levels", C.c_int), ("step", C.c_int), ("lossy", C.c_int), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int)]
 
 
 class Temporal(C.Structure):
@@ -105,6 +115,14 @@ SIGNATURES = {
     "pmctf_pp_conv64": [_P, _P, _P, _I, _P, _f, _P, _P, _P, _f, _f, _P, _I, _I, _I, _P],
     "pmctf_postprocess_workspace": [_I, _I],
     "pmctf_postprocess": [_P, C.POINTER(PostProcessD), _f, _f, _P, _I, _I, _I, _P, _LL, _P],
+    "pmctf_ctx_packed_bytes": [_I],
+    "pmctf_ctx_pack_conv": [_P, _I, _P, _P],
+    "pmctf_ctx_conv_in": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "pmctf_ctx_conv112": [_P, _P, _I, _P, _P, _P, _f, _P, _P, _I, _I, _I, _P],
+    "pmctf_ctx_lower_subband": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "pmctf_ctx_dcb_tail": [_P, _P, C.POINTER(CtxDcb), _P, _P, _I, _I, _I, _P],
+    "pmctf_ctx_head": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "pmctf_ctx_mask_step": [C.POINTER(CtxStep), _P],
     "pmctf_pmf_to_quantized_cdf": [_P, _I, _I, _P],
     "pmctf_rans_encoder_create": [_I, _I, _P],
     "pmctf_rans_encoder_destroy": [_P],
@@ -125,10 +143,10 @@ SIGNATURES = {
     "pmctf_umma_selftest": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P],
 }
 _RESTYPES = {"pmctf_error_string": C.c_char_p, "pmctf_lift2d_workspace": C.c_longlong, "pmctf_pp_packed_bytes": C.c_longlong,
-             "pmctf_postprocess_workspace": C.c_longlong, "pmctf_rans_encoded_size": C.c_longlong,
+             "pmctf_postprocess_workspace": C.c_longlong, "pmctf_rans_encoded_size": C.c_longlong, "pmctf_ctx_packed_bytes": C.c_longlong,
              "pmctf_launch_count": C.c_ulonglong}
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+NVCC_FLAGS = ["--threads", "8", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
 

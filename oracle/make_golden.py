@@ -272,8 +272,44 @@ def main_postprocess():
     np.savez_compressed(os.path.join(OUT, "postprocess.npz"), **out)
 
 
+def main_ctx4():
+    """tests/golden/ctx4.npz: the reference's ContextFusionFourStep (pMCTF/layers/context_fusion_4step.py:23-194) exactly as pWave
+    builds it (pWave.py:70-78: num_features 112, num_parameters 2, ctx_channels 2 below the top level, 1 at the top level), CPU
+    fp32, with the seeded weights of tests/ctx_weights.py (regenerated by the tests, not stored).  Inputs: a quantiser-scaled
+    subband (Laplacian, sigma 3, plus a smooth component), an LSTM-like context plane in [-1, 1] and, for ctx_channels 2, the
+    coarser level's reconstructed subband at half the size."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
+    import ctx_weights
+    from pMCTF.layers.context_fusion_4step import ContextFusionFourStep
+    out = {}
+    for tag, cc, seed in (("a", 2, 11), ("b", 1, 12)):
+        m = ContextFusionFourStep(in_channels=1, num_features=112, num_parameters=2, lossy=True, ctx_channels=cc).eval()
+        w = ctx_weights.make(seed, cc)
+        missing = m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+        g = torch.Generator().manual_seed(100 + seed)
+        N, H, W = 2, 24, 40
+        lap = torch.distributions.laplace.Laplace(0.0, 3.0).sample((N, 1, H, W))
+        x = lap + 4.0 * frames(N, H, W, 50 + seed) / 255.0
+        context = torch.tanh(torch.randn(N, 1, H, W, generator=g))
+        prev = torch.round(2.0 * torch.randn(N, 1, H // 2, W // 2, generator=g)) if cc == 2 else None
+        with torch.no_grad():
+            x_res, x_q, x_hat, s_hat = m(x, context=context, prev_subband=prev)
+            comp = m.compress(x, context=context, prev_subband=prev)
+        out.update({f"{tag}.x": npy(x), f"{tag}.context": npy(context), f"{tag}.x_res": npy(x_res), f"{tag}.x_q": npy(x_q),
+                    f"{tag}.x_hat": npy(x_hat), f"{tag}.s_hat": npy(s_hat), f"{tag}.seed": np.array(seed), f"{tag}.ctx_channels": np.array(cc)})
+        if prev is not None:
+            out[f"{tag}.prev"] = npy(prev)
+        for i in range(4):
+            out[f"{tag}.x_q_{i}"], out[f"{tag}.s_w_{i}"] = npy(comp[i]), npy(comp[4 + i])
+        print(f"ctx4 {tag}: scales {float(s_hat.min()):.3f}..{float(s_hat.max()):.3f} (mean {float(s_hat.mean()):.3f}), |x_q| mean "
+              f"{float(x_q.abs().mean()):.3f}, |x - x_hat| max {float((x - x_hat).abs().max()):.3f}, missing keys: {missing}")
+    np.savez_compressed(os.path.join(OUT, "ctx4.npz"), **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "postprocess":
+    if len(sys.argv) > 1 and sys.argv[1] == "ctx4":
+        main_ctx4()
+    elif len(sys.argv) > 1 and sys.argv[1] == "postprocess":
         main_postprocess()
     elif len(sys.argv) > 1 and sys.argv[1] == "lossless":
         main_lossless()

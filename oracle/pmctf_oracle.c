@@ -622,3 +622,30 @@ ORC_API void orc_conv3x3(const float *in, int ci, const float *w, const float *b
 {
     conv3x3_planar(in, ci, w, b, co, out, H, W, slope, res);
 }
+
+/* ---- generic nn.Conv2d(k x k, stride 1, zero padding k/2, groups) on ONE planar map [ci][H][W] -> [co][H][W], plain fp32: acc = bias,
+ * then fma over (ci, ky, kx).  Building block of the fp32 TOLERANCE oracle of the entropy-parameter networks
+ * (oracle/ctx_oracle.py: pMCTF/layers/context_fusion_4step.py, layers/video/layers.py:113-172). */
+ORC_API void orc_conv2d(const float *in, int ci_n, const float *w, const float *b, int co_n, int k, int groups, float *out, int H, int W)
+{
+    const int cig = ci_n / groups, cog = co_n / groups, r = k / 2;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int co = 0; co < co_n; ++co)
+        for (int y = 0; y < H; ++y) {
+            float *o = out + ((size_t)co * H + y) * W;
+            const int g = co / cog;
+            for (int x = 0; x < W; ++x) o[x] = b ? b[co] : 0.0f;
+            for (int c = 0; c < cig; ++c)
+                for (int ky = 0; ky < k; ++ky) {
+                    const int yy = y + ky - r;
+                    if (yy < 0 || yy >= H) continue;
+                    const float *ip = in + ((size_t)(g * cig + c) * H + yy) * W;
+                    const float *wp = w + (((size_t)co * cig + c) * k + ky) * k;
+                    for (int kx = 0; kx < k; ++kx) {
+                        const float wv = wp[kx];
+                        const int d = kx - r, x0 = d < 0 ? -d : 0, x1 = d > 0 ? W - d : W;
+                        for (int x = x0; x < x1; ++x) o[x] = __builtin_fmaf(wv, ip[x + d], o[x]);
+                    }
+                }
+        }
+}
