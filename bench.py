@@ -295,6 +295,98 @@ def run_postprocess(pkg, dev, pk):
             "torch_gpu_baseline": stock}
 
 
+CTX_LAYER_FLOPS = 2 * 9 * 112 * 112
+# per coefficient of a coded subband: 22 dense 3x3 + one 1x1 112 -> 112 layers, four 1|2 -> 112 input convolutions, the depthwise
+# head, three 112 -> 2 projections (context_fusion_4step.py:23-98; 2 FLOP per MAC)
+CTX_FLOPS_PER_COEFF = 22 * CTX_LAYER_FLOPS + 2 * 112 * 112 + 2 * 9 * 112 * 5 + 2 * 9 * 112 + 2 * 112 * 2 * 5
+
+
+def run_context_fusion(pkg, dev, pk):
+    """the four-step entropy-parameter network (ContextFusionFourStep, 80 % of the codec's FLOPs) on the
+    12 high-pass subbands of the 4-level decomposition of one 1080p luma plane (pWave.py:259-290).  Secondary block, NOT part of the
+    headline metric.  Reports the module (all launches incl. the CUDA-core layers) and the CTA-pair tensor-core layer alone against
+    the measured bf16 peak, and the same module on stock torch ops (cuDNN TF32 / fp32)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctx_weights
+    from learned_pmctf_b200 import _native as nat
+    from learned_pmctf_b200.layers.context_fusion_4step import ContextFusionFourStep
+    lib = nat.lib()
+
+    def timed(fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    g = torch.Generator(device=dev).manual_seed(11)
+    mods, inputs = {}, []
+    for cc in (2, 1):
+        m = ContextFusionFourStep(ctx_channels=cc).to(dev).eval()
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in ctx_weights.make(7, cc).items()})
+        mods[cc] = m
+    for lvl in range(4):
+        h, w = 576 >> lvl, 960 >> lvl
+        for _band in ("lh", "hl", "hh"):
+            cc = 2 if lvl < 3 else 1
+            x = torch.round(torch.randn((1, 1, h, w), device=dev, generator=g) * 4)
+            c = torch.tanh(torch.randn((1, 1, h, w), device=dev, generator=g))
+            p = torch.round(torch.randn((1, 1, h // 2, w // 2), device=dev, generator=g) * 2) if cc == 2 else None
+            inputs.append((mods[cc], x, c, p))
+    coeffs = sum(x.numel() for _, x, _, _ in inputs)
+
+    def ours():
+        for m, x, c, p in inputs:
+            m(x, context=c, prev_subband=p)
+
+    def stock():
+        for m, x, c, p in inputs:
+            m._forward_torch(x, c, p, False)
+    with torch.no_grad():
+        ms = timed(ours, 3)
+        base = {}
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            try:
+                base["tf32" if tf32 else "fp32"] = {"ms_per_plane": timed(stock, 1, warm=1)}
+            except Exception as ex:
+                base["tf32" if tf32 else "fp32"] = {"error": str(ex)[:100]}
+        torch.backends.cudnn.allow_tf32 = True
+    # the tensor-core layer alone on one level-0 subband (inputs + outputs 0.37 GB > L2)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    N, H, W = 1, 576, 960
+    wt = torch.randn((112, 112, 3, 3), device=dev, generator=g) * 0.03
+    bias = torch.zeros(112, device=dev)
+    packed = torch.empty(int(lib.pmctf_ctx_packed_bytes(9)), dtype=torch.uint8, device=dev)
+    nat.check(lib.pmctf_ctx_pack_conv(wt.data_ptr(), 9, packed.data_ptr(), st), "ctx_pack_conv")
+    xin = torch.randn((N, 14, H, W, 8), device=dev, generator=g).to(torch.bfloat16)
+    res = torch.randn((N, 28, H, W, 4), device=dev, generator=g)
+    of, ob = torch.empty_like(res), torch.empty_like(xin)
+    layer = {}
+    for tag, r, o32, bytes_px in (("bf16_out", None, None, 224 + 224), ("skip_f32_in_out", res, of, 224 + 448 + 448 + 224)):
+        lms = timed(lambda: nat.check(lib.pmctf_ctx_conv112(xin.data_ptr(), packed.data_ptr(), 9, bias.data_ptr(), r.data_ptr() if r is not None else None,
+                                                            None, 1.0, o32.data_ptr() if o32 is not None else None, ob.data_ptr(), N, H, W, st), "ctx_conv112"), 10)
+        tfl = CTX_LAYER_FLOPS * N * H * W / lms / 1e9
+        layer[tag] = {"ms": lms, "tflops": tfl, "frac_of_bf16_peak": tfl / pk["tf_sustained"],
+                      "algorithmic_hbm_gbs": bytes_px * N * H * W / lms / 1e6, "frac_of_hbm_peak": bytes_px * N * H * W / lms / 1e6 / pk["hbm_gbs"]}
+    pkg.ops.check_tc_error(dev, "context fusion block")
+    tf = CTX_FLOPS_PER_COEFF * coeffs / ms / 1e9
+    return {"what": "ContextFusionFourStep (context_fusion_4step.py:23-194; 112 features) forward on the 12 high-pass subbands of one 1080p luma "
+                    "plane (576x960 ... 72x120): 112->112 layers as tcgen05 CTA-pair implicit GEMMs (cta_group::2, M=256, N=112, bf16 operands, fp32 "
+                    "accumulation in TMEM, TMA tensor loads, weights resident half per CTA), fp32 skips / biases / heads",
+            "ms_per_plane": ms, "coefficients": coeffs, "algorithmic_flops_per_coefficient": CTX_FLOPS_PER_COEFF,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
+                         "peak_source": f"{pk['source']} bf16 dense, sustained",
+                         "scope": "the whole module call on all 12 subbands (about 37 launches per subband incl. the CUDA-core layers; the deep levels are launch-bound at batch 1)"},
+            "tensor_core_layer_576x960": layer, "torch_gpu_baseline": base}
+
+
 def run_uvg(args, pkg, G, par, model, dev, rank, world):
     """BASELINE configs[3] as written: 7 synthetic 1080p sequences x 96 frames (6 GOP-16s each) x the q_index list of
     test_pMCTF_flex.py:436-443, FLATTENED into 252 work items (q_index, sequence, gop), sharded round-robin over the ranks
@@ -508,6 +600,7 @@ def main():
     ap.add_argument("--uvg-sequences", type=int, default=7)
     ap.add_argument("--no-int8-peak", action="store_true", help="skip measuring the int8 dense peak of this GPU")
     ap.add_argument("--no-postprocess", action="store_true", help="skip the PostProcess block (section 8f row 2, secondary)")
+    ap.add_argument("--no-context-fusion", action="store_true", help="skip the entropy-parameter network block (section 8f row 1, secondary)")
     ap.add_argument("--workload", default="gop16", choices=["gop16", "train"],
                     help="gop16: the headline metric (default); train: BASELINE configs[4] training step (not the headline)")
     args = ap.parse_args()
@@ -658,6 +751,12 @@ def main():
             ppb = run_postprocess(pkg, dev, pk)
         except Exception as ex:   # a secondary block must never take the headline line down
             ppb = {"error": str(ex)[:200]}
+    ctxb = None
+    if world == 1 and not args.no_context_fusion and args.frames == FRAMES:
+        try:
+            ctxb = run_context_fusion(pkg, dev, pk)
+        except Exception as ex:
+            ctxb = {"error": str(ex)[:200]}
     # --- roofline of the dominant kernel -------------------------------------------------------------------
     mode = pkg.ops.get_conv_mode()
     flops = ks["pixels"] * pkg.ops.PU_FLOPS_PER_PX
@@ -733,7 +832,7 @@ def main():
                        "streams": "1" if args.single_stream else "2 per GPU: luma chain | chroma chain (independent on the path)",
                        "parallelism": f"gop-sharded dp{world}, all_gather of per-frame statistics per step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "torch_gpu_baseline": torch_gpu, "uvg": uvg, "postprocess": ppb,
+            "torch_gpu_baseline": torch_gpu, "uvg": uvg, "postprocess": ppb, "context_fusion": ctxb,
             "quality": {"mean_psnr_yuv_db": float(psnr[torch.isfinite(psnr)].mean()), "frames": int(psnr.numel())}}
     emit(line)
     if world > 1:

@@ -88,6 +88,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// "this thread has finished reading its accumulator rows" (the tcgen05.wait::ld before it has completed the reads): no memory
+// ordering is carried, so the arrive must not wait for the thread's outstanding global stores (a release at cluster scope would)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // bounded wait that synchronises with arrivals from the peer CTA
 __device__ __forceinline__ bool mbar_wait_cluster(uint32_t mbar_saddr, uint32_t parity, int max_tries = 1 << 22)
 {
@@ -282,8 +289,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
             const bool use_res = a.res != nullptr && valid, use_res2 = a.res2 != nullptr && valid;
             const float4 *rp = reinterpret_cast<const float4 *>(a.res) + (long long)n * CQ * plane_px + pix;
             const float4 *rp2 = reinterpret_cast<const float4 *>(a.res2) + (long long)n * CQ * plane_px + pix;
+            // the skip operands of this tile start their way from HBM to L2 while the MMAs of the tile are still running ...
+            if (use_res)
+                for (int j = 4; j < CQ; ++j) prefetch_l2(rp + j * plane_px);
+            if (use_res2)
+                for (int j = 4; j < CQ; ++j) prefetch_l2(rp2 + j * plane_px);
             float4 rr[4], rr2[4];
-            // the skip operands of the first 16 channels are requested before the accumulators are waited for
+            // ... and those of the first 16 channels are requested before the accumulators are waited for
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 rr[j] = use_res ? __ldg(rp + j * plane_px) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -344,7 +356,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
                 }
             }
             umma::fence_before_sync();
-            mbar_arrive_cluster(acc_empty_leader + 8 * abuf);
+            mbar_arrive_cluster_relaxed(acc_empty_leader + 8 * abuf);
         }
     }
     if (__syncthreads_or(!ok)) {
