@@ -144,11 +144,15 @@ class GaussianEncoder(AEHelper):
         if not scales.is_cuda:
             raise RuntimeError("stage(): CUDA tensors only (the host path is build_indexes + EntropyCoder.encode_with_indexes)")
         sc = scales.contiguous().float()
+        if sc.data_ptr() % 16:          # a slice of a larger tensor: the kernel reads 16-byte vectors
+            sc = sc.clone()
         n = sc.numel()
         sym_h, idx_h = self._staging.get(n)
         xs = None
         if x is not None:
             xs = x.contiguous().float()
+            if xs.data_ptr() % 16:
+                xs = xs.clone()
             if xs.numel() != n or xs.device != sc.device:
                 raise RuntimeError("symbols and scales must have the same number of elements on one device")
         st = torch.cuda.current_stream(sc.device)

@@ -1,0 +1,124 @@
+"""The autoregressive entropy-parameter network of the LL subband (reference: pMCTF/layers/context_fusion.py:9-204 with
+MaskedConv2d of pMCTF/layers/layers.py:23-52), as pWave++ instantiates it (pWave.py:80-82: 128 features, 2 parameters, no
+context input).
+
+The LL band of a 1080p plane is 72 x 120 coefficients (1/256 of the plane): this module is host-side torch code on stock
+convolutions, with the reference's module tree, parameter AND buffer names (`mask` buffers are part of its state_dicts).  The full-
+plane `forward` is what the training / evaluation pass uses; `forward_sequential` is the pixel-by-pixel form the bitstream path
+needs (every coefficient's parameters depend on the coefficients decoded before it)."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class MaskedConv2d(nn.Conv2d):
+    """PixelCNN-style causal convolution: type 'A' hides the centre tap and everything after it in raster order, 'B' keeps the
+    centre.  The mask is applied to the weights in place at every call, as the reference does (layers.py:49-51)."""
+
+    def __init__(self, *args, mask_type: str = "A", **kwargs):
+        super().__init__(*args, **kwargs)
+        if mask_type not in ("A", "B"):
+            raise ValueError(f'Invalid "mask_type" value "{mask_type}"')
+        mask = torch.ones_like(self.weight.data)
+        kh, kw = mask.shape[-2:]
+        mask[:, :, kh // 2, kw // 2 + (1 if mask_type == "B" else 0):] = 0
+        mask[:, :, kh // 2 + 1:] = 0
+        self.register_buffer("mask", mask)
+
+    def forward(self, x, onehot=None):
+        self.weight.data *= self.mask
+        return super().forward(x)
+
+
+def _masked3x3(cin, cout, mask_type):
+    return MaskedConv2d(cin, cout, kernel_size=(3, 3), stride=(1, 1), mask_type=mask_type, padding=(1, 1))
+
+
+class MaskResidual(nn.Module):
+    def __init__(self, num_features):
+        super().__init__()
+        self.conv1 = _masked3x3(num_features, num_features, "B")
+        self.lrelu = nn.LeakyReLU(0.2, inplace=True)
+        self.conv2 = _masked3x3(num_features, num_features, "B")
+        self.conv1_input = self.conv2_input = None
+        self.maskedWeight1 = self.maskedWeight2 = None
+
+    def forward(self, x):
+        return self.conv2(self.lrelu(self.conv1(x))) + x
+
+    def init_sequential(self, like):
+        self.conv1_input, self.conv2_input = torch.zeros_like(like), torch.zeros_like(like)
+        self.maskedWeight1 = self.conv1.weight * self.conv1.mask
+        self.maskedWeight2 = self.conv2.weight * self.conv2.mask
+
+    def forward_sequential(self, x, h, w, kernel_size, padding):
+        """one pixel: x [N,F,1,1] is written into the padded history of conv1's input at (h, w), the 3x3 window around it gives
+        conv1's output there, and the same again for conv2 (context_fusion.py:30-41)"""
+        self.conv1_input[:, :, h + padding:h + padding + 1, w + padding:w + padding + 1] = x
+        t = F.conv2d(self.conv1_input[:, :, h:h + kernel_size, w:w + kernel_size], self.maskedWeight1, bias=self.conv1.bias)
+        t = self.lrelu(t)
+        self.conv2_input[:, :, h + padding:h + padding + 1, w + padding:w + padding + 1] = t
+        t = F.conv2d(self.conv2_input[:, :, h:h + kernel_size, w:w + kernel_size], self.maskedWeight2, bias=self.conv2.bias)
+        return t + x
+
+
+class ContextFusionSubband(nn.Module):
+    def __init__(self, in_channels=1, ctx_channels=1, num_features=128, context=False, num_parameters=9, prev_ctxs=False,
+                 pretrained=None, ll_ctx=False, lower_subband=True, adaptive_quant=False):
+        super().__init__()
+        if context:
+            raise NotImplementedError("pWave++ builds the LL model without a context input (pWave.py:80-82)")
+        self.sequential_init = False
+        self.residual_blocks = 2
+        self.num_features, self.context, self.num_parameters, self.ctx_channels = num_features, context, num_parameters, ctx_channels
+        self.maskedConv1 = _masked3x3(in_channels, num_features, "A")
+        self.residualBlocks = nn.ModuleList(MaskResidual(num_features) for _ in range(self.residual_blocks))
+        self.maskedConv2 = _masked3x3(num_features, num_features, "B")
+        self.lrelu = nn.LeakyReLU(0.2, inplace=True)
+        self.convs = nn.ModuleList([nn.Conv2d(num_features, num_features, 1), nn.Conv2d(num_features, num_features, 1),
+                                    nn.Conv2d(num_features, num_parameters, 1)])
+        self.maskedWeight1 = self.maskedWeight2 = self.maskedConv2_input = self.mask1 = None
+
+    def _tail(self, x):
+        for i, c in enumerate(self.convs):
+            x = c(x)
+            if i < len(self.convs) - 1:
+                x = self.lrelu(x)
+        return x
+
+    def forward(self, x, context=None, prev_subband=None, channel_idx=0):
+        first = self.maskedConv1(x)
+        x = first
+        for blk in self.residualBlocks:
+            x = blk(x)
+        x = self.lrelu(self.maskedConv2(x + first))
+        return self._tail(x)
+
+    def init_sequential(self, y_hat):
+        self.maskedWeight1 = self.maskedConv1.weight * self.maskedConv1.mask
+        size = list(y_hat.size())
+        size[1] = self.num_features
+        self.mask1 = self.maskedConv1.mask[0].unsqueeze(0).repeat(size[0], 1, 1, 1)
+        self.maskedConv2_input = torch.zeros(size, dtype=y_hat.dtype, device=y_hat.device)
+        self.maskedWeight2 = self.maskedConv2.weight * self.maskedConv2.mask
+        for blk in self.residualBlocks:
+            blk.init_sequential(self.maskedConv2_input)
+        self.sequential_init = True
+
+    def forward_sequential(self, y_hat, h, w, context_list=None, channel_idx=0):
+        """parameters of coefficient (h, w) from the zero-padded plane of what has been coded so far (context_fusion.py:160-204)"""
+        if not self.sequential_init:
+            self.init_sequential(y_hat)
+        k, pad = 3, 1
+        crop = y_hat[:, :, h:h + k, w:w + k].detach().clone()
+        crop[self.mask1 == 0] = 0       # non-causal positions must not leak in even multiplied by a zero weight (-0, NaN)
+        t = F.conv2d(crop, self.maskedWeight1, bias=self.maskedConv1.bias)
+        first = t
+        for blk in self.residualBlocks:
+            t = blk.forward_sequential(t, h, w, k, pad)
+        t = t + first
+        self.maskedConv2_input[:, :, h + pad:h + pad + 1, w + pad:w + pad + 1] = t
+        t = F.conv2d(self.maskedConv2_input[:, :, h:h + k, w:w + k], self.maskedWeight2, bias=self.maskedConv2.bias)
+        return self._tail(self.lrelu(t))

@@ -244,6 +244,162 @@ class pWaveTransform:
         x_hat = self.decode(hat)          # the bands are dequantised already
         return x_hat, stats.sum(0)
 
+    # --- the coder around the transform (pWave.py:244-312, 381-529): entropy-parameter networks + rANS --------------------------
+    def has_entropy_model(self) -> bool:
+        return hasattr(self, "context_fusion") and hasattr(self, "context_prediction") and hasattr(self, "em")
+
+    def _coded_forward(self, x, q_scale, q_scale_ll):
+        """forward_one_channel (pWave.py:244-312): the LL band through its autoregressive model, then lh / hl / hh from the coarsest
+        level down, each through its four-step model with the long-term context of everything coded before it; the rate is the
+        Laplace estimate of the entropy model (gaussian_model.py:50-55)."""
+        top = self.decomp_levels - 1
+        y = self.encode(x)
+        hat = {lvl: {} for lvl in range(self.decomp_levels)}
+        bits = {lvl: {} for lvl in range(top, -1, -1)}
+        ll_hat = self._round(self.quantize_subband(y[top]["ll"], q_scale_ll))
+        scales, means = self.context_fusion[str(top)]["ll"](ll_hat).chunk(2, dim=1)
+        bits[top]["ll"] = self.em.get_y_laplace_bits(ll_hat - means, scales)
+        hat[top]["ll"] = ll_hat
+        bits["bits_total"] = torch.sum(bits[top]["ll"], dim=(1, 2, 3))
+        self.context_prediction.init_sequential(list(ll_hat.size()), ll_hat.device)
+        context = self.context_prediction.forward_one_subband(ll_hat, "ll", top)["context"]
+        for lvl in range(top, -1, -1):
+            for i, b in enumerate(BANDS):
+                ctx_b = context.chunk(3, dim=1)[i]
+                prev = hat[lvl + 1][b] if lvl < top else None
+                s = self.quantize_subband(y[lvl][b], q_scale)
+                _, s_q, s_hat, sc = self.context_fusion[str(lvl)][b](s, context=ctx_b, prev_subband=prev)
+                hat[lvl][b] = s_hat
+                bits[lvl][b] = self.em.get_y_laplace_bits(s_q, sc)
+                bits["bits_total"] = bits["bits_total"] + torch.sum(bits[lvl][b], dim=(1, 2, 3))
+                context = self.context_prediction.forward_one_subband(s_hat, b, lvl)["context"]
+        x_hat = self.decode(self.dequantize_subbands(hat, q_scale, q_scale_ll))
+        if self.lossy and hasattr(self, "dequantModule"):
+            x_hat = self.post_process(x_hat)
+        n = x_hat.size(0)
+        return {"x_hat": x_hat, "bits": bits, "likelihoods": bits, "subbands": hat,
+                "bpp_total": bits["bits_total"].sum() / (x_hat.size(2) * x_hat.size(3) * n), "bits_total": bits["bits_total"].sum() / n,
+                "mse": torch.mean((x - x_hat) ** 2)}
+
+    def update(self, force=False):
+        self.em.update(force)
+
+    def _ll_sequential(self, size, device, dtype, symbols=None):
+        """The LL band, coefficient by coefficient in raster order (pWave.py:531-584): parameters from the causal neighbourhood
+        of what is known so far, then the residual to the mean is encoded (symbols given) or decoded.  Returns the band."""
+        B, Cc, H, W = size
+        net = self.context_fusion[str(self.decomp_levels - 1)]["ll"]
+        enc = self.em.gaussian_encoder
+        pad = 1
+        if symbols is not None:
+            plane = torch.nn.functional.pad(symbols, (pad, pad, pad, pad))
+            out = torch.zeros_like(symbols)
+        else:
+            plane = torch.zeros((B, Cc, H + 2 * pad, W + 2 * pad), dtype=dtype, device=device)
+        for h in range(H):
+            for w in range(W):
+                scale, mean = net.forward_sequential(plane, h, w).chunk(2, dim=1)
+                if symbols is not None:
+                    cur = plane[:, 0:1, h + pad:h + pad + 1, w + pad:w + pad + 1]
+                    res = torch.round(torch.round(cur) - mean)
+                    out[:, :, h, w] = torch.round(res + mean)[:, :, 0, 0]
+                    enc.encode(res, scale)
+                else:
+                    rec = enc.decode_stream(scale, dtype, device) + mean
+                    plane[:, :, h + pad, w + pad] = torch.round(rec)[:, :, 0, 0]
+        net.sequential_init = False
+        return out if symbols is not None else plane[:, :, pad:-pad, pad:-pad].contiguous()
+
+    @torch.no_grad()
+    def compress(self, x, sideinfo=None, file_name=None, q_index=None, skip_decoding=False, qp_scale=None):
+        """pWave.compress (pWave.py:381-463): same arguments; writes the container of stream_helper.encode_image (:201-207) when
+        file_name is given and returns x_hat.  The four masked symbol planes of every band go to the native rANS coder as int16
+        symbols + table indexes produced by the quantiser kernel (ContextFusionFourStep.compress_staged)."""
+        _, num_channels, height, width = sideinfo
+        q, qll = self.q_pair(q_index, qp_scale)
+        x_in = torch.cat([x[:, i:i + 1] for i in range(3)], dim=0) if num_channels == 3 else x
+        top = self.decomp_levels - 1
+        y = self.encode(x_in)
+        hat = {lvl: {} for lvl in range(self.decomp_levels)}
+        ll = torch.round(self.quantize_subband(y[top]["ll"], qll))
+        coder, enc = self.em.entropy_coder, self.em.gaussian_encoder
+        coder.reset()
+        if skip_decoding:       # encoder-only shortcut of the reference: parameters of the whole band in one pass
+            scales, means = self.context_fusion[str(top)]["ll"](ll).chunk(2, dim=1)
+            res = torch.round(ll - means)
+            ll_hat = torch.round(res + means)
+            enc.encode(res, scales)
+        else:
+            ll_hat = self._ll_sequential(list(ll.size()), ll.device, ll.dtype, symbols=ll)
+        hat[top]["ll"] = ll_hat
+        self.context_prediction.init_sequential(list(ll.size()), ll.device)
+        context = self.context_prediction.forward_one_subband(ll_hat, "ll", top)["context"]
+        cdf, ln, off = enc.get_cdf_info()
+        for lvl in range(top, -1, -1):
+            for i, b in enumerate(BANDS):
+                ctx_b = context.chunk(3, dim=1)[i].contiguous()
+                prev = hat[lvl + 1][b] if lvl < top else None
+                s = self.quantize_subband(y[lvl][b], q)
+                net = self.context_fusion[str(lvl)][b]
+                if hasattr(net, "compress_staged") and s.is_cuda:
+                    s_hat, staged = net.compress_staged(s, context=ctx_b, prev_subband=prev)
+                    host = [(a.cpu(), c.cpu()) for a, c in staged]           # 4 + 4 small copies per band, one synchronisation
+                    for sym16, idx16 in host:
+                        coder.encoder.encode_with_indexes(sym16.numpy(), idx16.numpy(), cdf, ln, off)
+                else:
+                    o = net.compress(s, context=ctx_b, prev_subband=prev)
+                    s_hat = o[8]
+                    for k in range(4):
+                        enc.encode(o[k], o[4 + k])
+                hat[lvl][b] = s_hat
+                context = self.context_prediction.forward_one_subband(s_hat, b, lvl)["context"]
+        x_hat = self.decode(self.dequantize_subbands(hat, q, qll))
+        if self.lossy and hasattr(self, "dequantModule"):
+            x_hat = self.post_process(x_hat)
+        coder.flush()
+        stream = coder.get_encoded_stream()
+        self.last_stream = stream
+        if file_name is not None:
+            import struct
+            with open(file_name, "wb") as f:                                 # stream_helper.py:201-207
+                f.write(struct.pack(">3I", height, width, num_channels))
+                f.write(struct.pack(">I", len(stream)))
+                f.write(stream)
+        if num_channels == 3:
+            x_hat = torch.cat([x_hat[i:i + 1] for i in range(3)], dim=1)
+        return x_hat
+
+    @torch.no_grad()
+    def decompress(self, file_name, padding=64, q_index=None, qp_scale=None):
+        """pWave.decompress (pWave.py:467-529); file_name may also be the bytes object of such a file."""
+        import struct
+        q, qll = self.q_pair(q_index, qp_scale)
+        blob = file_name if isinstance(file_name, (bytes, bytearray)) else open(file_name, "rb").read()
+        height, width, num_channel = struct.unpack(">3I", blob[:12])
+        (n,) = struct.unpack(">I", blob[12:16])
+        self.em.entropy_coder.set_stream(bytes(blob[16:16 + n]))
+        p0 = next(self.parameters())
+        dtype, device = p0.dtype, p0.device
+        new_h, new_w = (height + padding - 1) // padding * padding, (width + padding - 1) // padding * padding
+        top = self.decomp_levels - 1
+        size = [num_channel, 1, new_h >> (top + 1), new_w >> (top + 1)]
+        hat = {lvl: {} for lvl in range(top, -1, -1)}
+        hat[top]["ll"] = ll = self._ll_sequential(size, device, dtype)
+        self.context_prediction.init_sequential(list(ll.size()), device)
+        context = self.context_prediction.forward_one_subband(ll, "ll", top)["context"]
+        for lvl in range(top, -1, -1):
+            for i, b in enumerate(BANDS):
+                ctx_b = context.chunk(3, dim=1)[i].contiguous()
+                prev = hat[lvl + 1][b] if lvl < top else None
+                hat[lvl][b] = s_hat = self.context_fusion[str(lvl)][b].decompress(self.em.gaussian_encoder, context=ctx_b, prev_subband=prev)
+                context = self.context_prediction.forward_one_subband(s_hat, b, lvl)["context"]
+        x_hat = self.decode(self.dequantize_subbands(hat, q, qll))
+        if self.lossy and hasattr(self, "dequantModule"):
+            x_hat = self.post_process(x_hat)
+        if num_channel == 3:
+            x_hat = torch.cat([x_hat[i:i + 1] for i in range(3)], dim=1)
+        return {"x_hat": x_hat}
+
     # --- the reference's transform-only loop (pWave.py:314-349) --------------------------------
     def spatial_wavelet_dec(self, x, q_scale=None, q_scale_ll=None, post_process=True, return_symbols=False):
         """encode -> round(clamp(s*q)) on every band -> dequantise -> decode [-> PostProcess].
@@ -262,7 +418,7 @@ class pWave(pWaveTransform, nn.Module):
     """Stand-alone hot-path subset of the reference's pWave (pWave.py:26-98): same constructor,
     same parameter names for the transform and the quantiser."""
 
-    def __init__(self, bitdepth=8, decomp_levels=4, lossy=True, postprocess=False):
+    def __init__(self, bitdepth=8, decomp_levels=4, lossy=True, postprocess=False, entropy_model=False):
         super().__init__()
         self.bitdepth = 8
         self.dynamic_range = float(2 ** bitdepth)
@@ -271,12 +427,27 @@ class pWave(pWaveTransform, nn.Module):
         self.decomp_levels = decomp_levels
         self.wavelet_transform = LiftingScheme2D(bitdepth=bitdepth, lossy=lossy, in_channels=1)
         self.clip_value = 8192.0 if lossy else float(torch.iinfo(torch.int16).max)  # pWave.py:55-58
-        self.QP = nn.Parameter(torch.ones((2, 1, 1, 1), dtype=torch.float) * 1 / 16)      # pWave.py:84-85
-        self.QP_ll = nn.Parameter(torch.ones((2, 1, 1, 1), dtype=torch.float) * 1 / 16)
         self._qc = _QCache()
-        if postprocess and lossy:   # pWave.py:61-62; optional here so that hot-path-only checkpoints keep loading
+        if entropy_model:           # pWave.py:60-82: the whole coder, module tree and names as in the reference
+            from ..entropy_models.gaussian_model import CompressionModel
+            from ..layers.context_fusion import ContextFusionSubband
+            from ..layers.context_fusion_4step import ContextFusionFourStep
+            from ..layers.long_context import SubbandContext
+            self.context_prediction = SubbandContext(in_channels=1, decomp_levels=decomp_levels)
+        if (postprocess or entropy_model) and lossy:   # pWave.py:61-62; optional so that hot-path-only checkpoints keep loading
             from ..layers.postprocessing import PostProcess
             self.dequantModule = PostProcess(in_channels=1, out_channels=1)
+        if entropy_model:
+            self.num_params = 2
+            self.em = CompressionModel(y_distribution="laplace")
+            self.context_fusion = nn.ModuleDict({
+                str(lvl): nn.ModuleDict({b: ContextFusionFourStep(in_channels=1, num_features=112, num_parameters=2, lossy=lossy,
+                                                                  ctx_channels=2 if lvl < decomp_levels - 1 else 1) for b in BANDS})
+                for lvl in range(decomp_levels)})
+            self.context_fusion[str(decomp_levels - 1)]["ll"] = ContextFusionSubband(num_features=128, num_parameters=2, context=False,
+                                                                                     in_channels=1)
+        self.QP = nn.Parameter(torch.ones((2, 1, 1, 1), dtype=torch.float) * 1 / 16)      # pWave.py:84-85
+        self.QP_ll = nn.Parameter(torch.ones((2, 1, 1, 1), dtype=torch.float) * 1 / 16)
 
     def forward(self, x, q_index=None, qp_scale=None):
         """pWave.forward (pWave.py:231-242): same signature, same step derivation, then forward_one_channel."""
@@ -295,6 +466,8 @@ class pWave(pWaveTransform, nn.Module):
         `bpp_total`) are NaN / None instead of invented numbers."""
         if q_scale is None:
             q_scale, q_scale_ll = self.QP[-1], self.QP_ll[-1]
+        if self.has_entropy_model():
+            return self._coded_forward(x, q_scale, q_scale_ll)
         top = self.decomp_levels - 1
         y = self.encode(x)
         subbands_hat = {lvl: {} for lvl in range(self.decomp_levels)}

@@ -106,13 +106,13 @@ class MCTFMixin:
 
 class pMCTF(MCTFMixin, nn.Module):
     def __init__(self, bitdepth=8, decomp_levels=4, lossy=True, two_stage_me=True, num_me_stages=2, quant_stage=True,
-                 postprocess=False, **kwargs):
+                 postprocess=False, entropy_model=False, **kwargs):
         super().__init__()
         self.bitdepth = bitdepth
         self.dynamic_range = 2 ** bitdepth - 1
         self.lossy = lossy
-        self.lp_coder = pWave(bitdepth, decomp_levels, lossy, postprocess=postprocess)
-        self.hp_coder = pWave(bitdepth, decomp_levels, lossy, postprocess=postprocess)
+        self.lp_coder = pWave(bitdepth, decomp_levels, lossy, postprocess=postprocess, entropy_model=entropy_model)
+        self.hp_coder = pWave(bitdepth, decomp_levels, lossy, postprocess=postprocess, entropy_model=entropy_model)
         self.temporal_filtering = nn.ModuleList([TemporalLifting(lossy=lossy) for _ in range(num_me_stages)])
         self.quant_stage = quant_stage
         if quant_stage:
@@ -166,6 +166,15 @@ def accelerate(ref_model):
         if dq is not None and all(hasattr(dq, n) for n in ("resBlocks", "conv1", "conv2", "conv3")):   # the reference's PostProcess
             from ...layers.postprocessing import PostProcess
             coder.dequantModule = adopt(PostProcess().to(next(dq.parameters()).device), dq)
+        cf = getattr(coder, "context_fusion", None)
+        if cf is not None:   # the reference's ContextFusionFourStep modules (context_fusion_4step.py:23) -> the tensor-core ones
+            from ...layers.context_fusion_4step import ContextFusionFourStep
+            for lvl in list(cf.keys()):
+                for band in ("lh", "hl", "hh"):
+                    old = cf[lvl][band]
+                    if all(hasattr(old, n) for n in ("y_hierarchical_prior_enc", "conv1_context", "y_spatial_prior_3_out")) and old.num_ch == 112:
+                        new = ContextFusionFourStep(ctx_channels=old.ctx_channels, lossy=old.lossy).to(next(old.parameters()).device)
+                        cf[lvl][band] = adopt(new, old).train(old.training)
         for m in _PWAVE_METHODS:
             setattr(coder, m, types.MethodType(getattr(pWaveTransform, m), coder))
     for m in _MCTF_METHODS:
