@@ -19,6 +19,7 @@ MCTF synthesis, plus the per-frame statistics and their NCCL gather.  Prints ONE
 from __future__ import annotations
 
 import argparse
+import subprocess
 import json
 import os
 import statistics
@@ -600,6 +601,7 @@ def main():
     ap.add_argument("--uvg-sequences", type=int, default=7)
     ap.add_argument("--no-int8-peak", action="store_true", help="skip measuring the int8 dense peak of this GPU")
     ap.add_argument("--no-postprocess", action="store_true", help="skip the PostProcess block (section 8f row 2, secondary)")
+    ap.add_argument("--no-train-block", action="store_true", help="skip the configs[4] training-step block (child process, secondary)")
     ap.add_argument("--no-context-fusion", action="store_true", help="skip the entropy-parameter network block (section 8f row 1, secondary)")
     ap.add_argument("--workload", default="gop16", choices=["gop16", "train"],
                     help="gop16: the headline metric (default); train: BASELINE configs[4] training step (not the headline)")
@@ -751,6 +753,18 @@ def main():
             ppb = run_postprocess(pkg, dev, pk)
         except Exception as ex:   # a secondary block must never take the headline line down
             ppb = {"error": str(ex)[:200]}
+    trainb = None
+    if world == 1 and not args.no_train_block and args.frames == FRAMES:
+        # configs[4] (training step, judge-added row): the `--workload train --torch-baseline` line of this same script, run in a child
+        # process after the timed region so that its CUDA graphs and allocator state cannot touch the headline numbers
+        try:
+            torch.cuda.synchronize(dev)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "train", "--torch-baseline", "--steps", "3", "--warmup", "3"],
+                               capture_output=True, text=True, timeout=600)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            trainb = json.loads(lines[-1]) if lines else {"error": (r.stderr or "no output")[-200:]}
+        except Exception as ex:
+            trainb = {"error": str(ex)[:200]}
     ctxb = None
     if world == 1 and not args.no_context_fusion and args.frames == FRAMES:
         try:
@@ -832,7 +846,7 @@ def main():
                        "streams": "1" if args.single_stream else "2 per GPU: luma chain | chroma chain (independent on the path)",
                        "parallelism": f"gop-sharded dp{world}, all_gather of per-frame statistics per step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "torch_gpu_baseline": torch_gpu, "uvg": uvg, "postprocess": ppb, "context_fusion": ctxb,
+            "torch_gpu_baseline": torch_gpu, "uvg": uvg, "postprocess": ppb, "context_fusion": ctxb, "train": trainb,
             "quality": {"mean_psnr_yuv_db": float(psnr[torch.isfinite(psnr)].mean()), "frames": int(psnr.numel())}}
     emit(line)
     if world > 1:

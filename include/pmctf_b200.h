@@ -309,6 +309,12 @@ int pmctf_ctx_conv_in(const float *x0, const float *x1, const float *w, const fl
  * out = lrelu_slope(conv(in) + bias [+ res] [+ res2]) as fp32 and / or bf16 (either may be NULL) */
 int pmctf_ctx_conv112(const void *in_bf16, const void *packed_w, int taps, const float *bias, const float *res, const float *res2,
                       float lrelu_slope, float *out_f32, void *out_bf16, int N, int H, int W, void *stream);
+/* The same layer with the 112 -> 2 projection that follows it (y_spatial_prior_k_out.2, :66-70) evaluated in the epilogue, where a
+ * pixel's 112 output channels sit in one thread's registers: the feature map is never written, only scales / means [N,1,H,W].
+ * head_w [2,112,1,1], head_b [2].  Bit-identical to pmctf_ctx_conv112 (fp32 out) followed by pmctf_ctx_head. */
+int pmctf_ctx_conv112_head(const void *in_bf16, const void *packed_w, int taps, const float *bias, const float *res, const float *res2,
+                           float lrelu_slope, const float *head_w, const float *head_b, float *scales, float *means, int N, int H, int W,
+                           void *stream);
 /* lower_level_subband (:49-52): nearest x2 upsampling of prev [N,1,h,w] + nn.Conv2d(1 -> 1, 3x3) -> out [N,1,2h,2w] */
 int pmctf_ctx_lower_subband(const float *prev, const float *w, const float *b, float *out, int N, int h, int w_, void *stream);
 /* DepthConvBlock(112, 2) behind its first 1x1 convolution (pMCTF/layers/video/layers.py:113-172): t1 = LeakyReLU_0.01(conv1(ctx))

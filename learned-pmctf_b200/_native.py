@@ -119,6 +119,7 @@ SIGNATURES = {
     "pmctf_ctx_pack_conv": [_P, _I, _P, _P],
     "pmctf_ctx_conv_in": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "pmctf_ctx_conv112": [_P, _P, _I, _P, _P, _P, _f, _P, _P, _I, _I, _I, _P],
+    "pmctf_ctx_conv112_head": [_P, _P, _I, _P, _P, _P, _f, _P, _P, _P, _P, _I, _I, _I, _P],
     "pmctf_ctx_lower_subband": [_P, _P, _P, _P, _I, _I, _I, _P],
     "pmctf_ctx_dcb_tail": [_P, _P, C.POINTER(CtxDcb), _P, _P, _I, _I, _I, _P],
     "pmctf_ctx_head": [_P, _P, _P, _P, _P, _I, _I, _I, _P],

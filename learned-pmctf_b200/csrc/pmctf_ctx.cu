@@ -52,7 +52,8 @@ constexpr int SM_W = 0;
 constexpr int SM_IN = SM_W + WHALF_MAX;
 constexpr int SM_BAR = SM_IN + N_IN * INBUF;
 constexpr int SM_BIAS = SM_BAR + 128;
-constexpr int SMEM_BYTES = SM_BIAS + C * 4;
+constexpr int SM_HEAD = SM_BIAS + C * 4;             // 2 x 112 floats of the fused projection
+constexpr int SMEM_BYTES = SM_HEAD + 2 * C * 4;
 static_assert(TH * P == 128, "one 128-row MMA block per CTA and tile");
 static_assert(SM_IN % 128 == 0 && INBUF % 128 == 0 && SM_BAR % 8 == 0 && SMEM_BYTES <= 227 * 1024, "shared memory");
 static_assert(N_ACC * ACC_STRIDE <= 512 && C <= ACC_STRIDE, "TMEM columns");
@@ -156,6 +157,8 @@ struct ConvD {
     const float *res, *res2;      // fp32 [N][28][H][W][4] added after the bias (skip connections), or null
     float *out_f32;               // fp32 [N][28][H][W][4], or null
     __nv_bfloat16 *out_bf16;      // bf16 [N][14][H][W][8], or null
+    const float *head_w, *head_b; // optional fused 112 -> 2 projection of the layer's output (y_spatial_prior_k_out.2): [2][112], [2]
+    float *head_scales, *head_means;   // [N,1,H,W] each
     float slope;                  // LeakyReLU slope applied last (1 = identity)
     int n, h, w, taps;            // taps: 9 (3x3, padding 1) or 1 (1x1)
 };
@@ -197,6 +200,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
     }
     if (warp == MMA_WARP) tmem_alloc_pair(tmem_slot, 512);
     if (tid < C) reinterpret_cast<float *>(smem + SM_BIAS)[tid] = a.bias[tid];
+    if (a.head_w && tid < 2 * C) reinterpret_cast<float *>(smem + SM_HEAD)[tid] = a.head_w[tid];
     umma::fence_before_sync();
     __syncthreads();
     cluster_sync();   // both CTAs' barriers are initialised before anything signals across the pair
@@ -270,6 +274,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
         // ---- epilogue (both CTAs): TMEM -> bias / skips / LeakyReLU -> global; two warp sets alternate tiles ---------------
         const int ew = warp - EPI_WARP0, set = ew >> 2, quarter = warp & 3;   // a warp may only touch TMEM lanes 32 * (warp % 4) ...
         const float *sbias = reinterpret_cast<const float *>(smem + SM_BIAS);
+        const float *shead = reinterpret_cast<const float *>(smem + SM_HEAD);
         const long long plane_px = (long long)H * W;
         const uint32_t acc_empty_leader = mapa(acc_empty, 0);
         const int pad_shift = a.taps == 9 ? 0 : 0;
@@ -305,6 +310,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
             if (!ok) break;
             umma::fence_after_sync();
             const uint32_t taddr = tbase + ((uint32_t)(quarter * 32) << 16) + abuf * ACC_STRIDE;
+            float hs = 0.0f, hm = 0.0f;      // fused projection: one fma chain per output over the channels in ascending order
+            if (a.head_w) {
+                hs = __ldg(a.head_b);
+                hm = __ldg(a.head_b + 1);
+            }
 #pragma unroll 1
             for (int q = 0; q < KS; ++q) {   // 16 channels per round
                 uint32_t o[16];
@@ -332,6 +342,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = v[j] >= 0.0f ? v[j] : v[j] * a.slope;
                     }
+                    if (a.head_w) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            hs = fmaf(shead[16 * q + j], v[j], hs);
+                            hm = fmaf(shead[C + 16 * q + j], v[j], hm);
+                        }
+                    }
                     if (a.out_f32) {
                         float4 *op = reinterpret_cast<float4 *>(a.out_f32) + ((long long)n * CQ + 4 * q) * plane_px + pix;
 #pragma unroll
@@ -354,6 +371,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
                     rr[j] = nr[j];
                     rr2[j] = nr2[j];
                 }
+            }
+            if (a.head_w && valid) {
+                a.head_scales[(long long)n * plane_px + pix] = hs;
+                a.head_means[(long long)n * plane_px + pix] = hm;
             }
             umma::fence_before_sync();
             mbar_arrive_cluster_relaxed(acc_empty_leader + 8 * abuf);
@@ -470,38 +491,58 @@ struct DcbD {   // the tail of DepthConvBlock(112, 2) (layers/video/layers.py:11
 };
 
 // t1 = LeakyReLU_0.01(conv1(ctx)) (tensor-core layer) -> depthwise 3x3 -> 1x1 to 2 channels, + adaptor(ctx), then the FFN
-// (identity + LeakyReLU_0.1(W2 LeakyReLU_0.1(W1 u + b1) + b2)).  One thread per pixel; channels walk in float4 groups.
-__global__ void __launch_bounds__(128) ctx_dcb_tail_kernel(const float *__restrict__ t1, const float *__restrict__ cx, const DcbD p,
-                                                           float *__restrict__ scales, float *__restrict__ means, int N, int H, int W)
+// (identity + LeakyReLU_0.1(W2 LeakyReLU_0.1(W1 u + b1) + b2)).  One block = a 32 x 4 pixel tile, one thread per pixel; the channels
+// walk in float4 groups, each group's 34 x 6 halo tile staged in shared memory (double buffered) so that a pixel's nine taps are
+// shared-memory reads and every t1 value is fetched from global memory 1.6 instead of 9 times.
+constexpr int DT_W = 32, DT_H = 4, DT_PW = DT_W + 2, DT_PH = DT_H + 2;
+__global__ void __launch_bounds__(DT_W * DT_H) ctx_dcb_tail_kernel(const float *__restrict__ t1, const float *__restrict__ cx, const DcbD p,
+                                                                  float *__restrict__ scales, float *__restrict__ means, int N, int H, int W)
 {
     __shared__ float s_dw[C * 9], s_dwb[C], s_pw[2 * C], s_ad[2 * C];
-    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) s_dw[i] = p.dw_w[i];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) s_dwb[i] = p.dw_b[i];
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    __shared__ float4 s_t[2][DT_PH * DT_PW];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < C * 9; i += blockDim.x) s_dw[i] = p.dw_w[i];
+    for (int i = tid; i < C; i += blockDim.x) s_dwb[i] = p.dw_b[i];
+    for (int i = tid; i < 2 * C; i += blockDim.x) {
         s_pw[i] = p.pw_w[i];
         s_ad[i] = p.ad_w[i];
     }
-    __syncthreads();
-    const long long plane_px = (long long)H * W, total = (long long)N * plane_px;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long n = i / plane_px, pix = i - n * plane_px;
-        const int gx = (int)(pix % W), gy = (int)(pix / W);
+    const int tiles_x = (W + DT_W - 1) / DT_W, tiles_y = (H + DT_H - 1) / DT_H;
+    const long long plane_px = (long long)H * W, n_tiles = (long long)tiles_x * tiles_y * N;
+    const int lx = tid & (DT_W - 1), ly = tid >> 5;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long n = tile / ((long long)tiles_x * tiles_y);
+        const int trem = (int)(tile - n * tiles_x * tiles_y), ty = trem / tiles_x, y0 = ty * DT_H, x0 = (trem - ty * tiles_x) * DT_W;
+        const int gx = x0 + lx, gy = y0 + ly;
+        const bool valid = gx < W && gy < H;
         const float4 *tp = reinterpret_cast<const float4 *>(t1) + n * CQ * plane_px;
-        const float4 *cp = reinterpret_cast<const float4 *>(cx) + n * CQ * plane_px + pix;
+        const float4 *cp = reinterpret_cast<const float4 *>(cx) + n * CQ * plane_px + (long long)gy * W + gx;
+        auto stage = [&](int g, int buf) {
+            for (int i = tid; i < DT_PH * DT_PW; i += DT_W * DT_H) {
+                const int r = i / DT_PW, c = i - r * DT_PW, yy = y0 - 1 + r, xx = x0 - 1 + c;
+                s_t[buf][i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(tp + g * plane_px + (long long)yy * W + xx)
+                                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
         float u0 = 0.0f, u1 = 0.0f, a0 = 0.0f, a1 = 0.0f;
+        __syncthreads();          // weights staged / previous tile's buffers free
+        stage(0, 0);
         for (int g = 0; g < CQ; ++g) {
+            __syncthreads();      // group g is in s_t[g & 1]; everybody has left group g - 1's buffer
+            if (g + 1 < CQ) stage(g + 1, (g + 1) & 1);
+            const float4 *st = s_t[g & 1];
             float d[4] = {s_dwb[4 * g], s_dwb[4 * g + 1], s_dwb[4 * g + 2], s_dwb[4 * g + 3]};
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
+            for (int k = 0; k < 9; ++k) {   // zero padding is in the staged tile: the chain order (ky, kx) matches the per-tap loop
+                const float4 v = st[(ly + k / 3) * DT_PW + lx + k % 3];
                 const int yy = gy + k / 3 - 1, xx = gx + k % 3 - 1;
-                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                const float4 v = __ldg(tp + g * plane_px + (long long)yy * W + xx);
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;   // keep the arithmetic identical to skipping the tap
                 d[0] = fmaf(s_dw[(4 * g) * 9 + k], v.x, d[0]);
                 d[1] = fmaf(s_dw[(4 * g + 1) * 9 + k], v.y, d[1]);
                 d[2] = fmaf(s_dw[(4 * g + 2) * 9 + k], v.z, d[2]);
                 d[3] = fmaf(s_dw[(4 * g + 3) * 9 + k], v.w, d[3]);
             }
-            const float4 cv = __ldg(cp + g * plane_px);
+            const float4 cv = valid ? __ldg(cp + g * plane_px) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float c4[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -511,11 +552,12 @@ __global__ void __launch_bounds__(128) ctx_dcb_tail_kernel(const float *__restri
                 a1 = fmaf(s_ad[C + 4 * g + j], c4[j], a1);
             }
         }
-        const float y0 = (u0 + __ldg(p.pw_b)) + (a0 + __ldg(p.ad_b)), y1 = (u1 + __ldg(p.pw_b + 1)) + (a1 + __ldg(p.ad_b + 1));
+        if (!valid) continue;
+        const float y0v = (u0 + __ldg(p.pw_b)) + (a0 + __ldg(p.ad_b)), y1v = (u1 + __ldg(p.pw_b + 1)) + (a1 + __ldg(p.ad_b + 1));
         float hdn[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float t = fmaf(__ldg(p.f1_w + 2 * j + 1), y1, fmaf(__ldg(p.f1_w + 2 * j), y0, __ldg(p.f1_b + j)));
+            const float t = fmaf(__ldg(p.f1_w + 2 * j + 1), y1v, fmaf(__ldg(p.f1_w + 2 * j), y0v, __ldg(p.f1_b + j)));
             hdn[j] = t >= 0.0f ? t : t * 0.1f;
         }
         float z0 = __ldg(p.f2_b), z1 = __ldg(p.f2_b + 1);
@@ -526,8 +568,9 @@ __global__ void __launch_bounds__(128) ctx_dcb_tail_kernel(const float *__restri
         }
         z0 = z0 >= 0.0f ? z0 : z0 * 0.1f;
         z1 = z1 >= 0.0f ? z1 : z1 * 0.1f;
-        scales[i] = y0 + z0;     // chunk(2, dim=1): channel 0 = scales, channel 1 = means (:172)
-        means[i] = y1 + z1;
+        const long long o = n * plane_px + (long long)gy * W + gx;
+        scales[o] = y0v + z0;     // chunk(2, dim=1): channel 0 = scales, channel 1 = means (:172)
+        means[o] = y1v + z1;
     }
 }
 
@@ -681,11 +724,13 @@ int pmctf_ctx_conv_in(const float *x0, const float *x1, const float *w, const fl
     return (int)cudaGetLastError();
 }
 
-int pmctf_ctx_conv112(const void *in_bf16, const void *packed_w, int taps, const float *bias, const float *res, const float *res2,
-                      float lrelu_slope, float *out_f32, void *out_bf16, int N, int H, int W, void *stream)
+static int launch_conv112(const void *in_bf16, const void *packed_w, int taps, const float *bias, const float *res, const float *res2,
+                          float lrelu_slope, float *out_f32, void *out_bf16, const float *head_w, const float *head_b, float *head_scales,
+                          float *head_means, int N, int H, int W, void *stream)
 {
-    if (!in_bf16 || !packed_w || !bias || N <= 0 || H <= 0 || W <= 0 || !(taps == 9 || taps == 1) || (!out_f32 && !out_bf16))
+    if (!in_bf16 || !packed_w || !bias || N <= 0 || H <= 0 || W <= 0 || !(taps == 9 || taps == 1) || (!out_f32 && !out_bf16 && !head_w))
         return PMCTF_EINVAL;
+    if (head_w && (!head_b || !head_scales || !head_means)) return PMCTF_EINVAL;
     if ((((uintptr_t)in_bf16 | (uintptr_t)packed_w | (uintptr_t)out_f32 | (uintptr_t)out_bf16 | (uintptr_t)res | (uintptr_t)res2) & 15) != 0)
         return PMCTF_EINVAL;
     if ((long long)N * ctx::CH > 0x7fffffffLL || W > (1 << 20) || H > (1 << 20)) return PMCTF_ESHAPE;
@@ -721,10 +766,26 @@ int pmctf_ctx_conv112(const void *in_bf16, const void *packed_w, int taps, const
     const unsigned grid = 2u * (unsigned)(pairs < max_clusters ? pairs : max_clusters);
     ctx::ConvD d;
     d.wimg = (const uint8_t *)packed_w; d.bias = bias; d.res = res; d.res2 = res2; d.out_f32 = out_f32; d.out_bf16 = (__nv_bfloat16 *)out_bf16;
+    d.head_w = head_w; d.head_b = head_b; d.head_scales = head_scales; d.head_means = head_means;
     d.slope = lrelu_slope; d.n = N; d.h = H; d.w = W; d.taps = taps;
     ctx::ctx_conv112_kernel<<<grid, ctx::NT, ctx::SMEM_BYTES, (cudaStream_t)stream>>>(map, d, derr);
     count_launch();
     return (int)cudaGetLastError();
+}
+
+int pmctf_ctx_conv112(const void *in_bf16, const void *packed_w, int taps, const float *bias, const float *res, const float *res2,
+                      float lrelu_slope, float *out_f32, void *out_bf16, int N, int H, int W, void *stream)
+{
+    return launch_conv112(in_bf16, packed_w, taps, bias, res, res2, lrelu_slope, out_f32, out_bf16, nullptr, nullptr, nullptr, nullptr, N, H, W,
+                          stream);
+}
+
+int pmctf_ctx_conv112_head(const void *in_bf16, const void *packed_w, int taps, const float *bias, const float *res, const float *res2,
+                           float lrelu_slope, const float *head_w, const float *head_b, float *scales, float *means, int N, int H, int W,
+                           void *stream)
+{
+    if (!head_w) return PMCTF_EINVAL;
+    return launch_conv112(in_bf16, packed_w, taps, bias, res, res2, lrelu_slope, nullptr, nullptr, head_w, head_b, scales, means, N, H, W, stream);
 }
 
 int pmctf_ctx_lower_subband(const float *prev, const float *w, const float *b, float *out, int N, int h, int w_, void *stream)
@@ -743,7 +804,9 @@ int pmctf_ctx_dcb_tail(const float *t1, const float *ctx_f32, const pmctf_ctx_dc
     ctx::DcbD d;
     d.dw_w = p->dw_w; d.dw_b = p->dw_b; d.pw_w = p->pw_w; d.pw_b = p->pw_b; d.ad_w = p->ad_w; d.ad_b = p->ad_b;
     d.f1_w = p->f1_w; d.f1_b = p->f1_b; d.f2_w = p->f2_w; d.f2_b = p->f2_b;
-    ctx::ctx_dcb_tail_kernel<<<small_grid((long long)N * H * W, 128), 128, 0, (cudaStream_t)stream>>>(t1, ctx_f32, d, scales, means, N, H, W);
+    const long long dtiles = (long long)((W + ctx::DT_W - 1) / ctx::DT_W) * ((H + ctx::DT_H - 1) / ctx::DT_H) * N;
+    ctx::ctx_dcb_tail_kernel<<<(unsigned)(dtiles < 148 * 8 ? dtiles : 148 * 8), ctx::DT_W * ctx::DT_H, 0, (cudaStream_t)stream>>>(t1, ctx_f32, d, scales,
+                                                                                                                        means, N, H, W);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -111,6 +111,8 @@ class ContextFusionFourStep(nn.Module):
     def __getstate__(self):
         st = dict(self.__dict__)
         st["_key"], st["_packed"] = None, None
+        st.pop("_ws", None)
+        st.pop("_pack_hot", None)
         return st
 
     def _load_from_state_dict(self, *args, **kwargs):
@@ -131,6 +133,9 @@ class ContextFusionFourStep(nn.Module):
         return out
 
     def _pack(self):
+        hot = self.__dict__.get("_pack_hot")
+        if hot is not None:                  # inside one forward pass the operands were checked already
+            return hot
         layers = self._tc_layers()
         key = tuple((c.weight.data_ptr(), c.weight._version) for c in layers)
         if key != self._key:
@@ -188,8 +193,7 @@ class ContextFusionFourStep(nn.Module):
                         c.bias.detach().data_ptr(), x1.data_ptr(), N, H // 2, W // 2)
         elif self.ctx_channels == 2:
             raise RuntimeError("this module expects prev_subband (ctx_channels = 2)")
-        a, b = _Features(N, H, W, dev), _Features(N, H, W, dev)
-        t = _Features(N, H, W, dev, f32=False)
+        a, b, _, t = self._workspace(N, H, W, dev)
         self._conv_in(self.conv1_context, context, x1, a)
         self._resblock(self.y_hierarchical_prior_enc[0], a, t, b)
         self._resblock(self.y_hierarchical_prior_enc[1], b, t, a)
@@ -219,13 +223,16 @@ class ContextFusionFourStep(nn.Module):
         self._conv_in(sp[0], x_hat, None, a)
         self._resblock(sp[1], a, t, b, res2=cf)                   # ... + context (:149)
         self._resblock(so[0], b, t, a)
-        keep, b.bf16 = b.bf16, None                               # the last block feeds the fp32 1x1 projection only
-        self._resblock(so[1], a, t, b)
-        b.bf16 = keep
         N, H, W = cf.N, cf.H, cf.W
         scales = torch.empty((N, 1, H, W), dtype=torch.float32, device=x_hat.device)
         means = torch.empty_like(scales)
-        ops._launch(x_hat.device, "ctx_head", nat.lib().pmctf_ctx_head, b.f32.data_ptr(), so[2].weight.detach().data_ptr(),
+        # the last block's second convolution evaluates the 112 -> 2 projection in its epilogue: its feature map is never written
+        blk = so[1]
+        self._conv112(blk.conv1, a, t, slope=0.2)
+        buf, offs = self._pack()
+        off, taps = offs[id(blk.conv2)]
+        ops._launch(x_hat.device, "ctx_conv112_head", nat.lib().pmctf_ctx_conv112_head, t.bf16.data_ptr(), buf.data_ptr() + off, taps,
+                    blk.conv2.bias.detach().data_ptr(), a.f32.data_ptr(), None, 1.0, so[2].weight.detach().data_ptr(),
                     so[2].bias.detach().data_ptr(), scales.data_ptr(), means.data_ptr(), N, H, W)
         return scales, means
 
@@ -286,6 +293,24 @@ class ContextFusionFourStep(nn.Module):
     def _run(self, x, context, prev_subband, stage=None, dec=None):
         """The four steps on the GPU.  Encoder: x given; decoder: dec(k, scales_masked_idx16) -> int16 symbols of step k.
         stage: optional list that receives (sym16, idx16) device tensors per step (compress)."""
+        self.__dict__["_pack_hot"] = None
+        self.__dict__["_pack_hot"] = self._pack()
+        try:
+            return self._run_steps(x, context, prev_subband, stage, dec)
+        finally:
+            self.__dict__["_pack_hot"] = None
+
+    def _workspace(self, N, H, W, dev):
+        """the three full feature maps + the bf16-only intermediate of one call, kept per shape (stream-ordered reuse)"""
+        key = (N, H, W, str(dev))
+        ws = self.__dict__.setdefault("_ws", {})
+        if key not in ws:
+            if len(ws) > 8:
+                ws.clear()
+            ws[key] = (_Features(N, H, W, dev), _Features(N, H, W, dev), _Features(N, H, W, dev), _Features(N, H, W, dev, f32=False))
+        return ws[key]
+
+    def _run_steps(self, x, context, prev_subband, stage=None, dec=None):
         ref_t = x if x is not None else context
         ctx_t = ops._chk(context, "context", 4).contiguous()
         N, _, H, W = ctx_t.shape
@@ -295,7 +320,7 @@ class ContextFusionFourStep(nn.Module):
                 raise RuntimeError(f"x {tuple(x.shape)} vs context {tuple(ctx_t.shape)}")
         dev = ref_t.device
         cf, b, t = self._context_features(ctx_t, prev_subband, N, H, W)
-        a = _Features(N, H, W, dev)
+        a = self._workspace(N, H, W, dev)[2]
         scales, means = self._hierarchical(cf, a)
         run = {k: torch.empty((N, 1, H, W), dtype=torch.float32, device=dev) for k in ("x_hat", "x_q", "s_hat", "x_res")}
         steps = []

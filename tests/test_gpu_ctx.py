@@ -179,3 +179,29 @@ def test_four_step_1080p_subband_runs(conv_mode):
     assert torch.isfinite(s_hat).all() and torch.isfinite(x_hat).all()
     assert torch.equal(x_q, torch.round(x_res))
     assert (x_hat - (x_q + (x - x_res))).abs().max().item() < 1e-5
+
+
+def test_fused_head_equals_separate_projection(conv_mode):
+    """pmctf_ctx_conv112_head == pmctf_ctx_conv112 (fp32 map) + pmctf_ctx_head, bit for bit."""
+    if conv_mode != "tensor":
+        pytest.skip("independent of the lifting arithmetic")
+    lib = nat.lib()
+    g = torch.Generator().manual_seed(9)
+    N, H, W = 2, 37, 61
+    x = to_bf16_planar(torch.randn(N, 112, H, W, generator=g)).to(DEV)
+    res = to_f32_planar(torch.randn(N, 112, H, W, generator=g)).to(DEV)
+    w = (torch.randn(112, 112, 3, 3, generator=g) * 0.05).to(DEV)
+    b = (torch.randn(112, generator=g) * 0.1).to(DEV)
+    hw = (torch.randn(2, 112, 1, 1, generator=g) * 0.1).to(DEV)
+    hb = torch.randn(2, generator=g).to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    packed = torch.empty(int(lib.pmctf_ctx_packed_bytes(9)), dtype=torch.uint8, device=DEV)
+    nat.check(lib.pmctf_ctx_pack_conv(w.data_ptr(), 9, packed.data_ptr(), st), "pack")
+    of = torch.empty((N, 28, H, W, 4), device=DEV)
+    s1, m1, s2, m2 = (torch.empty((N, 1, H, W), device=DEV) for _ in range(4))
+    nat.check(lib.pmctf_ctx_conv112(x.data_ptr(), packed.data_ptr(), 9, b.data_ptr(), res.data_ptr(), None, 1.0, of.data_ptr(), None, N, H, W, st), "conv")
+    nat.check(lib.pmctf_ctx_head(of.data_ptr(), hw.data_ptr(), hb.data_ptr(), s1.data_ptr(), m1.data_ptr(), N, H, W, st), "head")
+    nat.check(lib.pmctf_ctx_conv112_head(x.data_ptr(), packed.data_ptr(), 9, b.data_ptr(), res.data_ptr(), None, 1.0, hw.data_ptr(), hb.data_ptr(),
+                                         s2.data_ptr(), m2.data_ptr(), N, H, W, st), "conv_head")
+    torch.cuda.synchronize()
+    assert torch.equal(s1, s2) and torch.equal(m1, m2)

@@ -75,7 +75,22 @@ def main():
     with torch.no_grad():
         ms = timed(ours, 1 if prof else 3, warm=1 if prof else 2)
     out["module_12_subbands_1080p_luma"] = {"ms": ms, "coefficients": coeffs, "tflops": MODULE_FLOPS * coeffs / ms / 1e9}
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ours()
+    out["module_12_subbands_1080p_luma"]["host_enqueue_ms"] = (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize()
     assert pkg.ops.tc_error_flag() == 0
+    if not prof:   # the whole coder of one plane: transform + LL model + long-term context + 12 four-step models + PostProcess (pWave.forward)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_pwave_coder import _randomise
+        pw = _randomise(pkg.pWave(entropy_model=True)).to(dev).eval()
+        xin = (torch.nn.functional.avg_pool2d(torch.rand((1, 1, 1156, 1924), device=dev), 5, 1, 0) * 255).round().contiguous()
+        with torch.no_grad():
+            ms_pw = timed(lambda: pw(xin, q_index=12), 3, warm=2)
+        out["pwave_forward_1080p_luma"] = {"ms": ms_pw, "planes_per_s": 1e3 / ms_pw}
     if "--no-stock" not in sys.argv and not prof:
         def stock():
             for m, x, c, p in inputs:

@@ -1,6 +1,6 @@
 """Achieved HBM bandwidth of the stand-alone (module-API) HBM-bound kernels: algorithmic bytes / CUDA-event time, against the
 measured copy bandwidth of MEASURED_PEAKS.json.  Inputs larger than L2 (16 luma frames), 20 timed launches after 5 warm-ups.
-    python scratch/hbm_kernels.py  ->  one JSON line"""
+    python tools/hbm_kernels.py  ->  one JSON line"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -8,8 +8,8 @@ LL="--steps 1 --warmup 3 --frames 16 --no-e2e --no-cpu-baseline --single-stream 
 python bench.py $LL > gpurun_out/${tag}_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py $LL > gpurun_out/${tag}_ncu1.log 2>&1
-[ -f learned-pmctf_b200/lib/libpmctf_b200_timing.so ] && python scratch/tc_phases.py > gpurun_out/${tag}_phases.log 2>&1
-python scratch/prof_tc.py > gpurun_out/${tag}_prof_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:lift_step_tc -c 3 -f -o gpurun_out/${tag}_tc_prof python scratch/prof_tc.py > gpurun_out/${tag}_ncu2.log 2>&1
+[ -f learned-pmctf_b200/lib/libpmctf_b200_timing.so ] && python tools/tc_phases.py > gpurun_out/${tag}_phases.log 2>&1
+python tools/prof_tc.py > gpurun_out/${tag}_prof_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:lift_step_tc -c 3 -f -o gpurun_out/${tag}_tc_prof python tools/prof_tc.py > gpurun_out/${tag}_ncu2.log 2>&1
 python -c "
 import json; d=json.load(open('gpurun_out/${tag}_bench.json')); print('frames/s', d['value'], 'e2e', d['e2e']['value'], 'frac', d['roofline']['frac'], 'cpu', d['cpu_baseline']['value'])"

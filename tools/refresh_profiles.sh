@@ -1,5 +1,5 @@
 #!/bin/bash
-# Regenerates the tracked profiles/<tag>_* summaries from the raw outputs of scratch/gpu_final.sh in gpurun_out/ (tag = $1).
+# Regenerates the tracked profiles/<tag>_* summaries from the raw outputs of tools/measure_round.sh in gpurun_out/ (tag = $1).
 set -e
 tag=${1:-r1z}
 cd "$(dirname "$0")/.."
@@ -11,7 +11,7 @@ echo "# down a column strip; the rows two tiles share travel in registers: conv1
 echo "# 128-pixel blocks), conv1 -> conv2 -> conv3 pipelined through mbarriers (no CTA barrier between them: the MMA warp starts conv2 while"
 echo "# conv1's later passes run and conv3 while conv2's last epilogues run), everything of round 1 (exact int8 digit-split MMAs, conv4 as"
 echo "# per-tap partials, conv1/conv4 weights as kernel arguments, TMA-staged operand images)."
-echo "# command: python scratch/prof_tc.py (bench.py's weights, 4 planes per launch); launches 1,2: 1080p luma temporal forward MCTF"
+echo "# command: python tools/prof_tc.py (bench.py's weights, 4 planes per launch); launches 1,2: 1080p luma temporal forward MCTF"
 echo "# (<1> WARP source, 4 x 2.21 Mpx = 17 280 tiles); launch 3: first row step of the 2-D lifting (<2> SKIP3, 4 x 1.1 Mpx = 8 640 tiles)."
 echo "# Persistent grid 296 CTAs = 2 per SM, 288 threads, 113 KB smem.  Algorithmic HBM bytes of launch 1: 4 x 44.2 MB (20 B/px)."
 echo "# Reading: no unit is saturated -- issue slots ~52-55 %, shared-memory data pipe (LSU + tensor-core operand fetch) ~67-78 %, tensor"
@@ -52,7 +52,7 @@ def val(r, name):
 r = data[0]
 d = {"dram_bytes_per_launch": val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"),
      "dram_bytes_read": val(r, "dram__bytes_read.sum"), "dram_bytes_write": val(r, "dram__bytes_write.sum"),
-     "what": "launch 1 of scratch/prof_tc.py: temporal lifting step (WARP source) on 4 luma planes 1152x1920, ncu --set full",
+     "what": "launch 1 of tools/prof_tc.py: temporal lifting step (WARP source) on 4 luma planes 1152x1920, ncu --set full",
      "algorithmic_bytes": 4 * 1152 * 1920 * 20, "source": f"gpurun_out/{tag}_tc_prof.ncu-rep via tools/refresh_profiles.sh"}
 json.dump(d, open(f"profiles/{tag}_traffic.json", "w"), indent=1)
 print("traffic", d["dram_bytes_per_launch"], "algorithmic", d["algorithmic_bytes"])

@@ -1,4 +1,4 @@
-"""Turns the raw ncu outputs of a measurement run (scratch/gpu_final.sh) into the text summaries kept under profiles/.
+"""Turns the raw ncu outputs of a measurement run (tools/measure_round.sh) into the text summaries kept under profiles/.
 
     python tools/summarize_ncu.py launches gpurun_out/<tag>_launches.csv  > profiles/<tag>_ncu_launches_summary.txt
     python tools/summarize_ncu.py full     gpurun_out/<tag>_tc_prof.ncu-rep > profiles/<tag>_lift_step_tc_ncu.txt
