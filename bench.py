@@ -388,6 +388,60 @@ def run_context_fusion(pkg, dev, pk):
             "tensor_core_layer_576x960": layer, "torch_gpu_baseline": base}
 
 
+SPYNET_FLOPS_PER_PX = 2 * 49 * (8 * 32 + 32 * 64 + 64 * 32 + 32 * 16 + 16 * 2)     # one MEBasic; the 6-level pyramid costs 4/3 of it per pixel
+
+
+def run_spynet(pkg, dev, pk):
+    """SpyNet motion estimation (video_net.py:74-121) for one 1080p frame pair as pMCTF calls it (luma / 255
+    tiled to 3 channels, pMCTF_L.py:253-260).  Secondary block.  7x7 layers as tcgen05 CTA-pair implicit GEMMs (run-time channel
+    counts); the same module on stock torch ops beside it."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import spynet_weights
+    from learned_pmctf_b200.layers.video.video_net import ME_Spynet
+    m = ME_Spynet(L=6).to(dev).eval()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in spynet_weights.make(3).items()})
+    g = torch.Generator(device=dev).manual_seed(2)
+    a = torch.nn.functional.avg_pool2d(torch.rand((1, 1, 1156, 1924), device=dev, generator=g), 5, 1)
+    b = torch.roll(a, (2, -3), (2, 3))
+    im1, im2 = a.tile(1, 3, 1, 1).contiguous(), b.tile(1, 3, 1, 1).contiguous()
+
+    def timed(fn, reps, warm=2):
+        for _ in range(warm):
+            y = fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            y = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps, y
+    with torch.no_grad():
+        ms, flow = timed(lambda: m(im1, im2), 5)
+        base = {}
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            try:
+                sms, fs = timed(lambda: m._forward_torch(im1, im2), 2, warm=1)
+                base["tf32" if tf32 else "fp32"] = {"ms_per_pair": sms, "mean_abs_flow_diff_vs_ours_px": float((fs - flow).abs().mean())}
+            except Exception as ex:
+                base["tf32" if tf32 else "fp32"] = {"error": str(ex)[:100]}
+        torch.backends.cudnn.allow_tf32 = True
+    pkg.ops.check_tc_error(dev, "spynet block")
+    px = 1152 * 1920 * sum(0.25 ** i for i in range(6))
+    tf = SPYNET_FLOPS_PER_PX * px / ms / 1e9
+    return {"what": "ME_Spynet (video_net.py:94-121; 6 levels x five 7x7 convolutions 8->32->64->32->16->2) on one 1080p luma pair (1152x1920): "
+                    "layers as tcgen05 CTA-pair implicit GEMMs (cta_group::2, bf16 operands, TMA tensor loads, 49 taps addressed by descriptor "
+                    "start address), pyramid / upsampling / warp / operand packing in one CUDA-core kernel per level",
+            "ms_per_pair": ms, "pairs_per_s": 1e3 / ms, "algorithmic_flops_per_px": SPYNET_FLOPS_PER_PX,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
+                         "peak_source": f"{pk['source']} bf16 dense, sustained",
+                         "scope": "the whole estimator (36 launches: 6 levels x (prep + 5 layers)); N <= 64 per layer, so the MMAs are bounded by the "
+                                  "A-operand fetch from shared memory (128 x 32 B per 256x64x16 MMA), not by the tensor pipe"},
+            "torch_gpu_baseline": base}
+
+
 def run_uvg(args, pkg, G, par, model, dev, rank, world):
     """BASELINE configs[3] as written: 7 synthetic 1080p sequences x 96 frames (6 GOP-16s each) x the q_index list of
     test_pMCTF_flex.py:436-443, FLATTENED into 252 work items (q_index, sequence, gop), sharded round-robin over the ranks
@@ -601,6 +655,7 @@ def main():
     ap.add_argument("--uvg-sequences", type=int, default=7)
     ap.add_argument("--no-int8-peak", action="store_true", help="skip measuring the int8 dense peak of this GPU")
     ap.add_argument("--no-postprocess", action="store_true", help="skip the PostProcess block (section 8f row 2, secondary)")
+    ap.add_argument("--no-spynet", action="store_true", help="skip the SpyNet block (section 8f row 4, secondary)")
     ap.add_argument("--no-train-block", action="store_true", help="skip the configs[4] training-step block (child process, secondary)")
     ap.add_argument("--no-context-fusion", action="store_true", help="skip the entropy-parameter network block (section 8f row 1, secondary)")
     ap.add_argument("--workload", default="gop16", choices=["gop16", "train"],
@@ -765,6 +820,12 @@ def main():
             trainb = json.loads(lines[-1]) if lines else {"error": (r.stderr or "no output")[-200:]}
         except Exception as ex:
             trainb = {"error": str(ex)[:200]}
+    spyb = None
+    if world == 1 and not args.no_spynet and args.frames == FRAMES:
+        try:
+            spyb = run_spynet(pkg, dev, pk)
+        except Exception as ex:
+            spyb = {"error": str(ex)[:200]}
     ctxb = None
     if world == 1 and not args.no_context_fusion and args.frames == FRAMES:
         try:
@@ -846,7 +907,7 @@ def main():
                        "streams": "1" if args.single_stream else "2 per GPU: luma chain | chroma chain (independent on the path)",
                        "parallelism": f"gop-sharded dp{world}, all_gather of per-frame statistics per step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "torch_gpu_baseline": torch_gpu, "uvg": uvg, "postprocess": ppb, "context_fusion": ctxb, "train": trainb,
+            "torch_gpu_baseline": torch_gpu, "uvg": uvg, "postprocess": ppb, "context_fusion": ctxb, "spynet": spyb, "train": trainb,
             "quality": {"mean_psnr_yuv_db": float(psnr[torch.isfinite(psnr)].mean()), "frames": int(psnr.numel())}}
     emit(line)
     if world > 1:

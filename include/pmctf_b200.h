@@ -348,6 +348,24 @@ typedef struct {
 } pmctf_ctx_step_t;
 int pmctf_ctx_mask_step(const pmctf_ctx_step_t *s, void *stream);
 
+/* ---- SpyNet motion estimation: pMCTF/layers/video/video_net.py:74-121 ---------------------------
+ * pmctf_pair_conv: nn.Conv2d(cin, cout, k, padding = k/2), k = 1, 3 or 7, between channel-chunked bf16 maps as a tcgen05 CTA-pair
+ * implicit GEMM (run-time channel counts; the machine of pmctf_ctx_conv112).  in_bf16 [N][cin_pad/8][H][W][8] (cin_pad a multiple of
+ * 16, <= 64; channels beyond the layer's cin hold zeros or meet zero weights), weights packed once by pmctf_pair_pack_conv
+ * (OIHW fp32 [cout,cin,k,k] -> pmctf_pair_packed_bytes(k, cin_pad, cout_pad) bytes, 16-byte aligned, cout_pad a multiple of 16,
+ * <= 128).  out = lrelu_slope(conv + bias [+ add_nchw]) (slope 0 = ReLU, 1 = identity) written as bf16 [N][cout_pad/8][H][W][8]
+ * (padding channels zero) and / or fp32 NCHW [N,cout,H,W]; add_nchw (fp32 NCHW) only with out_nchw. */
+long long pmctf_pair_packed_bytes(int ks, int cin_pad, int cout_pad);
+int pmctf_pair_pack_conv(const float *w, int cout, int cin, int ks, int cin_pad, int cout_pad, void *packed, void *stream);
+int pmctf_pair_conv(const void *in_bf16, const void *packed_w, const float *bias, int ks, int cin_pad, int cout, int cout_pad, float slope,
+                    void *out_bf16, float *out_nchw, const float *add_nchw, int N, int H, int W, void *stream);
+/* One pyramid level's network input (video_net.py:113-119): flow_up [N,2,H,W] = 2 * bilinear x2 upsampling of flow [N,2,H/2,W/2]
+ * (F.interpolate, align_corners=False; flow == NULL: zeros, the coarsest level), im2 warped by it (flow_warp, video_net.py:32-55),
+ * and the bf16 operand records [im1 (3 ch), warp(im2) (3), flow_up (2), 8 zeros] as [N][2][H][W][8].  im1, im2: [N,3,H,W]. */
+int pmctf_spynet_prep(const float *im1, const float *im2, const float *flow, float *flow_up, void *rec_bf16, int N, int H, int W, void *stream);
+/* F.avg_pool2d(x, 2, 2) on `planes` planes of H x W (the image pyramid, video_net.py:104-106) */
+int pmctf_avgpool2(const float *in, float *out, long long planes, int H, int W, void *stream);
+
 /* ---- entropy-coder boundary ----------------------------------------------------------------
  * HOST functions (plain host pointers, no stream): the 64-bit rANS coder of pMCTF/cpp/rans/rans.cpp:76-168,272-331 behind the
  * sub-stream container of pMCTF/cpp/py_rans/py_rans.cpp:22-225 (what the reference binds as MLCodec_rans.RansEncoder /

@@ -2,7 +2,8 @@
 temporal lifting + pWave++ spatial lifting hot path behind the reference's nn.Module surface.
 
 Layout mirrors the reference package for the modules on the path:
-    layers.video.video_net                       flow_warp, bilineardownsacling
+    layers.video.video_net                       flow_warp, bilineardownsacling, ME_Spynet (SpyNet)
+    layers.context_fusion_4step / context_fusion / long_context   entropy-parameter networks (section 8f row 1)
     layers.video.wavelet_transform_temporal_mctf TemporalLifting
     layers.lifting_1d                            PredictUpdate, iWave1D, split, merge
     layers.wavelet_transform                     LiftingScheme2D
@@ -17,7 +18,7 @@ Layout mirrors the reference package for the modules on the path:
 """
 from . import _native, ops  # noqa: F401
 from .layers import LiftingScheme2D, PostProcess, PredictUpdate, iWave1D  # noqa: F401
-from .layers.video.video_net import bilineardownsacling, flow_warp  # noqa: F401
+from .layers.video.video_net import ME_Spynet, MEBasic, bilineardownsacling, flow_warp  # noqa: F401
 from .layers.video.wavelet_transform_temporal_mctf import TemporalLifting  # noqa: F401
 from .models.pWave import pWave  # noqa: F401
 from .models.video.pMCTF_L import accelerate, pMCTF  # noqa: F401

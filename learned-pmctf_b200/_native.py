@@ -13,7 +13,7 @@ ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("PMCTF_LIB") or os.path.join(_HERE, "lib", "libpmctf_b200.so")  # PMCTF_LIB: profiling builds only
 SOURCES = [os.path.join(_HERE, "csrc", "pmctf_kernels.cu"), os.path.join(_HERE, "csrc", "pmctf_umma_test.cu"),
            os.path.join(_HERE, "csrc", "pmctf_lift_tc.cu"), os.path.join(_HERE, "csrc", "pmctf_train.cu"),
-           os.path.join(_HERE, "csrc", "pmctf_pp.cu"), os.path.join(_HERE, "csrc", "pmctf_rans.cu"), os.path.join(_HERE, "csrc", "pmctf_ctx.cu")]
+           os.path.join(_HERE, "csrc", "pmctf_pp.cu"), os.path.join(_HERE, "csrc", "pmctf_rans.cu"), os.path.join(_HERE, "csrc", "pmctf_ctx.cu"), os.path.join(_HERE, "csrc", "pmctf_pairconv.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "pmctf_umma.cuh"), os.path.join(_HERE, "csrc", "pmctf_common.cuh")]
 INCLUDE = os.path.join(ROOT, "include")
 
@@ -124,6 +124,11 @@ SIGNATURES = {
     "pmctf_ctx_dcb_tail": [_P, _P, C.POINTER(CtxDcb), _P, _P, _I, _I, _I, _P],
     "pmctf_ctx_head": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "pmctf_ctx_mask_step": [C.POINTER(CtxStep), _P],
+    "pmctf_pair_packed_bytes": [_I, _I, _I],
+    "pmctf_pair_pack_conv": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "pmctf_pair_conv": [_P, _P, _P, _I, _I, _I, _I, _f, _P, _P, _P, _I, _I, _I, _P],
+    "pmctf_spynet_prep": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "pmctf_avgpool2": [_P, _P, _LL, _I, _I, _P],
     "pmctf_pmf_to_quantized_cdf": [_P, _I, _I, _P],
     "pmctf_rans_encoder_create": [_I, _I, _P],
     "pmctf_rans_encoder_destroy": [_P],
@@ -144,7 +149,7 @@ SIGNATURES = {
     "pmctf_umma_selftest": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P],
 }
 _RESTYPES = {"pmctf_error_string": C.c_char_p, "pmctf_lift2d_workspace": C.c_longlong, "pmctf_pp_packed_bytes": C.c_longlong,
-             "pmctf_postprocess_workspace": C.c_longlong, "pmctf_rans_encoded_size": C.c_longlong, "pmctf_ctx_packed_bytes": C.c_longlong,
+             "pmctf_postprocess_workspace": C.c_longlong, "pmctf_rans_encoded_size": C.c_longlong, "pmctf_ctx_packed_bytes": C.c_longlong, "pmctf_pair_packed_bytes": C.c_longlong,
              "pmctf_launch_count": C.c_ulonglong}
 
 NVCC_FLAGS = ["--threads", "8", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",

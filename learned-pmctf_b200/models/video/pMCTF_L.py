@@ -143,7 +143,8 @@ def accelerate(ref_model):
     """Graft the B200 hot path onto an instance of the REFERENCE pMCTF (pMCTF_L.py:29): its
     TemporalLifting / LiftingScheme2D submodules are replaced by ours with the SAME parameter
     tensors (state_dict keys and values unchanged), and the hot-path methods are rebound.  The
-    rest of the model (SpyNet, MV codec, context models, rANS, PostProcess) is untouched."""
+    four-step entropy-parameter networks, PostProcess and SpyNet are replaced the same way; the MV codec, the LL model and the
+    ConvLSTM context stay the reference's stock torch modules."""
     from ...layers import LiftingScheme2D
 
     def adopt(dst: nn.Module, src: nn.Module):
@@ -177,6 +178,10 @@ def accelerate(ref_model):
                         cf[lvl][band] = adopt(new, old).train(old.training)
         for m in _PWAVE_METHODS:
             setattr(coder, m, types.MethodType(getattr(pWaveTransform, m), coder))
+    of = getattr(ref_model, "optic_flow", None)
+    if of is not None and hasattr(of, "moduleBasic") and all(hasattr(b, "conv5") for b in of.moduleBasic):   # the reference's ME_Spynet
+        from ...layers.video.video_net import ME_Spynet
+        ref_model.optic_flow = adopt(ME_Spynet(L=of.L).to(next(of.parameters()).device), of).train(of.training)
     for m in _MCTF_METHODS:
         setattr(ref_model, m, types.MethodType(getattr(MCTFMixin, m), ref_model))
     import sys

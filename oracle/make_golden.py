@@ -306,8 +306,28 @@ def main_ctx4():
     np.savez_compressed(os.path.join(OUT, "ctx4.npz"), **out)
 
 
+def main_spynet():
+    """tests/golden/spynet.npz: the reference's ME_Spynet (pMCTF/layers/video/video_net.py:94-121) on a synthetic frame pair shifted by
+    (1.5, -0.75) px, as pMCTF feeds it (luma / 255 tiled to 3 channels, pMCTF_L.py:253-256), CPU fp32, seeded weights of
+    tests/spynet_weights.py."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
+    import spynet_weights
+    from pMCTF.layers.video.video_net import ME_Spynet
+    m = ME_Spynet(L=6).eval()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in spynet_weights.make(21).items()}, strict=True)
+    f = frames(2, 128, 192, 77)
+    cur = (f[0:1] / 255.0).tile((1, 3, 1, 1))
+    ref = (f[1:2] / 255.0).tile((1, 3, 1, 1))
+    with torch.no_grad():
+        flow = m(cur, ref)
+    print("spynet: flow range %.3f .. %.3f, mean |flow| %.3f" % (float(flow.min()), float(flow.max()), float(flow.abs().mean())))
+    np.savez_compressed(os.path.join(OUT, "spynet.npz"), cur=npy(cur[:, :1]), ref=npy(ref[:, :1]), flow=npy(flow), seed=np.array(21))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "ctx4":
+    if len(sys.argv) > 1 and sys.argv[1] == "spynet":
+        main_spynet()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ctx4":
         main_ctx4()
     elif len(sys.argv) > 1 and sys.argv[1] == "postprocess":
         main_postprocess()
