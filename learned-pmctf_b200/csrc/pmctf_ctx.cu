@@ -62,6 +62,17 @@ constexpr int EPI_SETS = 2, EPI_WARPS = 4 * EPI_SETS;
 constexpr int PRODUCER_WARP = 0, MMA_WARP = 1, EPI_WARP0 = 2;
 constexpr int NT = 32 * (EPI_WARP0 + EPI_WARPS);
 
+// The same geometry for any channel count that is a multiple of 16: 112 (the entropy-parameter network, the constants above) and
+// 64 (PostProcess, csrc/pmctf_pp.cu, whose 64 -> 64 layers run through this kernel as well).
+template <int CC>
+struct Geo {
+    static constexpr int C = CC, KS = CC / 16, CH = CC / 8, CQ = CC / 4;
+    static constexpr int PLANE = IN_R * P * 16, INBUF = CH * PLANE, NHALF = CC / 2, WSLAB = 2 * NHALF * 16, WHALF_MAX = 9 * KS * WSLAB;
+    static constexpr int SM_W = 0, SM_IN = SM_W + WHALF_MAX, SM_BAR = SM_IN + N_IN * INBUF, SM_BIAS = SM_BAR + 128, SM_HEAD = SM_BIAS + CC * 4;
+    static constexpr int SMEM_BYTES = SM_HEAD + 2 * CC * 4;
+    static_assert(SM_IN % 128 == 0 && INBUF % 128 == 0 && SM_BAR % 8 == 0 && SMEM_BYTES <= 227 * 1024 && CC % 16 == 0 && CC <= ACC_STRIDE, "geometry");
+};
+
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 256 (CTA pair), N = n
 __host__ __device__ constexpr uint32_t idesc_bf16_m256(uint32_t n)
 {
@@ -163,9 +174,13 @@ struct ConvD {
     int n, h, w, taps;            // taps: 9 (3x3, padding 1) or 1 (1x1)
 };
 
+template <int CC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
-    ctx_conv112_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvD a, int *__restrict__ err)
+    ctx_conv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvD a, int *__restrict__ err)
 {
+    using G = Geo<CC>;   // the names below shadow the namespace-level constants of the 112-channel case
+    constexpr int C = G::C, KS = G::KS, CH = G::CH, CQ = G::CQ, PLANE = G::PLANE, INBUF = G::INBUF, NHALF = G::NHALF, WSLAB = G::WSLAB;
+    constexpr int SM_W = G::SM_W, SM_IN = G::SM_IN, SM_BAR = G::SM_BAR, SM_BIAS = G::SM_BIAS, SM_HEAD = G::SM_HEAD;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);
     // barriers: in_full[2] (leader's are used), in_empty[2], acc_full[4], acc_empty[4] (leader's are used), weights, peer-weights
@@ -392,8 +407,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
 }
 
 // OIHW fp32 [112][112][k][k] -> per-rank bf16 operand images [rank][tap][k-step][chunk][56 rows][8 ci]
+template <int CC>
 __global__ void ctx_pack_kernel(const float *__restrict__ w, int taps, __nv_bfloat16 *__restrict__ img)
 {
+    constexpr int C = CC, KS = CC / 16, NHALF = CC / 2;
     const int total = 2 * taps * KS * 2 * NHALF * 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int t = i;
@@ -693,6 +710,70 @@ static unsigned small_grid(long long items, int per_block)
     return (unsigned)blocks;
 }
 
+template <int CC>
+static int launch_pair_conv(const void *in_bf16, const void *packed_w, int taps, const float *bias, const float *res, const float *res2,
+                          float lrelu_slope, float *out_f32, void *out_bf16, const float *head_w, const float *head_b, float *head_scales,
+                          float *head_means, int N, int H, int W, void *stream)
+{
+    if (!in_bf16 || !packed_w || !bias || N <= 0 || H <= 0 || W <= 0 || !(taps == 9 || taps == 1) || (!out_f32 && !out_bf16 && !head_w))
+        return PMCTF_EINVAL;
+    if (head_w && (!head_b || !head_scales || !head_means)) return PMCTF_EINVAL;
+    if ((((uintptr_t)in_bf16 | (uintptr_t)packed_w | (uintptr_t)out_f32 | (uintptr_t)out_bf16 | (uintptr_t)res | (uintptr_t)res2) & 15) != 0)
+        return PMCTF_EINVAL;
+    using G = ctx::Geo<CC>;
+    if ((long long)N * G::CH > 0x7fffffffLL || W > (1 << 20) || H > (1 << 20)) return PMCTF_ESHAPE;
+    static int configured_for[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
+    if (dev < 0 || dev >= 64) return PMCTF_EINVAL;
+    if (!configured_for[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(ctx::ctx_conv_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return (int)cudaGetLastError();
+        configured_for[dev] = sms;
+    }
+    encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc) return PMCTF_EINVAL;
+    CUtensorMap map;
+    const cuuint64_t gdim[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * G::CH};
+    const cuuint64_t gstr[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+    const cuuint32_t box[4] = {8, ctx::P, ctx::IN_R, G::CH};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(in_bf16), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return PMCTF_ESHAPE;
+    volatile int *herr = nullptr;
+    int *derr = nullptr;
+    int e = tc_watchdog(&herr, &derr);
+    if (e) return e;
+    if (herr[0] != 0) return PMCTF_ETIMEOUT;
+    const long long tiles = (long long)((W + ctx::TW - 1) / ctx::TW) * ((H + ctx::TH - 1) / ctx::TH) * N;
+    if (tiles <= 0 || tiles > 0x7fffffffLL) return PMCTF_ESHAPE;
+    const long long pairs = (tiles + 1) / 2, max_clusters = configured_for[dev] / 2;
+    const unsigned grid = 2u * (unsigned)(pairs < max_clusters ? pairs : max_clusters);
+    ctx::ConvD d;
+    d.wimg = (const uint8_t *)packed_w; d.bias = bias; d.res = res; d.res2 = res2; d.out_f32 = out_f32; d.out_bf16 = (__nv_bfloat16 *)out_bf16;
+    d.head_w = head_w; d.head_b = head_b; d.head_scales = head_scales; d.head_means = head_means;
+    d.slope = lrelu_slope; d.n = N; d.h = H; d.w = W; d.taps = taps;
+    ctx::ctx_conv_kernel<CC><<<grid, ctx::NT, G::SMEM_BYTES, (cudaStream_t)stream>>>(map, d, derr);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+// PostProcess (csrc/pmctf_pp.cu) runs its 64 -> 64 layers through the same kernel
+int pair_conv64(const void *in_bf16, const void *packed_w, const float *bias, const float *res, float slope, float *out_f32, void *out_bf16, int N,
+                int H, int W, void *stream)
+{
+    return launch_pair_conv<64>(in_bf16, packed_w, 9, bias, res, nullptr, slope, out_f32, out_bf16, nullptr, nullptr, nullptr, nullptr, N, H, W, stream);
+}
+int pair_pack64(const float *w, void *packed, void *stream)
+{
+    const int total = 2 * 9 * 4 * 2 * 32 * 8;
+    ctx::ctx_pack_kernel<64><<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, 9, (__nv_bfloat16 *)packed);
+    count_launch();
+    return (int)cudaGetLastError();
+}
 } // namespace pmctf
 
 using namespace pmctf;
@@ -705,7 +786,7 @@ int pmctf_ctx_pack_conv(const float *w, int taps, void *packed, void *stream)
 {
     if (!w || !packed || !(taps == 9 || taps == 1) || ((uintptr_t)packed & 15)) return PMCTF_EINVAL;
     const int total = 2 * taps * ctx::KS * 2 * ctx::NHALF * 8;
-    ctx::ctx_pack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, taps, (__nv_bfloat16 *)packed);
+    ctx::ctx_pack_kernel<112><<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, taps, (__nv_bfloat16 *)packed);
     count_launch();
     return (int)cudaGetLastError();
 }
@@ -724,59 +805,10 @@ int pmctf_ctx_conv_in(const float *x0, const float *x1, const float *w, const fl
     return (int)cudaGetLastError();
 }
 
-static int launch_conv112(const void *in_bf16, const void *packed_w, int taps, const float *bias, const float *res, const float *res2,
-                          float lrelu_slope, float *out_f32, void *out_bf16, const float *head_w, const float *head_b, float *head_scales,
-                          float *head_means, int N, int H, int W, void *stream)
-{
-    if (!in_bf16 || !packed_w || !bias || N <= 0 || H <= 0 || W <= 0 || !(taps == 9 || taps == 1) || (!out_f32 && !out_bf16 && !head_w))
-        return PMCTF_EINVAL;
-    if (head_w && (!head_b || !head_scales || !head_means)) return PMCTF_EINVAL;
-    if ((((uintptr_t)in_bf16 | (uintptr_t)packed_w | (uintptr_t)out_f32 | (uintptr_t)out_bf16 | (uintptr_t)res | (uintptr_t)res2) & 15) != 0)
-        return PMCTF_EINVAL;
-    if ((long long)N * ctx::CH > 0x7fffffffLL || W > (1 << 20) || H > (1 << 20)) return PMCTF_ESHAPE;
-    static int configured_for[64] = {0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
-    if (dev < 0 || dev >= 64) return PMCTF_EINVAL;
-    if (!configured_for[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(ctx::ctx_conv112_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx::SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        int sms = 0;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return (int)cudaGetLastError();
-        configured_for[dev] = sms;
-    }
-    encode_tiled_fn enc = tensor_map_encoder();
-    if (!enc) return PMCTF_EINVAL;
-    CUtensorMap map;
-    const cuuint64_t gdim[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * ctx::CH};
-    const cuuint64_t gstr[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-    const cuuint32_t box[4] = {8, ctx::P, ctx::IN_R, ctx::CH};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(in_bf16), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return PMCTF_ESHAPE;
-    volatile int *herr = nullptr;
-    int *derr = nullptr;
-    int e = tc_watchdog(&herr, &derr);
-    if (e) return e;
-    if (herr[0] != 0) return PMCTF_ETIMEOUT;
-    const long long tiles = (long long)((W + ctx::TW - 1) / ctx::TW) * ((H + ctx::TH - 1) / ctx::TH) * N;
-    if (tiles <= 0 || tiles > 0x7fffffffLL) return PMCTF_ESHAPE;
-    const long long pairs = (tiles + 1) / 2, max_clusters = configured_for[dev] / 2;
-    const unsigned grid = 2u * (unsigned)(pairs < max_clusters ? pairs : max_clusters);
-    ctx::ConvD d;
-    d.wimg = (const uint8_t *)packed_w; d.bias = bias; d.res = res; d.res2 = res2; d.out_f32 = out_f32; d.out_bf16 = (__nv_bfloat16 *)out_bf16;
-    d.head_w = head_w; d.head_b = head_b; d.head_scales = head_scales; d.head_means = head_means;
-    d.slope = lrelu_slope; d.n = N; d.h = H; d.w = W; d.taps = taps;
-    ctx::ctx_conv112_kernel<<<grid, ctx::NT, ctx::SMEM_BYTES, (cudaStream_t)stream>>>(map, d, derr);
-    count_launch();
-    return (int)cudaGetLastError();
-}
-
 int pmctf_ctx_conv112(const void *in_bf16, const void *packed_w, int taps, const float *bias, const float *res, const float *res2,
                       float lrelu_slope, float *out_f32, void *out_bf16, int N, int H, int W, void *stream)
 {
-    return launch_conv112(in_bf16, packed_w, taps, bias, res, res2, lrelu_slope, out_f32, out_bf16, nullptr, nullptr, nullptr, nullptr, N, H, W,
+    return launch_pair_conv<112>(in_bf16, packed_w, taps, bias, res, res2, lrelu_slope, out_f32, out_bf16, nullptr, nullptr, nullptr, nullptr, N, H, W,
                           stream);
 }
 
@@ -785,7 +817,7 @@ int pmctf_ctx_conv112_head(const void *in_bf16, const void *packed_w, int taps, 
                            void *stream)
 {
     if (!head_w) return PMCTF_EINVAL;
-    return launch_conv112(in_bf16, packed_w, taps, bias, res, res2, lrelu_slope, nullptr, nullptr, head_w, head_b, scales, means, N, H, W, stream);
+    return launch_pair_conv<112>(in_bf16, packed_w, taps, bias, res, res2, lrelu_slope, nullptr, nullptr, head_w, head_b, scales, means, N, H, W, stream);
 }
 
 int pmctf_ctx_lower_subband(const float *prev, const float *w, const float *b, float *out, int N, int h, int w_, void *stream)

@@ -28,6 +28,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "pmctf_b200.h"
 #include "pmctf_umma.cuh"
@@ -368,6 +369,19 @@ __global__ void __launch_bounds__(256) pp_to_bf16_kernel(const float *__restrict
 } // namespace pp
 
 int tc_watchdog(volatile int **host, int **dev);   // pmctf_kernels.cu: the per-device watchdog word (mapped pinned memory)
+// pmctf_ctx.cu: the CTA-pair kernel (cta_group::2, TMA tensor loads) instantiated for 64 channels -- same feature-map layouts
+int pair_conv64(const void *in_bf16, const void *packed_w, const float *bias, const float *res, float slope, float *out_f32, void *out_bf16, int N,
+                int H, int W, void *stream);
+int pair_pack64(const float *w, void *packed, void *stream);
+static bool use_pair()
+{   // PMCTF_PP_SINGLE_CTA=1 keeps the round-2a single-CTA kernel (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("PMCTF_PP_SINGLE_CTA");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
 void count_launch();                               // pmctf_kernels.cu
 
 static int launch_conv64(const pp::ConvD &d, cudaStream_t st)
@@ -412,6 +426,7 @@ int pmctf_pp_pack_conv(const float *w, int co, void *packed, void *stream)
 {
     if (!w || !packed || !(co == 64 || (co >= 1 && co <= 16))) return PMCTF_EINVAL;
     if (((uintptr_t)packed & 15) != 0) return PMCTF_EINVAL;
+    if (co == 64 && use_pair()) return pair_pack64(w, packed, stream);
     const int co_pad = co == 64 ? 64 : 16;
     pp::pp_pack_kernel<<<(36 * co_pad * 16 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, co, co_pad, (__nv_bfloat16 *)packed);
     count_launch();
@@ -453,6 +468,7 @@ int pmctf_pp_conv64(const void *in_bf16, const void *packed_w, const float *bias
         return PMCTF_EINVAL;
     }
     if ((((uintptr_t)in_bf16 | (uintptr_t)packed_w | (uintptr_t)out_f32 | (uintptr_t)out_bf16 | (uintptr_t)residual) & 15) != 0) return PMCTF_EINVAL;
+    if (co == 64 && use_pair()) return pair_conv64(in_bf16, packed_w, bias, residual, lrelu_slope, out_f32, out_bf16, N, H, W, stream);
     pp::ConvD d;
     d.in = (const __nv_bfloat16 *)in_bf16; d.wimg = (const uint8_t *)packed_w; d.bias = bias; d.res = residual;
     d.out_f32 = out_f32; d.out_bf16 = (__nv_bfloat16 *)out_bf16; d.x_plane = x_plane; d.y_plane = y_plane;

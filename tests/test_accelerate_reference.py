@@ -37,9 +37,14 @@ def test_accelerate_keeps_state_dict_and_swaps_hot_path(ref_model):
         assert type(coder.wavelet_transform).__module__.startswith("learned_pmctf_b200")
         assert coder.wavelet_transform.lift_v is coder.wavelet_transform.lift_h
         assert type(coder.dequantModule).__module__.startswith("learned_pmctf_b200")      # PostProcess (section 8f row 2) is ours now
-        assert type(coder.context_fusion).__module__.startswith(("pMCTF.", "torch."))      # the entropy-parameter nets are not
+        for lvl in coder.context_fusion:                                                   # the four-step models are ours (section 8f row 1) ...
+            for band in ("lh", "hl", "hh"):
+                assert type(coder.context_fusion[lvl][band]).__module__.startswith("learned_pmctf_b200")
+        assert type(coder.context_fusion["3"]["ll"]).__module__.startswith("pMCTF.")      # ... the LL model and the ConvLSTM context stay
+        assert type(coder.context_prediction).__module__.startswith("pMCTF.")
         assert coder.encode.__func__ is sys.modules["learned_pmctf_b200.models.pWave"].pWaveTransform.encode
-    assert type(m.optic_flow).__module__.startswith("pMCTF.") if hasattr(m, "optic_flow") else True
+    assert type(m.optic_flow).__module__.startswith("learned_pmctf_b200")                 # SpyNet (section 8f row 4) is ours now
+    assert all(type(x).__module__.startswith("pMCTF.") for x in m.mv_encoder)             # the MV codec is not
     assert m.forward_MCTF.__func__ is sys.modules["learned_pmctf_b200.models.video.pMCTF_L"].MCTFMixin.forward_MCTF
     # a strict load of the reference's own checkpoint format still works
     m.load_state_dict({k: v.clone() for k, v in m.state_dict().items()}, strict=True)
