@@ -177,3 +177,84 @@ class GaussianEncoder(AEHelper):
             idx = self.build_indexes(scales).reshape(-1)
         val = self.entropy_coder.decode_stream(idx, *self.get_cdf_info())
         return val.reshape(scales.shape).to(dtype).to(device)
+
+
+# ---- factorised prior of the MV hyper-latent (entropy_models.py:58-199) -------------------------------------------------------
+import torch.nn.functional as F  # noqa: E402
+from torch import nn  # noqa: E402
+
+
+class Bitparm(nn.Module):
+    def __init__(self, channel, final=False):
+        super().__init__()
+        self.final = final
+        self.h = nn.Parameter(torch.nn.init.normal_(torch.empty(channel).view(1, -1, 1, 1), 0, 0.01))
+        self.b = nn.Parameter(torch.nn.init.normal_(torch.empty(channel).view(1, -1, 1, 1), 0, 0.01))
+        self.a = None if final else nn.Parameter(torch.nn.init.normal_(torch.empty(channel).view(1, -1, 1, 1), 0, 0.01))
+
+    def forward(self, x):
+        x = x * F.softplus(self.h) + self.b
+        return x if self.final else x + torch.tanh(x) * torch.tanh(self.a)
+
+
+class BitEstimator(AEHelper, nn.Module):
+    """Per-channel learned CDF (four Bitparm stages + sigmoid); update() tabulates it into rANS tables whose support is where the
+    CDF leaves [1e-4, 1 - 1e-4] (entropy_models.py:123-176)."""
+
+    def __init__(self, channel):
+        super().__init__()
+        self.f1, self.f2, self.f3, self.f4 = Bitparm(channel), Bitparm(channel), Bitparm(channel), Bitparm(channel, True)
+        self.channel = channel
+
+    def forward(self, x):
+        return self.get_cdf(x)
+
+    def get_logits_cdf(self, x):
+        return self.f4(self.f3(self.f2(self.f1(x))))
+
+    def get_cdf(self, x):
+        return torch.sigmoid(self.get_logits_cdf(x))
+
+    def update(self, force=False, entropy_coder=None):
+        if entropy_coder is not None:
+            self.entropy_coder = entropy_coder
+        if not force and self._offset is not None:
+            return
+        with torch.no_grad():
+            device = next(self.parameters()).device
+            zero = torch.zeros(self.channel, device=device)
+            minima, maxima = zero + 50, zero + 50
+            for i in range(50, 1, -1):
+                lo = torch.squeeze(self.forward((zero - i)[None, :, None, None]))
+                minima = torch.where(lo < zero + 0.0001, zero + i, minima)
+            for i in range(50, 1, -1):
+                hi = torch.squeeze(self.forward((zero + i)[None, :, None, None]))
+                maxima = torch.where(hi > zero + 0.9999, zero + i, maxima)
+            minima, maxima = minima.int(), maxima.int()
+            pmf_start = zero - minima
+            pmf_length = maxima + minima + 1
+            max_length = pmf_length.max()
+            samples = torch.arange(max_length, device=device)[None, :] + pmf_start[:, None, None]
+            lower = self.forward(samples - 0.5).squeeze(0)
+            upper = self.forward(samples + 0.5).squeeze(0)
+            pmf = (upper - lower)[:, 0, :]
+            tail_mass = lower[:, 0, :1] + (1.0 - upper[:, 0, -1:])
+            self.set_cdf_info(EntropyCoder.pmf_to_cdf(pmf, tail_mass, pmf_length, max_length), pmf_length + 2, -minima)
+
+    @staticmethod
+    def build_indexes(size):
+        N, Cc, H, W = size
+        return torch.arange(Cc, dtype=torch.int).view(1, -1, 1, 1).repeat(N, 1, H, W)
+
+    @staticmethod
+    def build_indexes_np(size):
+        return BitEstimator.build_indexes(size).cpu().numpy()
+
+    def encode(self, x):
+        idx = self.build_indexes(x.size())
+        return self.entropy_coder.encode_with_indexes(x.reshape(-1), idx.reshape(-1), *self.get_cdf_info())
+
+    def decode_stream(self, size, dtype, device):
+        idx = self.build_indexes((1, self.channel, size[0], size[1]))
+        val = self.entropy_coder.decode_stream(idx.reshape(-1), *self.get_cdf_info())
+        return val.reshape(idx.shape).to(dtype).to(device)

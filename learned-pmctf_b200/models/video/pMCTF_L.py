@@ -62,16 +62,24 @@ class MCTFMixin:
         :333-336 -- note that it halves and 2x2-averages a given field exactly as below).  The keys that only the MV
         codec / entropy model can fill are None / NaN (see pWave.forward_one_channel)."""
         if mv_hat is None:
-            raise NotImplementedError("motion estimation + MV coding (SpyNet, SURVEY.md section 8f row 4) are not part of the hot path: "
-                                      "pass mv_hat= (the reference's forward_one_stage accepts it, pMCTF_L.py:333-336)")
-        bpp_mv_y, bpp_mv_z = None, None
-        ref_mv = {"mv_feature": None, "mv_y_hat": None}
-        mv_hat = bilineardownsacling(mv_hat) / 2                      # pMCTF_L.py:336
+            if not hasattr(self, "mv_encoder"):
+                raise NotImplementedError("this model was built without the motion path (pMCTF(motion=True, entropy_model=True)): "
+                                          "pass mv_hat= (the reference's forward_one_stage accepts it, pMCTF_L.py:333-336)")
+            mv_hat, ref_mv, bpp_mv_y, bpp_mv_z = self.compute_and_code_motion(ref_frame, cur_frame, q_index, dpb, stage_idx=stage_idx,
+                                                                              me_downsample=me_downsample)
+        else:
+            bpp_mv_y, bpp_mv_z = None, None
+            ref_mv = {"mv_feature": None, "mv_y_hat": None}
+            mv_hat = bilineardownsacling(mv_hat) / 2                      # pMCTF_L.py:336
         L_t, H_t, pred_frame, inv_pred_frame = self.forward_MCTF(ref_frame, cur_frame, mv_hat, stage_idx)
         qp_scale = self.get_curr_q(self.hp_q_scale[stage_idx], q_index) if self.quant_stage else None
         res_H = self.hp_coder.forward(H_t, q_index, qp_scale=qp_scale)
-        ret = {"bpp_mv_y": bpp_mv_y, "bpp_mv_z": bpp_mv_z, "bpp_me": None, "me_mse": self.mse(pred_frame, cur_frame),
-               "bpp": res_H["bpp_total"], "bpp_H": res_H["bpp_total"], "bit_H": res_H["bits_total"], "bit_ME": None,
+        coded_mv = bpp_mv_z is not None
+        ret = {"bpp_mv_y": bpp_mv_y, "bpp_mv_z": bpp_mv_z, "bpp_me": bpp_mv_z + bpp_mv_y if coded_mv else None,
+               "me_mse": self.mse(pred_frame, cur_frame),
+               "bpp": res_H["bpp_total"] + bpp_mv_z + bpp_mv_y if coded_mv else res_H["bpp_total"], "bpp_H": res_H["bpp_total"],
+               "bit_H": res_H["bits_total"],
+               "bit_ME": (bpp_mv_y + bpp_mv_z) * (ref_frame.size(2) * ref_frame.size(3)) if coded_mv else None,
                "mse_H": res_H["mse"], "mv_hat": mv_hat, "dpb": {"mv_feature": ref_mv["mv_feature"], "ref_mv_y": ref_mv["mv_y_hat"]},
                "H_t": res_H["x_hat"]}
         if code_lt:
@@ -83,6 +91,149 @@ class MCTFMixin:
             ret["L_t"] = L_t
         ret["bit"] = ret["bpp"] * (ref_frame.size(2) * ref_frame.size(3))
         return ret
+
+    # ---- motion estimation + MV coding (pMCTF_L.py:211-292, 397-524): host-side sequencing of SpyNet (tensor cores) and the MV codec ----
+    @staticmethod
+    def _rounded_q(q):
+        """stream_helper.get_rounded_q (:35-39): the step that travels implicitly with q_index, rounded to 1/100"""
+        import numpy as np
+        q = np.clip(q, 0.01, 655.0)
+        idx = int(np.round(q * 100))
+        return idx / 100, idx
+
+    def get_mv_y_q(self, q_index, stage_idx=0, inference=False):
+        enc = self.get_curr_q(self.mv_y_q_scale_enc[stage_idx], q_index)
+        dec = self.get_curr_q(self.mv_y_q_scale_dec[stage_idx], q_index)
+        if inference:
+            enc, dec = self._rounded_q(enc.cpu())[0], self._rounded_q(dec.cpu())[0]
+        return enc, dec
+
+    def mv_prior_param_decoder(self, mv_z_hat, dpb, me_num):
+        params = self.mv_hyper_prior_decoder[me_num](mv_z_hat)
+        if dpb["ref_mv_y"] is None:
+            params = self.mv_y_prior_fusion_adaptor_0[me_num](params)
+        else:
+            params = self.mv_y_prior_fusion_adaptor_1[me_num](torch.cat((params, dpb["ref_mv_y"]), dim=1))
+        return self.mv_y_prior_fusion[me_num](params)
+
+    def _me_inputs(self, ref_frame, cur_frame, me_downsample, first_only):
+        from ...layers.video.video_net import bilinearupsacling  # noqa: F401
+        cur = cur_frame[0] if first_only else cur_frame
+        ref = ref_frame[0] if first_only else ref_frame
+        mv_cur, mv_ref = cur.tile((1, 3, 1, 1)) / self.dynamic_range, ref.tile((1, 3, 1, 1)) / self.dynamic_range
+        if me_downsample > 1:
+            import torch.nn.functional as F
+            size = (mv_cur.size(2) // me_downsample, mv_cur.size(3) // me_downsample)
+            mv_cur = F.interpolate(mv_cur, size, mode="bilinear", align_corners=False)
+            mv_ref = F.interpolate(mv_ref, size, mode="bilinear", align_corners=False)
+        return mv_cur, mv_ref
+
+    def _adaptors(self, me_num):
+        return (self.mv_y_spatial_prior_adaptor_1[me_num], self.mv_y_spatial_prior_adaptor_2[me_num],
+                self.mv_y_spatial_prior_adaptor_3[me_num], self.mv_y_spatial_prior[me_num])
+
+    def compute_and_code_motion(self, ref_frame, cur_frame, q_index, dpb, stage_idx=0, me_downsample=1):
+        """Flow by SpyNet on the luma planes, analysis into the 1/16-resolution latent, hyper-prior, four-part prior coding (rate
+        estimate) and synthesis of the DECODED motion field the lifting uses (pMCTF_L.py:243-292)."""
+        from ...layers.video.video_net import bilinearupsacling
+        me_num = min(self.num_me_stages - 1, stage_idx)
+        q_enc, q_dec = self.get_mv_y_q(q_index, me_num)
+        first_only = not (self.training and cur_frame.size(0) != 3)
+        mv_cur, mv_ref = self._me_inputs(ref_frame, cur_frame, me_downsample, first_only)
+        est_mv = self.optic_flow(mv_cur, mv_ref)
+        mv_y = self.mv_encoder[me_num](est_mv, dpb["mv_feature"], q_enc)
+        mv_z = self.mv_hyper_prior_encoder[me_num](mv_y)
+        mv_z_hat = self.mv_coder.quant(mv_z)
+        params = self.mv_prior_param_decoder(mv_z_hat, dpb, me_num)
+        y_res, y_q, y_hat, scales_hat = self.mv_coder.forward_four_part_prior(mv_y, params, *self._adaptors(me_num))
+        mv_hat, mv_feature = self.mv_decoder[me_num](y_hat, q_dec)
+        if me_downsample > 1:
+            mv_hat = bilinearupsacling(mv_hat, factor=me_downsample) * me_downsample
+        y_for_bit, z_for_bit = (self.em.add_noise(y_res), self.em.add_noise(mv_z)) if self.training else (y_q, mv_z_hat)
+        bits_y = self.em.get_y_laplace_bits(y_for_bit, scales_hat)
+        bits_z = self.em.get_z_bits(z_for_bit, self.mv_bit_est[me_num])
+        px = ref_frame.size(2) * ref_frame.size(3)
+        bpp_y, bpp_z = torch.sum(bits_y, dim=(1, 2, 3)) / px, torch.sum(bits_z, dim=(1, 2, 3)) / px
+        red = torch.mean if self.training else torch.sum
+        return mv_hat, {"mv_feature": mv_feature, "mv_y_hat": y_hat}, red(bpp_y), red(bpp_z)
+
+    @torch.no_grad()
+    def compress_mv(self, ref_frame, cur_frame, dpb, stage_idx=0, q_index=0, me_downsample=1):
+        """The motion bitstream of one frame pair (pMCTF_L.py:448-497): hyper-latent through the factorised prior, the four
+        masked planes of the latent through the Laplace tables."""
+        from ...layers.video.video_net import bilinearupsacling
+        me_num = min(self.num_me_stages - 1, stage_idx)
+        q_enc, q_dec = self.get_mv_y_q(q_index, me_num, inference=True)
+        mv_cur, mv_ref = self._me_inputs(ref_frame, cur_frame, me_downsample, first_only=False)
+        est_mv = self.optic_flow(mv_cur, mv_ref)
+        mv_y = self.mv_encoder[me_num](est_mv, dpb["mv_feature"], q_enc)
+        mv_z_hat = torch.round(self.mv_hyper_prior_encoder[me_num](mv_y))
+        params = self.mv_prior_param_decoder(mv_z_hat, dpb, me_num)
+        out = self.mv_coder.compress_four_part_prior(mv_y, params, *self._adaptors(me_num))
+        mv_hat, mv_feature = self.mv_decoder[me_num](out[8], q_dec)
+        if me_downsample > 1:
+            mv_hat = bilinearupsacling(mv_hat, factor=me_downsample) * me_downsample
+        self.em.entropy_coder.reset()
+        self.mv_bit_est[me_num].encode(mv_z_hat)
+        for k in range(4):
+            self.em.gaussian_encoder.encode(out[k], out[4 + k])
+        self.em.entropy_coder.flush()
+        return {"bit_stream": self.em.entropy_coder.get_encoded_stream(), "mv_hat": mv_hat, "mv_feature": mv_feature, "mv_y_hat": out[8]}
+
+    @torch.no_grad()
+    def decompress_mv(self, string, dtype, height, width, dpb, stage_idx=0, q_index=0, me_downsample=1):
+        """pMCTF_L.py:499-524"""
+        from ...layers.video.video_net import bilinearupsacling
+        me_num = min(self.num_me_stages - 1, stage_idx)
+        _, q_dec = self.get_mv_y_q(q_index, me_num, inference=True)
+        self.em.entropy_coder.set_stream(string)
+        device = next(self.parameters()).device
+        zh, zw = int((height + 63) // 64 * 64 / 64 + 0.5), int((width + 63) // 64 * 64 / 64 + 0.5)    # stream_helper.get_downsampled_shape
+        mv_z_hat = self.mv_bit_est[me_num].decode_stream((zh, zw), dtype, device).to(device)
+        params = self.mv_prior_param_decoder(mv_z_hat, dpb, me_num)
+        y_hat = self.mv_coder.decompress_four_part_prior(params, *self._adaptors(me_num), gaussian_encoder=self.em.gaussian_encoder)
+        mv_hat, mv_feature = self.mv_decoder[me_num](y_hat, q_dec)
+        if me_downsample > 1:
+            mv_hat = bilinearupsacling(mv_hat, factor=me_downsample) * me_downsample
+        return {"mv_hat": mv_hat, "mv_feature": mv_feature, "mv_y_hat": y_hat}
+
+    @torch.no_grad()
+    def compress_one_stage(self, ref_frame, cur_frame, code_lt, mv_hat, ischroma, sideinfo=None, file_name=None, stage_idx=0, q_index=0,
+                           skip_decoding=False):
+        """pMCTF_L.py:397-420: lifting with the decoded field, then the H (and, at the last stage, L) frame through pWave.compress"""
+        import os.path as osp
+        if ischroma:
+            mv_hat = bilineardownsacling(mv_hat) / 2
+        L_t, H_t, _, _ = self.forward_MCTF(ref_frame, cur_frame, mv_hat, stage_idx)
+        H_hat = self.hp_coder.compress(H_t, sideinfo, file_name, q_index=q_index, skip_decoding=skip_decoding,
+                                       qp_scale=self.hp_qp_scale(stage_idx, q_index))
+        L_hat = None
+        if code_lt:
+            name_l = file_name.replace(osp.basename(file_name), "0_C_main.bin" if ischroma else "0_main.bin")
+            L_hat = self.lp_coder.compress(L_t, sideinfo, name_l, q_index=q_index, skip_decoding=skip_decoding)
+        return {"L_t": L_t, "H_t": H_t, "H_t_hat": H_hat, "L_t_hat": L_hat}
+
+    @torch.no_grad()
+    def decompress_one_stage(self, file_name, code_lt, ischroma, psize=128, q_index=0, stage_idx=0):
+        """pMCTF_L.py:422-439"""
+        import os.path as osp
+        pad = psize // 2 if ischroma else psize
+        H_t = self.hp_coder.decompress(file_name, padding=pad, q_index=q_index, qp_scale=self.hp_qp_scale(stage_idx, q_index))
+        L_t = None
+        if code_lt:
+            name_l = file_name.replace(osp.basename(file_name), "0_C_main.bin" if ischroma else "0_main.bin")
+            L_t = self.lp_coder.decompress(name_l, padding=pad, q_index=q_index)
+        return {"L_t": L_t, "H_t": H_t}
+
+    def update(self, force=False):
+        """entropy-coder tables of the whole model (pMCTF_L.py:441-446)"""
+        if hasattr(self, "em"):
+            self.em.update(force)
+            for est in self.mv_bit_est:
+                est.update(force, entropy_coder=self.em.entropy_coder)
+        for coder in (self.lp_coder, self.hp_coder):
+            if coder.has_entropy_model():
+                coder.update(force)
 
     def forward_MCTF(self, ref_frame, cur_frame, mv_hat, stage_idx=0, mv_down=False, want_pred=True, **out):
         """H = cur - P(warp(ref, mv)); L = ref + U(warp(H, -mv)) -> (L_t, H_t, pred, inv)  (pMCTF_L.py:297-312).
@@ -106,13 +257,43 @@ class MCTFMixin:
 
 class pMCTF(MCTFMixin, nn.Module):
     def __init__(self, bitdepth=8, decomp_levels=4, lossy=True, two_stage_me=True, num_me_stages=2, quant_stage=True,
-                 postprocess=False, entropy_model=False, **kwargs):
+                 postprocess=False, entropy_model=False, motion=False, **kwargs):
+        """motion=True + entropy_model=True builds the reference's WHOLE module tree (pMCTF_L.py:36-112): strict state_dict parity
+        with its checkpoints (3 224 entries for num_me_stages = 4), forward_one_stage without a given motion field, compress_mv /
+        decompress_mv, compress_one_stage / decompress_one_stage, update()."""
         super().__init__()
         self.bitdepth = bitdepth
         self.dynamic_range = 2 ** bitdepth - 1
         self.lossy = lossy
         self.lp_coder = pWave(bitdepth, decomp_levels, lossy, postprocess=postprocess, entropy_model=entropy_model)
         self.hp_coder = pWave(bitdepth, decomp_levels, lossy, postprocess=postprocess, entropy_model=entropy_model)
+        if motion:
+            from ...entropy_models.entropy_models import BitEstimator
+            from ...entropy_models.gaussian_model import CompressionModel
+            from ...layers.video.four_part_prior import MVCoderQuad
+            from ...layers.video.layers import DepthConvBlock
+            from ...layers.video.mv_codec import MvDec, MvEnc, get_hyper_dec_model, get_hyper_enc_model
+            from ...layers.video.video_net import ME_Spynet
+            self.channel_mv = mv = 64
+            self.channel_N, self.channel_M = 64, 32
+            n = num_me_stages
+            self.optic_flow = ME_Spynet(L=6)
+            self.mv_encoder = nn.ModuleList([MvEnc(2, mv) for _ in range(n)])
+            self.mv_decoder = nn.ModuleList([MvDec(2, mv) for _ in range(n)])
+            self.mv_hyper_prior_encoder = nn.ModuleList([get_hyper_enc_model(self.channel_N, mv) for _ in range(n)])
+            self.mv_hyper_prior_decoder = nn.ModuleList([get_hyper_dec_model(self.channel_N, mv) for _ in range(n)])
+            self.mv_y_prior_fusion_adaptor_0 = nn.ModuleList([DepthConvBlock(mv, mv * 2) for _ in range(n)])
+            self.mv_y_prior_fusion_adaptor_1 = nn.ModuleList([DepthConvBlock(mv * 2, mv * 2) for _ in range(n)])
+            self.mv_y_prior_fusion = nn.ModuleList([nn.Sequential(DepthConvBlock(mv * 2, mv * 3), DepthConvBlock(mv * 3, mv * 3)) for _ in range(n)])
+            self.mv_y_spatial_prior = nn.ModuleList([nn.Sequential(DepthConvBlock(mv * 3, mv * 3), DepthConvBlock(mv * 3, mv * 3),
+                                                                   DepthConvBlock(mv * 3, mv * 2)) for _ in range(n)])
+            for k in (1, 2, 3):
+                setattr(self, f"mv_y_spatial_prior_adaptor_{k}", nn.ModuleList([nn.Conv2d(mv * 4, mv * 3, 1) for _ in range(n)]))
+            self.mv_y_q_scale_enc = nn.ParameterList([nn.Parameter(torch.ones((2, 1, 1, 1))) for _ in range(n)])
+            self.mv_y_q_scale_dec = nn.ParameterList([nn.Parameter(torch.ones((2, 1, 1, 1))) for _ in range(n)])
+            self.mv_bit_est = nn.ModuleList([BitEstimator(mv) for _ in range(n)])
+            self.em = CompressionModel(y_distribution="laplace")
+            self.mv_coder = MVCoderQuad(enc_dec_quant=True)
         self.temporal_filtering = nn.ModuleList([TemporalLifting(lossy=lossy) for _ in range(num_me_stages)])
         self.quant_stage = quant_stage
         if quant_stage:
