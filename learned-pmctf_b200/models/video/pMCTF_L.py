@@ -235,6 +235,103 @@ class MCTFMixin:
             if coder.has_entropy_model():
                 coder.update(force)
 
+    def encode_one_stage(self, ref_frame, cur_frame, code_lt, dpb, output_path=None, pic_width=None, pic_height=None, psize=128,
+                         skip_decoding=False, stage_idx=0, q_index=0, me_downsample=1):
+        """One frame pair, luma then chroma with the luma's decoded field (pMCTF_L.py:525-637).  output_path None: the forward
+        (rate-estimate) path -- the reference's own version of this branch reads keys forward_one_stage does not return
+        (`result["mv_feature"]`) and cannot run; here it takes them from `result["dpb"]`.  With an output path: the
+        motion stream (`*_mv.bin`, stream_helper.encode_p), the luma and chroma frame streams, and -- unless skip_decoding -- the
+        decoder's reconstruction read back from those files."""
+        import os
+        import struct
+        import time
+        ref_y, ref_c = ref_frame
+        cur_y, cur_c = cur_frame
+        if output_path is None:
+            r = self.forward_one_stage(ref_y, cur_y, q_index, code_lt, dpb, stage_idx=stage_idx, me_downsample=me_downsample)
+            rc = self.forward_one_stage(ref_c, cur_c, q_index, code_lt, dpb, mv_hat=r["mv_hat"], stage_idx=stage_idx, me_downsample=me_downsample)
+            return {"L_t": r["L_t"], "H_t": r["H_t"], "L_tc": rc["L_t"], "H_tc": rc["H_t"],
+                    "bit_L": r["bit_L"] + rc["bit_L"] if code_lt else None, "bit_H": r["bit_H"] + rc["bit_H"],
+                    "bit_Lc": rc["bit_L"] if code_lt else None, "bit_Hc": rc["bit_H"], "bit_ME": r["bit_ME"], "mv_hat": r["mv_hat"],
+                    "dpb": r["dpb"], "decoding_time": 0, "encoding_time": 0}
+        t0 = time.time()
+        mv_out = output_path.replace(".bin", "_mv.bin")
+        enc_mv = self.compress_mv(ref_y, cur_y, dpb, stage_idx=stage_idx, q_index=q_index, me_downsample=me_downsample)
+        with open(mv_out, "wb") as f:                       # stream_helper.encode_p (:181-186): q index (unused, 0), length, stream
+            f.write(struct.pack(">H", 0) + struct.pack(">I", len(enc_mv["bit_stream"])) + enc_mv["bit_stream"])
+        mv_hat, mv_feature, mv_y_hat = enc_mv["mv_hat"], enc_mv["mv_feature"], enc_mv["mv_y_hat"]
+        out_y = self.compress_one_stage(ref_y, cur_y, code_lt, mv_hat, ischroma=False, sideinfo=[1, 1, pic_height, pic_width],
+                                        stage_idx=stage_idx, file_name=output_path, q_index=q_index, skip_decoding=skip_decoding)
+        name_c = output_path.replace(".bin", "_C_main.bin")
+        out_c = self.compress_one_stage(ref_c.to(ref_y.device), cur_c.to(ref_y.device), code_lt, mv_hat, ischroma=True,
+                                        sideinfo=[1, 2, pic_height // 2, pic_width // 2], file_name=name_c, stage_idx=stage_idx,
+                                        q_index=q_index, skip_decoding=skip_decoding)
+        encoding_time = time.time() - t0
+        size = lambda n: os.path.getsize(n) * 8.0  # noqa: E731
+        base = os.path.basename(output_path)
+        bits_H, bits_Hc, bits_me = size(output_path), size(name_c), size(mv_out)
+        bits_L = size(output_path.replace(base, "0_main.bin")) if code_lt else None
+        bits_Lc = size(output_path.replace(base, "0_C_main.bin")) if code_lt else None
+        decoding_time = 0
+        if not skip_decoding:
+            t0 = time.time()
+            blob = open(mv_out, "rb").read()
+            (n,) = struct.unpack(">I", blob[2:6])
+            dec_mv = self.decompress_mv(blob[6:6 + n], ref_y.dtype, ref_y.size(2), ref_y.size(3), dpb, stage_idx=stage_idx, q_index=q_index)
+            mv_hat, mv_feature = dec_mv["mv_hat"], dec_mv["mv_feature"]
+            dy = self.decompress_one_stage(output_path, code_lt, ischroma=False, psize=psize, q_index=q_index, stage_idx=stage_idx)
+            dc = self.decompress_one_stage(name_c, code_lt, ischroma=True, psize=psize, q_index=q_index, stage_idx=stage_idx)
+            decoding_time = time.time() - t0
+            L_t, H_t = (dy["L_t"]["x_hat"] if code_lt else out_y["L_t"]), dy["H_t"]["x_hat"]
+            L_tc, H_tc = (dc["L_t"]["x_hat"] if code_lt else out_c["L_t"]), dc["H_t"]["x_hat"]
+        else:
+            L_t, H_t = (out_y["L_t_hat"] if code_lt else out_y["L_t"]), out_y["H_t_hat"]
+            L_tc, H_tc = (out_c["L_t_hat"] if code_lt else out_c["L_t"]), out_c["H_t_hat"]
+        return {"L_t": L_t, "H_t": H_t, "L_tc": L_tc, "H_tc": H_tc, "bit_H": bits_H + bits_Hc, "bit_L": bits_L + bits_Lc if code_lt else None,
+                "bit_Lc": bits_Lc, "bit_Hc": bits_Hc, "bit_ME": bits_me, "mv_hat": mv_hat, "dpb": {"mv_feature": mv_feature, "ref_mv_y": mv_y_hat},
+                "decoding_time": decoding_time, "encoding_time": encoding_time}
+
+    @torch.no_grad()
+    def code_gop_forward(self, frames_y, frames_c, q_index=12, bin_folder=None, skip_decoding=True):
+        """The reference's GOP loop (test_pMCTF_flex.py:131-291) on this model: dyadic temporal analysis with motion estimated and
+        coded pair by pair (encode_one_stage), then the temporal synthesis.  frames_y: list of G padded luma planes [1,1,H,W],
+        frames_c: list of G chroma pairs [2,1,H/2,W/2].  bin_folder None: the forward (rate-estimate) path.  Returns the
+        reconstructed frames and the per-frame bit counts."""
+        import os
+        G = len(frames_y)
+        stages = G.bit_length() - 1
+        coded = [[frames_y[i], frames_c[i], None] for i in range(G)]
+        bits = [0.0] * G
+        n = G
+        for stage in range(stages):
+            n //= 2
+            dpb = {"mv_feature": None, "ref_mv_y": None}
+            step = 1 << stage
+            for grp in range(n):
+                i = grp * 2 * step
+                me_num = min(self.num_me_stages - 1, stage)
+                code_lt = stage + 1 == stages
+                path = os.path.join(bin_folder, f"{i + step}.bin") if bin_folder else None
+                r = self.encode_one_stage([coded[i][0], coded[i][1]], [coded[i + step][0], coded[i + step][1]], code_lt, dpb, output_path=path,
+                                          pic_height=frames_y[0].size(2), pic_width=frames_y[0].size(3), skip_decoding=skip_decoding,
+                                          stage_idx=me_num, q_index=q_index)
+                coded[i] = [r["L_t"], r["L_tc"], None]
+                coded[i + step] = [r["H_t"], r["H_tc"], r["mv_hat"]]
+                dpb = r["dpb"]
+                bits[i + step] = float(r["bit_H"]) + float(r["bit_ME"])
+                if code_lt:
+                    bits[i] = float(r["bit_L"])
+        for stage in reversed(range(stages)):
+            step = 1 << stage
+            for grp in reversed(range(G // (2 * step))):
+                i = grp * 2 * step
+                me_num = min(self.num_me_stages - 1, stage)
+                mv = coded[i + step][2]
+                ry, cy = self.inverse_MCTF(coded[i][0], coded[i + step][0], mv, stage_idx=me_num)
+                rc, cc = self.inverse_MCTF(coded[i][1], coded[i + step][1], mv, stage_idx=me_num, downscale=True)
+                coded[i], coded[i + step] = [ry, rc, None], [cy, cc, None]
+        return [c[0] for c in coded], [c[1] for c in coded], bits
+
     def forward_MCTF(self, ref_frame, cur_frame, mv_hat, stage_idx=0, mv_down=False, want_pred=True, **out):
         """H = cur - P(warp(ref, mv)); L = ref + U(warp(H, -mv)) -> (L_t, H_t, pred, inv)  (pMCTF_L.py:297-312).
         Two launches: each fuses warp + PredictUpdate CNN + lifting arithmetic.  `mv_down=True`

@@ -125,3 +125,38 @@ def test_full_stage_on_gpu(tmp_path, conv_mode):
     r, cc = m.inverse_MCTF(dec["L_t"]["x_hat"], dec["H_t"]["x_hat"], c["mv_hat"], stage_idx=0)
     assert torch.isfinite(r).all() and float(((cc - cur) ** 2).mean()) < 5000.0     # random-weight PostProcess: a sanity bound, not a quality claim
     assert P.ops.tc_error_flag() == 0
+
+
+@pytest.mark.gpu
+def test_gop4_forward_and_bitstream_paths(tmp_path, conv_mode):
+    """The reference's GOP loop on the full model at a small size: the forward (rate-estimate) path and the bitstream path with
+    the decoder reading the files back reconstruct the same frames where the same symbols are coded (the LL band's
+    autoregressive path and the skip_decoding shortcut are both exercised)."""
+    if conv_mode != "tensor":
+        pytest.skip("independent of the lifting arithmetic")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_pwave_coder import _randomise
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    m = P.pMCTF(num_me_stages=4, entropy_model=True, motion=True)
+    _randomise(m.lp_coder, 1), _randomise(m.hp_coder, 2)
+    _perturb(m)
+    m = m.to(dev).eval()
+    m.update(force=True)
+    g = np.random.default_rng(6)
+    base = g.random((1, 1, 136, 272)) * 255          # 128 x 256: multiples of the 128-pixel padding unit the decoder assumes (psize)
+    base = sum(np.roll(base, (dy, dx), (2, 3)) for dy in range(-2, 3) for dx in range(-2, 3)) / 25.0
+    ys, cs = [], []
+    for t in range(4):
+        f = np.round(base[:, :, 4:132, 4 + 2 * t:260 + 2 * t]).astype(np.float32)
+        ys.append(torch.from_numpy(f).to(dev))
+        cs.append(torch.from_numpy(np.stack([f[0, :, ::2, ::2], 255 - f[0, :, ::2, ::2]])).to(dev))
+    ry, rc, bits = m.code_gop_forward(ys, cs, q_index=12)
+    assert len(ry) == 4 and all(torch.isfinite(t).all() for t in ry + rc) and all(b > 0 for b in bits)
+    folder = str(tmp_path)
+    ry2, rc2, bits2 = m.code_gop_forward(ys, cs, q_index=12, bin_folder=folder, skip_decoding=False)
+    assert all(torch.isfinite(t).all() for t in ry2 + rc2)
+    assert os.path.exists(os.path.join(folder, "1.bin")) and os.path.exists(os.path.join(folder, "1_mv.bin")) and os.path.exists(os.path.join(folder, "0_main.bin"))
+    # the estimate and the real stream sizes agree to within the coder's overheads
+    assert 0.6 * sum(bits) < sum(bits2) < 1.6 * sum(bits) + 4000, (sum(bits), sum(bits2))
+    assert P.ops.tc_error_flag() == 0
