@@ -442,6 +442,53 @@ def run_spynet(pkg, dev, pk):
             "torch_gpu_baseline": base}
 
 
+def run_full_codec(pkg, dev):
+    """SURVEY.md section 8d throughput (2): the reference's whole GOP loop (test_pMCTF_flex.py:131-291, forward / rate-estimate path) on
+    the full model -- per frame pair SpyNet + MV codec + temporal lifting, then both pWave++ coders with their entropy-parameter
+    networks, long-term context and PostProcess on the luma and the two chroma planes, then the temporal synthesis -- for ONE
+    1080p GOP-16.  Everything the reference runs per GOP is inside the timed region.  Secondary block (the headline metric is the
+    lifting path alone, as north_star defines it)."""
+    import torch
+    m = pkg.pMCTF(num_me_stages=4, entropy_model=True, motion=True)
+    g = torch.Generator().manual_seed(17)
+    with torch.no_grad():
+        for k, p in m.named_parameters():       # non-degenerate random weights (the 0.02 init lets every activation vanish)
+            if k.endswith((".QP", ".QP_ll")):
+                p.copy_(torch.tensor([1 / 32, 1 / 2]).view(2, 1, 1, 1))
+            elif "q_scale" in k:
+                p.copy_(torch.tensor([0.8, 1.3]).view(2, 1, 1, 1))
+            elif p.dim() == 4 and "dequantModule" in k:
+                p.copy_((1e-4 if p.shape[0] == 1 else 0.04) * torch.randn(p.shape, generator=g))
+            elif p.dim() == 4 and p.shape[1] >= 64:
+                p.copy_(0.022 * torch.randn(p.shape, generator=g))
+            elif p.dim() == 4 and "temporal_filtering" not in k and "wavelet_transform" not in k:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+    m = m.to(dev).eval()
+    gd = torch.Generator(device=dev).manual_seed(5)
+    base = torch.nn.functional.avg_pool2d(torch.rand((1, 1, 1156 + 64, 1924 + 64), device=dev, generator=gd), 5, 1) * 255
+    ys, cs = [], []
+    for t in range(GOP):
+        y = base[:, :, t:t + 1152, 2 * t:2 * t + 1920].round().contiguous()
+        c = torch.nn.functional.avg_pool2d(y, 2)
+        ys.append(y)
+        cs.append(torch.cat([c, 255.0 - c], dim=0).round().contiguous())
+    with torch.no_grad():
+        m.code_gop_forward(ys[:4], cs[:4], q_index=12)     # warm-up: packs every weight image, fills the workspaces
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ry, rc, bits = m.code_gop_forward(ys, cs, q_index=12)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    pkg.ops.check_tc_error(dev, "full codec block")
+    ms = e0.elapsed_time(e1)
+    return {"what": "pMCTF(motion=True, entropy_model=True).code_gop_forward: the reference's GOP loop (encode_one_stage per pair: SpyNet, MV codec, "
+                    "forward_MCTF, hp / lp pWave.forward with the four-step entropy-parameter networks, ConvLSTM context, LL model, PostProcess, for "
+                    "luma and chroma; inverse_MCTF) on one 1080p 4:2:0 GOP-16, random weights, rate-estimate path",
+            "ms_per_gop": ms, "frames_per_s": GOP / (ms * 1e-3), "bits_per_frame_estimate": sum(bits) / GOP,
+            "on_our_kernels": "lifting, SpyNet, four-step networks, PostProcess; stock torch ops: MV codec, ConvLSTM context, LL model, rate estimate"}
+
+
 def run_uvg(args, pkg, G, par, model, dev, rank, world):
     """BASELINE configs[3] as written: 7 synthetic 1080p sequences x 96 frames (6 GOP-16s each) x the q_index list of
     test_pMCTF_flex.py:436-443, FLATTENED into 252 work items (q_index, sequence, gop), sharded round-robin over the ranks
@@ -655,6 +702,7 @@ def main():
     ap.add_argument("--uvg-sequences", type=int, default=7)
     ap.add_argument("--no-int8-peak", action="store_true", help="skip measuring the int8 dense peak of this GPU")
     ap.add_argument("--no-postprocess", action="store_true", help="skip the PostProcess block (section 8f row 2, secondary)")
+    ap.add_argument("--no-full-codec", action="store_true", help="skip the whole-codec GOP block (section 8d throughput 2, secondary)")
     ap.add_argument("--no-spynet", action="store_true", help="skip the SpyNet block (section 8f row 4, secondary)")
     ap.add_argument("--no-train-block", action="store_true", help="skip the configs[4] training-step block (child process, secondary)")
     ap.add_argument("--no-context-fusion", action="store_true", help="skip the entropy-parameter network block (section 8f row 1, secondary)")
@@ -826,6 +874,12 @@ def main():
             spyb = run_spynet(pkg, dev, pk)
         except Exception as ex:
             spyb = {"error": str(ex)[:200]}
+    fullb = None
+    if world == 1 and not args.no_full_codec and args.frames == FRAMES:
+        try:
+            fullb = run_full_codec(pkg, dev)
+        except Exception as ex:
+            fullb = {"error": str(ex)[:200]}
     ctxb = None
     if world == 1 and not args.no_context_fusion and args.frames == FRAMES:
         try:
@@ -907,7 +961,7 @@ def main():
                        "streams": "1" if args.single_stream else "2 per GPU: luma chain | chroma chain (independent on the path)",
                        "parallelism": f"gop-sharded dp{world}, all_gather of per-frame statistics per step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "torch_gpu_baseline": torch_gpu, "uvg": uvg, "postprocess": ppb, "context_fusion": ctxb, "spynet": spyb, "train": trainb,
+            "torch_gpu_baseline": torch_gpu, "uvg": uvg, "postprocess": ppb, "context_fusion": ctxb, "spynet": spyb, "full_codec": fullb, "train": trainb,
             "quality": {"mean_psnr_yuv_db": float(psnr[torch.isfinite(psnr)].mean()), "frames": int(psnr.numel())}}
     emit(line)
     if world > 1:
