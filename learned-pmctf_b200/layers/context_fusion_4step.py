@@ -12,8 +12,10 @@ and the masked quantiser are small CUDA-core kernels.  CUDA tensors only; under 
 formula from torch ops (training of the entropy model is not part of the hot path)."""
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -82,6 +84,31 @@ class _Features:
         return self.f32.permute(0, 1, 4, 2, 3).reshape(self.N, NUM_FEATURES, self.H, self.W)
 
 
+# The three full feature maps + the bf16-only intermediate of one call, shared by ALL four-step modules of the process (the 24 modules
+# of a codec run one after the other on one stream, so stream-ordered reuse is safe) and kept per shape, least recently used shapes
+# dropped beyond a byte budget (PMCTF_CTX_WORKSPACE_GB, default 24).
+_WS_CACHE = collections.OrderedDict()
+
+
+def _shared_workspace(N, H, W, dev):
+    key = (N, H, W, str(dev), torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WS_CACHE.get(key)
+    if ws is not None:
+        _WS_CACHE.move_to_end(key)
+        return ws
+    need = N * H * W * NUM_FEATURES * (3 * 6 + 2)
+    budget = float(os.environ.get("PMCTF_CTX_WORKSPACE_GB", "24")) * 2 ** 30
+    while _WS_CACHE and sum(v[4] for v in _WS_CACHE.values()) + need > budget:
+        _WS_CACHE.popitem(last=False)
+    ws = (_Features(N, H, W, dev), _Features(N, H, W, dev), _Features(N, H, W, dev), _Features(N, H, W, dev, f32=False), need)
+    _WS_CACHE[key] = ws
+    return ws
+
+
+def release_workspaces():
+    _WS_CACHE.clear()
+
+
 class ContextFusionFourStep(nn.Module):
     def __init__(self, in_channels=1, ctx_channels=1, num_features=NUM_FEATURES, num_parameters=2, ctx=True, lossy=True,
                  lower_subband=True):
@@ -111,7 +138,6 @@ class ContextFusionFourStep(nn.Module):
     def __getstate__(self):
         st = dict(self.__dict__)
         st["_key"], st["_packed"] = None, None
-        st.pop("_ws", None)
         st.pop("_pack_hot", None)
         return st
 
@@ -193,7 +219,7 @@ class ContextFusionFourStep(nn.Module):
                         c.bias.detach().data_ptr(), x1.data_ptr(), N, H // 2, W // 2)
         elif self.ctx_channels == 2:
             raise RuntimeError("this module expects prev_subband (ctx_channels = 2)")
-        a, b, _, t = self._workspace(N, H, W, dev)
+        a, b, _, t, _ = self._workspace(N, H, W, dev)
         self._conv_in(self.conv1_context, context, x1, a)
         self._resblock(self.y_hierarchical_prior_enc[0], a, t, b)
         self._resblock(self.y_hierarchical_prior_enc[1], b, t, a)
@@ -301,14 +327,7 @@ class ContextFusionFourStep(nn.Module):
             self.__dict__["_pack_hot"] = None
 
     def _workspace(self, N, H, W, dev):
-        """the three full feature maps + the bf16-only intermediate of one call, kept per shape (stream-ordered reuse)"""
-        key = (N, H, W, str(dev))
-        ws = self.__dict__.setdefault("_ws", {})
-        if key not in ws:
-            if len(ws) > 8:
-                ws.clear()
-            ws[key] = (_Features(N, H, W, dev), _Features(N, H, W, dev), _Features(N, H, W, dev), _Features(N, H, W, dev, f32=False))
-        return ws[key]
+        return _shared_workspace(N, H, W, dev)
 
     def _run_steps(self, x, context, prev_subband, stage=None, dec=None):
         ref_t = x if x is not None else context

@@ -292,25 +292,56 @@ class MCTFMixin:
                 "decoding_time": decoding_time, "encoding_time": encoding_time}
 
     @torch.no_grad()
-    def code_gop_forward(self, frames_y, frames_c, q_index=12, bin_folder=None, skip_decoding=True):
+    def code_gop_forward(self, frames_y, frames_c, q_index=12, bin_folder=None, skip_decoding=True, batched=False):
         """The reference's GOP loop (test_pMCTF_flex.py:131-291) on this model: dyadic temporal analysis with motion estimated and
         coded pair by pair (encode_one_stage), then the temporal synthesis.  frames_y: list of G padded luma planes [1,1,H,W],
         frames_c: list of G chroma pairs [2,1,H/2,W/2].  bin_folder None: the forward (rate-estimate) path.  Returns the
-        reconstructed frames and the per-frame bit counts."""
+        reconstructed frames and the per-frame bit counts.
+        batched=True (forward path only): the same results with the H frames of a stage coded as ONE batch per coder call -- motion
+        estimation / coding and the lifting stay pair by pair (the MV codec chains through `dpb`), but pWave.forward is independent per
+        frame, so the 8 / 4 / 2 / 1 luma planes (and twice as many chroma planes) of a stage share every launch."""
         import os
         G = len(frames_y)
         stages = G.bit_length() - 1
         coded = [[frames_y[i], frames_c[i], None] for i in range(G)]
         bits = [0.0] * G
         n = G
+        if batched and bin_folder is not None:
+            raise RuntimeError("batched=True is the forward (rate-estimate) path; the bitstream path writes one file per frame")
         for stage in range(stages):
             n //= 2
             dpb = {"mv_feature": None, "ref_mv_y": None}
             step = 1 << stage
+            me_num = min(self.num_me_stages - 1, stage)
+            code_lt = stage + 1 == stages
+            if batched:
+                Hy, Hc, me_bits = [], [], []
+                px = frames_y[0].size(2) * frames_y[0].size(3)
+                for grp in range(n):
+                    i = grp * 2 * step
+                    mv_hat, ref_mv, bpp_y, bpp_z = self.compute_and_code_motion(coded[i][0], coded[i + step][0], q_index, dpb, stage_idx=me_num)
+                    dpb = {"mv_feature": ref_mv["mv_feature"], "ref_mv_y": ref_mv["mv_y_hat"]}
+                    L_y, H_y, _, _ = self.forward_MCTF(coded[i][0], coded[i + step][0], mv_hat, me_num)
+                    L_c, H_c, _, _ = self.forward_MCTF(coded[i][1], coded[i + step][1], bilineardownsacling(mv_hat) / 2, me_num)
+                    coded[i] = [L_y, L_c, None]
+                    coded[i + step][2] = mv_hat
+                    Hy.append(H_y), Hc.append(H_c), me_bits.append((bpp_y + bpp_z) * px)
+                qp = self.hp_qp_scale(me_num, q_index)
+                ry = self.hp_coder.forward(torch.cat(Hy, 0), q_index, qp_scale=qp)
+                rc = self.hp_coder.forward(torch.cat(Hc, 0), q_index, qp_scale=qp)
+                by, bc = ry["bits"]["bits_total"], rc["bits"]["bits_total"]
+                for grp in range(n):
+                    j = grp * 2 * step + step
+                    coded[j][0], coded[j][1] = ry["x_hat"][grp:grp + 1], rc["x_hat"][2 * grp:2 * grp + 2]
+                    # the reference's per-call `bits_total` is the batch MEAN (pWave.py:308): luma + mean of the two chroma planes
+                    bits[j] = float(by[grp]) + float(bc[2 * grp:2 * grp + 2].mean()) + float(me_bits[grp])
+                if code_lt:
+                    rl, rlc = self.lp_coder.forward(coded[0][0], q_index), self.lp_coder.forward(coded[0][1], q_index)
+                    coded[0][0], coded[0][1] = rl["x_hat"], rlc["x_hat"]
+                    bits[0] = float(rl["bits_total"]) + float(rlc["bits_total"])
+                continue
             for grp in range(n):
                 i = grp * 2 * step
-                me_num = min(self.num_me_stages - 1, stage)
-                code_lt = stage + 1 == stages
                 path = os.path.join(bin_folder, f"{i + step}.bin") if bin_folder else None
                 r = self.encode_one_stage([coded[i][0], coded[i][1]], [coded[i + step][0], coded[i + step][1]], code_lt, dpb, output_path=path,
                                           pic_height=frames_y[0].size(2), pic_width=frames_y[0].size(3), skip_decoding=skip_decoding,

@@ -153,6 +153,13 @@ def test_gop4_forward_and_bitstream_paths(tmp_path, conv_mode):
         cs.append(torch.from_numpy(np.stack([f[0, :, ::2, ::2], 255 - f[0, :, ::2, ::2]])).to(dev))
     ry, rc, bits = m.code_gop_forward(ys, cs, q_index=12)
     assert len(ry) == 4 and all(torch.isfinite(t).all() for t in ry + rc) and all(b > 0 for b in bits)
+    # H frames of a stage as one batch per coder call: same reconstruction and rate (every frame is coded independently)
+    ry3, rc3, bits3 = m.code_gop_forward(ys, cs, q_index=12, batched=True)
+    # (the stock-torch parts -- ConvLSTM context, LL model -- may pick another cuDNN algorithm for another batch size, so "same" is to
+    # rounding: isolated symbols may flip, the bulk and the rate agree)
+    for a, b in zip(ry + rc, ry3 + rc3):
+        assert float((a - b).abs().mean()) < 0.05 * max(1.0, float(a.abs().mean()) / 100)
+    assert abs(sum(bits) - sum(bits3)) < 0.01 * sum(bits)
     folder = str(tmp_path)
     ry2, rc2, bits2 = m.code_gop_forward(ys, cs, q_index=12, bin_folder=folder, skip_decoding=False)
     assert all(torch.isfinite(t).all() for t in ry2 + rc2)
