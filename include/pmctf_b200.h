@@ -419,6 +419,11 @@ int pmctf_umma_selftest(const signed char *A, int a_bytes, const signed char *B,
  * flow_warp_bwd: adjoint of pmctf_flow_warp; gim [N,C,H,W] += dL/dim, gflow [flowN,2,H,W] += dL/dflow (caller zeroes; either
  * may be NULL). */
 int pmctf_conv3x3(const float *x, const float *w, const float *b, float *y, int N, int cin, int cout, int H, int W, void *stream);
+/* pmctf_conv3x3 with the element-wise step that follows it in PredictUpdate's forward / backward chain (lifting_1d.py:36-49) fused
+ * into the epilogue, over [N,cout,H,W] operands: mode 0 y = conv; 1 y = tanh(conv); 2 y = conv, y2 = tanh(conv); 3 y = conv + aux;
+ * 4 y = conv * (1 - aux^2) (data gradient through a tanh with output aux); 5 y = conv * (1 - aux^2) + aux2. */
+int pmctf_conv3x3_fused(const float *x, const float *w, const float *b, float *y, float *y2, const float *aux, const float *aux2, int mode,
+                        int N, int cin, int cout, int H, int W, void *stream);
 int pmctf_conv3x3_wgrad(const float *x, const float *g, float *gw, float *gb, int N, int cin, int cout, int H, int W, void *stream);
 int pmctf_flow_warp_bwd(const float *gout, const float *im, const float *flow, const float *lin_x, const float *lin_y, float *gim,
                         float *gflow, int N, int C, int H, int W, int flowN, float sign, void *stream);

@@ -144,6 +144,7 @@ SIGNATURES = {
     "pmctf_gaussian_symbolize": [_P, _P, _LL, _f, _f, _I, _P, _P, _P],
     "pmctf_frame_sse": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "pmctf_conv3x3": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pmctf_conv3x3_fused": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pmctf_conv3x3_wgrad": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pmctf_flow_warp_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _f, _P],
     "pmctf_umma_selftest": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P],

@@ -18,9 +18,35 @@ namespace train {
 
 constexpr int TX = 32, TY = 8; // output tile per CTA, one thread per pixel
 
+// Fused epilogues of the PredictUpdate forward / backward chain (lifting_1d.py:36-49): what the reference leaves to separate
+// element-wise ATen kernels over the 16-channel maps.  idx addresses y / y2 / aux / aux2 alike ([N,COUT,H,W]).
+//   EPI_NONE      y = acc
+//   EPI_TANH      y = tanh(acc)                               conv2: a2 = tanh(conv2(a1))
+//   EPI_DUAL      y = acc, y2 = tanh(acc)                     conv1: c1 and a1 = tanh(c1)
+//   EPI_ADD       y = acc + aux                               conv3: r = c1 + conv3(a2)
+//   EPI_DTANH     y = acc * (1 - aux^2)                       data gradient through a tanh whose OUTPUT is aux
+//   EPI_DTANH_ADD y = acc * (1 - aux^2) + aux2                the same plus the gradient of the residual branch
+enum { EPI_NONE = 0, EPI_TANH = 1, EPI_DUAL = 2, EPI_ADD = 3, EPI_DTANH = 4, EPI_DTANH_ADD = 5 };
+struct Epi {
+    const float *aux, *aux2;
+    float *y2;
+    int mode;
+};
+__device__ __forceinline__ void epilogue(const Epi &e, float acc, float *y, long long idx)
+{
+    switch (e.mode) {
+    case EPI_TANH: y[idx] = tanhf(acc); break;
+    case EPI_DUAL: y[idx] = acc; e.y2[idx] = tanhf(acc); break;
+    case EPI_ADD: y[idx] = acc + __ldg(e.aux + idx); break;
+    case EPI_DTANH: { const float a = __ldg(e.aux + idx); y[idx] = acc * (1.0f - a * a); break; }
+    case EPI_DTANH_ADD: { const float a = __ldg(e.aux + idx); y[idx] = acc * (1.0f - a * a) + __ldg(e.aux2 + idx); break; }
+    default: y[idx] = acc;
+    }
+}
+
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(TX * TY) conv3x3_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
-                                                          float *__restrict__ y, int H, int W)
+                                                          float *__restrict__ y, int H, int W, const Epi epi)
 {
     __shared__ float xs[CIN][TY + 2][TX + 2];
     __shared__ __align__(16) float ws[CIN * 9][COUT]; // [ci*9 + k][co]
@@ -52,9 +78,9 @@ __global__ void __launch_bounds__(TX * TY) conv3x3_kernel(const float *__restric
         }
     }
     if (gy < H && gx < W) {
-        float *yp = y + (long long)n * COUT * H * W + (long long)gy * W + gx;
+        const long long base = (long long)n * COUT * H * W + (long long)gy * W + gx;
 #pragma unroll
-        for (int co = 0; co < COUT; ++co) yp[(long long)co * H * W] = acc[co];
+        for (int co = 0; co < COUT; ++co) epilogue(epi, acc[co], y, base + (long long)co * H * W);
     }
 }
 
@@ -138,7 +164,7 @@ __device__ __forceinline__ float2 ffma2s(float2 a, float b, float2 c)
 constexpr int TX2 = 64; // conv16x16: 64 x 8 output tile, thread = 2 horizontally adjacent pixels x 16 output channels
 
 __global__ void __launch_bounds__(256) conv3x3_16x16_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
-                                                            float *__restrict__ y, int H, int W)
+                                                            float *__restrict__ y, int H, int W, const Epi epi)
 {
     extern __shared__ __align__(16) float dsm[];                         // 51.5 KB: opt-in dynamic shared memory
     float(*ws)[16] = reinterpret_cast<float(*)[16]>(dsm);                // [ci*9 + k][co]
@@ -185,12 +211,12 @@ __global__ void __launch_bounds__(256) conv3x3_16x16_kernel(const float *__restr
     }
     const int gy = y0 + ty, gx = x0 + 2 * tx;
     if (gy < H && gx < W) {
-        float *yp = y + (long long)n * 16 * H * W + (long long)gy * W + gx;
+        const long long base = (long long)n * 16 * H * W + (long long)gy * W + gx;
         const bool two = gx + 1 < W;
 #pragma unroll
         for (int co = 0; co < 16; ++co) {
-            yp[(long long)co * H * W] = acc[co].x;
-            if (two) yp[(long long)co * H * W + 1] = acc[co].y;
+            epilogue(epi, acc[co].x, y, base + (long long)co * H * W);
+            if (two) epilogue(epi, acc[co].y, y, base + (long long)co * H * W + 1);
         }
     }
 }
@@ -313,13 +339,14 @@ __global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const float *__restr
 
 using namespace pmctf::train;
 
-extern "C" int pmctf_conv3x3(const float *x, const float *w, const float *b, float *y, int N, int cin, int cout, int H, int W, void *stream)
+static int launch_conv3x3(const float *x, const float *w, const float *b, float *y, const Epi &epi, int N, int cin, int cout, int H, int W,
+                          void *stream)
 {
     if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0) return PMCTF_EINVAL;
     dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY, N), block(TX, TY);
     if (grid.y > 65535 || grid.z > 65535) return PMCTF_ESHAPE;
     cudaStream_t st = (cudaStream_t)stream;
-    if (cin == 1 && cout == 16) conv3x3_kernel<1, 16><<<grid, block, 0, st>>>(x, w, b, y, H, W);
+    if (cin == 1 && cout == 16) conv3x3_kernel<1, 16><<<grid, block, 0, st>>>(x, w, b, y, H, W, epi);
     else if (cin == 16 && cout == 16) {
         constexpr int SMEM = (144 * 16 + 16 * (TY + 2) * (TX2 + 2)) * 4;
         static bool configured = false;
@@ -328,12 +355,27 @@ extern "C" int pmctf_conv3x3(const float *x, const float *w, const float *b, flo
             if (e != cudaSuccess) return (int)e;
             configured = true;
         }
-        conv3x3_16x16_kernel<<<dim3((W + TX2 - 1) / TX2, (H + TY - 1) / TY, N), 256, SMEM, st>>>(x, w, b, y, H, W);
+        conv3x3_16x16_kernel<<<dim3((W + TX2 - 1) / TX2, (H + TY - 1) / TY, N), 256, SMEM, st>>>(x, w, b, y, H, W, epi);
     }
-    else if (cin == 16 && cout == 1) conv3x3_kernel<16, 1><<<grid, block, 0, st>>>(x, w, b, y, H, W);
-    else if (cin == 1 && cout == 1) conv3x3_kernel<1, 1><<<grid, block, 0, st>>>(x, w, b, y, H, W);
+    else if (cin == 16 && cout == 1) conv3x3_kernel<16, 1><<<grid, block, 0, st>>>(x, w, b, y, H, W, epi);
+    else if (cin == 1 && cout == 1) conv3x3_kernel<1, 1><<<grid, block, 0, st>>>(x, w, b, y, H, W, epi);
     else return PMCTF_ESHAPE;
     return (int)cudaGetLastError();
+}
+
+extern "C" int pmctf_conv3x3(const float *x, const float *w, const float *b, float *y, int N, int cin, int cout, int H, int W, void *stream)
+{
+    const Epi none = {nullptr, nullptr, nullptr, EPI_NONE};
+    return launch_conv3x3(x, w, b, y, none, N, cin, cout, H, W, stream);
+}
+
+extern "C" int pmctf_conv3x3_fused(const float *x, const float *w, const float *b, float *y, float *y2, const float *aux, const float *aux2, int mode,
+                                   int N, int cin, int cout, int H, int W, void *stream)
+{
+    if (mode < EPI_NONE || mode > EPI_DTANH_ADD) return PMCTF_EINVAL;
+    if ((mode == EPI_DUAL && !y2) || (mode >= EPI_ADD && !aux) || (mode == EPI_DTANH_ADD && !aux2)) return PMCTF_EINVAL;
+    const Epi e = {aux, aux2, y2, mode};
+    return launch_conv3x3(x, w, b, y, e, N, cin, cout, H, W, stream);
 }
 
 extern "C" int pmctf_conv3x3_wgrad(const float *x, const float *g, float *gw, float *gb, int N, int cin, int cout, int H, int W, void *stream)

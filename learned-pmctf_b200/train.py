@@ -102,9 +102,74 @@ def flow_warp(im, flow):
     return _FlowWarp.apply(im, flow)
 
 
+def _conv_fused(x, w, b, mode, aux=None, aux2=None, want_y2=False):
+    """pmctf_conv3x3_fused: conv3x3 + the element-wise step behind it (modes: include/pmctf_b200.h)"""
+    x, w = x.contiguous(), w.contiguous()
+    N, cin, H, W = x.shape
+    cout = w.size(0)
+    y = torch.empty((N, cout, H, W), dtype=torch.float32, device=x.device)
+    y2 = torch.empty_like(y) if want_y2 else None
+    ops._launch(ops._same_device(x, w), "conv3x3_fused", nat.lib().pmctf_conv3x3_fused, x.data_ptr(), w.data_ptr(),
+                b.contiguous().data_ptr() if b is not None else None, y.data_ptr(), y2.data_ptr() if y2 is not None else None,
+                aux.contiguous().data_ptr() if aux is not None else None, aux2.contiguous().data_ptr() if aux2 is not None else None, mode,
+                N, cin, cout, H, W)
+    return (y, y2) if want_y2 else y
+
+
+def _wgrad(x, g, w, has_bias):
+    N, cin, H, W = x.shape
+    cout = w.size(0)
+    gw = torch.zeros_like(w)
+    gb = torch.zeros(cout, dtype=torch.float32, device=x.device) if has_bias else None
+    ops._launch(ops._same_device(x, g), "conv3x3_wgrad", nat.lib().pmctf_conv3x3_wgrad, x.contiguous().data_ptr(), g.contiguous().data_ptr(),
+                gw.data_ptr(), gb.data_ptr() if gb is not None else None, N, cin, cout, H, W)
+    return gw, gb
+
+
+def _flip(w):
+    return w.transpose(0, 1).flip(2, 3).contiguous()
+
+
+class _PredictUpdate(torch.autograd.Function):
+    """PredictUpdate.forward (lifting_1d.py:36-49) and its backward as ONE autograd node on fused kernels: every element-wise step
+    over the 16-channel maps (two tanh, the residual add, the two tanh derivatives, the gradient sum of the residual branch) lives
+    in the epilogue of the convolution before it.  4 launches forward, 8 backward (4 data gradients, 4 weight gradients); saved for
+    backward: x, a1 = tanh(c1), a2 = tanh(c2), r = c1 + c3."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3, w4, b4):
+        x = ops._chk(x, "x", 4).contiguous()
+        c1, a1 = _conv_fused(x, w1, b1, 2, want_y2=True)
+        a2 = _conv_fused(a1, w2, b2, 1)
+        r = _conv_fused(a2, w3, b3, 3, aux=c1)
+        y = _conv_fused(r, w4, b4, 0)
+        ctx.save_for_backward(x, a1, a2, r, w1, w2, w3, w4)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, a1, a2, r, w1, w2, w3, w4 = ctx.saved_tensors
+        g = g.contiguous()
+        g_r = _conv_fused(g, _flip(w4), None, 0)
+        gw4, gb4 = _wgrad(r, g, w4, True)
+        g_c2 = _conv_fused(g_r, _flip(w3), None, 4, aux=a2)                    # through conv3, then tanh'(c2) = 1 - a2^2
+        gw3, gb3 = _wgrad(a2, g_r, w3, True)
+        g_c1 = _conv_fused(g_c2, _flip(w2), None, 5, aux=a1, aux2=g_r)          # through conv2 and tanh'(c1), plus the residual branch
+        gw2, gb2 = _wgrad(a1, g_c2, w2, True)
+        gx = _conv_fused(g_c1, _flip(w1), None, 0) if ctx.needs_input_grad[0] else None
+        gw1, gb1 = _wgrad(x, g_c1, w1, True)
+        return gx, gw1, gb1, gw2, gb2, gw3, gb3, gw4, gb4
+
+
+FUSED_PU = True     # False: the un-fused composition below (one autograd node per convolution, element-wise steps in torch)
+
+
 # ---- the reference's formulas on these primitives ---------------------------------------------------------------------
 def predict_update(pu, x):
     """PredictUpdate.forward (lifting_1d.py:36-49)."""
+    if FUSED_PU and all(c.bias is not None for c in (pu.conv1, pu.conv2, pu.conv3, pu.conv4)):
+        return _PredictUpdate.apply(x, pu.conv1.weight, pu.conv1.bias, pu.conv2.weight, pu.conv2.bias, pu.conv3.weight, pu.conv3.bias,
+                                    pu.conv4.weight, pu.conv4.bias)
     c1 = conv3x3(x, pu.conv1)
     a = torch.tanh(c1)
     a = torch.tanh(conv3x3(a, pu.conv2))

@@ -231,3 +231,33 @@ def test_batched_training_loss_backward(P):
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
     one = [Gm.training_loss_hot_path(m, clips[b:b + 1], [mvs[0][b::2], mvs[1][b::2]], q_index=8)[1] for b in range(2)]
     assert abs(float(dist) - float(sum(one) / 2)) <= 1e-4 * float(dist)
+
+
+@pytest.mark.parametrize("shape", [(2, 19, 45), (1, 64, 64), (3, 8, 130)])
+def test_fused_predict_update_node(P, shape):
+    """The single autograd node of PredictUpdate (fused tanh / residual / tanh' epilogues) against the same formula on F.conv2d:
+    output, input gradient and all eight parameter gradients."""
+    from learned_pmctf_b200 import train
+    torch.manual_seed(shape[1] + shape[2])
+    N, H, W = shape
+    pu = P.PredictUpdate(1).cuda()
+    with torch.no_grad():
+        for p in pu.parameters():
+            p.normal_(0, 0.2 if p.dim() == 4 else 0.05)
+    x = torch.randn(N, 1, H, W, device="cuda", requires_grad=True)
+    g = torch.randn(N, 1, H, W, device="cuda")
+    y = train.predict_update(pu, x)
+    assert type(y.grad_fn).__name__.startswith("_PredictUpdate")
+    y.backward(g)
+    got = [y.detach(), x.grad.clone()] + [p.grad.clone() for p in pu.parameters()]
+    x.grad = None
+    for p in pu.parameters():
+        p.grad = None
+    c1 = F.conv2d(x, pu.conv1.weight, pu.conv1.bias, padding=1)
+    a = torch.tanh(F.conv2d(torch.tanh(c1), pu.conv2.weight, pu.conv2.bias, padding=1))
+    yr = F.conv2d(c1 + F.conv2d(a, pu.conv3.weight, pu.conv3.bias, padding=1), pu.conv4.weight, pu.conv4.bias, padding=1)
+    yr.backward(g)
+    want = [yr.detach(), x.grad] + [p.grad for p in pu.parameters()]
+    tf32 = torch.backends.cudnn.allow_tf32
+    for a_, b_, name in zip(got, want, ["y", "dx"] + [n for n, _ in pu.named_parameters()]):
+        assert rel(a_, b_) <= (5e-3 if tf32 else 5e-5), (name, rel(a_, b_))
