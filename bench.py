@@ -376,6 +376,49 @@ def run_context_fusion(pkg, dev, pk):
         tfl = CTX_LAYER_FLOPS * N * H * W / lms / 1e9
         layer[tag] = {"ms": lms, "tflops": tfl, "frac_of_bf16_peak": tfl / pk["tf_sustained"],
                       "algorithmic_hbm_gbs": bytes_px * N * H * W / lms / 1e6, "frac_of_hbm_peak": bytes_px * N * H * W / lms / 1e6 / pk["hbm_gbs"]}
+    # the LL band's autoregressive model in its sequential (bitstream) form: one kernel per band (encoder) / per coefficient (decoder)
+    import time
+    from learned_pmctf_b200.entropy_models.gaussian_model import CompressionModel
+    from learned_pmctf_b200.layers.context_fusion import ContextFusionSubband
+    lln = ContextFusionSubband(num_features=128, num_parameters=2, context=False, in_channels=1)
+    with torch.no_grad():
+        for p_ in lln.parameters():
+            p_.normal_(0, 0.04 if p_.dim() == 4 else 0.05)
+        lln.convs[2].bias[0] += 1.5
+    lln = lln.to(dev).eval()
+    em = CompressionModel("laplace")
+    em.update()
+    cdf, ln, off = em.gaussian_encoder.get_cdf_info()
+    llq = torch.round(torch.randn((1, 1, 72, 120), device=dev, generator=g) * 6)
+    ll_seq = {}
+    with torch.no_grad():
+        lln.ar_encode(llq)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        ll_hat, s16, i16 = lln.ar_encode(llq)
+        torch.cuda.synchronize(dev)
+        ll_seq["encode_ms"] = (time.perf_counter() - t0) * 1e3
+        em.entropy_coder.reset()
+        em.entropy_coder.encoder.encode_with_indexes(s16, i16, cdf, ln, off)
+        em.entropy_coder.flush()
+        em.entropy_coder.set_stream(em.entropy_coder.get_encoded_stream())
+        dec = em.entropy_coder.decoder
+        t0 = time.perf_counter()
+        back = lln.ar_decode([1, 1, 72, 120], lambda i: dec.decode_stream(i, cdf, ln, off), dev)
+        ll_seq["decode_ms"] = (time.perf_counter() - t0) * 1e3
+        ll_seq["round_trip_exact"] = bool(torch.equal(back, ll_hat))
+        plane = torch.nn.functional.pad(ll_hat, (1, 1, 1, 1))          # the reference's formulation (ATen calls per coefficient), 3 rows timed
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for h in range(3):
+            for w in range(120):
+                lln.forward_sequential(plane, h, w)
+        torch.cuda.synchronize(dev)
+        ll_seq["torch_ops_ms_extrapolated"] = (time.perf_counter() - t0) * 1e3 * 72 / 3
+        lln.sequential_init = False
+    ll_seq["what"] = ("LL band of a 1080p luma plane (72x120 = 8 640 coefficients), sequential form (context_fusion.py:160-204 as driven by "
+                      "pWave.py:531-584): encoder = one kernel for the band, decoder = one kernel + one rANS step per coefficient; the "
+                      "reference's ~25 ATen calls per coefficient beside it (parameter evaluation only, without its per-coefficient coder calls)")
     pkg.ops.check_tc_error(dev, "context fusion block")
     tf = CTX_FLOPS_PER_COEFF * coeffs / ms / 1e9
     return {"what": "ContextFusionFourStep (context_fusion_4step.py:23-194; 112 features) forward on the 12 high-pass subbands of one 1080p luma "
@@ -385,7 +428,7 @@ def run_context_fusion(pkg, dev, pk):
             "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
                          "peak_source": f"{pk['source']} bf16 dense, sustained",
                          "scope": "the whole module call on all 12 subbands (about 37 launches per subband incl. the CUDA-core layers; the deep levels are launch-bound at batch 1)"},
-            "tensor_core_layer_576x960": layer, "torch_gpu_baseline": base}
+            "tensor_core_layer_576x960": layer, "ll_sequential": ll_seq, "torch_gpu_baseline": base}
 
 
 SPYNET_FLOPS_PER_PX = 2 * 49 * (8 * 32 + 32 * 64 + 64 * 32 + 32 * 16 + 16 * 2)     # one MEBasic; the 6-level pyramid costs 4/3 of it per pixel

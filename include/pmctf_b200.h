@@ -348,6 +348,31 @@ typedef struct {
 } pmctf_ctx_step_t;
 int pmctf_ctx_mask_step(const pmctf_ctx_step_t *s, void *stream);
 
+/* ---- the LL subband's autoregressive model in its sequential form (third module):
+ * pMCTF/layers/context_fusion.py:56-204 (ContextFusionSubband.forward_sequential) as driven by pWave._compress_subband_ar /
+ * _decompress_subband_ar (pWave.py:531-584).  One kernel evaluates a coefficient's whole network from five channel-last history
+ * planes; the encoder runs the band in one launch, the decoder one launch per coefficient (see csrc/pmctf_llar.cu).
+ * Weights are repacked once by pmctf_llar_pack: (cin = 1, taps = 4) maskedConv1 -> [4][128]; (128, 5) the masked 128 -> 128 layers
+ * -> [5][128][128] = [tap][ci][co]; (128, 0) a 1x1 layer -> [ci][co].  w_out / b_out: convs.2 in its state_dict layout [2,128,1,1]. */
+typedef struct {
+    const float *w_in, *b_in;
+    const float *w[5], *b[5];       /* residualBlocks.0.conv1, .0.conv2, .1.conv1, .1.conv2, maskedConv2 */
+    const float *w1[2], *b1[2];     /* convs.0, convs.1 */
+    const float *w_out, *b_out;     /* convs.2 */
+    float *Y;                       /* [B][H+2][W+2] reconstructed band, zero border; zeroed by the caller before the first coefficient */
+    float *hist[5];                 /* [B][H+2][W+2][128] each, zeroed by the caller */
+    int B, H, W;
+    float log_scale_min, log_scale_step;
+    int scale_levels;
+} pmctf_llar_t;
+int pmctf_llar_pack(const float *w, int cin, int taps, float *out, void *stream);
+/* encoder: yq [B,1,H,W] quantised band -> sym16 / idx16 [B][H*W] (symbol round(round(y) - mean) and scale-table index per
+ * coefficient, raster order) and, in p->Y, the band as the decoder will reconstruct it */
+int pmctf_llar_encode(const pmctf_llar_t *p, const float *yq, short *sym16, short *idx16, void *stream);
+/* decoder: parameters of coefficient `pos` (raster index); prev [B] = reconstructed value of coefficient pos - 1 (ignored for
+ * pos == 0), out_mean [B] / out_idx [B]: HOST-visible (mapped pinned) memory read after synchronising the stream */
+int pmctf_llar_decode_step(const pmctf_llar_t *p, int pos, const float *prev, float *out_mean, short *out_idx, void *stream);
+
 /* ---- SpyNet motion estimation: pMCTF/layers/video/video_net.py:74-121 ---------------------------
  * pmctf_pair_conv: nn.Conv2d(cin, cout, k, padding = k/2), k = 1, 3 or 7, between channel-chunked bf16 maps as a tcgen05 CTA-pair
  * implicit GEMM (run-time channel counts; the machine of pmctf_ctx_conv112).  in_bf16 [N][cin_pad/8][H][W][8] (cin_pad a multiple of

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("PMCTF_LIB") or os.path.join(_HERE, "lib", "libpmctf_b200.so")  # PMCTF_LIB: profiling builds only
 SOURCES = [os.path.join(_HERE, "csrc", "pmctf_kernels.cu"), os.path.join(_HERE, "csrc", "pmctf_umma_test.cu"),
            os.path.join(_HERE, "csrc", "pmctf_lift_tc.cu"), os.path.join(_HERE, "csrc", "pmctf_train.cu"),
-           os.path.join(_HERE, "csrc", "pmctf_pp.cu"), os.path.join(_HERE, "csrc", "pmctf_rans.cu"), os.path.join(_HERE, "csrc", "pmctf_ctx.cu"), os.path.join(_HERE, "csrc", "pmctf_pairconv.cu")]
+           os.path.join(_HERE, "csrc", "pmctf_pp.cu"), os.path.join(_HERE, "csrc", "pmctf_rans.cu"), os.path.join(_HERE, "csrc", "pmctf_ctx.cu"), os.path.join(_HERE, "csrc", "pmctf_pairconv.cu"), os.path.join(_HERE, "csrc", "pmctf_llar.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "pmctf_umma.cuh"), os.path.join(_HERE, "csrc", "pmctf_common.cuh")]
 INCLUDE = os.path.join(ROOT, "include")
 
@@ -65,6 +65,12 @@ class CtxStep(C.Structure):
     _fields_ = [("x", _fp), ("dec_sym", C.c_void_p), ("scales", _fp), ("means", _fp), ("x_hat", _fp), ("x_q", _fp), ("s_hat", _fp),
                 ("x_res", _fp), ("sym16", C.c_void_p), ("idx16", C.c_void_p), ("log_scale_min", _f), ("log_scale_step", _f),
                 ("scale_levels", C.c_int), ("step", C.c_int), ("lossy", C.c_int), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int)]
+
+
+class LLar(C.Structure):
+    _fields_ = [("w_in", _fp), ("b_in", _fp), ("w", _fp * 5), ("b", _fp * 5), ("w1", _fp * 2), ("b1", _fp * 2), ("w_out", _fp), ("b_out", _fp),
+                ("Y", _fp), ("hist", _fp * 5), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("log_scale_min", _f), ("log_scale_step", _f),
+                ("scale_levels", C.c_int)]
 
 
 class Temporal(C.Structure):
@@ -124,6 +130,9 @@ SIGNATURES = {
     "pmctf_ctx_dcb_tail": [_P, _P, C.POINTER(CtxDcb), _P, _P, _I, _I, _I, _P],
     "pmctf_ctx_head": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "pmctf_ctx_mask_step": [C.POINTER(CtxStep), _P],
+    "pmctf_llar_pack": [_P, _I, _I, _P, _P],
+    "pmctf_llar_encode": [C.POINTER(LLar), _P, _P, _P, _P],
+    "pmctf_llar_decode_step": [C.POINTER(LLar), _I, _P, _P, _P, _P],
     "pmctf_pair_packed_bytes": [_I, _I, _I],
     "pmctf_pair_pack_conv": [_P, _I, _I, _I, _I, _I, _P, _P],
     "pmctf_pair_conv": [_P, _P, _P, _I, _I, _I, _I, _f, _P, _P, _P, _I, _I, _I, _P],

@@ -5,12 +5,21 @@ context input).
 The LL band of a 1080p plane is 72 x 120 coefficients (1/256 of the plane): this module is host-side torch code on stock
 convolutions, with the reference's module tree, parameter AND buffer names (`mask` buffers are part of its state_dicts).  The full-
 plane `forward` is what the training / evaluation pass uses; `forward_sequential` is the pixel-by-pixel form the bitstream path
-needs (every coefficient's parameters depend on the coefficients decoded before it)."""
+needs (every coefficient's parameters depend on the coefficients decoded before it); on CUDA tensors that form runs as ONE kernel
+per coefficient (decoder) or per band (encoder) instead of the reference's ~25 ATen calls per coefficient: `ar_encode` / `ar_decode`
+(csrc/pmctf_llar.cu)."""
 from __future__ import annotations
 
+import ctypes as C
+import math
+
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from .. import _native as nat
+from .. import ops
 
 
 class MaskedConv2d(nn.Conv2d):
@@ -122,3 +131,85 @@ class ContextFusionSubband(nn.Module):
         self.maskedConv2_input[:, :, h + pad:h + pad + 1, w + pad:w + pad + 1] = t
         t = F.conv2d(self.maskedConv2_input[:, :, h:h + k, w:w + k], self.maskedWeight2, bias=self.maskedConv2.bias)
         return self._tail(self.lrelu(t))
+
+
+    # ---- the sequential form on the GPU (csrc/pmctf_llar.cu) -------------------------------------------------------------------
+    def _ar_weights(self):
+        convs = [self.maskedConv1, self.residualBlocks[0].conv1, self.residualBlocks[0].conv2, self.residualBlocks[1].conv1,
+                 self.residualBlocks[1].conv2, self.maskedConv2, self.convs[0], self.convs[1], self.convs[2]]
+        key = tuple((c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version) for c in convs)
+        cache = self.__dict__.get("_ar_cache")
+        if cache is None or cache[0] != key:
+            if self.num_features != 128 or self.num_parameters != 2 or self.maskedConv1.weight.shape[1] != 1:
+                raise RuntimeError("the sequential LL kernel is built for pWave++'s configuration (1 -> 128 features -> 2 parameters)")
+            lib, dev = nat.lib(), self.maskedConv1.weight.device
+            sizes = [4 * 128] + [5 * 128 * 128] * 5 + [128 * 128] * 2
+            buf = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            offs, off = [], 0
+            for c, sz, (cin, taps) in zip(convs[:8], sizes, [(1, 4)] + [(128, 5)] * 5 + [(128, 0)] * 2):
+                ops._launch(dev, "llar_pack", lib.pmctf_llar_pack, c.weight.detach().contiguous().data_ptr(), cin, taps, buf.data_ptr() + 4 * off)
+                offs.append(off)
+                off += sz
+            keep = [c.bias.detach().contiguous() for c in convs] + [convs[8].weight.detach().contiguous()]
+            cache = (key, buf, offs, keep)
+            self.__dict__["_ar_cache"] = cache
+        return cache
+
+    def _ar_desc(self, B, H, W, dev):
+        _, buf, offs, keep = self._ar_weights()
+        d = nat.LLar()
+        base = buf.data_ptr()
+        d.w_in, d.b_in = base + 4 * offs[0], keep[0].data_ptr()
+        for i in range(5):
+            d.w[i], d.b[i] = base + 4 * offs[1 + i], keep[1 + i].data_ptr()
+        for i in range(2):
+            d.w1[i], d.b1[i] = base + 4 * offs[6 + i], keep[6 + i].data_ptr()
+        d.w_out, d.b_out = keep[9].data_ptr(), keep[8].data_ptr()
+        Y = torch.zeros((B, H + 2, W + 2), dtype=torch.float32, device=dev)
+        hist = torch.zeros((5, B, H + 2, W + 2, 128), dtype=torch.float32, device=dev)
+        d.Y = Y.data_ptr()
+        for i in range(5):
+            d.hist[i] = hist[i].data_ptr()
+        d.B, d.H, d.W = B, H, W
+        d.log_scale_min = float(np.float32(math.log(0.01)))                       # GaussianEncoder('laplace'), entropy_models.py:204-221
+        d.log_scale_step = float(np.float32((math.log(64.0) - math.log(0.01)) / 255))
+        d.scale_levels = 256
+        return d, (Y, hist)
+
+    def ar_encode(self, yq):
+        """yq [B,1,H,W] quantised LL band (CUDA) -> (ll_hat [B,1,H,W] as the decoder will reconstruct it, int16 symbols, int16 table
+        indexes), the latter two as numpy arrays in the order the entropy coder consumes them: coefficient by coefficient in raster
+        order, planes of the batch innermost (one `encoder.encode` per coefficient in pWave.py:548-553)."""
+        yq = ops._chk(yq, "ll", 4).contiguous()
+        B, Cc, H, W = yq.shape
+        if Cc != 1:
+            raise RuntimeError("the LL band is single-channel")
+        d, (Y, _hist) = self._ar_desc(B, H, W, yq.device)
+        sym = torch.empty((B, H * W), dtype=torch.int16, device=yq.device)
+        idx = torch.empty_like(sym)
+        ops._launch(yq.device, "llar_encode", nat.lib().pmctf_llar_encode, C.byref(d), yq.data_ptr(), sym.data_ptr(), idx.data_ptr())
+        ll_hat = Y[:, 1:-1, 1:-1].unsqueeze(1).contiguous()
+        return ll_hat, sym.t().contiguous().cpu().numpy().reshape(-1), idx.t().contiguous().cpu().numpy().reshape(-1)
+
+    def ar_decode(self, size, decode, device):
+        """size = [B,1,H,W]; decode(idx int16 numpy [B]) -> int16 numpy [B] symbols of one coefficient.  One kernel launch + one
+        stream synchronisation + one rANS step per coefficient."""
+        B, Cc, H, W = size
+        if Cc != 1:
+            raise RuntimeError("the LL band is single-channel")
+        device = torch.device(device)
+        d, _keep = self._ar_desc(B, H, W, device)
+        prev = torch.zeros(B, dtype=torch.float32, pin_memory=True)
+        mean = torch.zeros(B, dtype=torch.float32, pin_memory=True)
+        idx = torch.zeros(B, dtype=torch.int16, pin_memory=True)
+        out = np.zeros((B, H * W), dtype=np.float32)
+        lib, st = nat.lib(), torch.cuda.current_stream(device)
+        prev_np, mean_np, idx_np = prev.numpy(), mean.numpy(), idx.numpy()
+        with torch.cuda.device(device):
+            for pos in range(H * W):
+                nat.check(lib.pmctf_llar_decode_step(C.byref(d), pos, prev.data_ptr(), mean.data_ptr(), idx.data_ptr(), st.cuda_stream), "llar_decode_step")
+                st.synchronize()
+                sym = decode(idx_np.copy()).astype(np.float32)
+                prev_np[:] = np.rint(sym + mean_np)                             # round(decoded + mean), fp32 like the kernel's encoder side
+                out[:, pos] = prev_np
+        return torch.from_numpy(out.reshape(B, 1, H, W)).to(device)

@@ -290,6 +290,14 @@ class pWaveTransform:
         B, Cc, H, W = size
         net = self.context_fusion[str(self.decomp_levels - 1)]["ll"]
         enc = self.em.gaussian_encoder
+        if hasattr(net, "ar_encode") and torch.device(device).type == "cuda":   # one kernel per band / per coefficient (csrc/pmctf_llar.cu)
+            cdf, ln, off = enc.get_cdf_info()
+            if symbols is not None:
+                ll_hat, sym16, idx16 = net.ar_encode(symbols)
+                enc.entropy_coder.encoder.encode_with_indexes(sym16, idx16, cdf, ln, off)
+                return ll_hat
+            dec = enc.entropy_coder.decoder
+            return net.ar_decode(size, lambda idx: dec.decode_stream(idx, cdf, ln, off), device).to(dtype)
         pad = 1
         if symbols is not None:
             plane = torch.nn.functional.pad(symbols, (pad, pad, pad, pad))

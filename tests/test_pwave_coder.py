@@ -92,3 +92,50 @@ def test_forward_rate_and_compress_decompress(tmp_path, conv_mode):
     assert torch.equal(back, x_hat)
     assert torch.equal(x_hat, out["x_hat"])       # same symbols through the forward pass and the bitstream path
     assert pkg.ops.tc_error_flag() == 0
+
+
+@pytest.mark.gpu
+def test_ll_sequential_kernel_vs_torch_form(conv_mode):
+    """The one-kernel sequential LL model against the module's own forward_sequential (the reference's formulation on torch ops):
+    same symbols and table indexes except where fp32 summation order moves a value across a rounding / table boundary; encoder and
+    decoder of the kernel agree exactly."""
+    if conv_mode != "tensor":
+        pytest.skip("independent of the lifting arithmetic")
+    from learned_pmctf_b200.entropy_models.gaussian_model import CompressionModel
+    from learned_pmctf_b200.layers.context_fusion import ContextFusionSubband
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    net = ContextFusionSubband(num_features=128, num_parameters=2, context=False, in_channels=1)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.normal_(0, 0.04 if p.dim() == 4 else 0.05)
+        net.convs[2].bias[0] += 1.5
+    net = net.to(dev).eval()
+    em = CompressionModel("laplace")
+    em.update()
+    B, H, W = 2, 9, 14
+    ll = torch.round(torch.randn(B, 1, H, W, device=dev) * 6)
+    with torch.no_grad():
+        ll_hat, sym16, idx16 = net.ar_encode(ll)
+        # the reference's loop on torch ops, conditioning on the same reconstruction
+        plane = torch.nn.functional.pad(ll_hat, (1, 1, 1, 1))
+        want_sym, want_idx = [], []
+        for h in range(H):
+            for w in range(W):
+                scale, mean = net.forward_sequential(plane, h, w).chunk(2, dim=1)
+                want_sym.append(torch.round(ll[:, :, h:h + 1, w:w + 1] - mean).reshape(-1))
+                want_idx.append(em.gaussian_encoder.build_indexes(scale.cpu()).reshape(-1))
+        net.sequential_init = False
+    want_sym = torch.stack(want_sym).reshape(-1).cpu().numpy().astype(np.int16)
+    want_idx = torch.stack(want_idx).reshape(-1).numpy().astype(np.int16)
+    assert (sym16 != want_sym).mean() < 0.02 and np.abs(sym16.astype(int) - want_sym).max() <= 1
+    assert (idx16 != want_idx).mean() < 0.05 and np.abs(idx16.astype(int) - want_idx).max() <= 1
+    # encode -> rANS -> decode with the kernel on both sides: exact
+    cdf, ln, off = em.gaussian_encoder.get_cdf_info()
+    em.entropy_coder.reset()
+    em.entropy_coder.encoder.encode_with_indexes(sym16, idx16, cdf, ln, off)
+    em.entropy_coder.flush()
+    em.entropy_coder.set_stream(em.entropy_coder.get_encoded_stream())
+    dec = em.entropy_coder.decoder
+    back = net.ar_decode([B, 1, H, W], lambda i: dec.decode_stream(i, cdf, ln, off), dev)
+    assert torch.equal(back, ll_hat)
