@@ -26,7 +26,8 @@ void count_launch();
 namespace llar {
 
 constexpr int F = 128;          // features
-constexpr int NT = 128;         // one thread per output channel
+constexpr int NT = 256;         // 32 groups of four output channels x 8 slices of the reduction dimension
+constexpr int KSL = 8;
 // causal taps in (dy, dx) relative to the current coefficient, padded-plane coordinates: type B = 5 taps, type A = the first 4
 __constant__ int c_dy[5] = {-1, -1, -1, 0, 0};
 __constant__ int c_dx[5] = {-1, 0, 1, -1, 0};
@@ -57,77 +58,106 @@ struct Run {
     short *out_idx;              // [B] host-mapped
 };
 
+struct Smem {
+    float in[5 * F];             // staged inputs of a layer: [tap][ci] or [ci]
+    float part[KSL * F];         // partial sums of the reduction slices
+    float out[F];                // a layer's output
+    float cur[F], first[F];      // running activation, maskedConv1's output (the outer skip, context_fusion.py:119)
+};
+
 __device__ __forceinline__ float lrelu(float v) { return v >= 0.0f ? v : v * 0.2f; }
 
-// one masked 128 -> 128 convolution at (h, w) from a channel-last history plane; in_s: [5][128] staging
-__device__ __forceinline__ float masked_layer(const float *__restrict__ hist, const float *__restrict__ w, const float *__restrict__ b, int h, int wd,
-                                              int Wp, float *in_s, int co)
+// out[co] = b[co] + sum_k w[k][co] * in[k], K = 640 (five taps x 128 channels) or 128: thread = four adjacent output channels x one
+// eighth of k (16-byte weight loads, eight in flight), partial sums folded in a fixed order -- the weights stream from L2, so the
+// layer is as fast as the loads one SM can keep in flight
+__device__ __forceinline__ void gemv(const float *__restrict__ w, const float *__restrict__ b, int K, Smem &s)
 {
-#pragma unroll
-    for (int t = 0; t < 5; ++t) in_s[t * F + co] = hist[((long long)(h + 1 + c_dy[t]) * Wp + (wd + 1 + c_dx[t])) * F + co];
-    __syncthreads();
-    float acc = b[co];
-    for (int t = 0; t < 5; ++t) {
-        const float *wt = w + (long long)t * F * F + co;
-        const float *it = in_s + t * F;
+    const int cg = threadIdx.x & 31, ks = threadIdx.x >> 5, per = K / KSL;
+    const float4 *wp = reinterpret_cast<const float4 *>(w) + (long long)(ks * per) * (F / 4) + cg;
+    const float *ip = s.in + ks * per;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
-        for (int ci = 0; ci < F; ++ci) acc = fmaf(__ldg(wt + (long long)ci * F), it[ci], acc);
+    for (int j = 0; j < per; ++j) {
+        const float4 wv = __ldg(wp + (long long)j * (F / 4));
+        const float x = ip[j];
+        acc.x = fmaf(wv.x, x, acc.x);
+        acc.y = fmaf(wv.y, x, acc.y);
+        acc.z = fmaf(wv.z, x, acc.z);
+        acc.w = fmaf(wv.w, x, acc.w);
+    }
+    *reinterpret_cast<float4 *>(s.part + ks * F + 4 * cg) = acc;
+    __syncthreads();
+    if (threadIdx.x < F) {
+        float v = b[threadIdx.x];
+#pragma unroll
+        for (int k = 0; k < KSL; ++k) v += s.part[k * F + threadIdx.x];
+        s.out[threadIdx.x] = v;
     }
     __syncthreads();
-    return acc;
 }
 
-__device__ __forceinline__ float dense_layer(const float *__restrict__ w, const float *__restrict__ b, float x, float *in_s, int co)
+// stage the five causal taps of a channel-last history plane around (h, w)
+__device__ __forceinline__ void stage_taps(const float *__restrict__ hist, int h, int wd, int Wp, Smem &s)
 {
-    in_s[co] = x;
+    for (int i = threadIdx.x; i < 5 * F; i += NT) {
+        const int t = i / F, ci = i - t * F;
+        s.in[i] = hist[((long long)(h + 1 + c_dy[t]) * Wp + (wd + 1 + c_dx[t])) * F + ci];
+    }
     __syncthreads();
-    float acc = b[co];
-#pragma unroll 8
-    for (int ci = 0; ci < F; ++ci) acc = fmaf(__ldg(w + (long long)ci * F + co), in_s[ci], acc);
-    __syncthreads();
-    return acc;
 }
 
 // parameters of coefficient (h, w) of plane `bi`; every thread returns the same (scale, mean)
-__device__ void coefficient(const Net &n, const Run &r, int bi, int h, int wd, float *in_s, float *red, float &scale, float &mean)
+__device__ void coefficient(const Net &n, const Run &r, int bi, int h, int wd, Smem &s, float &scale, float &mean)
 {
-    const int co = threadIdx.x, Hp = r.H + 2, Wp = r.W + 2;
+    const int tid = threadIdx.x, Hp = r.H + 2, Wp = r.W + 2;
     const float *Y = r.Y + (long long)bi * Hp * Wp;
-    // maskedConv1 (type A): the four causal neighbours of the reconstructed band
-    float t = n.b_in[co];
+    const long long plane = (long long)Hp * Wp * F, here = ((long long)(h + 1) * Wp + (wd + 1)) * F;
+    if (tid < F) {   // maskedConv1 (type A): the four causal neighbours of the reconstructed band
+        float t = n.b_in[tid];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) t = fmaf(__ldg(n.w_in + k * F + co), Y[(long long)(h + 1 + c_dy[k]) * Wp + (wd + 1 + c_dx[k])], t);
-    const float first = t;
-    const long long here = ((long long)(h + 1) * Wp + (wd + 1)) * F + co;
-    for (int k = 0; k < 2; ++k) {      // MaskResidual (context_fusion.py:30-41)
-        float *h1 = r.hist[2 * k] + (long long)bi * Hp * Wp * F, *h2 = r.hist[2 * k + 1] + (long long)bi * Hp * Wp * F;
-        h1[here] = t;
-        __syncthreads();
-        float u = lrelu(masked_layer(h1, n.w[2 * k], n.b[2 * k], h, wd, Wp, in_s, co));
-        h2[here] = u;
-        __syncthreads();
-        t = masked_layer(h2, n.w[2 * k + 1], n.b[2 * k + 1], h, wd, Wp, in_s, co) + t;
+        for (int k = 0; k < 4; ++k) t = fmaf(__ldg(n.w_in + k * F + tid), Y[(long long)(h + 1 + c_dy[k]) * Wp + (wd + 1 + c_dx[k])], t);
+        s.cur[tid] = s.first[tid] = t;
     }
-    t += first;
-    float *h5 = r.hist[4] + (long long)bi * Hp * Wp * F;
-    h5[here] = t;
     __syncthreads();
-    t = lrelu(masked_layer(h5, n.w[4], n.b[4], h, wd, Wp, in_s, co));
-    t = lrelu(dense_layer(n.w1[0], n.b1[0], t, in_s, co));
-    t = lrelu(dense_layer(n.w1[1], n.b1[1], t, in_s, co));
-    // convs.2: 128 -> 2, a fixed-order tree over the channels (identical on both sides)
-    red[co] = t * __ldg(n.w_out + co);
-    red[F + co] = t * __ldg(n.w_out + F + co);
+    for (int k = 0; k < 2; ++k) {      // MaskResidual (context_fusion.py:30-41)
+        float *h1 = r.hist[2 * k] + bi * plane, *h2 = r.hist[2 * k + 1] + bi * plane;
+        if (tid < F) h1[here + tid] = s.cur[tid];
+        __syncthreads();
+        stage_taps(h1, h, wd, Wp, s);
+        gemv(n.w[2 * k], n.b[2 * k], 5 * F, s);
+        if (tid < F) h2[here + tid] = lrelu(s.out[tid]);
+        __syncthreads();
+        stage_taps(h2, h, wd, Wp, s);
+        gemv(n.w[2 * k + 1], n.b[2 * k + 1], 5 * F, s);
+        if (tid < F) s.cur[tid] = s.out[tid] + s.cur[tid];
+        __syncthreads();
+    }
+    float *h5 = r.hist[4] + bi * plane;
+    if (tid < F) h5[here + tid] = s.cur[tid] + s.first[tid];
     __syncthreads();
-    for (int s = F / 2; s > 0; s >>= 1) {
-        if (co < s) {
-            red[co] += red[co + s];
-            red[F + co] += red[F + co + s];
+    stage_taps(h5, h, wd, Wp, s);
+    gemv(n.w[4], n.b[4], 5 * F, s);
+    for (int k = 0; k < 2; ++k) {      // convs.0, convs.1 (1x1) behind LeakyReLU
+        if (tid < F) s.in[tid] = lrelu(s.out[tid]);
+        __syncthreads();
+        gemv(n.w1[k], n.b1[k], F, s);
+    }
+    // convs.2: 128 -> 2 on lrelu(out), a fixed-order tree over the channels (identical on both sides)
+    if (tid < F) {
+        const float t = lrelu(s.out[tid]);
+        s.part[tid] = t * __ldg(n.w_out + tid);
+        s.part[F + tid] = t * __ldg(n.w_out + F + tid);
+    }
+    __syncthreads();
+    for (int st = F / 2; st > 0; st >>= 1) {
+        if (tid < st) {
+            s.part[tid] += s.part[tid + st];
+            s.part[F + tid] += s.part[F + tid + st];
         }
         __syncthreads();
     }
-    scale = red[0] + __ldg(n.b_out);
-    mean = red[F] + __ldg(n.b_out + 1);
+    scale = s.part[0] + __ldg(n.b_out);
+    mean = s.part[F] + __ldg(n.b_out + 1);
     __syncthreads();
 }
 
@@ -141,13 +171,13 @@ __device__ __forceinline__ short table_index(float scale, const Run &r)
 // encoder: the whole band of plane blockIdx.x in raster order
 __global__ void __launch_bounds__(NT) llar_encode_kernel(const Net n, const Run r)
 {
-    __shared__ float in_s[5 * F], red[2 * F];
+    __shared__ Smem s;
     const int bi = blockIdx.x, Wp = r.W + 2;
     float *Y = r.Y + (long long)bi * (r.H + 2) * Wp;
     for (int h = 0; h < r.H; ++h)
         for (int w = 0; w < r.W; ++w) {
             float scale, mean;
-            coefficient(n, r, bi, h, w, in_s, red, scale, mean);
+            coefficient(n, r, bi, h, w, s, scale, mean);
             if (threadIdx.x == 0) {
                 const long long p = (long long)bi * r.H * r.W + (long long)h * r.W + w;
                 const float sym = rintf(rintf(r.yq[p]) - mean);          // pWave.py:549-553: round(round(y) - mean)
@@ -162,7 +192,7 @@ __global__ void __launch_bounds__(NT) llar_encode_kernel(const Net n, const Run 
 // decoder: one coefficient; the previous coefficient's reconstruction arrives from the host
 __global__ void __launch_bounds__(NT) llar_decode_kernel(const Net n, const Run r)
 {
-    __shared__ float in_s[5 * F], red[2 * F];
+    __shared__ Smem s;
     const int bi = blockIdx.x, Wp = r.W + 2;
     float *Y = r.Y + (long long)bi * (r.H + 2) * Wp;
     if (r.pos > 0 && threadIdx.x == 0) {
@@ -171,7 +201,7 @@ __global__ void __launch_bounds__(NT) llar_decode_kernel(const Net n, const Run 
     }
     __syncthreads();
     float scale, mean;
-    coefficient(n, r, bi, r.pos / r.W, r.pos % r.W, in_s, red, scale, mean);
+    coefficient(n, r, bi, r.pos / r.W, r.pos % r.W, s, scale, mean);
     if (threadIdx.x == 0) {
         r.out_mean[bi] = mean;
         r.out_idx[bi] = table_index(scale, r);
