@@ -14,6 +14,6 @@ ncu --set full --clock-control none --import-source on -k regex:lift_step_tc -c 
 # secondary rows (section 8f): four-step network + SpyNet evidence; every ncu run is bounded (-c)
 bash tools/prof_ctx.sh ${tag}
 python tools/bench_spynet.py > gpurun_out/${tag}_spynet_bench.json 2>> gpurun_out/${tag}_bench.err && \
-ncu --set full --clock-control none --import-source on -k regex:pair_conv_kernel -s 10 -c 3 -f -o gpurun_out/${tag}_pair_conv python tools/bench_spynet.py > gpurun_out/${tag}_ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:pair_conv_kernel -s 25 -c 5 -f -o gpurun_out/${tag}_pair_conv python tools/bench_spynet.py > gpurun_out/${tag}_ncu3.log 2>&1
 python -c "
 import json; d=json.load(open('gpurun_out/${tag}_bench.json')); print('frames/s', d['value'], 'e2e', d['e2e']['value'], 'frac', d['roofline']['frac'], 'cpu', d['cpu_baseline']['value'])"

@@ -34,7 +34,7 @@ if [ -f gpurun_out/${tag}_pair_conv.ncu-rep ]; then
 {
 echo "# ncu --set full --clock-control none --import-source on ($tag): pair_conv_kernel (csrc/pmctf_pairconv.cu), the run-time-shaped CTA-pair"
 echo "# convolution, on SpyNet's 7x7 layers at the finest pyramid level of a 1080p pair (1 x 1152 x 1920; python tools/bench_spynet.py, launches"
-echo "# 11-13 of the kernel = three consecutive layers of one level).  N <= 64 output channels per layer: the MMAs (M = 256, N = 16..64, K = 16) are"
+echo "# 26-30 of the kernel = the five layers 8->32->64->32->16->2 of the finest level).  N <= 64 output channels per layer: the MMAs (M = 256, N = 16..64, K = 16) are"
 echo "# bounded by the A-operand fetch from shared memory, not by the tensor pipe; the 8 -> 32 layer pads K from 8 to 16."
 echo
 python tools/summarize_ncu.py full gpurun_out/${tag}_pair_conv.ncu-rep
