@@ -582,17 +582,22 @@ def run_uvg(args, pkg, G, par, model, dev, rank, world):
     e0.record()
     local = [one(it) for it in mine]
     local = torch.stack(local) if local else torch.zeros((0, GOP, G.N_STATS), dtype=torch.float64, device=dev)
+    em = torch.cuda.Event(enable_timing=True)
+    em.record()
     allst = par.gather_stats(local, len(items), rank, world)          # the ONE collective of the run
     e1.record()
     barrier()
     pkg.ops.check_tc_error(dev, "uvg workload")
     ms = par.max_over_ranks(e0.elapsed_time(e1), dev)
+    local_ms = e0.elapsed_time(em)                                    # this rank's own items, before it waits for anybody
+    local_max, local_min = par.max_over_ranks(local_ms, dev), -par.max_over_ranks(-local_ms, dev)
     cap = par.max_items_per_rank(len(items), world)
     psnr = allst[:, :, 6]
     return {"workload": f"configs[3]: {n_seq} synthetic 1080p sequences x {FRAMES} frames, GOP-16, q_index {q_list} flattened into "
                         f"{len(items)} items (q, sequence, gop), round-robin over {world} GPU(s), one gather of [items,16,{G.N_STATS}] fp64 at the end",
             "frames_per_s": len(items) * GOP / (ms * 1e-3), "unit": "frames/s", "scaling": "strong", "seconds": ms * 1e-3,
             "items": len(items), "items_max_per_rank": cap, "load_balance": len(items) / (world * cap),
+            "rank_compute_seconds_max_min": [local_max * 1e-3, local_min * 1e-3],
             "mean_psnr_yuv_db_by_q_index": {str(q): float(psnr[[i for i, it in enumerate(items) if it[0] == q]][torch.isfinite(
                 psnr[[i for i, it in enumerate(items) if it[0] == q]])].mean()) for q in q_list}}
 
