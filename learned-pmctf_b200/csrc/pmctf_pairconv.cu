@@ -26,13 +26,13 @@ namespace pmctf {
 namespace pair {
 
 constexpr int TH = 4, P = 32;                         // output rows per CTA tile; pixel pitch of the staged input
-constexpr int N_IN = 2, N_ACC = 4, ACC_STRIDE = 128;
+constexpr int N_IN = 2, MAX_DEPTH = 8, N_ACC = 4, ACC_STRIDE = 128;   // N_IN full-size tiles of room = up to MAX_DEPTH smaller ones
 constexpr int MAX_W = 100352;                         // bytes of resident weights per CTA
 constexpr int MAX_IN = 40960;                         // bytes of one staged tile (8 planes x 10 rows x 32 records x 16 B)
 constexpr int SM_W = 0;
 constexpr int SM_IN = SM_W + MAX_W;
 constexpr int SM_BAR = SM_IN + N_IN * MAX_IN;
-constexpr int SM_BIAS = SM_BAR + 128;
+constexpr int SM_BIAS = SM_BAR + 256;                 // barriers: in_full[8], in_empty[8], acc_full[4], acc_empty[4], weights, peer weights
 constexpr int SMEM_BYTES = SM_BIAS + 128 * 4;
 static_assert(SM_IN % 128 == 0 && MAX_IN % 128 == 0 && SM_BAR % 8 == 0 && SMEM_BYTES <= 227 * 1024, "shared memory");
 constexpr int EPI_SETS = 2, EPI_WARPS = 4 * EPI_SETS;
@@ -119,6 +119,25 @@ __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst_saddr, const CUten
         : "memory");
 }
 
+// The MMAs of one tile pair, issued by ONE thread.  That thread executes a dependent instruction every ~4 cycles, so the descriptor
+// arithmetic per MMA must stay at a handful of instructions or the issue loop, not the tensor pipe, paces the layer (measured: 132
+// cycles per MMA with run-time loops over taps and k-steps, against 16 cycles of math).  With the filter size and the k-step count as
+// template parameters every A-descriptor offset is an immediate; the B descriptor advances by one run-time stride per MMA.
+template <int KS, int KSTEPS>
+__device__ __forceinline__ void issue_tile(uint32_t d, uint64_t a0, uint64_t bd, uint64_t b_step, uint32_t idesc)
+{
+    constexpr int PLANE16 = (TH + KS - 1) * P;   // plane size in 16-byte units
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                mma_bf16_pair(d, a0 + (uint64_t)(ky * P + kx + 2 * ks * PLANE16), bd, idesc, (ky | kx | ks) ? 1u : 0u);
+                bd += b_step;
+            }
+}
+
 struct ConvD {
     const uint8_t *wimg;          // [rank][tap][k-step][chunk][cout_pad / 2 rows][8 ci] bf16
     const float *bias;            // [cout]
@@ -128,6 +147,7 @@ struct ConvD {
     float slope;                  // LeakyReLU slope applied before the stores (0 = ReLU, 1 = identity)
     int n, h, w;
     int ks, planes, cout, cout_pad;   // filter size (1, 3, 7), input planes of 8 channels (even), real / padded output channels
+    int depth;                        // input ring depth: as many staged tiles as fit the room of N_IN full-size ones (2 .. 8)
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
@@ -135,7 +155,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_BAR + 120);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_BAR + 248);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t rank = cluster_ctarank();
@@ -148,10 +168,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
     const int n_pairs = (n_tiles + 1) >> 1;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
-    const uint32_t in_full = umma::smem_u32(bars), in_empty = umma::smem_u32(bars + 2), acc_full = umma::smem_u32(bars + 4),
-                   acc_empty = umma::smem_u32(bars + 8), w_bar = umma::smem_u32(bars + 12), wpeer_bar = umma::smem_u32(bars + 13);
+    const uint32_t in_full = umma::smem_u32(bars), in_empty = umma::smem_u32(bars + 8), acc_full = umma::smem_u32(bars + 16),
+                   acc_empty = umma::smem_u32(bars + 20), w_bar = umma::smem_u32(bars + 24), wpeer_bar = umma::smem_u32(bars + 25);
+    const int depth = a.depth;
     if (tid == 0) {
-        for (int i = 0; i < N_IN; ++i) {
+        for (int i = 0; i < MAX_DEPTH; ++i) {
             umma::mbar_init(in_full + 8 * i, 1);
             umma::mbar_init(in_empty + 8 * i, 1);
         }
@@ -178,9 +199,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
         if (lane == 0) {
             int it = 0;
             for (int tp = cluster_id; tp < n_pairs; tp += n_clusters, ++it) {
-                const int buf = it & 1;
-                if (it >= N_IN) {
-                    ok = umma::mbar_wait(in_empty + 8 * buf, (uint32_t)((it >> 1) - 1) & 1u);
+                const int buf = it % depth, use = it / depth;
+                if (use > 0) {   // the MMAs that read this buffer `depth` tiles ago have completed (multicast commit)
+                    ok = umma::mbar_wait(in_empty + 8 * buf, (uint32_t)(use - 1) & 1u);
                     if (!ok) break;
                 }
                 int tile = 2 * tp + (int)rank;
@@ -188,7 +209,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
                 const int n = tile / (tiles_x * tiles_y), trem = tile - n * (tiles_x * tiles_y);
                 const int ty = trem / tiles_x, y0 = ty * TH, x0 = (trem - ty * tiles_x) * TW;
                 if (leader) umma::mbar_expect_tx(in_full + 8 * buf, 2u * (uint32_t)inbuf);
-                tma_load_4d_pair(umma::smem_u32(smem + SM_IN + buf * MAX_IN), &tmap, mapa(in_full + 8 * buf, 0), 0, x0 - pad, y0 - pad,
+                tma_load_4d_pair(umma::smem_u32(smem + SM_IN + buf * inbuf), &tmap, mapa(in_full + 8 * buf, 0), 0, x0 - pad, y0 - pad,
                                  n * a.planes);
             }
         }
@@ -202,8 +223,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
             const uint32_t idesc = idesc_bf16_m256((uint32_t)a.cout_pad);
             int it = 0;
             for (int tp = cluster_id; ok && tp < n_pairs; tp += n_clusters, ++it) {
-                const int buf = it & 1, abuf = it & (N_ACC - 1);
-                ok = __shfl_sync(0xffffffffu, (int)mbar_wait_cluster(in_full + 8 * buf, (uint32_t)(it >> 1) & 1u), 0) != 0;
+                const int buf = it % depth, abuf = it & (N_ACC - 1);
+                ok = __shfl_sync(0xffffffffu, (int)mbar_wait_cluster(in_full + 8 * buf, (uint32_t)(it / depth) & 1u), 0) != 0;
                 if (!ok) break;
                 if (it >= N_ACC) {
                     ok = __shfl_sync(0xffffffffu, (int)mbar_wait_cluster(acc_empty + 8 * abuf, (uint32_t)((it >> 2) - 1) & 1u), 0) != 0;
@@ -211,23 +232,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
                 }
                 umma::fence_after_sync();
                 if (umma::elect_one()) {
-                    const uint64_t a0 = umma::smem_desc(umma::smem_u32(smem + SM_IN + buf * MAX_IN), (uint32_t)plane_bytes, 128);
+                    const uint64_t a0 = umma::smem_desc(umma::smem_u32(smem + SM_IN + buf * inbuf), (uint32_t)plane_bytes, 128);
                     const uint64_t b0 = umma::smem_desc(umma::smem_u32(smem + SM_W), (uint32_t)(nhalf * 16), 128);
                     const uint32_t d = tbase + abuf * ACC_STRIDE;
                     const uint64_t a_kstep = (uint64_t)(2 * (plane_bytes >> 4)), b_step = (uint64_t)(wslab >> 4);
-                    uint64_t bd = b0;
-                    uint32_t acc = 0u;
-                    for (int ky = 0; ky < a.ks; ++ky)
-                        for (int kx = 0; kx < a.ks; ++kx) {
-                            uint64_t ad = a0 + (uint64_t)(ky * P + kx);
-#pragma unroll 4
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                mma_bf16_pair(d, ad, bd, idesc, acc);
-                                acc = 1u;
-                                ad += a_kstep;
-                                bd += b_step;
+                    const int shape = a.ks * 8 + ksteps;
+                    if (shape == 7 * 8 + 1) issue_tile<7, 1>(d, a0, b0, b_step, idesc);
+                    else if (shape == 7 * 8 + 2) issue_tile<7, 2>(d, a0, b0, b_step, idesc);
+                    else if (shape == 7 * 8 + 4) issue_tile<7, 4>(d, a0, b0, b_step, idesc);
+                    else if (shape == 3 * 8 + 1) issue_tile<3, 1>(d, a0, b0, b_step, idesc);
+                    else if (shape == 3 * 8 + 2) issue_tile<3, 2>(d, a0, b0, b_step, idesc);
+                    else if (shape == 3 * 8 + 4) issue_tile<3, 4>(d, a0, b0, b_step, idesc);
+                    else {   // any other (k, channels) combination: run-time loops
+                        uint64_t bd = b0;
+                        uint32_t acc = 0u;
+                        for (int ky = 0; ky < a.ks; ++ky)
+                            for (int kx = 0; kx < a.ks; ++kx) {
+                                uint64_t ad = a0 + (uint64_t)(ky * P + kx);
+                                for (int ks = 0; ks < ksteps; ++ks) {
+                                    mma_bf16_pair(d, ad, bd, idesc, acc);
+                                    acc = 1u;
+                                    ad += a_kstep;
+                                    bd += b_step;
+                                }
                             }
-                        }
+                    }
                     commit_pair(in_empty + 8 * buf);
                     commit_pair(acc_full + 8 * abuf);
                 }
@@ -486,6 +515,9 @@ int pmctf_pair_conv(const void *in_bf16, const void *packed_w, const float *bias
     pair::ConvD d;
     d.wimg = (const uint8_t *)packed_w; d.bias = bias; d.out_bf16 = (__nv_bfloat16 *)out_bf16; d.out_nchw = out_nchw; d.add_nchw = add_nchw;
     d.slope = slope; d.n = N; d.h = H; d.w = W; d.ks = ks; d.planes = planes; d.cout = cout; d.cout_pad = cout_pad;
+    const int inbuf = planes * (pair::TH + ks - 1) * pair::P * 16;
+    d.depth = pair::N_IN * pair::MAX_IN / inbuf;   // small input tiles (few channels) get a deeper ring: the TMA latency, not the MMAs, paces them
+    if (d.depth > pair::MAX_DEPTH) d.depth = pair::MAX_DEPTH;
     pair::pair_conv_kernel<<<grid, pair::NT, pair::SMEM_BYTES, (cudaStream_t)stream>>>(map, d, derr);
     count_launch();
     return (int)cudaGetLastError();
