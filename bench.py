@@ -523,23 +523,13 @@ def run_full_codec(pkg, dev):
         ry, rc, bits = m.code_gop_forward(ys, cs, q_index=12)
         e1.record()
         torch.cuda.synchronize(dev)
-        m.code_gop_forward(ys[:4], cs[:4], q_index=12, batched=True)
-        torch.cuda.synchronize(dev)
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        m.code_gop_forward(ys, cs, q_index=12, batched=True)
-        b1.record()
-        torch.cuda.synchronize(dev)
     pkg.ops.check_tc_error(dev, "full codec block")
     ms = e0.elapsed_time(e1)
-    ms_b = b0.elapsed_time(b1)
+
     return {"what": "pMCTF(motion=True, entropy_model=True).code_gop_forward: the reference's GOP loop (encode_one_stage per pair: SpyNet, MV codec, "
                     "forward_MCTF, hp / lp pWave.forward with the four-step entropy-parameter networks, ConvLSTM context, LL model, PostProcess, for "
                     "luma and chroma; inverse_MCTF) on one 1080p 4:2:0 GOP-16, random weights, rate-estimate path",
             "ms_per_gop": ms, "frames_per_s": GOP / (ms * 1e-3), "bits_per_frame_estimate": sum(bits) / GOP,
-            "batched": {"ms_per_gop": ms_b, "frames_per_s": GOP / (ms_b * 1e-3),
-                        "what": "same results with the H frames of a temporal stage coded as one batch per pWave.forward call (8 / 4 / 2 / 1 luma and "
-                                "16 / 8 / 4 / 2 chroma planes)"},
             "on_our_kernels": "lifting, SpyNet, four-step networks, PostProcess; stock torch ops: MV codec, ConvLSTM context, LL model, rate estimate"}
 
 

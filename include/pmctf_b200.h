@@ -391,6 +391,13 @@ int pmctf_spynet_prep(const float *im1, const float *im2, const float *flow, flo
 /* F.avg_pool2d(x, 2, 2) on `planes` planes of H x W (the image pyramid, video_net.py:104-106) */
 int pmctf_avgpool2(const float *in, float *out, long long planes, int H, int W, void *stream);
 
+/* Element-wise glue of the coder, one pass each.  pmctf_lstm_gates: the ConvLSTM cell of the long-term context behind its two
+ * convolutions (pMCTF/layers/long_context.py:16-34): a = a_in + a_hid, s = sigmoid(a), c_out = s c + s tanh(a), h_out = s tanh(c_out).
+ * pmctf_laplace_bits: CompressionModel.get_y_laplace_bits (pMCTF/entropy_models/gaussian_model.py:37-55): per-element
+ * max(-log2(cdf(y + .5) - cdf(y - .5) + 1e-5), 0) of a zero-mean Laplace with scale clamp(sigma, 1e-5, 1e10). */
+int pmctf_lstm_gates(const float *a_in, const float *a_hid, const float *c, float *h_out, float *c_out, long long n, void *stream);
+int pmctf_laplace_bits(const float *y, const float *sigma, float *bits, long long n, void *stream);
+
 /* ---- entropy-coder boundary ----------------------------------------------------------------
  * HOST functions (plain host pointers, no stream): the 64-bit rANS coder of pMCTF/cpp/rans/rans.cpp:76-168,272-331 behind the
  * sub-stream container of pMCTF/cpp/py_rans/py_rans.cpp:22-225 (what the reference binds as MLCodec_rans.RansEncoder /

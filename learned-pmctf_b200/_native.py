@@ -129,6 +129,8 @@ SIGNATURES = {
     "pmctf_ctx_lower_subband": [_P, _P, _P, _P, _I, _I, _I, _P],
     "pmctf_ctx_dcb_tail": [_P, _P, C.POINTER(CtxDcb), _P, _P, _I, _I, _I, _P],
     "pmctf_ctx_head": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "pmctf_lstm_gates": [_P, _P, _P, _P, _P, _LL, _P],
+    "pmctf_laplace_bits": [_P, _P, _P, _LL, _P],
     "pmctf_ctx_mask_step": [C.POINTER(CtxStep), _P],
     "pmctf_llar_pack": [_P, _I, _I, _P, _P],
     "pmctf_llar_encode": [C.POINTER(LLar), _P, _P, _P, _P],

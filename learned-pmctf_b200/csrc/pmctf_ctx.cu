@@ -681,6 +681,35 @@ __global__ void __launch_bounds__(256) ctx_mask_step_kernel(const StepD d)
     }
 }
 
+// ---- element-wise glue of the coder around the networks, one pass each instead of 8 / 25 ATen launches per subband ---------------
+// ConvLSTM cell behind its two convolutions (long_context.py:16-34): a = conv_in(x) + conv_hidden(h); all three gates are sigmoid(a),
+// the candidate is tanh(a): c' = s c + s tanh(a), h' = s tanh(c')
+__global__ void __launch_bounds__(256) lstm_gates_kernel(const float *__restrict__ a_in, const float *__restrict__ a_hid, const float *__restrict__ c,
+                                                         float *__restrict__ h_out, float *__restrict__ c_out, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float a = __ldg(a_in + i) + __ldg(a_hid + i);
+        const float s = 1.0f / (1.0f + expf(-a));
+        const float cn = s * __ldg(c + i) + s * tanhf(a);
+        c_out[i] = cn;
+        h_out[i] = s * tanhf(cn);
+    }
+}
+// rate estimate of a band (gaussian_model.py:37-55 with torch.distributions.Laplace.cdf): P = cdf(y + .5) - cdf(y - .5),
+// cdf(v) = .5 - .5 sign(v) expm1(-|v| / b), b = clamp(sigma, 1e-5, 1e10); bits = max(-log2(P + 1e-5), 0)
+__global__ void __launch_bounds__(256) laplace_bits_kernel(const float *__restrict__ y, const float *__restrict__ sigma, float *__restrict__ bits,
+                                                           long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float b = fminf(fmaxf(__ldg(sigma + i), 1e-5f), 1e10f), v = __ldg(y + i);
+        const float hi = v + 0.5f, lo = v - 0.5f;
+        const float shi = (hi > 0.0f) - (hi < 0.0f), slo = (lo > 0.0f) - (lo < 0.0f);
+        const float chi = 0.5f - 0.5f * shi * expm1f(-fabsf(hi) / b), clo = 0.5f - 0.5f * slo * expm1f(-fabsf(lo) / b);
+        const float t = -1.0f * logf((chi - clo) + 1e-5f) / 0.6931471805599453f;
+        bits[i] = fmaxf(t, 0.0f);
+    }
+}
+
 } // namespace ctx
 
 int tc_watchdog(volatile int **host, int **dev);   // pmctf_kernels.cu
@@ -847,6 +876,24 @@ int pmctf_ctx_head(const float *feat, const float *w, const float *b, float *sca
 {
     if (!feat || !w || !b || !scales || !means || N <= 0 || H <= 0 || W <= 0) return PMCTF_EINVAL;
     ctx::ctx_head_kernel<<<small_grid((long long)N * H * W, 256), 256, 0, (cudaStream_t)stream>>>(feat, w, b, scales, means, N, H, W);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int pmctf_lstm_gates(const float *a_in, const float *a_hid, const float *c, float *h_out, float *c_out, long long n, void *stream)
+{
+    if (n == 0) return 0;
+    if (!a_in || !a_hid || !c || !h_out || !c_out || n < 0) return PMCTF_EINVAL;
+    ctx::lstm_gates_kernel<<<small_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(a_in, a_hid, c, h_out, c_out, n);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int pmctf_laplace_bits(const float *y, const float *sigma, float *bits, long long n, void *stream)
+{
+    if (n == 0) return 0;
+    if (!y || !sigma || !bits || n < 0) return PMCTF_EINVAL;
+    ctx::laplace_bits_kernel<<<small_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(y, sigma, bits, n);
     count_launch();
     return (int)cudaGetLastError();
 }

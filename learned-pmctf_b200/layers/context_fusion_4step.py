@@ -109,6 +109,13 @@ def release_workspaces():
     _WS_CACHE.clear()
 
 
+_GRAPHS_ON = os.environ.get("PMCTF_CTX_GRAPHS", "1") != "0"
+
+
+class _GraphUnavailable(Exception):
+    pass
+
+
 class ContextFusionFourStep(nn.Module):
     def __init__(self, in_channels=1, ctx_channels=1, num_features=NUM_FEATURES, num_parameters=2, ctx=True, lossy=True,
                  lower_subband=True):
@@ -139,6 +146,8 @@ class ContextFusionFourStep(nn.Module):
         st = dict(self.__dict__)
         st["_key"], st["_packed"] = None, None
         st.pop("_pack_hot", None)
+        st.pop("_graphs", None)
+        st.pop("_ws_hot", None)
         return st
 
     def _load_from_state_dict(self, *args, **kwargs):
@@ -318,7 +327,18 @@ class ContextFusionFourStep(nn.Module):
 
     def _run(self, x, context, prev_subband, stage=None, dec=None):
         """The four steps on the GPU.  Encoder: x given; decoder: dec(k, scales_masked_idx16) -> int16 symbols of step k.
-        stage: optional list that receives (sym16, idx16) device tensors per step (compress)."""
+        stage: optional list that receives (sym16, idx16) device tensors per step (compress).
+        The encoder form (about 37 launches of our own kernels, none of them data dependent) is captured ONCE per (shape, weights,
+        stream) into a CUDA graph and replayed: the module is launch-bound on the host otherwise (the whole pWave.forward spent
+        48 ms enqueueing 32 ms of GPU work).  PMCTF_CTX_GRAPHS=0 keeps every launch eager."""
+        if dec is None and x is not None and _GRAPHS_ON and x.is_cuda and not torch.cuda.is_current_stream_capturing():
+            try:
+                return self._run_graphed(x, context, prev_subband, stage)
+            except _GraphUnavailable:
+                pass
+        return self._run_eager(x, context, prev_subband, stage, dec)
+
+    def _run_eager(self, x, context, prev_subband, stage=None, dec=None):
         self.__dict__["_pack_hot"] = None
         self.__dict__["_pack_hot"] = self._pack()
         try:
@@ -326,7 +346,56 @@ class ContextFusionFourStep(nn.Module):
         finally:
             self.__dict__["_pack_hot"] = None
 
+    def _run_graphed(self, x, context, prev_subband, stage):
+        x = ops._chk(x, "x", 4).contiguous()
+        context = ops._chk(context, "context", 4).contiguous()
+        if prev_subband is not None:
+            prev_subband = ops._chk(prev_subband, "prev_subband", 4).contiguous()
+        dev = x.device
+        stream = torch.cuda.current_stream(dev)
+        _, offs = self._pack()
+        key = (tuple(x.shape), prev_subband is not None, stage is not None, str(dev), stream.cuda_stream, self._key)
+        graphs = self.__dict__.setdefault("_graphs", collections.OrderedDict())
+        ent = graphs.get(key)
+        if ent is None:
+            if self.__dict__.get("_graph_failed"):
+                raise _GraphUnavailable()
+            N, _, H, W = x.shape
+            self._run_eager(x, context, prev_subband, [] if stage is not None else None)     # warm: kernel attributes, packed weights
+            ws = _shared_workspace(N, H, W, dev)                                              # shared, allocated outside the capture
+            sx, sc = x.clone(), context.clone()
+            sp = prev_subband.clone() if prev_subband is not None else None
+            st = [] if stage is not None else None
+            g = torch.cuda.CUDAGraph()
+            self.__dict__["_ws_hot"] = ws
+            try:
+                with torch.cuda.graph(g):
+                    run, _ = self._run_eager(sx, sc, sp, st)
+            except Exception:
+                self.__dict__["_graph_failed"] = True
+                raise _GraphUnavailable()
+            finally:
+                self.__dict__["_ws_hot"] = None
+            while len(graphs) >= 12:
+                graphs.popitem(last=False)
+            ent = graphs[key] = (g, sx, sc, sp, run, st, ws)
+        else:
+            graphs.move_to_end(key)
+        g, sx, sc, sp, run, st, _ws = ent
+        sx.copy_(x)
+        sc.copy_(context)
+        if sp is not None:
+            sp.copy_(prev_subband)
+        g.replay()
+        out = {k: v.clone() for k, v in run.items()}      # the graph owns its outputs: hand copies to the caller
+        if stage is not None:
+            stage.extend((a.clone(), b.clone()) for a, b in st)
+        return out, None
+
     def _workspace(self, N, H, W, dev):
+        hot = self.__dict__.get("_ws_hot")
+        if hot is not None:
+            return hot
         return _shared_workspace(N, H, W, dev)
 
     def _run_steps(self, x, context, prev_subband, stage=None, dec=None):

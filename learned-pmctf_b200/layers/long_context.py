@@ -20,6 +20,15 @@ class LSTM2D(nn.Module):
         self.conv_hidden = nn.Conv2d(hidden_size, hidden_size, 3, padding=1)
 
     def forward(self, x, hidden, cell_state):
+        if x.is_cuda and not torch.is_grad_enabled():      # the gate arithmetic as one kernel instead of eight ATen launches
+            from .. import _native as nat
+            from .. import ops
+            a_in, a_hid = self.conv_in(x).contiguous(), self.conv_hidden(hidden).contiguous()
+            c = cell_state.expand_as(a_in).contiguous()    # the cell state of the last cell broadcasts (long_context.py:165-169)
+            h_out, c_out = torch.empty_like(a_in), torch.empty_like(a_in)
+            ops._launch(x.device, "lstm_gates", nat.lib().pmctf_lstm_gates, a_in.data_ptr(), a_hid.data_ptr(), c.data_ptr(), h_out.data_ptr(),
+                        c_out.data_ptr(), a_in.numel())
+            return h_out, c_out
         a = self.conv_in(x) + self.conv_hidden(hidden)
         gate = torch.sigmoid(a)
         cell_state = gate * cell_state + gate * torch.tanh(a)

@@ -139,3 +139,28 @@ def test_ll_sequential_kernel_vs_torch_form(conv_mode):
     dec = em.entropy_coder.decoder
     back = net.ar_decode([B, 1, H, W], lambda i: dec.decode_stream(i, cdf, ln, off), dev)
     assert torch.equal(back, ll_hat)
+
+
+@pytest.mark.gpu
+def test_fused_glue_kernels_equal_torch_formulas(conv_mode):
+    """ConvLSTM gate kernel and Laplace rate kernel against the torch compositions they replace."""
+    if conv_mode != "tensor":
+        pytest.skip("independent of the lifting arithmetic")
+    from learned_pmctf_b200.entropy_models.gaussian_model import CompressionModel
+    from learned_pmctf_b200.layers.long_context import LSTM2D
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    cell = LSTM2D(1, 32).to(dev)
+    x, h, c = torch.randn(2, 1, 20, 30, device=dev), torch.randn(2, 32, 20, 30, device=dev), torch.randn(2, 32, 20, 30, device=dev)
+    with torch.no_grad():
+        h1, c1 = cell(x, h, c)
+    with torch.enable_grad():
+        h2, c2 = cell(x, h, c)
+    assert (h1 - h2).abs().max().item() < 1e-5 and (c1 - c2).abs().max().item() < 1e-5
+    em = CompressionModel("laplace")
+    y = torch.round(torch.randn(2, 1, 40, 50, device=dev) * 5)
+    s = torch.rand(2, 1, 40, 50, device=dev) * 4 - 0.2            # includes non-positive scales (clamped to 1e-5)
+    with torch.no_grad():
+        got = em.get_y_laplace_bits(y, s)
+    want = CompressionModel._interval_bits(torch.distributions.laplace.Laplace, y, s)
+    assert (got - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item())
