@@ -81,7 +81,7 @@ class pWaveTransform:
                     return val
             val = float(q.detach().reshape(()).to("cpu"))
             cache.append((q, q._version, val))
-            if len(cache) > 8:
+            if len(cache) > 32:
                 del cache[0]
             return val
         return float(q)
@@ -149,12 +149,27 @@ class pWaveTransform:
         return ops.quantize(s, 1.0, self.clip_value, self.lossy, do_round=self.lossy)
 
     def q_pair(self, q_index=None, qp_scale=None):
-        """(q, q_ll) as the reference derives them in forward/compress (pWave.py:231-238,383-392)."""
+        """(q, q_ll) as the reference derives them in forward/compress (pWave.py:231-238,383-392).  Outside autograd the pair is
+        cached per (q_index, qp_scale tensor, parameter versions) and the SAME tensor objects are handed out again, so that the
+        one device -> host read of their values (_q_float) happens once, not once per coded plane."""
         if q_index is None:
             return self.QP[-1], self.QP_ll[-1]
+        cacheable = not torch.is_grad_enabled() and not isinstance(q_index, list)
+        if cacheable:
+            cache = self.__dict__.setdefault("_qpair_cache", {})
+            key = (q_index, id(qp_scale) if isinstance(qp_scale, torch.Tensor) else qp_scale,
+                   qp_scale._version if isinstance(qp_scale, torch.Tensor) else None, self.QP.data_ptr(), self.QP._version,
+                   self.QP_ll.data_ptr(), self.QP_ll._version)
+            hit = cache.get(key)
+            if hit is not None:
+                return hit[0], hit[1]
         q, qll = self.get_curr_q(self.QP, q_index), self.get_curr_q(self.QP_ll, q_index)
         if qp_scale is not None:
             q, qll = q * qp_scale, qll * qp_scale
+        if cacheable:
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = (q, qll, qp_scale)      # qp_scale kept alive: its id is part of the key
         return q, qll
 
     def quantize_subband(self, subband, q_scale):

@@ -46,7 +46,16 @@ class MCTFMixin:
         """Temporal-layer-adaptive step scaling (pMCTF_L.py:343-347,404-408)."""
         if not self.quant_stage:
             return None
-        return self.get_curr_q(self.hp_q_scale[stage_idx], q_index)
+        p = self.hp_q_scale[stage_idx]
+        if torch.is_grad_enabled() or isinstance(q_index, list):
+            return self.get_curr_q(p, q_index)
+        cache = self.__dict__.setdefault("_hpq_cache", {})     # the same tensor object per (stage, q_index, parameter version): see pWave.q_pair
+        key = (stage_idx, q_index, p.data_ptr(), p._version)
+        if key not in cache:
+            if len(cache) > 128:
+                cache.clear()
+            cache[key] = self.get_curr_q(p, q_index)
+        return cache[key]
 
     @staticmethod
     def mse(x, y):
@@ -72,7 +81,7 @@ class MCTFMixin:
             ref_mv = {"mv_feature": None, "mv_y_hat": None}
             mv_hat = bilineardownsacling(mv_hat) / 2                      # pMCTF_L.py:336
         L_t, H_t, pred_frame, inv_pred_frame = self.forward_MCTF(ref_frame, cur_frame, mv_hat, stage_idx)
-        qp_scale = self.get_curr_q(self.hp_q_scale[stage_idx], q_index) if self.quant_stage else None
+        qp_scale = self.hp_qp_scale(stage_idx, q_index)
         res_H = self.hp_coder.forward(H_t, q_index, qp_scale=qp_scale)
         coded_mv = bpp_mv_z is not None
         ret = {"bpp_mv_y": bpp_mv_y, "bpp_mv_z": bpp_mv_z, "bpp_me": bpp_mv_z + bpp_mv_y if coded_mv else None,
