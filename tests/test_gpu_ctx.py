@@ -113,9 +113,20 @@ def test_four_step_vs_oracle_and_reference(tag, golden, conv_mode, capsys):
     d_scale = np.abs(s_hat.cpu().numpy() - o_s)
     n = x_q.numel()
     flips = int((x_q.cpu().numpy() != g[f"{tag}.x_q"]).sum())
+    # the same module on stock torch ops of this GPU, in the two arithmetics the reference itself can run in (cuDNN TF32 is its
+    # default on a GPU): how many final symbols THEY flip against the reference's CPU fp32 run
+    other = {}
+    for name, tf32 in (("cuDNN TF32", True), ("cuDNN fp32", False)):
+        keep = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        with torch.no_grad():
+            tq = m._forward_torch(x, context, prev, False)[1]
+        torch.backends.cudnn.allow_tf32 = keep
+        other[name] = int((tq.cpu().numpy() != g[f"{tag}.x_q"]).sum())
     with capsys.disabled():
         print(f"\n[ctx4 {tag}] bf16 tensor-core path vs fp32 oracle: |d mean| max {d_mean.max():.4f} mean {d_mean.mean():.5f}; "
-              f"|d scale| max {d_scale.max():.4f}; final symbols differing from the reference: {flips} of {n}")
+              f"|d scale| max {d_scale.max():.4f}; final symbols differing from the reference: {flips} of {n} "
+              f"(stock torch on this GPU: " + ", ".join(f"{k} {v}" for k, v in other.items()) + ")")
     # bf16 operands through 22 layers with activations up to ~8; a flipped symbol of an early step changes x_hat_so_far by 1 there
     # and with it the later steps' parameters in its neighbourhood, so the bound is on the bulk, the maximum is only reported
     assert d_mean.mean() < 0.01 and np.percentile(d_mean, 99) < 0.06 and d_scale.mean() < 0.01 and np.percentile(d_scale, 99) < 0.06
