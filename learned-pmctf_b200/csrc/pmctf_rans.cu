@@ -159,9 +159,9 @@ static int queue_symbols(std::vector<Interval> &q, const int16_t *sym, const int
 }
 
 // rans.cpp:141-168: the queue is coded last-in first-out so the decoder reads the symbols in their original order
-static void code_queue(std::vector<Interval> &q, std::vector<uint8_t> &bytes)
+static void code_queue(std::vector<Interval> &q, std::vector<uint8_t> &bytes, std::vector<uint32_t> &words)
 {
-    std::vector<uint32_t> words(q.size() + 2);
+    if (words.size() < q.size() + 2) words.resize(q.size() + 2);   // grow-only scratch of the sub-encoder: no fresh pages per flush
     Writer w;
     w.p = words.data() + words.size();
     for (size_t i = q.size(); i-- > 0;) {
@@ -218,6 +218,7 @@ public:
     }
     std::vector<Interval> queue;
     std::vector<uint8_t> bytes;
+    std::vector<uint32_t> words;
     int error = 0;
 
 private:
@@ -437,7 +438,7 @@ int pmctf_rans_encoder_flush(void *enc)
     if (!enc) return PMCTF_EINVAL;
     for (auto &p : static_cast<Encoder *>(enc)->parts) {
         SubEncoder *s = p.get();
-        s->submit([s] { code_queue(s->queue, s->bytes); });
+        s->submit([s] { code_queue(s->queue, s->bytes, s->words); });
     }
     return 0;
 }
