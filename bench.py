@@ -392,10 +392,32 @@ def run_context_fusion(pkg, dev, pk):
     llq = torch.round(torch.randn((1, 1, 72, 120), device=dev, generator=g) * 6)
     ll_seq = {}
     with torch.no_grad():
-        lln.ar_encode(llq)
+        # encoder, all coefficients at once (speculated history, checked; same symbols as the sequential kernel) ...
+        ref_out = lln.ar_encode(llq, parallel=False)
+        for _ in range(2):
+            par_out = lln.ar_encode(llq, parallel=True)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        ll_hat, s16, i16 = lln.ar_encode(llq)
+        for _ in range(5):
+            par_out = lln.ar_encode(llq, parallel=True)
+        torch.cuda.synchronize(dev)
+        ll_seq["encode_parallel_ms"] = (time.perf_counter() - t0) * 1e3 / 5
+        ll_seq["encode_parallel_path"] = lln.last_encode_path
+        ll_seq["encode_parallel_equals_sequential"] = bool(torch.equal(par_out[0], ref_out[0]) and (par_out[1] == ref_out[1]).all()
+                                                           and (par_out[2] == ref_out[2]).all())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lln(llq)
+        e0.record()
+        for _ in range(10):
+            lln(llq)                      # forward (rate-estimate path) on the same kernels
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ll_seq["forward_ms"] = e0.elapsed_time(e1) / 10
+        # ... and the strictly sequential kernels (decoder; encoder fallback)
+        lln.ar_encode(llq, parallel=False)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        ll_hat, s16, i16 = lln.ar_encode(llq, parallel=False)
         torch.cuda.synchronize(dev)
         ll_seq["encode_ms"] = (time.perf_counter() - t0) * 1e3
         em.entropy_coder.reset()
@@ -417,7 +439,9 @@ def run_context_fusion(pkg, dev, pk):
         ll_seq["torch_ops_ms_extrapolated"] = (time.perf_counter() - t0) * 1e3 * 72 / 3
         lln.sequential_init = False
     ll_seq["what"] = ("LL band of a 1080p luma plane (72x120 = 8 640 coefficients), sequential form (context_fusion.py:160-204 as driven by "
-                      "pWave.py:531-584): encoder = one kernel for the band, decoder = one kernel + one rANS step per coefficient; the "
+                      "pWave.py:531-584): encode_ms / decode_ms = the coefficient-by-coefficient kernels (encoder: one launch for the band, decoder: one "
+                      "launch + one rANS step per coefficient); encode_parallel_ms = what the encoder runs by default, the same arithmetic on all "
+                      "coefficients at once (seven launches, incl. the host read of the speculation flag and of the symbols); the "
                       "reference's ~25 ATen calls per coefficient beside it (parameter evaluation only, without its per-coefficient coder calls)")
     pkg.ops.check_tc_error(dev, "context fusion block")
     tf = CTX_FLOPS_PER_COEFF * coeffs / ms / 1e9
@@ -530,7 +554,7 @@ def run_full_codec(pkg, dev):
                     "forward_MCTF, hp / lp pWave.forward with the four-step entropy-parameter networks, ConvLSTM context, LL model, PostProcess, for "
                     "luma and chroma; inverse_MCTF) on one 1080p 4:2:0 GOP-16, random weights, rate-estimate path",
             "ms_per_gop": ms, "frames_per_s": GOP / (ms * 1e-3), "bits_per_frame_estimate": sum(bits) / GOP,
-            "on_our_kernels": "lifting, SpyNet, four-step networks, PostProcess; stock torch ops: MV codec, ConvLSTM context, LL model, rate estimate"}
+            "on_our_kernels": "lifting, SpyNet, four-step networks, LL model, PostProcess, ConvLSTM gates, rate estimate; stock torch convolutions: MV codec, ConvLSTM context"}
 
 
 def run_uvg(args, pkg, G, par, model, dev, rank, world):

@@ -369,6 +369,15 @@ int pmctf_llar_pack(const float *w, int cin, int taps, float *out, void *stream)
 /* encoder: yq [B,1,H,W] quantised band -> sym16 / idx16 [B][H*W] (symbol round(round(y) - mean) and scale-table index per
  * coefficient, raster order) and, in p->Y, the band as the decoder will reconstruct it */
 int pmctf_llar_encode(const pmctf_llar_t *p, const float *yq, short *sym16, short *idx16, void *stream);
+/* The same network on all coefficients of the band at once (the encoder knows them; so does the rate-estimate path,
+ * ContextFusionSubband.forward, context_fusion.py:143-158): seven launches, every output computed with exactly the arithmetic of
+ * the sequential form, so scales / means / symbols / indexes equal pmctf_llar_encode's bit for bit.  x [B][H][W]: the band
+ * (round_in != 0: the quantised band, rounded here as pWave.py:549-553 does).  Outputs (each may be NULL): sym16 / idx16 as
+ * pmctf_llar_encode, scales / means [B][H][W] fp32.  The history is SPECULATED to be round(x); *mismatch (device int, zeroed by the
+ * caller) is set when some coefficient's reconstruction round(symbol + mean) differs from it -- the caller then runs
+ * pmctf_llar_encode, whose history is the reconstruction by construction.  p->Y, p->hist as above (zero borders). */
+int pmctf_llar_forward(const pmctf_llar_t *p, const float *x, int round_in, short *sym16, short *idx16, float *scales, float *means,
+                       int *mismatch, void *stream);
 /* decoder: parameters of coefficient `pos` (raster index); prev [B] = reconstructed value of coefficient pos - 1 (ignored for
  * pos == 0), out_mean [B] / out_idx [B]: HOST-visible (mapped pinned) memory read after synchronising the stream */
 int pmctf_llar_decode_step(const pmctf_llar_t *p, int pos, const float *prev, float *out_mean, short *out_idx, void *stream);

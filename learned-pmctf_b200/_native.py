@@ -134,6 +134,7 @@ SIGNATURES = {
     "pmctf_ctx_mask_step": [C.POINTER(CtxStep), _P],
     "pmctf_llar_pack": [_P, _I, _I, _P, _P],
     "pmctf_llar_encode": [C.POINTER(LLar), _P, _P, _P, _P],
+    "pmctf_llar_forward": [C.POINTER(LLar), _P, _I, _P, _P, _P, _P, _P, _P],
     "pmctf_llar_decode_step": [C.POINTER(LLar), _I, _P, _P, _P, _P],
     "pmctf_pair_packed_bytes": [_I, _I, _I],
     "pmctf_pair_pack_conv": [_P, _I, _I, _I, _I, _I, _P, _P],

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -98,6 +99,8 @@ class ContextFusionSubband(nn.Module):
         return x
 
     def forward(self, x, context=None, prev_subband=None, channel_idx=0):
+        if x.is_cuda and not torch.is_grad_enabled() and x.size(1) == 1 and self.num_features == 128 and self.num_parameters == 2:
+            return self.ar_forward(x)     # evaluation: the whole band on the kernels of csrc/pmctf_llar.cu, bit-equal to the bitstream path
         first = self.maskedConv1(x)
         x = first
         for blk in self.residualBlocks:
@@ -176,7 +179,20 @@ class ContextFusionSubband(nn.Module):
         d.scale_levels = 256
         return d, (Y, hist)
 
-    def ar_encode(self, yq):
+    def ar_forward(self, x):
+        """forward (context_fusion.py:143-158) of a whole band x [B,1,H,W] on the layer-parallel kernels: -> [B,2,H,W] (scales,
+        means), each value computed with the arithmetic of the sequential form, i.e. exactly the parameters the bitstream path
+        codes with when the band is its own reconstruction."""
+        x = ops._chk(x, "ll", 4).contiguous()
+        B, _, H, W = x.shape
+        d, _keep = self._ar_desc(B, H, W, x.device)
+        out = torch.empty((2, B, H, W), dtype=torch.float32, device=x.device)
+        ops._launch(x.device, "llar_forward", nat.lib().pmctf_llar_forward, C.byref(d), x.data_ptr(), 0, None, None, out[0].data_ptr(),
+                    out[1].data_ptr(), None)
+        return out.permute(1, 0, 2, 3).contiguous()
+
+    # PMCTF_LL_SEQUENTIAL=1: always run the coefficient-by-coefficient encoder (A/B runs, tests)
+    def ar_encode(self, yq, parallel=None):
         """yq [B,1,H,W] quantised LL band (CUDA) -> (ll_hat [B,1,H,W] as the decoder will reconstruct it, int16 symbols, int16 table
         indexes), the latter two as numpy arrays in the order the entropy coder consumes them: coefficient by coefficient in raster
         order, planes of the batch innermost (one `encoder.encode` per coefficient in pWave.py:548-553)."""
@@ -187,7 +203,20 @@ class ContextFusionSubband(nn.Module):
         d, (Y, _hist) = self._ar_desc(B, H, W, yq.device)
         sym = torch.empty((B, H * W), dtype=torch.int16, device=yq.device)
         idx = torch.empty_like(sym)
-        ops._launch(yq.device, "llar_encode", nat.lib().pmctf_llar_encode, C.byref(d), yq.data_ptr(), sym.data_ptr(), idx.data_ptr())
+        if parallel is None:
+            parallel = os.environ.get("PMCTF_LL_SEQUENTIAL", "0") != "1"
+        self.last_encode_path = "sequential"
+        if parallel:
+            # the encoder knows every coefficient: all of them at once, the history speculated to be round(y); a coefficient whose
+            # reconstruction round(symbol + mean) differs from that (round(y) - mean ending in exactly .5) sends the band through the
+            # sequential kernel below, which conditions on the reconstruction by construction
+            flag = torch.zeros(1, dtype=torch.int32, device=yq.device)
+            ops._launch(yq.device, "llar_forward", nat.lib().pmctf_llar_forward, C.byref(d), yq.data_ptr(), 1, sym.data_ptr(), idx.data_ptr(),
+                        None, None, flag.data_ptr())
+            if int(flag.item()) == 0:
+                self.last_encode_path = "parallel"
+        if self.last_encode_path == "sequential":
+            ops._launch(yq.device, "llar_encode", nat.lib().pmctf_llar_encode, C.byref(d), yq.data_ptr(), sym.data_ptr(), idx.data_ptr())
         ll_hat = Y[:, 1:-1, 1:-1].unsqueeze(1).contiguous()
         return ll_hat, sym.t().contiguous().cpu().numpy().reshape(-1), idx.t().contiguous().cpu().numpy().reshape(-1)
 
