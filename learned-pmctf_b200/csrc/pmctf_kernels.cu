@@ -393,41 +393,88 @@ __global__ void __launch_bounds__(256) flow_warp_kernel(const float *__restrict_
 
 // the same with four pixels per thread, one in each of four consecutive rows: every load and store of a warp stays coalesced
 // (consecutive lanes = consecutive x) while the 8 motion-vector loads and then the 16 gathers of a thread are in flight together
-// (the one-pixel form is bound by memory latency); no index divisions
-__global__ void __launch_bounds__(128) flow_warp4_kernel(const float *__restrict__ im, const float *__restrict__ flow,
+// (the one-pixel form is bound by memory latency).  The kernel is bound by its instruction stream, not by HBM, so everything
+// that is not the reference's coordinate arithmetic is kept off it: 32-bit offsets inside a plane (H * W < 2^31, checked by the
+// launcher), one 64-bit base per plane, the sample position and the four weights computed once per pixel for all C channels,
+// the plane of the motion field resolved without an integer division when every image has its own field.
+#ifndef PMCTF_WARP_ROWS
+#define PMCTF_WARP_ROWS 4
+#endif
+#ifndef PMCTF_WARP_MINB
+#define PMCTF_WARP_MINB 12   // 40 registers: 48 warps per SM (measured: 8 ... 12 blocks equal within 1 %, 16 blocks spill and lose 6 %)
+#endif
+constexpr int WR = PMCTF_WARP_ROWS;   // rows per thread
+__global__ void __launch_bounds__(128, PMCTF_WARP_MINB) flow_warp4_kernel(const float *__restrict__ im, const float *__restrict__ flow,
                                                          const float *__restrict__ lin_x, const float *__restrict__ lin_y,
-                                                         float *__restrict__ out, int N, int C, int H, int W, int flowN,
+                                                         float *__restrict__ out, int N, int C, int H, int W, int share,
                                                          float sign, float sx, float sy, int round_out)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y0 = blockIdx.y * 4;
+    const int y0 = blockIdx.y * WR;
     const int n = blockIdx.z;
     if (x >= W) return;
-    const long long plane = (long long)H * W;
-    const float *fb = flow + (long long)(n / (N / flowN)) * 2 * plane + (long long)y0 * W + x;
+    const int plane = H * W;
+    const int f = (share == 1) ? n : n / share;      // `share` consecutive images use one field
+    const float *fb = flow + (size_t)f * 2 * (size_t)plane;
+    const int o0 = y0 * W + x;
     const float lx = __ldg(lin_x + x);
-    float fx[4], fy[4], ly[4];
+    const float xmax = (float)(W - 1), ymax = (float)(H - 1);
+    float fx[WR], fy[WR], ly[WR];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < WR; ++j) {
         fx[j] = fy[j] = ly[j] = 0.0f;
         if (y0 + j < H) {
-            fx[j] = sign * __ldg(fb + (long long)j * W);
-            fy[j] = sign * __ldg(fb + plane + (long long)j * W);
+            fx[j] = sign * __ldg(fb + o0 + j * W);
+            fy[j] = sign * __ldg(fb + plane + o0 + j * W);
             ly[j] = __ldg(lin_y + y0 + j);
         }
     }
+    // video_net.py:42-50 + ATen grid_sampler_2d (align_corners=True, border), op for op as warp_sample()
+    int idx[WR];
+    float nw[WR], ne[WR], sw[WR], se[WR];
+    bool x1ok[WR], y1ok[WR];
+#pragma unroll
+    for (int j = 0; j < WR; ++j) {
+        const float gx = lx + fx[j] / sx;
+        const float gy = ly[j] + fy[j] / sy;
+        float ix = (gx + 1.0f) * sx;
+        float iy = (gy + 1.0f) * sy;
+        ix = fminf(fmaxf(ix, 0.0f), xmax);
+        iy = fminf(fmaxf(iy, 0.0f), ymax);
+        const float xf = floorf(ix), yf = floorf(iy);
+        const float w = ix - xf, e = 1.0f - w, nn = iy - yf, so = 1.0f - nn;
+        nw[j] = so * e; ne[j] = so * w; sw[j] = nn * e; se[j] = nn * w;
+        const int x0i = (int)xf, y0i = (int)yf;
+        x1ok[j] = x0i + 1 <= W - 1;
+        y1ok[j] = y0i + 1 <= H - 1;
+        idx[j] = y0i * W + x0i;
+    }
+    const bool rnd = round_out != 0;
     for (int c = 0; c < C; ++c) {
-        const float *ip = im + ((long long)n * C + c) * plane;
-        float v[4];
+        const size_t pb = (size_t)(n * C + c) * (size_t)plane;
+        const float *ip = im + pb;
+        float v[WR];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            v[j] = (y0 + j < H) ? warp_sample(ip, W, 1, H, W, lx, ly[j], fx[j], fy[j], sx, sy) : 0.0f;
-            if (round_out) v[j] = rintf(v[j]);
+        for (int j = 0; j < WR; ++j) {
+            v[j] = 0.0f;
+            if (y0 + j < H) {
+                const float *p = ip + idx[j];
+                const float *q = p + W;
+                const float vnw = __ldg(p);
+                const float vne = x1ok[j] ? __ldg(p + 1) : 0.0f;
+                const float vsw = y1ok[j] ? __ldg(q) : 0.0f;
+                const float vse = (x1ok[j] && y1ok[j]) ? __ldg(q + 1) : 0.0f;
+                float acc = vnw * nw[j];
+                acc = fmaf(vne, ne[j], acc);
+                acc = fmaf(vsw, sw[j], acc);
+                acc = fmaf(vse, se[j], acc);
+                v[j] = rnd ? rintf(acc) : acc;
+            }
         }
-        float *op = out + ((long long)n * C + c) * plane + (long long)y0 * W + x;
+        float *op = out + pb + o0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (y0 + j < H) op[(long long)j * W] = v[j];
+        for (int j = 0; j < WR; ++j)
+            if (y0 + j < H) op[j * W] = v[j];
     }
 }
 
@@ -958,9 +1005,9 @@ int pmctf_flow_warp(const float *im, const float *flow, const float *lin_x, cons
     if (!im || !flow || !lin_x || !lin_y || !out || N <= 0 || C <= 0) return PMCTF_EINVAL;
     if (H < 2 || W < 2 || flowN < 1 || (N % flowN) || H > 65535 || N > 65535) return PMCTF_ESHAPE;
     const float sx = (float)(((double)W - 1.0) / 2.0), sy = (float)(((double)H - 1.0) / 2.0);
-    if (H >= 8 && (H + 3) / 4 <= 65535) {
-        flow_warp4_kernel<<<dim3((W + 127) / 128, (H + 3) / 4, N), 128, 0, (cudaStream_t)stream>>>(im, flow, lin_x, lin_y, out, N, C, H, W,
-                                                                                                 flowN, sign, sx, sy, round_out);
+    if (H >= 8 && (H + WR - 1) / WR <= 65535 && (long long)H * W < (1LL << 30) && (long long)N * C < (1LL << 31)) {
+        flow_warp4_kernel<<<dim3((W + 127) / 128, (H + WR - 1) / WR, N), 128, 0, (cudaStream_t)stream>>>(im, flow, lin_x, lin_y, out, N, C, H, W,
+                                                                                                 N / flowN, sign, sx, sy, round_out);
     } else {
         flow_warp_kernel<<<dim3((W + 255) / 256, H, N), 256, 0, (cudaStream_t)stream>>>(im, flow, lin_x, lin_y, out, N, C, H, W, flowN, sign,
                                                                                      sx, sy, round_out);
