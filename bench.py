@@ -429,6 +429,16 @@ def run_context_fusion(pkg, dev, pk):
         back = lln.ar_decode([1, 1, 72, 120], lambda i: dec.decode_stream(i, cdf, ln, off), dev)
         ll_seq["decode_ms"] = (time.perf_counter() - t0) * 1e3
         ll_seq["round_trip_exact"] = bool(torch.equal(back, ll_hat))
+        # the decoder the bitstream path runs by default: ONE launch for the band (cluster of eight CTAs per plane, weights resident
+        # in shared memory, device-side rANS decoder), incl. the stream upload and the hand-back of the reader position
+        for rep in range(2):
+            em.entropy_coder.set_stream(em.entropy_coder.get_encoded_stream())
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            band = lln.ar_decode_band([1, 1, 72, 120], em.entropy_coder.decoder, cdf, ln, off, dev)
+            torch.cuda.synchronize(dev)
+            ll_seq["decode_band_ms"] = (time.perf_counter() - t0) * 1e3
+        ll_seq["decode_band_exact"] = bool(band is not None and torch.equal(band, ll_hat))
         plane = torch.nn.functional.pad(ll_hat, (1, 1, 1, 1))          # the reference's formulation (ATen calls per coefficient), 3 rows timed
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
@@ -440,7 +450,8 @@ def run_context_fusion(pkg, dev, pk):
         lln.sequential_init = False
     ll_seq["what"] = ("LL band of a 1080p luma plane (72x120 = 8 640 coefficients), sequential form (context_fusion.py:160-204 as driven by "
                       "pWave.py:531-584): encode_ms / decode_ms = the coefficient-by-coefficient kernels (encoder: one launch for the band, decoder: one "
-                      "launch + one rANS step per coefficient); encode_parallel_ms = what the encoder runs by default, the same arithmetic on all "
+                      "launch + one rANS step per coefficient); decode_band_ms = what the decoder runs by default: one launch for the band, a cluster of "
+                      "eight CTAs with the weights resident in shared memory and a device-side rANS decoder; encode_parallel_ms = what the encoder runs by default, the same arithmetic on all "
                       "coefficients at once (seven launches, incl. the host read of the speculation flag and of the symbols); the "
                       "reference's ~25 ATen calls per coefficient beside it (parameter evaluation only, without its per-coefficient coder calls)")
     pkg.ops.check_tc_error(dev, "context fusion block")

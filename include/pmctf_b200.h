@@ -378,6 +378,15 @@ int pmctf_llar_encode(const pmctf_llar_t *p, const float *yq, short *sym16, shor
  * pmctf_llar_encode, whose history is the reconstruction by construction.  p->Y, p->hist as above (zero borders). */
 int pmctf_llar_forward(const pmctf_llar_t *p, const float *x, int round_in, short *sym16, short *idx16, float *scales, float *means,
                        int *mismatch, void *stream);
+/* decoder, the whole band in ONE launch: a cluster of eight CTAs per plane keeps the masked layers' weights resident in shared
+ * memory (one reduction slice per CTA, partial sums exchanged through distributed shared memory) and decodes the band's symbols
+ * with a device-side rANS decoder (rans.cpp:279-331), so there is no host round trip per coefficient.  words / nwords: device copy
+ * of the sub-stream's 32-bit words; state: device u64[4] = {rANS state, index of the next word, error flag (out), 0}, as exported by
+ * pmctf_rans_decoder_peek and written back with pmctf_rans_decoder_seek; cdfs [cdf_num][cdf_stride] / cdfs_sizes / offsets: DEVICE
+ * copies of the tables pmctf_rans_decode_stream takes; out [B][H*W]: the reconstructed band round(symbol + mean) (also left in
+ * p->Y).  Same values as pmctf_llar_decode_step + pmctf_rans_decode_stream coefficient by coefficient.  B <= 16. */
+int pmctf_llar_decode_band(const pmctf_llar_t *p, const unsigned int *words, long long nwords, unsigned long long *state, const int *cdfs,
+                           int cdf_num, int cdf_stride, const int *cdfs_sizes, const int *offsets, float *out, void *stream);
 /* decoder: parameters of coefficient `pos` (raster index); prev [B] = reconstructed value of coefficient pos - 1 (ignored for
  * pos == 0), out_mean [B] / out_idx [B]: HOST-visible (mapped pinned) memory read after synchronising the stream */
 int pmctf_llar_decode_step(const pmctf_llar_t *p, int pos, const float *prev, float *out_mean, short *out_idx, void *stream);
@@ -428,6 +437,11 @@ int pmctf_rans_get_encoded_stream(void *enc, unsigned char *out, long long capac
 int pmctf_rans_decoder_create(int stream_part, void **dec);
 int pmctf_rans_decoder_destroy(void *dec);
 int pmctf_rans_decoder_set_stream(void *dec, const unsigned char *bytes, long long n);
+/* state of one sub-stream's reader, for decoders that continue on the device (pmctf_llar_decode_band): x = rANS state, pos = index
+ * of the next unread 32-bit word, words / nwords = the decoder's own copy of the sub-stream (valid until the next set_stream) */
+int pmctf_rans_decoder_parts(void *dec);
+int pmctf_rans_decoder_peek(void *dec, int part, unsigned long long *x, long long *pos, long long *nwords, const unsigned int **words);
+int pmctf_rans_decoder_seek(void *dec, int part, unsigned long long x, long long pos);
 int pmctf_rans_decode_stream(void *dec, const short *indexes, long long n, const int *cdfs, int cdf_num, int cdf_stride,
                              const int *cdfs_sizes, const int *offsets, short *out);
 /* DEVICE: what entropy_models.py:37-40 and GaussianEncoder.build_indexes (:266-270) do with two blocking copies per coded step,

@@ -136,6 +136,10 @@ SIGNATURES = {
     "pmctf_llar_encode": [C.POINTER(LLar), _P, _P, _P, _P],
     "pmctf_llar_forward": [C.POINTER(LLar), _P, _I, _P, _P, _P, _P, _P, _P],
     "pmctf_llar_decode_step": [C.POINTER(LLar), _I, _P, _P, _P, _P],
+    "pmctf_llar_decode_band": [C.POINTER(LLar), _P, C.c_longlong, _P, _P, _I, _I, _P, _P, _P, _P],
+    "pmctf_rans_decoder_parts": [_P],
+    "pmctf_rans_decoder_peek": [_P, _I, _P, _P, _P, _P],
+    "pmctf_rans_decoder_seek": [_P, _I, C.c_ulonglong, C.c_longlong],
     "pmctf_pair_packed_bytes": [_I, _I, _I],
     "pmctf_pair_pack_conv": [_P, _I, _I, _I, _I, _I, _P, _P],
     "pmctf_pair_conv": [_P, _P, _P, _I, _I, _I, _I, _f, _P, _P, _P, _I, _I, _I, _P],

@@ -21,11 +21,14 @@
 
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "pmctf_b200.h"
 
 namespace pmctf {
 void count_launch();
 namespace llar {
+namespace cg = cooperative_groups;
 
 constexpr int F = 128;          // features
 constexpr int NT = 256;         // 32 groups of four output channels x 8 slices of the reduction dimension
@@ -398,6 +401,225 @@ __global__ void __launch_bounds__(NT) llar_par_layer_kernel(const Net n, const R
     }
 }
 
+// ---- the DECODER of a whole band in one launch -------------------------------------------------------------------------------
+// The decoder is sequential by definition (a coefficient's parameters need the coefficients before it), so what can be removed
+// is everything around the arithmetic: (1) the host round trip per coefficient -- the rANS decoder of the band's symbols runs on
+// the device, inside the kernel; (2) the weight traffic -- coefficient() streams 1.8 MB of weights from L2 through ONE SM per
+// coefficient (>= 14 us at the L2 -> SM rate).  Here a CLUSTER of eight CTAs works on one plane: CTA r owns reduction slice r of
+// every masked 128 -> 128 layer (the contract's eight slices: 80 inputs x 128 outputs = 40 KB per layer, 200 KB for the five
+// layers, RESIDENT in its shared memory for the whole band), computes that slice's partial sums (one fma chain per output, the
+// same chain as gemv()), and stores them into CTA 0's shared memory through the cluster's distributed shared memory; CTA 0 folds
+// the eight partials onto the bias in the contract's order, applies the layer's epilogue, and broadcasts the 128 values to every
+// CTA (they are the (0, 0) tap of the next layer and the (0, -1) tap of the next coefficient) and to the global history planes
+// (the taps of the next row, prefetched one coefficient ahead into a four-column ring).  Two cluster barriers per layer.
+// Same values as coefficient() bit for bit (tests/test_gpu_llar.py).
+constexpr int CL = 8;                                   // cluster size = reduction slices of the contract
+constexpr int SL = 5 * F / KSL;                         // 80 inputs per slice of a masked layer
+constexpr int C_W = 0, C_UP = C_W + 5 * SL * F, C_CP = C_UP + 5 * 4 * F, C_BC = C_CP + 2 * 5 * F, C_PART = C_BC + 3 * F,
+              C_IN = C_PART + CL * F, C_RED = C_IN + F, C_FLOATS = C_RED + 2 * F;
+static_assert(C_FLOATS * 4 <= 227 * 1024, "cluster decoder: shared memory");
+
+struct DevRans {
+    const unsigned int *words;      // the sub-stream's 32-bit words (device copy)
+    long long nwords;
+    unsigned long long *state;      // [0] rANS state x, [1] index of the next word, [2] error flag, [3] turn counter (planes of a batch)
+    const int *cdf, *sizes, *offsets;
+    int num, stride;
+};
+
+// one symbol of table `ti` (decode_part of pmctf_rans.cu / rans.cpp:279-331 on the device; the tables are non-decreasing, so the
+// reference's linear scan is an upper-bound search)
+__device__ int rans_decode_one(const DevRans &d, int ti, unsigned long long &x, unsigned long long &pos, bool &bad)
+{
+    auto next = [&]() -> unsigned long long {
+        if ((long long)pos >= d.nwords) { bad = true; return 0ull; }
+        return (unsigned long long)d.words[pos++];
+    };
+    auto get_raw = [&]() -> unsigned int {
+        const unsigned int v = (unsigned int)(x & 15ull);
+        x >>= 4;
+        if (x < (1ull << 31)) x = (x << 32) | next();
+        return v;
+    };
+    if (ti < 0 || ti >= d.num) { bad = true; return 0; }
+    const int *cdf = d.cdf + (long long)ti * d.stride;
+    const int size = d.sizes[ti], escape = size - 2;
+    if (escape < 0 || size > d.stride) { bad = true; return 0; }
+    const unsigned int target = (unsigned int)(x & 0xFFFFull);
+    int lo = 0, hi = size - 1;          // s = number of entries of cdf[1 .. size-1] that are <= target
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((unsigned int)cdf[mid] <= target) lo = mid; else hi = mid - 1;
+    }
+    const int sI = lo;
+    if (sI + 1 >= size) { bad = true; return 0; }
+    const unsigned int start = (unsigned int)cdf[sI], freq = (unsigned int)(cdf[sI + 1] - cdf[sI]);
+    x = (unsigned long long)freq * (x >> 16) + (x & 0xFFFFull) - start;
+    if (x < (1ull << 31)) x = (x << 32) | next();
+    int v = sI;
+    if (v == escape) {
+        unsigned int dg = get_raw();
+        int digits = (int)dg;
+        while (dg == 15u) {
+            dg = get_raw();
+            digits += (int)dg;
+            if (digits > 64) { bad = true; return 0; }
+        }
+        unsigned int raw = 0;
+        for (int j = 0; j < digits; ++j) raw |= get_raw() << (j * 4);
+        v = (int)(raw >> 1);
+        v = (raw & 1u) ? -v - 1 : v + escape;
+    }
+    return (int)(short)(v + d.offsets[ti]);
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(F) llar_cluster_decode_kernel(const Net n, const Run r, const DevRans d, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) float sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), bi = blockIdx.y, tid = threadIdx.x;
+    float *wres = sm + C_W, *up = sm + C_UP, *cp = sm + C_CP, *bc = sm + C_BC, *part = sm + C_PART, *in = sm + C_IN, *red = sm + C_RED;
+    const int Hp = r.H + 2, Wp = r.W + 2, HW = r.H * r.W;
+    const long long plane = (long long)Hp * Wp * F;
+    float *Y = r.Y + (long long)bi * Hp * Wp;
+    float *hist[5];
+#pragma unroll
+    for (int L = 0; L < 5; ++L) hist[L] = r.hist[L] + bi * plane;
+    // this CTA's slice of the masked layers: resident for the whole band; of the two 1x1 layers: 16 inputs per output, in registers
+    for (int L = 0; L < 5; ++L)
+        for (int j = 0; j < SL; ++j) wres[(L * SL + j) * F + tid] = __ldg(n.w[L] + (long long)(SL * rank + j) * F + tid);
+    float w1a[16], w1b[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        w1a[j] = __ldg(n.w1[0] + (16 * rank + j) * F + tid);
+        w1b[j] = __ldg(n.w1[1] + (16 * rank + j) * F + tid);
+    }
+    float win[4], bl[5];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) win[k] = __ldg(n.w_in + k * F + tid);
+#pragma unroll
+    for (int L = 0; L < 5; ++L) bl[L] = __ldg(n.b[L] + tid);
+    const float bin = __ldg(n.b_in + tid), b1a = __ldg(n.b1[0] + tid), b1b = __ldg(n.b1[1] + tid);
+    const float wo0 = __ldg(n.w_out + tid), wo1 = __ldg(n.w_out + F + tid);
+    float *part0 = cluster.map_shared_rank(part, 0);
+    for (int i = tid; i < C_FLOATS - C_UP; i += F) sm[C_UP + i] = 0.0f;
+    cluster.sync();
+    bool bad = false;
+    for (int h = 0; h < r.H; ++h) {
+        // row start: the left neighbour is the zero border; the ring of the row above holds columns -1, 0, 1 (padded row h = image row h - 1)
+#pragma unroll
+        for (int L = 0; L < 5; ++L) {
+            cp[(1 * 5 + L) * F + tid] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) up[(L * 4 + c) * F + tid] = __ldcg(hist[L] + ((long long)h * Wp + c) * F + tid);
+        }
+        for (int w = 0; w < r.W; ++w) {
+            const int ci = w & 1, pi = ci ^ 1;
+            const long long here = ((long long)(h + 1) * Wp + (w + 1)) * F;
+            float pf[5];
+            const bool pre = w + 2 <= r.W;      // column w + 2 of the row above: needed by the next coefficient
+#pragma unroll
+            for (int L = 0; L < 5; ++L) pf[L] = pre ? __ldcg(hist[L] + ((long long)h * Wp + (w + 3)) * F + tid) : 0.0f;
+            if (rank == 0) {                    // maskedConv1 (type A) on the reconstructed band
+                float t = bin;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t = fmaf(win[k], Y[(long long)(h + 1 + c_dy[k]) * Wp + (w + 1 + c_dx[k])], t);
+                for (int q = 0; q < CL; ++q) cluster.map_shared_rank(cp, q)[(ci * 5 + 0) * F + tid] = t;
+                hist[0][here + tid] = t;
+            }
+            cluster.sync();
+            for (int L = 0; L < 5; ++L) {
+                if (tid < SL) {
+                    const int k = SL * rank + tid, t = k >> 7, c = k & (F - 1);
+                    float x;
+                    if (t < 3) x = up[(L * 4 + ((w + t) & 3)) * F + c];
+                    else if (t == 3) x = cp[(pi * 5 + L) * F + c];
+                    else x = cp[(ci * 5 + L) * F + c];
+                    in[tid] = x;
+                }
+                __syncthreads();
+                float acc = 0.0f;
+#pragma unroll 8
+                for (int j = 0; j < SL; ++j) acc = fmaf(wres[(L * SL + j) * F + tid], in[j], acc);
+                part0[rank * F + tid] = acc;
+                cluster.sync();
+                if (rank == 0) {
+                    float v = bl[L];
+#pragma unroll
+                    for (int q = 0; q < CL; ++q) v += part[q * F + tid];
+                    float o;
+                    if (L == 0 || L == 2) o = lrelu(v);
+                    else if (L == 1) o = v + cp[(ci * 5 + 0) * F + tid];
+                    else if (L == 3) o = (v + cp[(ci * 5 + 2) * F + tid]) + cp[(ci * 5 + 0) * F + tid];
+                    else o = v;
+                    if (L < 4) {
+                        for (int q = 0; q < CL; ++q) cluster.map_shared_rank(cp, q)[(ci * 5 + L + 1) * F + tid] = o;
+                        hist[L + 1][here + tid] = o;
+                    } else {
+                        for (int q = 0; q < CL; ++q) cluster.map_shared_rank(bc, q)[tid] = o;
+                    }
+                }
+                cluster.sync();
+            }
+            for (int k = 0; k < 2; ++k) {       // convs.0, convs.1 behind LeakyReLU
+                if (tid < 16) in[tid] = lrelu(bc[k * F + 16 * rank + tid]);
+                __syncthreads();
+                float acc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc = fmaf(k == 0 ? w1a[j] : w1b[j], in[j], acc);
+                part0[rank * F + tid] = acc;
+                cluster.sync();
+                if (rank == 0) {
+                    float v = k == 0 ? b1a : b1b;
+#pragma unroll
+                    for (int q = 0; q < CL; ++q) v += part[q * F + tid];
+                    for (int q = 0; q < CL; ++q) cluster.map_shared_rank(bc, q)[(k + 1) * F + tid] = v;
+                }
+                cluster.sync();
+            }
+            if (rank == 0) {                    // convs.2 (multiply, fixed-order tree), the symbol, the reconstruction
+                const float t = lrelu(bc[2 * F + tid]);
+                red[tid] = t * wo0;
+                red[F + tid] = t * wo1;
+                __syncthreads();
+                for (int st = F / 2; st > 0; st >>= 1) {
+                    if (tid < st) {
+                        red[tid] += red[tid + st];
+                        red[F + tid] += red[F + tid + st];
+                    }
+                    __syncthreads();
+                }
+                if (tid == 0) {
+                    const float scale = red[0] + __ldg(n.b_out), mean = red[F] + __ldg(n.b_out + 1);
+                    const int ti = table_index(scale, r);
+                    volatile unsigned long long *stt = d.state;
+                    const unsigned long long turn = (unsigned long long)(h * r.W + w) * (unsigned long long)r.B + (unsigned long long)bi;
+                    if (r.B > 1) {              // the planes of a batch share the stream: plane order inside a coefficient
+                        while (stt[3] != turn) { }
+                        __threadfence();
+                    }
+                    unsigned long long x = stt[0], pos = stt[1];
+                    const int sym = rans_decode_one(d, ti, x, pos, bad);
+                    stt[0] = x;
+                    stt[1] = pos;
+                    if (bad) stt[2] = 1ull;
+                    __threadfence();
+                    stt[3] = turn + 1ull;
+                    const float rec = rintf((float)sym + mean);
+                    Y[(long long)(h + 1) * Wp + (w + 1)] = rec;
+                    out[(long long)bi * HW + h * r.W + w] = rec;
+                }
+                __syncthreads();
+            }
+            if (pre) {
+#pragma unroll
+                for (int L = 0; L < 5; ++L) up[(L * 4 + ((w + 3) & 3)) * F + tid] = pf[L];
+            }
+        }
+    }
+    cluster.sync();      // no CTA leaves while its shared memory may still be written remotely
+}
+
 // OIHW masked weights -> the causal-tap layouts above.  src [128][cin][3][3]; dst [taps][cin][128]
 __global__ void llar_pack_kernel(const float *__restrict__ w, int cin, int taps, float *__restrict__ out)
 {
@@ -487,6 +709,24 @@ int pmctf_llar_forward(const pmctf_llar_t *p, const float *x, int round_in, shor
     llar::llar_par_layer_kernel<3><<<grid, llar::NT, 0, st>>>(n, r, 3, 3, 4, 2, 0, none);   // res1.conv2:  hist4 = (. + hist2) + hist0
     llar::llar_par_layer_kernel<4><<<grid, llar::NT, 0, st>>>(n, r, 4, 4, 0, 0, 0, o);      // maskedConv2, convs.0-2, symbols
     for (int i = 0; i < 7; ++i) count_launch();
+    return (int)cudaGetLastError();
+}
+
+int pmctf_llar_decode_band(const pmctf_llar_t *p, const unsigned int *words, long long nwords, unsigned long long *state, const int *cdfs,
+                           int cdf_num, int cdf_stride, const int *cdfs_sizes, const int *offsets, float *out, void *stream)
+{
+    llar::Net n;
+    llar::Run r;
+    int e = fill(p, n, r);
+    if (e) return e;
+    if (!words || nwords < 0 || !state || !cdfs || !cdfs_sizes || !offsets || cdf_num <= 0 || cdf_stride < 2 || !out) return PMCTF_EINVAL;
+    if (p->B > 16 || (long long)p->H * p->W > 0x7fffffffLL) return PMCTF_ESHAPE;   // every plane's cluster must be resident: they take turns on the stream
+    const llar::DevRans d{words, nwords, state, cdfs, cdfs_sizes, offsets, cdf_num, cdf_stride};
+    constexpr int SMEM = llar::C_FLOATS * 4;
+    cudaError_t ce = cudaFuncSetAttribute(llar::llar_cluster_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (ce != cudaSuccess) return (int)ce;
+    llar::llar_cluster_decode_kernel<<<dim3(llar::CL, (unsigned)p->B), llar::F, SMEM, (cudaStream_t)stream>>>(n, r, d, out);
+    count_launch();
     return (int)cudaGetLastError();
 }
 

@@ -568,6 +568,36 @@ int pmctf_rans_decode_stream(void *dec, const short *indexes, long long n, const
     return 0;
 }
 
+int pmctf_rans_decoder_parts(void *dec)
+{
+    return dec ? (int)static_cast<Decoder *>(dec)->parts.size() : 0;
+}
+
+int pmctf_rans_decoder_peek(void *dec, int part, unsigned long long *x, long long *pos, long long *nwords, const unsigned int **words)
+{
+    if (!dec || !x || !pos || !nwords || !words) return PMCTF_EINVAL;
+    Decoder *D = static_cast<Decoder *>(dec);
+    if (!D->has_stream || part < 0 || part >= (int)D->parts.size()) return PMCTF_EINVAL;
+    Decoder::Part &p = D->parts[(size_t)part];
+    *x = p.r.x;
+    *pos = (long long)(p.r.p - p.words.data());
+    *nwords = (long long)p.words.size();
+    *words = p.words.data();
+    return 0;
+}
+
+int pmctf_rans_decoder_seek(void *dec, int part, unsigned long long x, long long pos)
+{
+    if (!dec) return PMCTF_EINVAL;
+    Decoder *D = static_cast<Decoder *>(dec);
+    if (!D->has_stream || part < 0 || part >= (int)D->parts.size()) return PMCTF_EINVAL;
+    Decoder::Part &p = D->parts[(size_t)part];
+    if (pos < 2 || pos > (long long)p.words.size()) return PMCTF_EINVAL;
+    p.r.x = x;
+    p.r.p = p.words.data() + pos;
+    return 0;
+}
+
 int pmctf_gaussian_symbolize(const float *symbols, const float *scales, long long n, float log_scale_min, float log_scale_step,
                              int scale_levels, short *sym16, short *idx16, void *stream)
 {

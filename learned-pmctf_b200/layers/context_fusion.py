@@ -220,9 +220,43 @@ class ContextFusionSubband(nn.Module):
         ll_hat = Y[:, 1:-1, 1:-1].unsqueeze(1).contiguous()
         return ll_hat, sym.t().contiguous().cpu().numpy().reshape(-1), idx.t().contiguous().cpu().numpy().reshape(-1)
 
+    def ar_decode_band(self, size, rans_decoder, cdf, cdf_sizes, offsets, device):
+        """The whole band in ONE launch (pmctf_llar_decode_band): a cluster of eight CTAs per plane with the weights resident in
+        shared memory, the band's symbols decoded by the device-side rANS decoder from the (single) sub-stream of `rans_decoder`
+        (a models.MLCodec_rans.RansDecoder), whose reader is moved past the band afterwards.  -> [B,1,H,W], or None when the
+        configuration is outside the kernel's (several sub-streams, more than 16 planes)."""
+        B, Cc, H, W = size
+        lib, device = nat.lib(), torch.device(device)
+        h = getattr(rans_decoder, "_h", None)
+        if Cc != 1 or B > 16 or h is None or lib.pmctf_rans_decoder_parts(h) != 1 or os.environ.get("PMCTF_LL_SEQUENTIAL", "0") == "1":
+            return None
+        x, pos, nwords, words = C.c_ulonglong(), C.c_longlong(), C.c_longlong(), C.c_void_p()
+        nat.check(lib.pmctf_rans_decoder_peek(h, 0, C.byref(x), C.byref(pos), C.byref(nwords), C.byref(words)), "rans_decoder_peek")
+        wnp = np.ctypeslib.as_array(C.cast(words, C.POINTER(C.c_uint32)), shape=(max(int(nwords.value), 1),))[: int(nwords.value)]
+        key = (id(cdf), id(cdf_sizes), id(offsets), str(device))
+        tabs = self.__dict__.get("_ar_tables")
+        if tabs is None or tabs[0] != key:
+            from ..models.MLCodec_rans import _tables
+            cd, sz, of = _tables(cdf, cdf_sizes, offsets)
+            tabs = (key, torch.from_numpy(cd.copy()).to(device), torch.from_numpy(sz.copy()).to(device), torch.from_numpy(of.copy()).to(device),
+                    (cdf, cdf_sizes, offsets))
+            self.__dict__["_ar_tables"] = tabs
+        _, cd, sz, of, _keep = tabs
+        wdev = torch.from_numpy(wnp.view(np.int32).copy()).to(device) if wnp.size else torch.zeros(1, dtype=torch.int32, device=device)
+        state = torch.tensor([x.value if x.value < (1 << 63) else x.value - (1 << 64), pos.value, 0, 0], dtype=torch.int64, device=device)
+        d, _keepbuf = self._ar_desc(B, H, W, device)
+        out = torch.empty((B, H * W), dtype=torch.float32, device=device)
+        ops._launch(device, "llar_decode_band", lib.pmctf_llar_decode_band, C.byref(d), wdev.data_ptr(), int(nwords.value), state.data_ptr(),
+                    cd.data_ptr(), cd.shape[0], cd.shape[1], sz.data_ptr(), of.data_ptr(), out.data_ptr())
+        st = state.cpu().tolist()
+        if st[2] != 0:
+            raise RuntimeError("LL band: the entropy-coded stream ended early or is corrupt")
+        nat.check(lib.pmctf_rans_decoder_seek(h, 0, C.c_ulonglong(st[0] & ((1 << 64) - 1)), st[1]), "rans_decoder_seek")
+        return out.view(B, 1, H, W)
+
     def ar_decode(self, size, decode, device):
         """size = [B,1,H,W]; decode(idx int16 numpy [B]) -> int16 numpy [B] symbols of one coefficient.  One kernel launch + one
-        stream synchronisation + one rANS step per coefficient."""
+        stream synchronisation + one rANS step per coefficient (the fallback of ar_decode_band)."""
         B, Cc, H, W = size
         if Cc != 1:
             raise RuntimeError("the LL band is single-channel")

@@ -312,7 +312,10 @@ class pWaveTransform:
                 enc.entropy_coder.encoder.encode_with_indexes(sym16, idx16, cdf, ln, off)
                 return ll_hat
             dec = enc.entropy_coder.decoder
-            return net.ar_decode(size, lambda idx: dec.decode_stream(idx, cdf, ln, off), device).to(dtype)
+            band = net.ar_decode_band(size, dec, cdf, ln, off, device) if hasattr(net, "ar_decode_band") else None
+            if band is None:          # several sub-streams / large batches: one launch + one host rANS step per coefficient
+                band = net.ar_decode(size, lambda idx: dec.decode_stream(idx, cdf, ln, off), device)
+            return band.to(dtype)
         pad = 1
         if symbols is not None:
             plane = torch.nn.functional.pad(symbols, (pad, pad, pad, pad))

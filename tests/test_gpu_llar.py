@@ -104,3 +104,41 @@ def test_llar_forward_rejects_bad_arguments():
     s16 = torch.zeros(16, dtype=torch.int16, device=dev)
     assert lib.pmctf_llar_forward(C.byref(d), x.data_ptr(), 1, s16.data_ptr(), None, None, None, None, st) != 0   # symbols without indexes
     assert lib.pmctf_llar_forward(C.byref(d), None, 0, None, None, x.data_ptr(), None, None, st) != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 9, 14), (2, 7, 5), (1, 3, 1), (1, 72, 120), (3, 1, 6)])
+def test_band_decoder_round_trip_and_stream_position(shape):
+    """encode -> rANS -> the one-launch cluster decoder (device-side rANS): the band equals the encoder's reconstruction, equals
+    the per-coefficient decoder's, and the host decoder continues correctly behind the band (symbols coded after it)"""
+    from learned_pmctf_b200.entropy_models.gaussian_model import CompressionModel
+    dev = torch.device("cuda:0")
+    net = _net(dev)
+    em = CompressionModel("laplace")
+    em.update()
+    cdf, ln, off = em.gaussian_encoder.get_cdf_info()
+    B, H, W = shape
+    g = torch.Generator(device="cpu").manual_seed(17)
+    ll = torch.round(torch.randn(B, 1, H, W, generator=g) * 6).to(dev)
+    if H * W > 40:
+        ll[0, 0, 1, 2] = 700.0          # far outside every table: the escape path with raw digits
+        ll[0, 0, 2, 3] = -900.0
+    tail_sym = np.array([3, -2, 0, 41, -300, 1], dtype=np.int16)
+    tail_idx = np.array([5, 100, 255, 17, 3, 64], dtype=np.int16)
+    with torch.no_grad():
+        ll_hat, sym16, idx16 = net.ar_encode(ll)
+        coder = em.entropy_coder
+        for use_band in (True, False):
+            coder.reset()
+            coder.encoder.encode_with_indexes(sym16, idx16, cdf, ln, off)
+            coder.encoder.encode_with_indexes(tail_sym, tail_idx, cdf, ln, off)
+            coder.flush()
+            coder.set_stream(coder.get_encoded_stream())
+            dec = coder.decoder
+            if use_band:
+                back = net.ar_decode_band([B, 1, H, W], dec, cdf, ln, off, dev)
+                assert back is not None
+            else:
+                back = net.ar_decode([B, 1, H, W], lambda i: dec.decode_stream(i, cdf, ln, off), dev)
+            assert torch.equal(back, ll_hat), use_band
+            assert np.array_equal(np.asarray(dec.decode_stream(tail_idx, cdf, ln, off)), tail_sym), use_band
