@@ -408,15 +408,18 @@ __global__ void __launch_bounds__(NT) llar_par_layer_kernel(const Net n, const R
 // coefficient (>= 14 us at the L2 -> SM rate).  Here a CLUSTER of eight CTAs works on one plane: CTA r owns reduction slice r of
 // every masked 128 -> 128 layer (the contract's eight slices: 80 inputs x 128 outputs = 40 KB per layer, 200 KB for the five
 // layers, RESIDENT in its shared memory for the whole band), computes that slice's partial sums (one fma chain per output, the
-// same chain as gemv()), and stores them into CTA 0's shared memory through the cluster's distributed shared memory; CTA 0 folds
-// the eight partials onto the bias in the contract's order, applies the layer's epilogue, and broadcasts the 128 values to every
-// CTA (they are the (0, 0) tap of the next layer and the (0, -1) tap of the next coefficient) and to the global history planes
-// (the taps of the next row, prefetched one coefficient ahead into a four-column ring).  Two cluster barriers per layer.
+// same chain as gemv()) and stores them into EVERY CTA's shared memory through the cluster's distributed shared memory; after
+// one cluster barrier every CTA folds the eight partials onto the bias in the contract's order and applies the layer's epilogue
+// itself -- eight identical copies of the 128 values (the (0, 0) tap of the next layer, the (0, -1) tap of the next coefficient),
+// nothing to broadcast, ONE barrier per layer (seven per coefficient, an eighth behind the rANS step).  CTA 0 also writes the
+// values to the global history planes: the taps of the next row, which every CTA prefetches one coefficient ahead into a
+// four-column ring.  The first version (CTA 0 folds and broadcasts: two barriers per layer) took 99 ms per 1080p band.
 // Same values as coefficient() bit for bit (tests/test_gpu_llar.py).
 constexpr int CL = 8;                                   // cluster size = reduction slices of the contract
 constexpr int SL = 5 * F / KSL;                         // 80 inputs per slice of a masked layer
 constexpr int C_W = 0, C_UP = C_W + 5 * SL * F, C_CP = C_UP + 5 * 4 * F, C_BC = C_CP + 2 * 5 * F, C_PART = C_BC + 3 * F,
-              C_IN = C_PART + CL * F, C_RED = C_IN + F, C_FLOATS = C_RED + 2 * F;
+              C_IN = C_PART + 2 * CL * F, C_RED = C_IN + F, C_MISC = C_RED + 2 * F, C_FLOATS = C_MISC + 16;
+constexpr int M_YLEFT = 4;                              // misc[0..3]: ring of the reconstructed row above, misc[4]: the left neighbour
 static_assert(C_FLOATS * 4 <= 227 * 1024, "cluster decoder: shared memory");
 
 struct DevRans {
@@ -478,7 +481,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(F) llar_cluster_dec
     extern __shared__ __align__(16) float sm[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank(), bi = blockIdx.y, tid = threadIdx.x;
-    float *wres = sm + C_W, *up = sm + C_UP, *cp = sm + C_CP, *bc = sm + C_BC, *part = sm + C_PART, *in = sm + C_IN, *red = sm + C_RED;
+    float *wres = sm + C_W, *up = sm + C_UP, *cp = sm + C_CP, *bc = sm + C_BC, *part = sm + C_PART, *in = sm + C_IN, *red = sm + C_RED,
+          *misc = sm + C_MISC;
     const int Hp = r.H + 2, Wp = r.W + 2, HW = r.H * r.W;
     const long long plane = (long long)Hp * Wp * F;
     float *Y = r.Y + (long long)bi * Hp * Wp;
@@ -501,33 +505,58 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(F) llar_cluster_dec
     for (int L = 0; L < 5; ++L) bl[L] = __ldg(n.b[L] + tid);
     const float bin = __ldg(n.b_in + tid), b1a = __ldg(n.b1[0] + tid), b1b = __ldg(n.b1[1] + tid);
     const float wo0 = __ldg(n.w_out + tid), wo1 = __ldg(n.w_out + F + tid);
-    float *part0 = cluster.map_shared_rank(part, 0);
+    float *rpart[CL];       // every CTA receives every slice's partial sums and folds them itself (same order, same values):
+#pragma unroll              // one cluster barrier per layer instead of two, nothing to broadcast
+    for (int q = 0; q < CL; ++q) rpart[q] = cluster.map_shared_rank(part, q);
     for (int i = tid; i < C_FLOATS - C_UP; i += F) sm[C_UP + i] = 0.0f;
     cluster.sync();
     bool bad = false;
+    unsigned long long rx = 0, rpos = 0;    // a single plane keeps the reader in the registers of the decoding thread
+    if (rank == 0 && tid == 0 && r.B == 1) {
+        rx = d.state[0];
+        rpos = d.state[1];
+    }
+    int pp = 0;             // the partial sums alternate between two buffers: a CTA may already send a layer's while another still folds the one before
+    // one exchange: this CTA's partial to all, barrier, fold onto the bias in slice order
+    auto exchange = [&](float acc, float bias) -> float {
+#pragma unroll
+        for (int q = 0; q < CL; ++q) rpart[q][(pp * CL + rank) * F + tid] = acc;
+        cluster.sync();
+        float v = bias;
+#pragma unroll
+        for (int q = 0; q < CL; ++q) v += part[(pp * CL + q) * F + tid];
+        pp ^= 1;
+        return v;
+    };
     for (int h = 0; h < r.H; ++h) {
-        // row start: the left neighbour is the zero border; the ring of the row above holds columns -1, 0, 1 (padded row h = image row h - 1)
+        // row start: the left neighbour is the zero border; the rings of the row above hold columns -1, 0, 1 (padded row h = image row h - 1)
 #pragma unroll
         for (int L = 0; L < 5; ++L) {
             cp[(1 * 5 + L) * F + tid] = 0.0f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) up[(L * 4 + c) * F + tid] = __ldcg(hist[L] + ((long long)h * Wp + c) * F + tid);
         }
+        if (tid < 3) misc[tid] = __ldcg(Y + (long long)h * Wp + tid);
+        if (tid == 3) misc[M_YLEFT] = 0.0f;
+        __syncthreads();
         for (int w = 0; w < r.W; ++w) {
             const int ci = w & 1, pi = ci ^ 1;
             const long long here = ((long long)(h + 1) * Wp + (w + 1)) * F;
-            float pf[5];
+            float pf[5], pfy = 0.0f;
             const bool pre = w + 2 <= r.W;      // column w + 2 of the row above: needed by the next coefficient
 #pragma unroll
             for (int L = 0; L < 5; ++L) pf[L] = pre ? __ldcg(hist[L] + ((long long)h * Wp + (w + 3)) * F + tid) : 0.0f;
-            if (rank == 0) {                    // maskedConv1 (type A) on the reconstructed band
+            if (pre && tid == 0) pfy = __ldcg(Y + (long long)h * Wp + (w + 3));
+            {                                   // maskedConv1 (type A) on the reconstructed band
                 float t = bin;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) t = fmaf(win[k], Y[(long long)(h + 1 + c_dy[k]) * Wp + (w + 1 + c_dx[k])], t);
-                for (int q = 0; q < CL; ++q) cluster.map_shared_rank(cp, q)[(ci * 5 + 0) * F + tid] = t;
-                hist[0][here + tid] = t;
+                t = fmaf(win[0], misc[w & 3], t);
+                t = fmaf(win[1], misc[(w + 1) & 3], t);
+                t = fmaf(win[2], misc[(w + 2) & 3], t);
+                t = fmaf(win[3], misc[M_YLEFT], t);
+                cp[(ci * 5 + 0) * F + tid] = t;
+                if (rank == 0) hist[0][here + tid] = t;
             }
-            cluster.sync();
+            __syncthreads();
             for (int L = 0; L < 5; ++L) {
                 if (tid < SL) {
                     const int k = SL * rank + tid, t = k >> 7, c = k & (F - 1);
@@ -541,25 +570,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(F) llar_cluster_dec
                 float acc = 0.0f;
 #pragma unroll 8
                 for (int j = 0; j < SL; ++j) acc = fmaf(wres[(L * SL + j) * F + tid], in[j], acc);
-                part0[rank * F + tid] = acc;
-                cluster.sync();
-                if (rank == 0) {
-                    float v = bl[L];
-#pragma unroll
-                    for (int q = 0; q < CL; ++q) v += part[q * F + tid];
-                    float o;
-                    if (L == 0 || L == 2) o = lrelu(v);
-                    else if (L == 1) o = v + cp[(ci * 5 + 0) * F + tid];
-                    else if (L == 3) o = (v + cp[(ci * 5 + 2) * F + tid]) + cp[(ci * 5 + 0) * F + tid];
-                    else o = v;
-                    if (L < 4) {
-                        for (int q = 0; q < CL; ++q) cluster.map_shared_rank(cp, q)[(ci * 5 + L + 1) * F + tid] = o;
-                        hist[L + 1][here + tid] = o;
-                    } else {
-                        for (int q = 0; q < CL; ++q) cluster.map_shared_rank(bc, q)[tid] = o;
-                    }
+                const float v = exchange(acc, bl[L]);
+                float o;
+                if (L == 0 || L == 2) o = lrelu(v);
+                else if (L == 1) o = v + cp[(ci * 5 + 0) * F + tid];
+                else if (L == 3) o = (v + cp[(ci * 5 + 2) * F + tid]) + cp[(ci * 5 + 0) * F + tid];
+                else o = v;
+                if (L < 4) {
+                    cp[(ci * 5 + L + 1) * F + tid] = o;
+                    if (rank == 0) hist[L + 1][here + tid] = o;
+                } else {
+                    bc[tid] = o;
                 }
-                cluster.sync();
+                __syncthreads();
             }
             for (int k = 0; k < 2; ++k) {       // convs.0, convs.1 behind LeakyReLU
                 if (tid < 16) in[tid] = lrelu(bc[k * F + 16 * rank + tid]);
@@ -567,15 +590,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(F) llar_cluster_dec
                 float acc = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc = fmaf(k == 0 ? w1a[j] : w1b[j], in[j], acc);
-                part0[rank * F + tid] = acc;
-                cluster.sync();
-                if (rank == 0) {
-                    float v = k == 0 ? b1a : b1b;
-#pragma unroll
-                    for (int q = 0; q < CL; ++q) v += part[q * F + tid];
-                    for (int q = 0; q < CL; ++q) cluster.map_shared_rank(bc, q)[(k + 1) * F + tid] = v;
-                }
-                cluster.sync();
+                bc[(k + 1) * F + tid] = exchange(acc, k == 0 ? b1a : b1b);
+                __syncthreads();
             }
             if (rank == 0) {                    // convs.2 (multiply, fixed-order tree), the symbol, the reconstruction
                 const float t = lrelu(bc[2 * F + tid]);
@@ -597,27 +613,38 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(F) llar_cluster_dec
                     if (r.B > 1) {              // the planes of a batch share the stream: plane order inside a coefficient
                         while (stt[3] != turn) { }
                         __threadfence();
+                        rx = stt[0];
+                        rpos = stt[1];
                     }
-                    unsigned long long x = stt[0], pos = stt[1];
-                    const int sym = rans_decode_one(d, ti, x, pos, bad);
-                    stt[0] = x;
-                    stt[1] = pos;
-                    if (bad) stt[2] = 1ull;
-                    __threadfence();
-                    stt[3] = turn + 1ull;
+                    const int sym = rans_decode_one(d, ti, rx, rpos, bad);
+                    if (r.B > 1) {
+                        stt[0] = rx;
+                        stt[1] = rpos;
+                        __threadfence();
+                        stt[3] = turn + 1ull;
+                    }
                     const float rec = rintf((float)sym + mean);
                     Y[(long long)(h + 1) * Wp + (w + 1)] = rec;
                     out[(long long)bi * HW + h * r.W + w] = rec;
+#pragma unroll
+                    for (int q = 0; q < CL; ++q) cluster.map_shared_rank(misc, q)[M_YLEFT] = rec;   // the next coefficient's left neighbour
                 }
-                __syncthreads();
             }
             if (pre) {
 #pragma unroll
                 for (int L = 0; L < 5; ++L) up[(L * 4 + ((w + 3) & 3)) * F + tid] = pf[L];
+                if (tid == 0) misc[(w + 3) & 3] = pfy;
             }
+            cluster.sync();                     // the reconstruction has reached every CTA
         }
     }
-    cluster.sync();      // no CTA leaves while its shared memory may still be written remotely
+    if (rank == 0 && tid == 0) {
+        if (r.B == 1) {
+            d.state[0] = rx;
+            d.state[1] = rpos;
+        }
+        if (bad) d.state[2] = 1ull;
+    }
 }
 
 // OIHW masked weights -> the causal-tap layouts above.  src [128][cin][3][3]; dst [taps][cin][128]
