@@ -431,6 +431,11 @@ int pmctf_rans_encoder_destroy(void *enc);
 int pmctf_rans_encoder_reset(void *enc);
 int pmctf_rans_encode_with_indexes(void *enc, const short *symbols, const short *indexes, long long n, const int *cdfs, int cdf_num,
                                    int cdf_stride, const int *cdfs_sizes, const int *offsets);
+/* the same as ceil(n / chunk) consecutive pmctf_rans_encode_with_indexes calls of `chunk` symbols each: every chunk is shared out
+ * over the sub-streams on its own (py_rans.cpp:45-59), as the reference's per-coefficient encoder.encode calls of the LL band are
+ * (pWave.py:548-553) -- what a decoder asking for `chunk` symbols per call (or pmctf_llar_decode_band) expects */
+int pmctf_rans_encode_chunked(void *enc, const short *symbols, const short *indexes, long long n, long long chunk, const int *cdfs,
+                              int cdf_num, int cdf_stride, const int *cdfs_sizes, const int *offsets);
 int pmctf_rans_encoder_flush(void *enc);
 long long pmctf_rans_encoded_size(void *enc);
 int pmctf_rans_get_encoded_stream(void *enc, unsigned char *out, long long capacity);

@@ -150,6 +150,7 @@ SIGNATURES = {
     "pmctf_rans_encoder_destroy": [_P],
     "pmctf_rans_encoder_reset": [_P],
     "pmctf_rans_encode_with_indexes": [_P, _P, _P, _LL, _P, _I, _I, _P, _P],
+    "pmctf_rans_encode_chunked": [_P, _P, _P, _LL, _LL, _P, _I, _I, _P, _P],
     "pmctf_rans_encoder_flush": [_P],
     "pmctf_rans_encoded_size": [_P],
     "pmctf_rans_get_encoded_stream": [_P, _P, _LL],

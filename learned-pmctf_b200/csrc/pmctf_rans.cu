@@ -19,6 +19,8 @@
 // ONE pass (gaussian_symbolize_kernel, HBM-bound, 12 B per coefficient) so a single copy per coded step reaches the host;
 // the strictly sequential state update runs on the host cores, one thread per sub-stream, behind a C ABI.
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <stdint.h>
 #include <string.h>
 
@@ -428,6 +430,40 @@ int pmctf_rans_encode_with_indexes(void *enc, const short *symbols, const short 
         s->submit([s, s16, i16, t] {
             const int rc = queue_symbols(s->queue, s16->data(), i16->data(), (long long)s16->size(), *t);
             if (rc && !s->error) s->error = rc;
+        });
+    }
+    return 0;
+}
+
+int pmctf_rans_encode_chunked(void *enc, const short *symbols, const short *indexes, long long n, long long chunk, const int *cdfs,
+                              int cdf_num, int cdf_stride, const int *cdfs_sizes, const int *offsets)
+{   // the same as ceil(n / chunk) consecutive pmctf_rans_encode_with_indexes calls of `chunk` symbols each (the last one shorter):
+    // every chunk is shared out over the sub-streams on its own, which is what a decoder that asks for `chunk` symbols per call sees
+    if (!enc || n < 0 || chunk <= 0 || (n > 0 && (!symbols || !indexes))) return PMCTF_EINVAL;
+    auto t = std::make_shared<Tables>();
+    int e = make_tables(*t, cdfs, cdf_num, cdf_stride, cdfs_sizes, offsets);
+    if (e) return e;
+    Encoder *E = static_cast<Encoder *>(enc);
+    const long long parts = (long long)E->parts.size();
+    std::vector<std::shared_ptr<std::vector<int16_t>>> s16((size_t)parts), i16((size_t)parts);
+    for (long long i = 0; i < parts; ++i) {
+        s16[(size_t)i] = std::make_shared<std::vector<int16_t>>();
+        i16[(size_t)i] = std::make_shared<std::vector<int16_t>>();
+    }
+    for (long long c0 = 0; c0 < n; c0 += chunk) {
+        const long long m = std::min(chunk, n - c0), each = m / parts;
+        for (long long i = 0; i < parts; ++i) {
+            const long long cnt = i < parts - 1 ? each : m - each * (parts - 1);
+            s16[(size_t)i]->insert(s16[(size_t)i]->end(), symbols + c0 + i * each, symbols + c0 + i * each + cnt);
+            i16[(size_t)i]->insert(i16[(size_t)i]->end(), indexes + c0 + i * each, indexes + c0 + i * each + cnt);
+        }
+    }
+    for (long long i = 0; i < parts; ++i) {
+        SubEncoder *sp = E->parts[(size_t)i].get();
+        auto a = s16[(size_t)i], b = i16[(size_t)i];
+        sp->submit([sp, a, b, t] {
+            const int rc = queue_symbols(sp->queue, a->data(), b->data(), (long long)a->size(), *t);
+            if (rc && !sp->error) sp->error = rc;
         });
     }
     return 0;

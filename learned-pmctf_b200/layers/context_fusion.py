@@ -222,16 +222,20 @@ class ContextFusionSubband(nn.Module):
 
     def ar_decode_band(self, size, rans_decoder, cdf, cdf_sizes, offsets, device):
         """The whole band in ONE launch (pmctf_llar_decode_band): a cluster of eight CTAs per plane with the weights resident in
-        shared memory, the band's symbols decoded by the device-side rANS decoder from the (single) sub-stream of `rans_decoder`
-        (a models.MLCodec_rans.RansDecoder), whose reader is moved past the band afterwards.  -> [B,1,H,W], or None when the
-        configuration is outside the kernel's (several sub-streams, more than 16 planes)."""
+        shared memory, the band's symbols decoded by the device-side rANS decoder from the sub-stream of `rans_decoder` (a
+        models.MLCodec_rans.RansDecoder) that holds them, whose reader is moved past the band afterwards.  -> [B,1,H,W], or None
+        when the configuration is outside the kernel's (a coefficient's symbols spread over several sub-streams, more than 16 planes)."""
         B, Cc, H, W = size
         lib, device = nat.lib(), torch.device(device)
         h = getattr(rans_decoder, "_h", None)
-        if Cc != 1 or B > 16 or h is None or lib.pmctf_rans_decoder_parts(h) != 1 or os.environ.get("PMCTF_LL_SEQUENTIAL", "0") == "1":
+        if Cc != 1 or B > 16 or h is None or os.environ.get("PMCTF_LL_SEQUENTIAL", "0") == "1":
             return None
+        parts = lib.pmctf_rans_decoder_parts(h)
+        if parts != 1 and B >= parts:
+            return None                   # a coefficient's B symbols would come from several sub-streams
+        part = parts - 1                  # B < parts: every share but the last is empty (py_rans.cpp:45-59)
         x, pos, nwords, words = C.c_ulonglong(), C.c_longlong(), C.c_longlong(), C.c_void_p()
-        nat.check(lib.pmctf_rans_decoder_peek(h, 0, C.byref(x), C.byref(pos), C.byref(nwords), C.byref(words)), "rans_decoder_peek")
+        nat.check(lib.pmctf_rans_decoder_peek(h, part, C.byref(x), C.byref(pos), C.byref(nwords), C.byref(words)), "rans_decoder_peek")
         wnp = np.ctypeslib.as_array(C.cast(words, C.POINTER(C.c_uint32)), shape=(max(int(nwords.value), 1),))[: int(nwords.value)]
         key = (id(cdf), id(cdf_sizes), id(offsets), str(device))
         tabs = self.__dict__.get("_ar_tables")
@@ -251,7 +255,7 @@ class ContextFusionSubband(nn.Module):
         st = state.cpu().tolist()
         if st[2] != 0:
             raise RuntimeError("LL band: the entropy-coded stream ended early or is corrupt")
-        nat.check(lib.pmctf_rans_decoder_seek(h, 0, C.c_ulonglong(st[0] & ((1 << 64) - 1)), st[1]), "rans_decoder_seek")
+        nat.check(lib.pmctf_rans_decoder_seek(h, part, C.c_ulonglong(st[0] & ((1 << 64) - 1)), st[1]), "rans_decoder_seek")
         return out.view(B, 1, H, W)
 
     def ar_decode(self, size, decode, device):

@@ -35,12 +35,17 @@ class RansEncoder:
         if h:
             self._destroy(h)
 
-    def encode_with_indexes(self, symbols, indexes, cdfs, cdfs_sizes, offsets) -> None:
+    def encode_with_indexes(self, symbols, indexes, cdfs, cdfs_sizes, offsets, chunk=None) -> None:
+        """chunk: behave as consecutive calls of `chunk` symbols each (every chunk shared out over the sub-streams on its own)"""
         sym = np.ascontiguousarray(symbols, dtype=np.int16).reshape(-1)
         idx = np.ascontiguousarray(indexes, dtype=np.int16).reshape(-1)
         if sym.size != idx.size:
             raise RuntimeError("one table index per symbol")
         cdfs, sizes, offs = _tables(cdfs, cdfs_sizes, offsets)
+        if chunk is not None:
+            nat.check(nat.lib().pmctf_rans_encode_chunked(self._h, _ptr(sym), _ptr(idx), sym.size, int(chunk), _ptr(cdfs), cdfs.shape[0],
+                                                          cdfs.shape[1], _ptr(sizes), _ptr(offs)), "rans_encode_chunked")
+            return
         nat.check(nat.lib().pmctf_rans_encode_with_indexes(self._h, _ptr(sym), _ptr(idx), sym.size, _ptr(cdfs), cdfs.shape[0],
                                                            cdfs.shape[1], _ptr(sizes), _ptr(offs)), "rans_encode_with_indexes")
 

@@ -309,7 +309,8 @@ class pWaveTransform:
             cdf, ln, off = enc.get_cdf_info()
             if symbols is not None:
                 ll_hat, sym16, idx16 = net.ar_encode(symbols)
-                enc.entropy_coder.encoder.encode_with_indexes(sym16, idx16, cdf, ln, off)
+                # one coefficient (B symbols) per share-out over the sub-streams, as the reference's per-coefficient encode calls
+                enc.entropy_coder.encoder.encode_with_indexes(sym16, idx16, cdf, ln, off, chunk=B)
                 return ll_hat
             dec = enc.entropy_coder.decoder
             band = net.ar_decode_band(size, dec, cdf, ln, off, device) if hasattr(net, "ar_decode_band") else None

@@ -107,14 +107,15 @@ def test_llar_forward_rejects_bad_arguments():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("stream_part", [1, 4])
 @pytest.mark.parametrize("shape", [(1, 9, 14), (2, 7, 5), (1, 3, 1), (1, 72, 120), (3, 1, 6)])
-def test_band_decoder_round_trip_and_stream_position(shape):
+def test_band_decoder_round_trip_and_stream_position(shape, stream_part):
     """encode -> rANS -> the one-launch cluster decoder (device-side rANS): the band equals the encoder's reconstruction, equals
     the per-coefficient decoder's, and the host decoder continues correctly behind the band (symbols coded after it)"""
     from learned_pmctf_b200.entropy_models.gaussian_model import CompressionModel
     dev = torch.device("cuda:0")
     net = _net(dev)
-    em = CompressionModel("laplace")
+    em = CompressionModel("laplace", ec_thread=False, stream_part=stream_part)
     em.update()
     cdf, ln, off = em.gaussian_encoder.get_cdf_info()
     B, H, W = shape
@@ -130,7 +131,7 @@ def test_band_decoder_round_trip_and_stream_position(shape):
         coder = em.entropy_coder
         for use_band in (True, False):
             coder.reset()
-            coder.encoder.encode_with_indexes(sym16, idx16, cdf, ln, off)
+            coder.encoder.encode_with_indexes(sym16, idx16, cdf, ln, off, chunk=B)     # one coefficient per share-out, as pWave does
             coder.encoder.encode_with_indexes(tail_sym, tail_idx, cdf, ln, off)
             coder.flush()
             coder.set_stream(coder.get_encoded_stream())

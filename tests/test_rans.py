@@ -274,3 +274,46 @@ def test_device_staging_round_trip(conv_mode):
     em.entropy_coder.set_stream(stream)
     back = em.gaussian_encoder.decode_stream(scales, torch.float32, dev)
     assert torch.equal(back, sym.clamp(-30000, 30000))
+
+
+@pytest.mark.parametrize("parts,chunk", [(1, 1), (4, 1), (4, 3), (3, 7), (2, 1000)])
+def test_chunked_encode_equals_consecutive_calls(tables, parts, chunk, conv_mode):
+    """encode_with_indexes(..., chunk=c) produces the byte-identical stream of ceil(n / c) consecutive calls (what the LL band's
+    one-call encoder must look like to a decoder that asks for one coefficient per call, pWave.py:548-553), and a decoder reading
+    `chunk` symbols per call gets the symbols back"""
+    if conv_mode != "tensor":
+        pytest.skip("independent of the convolution arithmetic")
+    cdf, sizes, offs = tables
+    n = 211
+    sym, idx = _symbols(n, 5, tables, wild=False)
+    one = MLCodec_rans.RansEncoder(False, parts)
+    one.encode_with_indexes(sym, idx, cdf, sizes, offs, chunk=chunk)
+    one.flush()
+    many = MLCodec_rans.RansEncoder(False, parts)
+    for c0 in range(0, n, chunk):
+        many.encode_with_indexes(sym[c0:c0 + chunk], idx[c0:c0 + chunk], cdf, sizes, offs)
+    many.flush()
+    stream = one.get_encoded_stream()
+    assert np.array_equal(stream, many.get_encoded_stream())
+    dec = MLCodec_rans.RansDecoder(parts)
+    dec.set_stream(stream)
+    back = np.concatenate([dec.decode_stream(idx[c0:c0 + chunk], cdf, sizes, offs) for c0 in range(0, n, chunk)])
+    assert np.array_equal(back, sym)
+    # the reader position survives a peek / seek round trip (the hand-over to the device-side decoder)
+    import ctypes as C
+    from learned_pmctf_b200 import _native as nat
+    lib = nat.lib()
+    assert lib.pmctf_rans_decoder_parts(dec._h) == parts
+    dec.set_stream(stream)
+    first = dec.decode_stream(idx[:chunk], cdf, sizes, offs)
+    saved = []
+    for p in range(parts):
+        x, pos, nw, w = C.c_ulonglong(), C.c_longlong(), C.c_longlong(), C.c_void_p()
+        assert lib.pmctf_rans_decoder_peek(dec._h, p, C.byref(x), C.byref(pos), C.byref(nw), C.byref(w)) == 0
+        saved.append((x.value, pos.value))
+    second = dec.decode_stream(idx[chunk:2 * chunk], cdf, sizes, offs)
+    for p, (x, pos) in enumerate(saved):
+        assert lib.pmctf_rans_decoder_seek(dec._h, p, C.c_ulonglong(x), pos) == 0
+    assert np.array_equal(dec.decode_stream(idx[chunk:2 * chunk], cdf, sizes, offs), second)
+    assert np.array_equal(first, sym[:chunk])
+    assert lib.pmctf_rans_decoder_seek(dec._h, parts, C.c_ulonglong(0), 2) != 0
