@@ -12,6 +12,8 @@ state_dict keys are the reference's: wavelet_transform.{lift_h,lift_v}.*, QP, QP
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -466,7 +468,11 @@ class pWave(pWaveTransform, nn.Module):
             self.dequantModule = PostProcess(in_channels=1, out_channels=1)
         if entropy_model:
             self.num_params = 2
-            self.em = CompressionModel(y_distribution="laplace")
+            # the reference's coder configuration (pWave.py:66: no worker thread, one sub-stream).  PMCTF_EC_THREAD=1 queues and codes
+            # on a worker thread under the GPU work of the next band (same bytes); PMCTF_STREAM_PART=n writes n sub-streams coded
+            # concurrently (the reference's container for stream_part = n, py_rans.cpp:67-113)
+            self.em = CompressionModel(y_distribution="laplace", ec_thread=os.environ.get("PMCTF_EC_THREAD", "0") == "1",
+                                       stream_part=int(os.environ.get("PMCTF_STREAM_PART", "1")))
             self.context_fusion = nn.ModuleDict({
                 str(lvl): nn.ModuleDict({b: ContextFusionFourStep(in_channels=1, num_features=112, num_parameters=2, lossy=lossy,
                                                                   ctx_channels=2 if lvl < decomp_levels - 1 else 1) for b in BANDS})

@@ -31,4 +31,5 @@ with torch.no_grad():
         torch.cuda.synchronize()
         out["decompress_ms"] = (time.perf_counter() - t0) * 1e3
     out["round_trip_exact"] = bool(torch.equal(back, x_hat))
+out["coder"] = {"ec_thread": os.environ.get("PMCTF_EC_THREAD", "0") == "1", "stream_part": int(os.environ.get("PMCTF_STREAM_PART", "1"))}
 print(json.dumps(out))
