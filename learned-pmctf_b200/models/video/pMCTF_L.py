@@ -461,8 +461,8 @@ def accelerate(ref_model):
     """Graft the B200 hot path onto an instance of the REFERENCE pMCTF (pMCTF_L.py:29): its
     TemporalLifting / LiftingScheme2D submodules are replaced by ours with the SAME parameter
     tensors (state_dict keys and values unchanged), and the hot-path methods are rebound.  The
-    four-step entropy-parameter networks, PostProcess and SpyNet are replaced the same way; the MV codec, the LL model and the
-    ConvLSTM context stay the reference's stock torch modules."""
+    four-step entropy-parameter networks, the LL band's autoregressive model, PostProcess and SpyNet are replaced the same way; the
+    MV codec and the ConvLSTM context stay the reference's stock torch modules."""
     from ...layers import LiftingScheme2D
 
     def adopt(dst: nn.Module, src: nn.Module):
@@ -473,6 +473,14 @@ def accelerate(ref_model):
             for p in path:
                 mod = getattr(mod, p)
             mod._parameters[leaf] = src_params[name]
+        src_bufs = dict(src.named_buffers(remove_duplicate=False))
+        for name, _ in list(dst.named_buffers(remove_duplicate=False)):   # e.g. the masks of the LL model's masked convolutions
+            if name in src_bufs:
+                mod = dst
+                *path, leaf = name.split(".")
+                for p in path:
+                    mod = getattr(mod, p)
+                mod._buffers[leaf] = src_bufs[name]
         return dst
 
     for i, tl in enumerate(ref_model.temporal_filtering):
@@ -494,6 +502,12 @@ def accelerate(ref_model):
                     if all(hasattr(old, n) for n in ("y_hierarchical_prior_enc", "conv1_context", "y_spatial_prior_3_out")) and old.num_ch == 112:
                         new = ContextFusionFourStep(ctx_channels=old.ctx_channels, lossy=old.lossy).to(next(old.parameters()).device)
                         cf[lvl][band] = adopt(new, old).train(old.training)
+                old = cf[lvl]["ll"] if "ll" in cf[lvl] else None   # the LL band's autoregressive model (context_fusion.py:56): evaluation forward on csrc/pmctf_llar.cu
+                if old is not None and all(hasattr(old, n) for n in ("maskedConv1", "residualBlocks", "maskedConv2", "convs")) \
+                        and getattr(old, "num_features", 0) == 128 and not getattr(old, "context", False):
+                    from ...layers.context_fusion import ContextFusionSubband
+                    new = ContextFusionSubband(num_features=128, num_parameters=old.num_parameters, context=False, in_channels=1)
+                    cf[lvl]["ll"] = adopt(new.to(next(old.parameters()).device), old).train(old.training)
         for m in _PWAVE_METHODS:
             setattr(coder, m, types.MethodType(getattr(pWaveTransform, m), coder))
     of = getattr(ref_model, "optic_flow", None)

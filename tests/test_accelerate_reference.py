@@ -40,7 +40,7 @@ def test_accelerate_keeps_state_dict_and_swaps_hot_path(ref_model):
         for lvl in coder.context_fusion:                                                   # the four-step models are ours (section 8f row 1) ...
             for band in ("lh", "hl", "hh"):
                 assert type(coder.context_fusion[lvl][band]).__module__.startswith("learned_pmctf_b200")
-        assert type(coder.context_fusion["3"]["ll"]).__module__.startswith("pMCTF.")      # ... the LL model and the ConvLSTM context stay
+        assert type(coder.context_fusion["3"]["ll"]).__module__.startswith("learned_pmctf_b200")   # ... and so is the LL model; the ConvLSTM context stays
         assert type(coder.context_prediction).__module__.startswith("pMCTF.")
         assert coder.encode.__func__ is sys.modules["learned_pmctf_b200.models.pWave"].pWaveTransform.encode
     assert type(m.optic_flow).__module__.startswith("learned_pmctf_b200")                 # SpyNet (section 8f row 4) is ours now
