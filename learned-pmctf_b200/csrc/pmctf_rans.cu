@@ -118,6 +118,7 @@ struct Tables {   // one shared copy of the caller's CDF tables per encode / dec
     std::vector<int32_t> cdf;      // [num][stride]
     std::vector<int32_t> sizes, offsets;
     int num = 0, stride = 0;
+    bool monotone = true;          // every row non-decreasing over its size: the decoder may bisect
 };
 
 // queue the intervals of `n` symbols (rans.cpp:76-139): symbols whose table index is negative are skipped, values outside
@@ -270,8 +271,17 @@ static int decode_part(Reader &r, const int16_t *idx, long long n, const Tables 
         const int32_t size = t.sizes[ti], escape = size - 2;
         if (escape < 0 || size > t.stride) return PMCTF_EINVAL;
         const uint32_t target = r.peek(PROB_BITS);
-        int32_t s = 0;   // first entry above the target, minus one (tables are short: linear scan as in the reference)
-        while (s + 1 < size && (uint32_t)cdf[s + 1] <= target) ++s;
+        // first entry above the target, minus one.  The reference scans linearly from entry 0 (rans.cpp:296-300); the tables are
+        // non-decreasing, so the same entry is found by bisection in 7 probes instead of ~50 (the mode of a table sits in its middle)
+        int32_t s = 0, hi = size - 1;
+        if (t.monotone) {
+            while (s < hi) {
+                const int32_t mid = (s + hi + 1) >> 1;
+                if ((uint32_t)cdf[mid] <= target) s = mid; else hi = mid - 1;
+            }
+        } else {
+            while (s + 1 < size && (uint32_t)cdf[s + 1] <= target) ++s;
+        }
         if (s + 1 >= size) return PMCTF_EINVAL;
         r.advance((uint32_t)cdf[s], (uint32_t)(cdf[s + 1] - cdf[s]), PROB_BITS);
         int32_t v = s;
@@ -302,8 +312,12 @@ static int make_tables(Tables &t, const int *cdfs, int num, int stride, const in
     t.cdf.assign(cdfs, cdfs + (size_t)num * stride);
     t.sizes.assign(sizes, sizes + num);
     t.offsets.assign(offsets, offsets + num);
-    for (int i = 0; i < num; ++i)
+    for (int i = 0; i < num; ++i) {
         if (t.sizes[i] < 2 || t.sizes[i] > stride) return PMCTF_EINVAL;
+        const int32_t *row = t.cdf.data() + (size_t)i * stride;
+        for (int j = 1; j < t.sizes[i]; ++j)
+            if ((uint32_t)row[j] < (uint32_t)row[j - 1]) t.monotone = false;
+    }
     return 0;
 }
 
