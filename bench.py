@@ -551,20 +551,24 @@ def run_full_codec(pkg, dev):
         ys.append(y)
         cs.append(torch.cat([c, 255.0 - c], dim=0).round().contiguous())
     with torch.no_grad():
-        m.code_gop_forward(ys[:4], cs[:4], q_index=12)     # warm-up: packs every weight image, fills the workspaces
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ry, rc, bits = m.code_gop_forward(ys, cs, q_index=12)
-        e1.record()
-        torch.cuda.synchronize(dev)
+        m.code_gop_forward(ys[:4], cs[:4], q_index=12)     # warm-up: packs every weight image, captures the four-step graphs (each
+        m.code_gop_forward(ys, cs, q_index=12)             # capture empties torch's allocator cache), then one GOP-16 fills the
+        torch.cuda.synchronize(dev)                        # allocator and the workspaces at the timed size
+        per = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ry, rc, bits = m.code_gop_forward(ys, cs, q_index=12)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            per.append(e0.elapsed_time(e1))
     pkg.ops.check_tc_error(dev, "full codec block")
-    ms = e0.elapsed_time(e1)
+    ms = sorted(per)[1]                                    # median of three GOPs
 
     return {"what": "pMCTF(motion=True, entropy_model=True).code_gop_forward: the reference's GOP loop (encode_one_stage per pair: SpyNet, MV codec, "
                     "forward_MCTF, hp / lp pWave.forward with the four-step entropy-parameter networks, ConvLSTM context, LL model, PostProcess, for "
                     "luma and chroma; inverse_MCTF) on one 1080p 4:2:0 GOP-16, random weights, rate-estimate path",
-            "ms_per_gop": ms, "frames_per_s": GOP / (ms * 1e-3), "bits_per_frame_estimate": sum(bits) / GOP,
+            "ms_per_gop": ms, "ms_per_gop_runs": per, "frames_per_s": GOP / (ms * 1e-3), "bits_per_frame_estimate": sum(bits) / GOP,
             "on_our_kernels": "lifting, SpyNet, four-step networks, LL model, PostProcess, ConvLSTM gates, rate estimate; stock torch convolutions: MV codec, ConvLSTM context"}
 
 
