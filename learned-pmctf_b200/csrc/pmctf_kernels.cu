@@ -627,31 +627,37 @@ __global__ void __launch_bounds__(256) quantize_code_kernel(const float *__restr
 }
 
 // 8-bit samples -> fp32 planes, zero-padded bottom/right (np_image_to_tensor + F.pad, test_pMCTF_flex.py:151-192)
+constexpr int UNPACK_ROWS = 4;   // rows per thread: four loads in flight before the four 16-byte stores, a quarter of the blocks
 __global__ void __launch_bounds__(256) unpack_u8_kernel(const unsigned char *__restrict__ src, float *__restrict__ dst,
                                                         int h0, int w0, int hp, int wp)
 {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y;
+    const int y0 = blockIdx.y * UNPACK_ROWS;
     const long long n = blockIdx.z;
     if (x4 >= wp) return;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (y < h0) {
-        const unsigned char *sp = src + (n * h0 + y) * (long long)w0;
-        if (x4 + 3 < w0 && (w0 & 3) == 0) {
-            const uchar4 u = *reinterpret_cast<const uchar4 *>(sp + x4);
-            v = make_float4(u.x, u.y, u.z, u.w);
-        } else {
-            if (x4 + 0 < w0) v.x = sp[x4 + 0];
-            if (x4 + 1 < w0) v.y = sp[x4 + 1];
-            if (x4 + 2 < w0) v.z = sp[x4 + 2];
-            if (x4 + 3 < w0) v.w = sp[x4 + 3];
+    const bool vec = x4 + 3 < w0 && (w0 & 3) == 0;
+    float4 v[UNPACK_ROWS];
+#pragma unroll
+    for (int j = 0; j < UNPACK_ROWS; ++j) {
+        const int y = y0 + j;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y < h0) {
+            const unsigned char *sp = src + (n * h0 + y) * (long long)w0;
+            if (vec) {
+                const uchar4 u = __ldg(reinterpret_cast<const uchar4 *>(sp + x4));
+                v[j] = make_float4(u.x, u.y, u.z, u.w);
+            } else {
+                if (x4 + 0 < w0) v[j].x = sp[x4 + 0];
+                if (x4 + 1 < w0) v[j].y = sp[x4 + 1];
+                if (x4 + 2 < w0) v[j].z = sp[x4 + 2];
+                if (x4 + 3 < w0) v[j].w = sp[x4 + 3];
+            }
         }
     }
-    *reinterpret_cast<float4 *>(dst + (n * hp + y) * (long long)wp + x4) = v;
+#pragma unroll
+    for (int j = 0; j < UNPACK_ROWS; ++j)
+        if (y0 + j < hp) *reinterpret_cast<float4 *>(dst + (n * hp + y0 + j) * (long long)wp + x4) = v[j];
 }
-
-// sum over the un-padded area of (round(clamp(rec, 0, 255)) - orig)^2 per plane: the PSNR numerators of
-// test_pMCTF_flex.py:300-310, as exact integers
 __global__ void __launch_bounds__(256) frame_sse_kernel(const float *__restrict__ rec, const unsigned char *__restrict__ orig,
                                                         int h0, int w0, int hp, int wp, unsigned long long *__restrict__ sse, int vec)
 {
@@ -663,13 +669,19 @@ __global__ void __launch_bounds__(256) frame_sse_kernel(const float *__restrict_
         const unsigned char *op = orig + (n * h0 + y) * (long long)w0;
         unsigned int row = 0;   // <= 255^2 * (w0 / threads + 4) per thread
         const int w4 = vec ? w0 >> 2 : 0;
-        for (int i = threadIdx.x; i < w4; i += blockDim.x) {
-            const float4 r = __ldg(reinterpret_cast<const float4 *>(rp) + i);
-            const uchar4 o = __ldg(reinterpret_cast<const uchar4 *>(op) + i);
+        auto sq4 = [](const float4 r, const uchar4 o) -> unsigned int {
             const int d0 = (int)rintf(fminf(fmaxf(r.x, 0.0f), 255.0f)) - (int)o.x, d1 = (int)rintf(fminf(fmaxf(r.y, 0.0f), 255.0f)) - (int)o.y;
             const int d2 = (int)rintf(fminf(fmaxf(r.z, 0.0f), 255.0f)) - (int)o.z, d3 = (int)rintf(fminf(fmaxf(r.w, 0.0f), 255.0f)) - (int)o.w;
-            row += (unsigned int)(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
+            return (unsigned int)(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
+        };
+        int i = threadIdx.x;
+        for (; i + (int)blockDim.x < w4; i += 2 * blockDim.x) {   // two independent pairs of loads in flight (integer sums: any order)
+            const float4 r0 = __ldg(reinterpret_cast<const float4 *>(rp) + i), r1 = __ldg(reinterpret_cast<const float4 *>(rp) + i + blockDim.x);
+            const uchar4 o0 = __ldg(reinterpret_cast<const uchar4 *>(op) + i), o1 = __ldg(reinterpret_cast<const uchar4 *>(op) + i + blockDim.x);
+            row += sq4(r0, o0) + sq4(r1, o1);
         }
+        for (; i < w4; i += blockDim.x)
+            row += sq4(__ldg(reinterpret_cast<const float4 *>(rp) + i), __ldg(reinterpret_cast<const uchar4 *>(op) + i));
         for (int x = 4 * w4 + threadIdx.x; x < w0; x += blockDim.x) {
             const int d = (int)rintf(fminf(fmaxf(rp[x], 0.0f), 255.0f)) - (int)op[x];
             row += (unsigned int)(d * d);
@@ -1316,7 +1328,7 @@ int pmctf_unpack_u8(const unsigned char *src, float *dst, int n, int h0, int w0,
     if (n == 0) return 0;
     if (!src || !dst || n < 0 || h0 <= 0 || w0 <= 0) return PMCTF_EINVAL;
     if (hp < h0 || wp < w0 || (wp & 3) || hp > 65535 || n > 65535) return PMCTF_ESHAPE;
-    unpack_u8_kernel<<<dim3((wp / 4 + 255) / 256, hp, n), 256, 0, (cudaStream_t)stream>>>(src, dst, h0, w0, hp, wp);
+    unpack_u8_kernel<<<dim3((wp / 4 + 255) / 256, (hp + UNPACK_ROWS - 1) / UNPACK_ROWS, n), 256, 0, (cudaStream_t)stream>>>(src, dst, h0, w0, hp, wp);
     return PMCTF_LAUNCHED();
 }
 
