@@ -78,6 +78,17 @@ __device__ __forceinline__ float2 add2v(float2 a, float2 b)
     return *reinterpret_cast<float2 *>(&d);
 }
 
+// PMCTF_TANH_IMAD: (shared-memory address of the table) - 4 * 0x4B400000, made opaque so that it stays ONE register and the
+// entry's address is one shift-add of the rounded float's bits (see tanh_det2)
+__device__ __forceinline__ const float *tanh_table_base(const float *tab_smem)
+{
+    // + entry 0 of the table in global memory (tanh(0) = +0.0f: the bits are 0), which the assembler cannot fold: otherwise it
+    // splits the constant back into an immediate offset of the load plus an add per lookup
+    const unsigned int zero = *reinterpret_cast<const volatile unsigned int *>(g_tanh_bits);
+    const unsigned int tb = (unsigned int)__cvta_generic_to_shared(tab_smem) - 0x2D000000u + zero;
+    return reinterpret_cast<const float *>((size_t)tb);
+}
+
 // tanh_det of two values at once on the packed fp32x2 pipe: the same values per element.  rint(128 |x|) and the table index come
 // from the 1.5 * 2^23 trick (fma(m, -128, M) = M + rint(128 |x|) exactly, ties to even like rintf) instead of FRND + F2I, which
 // keeps the conversion (XU) pipe out of the hot loop; the sign arrangement of the contract needs no packed negation.
@@ -107,7 +118,16 @@ __device__ __forceinline__ float2 tanh_det2(float2 x, const float *__restrict__ 
 #if defined(PMCTF_WHATIF) && (PMCTF_WHATIF & 2)
     const float2 T = make_float2(fi.x * 0.0008f, fi.y * 0.0008f);
 #else
+#if defined(PMCTF_TANH_IMAD)
+    // the float's bits are 0x4B400000 + n (n = the table index, <= 1152): the shared-memory address of entry n is ONE shift-add,
+    // (bits << 2) + (table address - 4 * 0x4B400000) in wrap-around 32-bit arithmetic, instead of a shift, a mask and an add
+    const unsigned int tb = (unsigned int)(size_t)tab;     // PMCTF_TANH_IMAD: `tab` carries tanh_table_base(), not a pointer
+    float2 T;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(T.x) : "r"((unsigned int)__float_as_int(tm.x) * 4u + tb));
+    asm("ld.shared.f32 %0, [%1];" : "=f"(T.y) : "r"((unsigned int)__float_as_int(tm.y) * 4u + tb));
+#else
     const float2 T = make_float2(tab[__float_as_int(tm.x) & 0x7FF], tab[__float_as_int(tm.y) & 0x7FF]);
+#endif
 #endif
     const float2 Q = fma2v(T, T, make_float2(-1.0f, -1.0f));
     const float2 R = mul2v(T, Q);

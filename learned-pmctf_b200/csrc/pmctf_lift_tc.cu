@@ -269,6 +269,9 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
     __syncthreads();
     umma::fence_after_sync();
     const bool xfast_src = a.src.cs <= a.src.rs;
+#if defined(PMCTF_TANH_IMAD)
+    ttab = const_cast<float *>(tanh_table_base(ttab));   // from here on only tanh_det2 uses it
+#endif
 
     // ---- persistent loop over tiles.  Tiles are numbered column-major (plane, column strip, row), every CTA takes one contiguous
     //      range, so it walks DOWN a column strip.  A tile whose upper neighbour was the previous tile of this CTA is a
