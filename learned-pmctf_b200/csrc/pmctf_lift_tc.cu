@@ -770,6 +770,30 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
             if (gy >= H || gx >= W) continue;
             // conv4 (16 -> 1): out = ((b4 + T_0) + T_1) + ... + T_8 over the 3x3 neighbourhood of partials
             float tk[9];
+#if defined(PMCTF_GATHER_ROWS)
+            // the same addresses, resolved per neighbour ROW: a row lies wholly in the carried records (rows 0, 1 of a continuation
+            // tile) or wholly in the blocks (c + dx < P), and inside the blocks word mm of tap k sits at 4 mm + 1536 (mm >> 7) + const(k)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int ri = r + dy;
+                if (cont && ri < 2) {
+                    const uint8_t *pb = A1 + (ri * P + c) * 4;
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int k9 = 3 * dy + dx;
+                        tk[k9] = *reinterpret_cast<const float *>(pb + dx * 4 + (k9 >> 2) * PLANE + (k9 & 3) * (8 * P));
+                    }
+                } else {
+                    const int mr = ri * P + c - c3s;
+                    const uint8_t *pb = A1 + c3s * 16 + mr * 4;
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int k9 = 3 * dy + dx;
+                        tk[k9] = *reinterpret_cast<const float *>(pb + ((mr + dx) >> 7) * 1536 + dx * 4 + (k9 >> 2) * PLANE + (k9 & 3) * 512);
+                    }
+                }
+            }
+#else
 #pragma unroll
             for (int k9 = 0; k9 < 9; ++k9) {
                 const int m = (r + k9 / 3) * P + c + (k9 % 3);   // conv3 pixel index (origin (-1,-1)) of the neighbour
@@ -777,6 +801,7 @@ __global__ void __launch_bounds__(NT, 2) lift_step_tc_kernel(const __grid_consta
                 const int off = mm >= 0 ? c3s * 16 + (mm >> 7) * 2048 + (k9 & 3) * 512 + (mm & 127) * 4 : (k9 & 3) * (8 * P) + m * 4;
                 tk[k9] = *reinterpret_cast<const float *>(A1 + (k9 >> 2) * PLANE + off);
             }
+#endif
             float pu = cw.b4;
 #pragma unroll
             for (int k9 = 0; k9 < 9; ++k9) pu = pu + tk[k9];

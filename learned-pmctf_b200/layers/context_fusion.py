@@ -250,8 +250,11 @@ class ContextFusionSubband(nn.Module):
         state = torch.tensor([x.value if x.value < (1 << 63) else x.value - (1 << 64), pos.value, 0, 0], dtype=torch.int64, device=device)
         d, _keepbuf = self._ar_desc(B, H, W, device)
         out = torch.empty((B, H * W), dtype=torch.float32, device=device)
-        ops._launch(device, "llar_decode_band", lib.pmctf_llar_decode_band, C.byref(d), wdev.data_ptr(), int(nwords.value), state.data_ptr(),
-                    cd.data_ptr(), cd.shape[0], cd.shape[1], sz.data_ptr(), of.data_ptr(), out.data_ptr())
+        with torch.cuda.device(device):
+            rc = lib.pmctf_llar_decode_band(C.byref(d), wdev.data_ptr(), int(nwords.value), state.data_ptr(), cd.data_ptr(), cd.shape[0],
+                                            cd.shape[1], sz.data_ptr(), of.data_ptr(), out.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+        if rc != 0:       # the cluster could not be launched here (e.g. no eight free SMs with 222 KB of shared memory in one GPC):
+            return None   # nothing was decoded, the reader has not moved -- the caller takes the per-coefficient path
         st = state.cpu().tolist()
         if st[2] != 0:
             raise RuntimeError("LL band: the entropy-coded stream ended early or is corrupt")
