@@ -78,6 +78,11 @@ __device__ __forceinline__ float2 add2v(float2 a, float2 b)
     return *reinterpret_cast<float2 *>(&d);
 }
 
+// default since the r2w11 A/B (profiles/r2_whatif.txt): +1.3 % on the tensor-core step, same values; -DPMCTF_TANH_NO_IMAD restores the
+// shift / mask / add addressing
+#if !defined(PMCTF_TANH_NO_IMAD) && !defined(PMCTF_TANH_IMAD)
+#define PMCTF_TANH_IMAD 1
+#endif
 // PMCTF_TANH_IMAD: (shared-memory address of the table) - 4 * 0x4B400000, made opaque so that it stays ONE register and the
 // entry's address is one shift-add of the rounded float's bits (see tanh_det2)
 __device__ __forceinline__ const float *tanh_table_base(const float *tab_smem)

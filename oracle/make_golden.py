@@ -324,8 +324,45 @@ def main_spynet():
     np.savez_compressed(os.path.join(OUT, "spynet.npz"), cur=npy(cur[:, :1]), ref=npy(ref[:, :1]), flow=npy(flow), seed=np.array(21))
 
 
+def main_llar():
+    """tests/golden/llar.npz: the reference's LL-band autoregressive model ContextFusionSubband (pMCTF/layers/context_fusion.py:56-204)
+    driven coefficient by coefficient exactly as pWave._compress_subband_ar does (pMCTF/models/pWave.py:531-553: forward_sequential on
+    the padded band, symbol = round(y - mean), reconstruction round(symbol + mean); the reconstruction is NOT fed back on the encoder
+    side -- the padded input is the quantised band itself), CPU fp32, seeded weights of llar_weights()."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
+    from llar_weights import llar_weights
+    from pMCTF.layers.context_fusion import ContextFusionSubband
+    out = {}
+    for tag, seed, (H, W) in (("a", 31, (9, 14)), ("b", 32, (12, 7))):
+        m = ContextFusionSubband(num_features=128, num_parameters=2, context=False, in_channels=1).eval()
+        sd = llar_weights(seed)
+        full = m.state_dict()
+        for k, v in sd.items():
+            full[k] = torch.from_numpy(v)
+        m.load_state_dict(full, strict=True)      # the mask buffers keep their constructed values
+        g = torch.Generator().manual_seed(200 + seed)
+        y = torch.round(torch.randn(1, 1, H, W, generator=g) * 6)
+        pad = F.pad(y, (1, 1, 1, 1))
+        scales, means, sym, rec = (np.zeros((H, W), np.float32) for _ in range(4))
+        with torch.no_grad():
+            for h in range(H):
+                for w in range(W):
+                    p = m.forward_sequential(pad, h, w)
+                    sc, mu = p.chunk(2, dim=1)
+                    res = (pad[:, :, h + 1:h + 2, w + 1:w + 2] - mu).round()
+                    scales[h, w], means[h, w], sym[h, w], rec[h, w] = float(sc), float(mu), float(res), float((res + mu).round())
+            full_plane = m(y)
+        out.update({f"{tag}.y": npy(y[0, 0]), f"{tag}.scales": scales, f"{tag}.means": means, f"{tag}.symbols": sym, f"{tag}.recon": rec,
+                    f"{tag}.full_plane": npy(full_plane[0]), f"{tag}.seed": np.array(seed)})
+        print(f"llar {tag}: mean range {means.min():.3f}..{means.max():.3f}, scale {scales.min():.3f}..{scales.max():.3f}, "
+              f"|sequential - full plane| max {np.abs(np.stack([scales, means]) - npy(full_plane[0])).max():.2e}, recon == y: {np.array_equal(rec, npy(y[0, 0]))}")
+    np.savez_compressed(os.path.join(OUT, "llar.npz"), **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "spynet":
+    if len(sys.argv) > 1 and sys.argv[1] == "llar":
+        main_llar()
+    elif len(sys.argv) > 1 and sys.argv[1] == "spynet":
         main_spynet()
     elif len(sys.argv) > 1 and sys.argv[1] == "ctx4":
         main_ctx4()

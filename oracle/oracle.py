@@ -406,3 +406,28 @@ def conv3x3(x, w, b, slope=1.0, res=None):
     r = _a(res) if res is not None else None
     lib().orc_conv3x3(_p(x), ci, _p(w), _p(b), co, _p(out), H, W, C.c_float(slope), _p(r) if r is not None else None)
     return out
+
+
+def llar_encode(sd, yq):
+    """The LL band's autoregressive model, coefficient by coefficient, under the fp32 contract stated at orc_llar_encode
+    (pmctf_oracle.c): reference pMCTF/layers/context_fusion.py:56-204 as driven by pMCTF/models/pWave.py:531-553.
+    sd: state_dict of a ContextFusionSubband (numpy arrays; keys maskedConv1.*, residualBlocks.{0,1}.conv{1,2}.*, maskedConv2.*,
+    convs.{0,1,2}.*); yq [H,W] fp32 quantised band.  -> (scales, means, symbols, reconstruction), each [H,W] fp32."""
+    f = lambda k: np.ascontiguousarray(sd[k], dtype=np.float32)   # noqa: E731
+    names = ["residualBlocks.0.conv1", "residualBlocks.0.conv2", "residualBlocks.1.conv1", "residualBlocks.1.conv2", "maskedConv2"]
+    w128 = np.ascontiguousarray(np.stack([f(n + ".weight") for n in names]))
+    b128 = np.ascontiguousarray(np.stack([f(n + ".bias") for n in names]))
+    w1 = np.ascontiguousarray(np.stack([f("convs.0.weight").reshape(128, 128), f("convs.1.weight").reshape(128, 128)]))
+    b1 = np.ascontiguousarray(np.stack([f("convs.0.bias"), f("convs.1.bias")]))
+    wout, bout = f("convs.2.weight").reshape(2, 128).copy(), f("convs.2.bias")
+    w_in, b_in = f("maskedConv1.weight").reshape(128, 9).copy(), f("maskedConv1.bias")
+    assert w128.shape == (5, 128, 128, 3, 3) and w_in.shape == (128, 9) and wout.shape == (2, 128)
+    yq = np.ascontiguousarray(yq, dtype=np.float32)
+    H, W = yq.shape
+    outs = [np.empty((H, W), dtype=np.float32) for _ in range(4)]
+    P = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    fn = lib().orc_llar_encode
+    fn.restype = None
+    fn.argtypes = [C.c_void_p] * 9 + [C.c_int, C.c_int] + [C.c_void_p] * 4
+    fn(P(w_in), P(b_in), P(w128), P(b128), P(w1), P(b1), P(wout), P(bout), P(yq), H, W, *[P(o) for o in outs])
+    return tuple(outs)

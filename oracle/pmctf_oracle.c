@@ -649,3 +649,101 @@ ORC_API void orc_conv2d(const float *in, int ci_n, const float *w, const float *
                 }
         }
 }
+
+/* ---- the LL subband's autoregressive entropy-parameter model, coefficient by coefficient in raster order: ContextFusionSubband
+ * (pMCTF/layers/context_fusion.py:56-204, forward_sequential) as driven by pWave._compress_subband_ar (pMCTF/models/pWave.py:531-553).
+ * fp32 CONTRACT shared as a specification with csrc/pmctf_llar.cu:
+ *   - a masked 3x3 layer reads the causal taps (dy, dx) = (-1,-1), (-1,0), (-1,1), (0,-1) [type A] + (0,0) [type B] of a zero-padded map;
+ *   - its reduction index k = tap * 128 + ci (1x1 layers: k = ci) is cut into EIGHT equal slices; a slice is one fma chain from 0 in k
+ *     order; out = ((bias + slice_0) + slice_1) + ... + slice_7;
+ *   - the 1 -> 128 input layer is one fma chain from the bias over its four taps;
+ *   - residual blocks (context_fusion.py:30-41): t = lrelu(conv1(x)); x = conv2(t) + x; after the two blocks x = x + first;
+ *   - tail: lrelu, 1x1, lrelu, 1x1, lrelu, then the 128 -> 2 layer as t[c] * w[c] products folded by the tree r[i] += r[i + s],
+ *     s = 64, 32, ..., 1, plus its bias;
+ *   - symbol = rint(rint(y) - mean); the history the next coefficients see is the RECONSTRUCTION rint(symbol + mean).
+ * Weights in their state_dict (OIHW) layout; masked taps are simply never read.  w128: the five masked 128 -> 128 layers
+ * (residualBlocks.0.conv1, .0.conv2, .1.conv1, .1.conv2, maskedConv2), each [128][128][3][3]; w1: convs.0, convs.1 [128][128]; wout [2][128]. */
+static inline float orc_lrelu(float v) { return v >= 0.0f ? v : v * 0.2f; }
+
+ORC_API void orc_llar_encode(const float *w_in, const float *b_in, const float *w128, const float *b128, const float *w1, const float *b1,
+                             const float *wout, const float *bout, const float *yq, int H, int W, float *scales, float *means, float *symbols,
+                             float *recon)
+{
+    enum { F = 128, KS = 8 };
+    static const int DY[5] = {-1, -1, -1, 0, 0}, DX[5] = {-1, 0, 1, -1, 0};
+    const int Hp = H + 2, Wp = W + 2;
+    float *Y = (float *)calloc((size_t)Hp * Wp, sizeof(float));
+    float *hist = (float *)calloc((size_t)5 * Hp * Wp * F, sizeof(float));   /* inputs of the five masked layers, channel-last */
+    float in[5 * F], out[F], cur[F], first[F], red0[F], red1[F];
+    for (int h = 0; h < H; ++h)
+        for (int w = 0; w < W; ++w) {
+            const size_t here = ((size_t)(h + 1) * Wp + (w + 1)) * F;
+            for (int co = 0; co < F; ++co) {
+                float t = b_in[co];
+                for (int k = 0; k < 4; ++k) t = __builtin_fmaf(w_in[(size_t)co * 9 + (DY[k] + 1) * 3 + (DX[k] + 1)], Y[(size_t)(h + 1 + DY[k]) * Wp + (w + 1 + DX[k])], t);
+                cur[co] = first[co] = t;
+            }
+            for (int L = 0; L < 5; ++L) {
+                float *plane = hist + (size_t)L * Hp * Wp * F;
+                if (L == 4)
+                    for (int c = 0; c < F; ++c) cur[c] = cur[c] + first[c];
+                if (L == 1 || L == 3) {
+                    for (int c = 0; c < F; ++c) plane[here + c] = orc_lrelu(out[c]);
+                } else {
+                    for (int c = 0; c < F; ++c) plane[here + c] = cur[c];
+                }
+                for (int t = 0; t < 5; ++t)
+                    for (int c = 0; c < F; ++c) in[t * F + c] = plane[((size_t)(h + 1 + DY[t]) * Wp + (w + 1 + DX[t])) * F + c];
+                const float *wl = w128 + (size_t)L * F * F * 9, *bl = b128 + (size_t)L * F;
+                const int per = 5 * F / KS;
+                for (int co = 0; co < F; ++co) {
+                    float v = bl[co];
+                    for (int s = 0; s < KS; ++s) {
+                        float acc = 0.0f;
+                        for (int j = 0; j < per; ++j) {
+                            const int k = s * per + j, t = k / F, ci = k % F;
+                            acc = __builtin_fmaf(wl[((size_t)co * F + ci) * 9 + (DY[t] + 1) * 3 + (DX[t] + 1)], in[k], acc);
+                        }
+                        v += acc;
+                    }
+                    out[co] = v;
+                }
+                if (L == 1 || L == 3)
+                    for (int c = 0; c < F; ++c) cur[c] = out[c] + cur[c];
+            }
+            for (int k1 = 0; k1 < 2; ++k1) {
+                for (int c = 0; c < F; ++c) in[c] = orc_lrelu(out[c]);
+                const float *wl = w1 + (size_t)k1 * F * F, *bl = b1 + (size_t)k1 * F;
+                const int per = F / KS;
+                for (int co = 0; co < F; ++co) {
+                    float v = bl[co];
+                    for (int s = 0; s < KS; ++s) {
+                        float acc = 0.0f;
+                        for (int j = 0; j < per; ++j) acc = __builtin_fmaf(wl[(size_t)co * F + s * per + j], in[s * per + j], acc);
+                        v += acc;
+                    }
+                    cur[co] = v;          /* scratch: out is still being read through `in` only */
+                }
+                for (int c = 0; c < F; ++c) out[c] = cur[c];
+            }
+            for (int c = 0; c < F; ++c) {
+                const float t = orc_lrelu(out[c]);
+                red0[c] = t * wout[c];
+                red1[c] = t * wout[F + c];
+            }
+            for (int st = F / 2; st > 0; st >>= 1)
+                for (int c = 0; c < st; ++c) {
+                    red0[c] += red0[c + st];
+                    red1[c] += red1[c + st];
+                }
+            const float scale = red0[0] + bout[0], mean = red1[0] + bout[1];
+            const float sym = rintf(rintf(yq[(size_t)h * W + w]) - mean), rec = rintf(sym + mean);
+            Y[(size_t)(h + 1) * Wp + (w + 1)] = rec;
+            scales[(size_t)h * W + w] = scale;
+            means[(size_t)h * W + w] = mean;
+            symbols[(size_t)h * W + w] = sym;
+            recon[(size_t)h * W + w] = rec;
+        }
+    free(Y);
+    free(hist);
+}

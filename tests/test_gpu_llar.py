@@ -143,3 +143,27 @@ def test_band_decoder_round_trip_and_stream_position(shape, stream_part):
                 back = net.ar_decode([B, 1, H, W], lambda i: dec.decode_stream(i, cdf, ln, off), dev)
             assert torch.equal(back, ll_hat), use_band
             assert np.array_equal(np.asarray(dec.decode_stream(tail_idx, cdf, ln, off)), tail_sym), use_band
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(9, 14), (18, 30)])
+def test_kernels_equal_cpu_oracle_bit_for_bit(shape):
+    """scales, means, symbols and the reconstructed band of the LL kernels == oracle/pmctf_oracle.c:orc_llar_encode (the same fp32
+    contract restated on the CPU from the state_dict-layout weights), every float bit for bit"""
+    from oracle import oracle as orc
+    dev = torch.device("cuda:0")
+    net = _net(dev)
+    H, W = shape
+    g = torch.Generator(device="cpu").manual_seed(23)
+    ll = torch.round(torch.randn(1, 1, H, W, generator=g) * 6)
+    sd = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
+    o_scale, o_mean, o_sym, o_rec = orc.llar_encode(sd, ll[0, 0].numpy())
+    with torch.no_grad():
+        params = net(ll.to(dev))                                # layer-parallel kernels
+        hat_p, sym_p, _ = net.ar_encode(ll.to(dev), parallel=True)
+        hat_s, sym_s, _ = net.ar_encode(ll.to(dev), parallel=False)   # coefficient-by-coefficient kernel
+    assert np.array_equal(o_rec, ll[0, 0].numpy())              # no exact tie in this band: the speculated history is the true one
+    assert np.array_equal(params[0, 0].cpu().numpy(), o_scale)
+    assert np.array_equal(params[0, 1].cpu().numpy(), o_mean)
+    assert np.array_equal(sym_p.reshape(H, W), o_sym.astype(np.int16)) and np.array_equal(sym_s, sym_p)
+    assert np.array_equal(hat_p[0, 0].cpu().numpy(), o_rec) and torch.equal(hat_s, hat_p)
