@@ -77,6 +77,31 @@ def test_flow_warp_vs_oracle(P, shape, fn):
         assert_bitexact(got, want, f"flow_warp {shape} sign {sign}")
 
 
+@pytest.mark.parametrize("shape,fn", [((2, 1, 45, 200), 2), ((1, 1, 96, 333), 1), ((4, 1, 32, 128), 2), ((1, 1, 130, 129), 1)])
+def test_flow_warp_wide_planes_vs_oracle(P, shape, fn):
+    """single-channel planes wider than one 128-thread block and ragged in both directions, with vectors that differ from lane to lane
+    (a warp's taps land in different rows), a band of long vectors, vectors out of the frame on all four sides (border clamp) and a row
+    of zero vectors (-0.0 under sign = -1)"""
+    n, _, h, w = shape
+    g = np.random.default_rng(5)
+    fl = smooth_flow(fn, h, w, 2)
+    fl += g.normal(0, 3.0, fl.shape).astype(np.float32)                 # lanes of a warp land in different rows
+    fl[:, :, : h // 3, w // 4: w // 2] *= 4.0                            # a band of long vectors
+    fl[:, 0, :, :6] -= 70.0                                              # out of the frame: left / right / top / bottom
+    fl[:, 0, :, -6:] += 70.0
+    fl[:, 1, :5, :] -= 50.0
+    fl[:, 1, -5:, :] += 50.0
+    fl[:, :, h // 2, :] = 0.0                                            # zero vectors (and -0.0 under sign = -1)
+    im = rnd(shape, 3)
+    for sign in (1.0, -1.0):
+        got = npy(P.ops.flow_warp(cu(im), cu(fl), sign))
+        if fn in (1, n):
+            want = orc.flow_warp(im, fl, sign)
+        else:
+            want = np.concatenate([orc.flow_warp(im[2 * i:2 * i + 2], fl[i:i + 1], sign) for i in range(fn)])
+        assert_bitexact(got, want, f"flow_warp wide {shape} sign {sign}")
+
+
 @pytest.mark.parametrize("tag", ["luma", "chromaN", "tile", "rgb"])
 def test_flow_warp_vs_reference_golden(P, golden, tag):
     g = golden("warp")
