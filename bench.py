@@ -212,6 +212,9 @@ def measure_int8_peak(dev, seconds=2.0):
         return {"burst_tops": None, "sustained_tops": None, "how": f"unavailable: {ex}"}
 
 
+PROFILE_TAG = "r2x"   # tag of the round's closing measurement set under profiles/ (tools/measure_round.sh + tools/refresh_profiles.sh)
+
+
 def profiled_traffic():
     """dram bytes per launch of the dominant kernel from THIS round's ncu --set full capture (tools/refresh_profiles.sh writes
     profiles/<tag>_traffic.json beside the summary it was read from).  None when no such artifact exists."""
@@ -221,6 +224,8 @@ def profiled_traffic():
         for f in sorted(os.listdir(pdir)):
             if f.endswith("_traffic.json") and f.startswith("r2"):
                 best = os.path.join(pdir, f)
+        if os.path.exists(os.path.join(pdir, PROFILE_TAG + "_traffic.json")):   # the capture of the closing measurement set
+            best = os.path.join(pdir, PROFILE_TAG + "_traffic.json")
         if best:
             with open(best) as fh:
                 d = json.load(fh)
